@@ -1,0 +1,97 @@
+"""Complex-aware Adam with the reference's update rule (reference: /root/reference/util/Adam.py) as
+ONE fused multi-tensor CUDA launch per <= 48 parameter tensors (the reference issues ~9 elementwise
+launches per tensor from a Python loop).
+
+Same constructor, ``param_groups`` / ``state`` layout (``step``, ``exp_avg``, ``exp_avg_sq``
+[, ``max_exp_avg_sq``]; complex parameters keep complex64 moments, Adam.py:130-138) and the same
+semantics: L2 weight decay added to the gradient, ONE shared |g|^2 second moment per complex
+element (Adam.py:40), parameters without a gradient skipped (Adam.py:122).
+"""
+import ctypes as C
+
+import torch
+from torch.optim.optimizer import Optimizer
+
+from ._lib import FnmError, check, lib
+
+
+def _as_float_view(t):
+    return torch.view_as_real(t) if t.is_complex() else t
+
+
+class Adam(Optimizer):
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0, amsgrad=False):
+        if not 0.0 <= lr:
+            raise ValueError("Invalid learning rate: {}".format(lr))
+        if not 0.0 <= eps:
+            raise ValueError("Invalid epsilon value: {}".format(eps))
+        if not 0.0 <= betas[0] < 1.0:
+            raise ValueError("Invalid beta parameter at index 0: {}".format(betas[0]))
+        if not 0.0 <= betas[1] < 1.0:
+            raise ValueError("Invalid beta parameter at index 1: {}".format(betas[1]))
+        if not 0.0 <= weight_decay:
+            raise ValueError("Invalid weight_decay value: {}".format(weight_decay))
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, amsgrad=amsgrad))
+
+    def __setstate__(self, state):
+        super().__setstate__(state)
+        for group in self.param_groups:
+            group.setdefault("amsgrad", False)
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        for group in self.param_groups:
+            beta1, beta2 = group["betas"]
+            by_step = {}
+            for p in group["params"]:
+                if p.grad is None:
+                    continue
+                if p.grad.is_sparse:
+                    raise RuntimeError("Adam does not support sparse gradients, please consider SparseAdam instead")
+                if not p.is_cuda:
+                    raise FnmError("fnm_b200.Adam updates CUDA parameters only (no CPU fallback)")
+                if group["amsgrad"] and p.is_complex():
+                    raise RuntimeError("maximum not implemented for complex tensors.")   # as util/Adam.py:43
+                state = self.state[p]
+                if len(state) == 0:
+                    state["step"] = 0
+                    state["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                    state["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                    if group["amsgrad"]:
+                        state["max_exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                state["step"] += 1
+                by_step.setdefault(state["step"], []).append(p)
+            for step, plist in by_step.items():
+                self._launch(plist, step, group, beta1, beta2)
+        return loss
+
+    def _launch(self, plist, step, group, beta1, beta2):
+        n = len(plist)
+        vp = C.c_void_p * n
+        keep = []                      # float views must outlive the launch call
+
+        def table(tensors):
+            views = []
+            for t in tensors:
+                if not t.is_contiguous():
+                    raise FnmError("fnm_b200.Adam needs contiguous parameters, gradients and state")
+                views.append(_as_float_view(t))
+            keep.extend(views)
+            return vp(*[v.data_ptr() for v in views])
+
+        p_tab = table([p.data for p in plist])
+        g_tab = table([p.grad if p.grad.dtype == p.dtype else p.grad.to(p.dtype) for p in plist])
+        m_tab = table([self.state[p]["exp_avg"] for p in plist])
+        v_tab = table([self.state[p]["exp_avg_sq"] for p in plist])
+        x_tab = table([self.state[p]["max_exp_avg_sq"] for p in plist]) if group["amsgrad"] else None
+        numel = (C.c_int64 * n)(*[p.numel() * (2 if p.is_complex() else 1) for p in plist])
+        cplx = (C.c_uint8 * n)(*[1 if p.is_complex() else 0 for p in plist])
+        stream = C.c_void_p(torch.cuda.current_stream(plist[0].device).cuda_stream)
+        check(lib().fnm_adam_multi_tensor(n, p_tab, g_tab, m_tab, v_tab, x_tab, numel, cplx,
+                                          float(group["lr"]), float(beta1), float(beta2), float(group["eps"]),
+                                          float(group["weight_decay"]), int(bool(group["amsgrad"])), int(step), None,
+                                          stream), "fnm_adam_multi_tensor")

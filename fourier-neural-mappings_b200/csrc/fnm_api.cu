@@ -1,0 +1,324 @@
+// extern "C" surface of libfnm_b200 (see include/fnm_b200.h): argument checks, workspace carving,
+// and the stage chains that make up a fused Fourier layer / F2V / V2F, forward and backward.
+#include "fnm_common.cuh"
+#include "fnm_stages.cuh"
+
+namespace fnm {
+
+static thread_local char g_err[512] = "";
+
+char* err_buf() { return g_err; }
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+int check_launch(const char* what) {
+    const cudaError_t e = cudaPeekAtLastError();
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(FNM_ECUDA, "%s: %s", what, cudaGetErrorString(e));
+    }
+    return FNM_OK;
+}
+
+static int check_plan(const fnm_plan* p, bool need_in, bool need_out) {
+    FNM_REQUIRE(p != nullptr, "plan is NULL");
+    FNM_REQUIRE(p->B > 0 && p->R > 0 && p->NY > 0 && p->Ci > 0 && p->Co > 0, "plan: non-positive extent");
+    FNM_REQUIRE(p->rows_per_w > 0 && p->rows_per_w <= p->R, "plan: rows_per_w out of range");
+    if (need_in) {
+        FNM_REQUIRE(p->P1 > 0 && p->P2 > 0, "plan: bad input grid");
+        FNM_REQUIRE(p->ay && p->ayT && p->ex && p->fxb, "plan: analysis tables missing");
+    }
+    if (need_out) {
+        FNM_REQUIRE(p->S1 > 0 && p->S2 > 0, "plan: bad output grid");
+        FNM_REQUIRE(p->by && p->byT && p->fx && p->exb, "plan: synthesis tables missing");
+    }
+    return FNM_OK;
+}
+
+struct LayerWs {
+    size_t T, Oh, Z, Gh, partial;      // float counts
+};
+
+static LayerWs layer_ws(const fnm_plan* p) {
+    LayerWs w;
+    const size_t LY = 2 * (size_t)p->NY;
+    const size_t cmax = p->Ci > p->Co ? p->Ci : p->Co;
+    const size_t rows = (size_t)p->B * (p->P1 > p->S1 ? p->P1 : p->S1);
+    w.T = rows * LY * cmax;                               // T / Tg, then reused as Z / Zg
+    w.Oh = (size_t)p->R * p->NY * 2 * p->B * cmax;        // Oh / Gxh
+    w.Z = rows * LY * cmax;
+    w.Gh = (size_t)p->R * p->NY * 2 * p->B * cmax;
+    w.partial = simt_conv_wgrad_workspace((int64_t)p->B * p->S1 * p->S2, p->Ci, p->Co) / sizeof(float);
+    return w;
+}
+
+}  // namespace fnm
+
+using namespace fnm;
+
+extern "C" {
+
+const char* fnm_version(void) { return "fnm_b200 0.1 (sm_100a)"; }
+const char* fnm_last_error(void) { return err_buf(); }
+int fnm_has_tcgen05(void) { return tc_available(); }
+
+// ------------------------------------------------------------------------------------------------
+// individual stages
+// ------------------------------------------------------------------------------------------------
+int fnm_ydft(const float* x, const float* tab, float* T, int64_t rows, int P2, int LY, int C, int act_in, int mode,
+             fnm_stream_t stream) {
+    FNM_REQUIRE(x && tab && T, "ydft: NULL pointer");
+    FNM_REQUIRE(rows >= 0 && P2 > 0 && LY > 0 && C > 0, "ydft: bad extents");
+    if (tc_ydft_supported(rows, P2, LY, C)) return tc_ydft(x, tab, T, rows, P2, LY, C, act_in, mode, as_stream(stream));
+    return simt_ydft(x, tab, T, rows, P2, LY, C, act_in, as_stream(stream));
+}
+
+int fnm_xdft(const float* T, const float* ex, float* Xh, int B, int P1, int R, int NY, int C, fnm_stream_t stream) {
+    FNM_REQUIRE(T && ex && Xh, "xdft: NULL pointer");
+    FNM_REQUIRE(B > 0 && P1 > 0 && R > 0 && NY > 0 && C > 0, "xdft: bad extents");
+    return simt_xdft(T, ex, Xh, B, P1, R, NY, C, as_stream(stream));
+}
+
+int fnm_xsyn(const float* Oh, const float* fx, float* Z, int B, int S1, int R, int NY, int C, fnm_stream_t stream) {
+    FNM_REQUIRE(Oh && fx && Z, "xsyn: NULL pointer");
+    FNM_REQUIRE(B > 0 && S1 > 0 && R > 0 && NY > 0 && C > 0, "xsyn: bad extents");
+    return simt_xsyn(Oh, fx, Z, B, S1, R, NY, C, as_stream(stream));
+}
+
+int fnm_mix_fwd(const float* Xh, const float* w0, const float* w1, int rows_per_w, float* Oh, int B, int R, int NY,
+                int Ci, int Co, fnm_stream_t stream) {
+    FNM_REQUIRE(Xh && w0 && Oh, "mix_fwd: NULL pointer");
+    FNM_REQUIRE(rows_per_w == R || (w1 && 2 * rows_per_w == R), "mix_fwd: weight rows do not cover R");
+    return simt_mix_fwd(Xh, w0, w1, rows_per_w, Oh, B, R, NY, Ci, Co, as_stream(stream));
+}
+
+int fnm_mix_bwd_x(const float* Gh, const float* w0, const float* w1, int rows_per_w, float* Gxh, int B, int R, int NY,
+                  int Ci, int Co, fnm_stream_t stream) {
+    FNM_REQUIRE(Gh && w0 && Gxh, "mix_bwd_x: NULL pointer");
+    FNM_REQUIRE(rows_per_w == R || (w1 && 2 * rows_per_w == R), "mix_bwd_x: weight rows do not cover R");
+    return simt_mix_bwd_x(Gh, w0, w1, rows_per_w, Gxh, B, R, NY, Ci, Co, as_stream(stream));
+}
+
+int fnm_mix_bwd_w(const float* Xh, const float* Gh, float* dw0, float* dw1, int rows_per_w, int B, int R, int NY,
+                  int Ci, int Co, fnm_stream_t stream) {
+    FNM_REQUIRE(Xh && Gh && dw0, "mix_bwd_w: NULL pointer");
+    FNM_REQUIRE(rows_per_w == R || (dw1 && 2 * rows_per_w == R), "mix_bwd_w: weight rows do not cover R");
+    return simt_mix_bwd_w(Xh, Gh, dw0, dw1, rows_per_w, B, R, NY, Ci, Co, as_stream(stream));
+}
+
+int fnm_pointwise_ysyn(const float* x, int act_in, const float* wc, int wc_is_kn, const float* bias, const float* Z,
+                       const float* by, const float* mul_gelu_grad_of, float* out, int64_t rows, int S2, int LY, int K,
+                       int N, int mode, fnm_stream_t stream) {
+    FNM_REQUIRE(Z && by && out, "pointwise_ysyn: NULL pointer");
+    FNM_REQUIRE(rows >= 0 && S2 > 0 && LY > 0 && N > 0 && K >= 0, "pointwise_ysyn: bad extents");
+    FNM_REQUIRE((x == nullptr) == (wc == nullptr) || K == 0, "pointwise_ysyn: x and wc must be given together");
+    if (tc_pointwise_ysyn_supported(rows, S2, LY, (x && wc) ? K : 0, N))
+        return tc_pointwise_ysyn(x, act_in, wc, wc_is_kn, bias, Z, by, mul_gelu_grad_of, out, rows, S2, LY, K, N, mode,
+                                 as_stream(stream));
+    return simt_pointwise_ysyn(x, act_in, wc, wc_is_kn, bias, Z, by, mul_gelu_grad_of, out, rows, S2, LY, K, N,
+                               as_stream(stream));
+}
+
+size_t fnm_conv_wgrad_workspace_bytes(int64_t npos, int Ci, int Co) { return simt_conv_wgrad_workspace(npos, Ci, Co); }
+
+int fnm_conv_wgrad(const float* g, const float* x, int act_in, float* dwc, float* dbc, int64_t npos, int Ci, int Co,
+                   void* workspace, size_t workspace_bytes, int mode, fnm_stream_t stream) {
+    (void)mode;
+    FNM_REQUIRE(g && x && workspace, "conv_wgrad: NULL pointer");
+    if (workspace_bytes < simt_conv_wgrad_workspace(npos, Ci, Co)) return fail(FNM_EWORKSPACE, "conv_wgrad: workspace too small");
+    return simt_conv_wgrad(g, x, act_in, dwc, dbc, npos, Ci, Co, static_cast<float*>(workspace), as_stream(stream));
+}
+
+int fnm_gelu_fwd(const float* z, float* y, int64_t n, fnm_stream_t stream) {
+    FNM_REQUIRE(z && y, "gelu_fwd: NULL pointer");
+    return gelu_launch(nullptr, z, y, n, false, as_stream(stream));
+}
+
+int fnm_gelu_bwd(const float* g_y, const float* z, float* g_z, int64_t n, fnm_stream_t stream) {
+    FNM_REQUIRE(g_y && z && g_z, "gelu_bwd: NULL pointer");
+    return gelu_launch(g_y, z, g_z, n, true, as_stream(stream));
+}
+
+int fnm_adam_multi_tensor(int n, float* const* p, const float* const* g, float* const* m, float* const* v,
+                          float* const* vmax, const int64_t* numel, const uint8_t* is_complex, double lr, double beta1,
+                          double beta2, double eps, double weight_decay, int amsgrad, int step, const int32_t* step_dev,
+                          fnm_stream_t stream) {
+    FNM_REQUIRE(n >= 0, "adam: negative tensor count");
+    if (n == 0) return FNM_OK;
+    FNM_REQUIRE(p && g && m && v && numel && is_complex, "adam: NULL table");
+    FNM_REQUIRE(step >= 1 || step_dev, "adam: step must be >= 1");
+    return adam_launch(n, p, g, m, v, vmax, numel, is_complex, lr, beta1, beta2, eps, weight_decay, amsgrad, step,
+                       step_dev, as_stream(stream));
+}
+
+int fnm_counter_inc(int32_t* counter, fnm_stream_t stream) {
+    FNM_REQUIRE(counter, "counter_inc: NULL pointer");
+    return counter_inc(counter, as_stream(stream));
+}
+
+// ------------------------------------------------------------------------------------------------
+// fused Fourier layer
+// ------------------------------------------------------------------------------------------------
+size_t fnm_fourier_layer_workspace_bytes(const fnm_plan* plan) {
+    if (!plan) return 0;
+    const LayerWs w = layer_ws(plan);
+    return (w.T + w.Oh + w.Z + w.Gh + w.partial) * sizeof(float) + 5 * 256;
+}
+
+int fnm_fourier_layer_fwd(const fnm_plan* p, const float* xin, int act_in, const float* w0, const float* w1,
+                          const float* wc, const float* bc, float* z_out, float* xh_save, void* workspace,
+                          size_t workspace_bytes, fnm_stream_t stream) {
+    FNM_TRY(check_plan(p, true, true));
+    FNM_REQUIRE(xin && w0 && z_out && xh_save && workspace, "layer_fwd: NULL pointer");
+    FNM_REQUIRE(p->rows_per_w == p->R || (w1 && 2 * p->rows_per_w == p->R), "layer_fwd: weight rows do not cover R");
+    if (wc && (p->S1 != p->P1 || p->S2 != p->P2))
+        return fail(FNM_ENOTSUP, "layer_fwd: the pointwise branch cannot be fused with a resolution change");
+    if (workspace_bytes < fnm_fourier_layer_workspace_bytes(p)) return fail(FNM_EWORKSPACE, "layer_fwd: workspace too small");
+    cudaStream_t st = as_stream(stream);
+    const LayerWs w = layer_ws(p);
+    Carver cv(workspace, workspace_bytes);
+    float* T = cv.take(w.T);
+    float* Oh = cv.take(w.Oh);
+    float* Z = cv.take(w.Z);
+    const int LY = 2 * p->NY;
+    FNM_TRY(fnm_ydft(xin, p->ay, T, (int64_t)p->B * p->P1, p->P2, LY, p->Ci, act_in, p->mode, stream));
+    FNM_TRY(simt_xdft(T, p->ex, xh_save, p->B, p->P1, p->R, p->NY, p->Ci, st));
+    FNM_TRY(simt_mix_fwd(xh_save, w0, w1, p->rows_per_w, Oh, p->B, p->R, p->NY, p->Ci, p->Co, st));
+    FNM_TRY(simt_xsyn(Oh, p->fx, Z, p->B, p->S1, p->R, p->NY, p->Co, st));
+    return fnm_pointwise_ysyn(wc ? xin : nullptr, act_in, wc, 0, bc, Z, p->by, nullptr, z_out, (int64_t)p->B * p->S1,
+                              p->S2, LY, p->Ci, p->Co, p->mode, stream);
+}
+
+int fnm_fourier_layer_bwd(const fnm_plan* p, const float* g_z, const float* xin, int act_in, const float* w0,
+                          const float* w1, const float* wc, const float* xh_save, float* g_in, float* dw0, float* dw1,
+                          float* dwc, float* dbc, void* workspace, size_t workspace_bytes, fnm_stream_t stream) {
+    FNM_TRY(check_plan(p, true, true));
+    FNM_REQUIRE(g_z && xin && w0 && xh_save && workspace, "layer_bwd: NULL pointer");
+    FNM_REQUIRE(p->rows_per_w == p->R || (w1 && 2 * p->rows_per_w == p->R), "layer_bwd: weight rows do not cover R");
+    if (wc && (p->S1 != p->P1 || p->S2 != p->P2))
+        return fail(FNM_ENOTSUP, "layer_bwd: the pointwise branch cannot be fused with a resolution change");
+    if (workspace_bytes < fnm_fourier_layer_workspace_bytes(p)) return fail(FNM_EWORKSPACE, "layer_bwd: workspace too small");
+    cudaStream_t st = as_stream(stream);
+    const LayerWs w = layer_ws(p);
+    Carver cv(workspace, workspace_bytes);
+    float* Tg = cv.take(w.T);
+    float* Gxh = cv.take(w.Oh);
+    float* Zg = cv.take(w.Z);
+    float* Gh = cv.take(w.Gh);
+    float* partial = cv.take(w.partial);
+    const int LY = 2 * p->NY;
+    // analysis of g_z (c_l/N folded into byT), A.2 first line
+    FNM_TRY(fnm_ydft(g_z, p->byT, Tg, (int64_t)p->B * p->S1, p->S2, LY, p->Co, 0, p->mode, stream));
+    FNM_TRY(simt_xdft(Tg, p->exb, Gh, p->B, p->S1, p->R, p->NY, p->Co, st));
+    if (dw0) FNM_TRY(simt_mix_bwd_w(xh_save, Gh, dw0, dw1, p->rows_per_w, p->B, p->R, p->NY, p->Ci, p->Co, st));
+    if (wc && (dwc || dbc))
+        FNM_TRY(simt_conv_wgrad(g_z, xin, act_in, dwc, dbc, (int64_t)p->B * p->S1 * p->S2, p->Ci, p->Co, partial, st));
+    if (g_in) {
+        FNM_TRY(simt_mix_bwd_x(Gh, w0, w1, p->rows_per_w, Gxh, p->B, p->R, p->NY, p->Ci, p->Co, st));
+        FNM_TRY(simt_xsyn(Gxh, p->fxb, Zg, p->B, p->P1, p->R, p->NY, p->Ci, st));
+        FNM_TRY(fnm_pointwise_ysyn(wc ? g_z : nullptr, 0, wc, 1, nullptr, Zg, p->ayT, act_in ? xin : nullptr, g_in,
+                                   (int64_t)p->B * p->P1, p->P2, LY, p->Co, p->Ci, p->mode, stream));
+    }
+    return FNM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// F2V
+// ------------------------------------------------------------------------------------------------
+size_t fnm_lfunc_workspace_bytes(const fnm_plan* p) {
+    if (!p) return 0;
+    const size_t LY = 2 * (size_t)p->NY;
+    const size_t T = (size_t)p->B * p->P1 * LY * p->Ci;
+    const size_t Gxh = (size_t)p->R * p->NY * 2 * p->B * p->Ci;
+    const size_t cmax = p->Ci > p->Co ? p->Ci : p->Co;
+    return (T + Gxh) * sizeof(float) + simt_mode_split_workspace(p->R * p->NY, p->B, (int)cmax) + 4 * 256;
+}
+
+int fnm_lfunc_fwd(const fnm_plan* p, const float* xin, int act_in, const float* w, const float* cc, float* out,
+                  float* xh_save, void* workspace, size_t workspace_bytes, fnm_stream_t stream) {
+    FNM_TRY(check_plan(p, true, false));
+    FNM_REQUIRE(xin && w && cc && out && xh_save && workspace, "lfunc_fwd: NULL pointer");
+    if (workspace_bytes < fnm_lfunc_workspace_bytes(p)) return fail(FNM_EWORKSPACE, "lfunc_fwd: workspace too small");
+    cudaStream_t st = as_stream(stream);
+    Carver cv(workspace, workspace_bytes);
+    const int LY = 2 * p->NY;
+    float* T = cv.take((size_t)p->B * p->P1 * LY * p->Ci);
+    float* partial = cv.take(simt_mode_split_workspace(p->R * p->NY, p->B, p->Co) / sizeof(float));
+    FNM_TRY(fnm_ydft(xin, p->ay, T, (int64_t)p->B * p->P1, p->P2, LY, p->Ci, act_in, p->mode, stream));
+    FNM_TRY(simt_xdft(T, p->ex, xh_save, p->B, p->P1, p->R, p->NY, p->Ci, st));
+    return simt_lfunc_contract(xh_save, w, cc, out, partial, p->B, p->R, p->NY, p->Ci, p->Co, st);
+}
+
+int fnm_lfunc_bwd(const fnm_plan* p, const float* g_out, const float* xin, int act_in, const float* w, const float* cc,
+                  const float* xh_save, float* g_in, float* dw, void* workspace, size_t workspace_bytes,
+                  fnm_stream_t stream) {
+    FNM_TRY(check_plan(p, true, false));
+    FNM_REQUIRE(g_out && xin && w && cc && xh_save && workspace, "lfunc_bwd: NULL pointer");
+    if (workspace_bytes < fnm_lfunc_workspace_bytes(p)) return fail(FNM_EWORKSPACE, "lfunc_bwd: workspace too small");
+    cudaStream_t st = as_stream(stream);
+    Carver cv(workspace, workspace_bytes);
+    const int LY = 2 * p->NY;
+    float* Zg = cv.take((size_t)p->B * p->P1 * LY * p->Ci);
+    float* Gxh = cv.take((size_t)p->R * p->NY * 2 * p->B * p->Ci);
+    if (dw) FNM_TRY(simt_lfunc_bwd_w(g_out, xh_save, cc, dw, p->B, p->R, p->NY, p->Ci, p->Co, st));
+    if (g_in) {
+        FNM_TRY(simt_lfunc_bwd_x(g_out, w, cc, Gxh, p->B, p->R, p->NY, p->Ci, p->Co, st));
+        FNM_TRY(simt_xsyn(Gxh, p->fxb, Zg, p->B, p->P1, p->R, p->NY, p->Ci, st));
+        FNM_TRY(fnm_pointwise_ysyn(nullptr, 0, nullptr, 0, nullptr, Zg, p->ayT, act_in ? xin : nullptr, g_in,
+                                   (int64_t)p->B * p->P1, p->P2, LY, 0, p->Ci, p->mode, stream));
+    }
+    return FNM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// V2F
+// ------------------------------------------------------------------------------------------------
+size_t fnm_ldec_workspace_bytes(const fnm_plan* p) {
+    if (!p) return 0;
+    const size_t LY = 2 * (size_t)p->NY;
+    const size_t Z = (size_t)p->B * p->S1 * LY * p->Co;
+    const size_t Oh = (size_t)p->R * p->NY * 2 * p->B * p->Co;
+    return (Z + Oh) * sizeof(float) + simt_mode_split_workspace(p->R * p->NY, p->B, p->Ci) + 4 * 256;
+}
+
+int fnm_ldec_fwd(const fnm_plan* p, const float* v, const float* w, float* y_out, void* workspace,
+                 size_t workspace_bytes, fnm_stream_t stream) {
+    FNM_TRY(check_plan(p, false, true));
+    FNM_REQUIRE(v && w && y_out && workspace, "ldec_fwd: NULL pointer");
+    if (workspace_bytes < fnm_ldec_workspace_bytes(p)) return fail(FNM_EWORKSPACE, "ldec_fwd: workspace too small");
+    cudaStream_t st = as_stream(stream);
+    Carver cv(workspace, workspace_bytes);
+    const int LY = 2 * p->NY;
+    float* Z = cv.take((size_t)p->B * p->S1 * LY * p->Co);
+    float* Oh = cv.take((size_t)p->R * p->NY * 2 * p->B * p->Co);
+    FNM_TRY(simt_ldec_mix(v, w, Oh, p->B, p->R, p->NY, p->Ci, p->Co, st));
+    FNM_TRY(simt_xsyn(Oh, p->fx, Z, p->B, p->S1, p->R, p->NY, p->Co, st));
+    return fnm_pointwise_ysyn(nullptr, 0, nullptr, 0, nullptr, Z, p->by, nullptr, y_out, (int64_t)p->B * p->S1, p->S2,
+                              LY, 0, p->Co, p->mode, stream);
+}
+
+int fnm_ldec_bwd(const fnm_plan* p, const float* g_y, const float* v, const float* w, float* g_v, float* dw,
+                 void* workspace, size_t workspace_bytes, fnm_stream_t stream) {
+    FNM_TRY(check_plan(p, false, true));
+    FNM_REQUIRE(g_y && v && w && workspace, "ldec_bwd: NULL pointer");
+    if (workspace_bytes < fnm_ldec_workspace_bytes(p)) return fail(FNM_EWORKSPACE, "ldec_bwd: workspace too small");
+    cudaStream_t st = as_stream(stream);
+    Carver cv(workspace, workspace_bytes);
+    const int LY = 2 * p->NY;
+    float* Tg = cv.take((size_t)p->B * p->S1 * LY * p->Co);
+    float* Gh = cv.take((size_t)p->R * p->NY * 2 * p->B * p->Co);
+    float* partial = cv.take(simt_mode_split_workspace(p->R * p->NY, p->B, p->Ci) / sizeof(float));
+    FNM_TRY(fnm_ydft(g_y, p->byT, Tg, (int64_t)p->B * p->S1, p->S2, LY, p->Co, 0, p->mode, stream));
+    FNM_TRY(simt_xdft(Tg, p->exb, Gh, p->B, p->S1, p->R, p->NY, p->Co, st));
+    if (dw) FNM_TRY(simt_ldec_bwd_w(v, Gh, dw, p->B, p->R, p->NY, p->Ci, p->Co, st));
+    if (g_v) FNM_TRY(simt_ldec_bwd_v(Gh, w, g_v, partial, p->B, p->R, p->NY, p->Ci, p->Co, st));
+    return FNM_OK;
+}
+
+}  // extern "C"

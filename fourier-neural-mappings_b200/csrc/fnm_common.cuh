@@ -1,0 +1,55 @@
+// Shared device/host helpers for libfnm_b200 (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+
+#include "../../include/fnm_b200.h"
+
+namespace fnm {
+
+// ---- error reporting (thread-local: forward runs on the main thread, backward on autograd's worker)
+char* err_buf();
+int fail(int code, const char* fmt, ...);
+int check_launch(const char* what);
+
+#define FNM_REQUIRE(cond, ...)                                   \
+    do {                                                         \
+        if (!(cond)) return ::fnm::fail(FNM_EINVAL, __VA_ARGS__); \
+    } while (0)
+
+#define FNM_TRY(expr)                   \
+    do {                                \
+        int _rc = (expr);               \
+        if (_rc != FNM_OK) return _rc;  \
+    } while (0)
+
+static inline cudaStream_t as_stream(fnm_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// ---- exact (erf) GELU, the F.gelu default the reference uses (models/shared.py:13-14)
+__device__ __forceinline__ float gelu_f(float x) {
+    return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+}
+__device__ __forceinline__ float gelu_grad_f(float x) {
+    const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
+    const float pdf = 0.39894228040143267794f * expf(-0.5f * x * x);
+    return cdf + x * pdf;
+}
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// carve consecutive 256-byte aligned float buffers out of a caller-owned workspace
+struct Carver {
+    char* base;
+    size_t off, cap;
+    Carver(void* p, size_t bytes) : base(static_cast<char*>(p)), off(0), cap(bytes) {}
+    float* take(size_t nfloats) {
+        size_t o = align_up(off, 256);
+        off = o + nfloats * sizeof(float);
+        return reinterpret_cast<float*>(base + o);
+    }
+    bool ok() const { return off <= cap; }
+};
+
+}  // namespace fnm

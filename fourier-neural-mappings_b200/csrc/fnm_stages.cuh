@@ -1,0 +1,52 @@
+// Internal C++ interface between the extern "C" layer (fnm_api.cu) and the kernel files.
+#pragma once
+#include "fnm_common.cuh"
+
+namespace fnm {
+
+// ---- fp32 SIMT stages (fnm_simt.cu)
+int simt_ydft(const float* x, const float* tab, float* T, int64_t rows, int P2, int LY, int C, int act, cudaStream_t st);
+int simt_xdft(const float* T, const float* ex, float* Xh, int B, int P1, int R, int NY, int C, cudaStream_t st);
+int simt_xsyn(const float* Oh, const float* fx, float* Z, int B, int S1, int R, int NY, int C, cudaStream_t st);
+int simt_mix_fwd(const float* Xh, const float* w0, const float* w1, int rpw, float* Oh, int B, int R, int NY, int Ci,
+                 int Co, cudaStream_t st);
+int simt_mix_bwd_x(const float* Gh, const float* w0, const float* w1, int rpw, float* Gxh, int B, int R, int NY, int Ci,
+                   int Co, cudaStream_t st);
+int simt_mix_bwd_w(const float* Xh, const float* Gh, float* dw0, float* dw1, int rpw, int B, int R, int NY, int Ci,
+                   int Co, cudaStream_t st);
+int simt_pointwise_ysyn(const float* x, int act, const float* wc, int wc_is_kn, const float* bias, const float* Z,
+                        const float* by, const float* mul, float* out, int64_t rows, int S2, int LY, int K, int N,
+                        cudaStream_t st);
+size_t simt_conv_wgrad_workspace(int64_t npos, int Ci, int Co);
+int simt_conv_wgrad(const float* g, const float* x, int act, float* dwc, float* dbc, int64_t npos, int Ci, int Co,
+                    float* partial, cudaStream_t st);
+size_t simt_mode_split_workspace(int nmodes, int B, int C);
+int simt_lfunc_contract(const float* Xh, const float* w, const float* cc, float* out, float* partial, int B, int R,
+                        int NY, int Ci, int Co, cudaStream_t st);
+int simt_lfunc_bwd_x(const float* g, const float* w, const float* cc, float* Gxh, int B, int R, int NY, int Ci, int Co,
+                     cudaStream_t st);
+int simt_lfunc_bwd_w(const float* g, const float* Xh, const float* cc, float* dw, int B, int R, int NY, int Ci, int Co,
+                     cudaStream_t st);
+int simt_ldec_mix(const float* v, const float* w, float* Oh, int B, int R, int NY, int Ci, int Co, cudaStream_t st);
+int simt_ldec_bwd_w(const float* v, const float* Gh, float* dw, int B, int R, int NY, int Ci, int Co, cudaStream_t st);
+int simt_ldec_bwd_v(const float* Gh, const float* w, float* dv, float* partial, int B, int R, int NY, int Ci, int Co,
+                    cudaStream_t st);
+
+// ---- optimiser / elementwise (fnm_adam.cu)
+int adam_launch(int n, float* const* p, const float* const* g, float* const* m, float* const* v, float* const* vmax,
+                const int64_t* numel, const uint8_t* is_complex, double lr, double beta1, double beta2, double eps,
+                double wd, int amsgrad, int step, const int32_t* step_dev, cudaStream_t st);
+int counter_inc(int32_t* c, cudaStream_t st);
+int gelu_launch(const float* g, const float* z, float* out, int64_t n, bool grad, cudaStream_t st);
+
+// ---- tcgen05 / TMA kernels for the heavy spatial passes (fnm_tc.cu)
+int tc_available();
+bool tc_ydft_supported(int64_t rows, int P2, int LY, int C);
+int tc_ydft(const float* x, const float* tab, float* T, int64_t rows, int P2, int LY, int C, int act, int mode,
+            cudaStream_t st);
+bool tc_pointwise_ysyn_supported(int64_t rows, int S2, int LY, int K, int N);
+int tc_pointwise_ysyn(const float* x, int act, const float* wc, int wc_is_kn, const float* bias, const float* Z,
+                      const float* by, const float* mul, float* out, int64_t rows, int S2, int LY, int K, int N,
+                      int mode, cudaStream_t st);
+
+}  // namespace fnm

@@ -1,0 +1,113 @@
+"""The layer loop every Fourier Neural Mapping shares, on channels-last activations.
+
+Reference: the three-line loop ``x = w(x) + speconv(x); x = self.act(x)`` of
+/root/reference/models/func_to_func2d.py:89-95 (and its twins in the other model files).  With
+GELU the activation is never materialised between layers: each fused layer kernel stores its
+pre-activation z and the NEXT layer applies GELU while loading ("save only
+the pre-activation"); backward multiplies by GELU'(z) in the producing kernel's epilogue.
+"""
+import torch
+import torch.nn.functional as F
+
+from .. import ops
+from ..shared import projector1d, projector2d
+
+_TORCH_ACTS = {"tanh": torch.tanh, "relu": F.relu, "elu": F.elu, "leaky_relu": F.leaky_relu}
+
+
+class Pending:
+    """A channels-last activation whose GELU may still be pending (``z`` holds the pre-activation)."""
+
+    __slots__ = ("z", "act")
+
+    def __init__(self, z, act=False):
+        self.z, self.act = z, act
+
+    def value(self):
+        return ops.gelu(self.z) if self.act else self.z
+
+
+def _layer_tables(speconv, P1, P2, one_d, s=None):
+    if one_d:
+        return speconv.tables(P2, s)
+    return speconv.tables(P1, P2, s)
+
+
+def run_layers(state, speconvs, ws, act_name, act_flags, one_d, last_s=None):
+    """Apply the Fourier layers to ``state`` (a Pending over a (B, P1, P2, C) tensor; P1 = 1 in 1-D).
+    ``act_flags[i]`` says whether layer i is followed by the activation.  ``last_s`` (padded output
+    resolution) switches the LAST layer to the resolution-changing form
+    ``w(projector(x, s)) + speconv(x, s)`` (func_to_func2d.py:95)."""
+    n = len(speconvs)
+    fused_gelu = act_name == "gelu"
+    for i, (sc, w) in enumerate(zip(speconvs, ws)):
+        z_in = state.z
+        _, P1, P2, _ = z_in.shape
+        w1 = None if one_d else sc.weights2
+        last = i == n - 1
+        change = False
+        if last and last_s is not None:
+            target = (int(last_s),) if one_d else tuple(int(v) for v in last_s)
+            change = target != ((P2,) if one_d else (P1, P2))
+        if change:
+            x = state.value()
+            z = ops.fourier_layer(x, sc.weights1, w1, None, None, _layer_tables(sc, P1, P2, one_d, last_s))
+            # the pointwise branch acts on the Fourier-resampled input: adjacent op
+            if one_d:
+                xc = projector1d(x.squeeze(1).permute(0, 2, 1), last_s)
+                z = z + w(xc).permute(0, 2, 1).unsqueeze(1)
+            else:
+                xc = projector2d(x.permute(0, 3, 1, 2), last_s)
+                z = z + w(xc).permute(0, 2, 3, 1)
+        else:
+            z = ops.fourier_layer(z_in, sc.weights1, w1, w.weight, w.bias, _layer_tables(sc, P1, P2, one_d),
+                                  act_in=state.act)
+        if not act_flags[i]:
+            state = Pending(z, False)
+        elif fused_gelu:
+            state = Pending(z, True)
+        else:
+            state = Pending(_TORCH_ACTS[act_name](z), False)
+    return state
+
+
+def lift(x, fc0, padding, get_grid, one_d):
+    """Lifting + zero padding at the END of each axis (func_to_func2d.py:79-86) -> channels-last
+    (B, P1, P2, C) (P1 = 1 in 1-D).  Adjacent op: plain torch."""
+    from ..shared import get_grid1d, get_grid2d
+    if one_d:
+        n = x.shape[-1]
+        x = x.permute(0, 2, 1)
+        if get_grid:
+            x = torch.cat((x, get_grid1d(x.shape, x.device).to(x.dtype)), dim=-1)
+        x = fc0(x)
+        x = F.pad(x, [0, 0, 0, n // padding])
+        return x.unsqueeze(1), (n,)
+    n1, n2 = x.shape[-2:]
+    x = x.permute(0, 2, 3, 1)
+    if get_grid:
+        x = torch.cat((x, get_grid2d(x.shape, x.device).to(x.dtype)), dim=-1)
+    x = fc0(x)
+    x = F.pad(x, [0, 0, 0, n2 // padding, 0, n1 // padding])
+    return x, (n1, n2)
+
+
+def crop(x, cut, one_d):
+    """Remove the padding (func_to_func2d.py:98-101).  Like the reference's ``:-c`` slice, c == 0
+    yields an empty axis."""
+    if one_d:
+        return x[:, :, :-cut[0], :] if cut[0] != 0 else x[:, :, :0, :]
+    x = x[:, :-cut[0], :, :] if cut[0] != 0 else x[:, :0, :, :]
+    return x[:, :, :-cut[1], :] if cut[1] != 0 else x[:, :, :0, :]
+
+
+def functional_end(state, lfunc0, mlpfunc0, head, one_d):
+    """F2V end (func_to_vec2d.py:97-110): nonlocal functionals || pointwise MLP + trapezoid rule."""
+    z = state.z
+    _, P1, P2, _ = z.shape
+    tables = lfunc0.tables(P2) if one_d else lfunc0.tables(P1, P2)
+    nonlocal_feats = ops.linear_functional(z, lfunc0.weights, tables, act_in=state.act)
+    h = mlpfunc0(state.value())                               # (B, P1, P2, width_lfunc)
+    h = torch.trapz(h, dx=1.0 / P2, dim=2)
+    h = h.squeeze(1) if one_d else torch.trapz(h, dx=1.0 / P1, dim=1)
+    return head(torch.cat((nonlocal_feats, h), dim=1))

@@ -1,0 +1,244 @@
+"""torch.autograd.Function wrappers over the C ABI (hand-written forward AND backward kernels).
+
+Tensors here are channels-last fp32: ``x[b, x, y, c]`` (1-D problems: ``x[b, 1, y, c]``).
+Everything is allocated with ``torch.empty`` (caching allocator) and handed to the library as raw
+device pointers together with the current CUDA stream; the library never allocates or syncs.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import FNM_MODE_FP32, FNM_MODE_TF32, check, lib
+
+_MODE = FNM_MODE_FP32
+
+
+def set_compute_mode(mode):
+    """'fp32' (default; 1e-5 parity with the reference) or 'tf32' (single-pass tensor cores,
+    looser stated tolerance)."""
+    global _MODE
+    if mode not in ("fp32", "tf32"):
+        raise ValueError("mode must be 'fp32' or 'tf32'")
+    _MODE = FNM_MODE_FP32 if mode == "fp32" else FNM_MODE_TF32
+
+
+def get_compute_mode():
+    return "fp32" if _MODE == FNM_MODE_FP32 else "tf32"
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise _lib.FnmError("the Fourier-layer hot path runs on CUDA only (no CPU fallback): got a "
+                                f"{t.device} tensor")
+
+
+def _f32c(t):
+    if t.dtype != torch.float32:
+        raise TypeError(f"expected float32, got {t.dtype}")
+    return t.contiguous()
+
+
+def _cplx(t):
+    """complex64 parameter -> contiguous float view of interleaved (re, im)."""
+    if t.dtype != torch.complex64:
+        raise TypeError(f"expected complex64 weights, got {t.dtype}")
+    return torch.view_as_real(t.contiguous())
+
+
+_WS = {}
+
+
+def _workspace(device, nbytes):
+    """Per-(device, stream) scratch, grown on demand.  Stages of one call run in stream order, and
+    every call on the same stream is ordered after the previous one, so one buffer suffices."""
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    buf = _WS.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(int(nbytes * 1.25) + 1024, dtype=torch.uint8, device=device)
+        _WS[key] = buf
+    return buf
+
+
+class FourierLayerFn(torch.autograd.Function):
+    """z = Conv1x1(f(xin)) + bias + SpectralConv(f(xin)), f = GELU if act_in else identity.
+    wc / bc may be None (bare SpectralConv)."""
+
+    @staticmethod
+    def forward(ctx, xin, w0, w1, wc, bc, tables, act_in):
+        _need_cuda(xin, w0, w1, wc, bc)
+        xin = _f32c(xin)
+        B, P1, P2, Ci = xin.shape
+        Co = w0.shape[1]
+        if (P1, P2) != (tables.P1, tables.P2) or w0.shape[0] != Ci:
+            raise ValueError(f"input {tuple(xin.shape)} does not match the plan / weights")
+        plan = tables.c_plan(xin.device, B, Ci, Co, _MODE)
+        w0r = _cplx(w0)
+        w1r = _cplx(w1) if w1 is not None else None
+        wcc = _f32c(wc.reshape(Co, Ci)) if wc is not None else None
+        bcc = _f32c(bc) if bc is not None else None
+        z = torch.empty((B, tables.S1, tables.S2, Co), dtype=torch.float32, device=xin.device)
+        xh = torch.empty((tables.R, tables.NY, 2, B, Ci), dtype=torch.float32, device=xin.device)
+        L = lib()
+        nbytes = L.fnm_fourier_layer_workspace_bytes(C.byref(plan))
+        ws = _workspace(xin.device, nbytes)
+        check(L.fnm_fourier_layer_fwd(C.byref(plan), _ptr(xin), int(act_in), _ptr(w0r), _ptr(w1r), _ptr(wcc), _ptr(bcc),
+                                      _ptr(z), _ptr(xh), _ptr(ws), ws.numel(), _stream()), "fnm_fourier_layer_fwd")
+        ctx.save_for_backward(xin, w0, w1, wc, xh)
+        ctx.tables, ctx.act_in, ctx.has_bias = tables, bool(act_in), bc is not None
+        return z
+
+    @staticmethod
+    def backward(ctx, gz):
+        xin, w0, w1, wc, xh = ctx.saved_tensors
+        tables = ctx.tables
+        gz = _f32c(gz)
+        B, P1, P2, Ci = xin.shape
+        Co = w0.shape[1]
+        plan = tables.c_plan(xin.device, B, Ci, Co, _MODE)
+        need_x, need_w0, need_w1, need_wc, need_bc = ctx.needs_input_grad[:5]
+        g_in = torch.empty_like(xin) if need_x else None
+        want_w = need_w0 or (w1 is not None and need_w1)
+        dw0 = torch.empty_like(w0) if want_w else None
+        dw1 = torch.empty_like(w1) if (want_w and w1 is not None) else None
+        dwc = torch.empty_like(wc) if (wc is not None and need_wc) else None
+        dbc = torch.empty((Co,), dtype=torch.float32, device=xin.device) if (ctx.has_bias and need_bc) else None
+        w0r = _cplx(w0)
+        w1r = _cplx(w1) if w1 is not None else None
+        wcc = _f32c(wc.reshape(Co, Ci)) if wc is not None else None
+        L = lib()
+        nbytes = L.fnm_fourier_layer_workspace_bytes(C.byref(plan))
+        ws = _workspace(xin.device, nbytes)
+        check(L.fnm_fourier_layer_bwd(
+            C.byref(plan), _ptr(gz), _ptr(xin), int(ctx.act_in), _ptr(w0r), _ptr(w1r), _ptr(wcc), _ptr(xh),
+            _ptr(g_in), _ptr(torch.view_as_real(dw0)) if dw0 is not None else None,
+            _ptr(torch.view_as_real(dw1)) if dw1 is not None else None, _ptr(dwc), _ptr(dbc),
+            _ptr(ws), ws.numel(), _stream()), "fnm_fourier_layer_bwd")
+        return g_in, dw0, dw1, dwc, dbc, None, None
+
+
+class LinearFunctionalFn(torch.autograd.Function):
+    """out[b, o] = F2V functional of f(xin) (LinearFunctionals1d/2d)."""
+
+    @staticmethod
+    def forward(ctx, xin, w, tables, act_in):
+        _need_cuda(xin, w)
+        xin = _f32c(xin)
+        B, P1, P2, Ci = xin.shape
+        Co = w.shape[1]
+        if (P1, P2) != (tables.P1, tables.P2) or w.shape[0] != Ci:
+            raise ValueError(f"input {tuple(xin.shape)} does not match the plan / weights")
+        plan = tables.c_plan(xin.device, B, Ci, Co, _MODE)
+        cc = tables.device(xin.device)["cc"]
+        out = torch.empty((B, Co), dtype=torch.float32, device=xin.device)
+        xh = torch.empty((tables.R, tables.NY, 2, B, Ci), dtype=torch.float32, device=xin.device)
+        L = lib()
+        ws = _workspace(xin.device, L.fnm_lfunc_workspace_bytes(C.byref(plan)))
+        check(L.fnm_lfunc_fwd(C.byref(plan), _ptr(xin), int(act_in), _ptr(_cplx(w)), _ptr(cc), _ptr(out), _ptr(xh),
+                              _ptr(ws), ws.numel(), _stream()), "fnm_lfunc_fwd")
+        ctx.save_for_backward(xin, w, xh)
+        ctx.tables, ctx.act_in = tables, bool(act_in)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        xin, w, xh = ctx.saved_tensors
+        tables = ctx.tables
+        g = _f32c(g)
+        B, _, _, Ci = xin.shape
+        Co = w.shape[1]
+        plan = tables.c_plan(xin.device, B, Ci, Co, _MODE)
+        cc = tables.device(xin.device)["cc"]
+        g_in = torch.empty_like(xin) if ctx.needs_input_grad[0] else None
+        dw = torch.empty_like(w) if ctx.needs_input_grad[1] else None
+        L = lib()
+        ws = _workspace(xin.device, L.fnm_lfunc_workspace_bytes(C.byref(plan)))
+        check(L.fnm_lfunc_bwd(C.byref(plan), _ptr(g), _ptr(xin), int(ctx.act_in), _ptr(_cplx(w)), _ptr(cc), _ptr(xh),
+                              _ptr(g_in), _ptr(torch.view_as_real(dw)) if dw is not None else None,
+                              _ptr(ws), ws.numel(), _stream()), "fnm_lfunc_bwd")
+        return g_in, dw, None, None
+
+
+class LinearDecoderFn(torch.autograd.Function):
+    """y[b, x, y, o] = V2F decoder of the vector v[b, i] (LinearDecoder1d/2d)."""
+
+    @staticmethod
+    def forward(ctx, v, w, tables):
+        _need_cuda(v, w)
+        v = _f32c(v)
+        B, Ci = v.shape
+        Co = w.shape[1]
+        if w.shape[0] != Ci:
+            raise ValueError("vector width does not match the weights")
+        plan = tables.c_plan(v.device, B, Ci, Co, _MODE)
+        y = torch.empty((B, tables.S1, tables.S2, Co), dtype=torch.float32, device=v.device)
+        L = lib()
+        ws = _workspace(v.device, L.fnm_ldec_workspace_bytes(C.byref(plan)))
+        check(L.fnm_ldec_fwd(C.byref(plan), _ptr(v), _ptr(_cplx(w)), _ptr(y), _ptr(ws), ws.numel(), _stream()),
+              "fnm_ldec_fwd")
+        ctx.save_for_backward(v, w)
+        ctx.tables = tables
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        v, w = ctx.saved_tensors
+        tables = ctx.tables
+        gy = _f32c(gy)
+        B, Ci = v.shape
+        Co = w.shape[1]
+        plan = tables.c_plan(v.device, B, Ci, Co, _MODE)
+        gv = torch.empty_like(v) if ctx.needs_input_grad[0] else None
+        dw = torch.empty_like(w) if ctx.needs_input_grad[1] else None
+        L = lib()
+        ws = _workspace(v.device, L.fnm_ldec_workspace_bytes(C.byref(plan)))
+        check(L.fnm_ldec_bwd(C.byref(plan), _ptr(gy), _ptr(v), _ptr(_cplx(w)), _ptr(gv),
+                             _ptr(torch.view_as_real(dw)) if dw is not None else None,
+                             _ptr(ws), ws.numel(), _stream()), "fnm_ldec_bwd")
+        return gv, dw, None
+
+
+class GeluFn(torch.autograd.Function):
+    """Stand-alone exact GELU for a trunk that ends with an activation."""
+
+    @staticmethod
+    def forward(ctx, z):
+        _need_cuda(z)
+        z = _f32c(z)
+        y = torch.empty_like(z)
+        check(lib().fnm_gelu_fwd(_ptr(z), _ptr(y), z.numel(), _stream()), "fnm_gelu_fwd")
+        ctx.save_for_backward(z)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        (z,) = ctx.saved_tensors
+        gy = _f32c(gy)
+        gz = torch.empty_like(z)
+        check(lib().fnm_gelu_bwd(_ptr(gy), _ptr(z), _ptr(gz), z.numel(), _stream()), "fnm_gelu_bwd")
+        return gz
+
+
+def fourier_layer(xin, w0, w1, wc, bc, tables, act_in=False):
+    return FourierLayerFn.apply(xin, w0, w1, wc, bc, tables, act_in)
+
+
+def linear_functional(xin, w, tables, act_in=False):
+    return LinearFunctionalFn.apply(xin, w, tables, act_in)
+
+
+def linear_decoder(v, w, tables):
+    return LinearDecoderFn.apply(v, w, tables)
+
+
+def gelu(z):
+    return GeluFn.apply(z)

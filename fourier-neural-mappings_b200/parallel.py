@@ -1,0 +1,91 @@
+"""Data parallelism for the train step: one process per GPU, batch sharded, parameters and Adam
+state replicated, ONE exchange per step -- a SUM all-reduce of the weight gradients.
+
+SUM (not DDP's mean) because the reference loss sums over the batch
+(``LpLoss(size_average=False)``, /root/reference/advection_diffusion/func_to_func/train_fno.py:98,
+util/utilities_module.py:195-199): summed shard gradients equal the global-batch gradient, so the
+replicated Adam step is identical on every rank.  The reference itself has no distributed code
+(SURVEY.md section 2.2); this layer is new.
+
+Gradients live in ONE flat fp32 buffer (complex64 viewed as 2 x fp32); every ``param.grad`` is a
+view into it, so the exchange is a single NCCL all-reduce over NVLink (gloo on CPU in the tests)
+with no packing copies, and ``zero_grad`` is one memset.
+"""
+import torch
+import torch.distributed as dist
+
+
+class FlatGradients:
+    """Owns the flat gradient buffer of ``params`` and keeps ``p.grad`` pointing into it."""
+
+    def __init__(self, params):
+        self.params = [p for p in params if p.requires_grad]
+        if not self.params:
+            raise ValueError("no trainable parameters")
+        dev = self.params[0].device
+        self.offsets, total = [], 0
+        for p in self.params:
+            if p.device != dev:
+                raise ValueError("all parameters must live on one device")
+            n = p.numel() * (2 if p.is_complex() else 1)
+            self.offsets.append((total, n))
+            total += (n + 63) // 64 * 64                     # 256-byte aligned slots
+        self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.attach()
+
+    def attach(self):
+        for p, (off, n) in zip(self.params, self.offsets):
+            chunk = self.flat[off:off + n]
+            view = torch.view_as_complex(chunk.view(-1, 2)).view(p.shape) if p.is_complex() else chunk.view(p.shape)
+            p.grad = view
+
+    def zero_(self):
+        """Replacement for ``optimizer.zero_grad()``: keeps the views alive (set_to_none would drop them)."""
+        self.flat.zero_()
+        for p in self.params:
+            if p.grad is None:
+                self.attach()
+                break
+
+    def all_reduce(self, group=None, async_op=False):
+        """SUM over ranks; no-op in a single-process run."""
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+            return None
+        return dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
+
+
+def shard_batch(x, rank, world):
+    """Rank r trains on samples [r*B/G, (r+1)*B/G)."""
+    b = x.shape[0]
+    if b % world:
+        raise ValueError(f"global batch {b} is not divisible by {world} ranks")
+    per = b // world
+    return x[rank * per:(rank + 1) * per]
+
+
+def broadcast_parameters(module, src=0):
+    """Make every rank start from rank ``src``'s weights."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        for t in list(module.parameters()) + list(module.buffers()):
+            data = torch.view_as_real(t.data) if t.is_complex() else t.data
+            dist.broadcast(data, src)
+
+
+def train_step(model, optimizer, grads, loss_fn, x, y, group=None):
+    """zero_grad -> forward -> loss -> backward -> SUM all-reduce -> Adam (train_fno.py:187-197 +
+    the exchange).  Returns the LOCAL loss tensor (no host sync)."""
+    grads.zero_()
+    out = model(x)
+    loss = loss_fn(out, y)
+    loss.backward()
+    grads.all_reduce(group)
+    optimizer.step()
+    return loss
+
+
+def rel_l2_sum(out, y, eps=1e-6):
+    """The reference's training loss: LpLoss(size_average=False) (utilities_module.py:188-204)."""
+    b = out.shape[0]
+    num = torch.norm(out.reshape(b, -1) - y.reshape(b, -1), 2, 1)
+    den = torch.norm(y.reshape(b, -1), 2, 1) + eps
+    return torch.sum(num / den)

@@ -1,0 +1,198 @@
+"""Mode plans: the host-side index bookkeeping of the reference turned into small twiddle tables.
+
+The reference decides which Fourier bins a layer reads, where they land on the output grid and
+which are dropped with tensor slicing / ``torch.cat`` / ``zeros`` inside ``resize_rfft``,
+``resize_fft`` and ``resize_rfft2`` (/root/reference/models/shared.py:61-108, 136-147) and in the
+corner-block assignments of ``SpectralConv2d.forward`` (shared.py:330-333).  Here the same rules
+are applied once, on INDEX arrays, and baked into dense truncated-DFT tables (float64 trig,
+rounded to fp32) that the CUDA kernels contract against; see include/fnm_b200.h for the layouts.
+"""
+import math
+from functools import lru_cache
+
+import numpy as np
+import torch
+
+from ._lib import FNM_MODE_FP32, FnmPlan
+
+
+# ------------------------------------------------------------------------------------------
+# index maps
+# ------------------------------------------------------------------------------------------
+def onesided_source(n_have, s):
+    """Destination j of the one-sided resize (shared.py:61-80) takes source column ``out[j]`` (-1: zero)."""
+    if s < 1:
+        raise ValueError("s must be greater than or equal to 1.")
+    want = s // 2 + 1
+    out = np.full(want, -1, dtype=np.int64)
+    keep = min(want, n_have)
+    out[:keep] = np.arange(keep)
+    return out
+
+
+def twosided_source(n_have, s):
+    """Destination j of the two-sided resize (shared.py:83-108) takes source row ``out[j]`` (-1: zero)."""
+    if s < 1:
+        raise ValueError("s must be greater than or equal to 1.")
+    src = np.arange(n_have, dtype=np.int64)
+    if s >= n_have:
+        head = n_have // 2
+        return np.concatenate([src[:head], np.full(s - n_have, -1, dtype=np.int64), src[head:]])
+    if s == 1:
+        return src[:1]
+    front = s // 2 + 1 if s % 2 else s // 2
+    return np.concatenate([src[:front], src[n_have - (s - front):]])
+
+
+def _destination(source_map, n_src):
+    dst = np.full(n_src, -1, dtype=np.int64)
+    alive = source_map >= 0
+    dst[source_map[alive]] = np.nonzero(alive)[0]
+    return dst
+
+
+def _c2r_weight(bins, n):
+    c = np.where(bins < 0, 0.0, 2.0)
+    c[bins == 0] = 1.0
+    if n % 2 == 0:
+        c[bins == n // 2] = 1.0
+    return c
+
+
+def _cos_sin(bins, n):
+    """cos / sin of 2*pi*bin*j/n for j < n, shape (len(bins), n); dead bins (-1) give zero rows.
+    The product bin*j is reduced mod n in integers so large grids lose no precision, and the
+    exact zeros of the quarter-period points are snapped."""
+    j = np.arange(n, dtype=np.int64)
+    k = (np.maximum(bins, 0)[:, None] * j[None, :]) % n
+    ang = 2.0 * math.pi * k.astype(np.float64) / n
+    c, s = np.cos(ang), np.sin(ang)
+    s[(2 * k) % n == 0] = 0.0
+    c[((4 * k) % n == 0) & ((2 * k) % n != 0)] = 0.0
+    dead = bins < 0
+    c[dead, :] = 0.0
+    s[dead, :] = 0.0
+    return c, s
+
+
+def _embed_analysis(bins, n):
+    """[(ro,r)][(j,ri)] real embedding of e_r(j) = exp(-2 pi i bin_r j / n)."""
+    c, s = _cos_sin(bins, n)
+    r = len(bins)
+    t = np.zeros((2, r, n, 2))
+    t[0, :, :, 0], t[0, :, :, 1] = c, s
+    t[1, :, :, 0], t[1, :, :, 1] = -s, c
+    return t.reshape(2 * r, 2 * n)
+
+
+def _embed_synthesis(bins, n):
+    """[(j,ro)][(ri,r)] real embedding of f_r(j) = exp(+2 pi i bin_r j / n)."""
+    c, s = _cos_sin(bins, n)
+    r = len(bins)
+    t = np.zeros((n, 2, 2, r))
+    t[:, 0, 0, :], t[:, 0, 1, :] = c.T, -s.T
+    t[:, 1, 0, :], t[:, 1, 1, :] = s.T, c.T
+    return t.reshape(2 * n, 2 * r)
+
+
+class ModeTables:
+    """Host tables of one (kind, grid, modes) combination; device copies are made on demand."""
+
+    def __init__(self, kind, P1, P2, S1, S2, rows_in, rows_out, cols_in, cols_out, scale_in, scale_out,
+                 rows_per_w, cc=None):
+        self.kind = kind
+        self.P1, self.P2, self.S1, self.S2 = P1, P2, S1, S2
+        self.R, self.NY = len(rows_in if rows_in is not None else rows_out), \
+            len(cols_in if cols_in is not None else cols_out)
+        self.rows_per_w = rows_per_w
+        self.rows_in, self.rows_out, self.cols_in, self.cols_out = rows_in, rows_out, cols_in, cols_out
+        host = {}
+        if cols_in is not None:
+            c, s = _cos_sin(cols_in, P2)
+            ay = np.concatenate([scale_in * c, -scale_in * s], axis=0)            # [(ri,l)][y]
+            host["ay"], host["ayT"] = ay, ay.T
+            host["ex"] = _embed_analysis(rows_in, P1)
+            host["fxb"] = _embed_synthesis(rows_in, P1)
+        if cols_out is not None:
+            c, s = _cos_sin(cols_out, S2)
+            w = (scale_out * _c2r_weight(cols_out, S2))[:, None]
+            byT = np.concatenate([w * c, -w * s], axis=0)                         # [(ri,l)][y']
+            host["byT"], host["by"] = byT, byT.T
+            host["fx"] = _embed_synthesis(rows_out, S1)
+            host["exb"] = _embed_analysis(rows_out, S1)
+        if cc is not None:
+            host["cc"] = cc
+        self.host = {k: np.ascontiguousarray(v, dtype=np.float32) for k, v in host.items()}
+        self._dev = {}
+
+    def device(self, device):
+        key = str(device)
+        if key not in self._dev:
+            self._dev[key] = {k: torch.from_numpy(v).to(device) for k, v in self.host.items()}
+        return self._dev[key]
+
+    def c_plan(self, device, B, Ci, Co, mode=FNM_MODE_FP32):
+        d = self.device(device)
+        p = FnmPlan()
+        p.B, p.P1, p.P2, p.S1, p.S2 = B, self.P1, self.P2, self.S1, self.S2
+        p.R, p.NY, p.Ci, p.Co, p.rows_per_w, p.mode = self.R, self.NY, Ci, Co, self.rows_per_w, mode
+        for name in ("ay", "ayT", "by", "byT", "ex", "fx", "exb", "fxb"):
+            setattr(p, name, d[name].data_ptr() if name in d else None)
+        return p
+
+
+@lru_cache(maxsize=256)
+def spectral_tables(P1, P2, m1, m2, S1=None, S2=None, one_d=False):
+    """SpectralConv1d (one_d: P1 = 1, weights1 only) / SpectralConv2d (weights1 | weights2)."""
+    S1 = P1 if S1 is None else S1
+    S2 = P2 if S2 is None else S2
+    if S1 < 1 or S2 < 1:
+        raise ValueError("s must be greater than or equal to 1.")
+    if m2 > P2 // 2 + 1:
+        raise ValueError(f"modes ({m2}) exceed the one-sided spectrum of a {P2}-point axis ({P2 // 2 + 1})")
+    if one_d:
+        rows_in = np.zeros(1, dtype=np.int64)
+        rows_out = rows_in.copy()
+        rows_per_w = 1
+    else:
+        if 2 * m1 > P1:
+            raise ValueError(f"modes1={m1} needs a grid of at least {2 * m1} points along x (got {P1}): the "
+                             "two corner blocks of the reference would overlap")
+        rows_in = np.concatenate([np.arange(m1), np.arange(P1 - m1, P1)]).astype(np.int64)
+        rows_out = rows_in if S1 == P1 else _destination(twosided_source(P1, S1), P1)[rows_in]
+        rows_per_w = m1
+    cols_in = np.arange(m2, dtype=np.int64)
+    cols_out = cols_in if S2 == P2 else _destination(onesided_source(P2 // 2 + 1, S2), P2 // 2 + 1)[cols_in]
+    return ModeTables("spectral", P1, P2, S1, S2, rows_in, rows_out, cols_in, cols_out,
+                      1.0, 1.0 / (P1 * P2), rows_per_w)
+
+
+@lru_cache(maxsize=256)
+def functional_tables(P1, P2, m1, m2, one_d=False):
+    """LinearFunctionals1d (weights (Ci,Co,m+1)) / LinearFunctionals2d (weights (Ci,Co,2*m1,m2+1))."""
+    cols_in = onesided_source(P2 // 2 + 1, 2 * m2)
+    if one_d:
+        rows_in = np.zeros(1, dtype=np.int64)
+        cc = np.full((1, m2 + 1), 2.0)
+        cc[0, 0] = 1.0                                                   # shared.py:254
+    else:
+        rows_in = twosided_source(P1, 2 * m1)
+        cc = np.full((2 * m1, m2 + 1), 2.0)                              # shared.py:380-381
+        cc[m1:, 0] = 0.0
+        cc[0, 0] = 1.0
+    return ModeTables("functional", P1, P2, P1, P2, rows_in, None, cols_in, None,
+                      1.0 / (P1 * P2), 0.0, len(rows_in), cc=cc)
+
+
+@lru_cache(maxsize=256)
+def decoder_tables(S1, S2, m1, m2, one_d=False):
+    """LinearDecoder1d / LinearDecoder2d: weight row r / column l -> bin of the (S1, S2) grid."""
+    if S1 < 1 or S2 < 1:
+        raise ValueError("s must be greater than or equal to 1.")
+    cols_out = _destination(onesided_source(m2 + 1, S2), m2 + 1)
+    if one_d:
+        rows_out = np.zeros(1, dtype=np.int64)
+    else:
+        rows_out = _destination(twosided_source(2 * m1, S1), 2 * m1)
+    return ModeTables("decoder", S1, S2, S1, S2, None, rows_out, None, cols_out,
+                      0.0, 1.0 / (S1 * S2), len(rows_out))

@@ -1,0 +1,174 @@
+/*
+ * fnm_b200.h -- C ABI of the B200-native Fourier-layer hot path (libfnm_b200.so).
+ *
+ * The reference (nickhnelsen/fourier-neural-mappings) has NO FFI / plugin boundary: the hot path
+ * sits behind Python nn.Modules (models/shared.py) and an optimizer (util/Adam.py) that delegate
+ * all arithmetic to torch.fft / einsum / conv / gelu.  This header is the boundary a native
+ * replacement of those call sites binds to; each entry point cites the reference lines it
+ * replaces.  Python binds it with ctypes; no torch types appear here.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer to fp32 data unless stated otherwise; complex64 tensors are
+ *     passed as float* to interleaved (re, im) pairs in the reference's own layout;
+ *   - activations are channels-last:  X[b][x][y][c]  (1-D problems use P1 = S1 = 1, R = 1);
+ *   - the library never allocates, frees or synchronises: outputs, saved tensors and scratch are
+ *     caller-owned (torch caching allocator), every launch goes to the explicit `stream`;
+ *   - re-entrant: no state is carried between calls (backward runs on autograd's worker thread);
+ *   - return value 0 = OK, otherwise an FNM_E* code and fnm_last_error() (thread-local) explains.
+ *
+ * Mode plan.  All transforms are TRUNCATED dense DFTs driven by small host-built tables, so the
+ * reference's mode bookkeeping (resize_rfft / resize_fft / resize_rfft2, shared.py:61-108,136-147;
+ * which bins are read, where they land, which are dropped) lives entirely in the tables:
+ *   R   retained kx rows of the (stacked) weight        NY  retained ky columns, LY = 2*NY
+ *   ay  [LY][P2]   analysis along y   (rows: Re a_l, Im a_l;  a_l(y) = scale_in * e^{-i th_y})
+ *   ayT [P2][LY]   its transpose      (backward synthesis along y)
+ *   by  [S2][LY]   synthesis along y  (cols: Re b_l, -Im b_l; b_l(y) = scale_out * c_l e^{+i th_y})
+ *   byT [LY][S2]   its transpose      (backward analysis along y)
+ *   ex  [2R][2P1]  analysis along x, real-embedded complex (rows (ro,r), cols (x,ri))
+ *   fx  [2S1][2R]  synthesis along x, real-embedded complex (rows (x,ro), cols (ri,r))
+ *   exb [2R][2S1]  conj(fx)^T embedded (backward analysis along x)
+ *   fxb [2P1][2R]  conj(ex)^T embedded (backward synthesis along x)
+ * Intermediate layouts
+ *   T  [B][P1][2][NY][C]   y-transformed rows (planar re/im)
+ *   Xh [R][NY][2][B][C]    spectrum, mode-major, planar re/im   (x-hat, o-hat, g-hat alike)
+ *   Z  [B][S1][2][NY][C]   x-synthesised rows
+ */
+#ifndef FNM_B200_H
+#define FNM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* fnm_stream_t;                 /* cudaStream_t */
+
+enum {
+    FNM_OK = 0,
+    FNM_EINVAL = 1,                         /* bad argument / unsupported shape */
+    FNM_ECUDA = 2,                          /* CUDA runtime error at launch */
+    FNM_ENOTSUP = 3,                        /* valid request this build cannot serve */
+    FNM_EWORKSPACE = 4                      /* workspace too small */
+};
+
+/* compute mode of the GEMM-shaped stages */
+enum {
+    FNM_MODE_FP32 = 0,                      /* fp32-parity mode (SIMT FMA / 3xTF32 split on tensor cores) */
+    FNM_MODE_TF32 = 1                       /* single-pass TF32 tensor cores, looser stated tolerance */
+};
+
+typedef struct fnm_plan {
+    int32_t B;                              /* batch (samples on this rank) */
+    int32_t P1, P2;                         /* input grid  (P1 = 1 for 1-D) */
+    int32_t S1, S2;                         /* output grid (= input grid unless the resolution changes) */
+    int32_t R, NY;                          /* retained weight rows / columns */
+    int32_t Ci, Co;                         /* channels in / out */
+    int32_t rows_per_w;                     /* weight rows held by ONE weight tensor: m1 for
+                                               SpectralConv2d (weights1|weights2), R otherwise */
+    int32_t mode;                           /* FNM_MODE_* */
+    int32_t reserved;
+    const float *ay, *ayT, *by, *byT, *ex, *fx, *exb, *fxb;
+} fnm_plan;
+
+const char* fnm_version(void);
+const char* fnm_last_error(void);
+/* 1 when the library was built with the tcgen05/TMA kernels (sm_100a) */
+int fnm_has_tcgen05(void);
+
+/* ---- fused Fourier layer: replaces `x = w(x) + speconv(x)` (+ the activation of the PREVIOUS
+ *      layer applied on load), models/func_to_func2d.py:89-95, func_to_func1d.py:85-91,
+ *      func_to_vec2d.py:92-94, vec_to_func2d.py:92-95, vec_to_vec2d.py:99-101 and 1-D twins; i.e.
+ *      SpectralConv{1,2}d.forward (shared.py:193-216, 315-341) + nn.Conv{1,2}d(C,C,1) + bias, with
+ *      F.gelu (shared.py:13-14) folded into the consumer's load.
+ *        z[b,x,y,o] = sum_i wc[o,i] f(xin[b,x,y,i]) + bc[o] + SpectralConv(f(xin))[b,x,y,o]
+ *      f = GELU(erf) if act_in else identity.  wc == NULL drops the pointwise branch (bare
+ *      SpectralConv*).  xh_save [R][NY][2][B][Ci] receives the input spectrum for backward.      */
+size_t fnm_fourier_layer_workspace_bytes(const fnm_plan* plan);
+int fnm_fourier_layer_fwd(const fnm_plan* plan, const float* xin, int act_in,
+                          const float* w0, const float* w1,          /* complex (Ci,Co,rows_per_w,NY) */
+                          const float* wc, const float* bc,          /* (Co,Ci), (Co) or NULL */
+                          float* z_out, float* xh_save,
+                          void* workspace, size_t workspace_bytes, fnm_stream_t stream);
+/* backward of the above (autograd of the same reference lines).  g_z = dL/dz.  Outputs:
+ *   g_in = dL/d xin (already multiplied by GELU'(xin) when act_in), dw0/dw1 complex grads in the
+ *   reference layout, dwc (Co,Ci), dbc (Co).  Any of g_in / dw0 / dwc may be NULL to skip it.      */
+int fnm_fourier_layer_bwd(const fnm_plan* plan, const float* g_z, const float* xin, int act_in,
+                          const float* w0, const float* w1, const float* wc, const float* xh_save,
+                          float* g_in, float* dw0, float* dw1, float* dwc, float* dbc,
+                          void* workspace, size_t workspace_bytes, fnm_stream_t stream);
+
+/* ---- F2V: LinearFunctionals{1,2}d.forward (shared.py:239-254, 365-383).
+ *      out[b,o] = sum_{i,r,l} cc[r,l] Re( xh[b,i,r,l] W[i,o,r,l] ),  xh = truncated DFT of f(xin)
+ *      (tables carry the 1/(P1 P2) of norm="forward").  cc [R][NY] holds the 2/1/0 weights of
+ *      shared.py:254,380-381.                                                                     */
+size_t fnm_lfunc_workspace_bytes(const fnm_plan* plan);
+int fnm_lfunc_fwd(const fnm_plan* plan, const float* xin, int act_in, const float* w, const float* cc,
+                  float* out, float* xh_save, void* workspace, size_t workspace_bytes, fnm_stream_t stream);
+int fnm_lfunc_bwd(const fnm_plan* plan, const float* g_out, const float* xin, int act_in,
+                  const float* w, const float* cc, const float* xh_save,
+                  float* g_in, float* dw, void* workspace, size_t workspace_bytes, fnm_stream_t stream);
+
+/* ---- V2F: LinearDecoder{1,2}d.forward (shared.py:276-289, 406-419).
+ *      y[b,x,y,o] = irfft2( zero-pad( sum_i v[b,i] W[i,o,r,l] ), s )   (tables carry 1/(S1 S2))     */
+size_t fnm_ldec_workspace_bytes(const fnm_plan* plan);
+int fnm_ldec_fwd(const fnm_plan* plan, const float* v, const float* w, float* y_out,
+                 void* workspace, size_t workspace_bytes, fnm_stream_t stream);
+int fnm_ldec_bwd(const fnm_plan* plan, const float* g_y, const float* v, const float* w,
+                 float* g_v, float* dw, void* workspace, size_t workspace_bytes, fnm_stream_t stream);
+
+/* ---- stand-alone activation for a trunk that ENDS with GELU (func_to_vec2d.py:94):
+ *      y = GELU(z);  g_z = g_y * GELU'(z)   (shared.py:13-14 -> F.gelu, exact erf)                */
+int fnm_gelu_fwd(const float* z, float* y, int64_t n, fnm_stream_t stream);
+int fnm_gelu_bwd(const float* g_y, const float* z, float* g_z, int64_t n, fnm_stream_t stream);
+
+/* ---- complex-aware Adam, util/Adam.py:25-51 (`adam()`), one fused multi-tensor launch per <=
+ *      FNM_ADAM_MAX_TENSORS tensors.  Host arrays of n device pointers.  numel[] counts FLOATS
+ *      (2 per complex element); is_complex[t] != 0 selects the shared |g|^2 second moment
+ *      (Adam.py:40).  vmax may be NULL unless amsgrad.  step is the 1-based step count t; if
+ *      step_dev != NULL the kernel reads t from that device int32 instead (CUDA-graph replay).     */
+#define FNM_ADAM_MAX_TENSORS 48
+int fnm_adam_multi_tensor(int n, float* const* p, const float* const* g, float* const* m, float* const* v,
+                          float* const* vmax, const int64_t* numel, const uint8_t* is_complex,
+                          double lr, double beta1, double beta2, double eps, double weight_decay,
+                          int amsgrad, int step, const int32_t* step_dev, fnm_stream_t stream);
+/* *counter += 1 on the stream (device-side step count for graph replay) */
+int fnm_counter_inc(int32_t* counter, fnm_stream_t stream);
+
+/* ---- individual stages (exported for tests, profiling and composition) ------------------------- */
+/* T[row][l'][c] = sum_y tab[l'][y] f(x[row][y][c]);  rows = B*P1, tab [LY][P2]  (rfft along y,
+ * truncated: shared.py:204,326)                                                                    */
+int fnm_ydft(const float* x, const float* tab, float* T, int64_t rows, int P2, int LY, int C, int act_in,
+             int mode, fnm_stream_t stream);
+/* Xh[r][l][ro][b][c] = sum_{x,ri} ex[(ro,r)][(x,ri)] T[b][x][ri][l][c]   (C2C along x, truncated)   */
+int fnm_xdft(const float* T, const float* ex, float* Xh, int B, int P1, int R, int NY, int C, fnm_stream_t stream);
+/* Z[b][x][ro][l][c] = sum_{ri,r} fx[(x,ro)][(ri,r)] Oh[r][l][ri][b][c]   (inverse C2C along x)       */
+int fnm_xsyn(const float* Oh, const float* fx, float* Z, int B, int S1, int R, int NY, int C, fnm_stream_t stream);
+/* compl_mul (shared.py:48-53): Oh[m][.][b][o] = sum_i Xh[m][.][b][i] W[i][o][m]  (complex)           */
+int fnm_mix_fwd(const float* Xh, const float* w0, const float* w1, int rows_per_w, float* Oh,
+                int B, int R, int NY, int Ci, int Co, fnm_stream_t stream);
+/* Gxh[m][.][b][i] = sum_o Gh[m][.][b][o] conj(W[i][o][m]) */
+int fnm_mix_bwd_x(const float* Gh, const float* w0, const float* w1, int rows_per_w, float* Gxh,
+                  int B, int R, int NY, int Ci, int Co, fnm_stream_t stream);
+/* dW[i][o][m] = sum_b conj(Xh[m][.][b][i]) Gh[m][.][b][o]  (written in the reference layout)          */
+int fnm_mix_bwd_w(const float* Xh, const float* Gh, float* dw0, float* dw1, int rows_per_w,
+                  int B, int R, int NY, int Ci, int Co, fnm_stream_t stream);
+/* fused pointwise + y-synthesis + epilogue (irfft along y fused with the 1x1 conv, bias, and the
+ * GELU' of the backward pass):
+ *   out[row][y][n] = ( sum_k f(x[row][y][k]) Wk[k][n] + sum_l' by[y][l'] Z[row][l'][n] + bias[n] )
+ *                    * ( mul_gelu_grad_of ? GELU'(mul_gelu_grad_of[row][y][n]) : 1 )
+ *   Wk[k][n] = wc[n][k] (wc_is_kn == 0: forward, wc is (Co,Ci)) or wc[k][n] (wc_is_kn != 0: backward).
+ *   x == NULL (or K == 0) drops the pointwise term; bias may be NULL.                               */
+int fnm_pointwise_ysyn(const float* x, int act_in, const float* wc, int wc_is_kn, const float* bias,
+                       const float* Z, const float* by, const float* mul_gelu_grad_of, float* out,
+                       int64_t rows, int S2, int LY, int K, int N, int mode, fnm_stream_t stream);
+/* dwc[o][i] = sum_pos g[pos][o] f(x[pos][i]);  dbc[o] = sum_pos g[pos][o]   (conv weight/bias grads) */
+size_t fnm_conv_wgrad_workspace_bytes(int64_t npos, int Ci, int Co);
+int fnm_conv_wgrad(const float* g, const float* x, int act_in, float* dwc, float* dbc, int64_t npos,
+                   int Ci, int Co, void* workspace, size_t workspace_bytes, int mode, fnm_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FNM_B200_H */

@@ -1,0 +1,295 @@
+"""GPU parity tests: the CUDA path (through the C ABI, via the drop-in nn.Modules) against
+ (a) the golden fixtures produced by the unmodified reference, and
+ (b) the CPU oracle on seeded inputs at sizes the oracle finishes in seconds.
+Tolerance (north star): rel-L2 <= 1e-5 for fp32 outputs, gradients and parameters."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import fnm_oracle as O
+from tests.helpers import TOL_FP32, group, load_npz, rel_l2, t
+
+pytestmark = pytest.mark.gpu
+
+import fnm_b200                                    # noqa: E402
+from fnm_b200 import shared as S                   # noqa: E402
+
+DEV = "cuda"
+BLOCKS = load_npz("blocks.npz")
+
+
+def _s(g, n):
+    s = g["s"]
+    if s[0] < 0:
+        return None
+    return int(s[0]) if n == 1 else tuple(int(v) for v in s)
+
+
+def _load(mod, g):
+    with torch.no_grad():
+        for n, p in mod.named_parameters():
+            p.copy_(torch.from_numpy(g[n]))
+    return mod.to(DEV)
+
+
+def _check_block(mod, g, fwd_kwargs):
+    x = t(g["x"]).to(DEV).requires_grad_(True)
+    y = mod(x, **fwd_kwargs)
+    assert tuple(y.shape) == g["y"].shape
+    assert rel_l2(y, g["y"]) < TOL_FP32
+    y.backward(t(g["g"]).to(DEV))
+    assert rel_l2(x.grad, g["dx"]) < TOL_FP32
+    for n, p in mod.named_parameters():
+        assert rel_l2(p.grad, g["d" + n]) < TOL_FP32, n
+
+
+# ------------------------------------------------------------ golden fixtures: blocks ------
+@pytest.mark.parametrize("tag", ["sc2_odd", "sc2_nyq", "sc2_rect", "sc2_down", "sc2_up", "sc2_cut"])
+def test_golden_spectral_conv2d(tag):
+    g = group(BLOCKS, tag)
+    ci, co, m1, m2 = g["weights1"].shape
+    _check_block(_load(S.SpectralConv2d(ci, co, m1, m2), g), g, {"s": _s(g, 2)})
+
+
+@pytest.mark.parametrize("tag", ["sc1_even", "sc1_odd", "sc1_nyq", "sc1_down", "sc1_up"])
+def test_golden_spectral_conv1d(tag):
+    g = group(BLOCKS, tag)
+    ci, co, m = g["weights1"].shape
+    _check_block(_load(S.SpectralConv1d(ci, co, m), g), g, {"s": _s(g, 1)})
+
+
+@pytest.mark.parametrize("tag", ["lf2", "lf2_odd", "lf2_pad"])
+def test_golden_linear_functionals2d(tag):
+    g = group(BLOCKS, tag)
+    ci, co, r, c = g["weights"].shape
+    mod = _load(S.LinearFunctionals2d(ci, co, r // 2, c - 1), g)
+    _check_block(mod, g, {})
+    assert torch.all(mod.weights.grad[:, :, r // 2:, 0] == 0)        # dead weights: exactly zero grad
+
+
+@pytest.mark.parametrize("tag", ["lf1", "lf1_odd", "lf1_pad"])
+def test_golden_linear_functionals1d(tag):
+    g = group(BLOCKS, tag)
+    ci, co, c = g["weights"].shape
+    _check_block(_load(S.LinearFunctionals1d(ci, co, c - 1), g), g, {})
+
+
+@pytest.mark.parametrize("tag", ["ld2", "ld2_odd", "ld2_cut", "ld2_cut_odd"])
+def test_golden_linear_decoder2d(tag):
+    g = group(BLOCKS, tag)
+    ci, co, r, c = g["weights"].shape
+    _check_block(_load(S.LinearDecoder2d(ci, co, r // 2, c - 1), g), g, {"s": _s(g, 2)})
+
+
+@pytest.mark.parametrize("tag", ["ld1", "ld1_odd", "ld1_cut"])
+def test_golden_linear_decoder1d(tag):
+    g = group(BLOCKS, tag)
+    ci, co, c = g["weights"].shape
+    _check_block(_load(S.LinearDecoder1d(ci, co, c - 1), g), g, {"s": _s(g, 1)})
+
+
+# ------------------------------------------------------------ golden fixtures: models ------
+MODELS = {
+    "fno2d": lambda: fnm_b200.FNO2d(3, 3, 8, n_layers=3, width_final=16),
+    "fno2d_res": lambda: fnm_b200.FNO2d(3, 3, 8, s_outputspace=(8, 8), n_layers=2, width_final=16, d_in=2, d_out=2),
+    "fno1d": lambda: fnm_b200.FNO1d(5, 8, n_layers=3, width_final=16),
+    "fnf2d": lambda: fnm_b200.FNF2d(3, 3, 8, width_final=16, d_in=2, d_out=2, n_layers=3),
+    "fnf1d": lambda: fnm_b200.FNF1d(5, 8, width_final=16, d_out=3, n_layers=3),
+    "fnd2d": lambda: fnm_b200.FND2d(5, (16, 16), modes1=3, modes2=3, width=8, width_initial=16, width_final=16,
+                                    n_layers=3),
+    "fnd1d": lambda: fnm_b200.FND1d(5, 32, modes1=5, width=8, width_initial=16, width_final=16, n_layers=3),
+    "fnn2d": lambda: fnm_b200.FNN2d(5, 3, s_latentspace=(16, 16), modes1=3, modes2=3, width=8, width_initial=16,
+                                    width_final=16, n_layers=4),
+    "fnn1d": lambda: fnm_b200.FNN1d(5, 3, s_latentspace=32, modes1=5, width=8, width_initial=16, width_final=16,
+                                    n_layers=3),
+}
+
+
+@pytest.mark.parametrize("name", sorted(MODELS))
+def test_golden_model_train_steps(name):
+    """Reference weights in, then 3 x (forward, rel-L2 sum loss, backward, fused Adam): output, loss,
+    every gradient and every parameter after 3 steps must match the reference run."""
+    d = load_npz(f"model_{name}.npz")
+    model = MODELS[name]()
+    missing = model.load_state_dict({k: torch.from_numpy(v) for k, v in group(d, "w0").items()}, strict=True)
+    assert not missing.missing_keys and not missing.unexpected_keys
+    model = model.to(DEV)
+    opt = fnm_b200.Adam(model.parameters(), lr=1e-3, weight_decay=1e-4)
+    x, y = t(d["x"]).to(DEV), t(d["y"]).to(DEV)
+    for step in range(3):
+        opt.zero_grad()
+        out = model(x)
+        loss = fnm_b200.parallel.rel_l2_sum(out, y)
+        loss.backward()
+        if step == 0:
+            assert tuple(out.shape) == d["out0"].shape
+            assert rel_l2(out, d["out0"]) < TOL_FP32
+            assert rel_l2(loss, d["loss0"]) < TOL_FP32
+            for k, p in model.named_parameters():
+                got = p.grad if p.grad is not None else torch.zeros_like(p)
+                assert rel_l2(got, d[f"g0.{k}"]) < TOL_FP32, k
+        opt.step()
+    assert rel_l2(loss, d["loss_last"]) < TOL_FP32
+    for k, v in model.state_dict().items():
+        assert rel_l2(v, d[f"w3.{k}"]) < TOL_FP32, k
+
+
+@pytest.mark.parametrize("tag,kw", [("plain", dict(lr=1e-3)), ("wd", dict(lr=2e-3, weight_decay=1e-2)),
+                                    ("ams", dict(lr=1e-3, weight_decay=1e-4, amsgrad=True))])
+def test_golden_adam(tag, kw):
+    d = group(load_npz("adam.npz"), tag)
+    use_c = tag != "ams"
+    pc = torch.nn.Parameter(t(d["pc0"]).to(DEV))
+    pr = torch.nn.Parameter(t(d["pr0"]).to(DEV))
+    opt = fnm_b200.Adam([pc, pr] if use_c else [pr], **kw)
+    for step in range(4):
+        pc.grad = t(d[f"gc{step}"]).to(DEV) if use_c else None
+        pr.grad = t(d[f"gr{step}"]).to(DEV)
+        opt.step()
+        if use_c:
+            assert rel_l2(pc, d[f"pc{step + 1}"]) < 1e-6
+        assert rel_l2(pr, d[f"pr{step + 1}"]) < 1e-6
+    if use_c:
+        assert rel_l2(opt.state[pc]["exp_avg"], d["mc"]) < 1e-6
+        assert rel_l2(opt.state[pc]["exp_avg_sq"], d["vc"]) < 1e-6
+
+
+def test_adam_amsgrad_rejects_complex_like_reference():
+    pc = torch.nn.Parameter(torch.ones(2, 2, dtype=torch.cfloat, device=DEV))
+    pc.grad = torch.ones_like(pc)
+    with pytest.raises(RuntimeError):
+        fnm_b200.Adam([pc], amsgrad=True).step()
+
+
+def test_adam_differs_from_torch_adam():
+    """The reference rule (|g|^2 shared moment) is NOT torch.optim.Adam's (separate re/im moments)."""
+    torch.manual_seed(0)
+    p0 = torch.randn(64, dtype=torch.cfloat, device=DEV)
+    a, b = torch.nn.Parameter(p0.clone()), torch.nn.Parameter(p0.clone())
+    oa, ob = fnm_b200.Adam([a], lr=1e-2), torch.optim.Adam([b], lr=1e-2)
+    for i in range(3):
+        g = torch.randn(64, dtype=torch.cfloat, device=DEV)
+        a.grad, b.grad = g.clone(), g.clone()
+        oa.step()
+        ob.step()
+    assert rel_l2(a, b) > 1e-4
+
+
+# ------------------------------------------------------------ oracle at BASELINE-like sizes -
+def _oracle_layer(x, w1, w2, wc, bc, act):
+    y = O.pointwise_conv(x, wc, bc) + (O.spectral_conv1d(x, w1) if w2 is None else O.spectral_conv2d(x, w1, w2))
+    return torch.nn.functional.gelu(y) if act else y
+
+
+@pytest.mark.parametrize("shape", [
+    dict(B=3, C=32, P=(72, 72), m=(12, 12)),          # config 1 layer
+    dict(B=2, C=32, P=(62, 57), m=(12, 12)),          # odd / non-multiple-of-4 grid (config 3 flavour)
+    dict(B=2, C=64, P=(36, 40), m=(16, 16)),          # config 4 width
+    dict(B=2, C=20, P=(24, 20), m=(5, 7)),            # channel count that is no multiple of 16
+    dict(B=4, C=64, P=(1152,), m=(16,)),              # config 2 layer (1-D)
+    dict(B=2, C=24, P=(45,), m=(9,)),                 # odd 1-D grid
+])
+def test_fused_layers_vs_oracle(shape):
+    """Two chained fused layers (GELU between them is applied on load) + trailing GELU, forward and
+    all gradients, against the CPU oracle."""
+    torch.manual_seed(5)
+    B, C, P, m = shape["B"], shape["C"], shape["P"], shape["m"]
+    one_d = len(P) == 1
+    Sc = (lambda: S.SpectralConv1d(C, C, m[0])) if one_d else (lambda: S.SpectralConv2d(C, C, m[0], m[1]))
+    Conv = torch.nn.Conv1d if one_d else torch.nn.Conv2d
+    scs = torch.nn.ModuleList([Sc(), Sc()])
+    ws = torch.nn.ModuleList([Conv(C, C, 1), Conv(C, C, 1)])
+    with torch.no_grad():
+        for sc in scs:                   # O(1) spectral branch so both branches matter
+            for p in sc.parameters():
+                p.mul_(C)
+    x_cpu = torch.randn(B, C, *P)
+    g_cpu = torch.randn(B, C, *P)
+    # oracle (CPU fp32)
+    xo = x_cpu.clone().requires_grad_(True)
+    po = {f"{k}": v.detach().clone().requires_grad_(True) for k, v in
+          list(scs.named_parameters(prefix="sc")) + list(ws.named_parameters(prefix="w"))}
+    h = xo
+    for i in range(2):
+        w2 = None if one_d else po[f"sc.{i}.weights2"]
+        h = _oracle_layer(h, po[f"sc.{i}.weights1"], w2, po[f"w.{i}.weight"], po[f"w.{i}.bias"], True)
+    h.backward(g_cpu)
+    # CUDA path
+    from fnm_b200.models._trunk import Pending, run_layers
+    scs, ws = scs.to(DEV), ws.to(DEV)
+    xg = x_cpu.to(DEV).requires_grad_(True)
+    xcl = xg.permute(0, 2, 1).unsqueeze(1) if one_d else xg.permute(0, 2, 3, 1)
+    state = run_layers(Pending(xcl), scs, ws, "gelu", [True, True], one_d)
+    out = state.value()
+    out = out.squeeze(1).permute(0, 2, 1) if one_d else out.permute(0, 3, 1, 2)
+    assert rel_l2(out, h) < TOL_FP32
+    out.backward(g_cpu.to(DEV))
+    assert rel_l2(xg.grad, xo.grad) < TOL_FP32
+    got = dict(list(scs.named_parameters(prefix="sc")) + list(ws.named_parameters(prefix="w")))
+    for k, v in po.items():
+        assert rel_l2(got[k].grad, v.grad) < TOL_FP32, k
+
+
+@pytest.mark.parametrize("act", ["gelu", "relu", "tanh"])
+def test_full_model_config1_shape_vs_oracle(act):
+    """FNO2d at the config-1 architecture (64x64, modes 12, width 32, 4 layers), batch 4."""
+    torch.manual_seed(0)
+    model = fnm_b200.FNO2d(12, 12, 32, act=act)
+    p = {k: v.detach().clone().requires_grad_(True) for k, v in model.state_dict().items()}
+    x = torch.randn(4, 1, 64, 64, generator=torch.Generator().manual_seed(1234))
+    y = torch.randn(4, 1, 64, 64, generator=torch.Generator().manual_seed(1235))
+    ref = O.f2f_forward(p, x, act=act)
+    O.rel_l2_sum(ref, y).backward()
+    model = model.to(DEV)
+    out = model(x.to(DEV))
+    fnm_b200.parallel.rel_l2_sum(out, y.to(DEV)).backward()
+    assert rel_l2(out, ref) < TOL_FP32
+    for k, q in model.named_parameters():
+        assert rel_l2(q.grad, p[k].grad) < TOL_FP32, k
+
+
+def test_extra_leading_dims_like_reference_einsum():
+    """The `...` of compl_mul (shared.py:53): extra dims between channels and space act as batch."""
+    torch.manual_seed(1)
+    sc = S.SpectralConv1d(3, 4, 5)
+    x = torch.randn(2, 3, 6, 16)
+    ref = O.spectral_conv1d(x, sc.weights1.detach())
+    got = sc.to(DEV)(x.to(DEV))
+    assert tuple(got.shape) == tuple(ref.shape)
+    assert rel_l2(got, ref) < TOL_FP32
+    ld = S.LinearDecoder1d(3, 4, 5)
+    v = torch.randn(2, 3, 7)
+    ref = O.linear_decoder1d(v, ld.weights.detach(), 12)
+    got = ld.to(DEV)(v.to(DEV), 12)
+    assert tuple(got.shape) == tuple(ref.shape)
+    assert rel_l2(got, ref) < TOL_FP32
+    lf = S.LinearFunctionals1d(3, 4, 5)
+    xx = torch.randn(2, 3, 6, 16)
+    ref = O.linear_functionals1d(xx, lf.weights.detach())
+    got = lf.to(DEV)(xx.to(DEV))
+    assert tuple(got.shape) == tuple(ref.shape)
+    assert rel_l2(got, ref) < TOL_FP32
+
+
+def test_size_independent_properties_at_full_size():
+    """At the config-5 layer size (C=128, 288x288, modes 32; batch 2): linearity of the spectral
+    branch and the adjoint identity <L x, g> = <x, L^T g> that ties forward to backward."""
+    torch.manual_seed(2)
+    C = 128
+    sc = S.SpectralConv2d(C, C, 32, 32).to(DEV)
+    with torch.no_grad():
+        sc.weights1.mul_(C)
+        sc.weights2.mul_(C)
+    x1 = torch.randn(2, C, 288, 288, device=DEV)
+    x2 = torch.randn(2, C, 288, 288, device=DEV)
+    with torch.no_grad():
+        lhs = sc(2.0 * x1 - 3.0 * x2)
+        rhs = 2.0 * sc(x1) - 3.0 * sc(x2)
+    assert rel_l2(lhs, rhs) < TOL_FP32
+    xa = x1.clone().requires_grad_(True)
+    y = sc(xa)
+    g = torch.randn_like(y)
+    y.backward(g)
+    a = (y.detach().double() * g.double()).sum().item()
+    b = (xa.grad.double() * x1.double()).sum().item()
+    assert abs(a - b) <= 1e-5 * max(abs(a), abs(b), 1.0)
