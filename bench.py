@@ -1,0 +1,382 @@
+#!/usr/bin/env python
+"""Benchmark of the Fourier-layer hot path: FNO train samples/sec (fwd + bwd + Adam).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg5] [--impl reference]
+
+One "step" = zero_grad -> forward -> rel-L2 sum loss -> backward -> (SUM all-reduce, N > 1) -> Adam on
+one synthetic batch (reference loop: advection_diffusion/func_to_func/train_fno.py:187-197).
+Default workload = BASELINE.json configs[4] ("large FNO2d 256x256, modes 32, width 128"), the
+config the 1/2/4/8-GPU metric is quoted on, at its per-GPU batch of 32 (global 256 on 8 GPUs, weak
+scaling).  Other BASELINE configs: --workload cfg1 | cfg2 | cfg3 | cfg4.
+
+Prints ONE JSON line (rank 0).  `value` is device-timed with inputs resident in HBM; `e2e` includes the
+pinned-host -> device copy of each step's batch and the device -> host read of the loss.
+`--impl reference` times the reference algorithm's CPU path (the oracle port: same torch.fft /
+einsum / conv calls as the reference, on all host cores) on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+WORKLOADS = {
+    # name: (description, family, ctor kwargs, per-GPU batch, x shape (no batch), CPU sample batch)
+    "cfg1": ("FNO2d 64x64 modes12 width32 L4 batch20", "fno2d",
+             dict(modes1=12, modes2=12, width=32), 20, (1, 64, 64), 20),
+    "cfg2": ("FNO1d 1024 modes16 width64 L4 batch64", "fno1d",
+             dict(modes1=16, width=64), 64, (1, 1024), 64),
+    "cfg3": ("FNF2d 221x51 modes12 width32 batch128", "fnf2d",
+             dict(modes1=12, modes2=12, width=32, d_in=2, d_out=2), 128, (2, 221, 51), 16),
+    "cfg4": ("FND2d 20->128x128 modes16 width64 batch20", "fnd2d",
+             dict(d_in=20, s_outputspace=(128, 128), modes1=16, modes2=16, width=64), 20, (20,), 4),
+    "cfg5": ("FNO2d 256x256 modes32 width128 L4 batch32/GPU (global 256 on 8 GPUs)", "fno2d",
+             dict(modes1=32, modes2=32, width=128), 32, (1, 256, 256), 1),
+}
+
+
+def build_model(family, kw):
+    import fnm_b200
+    ctor = {"fno2d": fnm_b200.FNO2d, "fno1d": fnm_b200.FNO1d, "fnf2d": fnm_b200.FNF2d, "fnd2d": fnm_b200.FND2d}[family]
+    return ctor(**kw)
+
+
+def oracle_forward(family, kw):
+    from oracle import fnm_oracle as O
+    if family in ("fno2d", "fno1d"):
+        return lambda p, x: O.f2f_forward(p, x)
+    if family == "fnf2d":
+        return lambda p, x: O.f2v_forward(p, x)
+    return lambda p, x: O.v2f_forward(p, x, kw["s_outputspace"])
+
+
+def synth(shape, seed):
+    return torch.randn(*shape, generator=torch.Generator().manual_seed(seed))
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [c.strip() for c in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return d.get("hbm_gbs", 6650.0), "MEASURED_PEAKS.json hbm_gbs"
+    return 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------
+def run_reference(args, rank):
+    """CPU arm: the oracle port of the reference algorithm on the host cores, bounded sample."""
+    if rank != 0:
+        return
+    from oracle import fnm_oracle as O
+    desc, family, kw, batch, xshape, cpu_batch = WORKLOADS[args.workload]
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(0)
+    model = build_model(family, kw)
+    p = {k: v.detach().clone().requires_grad_(True) for k, v in model.state_dict().items()}
+    del model
+    fwd = oracle_forward(family, kw)
+    x = synth((cpu_batch,) + xshape, 1234)
+    with torch.no_grad():
+        yshape = fwd(p, x).shape
+    y = synth(tuple(yshape), 1235)
+    state = O.AdamState()
+    for _ in range(args.warmup):
+        O.train_step(fwd, p, x, y, state, lr=1e-3, weight_decay=1e-4)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        O.train_step(fwd, p, x, y, state, lr=1e-3, weight_decay=1e-4)
+    dt = time.perf_counter() - t0
+    value = cpu_batch * args.steps / dt
+    sample = f"batch {cpu_batch} of the workload's {batch} per step, {args.steps} steps after {args.warmup} warm-up"
+    print(json.dumps({
+        "impl": "reference", "metric": "train_samples_per_sec", "value": value, "unit": "samples/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {desc}", "device": "cpu", "threads": cores},
+        "cpu_baseline": {"value": value, "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def cpu_baseline(workload, budget_s=25.0):
+    """Bounded CPU sample of the same step with the oracle port (reported baseline, not a target)."""
+    from oracle import fnm_oracle as O
+    desc, family, kw, batch, xshape, cpu_batch = WORKLOADS[workload]
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(0)
+    model = build_model(family, kw)
+    p = {k: v.detach().clone().requires_grad_(True) for k, v in model.state_dict().items()}
+    del model
+    fwd = oracle_forward(family, kw)
+    x = synth((cpu_batch,) + xshape, 1234)
+    with torch.no_grad():
+        y = synth(tuple(fwd(p, x).shape), 1235)
+    state = O.AdamState()
+    O.train_step(fwd, p, x, y, state, lr=1e-3, weight_decay=1e-4)           # warm-up
+    n, t0 = 0, time.perf_counter()
+    while True:
+        O.train_step(fwd, p, x, y, state, lr=1e-3, weight_decay=1e-4)
+        n += 1
+        dt = time.perf_counter() - t0
+        if dt > budget_s or n >= 20 or (n >= 2 and dt * (n + 1) / n > budget_s):
+            break
+    return {"value": cpu_batch * n / dt, "unit": "samples/s", "cores": cores, "kind": "port",
+            "sample": f"batch {cpu_batch} of {batch}, {n} steps after 1 warm-up, {dt:.1f} s"}
+
+
+# ------------------------------------------------------------------------------------------------
+def kernel_algorithmic_bytes(name, wl, model):
+    """ALGORITHMIC bytes one train step moves through kernel `name`:
+    A = 4*B*C*P1*P2 bytes is one fp32 activation of the trunk."""
+    A, L, lyf = wl["A"], wl["layers"], wl["ly_frac"]
+    return {
+        "pointwise_ysyn": L * (2 * A + 3 * A),          # fwd: read x, write z; bwd: read g_z, z_prev, write g_in
+        "ydft": 2 * L * A * (1 + lyf),                  # fwd + bwd analysis: read A, write the LY/P2 partial transform
+        "conv_wgrad": L * 2 * A,                        # read g_z and x
+        "adam": 28 * wl["n_real_params"],               # read p,g,m,v; write p,m,v
+        "xdft": 2 * L * A * lyf, "xsyn": 2 * L * A * lyf,
+        "mix_fwd": L * wl["w_bytes"], "mix_bwd_x": L * wl["w_bytes"], "mix_bwd_w": L * wl["w_bytes"],
+    }.get(name)
+
+
+def run_ours(args, rank, world):
+    import torch.distributed as dist
+    import fnm_b200
+    from fnm_b200 import _lib
+    from fnm_b200.parallel import FlatGradients, rel_l2_sum
+
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    desc, family, kw, batch, xshape, _ = WORKLOADS[args.workload]
+    torch.manual_seed(0)
+    model = build_model(family, kw).to(dev)
+    fnm_b200.parallel.broadcast_parameters(model)
+    opt = fnm_b200.Adam(model.parameters(), lr=1e-3, weight_decay=1e-4)
+    grads = FlatGradients(model.parameters())
+
+    x_host = synth((batch,) + xshape, 1234 + rank).pin_memory()
+    x = x_host.to(dev)
+    with torch.no_grad():
+        yshape = tuple(model(x).shape)
+    y_host = synth(yshape, 1235 + rank).pin_memory()
+    y = y_host.to(dev)
+
+    def step(xd, yd):
+        grads.zero_()
+        out = model(xd)
+        loss = rel_l2_sum(out, yd)
+        loss.backward()
+        grads.all_reduce()
+        opt.step()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item()
+
+    for _ in range(args.warmup):
+        step(x, y)
+    # ---- timed region: K steps, inputs resident in HBM
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step(x, y)
+    e1.record()
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    launches = _lib.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- end to end: host batch -> device, step, loss -> host, every step
+    xd, yd = torch.empty_like(x), torch.empty_like(y)
+    for _ in range(2):
+        xd.copy_(x_host, non_blocking=True); yd.copy_(y_host, non_blocking=True)
+        step(xd, yd).item()
+    barrier()
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(args.steps):
+        xd.copy_(x_host, non_blocking=True)
+        yd.copy_(y_host, non_blocking=True)
+        loss_val = step(xd, yd).item()
+    e1.record()
+    barrier()
+    ms_e2e = max_over_ranks(max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3 if world == 1 else 0.0))
+
+    # ---- per-kernel device time of the same step (CUDA events around every launch, separate pass)
+    prof = None
+    if rank == 0:
+        nprof = 2
+        _lib.profile_begin()
+        for _ in range(nprof):
+            step(x, y)
+        torch.cuda.synchronize()
+        prof = {k: (c / nprof, t / nprof) for k, (c, t) in _lib.profile_end().items()}
+    barrier()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel
+    trunk = [m for m in model.modules() if isinstance(m, (fnm_b200.SpectralConv2d, fnm_b200.SpectralConv1d))]
+    C = trunk[0].in_channels
+    if family == "fno1d":
+        P1, P2 = 1, xshape[-1] + xshape[-1] // 8
+        ny, wb = trunk[0].modes1, trunk[0].weights1.numel() * 8
+    elif family == "fnd2d":
+        P1, P2 = (s + s // 8 for s in kw["s_outputspace"])
+        ny, wb = trunk[0].modes2, 2 * trunk[0].weights1.numel() * 8
+    else:
+        P1, P2 = xshape[-2] + xshape[-2] // 8, xshape[-1] + xshape[-1] // 8
+        ny, wb = trunk[0].modes2, 2 * trunk[0].weights1.numel() * 8
+    n_real = sum(p.numel() * (2 if p.is_complex() else 1) for p in model.parameters())
+    wl = {"A": 4 * batch * C * P1 * P2, "layers": len(trunk), "ly_frac": 2 * ny / P2, "n_real_params": n_real,
+          "w_bytes": wb}
+    peak, peak_src = measured_peaks()
+    kernels = []
+    total_ms = sum(t for _, t in prof.values()) or 1.0
+    for name, (cnt, t) in sorted(prof.items(), key=lambda kv: -kv[1][1]):
+        ab = kernel_algorithmic_bytes(name, wl, model)
+        kernels.append({"name": name, "launches_per_step": cnt, "ms_per_step": round(t, 4),
+                        "share": round(t / total_ms, 4),
+                        "algorithmic_GB_per_step": None if ab is None else round(ab / 1e9, 4),
+                        "GBps": None if ab is None or t <= 0 else round(ab / 1e6 / t, 1)})
+    top = kernels[0]
+    roofline = {"kernel": top["name"], "bound": "hbm", "achieved": top["GBps"], "peak": peak, "unit": "GB/s",
+                "frac": None if top["GBps"] is None else round(top["GBps"] / peak, 4), "traffic": None,
+                "peak_source": peak_src, "launches_per_step": top["launches_per_step"],
+                "ms_per_launch": round(top["ms_per_step"] / max(top["launches_per_step"], 1), 4),
+                "algorithmic_bytes_per_step": None if top["algorithmic_GB_per_step"] is None else top["algorithmic_GB_per_step"] * 1e9,
+                "trunk_5A_L_GBps": round(5 * wl["A"] * wl["layers"] / 1e6 / (ms / args.steps), 1)}
+
+    cpu = cpu_baseline(args.workload) if (world == 1 and not args.no_cpu_baseline) else None
+    samples = batch * world * args.steps
+    line = {
+        "metric": "train_samples_per_sec", "value": samples / (ms / 1e3), "unit": "samples/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {desc}", "batch_per_gpu": batch, "global_batch": batch * world,
+                   "parallelism": f"dp{world}", "compute_mode": fnm_b200.get_compute_mode(),
+                   "tcgen05": bool(_lib.lib().fnm_has_tcgen05()),
+                   "l2": ("working set %.0f MB per activation, larger than the 126 MB L2" % (wl["A"] / 1e6))
+                   if wl["A"] > 126e6 else "working set fits L2 (back-to-back steps, no flush)",
+                   "optimizer": "complex-aware Adam lr 1e-3 wd 1e-4", "loss": "relative L2, summed over the batch"},
+        "clocks": clocks,
+        "e2e": {"value": samples / (ms_e2e / 1e3), "unit": "samples/s",
+                "h2d_bytes_per_step": (x_host.numel() + y_host.numel()) * 4, "d2h_bytes_per_step": 4,
+                "ms_per_step": ms_e2e / args.steps, "last_loss": loss_val},
+        "gpu_launches": int(launches),
+        "roofline": roofline,
+        "kernels": kernels,
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg5", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if args.warmup < 3:
+        args.warmup = 3
+    if world != args.gpus and world == 1 and args.gpus > 1:
+        # launched without torchrun: re-exec under torch.distributed.run
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", "29511", os.path.abspath(__file__)] + sys.argv[1:]
+        sys.exit(subprocess.call(cmd))
+    run_ours(args, rank, world)
+
+
+if __name__ == "__main__":
+    main()

@@ -33,6 +33,9 @@ PROTOTYPES = {
     "fnm_version": (C.c_char_p, []),
     "fnm_last_error": (C.c_char_p, []),
     "fnm_has_tcgen05": (_i32, []),
+    "fnm_launch_count": (_i64, []),
+    "fnm_profile_begin": (_i32, []),
+    "fnm_profile_end": (_sz, [C.c_char_p, _sz]),
     "fnm_fourier_layer_workspace_bytes": (_sz, [_PP]),
     "fnm_fourier_layer_fwd": (_i32, [_PP, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "fnm_fourier_layer_bwd": (_i32, [_PP, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
@@ -101,3 +104,23 @@ def check(rc, what=""):
 
 def version():
     return lib().fnm_version().decode()
+
+
+def launch_count():
+    return int(lib().fnm_launch_count())
+
+
+def profile_begin():
+    check(lib().fnm_profile_begin(), "fnm_profile_begin")
+
+
+def profile_end():
+    """{kernel name: (launches, total_ms)} of everything launched since profile_begin()."""
+    buf = C.create_string_buffer(1 << 16)
+    lib().fnm_profile_end(buf, len(buf))
+    out = {}
+    for item in buf.value.decode().split(";"):
+        if item:
+            name, cnt, ms = item.rsplit(":", 2)
+            out[name] = (int(cnt), float(ms))
+    return out

@@ -145,7 +145,10 @@ int adam_launch(int n, float* const* p, const float* const* g, float* const* m, 
         a.block_start[used] = blocks;
         a.n = used; a.lr = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.wd = wd;
         a.amsgrad = amsgrad; a.step = step; a.step_dev = step_dev;
-        adam_kernel<<<blocks, ADAM_THREADS, 0, st>>>(a);
+        {
+            LaunchScope ls("adam", st);
+            adam_kernel<<<blocks, ADAM_THREADS, 0, st>>>(a);
+        }
         FNM_TRY(check_launch("adam"));
     }
     return FNM_OK;
@@ -154,7 +157,10 @@ int adam_launch(int n, float* const* p, const float* const* g, float* const* m, 
 __global__ void counter_inc_kernel(int* c) { *c += 1; }
 
 int counter_inc(int32_t* c, cudaStream_t st) {
-    counter_inc_kernel<<<1, 1, 0, st>>>(c);
+    {
+        LaunchScope ls("counter_inc", st);
+        counter_inc_kernel<<<1, 1, 0, st>>>(c);
+    }
     return check_launch("counter_inc");
 }
 
@@ -185,8 +191,11 @@ int gelu_launch(const float* g, const float* z, float* out, int64_t n, bool grad
     int64_t blocks = (n / 4 + 255) / 256;
     if (blocks > 148 * 16) blocks = 148 * 16;
     if (blocks < 1) blocks = 1;
-    if (grad) gelu_kernel<true><<<(int)blocks, 256, 0, st>>>(g, z, out, n);
-    else gelu_kernel<false><<<(int)blocks, 256, 0, st>>>(nullptr, z, out, n);
+    {
+        LaunchScope ls(grad ? "gelu_bwd" : "gelu_fwd", st);
+        if (grad) gelu_kernel<true><<<(int)blocks, 256, 0, st>>>(g, z, out, n);
+        else gelu_kernel<false><<<(int)blocks, 256, 0, st>>>(nullptr, z, out, n);
+    }
     return check_launch("gelu");
 }
 

@@ -3,6 +3,13 @@
 #include "fnm_common.cuh"
 #include "fnm_stages.cuh"
 
+#include <string.h>
+#include <atomic>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
 namespace fnm {
 
 static thread_local char g_err[512] = "";
@@ -24,6 +31,34 @@ int check_launch(const char* what) {
         return fail(FNM_ECUDA, "%s: %s", what, cudaGetErrorString(e));
     }
     return FNM_OK;
+}
+
+// ---- instrumentation ---------------------------------------------------------------------------
+static std::atomic<long long> g_launches{0};
+static std::atomic<int> g_profiling{0};
+static std::mutex g_prof_mu;
+struct ProfRec { const char* name; cudaEvent_t e0, e1; };
+static std::vector<ProfRec> g_prof;
+
+LaunchScope::LaunchScope(const char* name_, cudaStream_t st_) : name(name_), st(st_), slot(-1) {
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    if (g_profiling.load(std::memory_order_relaxed)) {
+        ProfRec r;
+        r.name = name;
+        if (cudaEventCreate(&r.e0) == cudaSuccess && cudaEventCreate(&r.e1) == cudaSuccess) {
+            cudaEventRecord(r.e0, st);
+            std::lock_guard<std::mutex> lk(g_prof_mu);
+            g_prof.push_back(r);
+            slot = (int)g_prof.size() - 1;
+        }
+    }
+}
+
+LaunchScope::~LaunchScope() {
+    if (slot >= 0) {
+        std::lock_guard<std::mutex> lk(g_prof_mu);
+        cudaEventRecord(g_prof[slot].e1, st);
+    }
 }
 
 static int check_plan(const fnm_plan* p, bool need_in, bool need_out) {
@@ -67,6 +102,45 @@ extern "C" {
 const char* fnm_version(void) { return "fnm_b200 0.1 (sm_100a)"; }
 const char* fnm_last_error(void) { return err_buf(); }
 int fnm_has_tcgen05(void) { return tc_available(); }
+
+int64_t fnm_launch_count(void) { return g_launches.load(); }
+
+int fnm_profile_begin(void) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    for (auto& r : g_prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+    g_prof.clear();
+    g_profiling.store(1);
+    return FNM_OK;
+}
+
+size_t fnm_profile_end(char* buf, size_t n) {
+    g_profiling.store(0);
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    std::map<std::string, std::pair<long long, double>> agg;
+    for (auto& r : g_prof) {
+        float ms = 0.f;
+        if (cudaEventSynchronize(r.e1) == cudaSuccess && cudaEventElapsedTime(&ms, r.e0, r.e1) == cudaSuccess) {
+            auto& a = agg[r.name];
+            a.first += 1;
+            a.second += ms;
+        }
+        cudaEventDestroy(r.e0);
+        cudaEventDestroy(r.e1);
+    }
+    g_prof.clear();
+    std::string out;
+    char line[160];
+    for (auto& kv : agg) {
+        snprintf(line, sizeof(line), "%s:%lld:%.6f;", kv.first.c_str(), kv.second.first, kv.second.second);
+        out += line;
+    }
+    if (buf && n > 0) {
+        const size_t k = out.size() < n - 1 ? out.size() : n - 1;
+        memcpy(buf, out.data(), k);
+        buf[k] = 0;
+    }
+    return out.size() + 1;
+}
 
 // ------------------------------------------------------------------------------------------------
 // individual stages

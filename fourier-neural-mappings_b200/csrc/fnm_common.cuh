@@ -14,6 +14,16 @@ char* err_buf();
 int fail(int code, const char* fmt, ...);
 int check_launch(const char* what);
 
+// Brackets one kernel launch: counts it and, while profiling is on, records a CUDA-event pair on the
+// launching stream.  Usage:  { LaunchScope ls("name", st); kernel<<<...>>>(...); }  then check_launch.
+struct LaunchScope {
+    const char* name;
+    cudaStream_t st;
+    int slot;
+    LaunchScope(const char* name_, cudaStream_t st_);
+    ~LaunchScope();
+};
+
 #define FNM_REQUIRE(cond, ...)                                   \
     do {                                                         \
         if (!(cond)) return ::fnm::fail(FNM_EINVAL, __VA_ARGS__); \

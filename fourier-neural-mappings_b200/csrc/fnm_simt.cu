@@ -131,7 +131,10 @@ static int launch_engine(const P& p, int64_t nbatch, cudaStream_t st, const char
     const int64_t blocks = nbatch * tm * tn;
     if (blocks <= 0) return FNM_OK;
     if (blocks > 0x7fffffffLL) return fail(FNM_EINVAL, "%s: grid too large (%lld blocks)", what, (long long)blocks);
-    gemm_engine<BM, BN, P><<<(unsigned)blocks, (BM / 4) * (BN / 4), 0, st>>>(p, tm, tn);
+    {
+        LaunchScope ls(what, st);
+        gemm_engine<BM, BN, P><<<(unsigned)blocks, (BM / 4) * (BN / 4), 0, st>>>(p, tm, tn);
+    }
     return check_launch(what);
 }
 
@@ -538,7 +541,10 @@ int simt_conv_wgrad(const float* g, const float* x, int act, float* dwc, float* 
     p.g = g; p.x = x; p.partial = partial; p.M = Co; p.N = Ci + 1; p.Ci = Ci; p.act = act; p.npos = npos; p.chunk = chunk;
     FNM_TRY(launch_auto(p, nsplit, st, "conv_wgrad"));
     const int count = Co * (Ci + 1);
-    conv_wgrad_reduce<<<(count + 255) / 256, 256, 0, st>>>(partial, nsplit, Co, Ci, dwc, dbc);
+    {
+        LaunchScope ls("conv_wgrad_reduce", st);
+        conv_wgrad_reduce<<<(count + 255) / 256, 256, 0, st>>>(partial, nsplit, Co, Ci, dwc, dbc);
+    }
     return check_launch("conv_wgrad_reduce");
 }
 
@@ -562,7 +568,10 @@ int simt_lfunc_contract(const float* Xh, const float* w, const float* cc, float*
     p.Xh = Xh; p.cc = cc; p.partial = partial; p.w = make_w(w, nullptr, R, NY, Co);
     p.M = B; p.N = Co; p.Ci = Ci; p.nmodes = R * NY; p.per = per;
     FNM_TRY(launch_auto(p, nsplit, st, "lfunc_contract"));
-    sum_partials<<<(B * Co + 255) / 256, 256, 0, st>>>(partial, nsplit, B * Co, out);
+    {
+        LaunchScope ls("lfunc_reduce", st);
+        sum_partials<<<(B * Co + 255) / 256, 256, 0, st>>>(partial, nsplit, B * Co, out);
+    }
     return check_launch("lfunc_reduce");
 }
 
@@ -601,7 +610,10 @@ int simt_ldec_bwd_v(const float* Gh, const float* w, float* dv, float* partial, 
     p.Gh = Gh; p.partial = partial; p.w = make_w(w, nullptr, R, NY, Co);
     p.M = B; p.N = Ci; p.Co = Co; p.nmodes = R * NY; p.per = per;
     FNM_TRY(launch_auto(p, nsplit, st, "ldec_bwd_v"));
-    sum_partials<<<(B * Ci + 255) / 256, 256, 0, st>>>(partial, nsplit, B * Ci, dv);
+    {
+        LaunchScope ls("ldec_reduce", st);
+        sum_partials<<<(B * Ci + 255) / 256, 256, 0, st>>>(partial, nsplit, B * Ci, dv);
+    }
     return check_launch("ldec_reduce");
 }
 

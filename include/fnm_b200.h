@@ -77,6 +77,15 @@ const char* fnm_last_error(void);
 /* 1 when the library was built with the tcgen05/TMA kernels (sm_100a) */
 int fnm_has_tcgen05(void);
 
+/* ---- instrumentation (used by bench.py; never on by default) --------------------------------------
+ * fnm_launch_count(): kernels launched by this library in this process so far.
+ * fnm_profile_begin(): start recording a CUDA-event pair around EVERY kernel launch (on the launching
+ *   stream).  fnm_profile_end(buf, n): synchronise the recorded events, stop recording and write
+ *   "name:launches:total_ms;..." (aggregated by kernel name) into buf; returns bytes needed.        */
+int64_t fnm_launch_count(void);
+int fnm_profile_begin(void);
+size_t fnm_profile_end(char* buf, size_t n);
+
 /* ---- fused Fourier layer: replaces `x = w(x) + speconv(x)` (+ the activation of the PREVIOUS
  *      layer applied on load), models/func_to_func2d.py:89-95, func_to_func1d.py:85-91,
  *      func_to_vec2d.py:92-94, vec_to_func2d.py:92-95, vec_to_vec2d.py:99-101 and 1-D twins; i.e.

@@ -28,6 +28,10 @@ produced by importing the unmodified reference in the build container
 function here against them.
 
 Parameters are passed as a flat ``dict`` using the reference's ``state_dict`` key names.
+
+Unlike the reference (whose spectral buffers are hard-coded complex64) the functions follow the
+dtype of their inputs, so the same code run in float64 / complex128 gives the "truth" used to
+measure the fp32 noise floor of ill-conditioned quantities (tests/helpers.py: ``assert_parity``).
 """
 import math
 
@@ -59,7 +63,7 @@ def activation(name):
 # mode bookkeeping (shared.py:61-108, 136-147)
 # --------------------------------------------------------------------------------------
 def _zeros_like_tail(a, n):
-    return torch.zeros(a.shape[:-1] + (n,), dtype=torch.cfloat, device=a.device)
+    return torch.zeros(a.shape[:-1] + (n,), dtype=a.dtype, device=a.device)
 
 
 def keep_half_spectrum(a, s):
@@ -108,7 +112,7 @@ def spectral_conv1d(x, w1, s=None):
     xh = tfft.rfft(x)
     lead = list(x.shape[:-1])
     lead[1] = w1.shape[1]
-    oh = torch.zeros(*lead, p // 2 + 1, dtype=torch.cfloat, device=x.device)
+    oh = torch.zeros(*lead, p // 2 + 1, dtype=xh.dtype, device=x.device)
     oh[..., :m] = mix(xh[..., :m], w1)
     if s is None or s == p:
         return tfft.irfft(oh, n=p)
@@ -122,7 +126,7 @@ def spectral_conv2d(x, w1, w2, s=None):
     xh = tfft.rfft2(x)
     lead = list(x.shape[:-2])
     lead[1] = w1.shape[1]
-    oh = torch.zeros(*lead, p1, p2 // 2 + 1, dtype=torch.cfloat, device=x.device)
+    oh = torch.zeros(*lead, p1, p2 // 2 + 1, dtype=xh.dtype, device=x.device)
     oh[..., :m1, :m2] = mix(xh[..., :m1, :m2], w1)
     oh[..., p1 - m1:, :m2] = mix(xh[..., p1 - m1:, :m2], w2)
     if s is None or tuple(s) == (p1, p2):
@@ -150,13 +154,13 @@ def linear_functionals2d(x, w):
 
 def linear_decoder1d(v, w, s):
     """shared.py:276-289.  v (B, Ci, ...) real -> (B, Co, ..., s); w (Ci, Co, m+1)."""
-    oh = mix(v[..., None].type(torch.cfloat), w)
+    oh = mix(v[..., None].to(w.dtype), w)
     return tfft.irfft(keep_half_spectrum(oh, s), n=s)
 
 
 def linear_decoder2d(v, w, s):
     """shared.py:406-419.  v (B, Ci, ...) real -> (B, Co, ..., s1, s2); w (Ci, Co, 2*m1, m2+1)."""
-    oh = mix(v[..., None, None].type(torch.cfloat), w)
+    oh = mix(v[..., None, None].to(w.dtype), w)
     return tfft.irfft2(keep_spectrum2(oh, tuple(s)), s=tuple(s))
 
 
@@ -203,7 +207,7 @@ def unit_grid(shape, device):
     """shared.py:111-118 / 150-159: coordinates in [0,1] (end points included), channels-last."""
     if len(shape) == 3:
         b, n1 = shape[0], shape[1]
-        return torch.linspace(0, 1, n1).reshape(1, n1, 1).repeat(b, 1, 1).to(device)
+        return torch.linspace(0, 1, n1).reshape(1, n1, 1).repeat(b, 1, 1).to(device)   # fp32 like the reference
     b, n1, n2 = shape[0], shape[1], shape[2]
     gx = torch.linspace(0, 1, n1).reshape(1, n1, 1, 1).repeat(b, 1, n2, 1)
     gy = torch.linspace(0, 1, n2).reshape(1, 1, n2, 1).repeat(b, n1, 1, 1)

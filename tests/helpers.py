@@ -43,3 +43,25 @@ def group(d, tag):
 
 def t(a, **kw):
     return torch.from_numpy(np.ascontiguousarray(a)).clone().requires_grad_(kw.get("grad", False))
+
+
+def to64(v):
+    v = v.detach().cpu() if isinstance(v, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(v))
+    return v.to(torch.complex128 if v.is_complex() else torch.float64)
+
+
+def assert_parity(got, ref32, truth64=None, tol=TOL_FP32, what=""):
+    """Parity rule.  ``got`` must match the reference's fp32 result ``ref32`` to rel-L2 <= tol.
+    Some quantities are ill-conditioned in fp32 (e.g. spectral-weight gradients of high modes when
+    the activation is dominated by its mean: the reference's own FFT carries an error of order
+    eps*||x|| in EVERY bin), so two correct fp32 implementations differ by more than tol there.  For
+    those, when a float64 evaluation ``truth64`` of the same algorithm is supplied, ``got`` must be
+    at least as close to the truth as the reference itself is (factor 1.5 for sampling noise)."""
+    e = rel_l2(got, ref32)
+    if e < tol:
+        return e
+    assert truth64 is not None, f"{what}: rel-L2 {e:.3e} >= {tol:.0e}"
+    e_got, e_ref = rel_l2(got, truth64), rel_l2(ref32, truth64)
+    assert e_got <= max(tol, 1.5 * e_ref), \
+        f"{what}: rel-L2 vs reference {e:.3e}; vs float64 truth: ours {e_got:.3e}, reference's own {e_ref:.3e}"
+    return e

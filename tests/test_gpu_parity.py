@@ -7,7 +7,7 @@ import pytest
 import torch
 
 from oracle import fnm_oracle as O
-from tests.helpers import TOL_FP32, group, load_npz, rel_l2, t
+from tests.helpers import TOL_FP32, assert_parity, group, load_npz, rel_l2, t, to64
 
 pytestmark = pytest.mark.gpu
 
@@ -105,10 +105,24 @@ MODELS = {
 }
 
 
+ORACLE_FWD = {
+    "fno2d": lambda p, x: O.f2f_forward(p, x),
+    "fno2d_res": lambda p, x: O.f2f_forward(p, x, s_outputspace=(8, 8)),
+    "fno1d": lambda p, x: O.f2f_forward(p, x),
+    "fnf2d": lambda p, x: O.f2v_forward(p, x),
+    "fnf1d": lambda p, x: O.f2v_forward(p, x),
+    "fnd2d": lambda p, x: O.v2f_forward(p, x, (16, 16)),
+    "fnd1d": lambda p, x: O.v2f_forward(p, x, 32),
+    "fnn2d": lambda p, x: O.v2v_forward(p, x, (16, 16)),
+    "fnn1d": lambda p, x: O.v2v_forward(p, x, 32),
+}
+
+
 @pytest.mark.parametrize("name", sorted(MODELS))
 def test_golden_model_train_steps(name):
     """Reference weights in, then 3 x (forward, rel-L2 sum loss, backward, fused Adam): output, loss,
-    every gradient and every parameter after 3 steps must match the reference run."""
+    every gradient and every parameter after 3 steps must match the reference run (fixtures); a
+    float64 run of the oracle supplies the truth for the noise-floor rule of assert_parity."""
     d = load_npz(f"model_{name}.npz")
     model = MODELS[name]()
     missing = model.load_state_dict({k: torch.from_numpy(v) for k, v in group(d, "w0").items()}, strict=True)
@@ -116,6 +130,15 @@ def test_golden_model_train_steps(name):
     model = model.to(DEV)
     opt = fnm_b200.Adam(model.parameters(), lr=1e-3, weight_decay=1e-4)
     x, y = t(d["x"]).to(DEV), t(d["y"]).to(DEV)
+    # float64 truth of the same 3 steps
+    p64 = {k: to64(v).requires_grad_(True) for k, v in group(d, "w0").items()}
+    st64 = O.AdamState()
+    g64 = {}
+    for step in range(3):
+        loss64, out64 = O.train_step(ORACLE_FWD[name], p64, to64(d["x"]), to64(d["y"]), st64, lr=1e-3, weight_decay=1e-4)
+        if step == 0:
+            out64_0, loss64_0 = out64, loss64
+            g64 = {k: (v.grad.clone() if v.grad is not None else torch.zeros_like(v)) for k, v in p64.items()}
     for step in range(3):
         opt.zero_grad()
         out = model(x)
@@ -123,15 +146,15 @@ def test_golden_model_train_steps(name):
         loss.backward()
         if step == 0:
             assert tuple(out.shape) == d["out0"].shape
-            assert rel_l2(out, d["out0"]) < TOL_FP32
-            assert rel_l2(loss, d["loss0"]) < TOL_FP32
+            assert_parity(out, d["out0"], out64_0, what="out")
+            assert_parity(loss, d["loss0"], loss64_0, what="loss")
             for k, p in model.named_parameters():
                 got = p.grad if p.grad is not None else torch.zeros_like(p)
-                assert rel_l2(got, d[f"g0.{k}"]) < TOL_FP32, k
+                assert_parity(got, d[f"g0.{k}"], g64[k], what=f"grad {k}")
         opt.step()
-    assert rel_l2(loss, d["loss_last"]) < TOL_FP32
+    assert_parity(loss, d["loss_last"], loss64, what="loss after 3 steps")
     for k, v in model.state_dict().items():
-        assert rel_l2(v, d[f"w3.{k}"]) < TOL_FP32, k
+        assert_parity(v, d[f"w3.{k}"], p64[k], what=f"param {k}")
 
 
 @pytest.mark.parametrize("tag,kw", [("plain", dict(lr=1e-3)), ("wd", dict(lr=2e-3, weight_decay=1e-2)),
