@@ -37,11 +37,11 @@ PROTOTYPES = {
     "fnm_profile_begin": (_i32, []),
     "fnm_profile_end": (_sz, [C.c_char_p, _sz]),
     "fnm_fourier_layer_workspace_bytes": (_sz, [_PP]),
-    "fnm_fourier_layer_fwd": (_i32, [_PP, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
-    "fnm_fourier_layer_bwd": (_i32, [_PP, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "fnm_fourier_layer_fwd": (_i32, [_PP, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "fnm_fourier_layer_bwd": (_i32, [_PP, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "fnm_lfunc_workspace_bytes": (_sz, [_PP]),
     "fnm_lfunc_fwd": (_i32, [_PP, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
-    "fnm_lfunc_bwd": (_i32, [_PP, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "fnm_lfunc_bwd": (_i32, [_PP, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "fnm_ldec_workspace_bytes": (_sz, [_PP]),
     "fnm_ldec_fwd": (_i32, [_PP, _vp, _vp, _vp, _vp, _sz, _vp]),
     "fnm_ldec_bwd": (_i32, [_PP, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
@@ -56,7 +56,7 @@ PROTOTYPES = {
     "fnm_mix_fwd": (_i32, [_vp, _vp, _vp, _i32, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
     "fnm_mix_bwd_x": (_i32, [_vp, _vp, _vp, _i32, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
     "fnm_mix_bwd_w": (_i32, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
-    "fnm_pointwise_ysyn": (_i32, [_vp, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32,
+    "fnm_pointwise_ysyn": (_i32, [_vp, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32,
                                   _i32, _vp]),
     "fnm_conv_wgrad_workspace_bytes": (_sz, [_i64, _i32, _i32]),
     "fnm_conv_wgrad": (_i32, [_vp, _vp, _i32, _vp, _vp, _i64, _i32, _i32, _vp, _sz, _i32, _vp]),

@@ -187,15 +187,15 @@ int fnm_mix_bwd_w(const float* Xh, const float* Gh, float* dw0, float* dw1, int 
 }
 
 int fnm_pointwise_ysyn(const float* x, int act_in, const float* wc, int wc_is_kn, const float* bias, const float* Z,
-                       const float* by, const float* mul_gelu_grad_of, float* out, int64_t rows, int S2, int LY, int K,
-                       int N, int mode, fnm_stream_t stream) {
+                       const float* by, const float* mul_gelu_grad_of, float* out, float* out_act, int64_t rows, int S2,
+                       int LY, int K, int N, int mode, fnm_stream_t stream) {
     FNM_REQUIRE(Z && by && out, "pointwise_ysyn: NULL pointer");
     FNM_REQUIRE(rows >= 0 && S2 > 0 && LY > 0 && N > 0 && K >= 0, "pointwise_ysyn: bad extents");
     FNM_REQUIRE((x == nullptr) == (wc == nullptr) || K == 0, "pointwise_ysyn: x and wc must be given together");
     if (tc_pointwise_ysyn_supported(rows, S2, LY, (x && wc) ? K : 0, N))
-        return tc_pointwise_ysyn(x, act_in, wc, wc_is_kn, bias, Z, by, mul_gelu_grad_of, out, rows, S2, LY, K, N, mode,
-                                 as_stream(stream));
-    return simt_pointwise_ysyn(x, act_in, wc, wc_is_kn, bias, Z, by, mul_gelu_grad_of, out, rows, S2, LY, K, N,
+        return tc_pointwise_ysyn(x, act_in, wc, wc_is_kn, bias, Z, by, mul_gelu_grad_of, out, out_act, rows, S2, LY, K, N,
+                                 mode, as_stream(stream));
+    return simt_pointwise_ysyn(x, act_in, wc, wc_is_kn, bias, Z, by, mul_gelu_grad_of, out, out_act, rows, S2, LY, K, N,
                                as_stream(stream));
 }
 
@@ -246,8 +246,8 @@ size_t fnm_fourier_layer_workspace_bytes(const fnm_plan* plan) {
 }
 
 int fnm_fourier_layer_fwd(const fnm_plan* p, const float* xin, int act_in, const float* w0, const float* w1,
-                          const float* wc, const float* bc, float* z_out, float* xh_save, void* workspace,
-                          size_t workspace_bytes, fnm_stream_t stream) {
+                          const float* wc, const float* bc, float* z_out, float* x_act_out, float* xh_save,
+                          void* workspace, size_t workspace_bytes, fnm_stream_t stream) {
     FNM_TRY(check_plan(p, true, true));
     FNM_REQUIRE(xin && w0 && z_out && xh_save && workspace, "layer_fwd: NULL pointer");
     FNM_REQUIRE(p->rows_per_w == p->R || (w1 && 2 * p->rows_per_w == p->R), "layer_fwd: weight rows do not cover R");
@@ -265,12 +265,12 @@ int fnm_fourier_layer_fwd(const fnm_plan* p, const float* xin, int act_in, const
     FNM_TRY(simt_xdft(T, p->ex, xh_save, p->B, p->P1, p->R, p->NY, p->Ci, st));
     FNM_TRY(simt_mix_fwd(xh_save, w0, w1, p->rows_per_w, Oh, p->B, p->R, p->NY, p->Ci, p->Co, st));
     FNM_TRY(simt_xsyn(Oh, p->fx, Z, p->B, p->S1, p->R, p->NY, p->Co, st));
-    return fnm_pointwise_ysyn(wc ? xin : nullptr, act_in, wc, 0, bc, Z, p->by, nullptr, z_out, (int64_t)p->B * p->S1,
-                              p->S2, LY, p->Ci, p->Co, p->mode, stream);
+    return fnm_pointwise_ysyn(wc ? xin : nullptr, act_in, wc, 0, bc, Z, p->by, nullptr, z_out, x_act_out,
+                              (int64_t)p->B * p->S1, p->S2, LY, p->Ci, p->Co, p->mode, stream);
 }
 
-int fnm_fourier_layer_bwd(const fnm_plan* p, const float* g_z, const float* xin, int act_in, const float* w0,
-                          const float* w1, const float* wc, const float* xh_save, float* g_in, float* dw0, float* dw1,
+int fnm_fourier_layer_bwd(const fnm_plan* p, const float* g_z, const float* xin, int act_in, const float* zin_pre,
+                          const float* w0, const float* w1, const float* wc, const float* xh_save, float* g_in, float* dw0, float* dw1,
                           float* dwc, float* dbc, void* workspace, size_t workspace_bytes, fnm_stream_t stream) {
     FNM_TRY(check_plan(p, true, true));
     FNM_REQUIRE(g_z && xin && w0 && xh_save && workspace, "layer_bwd: NULL pointer");
@@ -296,7 +296,8 @@ int fnm_fourier_layer_bwd(const fnm_plan* p, const float* g_z, const float* xin,
     if (g_in) {
         FNM_TRY(simt_mix_bwd_x(Gh, w0, w1, p->rows_per_w, Gxh, p->B, p->R, p->NY, p->Ci, p->Co, st));
         FNM_TRY(simt_xsyn(Gxh, p->fxb, Zg, p->B, p->P1, p->R, p->NY, p->Ci, st));
-        FNM_TRY(fnm_pointwise_ysyn(wc ? g_z : nullptr, 0, wc, 1, nullptr, Zg, p->ayT, act_in ? xin : nullptr, g_in,
+        const float* mul = zin_pre ? zin_pre : (act_in ? xin : nullptr);
+        FNM_TRY(fnm_pointwise_ysyn(wc ? g_z : nullptr, 0, wc, 1, nullptr, Zg, p->ayT, mul, g_in, nullptr,
                                    (int64_t)p->B * p->P1, p->P2, LY, p->Co, p->Ci, p->mode, stream));
     }
     return FNM_OK;
@@ -329,8 +330,8 @@ int fnm_lfunc_fwd(const fnm_plan* p, const float* xin, int act_in, const float* 
     return simt_lfunc_contract(xh_save, w, cc, out, partial, p->B, p->R, p->NY, p->Ci, p->Co, st);
 }
 
-int fnm_lfunc_bwd(const fnm_plan* p, const float* g_out, const float* xin, int act_in, const float* w, const float* cc,
-                  const float* xh_save, float* g_in, float* dw, void* workspace, size_t workspace_bytes,
+int fnm_lfunc_bwd(const fnm_plan* p, const float* g_out, const float* xin, int act_in, const float* zin_pre,
+                  const float* w, const float* cc, const float* xh_save, float* g_in, float* dw, void* workspace, size_t workspace_bytes,
                   fnm_stream_t stream) {
     FNM_TRY(check_plan(p, true, false));
     FNM_REQUIRE(g_out && xin && w && cc && xh_save && workspace, "lfunc_bwd: NULL pointer");
@@ -344,7 +345,8 @@ int fnm_lfunc_bwd(const fnm_plan* p, const float* g_out, const float* xin, int a
     if (g_in) {
         FNM_TRY(simt_lfunc_bwd_x(g_out, w, cc, Gxh, p->B, p->R, p->NY, p->Ci, p->Co, st));
         FNM_TRY(simt_xsyn(Gxh, p->fxb, Zg, p->B, p->P1, p->R, p->NY, p->Ci, st));
-        FNM_TRY(fnm_pointwise_ysyn(nullptr, 0, nullptr, 0, nullptr, Zg, p->ayT, act_in ? xin : nullptr, g_in,
+        const float* mul = zin_pre ? zin_pre : (act_in ? xin : nullptr);
+        FNM_TRY(fnm_pointwise_ysyn(nullptr, 0, nullptr, 0, nullptr, Zg, p->ayT, mul, g_in, nullptr,
                                    (int64_t)p->B * p->P1, p->P2, LY, 0, p->Ci, p->mode, stream));
     }
     return FNM_OK;
@@ -373,8 +375,8 @@ int fnm_ldec_fwd(const fnm_plan* p, const float* v, const float* w, float* y_out
     float* Oh = cv.take((size_t)p->R * p->NY * 2 * p->B * p->Co);
     FNM_TRY(simt_ldec_mix(v, w, Oh, p->B, p->R, p->NY, p->Ci, p->Co, st));
     FNM_TRY(simt_xsyn(Oh, p->fx, Z, p->B, p->S1, p->R, p->NY, p->Co, st));
-    return fnm_pointwise_ysyn(nullptr, 0, nullptr, 0, nullptr, Z, p->by, nullptr, y_out, (int64_t)p->B * p->S1, p->S2,
-                              LY, 0, p->Co, p->mode, stream);
+    return fnm_pointwise_ysyn(nullptr, 0, nullptr, 0, nullptr, Z, p->by, nullptr, y_out, nullptr, (int64_t)p->B * p->S1,
+                              p->S2, LY, 0, p->Co, p->mode, stream);
 }
 
 int fnm_ldec_bwd(const fnm_plan* p, const float* g_y, const float* v, const float* w, float* g_v, float* dw,

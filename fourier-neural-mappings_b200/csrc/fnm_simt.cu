@@ -282,7 +282,7 @@ struct MixBwdWP : FullK {
 // fused pointwise + y-synthesis (+ bias, + GELU' multiply).  batch = row; M = S2, K = Kc + LY
 struct PointwiseYsynP : FullK {
     const float* x; const float* wc; const float* bias; const float* Z; const float* by; const float* mul;
-    float* out;
+    float* out; float* out_act;
     int M, N, Kc, LY, act, wc_is_kn;
     static constexpr bool A_MFAST = false, B_NFAST = true;
     __device__ __forceinline__ float a(int row, int y, int k) const {
@@ -301,6 +301,7 @@ struct PointwiseYsynP : FullK {
         if (bias) v += __ldg(bias + n);
         if (mul) v *= gelu_grad_f(__ldg(mul + idx));
         out[idx] = v;
+        if (out_act) out_act[idx] = gelu_f(v);
     }
 };
 
@@ -510,11 +511,11 @@ int simt_mix_bwd_w(const float* Xh, const float* Gh, float* dw0, float* dw1, int
 }
 
 int simt_pointwise_ysyn(const float* x, int act, const float* wc, int wc_is_kn, const float* bias, const float* Z,
-                        const float* by, const float* mul, float* out, int64_t rows, int S2, int LY, int K, int N,
-                        cudaStream_t st) {
+                        const float* by, const float* mul, float* out, float* out_act, int64_t rows, int S2, int LY,
+                        int K, int N, cudaStream_t st) {
     PointwiseYsynP p;
     const int Kc = (x && wc) ? K : 0;
-    p.K = Kc + LY; p.x = x; p.wc = wc; p.bias = bias; p.Z = Z; p.by = by; p.mul = mul; p.out = out;
+    p.K = Kc + LY; p.x = x; p.wc = wc; p.bias = bias; p.Z = Z; p.by = by; p.mul = mul; p.out = out; p.out_act = out_act;
     p.M = S2; p.N = N; p.Kc = Kc; p.LY = LY; p.act = act; p.wc_is_kn = wc_is_kn;
     return launch_auto(p, rows, st, "pointwise_ysyn");
 }

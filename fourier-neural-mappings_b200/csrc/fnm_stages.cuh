@@ -15,8 +15,8 @@ int simt_mix_bwd_x(const float* Gh, const float* w0, const float* w1, int rpw, f
 int simt_mix_bwd_w(const float* Xh, const float* Gh, float* dw0, float* dw1, int rpw, int B, int R, int NY, int Ci,
                    int Co, cudaStream_t st);
 int simt_pointwise_ysyn(const float* x, int act, const float* wc, int wc_is_kn, const float* bias, const float* Z,
-                        const float* by, const float* mul, float* out, int64_t rows, int S2, int LY, int K, int N,
-                        cudaStream_t st);
+                        const float* by, const float* mul, float* out, float* out_act, int64_t rows, int S2, int LY,
+                        int K, int N, cudaStream_t st);
 size_t simt_conv_wgrad_workspace(int64_t npos, int Ci, int Co);
 int simt_conv_wgrad(const float* g, const float* x, int act, float* dwc, float* dbc, int64_t npos, int Ci, int Co,
                     float* partial, cudaStream_t st);
@@ -46,7 +46,7 @@ int tc_ydft(const float* x, const float* tab, float* T, int64_t rows, int P2, in
             cudaStream_t st);
 bool tc_pointwise_ysyn_supported(int64_t rows, int S2, int LY, int K, int N);
 int tc_pointwise_ysyn(const float* x, int act, const float* wc, int wc_is_kn, const float* bias, const float* Z,
-                      const float* by, const float* mul, float* out, int64_t rows, int S2, int LY, int K, int N,
-                      int mode, cudaStream_t st);
+                      const float* by, const float* mul, float* out, float* out_act, int64_t rows, int S2, int LY,
+                      int K, int N, int mode, cudaStream_t st);
 
 }  // namespace fnm

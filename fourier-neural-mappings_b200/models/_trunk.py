@@ -16,15 +16,22 @@ _TORCH_ACTS = {"tanh": torch.tanh, "relu": F.relu, "elu": F.elu, "leaky_relu": F
 
 
 class Pending:
-    """A channels-last activation whose GELU may still be pending (``z`` holds the pre-activation)."""
+    """A channels-last activation of the trunk.  ``z`` is the differentiable tensor; when ``act`` is
+    set its GELU is still pending, and ``x`` may hold GELU(z) already (written by the producing
+    kernel's epilogue, detached: gradients flow through ``z``)."""
 
-    __slots__ = ("z", "act")
+    __slots__ = ("z", "act", "x")
 
-    def __init__(self, z, act=False):
-        self.z, self.act = z, act
+    def __init__(self, z, act=False, x=None):
+        self.z, self.act, self.x = z, act, x
 
     def value(self):
-        return ops.gelu(self.z) if self.act else self.z
+        """The activated tensor as a differentiable value (for consumers outside the fused layers)."""
+        if not self.act:
+            return self.z
+        y = ops.gelu(self.z)
+        self.x = y.detach()
+        return y
 
 
 def _layer_tables(speconv, P1, P2, one_d, s=None):
@@ -51,7 +58,7 @@ def run_layers(state, speconvs, ws, act_name, act_flags, one_d, last_s=None):
             change = target != ((P2,) if one_d else (P1, P2))
         if change:
             x = state.value()
-            z = ops.fourier_layer(x, sc.weights1, w1, None, None, _layer_tables(sc, P1, P2, one_d, last_s))
+            z, _ = ops.fourier_layer(x, sc.weights1, w1, None, None, _layer_tables(sc, P1, P2, one_d, last_s))
             # the pointwise branch acts on the Fourier-resampled input: adjacent op
             if one_d:
                 xc = projector1d(x.squeeze(1).permute(0, 2, 1), last_s)
@@ -60,12 +67,15 @@ def run_layers(state, speconvs, ws, act_name, act_flags, one_d, last_s=None):
                 xc = projector2d(x.permute(0, 3, 1, 2), last_s)
                 z = z + w(xc).permute(0, 2, 3, 1)
         else:
-            z = ops.fourier_layer(z_in, sc.weights1, w1, w.weight, w.bias, _layer_tables(sc, P1, P2, one_d),
-                                  act_in=state.act)
+            xo = None
+            # the activated copy is produced in this layer's epilogue when another fused layer consumes it
+            want = bool(act_flags[i]) and fused_gelu and not last
+            z, xo = ops.fourier_layer(z_in, sc.weights1, w1, w.weight, w.bias, _layer_tables(sc, P1, P2, one_d),
+                                      act_in=state.act, xact=state.x, want_act_out=want)
         if not act_flags[i]:
             state = Pending(z, False)
         elif fused_gelu:
-            state = Pending(z, True)
+            state = Pending(z, True, xo if not change else None)
         else:
             state = Pending(_TORCH_ACTS[act_name](z), False)
     return state
@@ -106,8 +116,9 @@ def functional_end(state, lfunc0, mlpfunc0, head, one_d):
     z = state.z
     _, P1, P2, _ = z.shape
     tables = lfunc0.tables(P2) if one_d else lfunc0.tables(P1, P2)
-    nonlocal_feats = ops.linear_functional(z, lfunc0.weights, tables, act_in=state.act)
-    h = mlpfunc0(state.value())                               # (B, P1, P2, width_lfunc)
+    xv = state.value()                                        # differentiable GELU(z) for the pointwise branch
+    nonlocal_feats = ops.linear_functional(z, lfunc0.weights, tables, act_in=state.act, xact=state.x)
+    h = mlpfunc0(xv)                                          # (B, P1, P2, width_lfunc)
     h = torch.trapz(h, dx=1.0 / P2, dim=2)
     h = h.squeeze(1) if one_d else torch.trapz(h, dx=1.0 / P1, dim=1)
     return head(torch.cat((nonlocal_feats, h), dim=1))

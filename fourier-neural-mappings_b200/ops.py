@@ -70,102 +70,114 @@ def _workspace(device, nbytes):
 
 
 class FourierLayerFn(torch.autograd.Function):
-    """z = Conv1x1(f(xin)) + bias + SpectralConv(f(xin)), f = GELU if act_in else identity.
-    wc / bc may be None (bare SpectralConv)."""
+    """z = Conv1x1(f(zin)) + bias + SpectralConv(f(zin)), f = GELU if act_in else identity; optionally
+    also returns GELU(z) (non-differentiable cache for the next layer).
+
+    ``xact`` is an optional cached GELU(zin) produced by the previous layer's epilogue: the kernels then
+    read it with no activation on load, and backward multiplies by GELU'(zin).  wc / bc may be None
+    (bare SpectralConv)."""
 
     @staticmethod
-    def forward(ctx, xin, w0, w1, wc, bc, tables, act_in):
-        _need_cuda(xin, w0, w1, wc, bc)
-        xin = _f32c(xin)
-        B, P1, P2, Ci = xin.shape
+    def forward(ctx, zin, xact, w0, w1, wc, bc, tables, act_in, want_act_out):
+        _need_cuda(zin, xact, w0, w1, wc, bc)
+        cached = bool(act_in) and xact is not None
+        xk = _f32c(xact) if cached else _f32c(zin)
+        kact = 0 if cached else int(bool(act_in))
+        B, P1, P2, Ci = xk.shape
         Co = w0.shape[1]
         if (P1, P2) != (tables.P1, tables.P2) or w0.shape[0] != Ci:
-            raise ValueError(f"input {tuple(xin.shape)} does not match the plan / weights")
-        plan = tables.c_plan(xin.device, B, Ci, Co, _MODE)
+            raise ValueError(f"input {tuple(xk.shape)} does not match the plan / weights")
+        plan = tables.c_plan(xk.device, B, Ci, Co, _MODE)
         w0r = _cplx(w0)
         w1r = _cplx(w1) if w1 is not None else None
         wcc = _f32c(wc.reshape(Co, Ci)) if wc is not None else None
         bcc = _f32c(bc) if bc is not None else None
-        z = torch.empty((B, tables.S1, tables.S2, Co), dtype=torch.float32, device=xin.device)
-        xh = torch.empty((tables.R, tables.NY, 2, B, Ci), dtype=torch.float32, device=xin.device)
+        z = torch.empty((B, tables.S1, tables.S2, Co), dtype=torch.float32, device=xk.device)
+        xo = torch.empty_like(z) if want_act_out else None
+        xh = torch.empty((tables.R, tables.NY, 2, B, Ci), dtype=torch.float32, device=xk.device)
         L = lib()
         nbytes = L.fnm_fourier_layer_workspace_bytes(C.byref(plan))
-        ws = _workspace(xin.device, nbytes)
-        check(L.fnm_fourier_layer_fwd(C.byref(plan), _ptr(xin), int(act_in), _ptr(w0r), _ptr(w1r), _ptr(wcc), _ptr(bcc),
-                                      _ptr(z), _ptr(xh), _ptr(ws), ws.numel(), _stream()), "fnm_fourier_layer_fwd")
-        ctx.save_for_backward(xin, w0, w1, wc, xh)
-        ctx.tables, ctx.act_in, ctx.has_bias = tables, bool(act_in), bc is not None
-        return z
+        ws = _workspace(xk.device, nbytes)
+        check(L.fnm_fourier_layer_fwd(C.byref(plan), _ptr(xk), kact, _ptr(w0r), _ptr(w1r), _ptr(wcc), _ptr(bcc),
+                                      _ptr(z), _ptr(xo), _ptr(xh), _ptr(ws), ws.numel(), _stream()),
+              "fnm_fourier_layer_fwd")
+        ctx.save_for_backward(xk, _f32c(zin) if cached else None, w0, w1, wc, xh)
+        ctx.tables, ctx.kact, ctx.has_bias = tables, kact, bc is not None
+        if xo is not None:
+            ctx.mark_non_differentiable(xo)
+        return z, xo
 
     @staticmethod
-    def backward(ctx, gz):
-        xin, w0, w1, wc, xh = ctx.saved_tensors
+    def backward(ctx, gz, _gxo=None):
+        xk, zpre, w0, w1, wc, xh = ctx.saved_tensors
         tables = ctx.tables
         gz = _f32c(gz)
-        B, P1, P2, Ci = xin.shape
+        B, P1, P2, Ci = xk.shape
         Co = w0.shape[1]
-        plan = tables.c_plan(xin.device, B, Ci, Co, _MODE)
-        need_x, need_w0, need_w1, need_wc, need_bc = ctx.needs_input_grad[:5]
-        g_in = torch.empty_like(xin) if need_x else None
+        plan = tables.c_plan(xk.device, B, Ci, Co, _MODE)
+        need_x, _, need_w0, need_w1, need_wc, need_bc = ctx.needs_input_grad[:6]
+        g_in = torch.empty_like(xk) if need_x else None
         want_w = need_w0 or (w1 is not None and need_w1)
         dw0 = torch.empty_like(w0) if want_w else None
         dw1 = torch.empty_like(w1) if (want_w and w1 is not None) else None
         dwc = torch.empty_like(wc) if (wc is not None and need_wc) else None
-        dbc = torch.empty((Co,), dtype=torch.float32, device=xin.device) if (ctx.has_bias and need_bc) else None
+        dbc = torch.empty((Co,), dtype=torch.float32, device=xk.device) if (ctx.has_bias and need_bc) else None
         w0r = _cplx(w0)
         w1r = _cplx(w1) if w1 is not None else None
         wcc = _f32c(wc.reshape(Co, Ci)) if wc is not None else None
         L = lib()
         nbytes = L.fnm_fourier_layer_workspace_bytes(C.byref(plan))
-        ws = _workspace(xin.device, nbytes)
+        ws = _workspace(xk.device, nbytes)
         check(L.fnm_fourier_layer_bwd(
-            C.byref(plan), _ptr(gz), _ptr(xin), int(ctx.act_in), _ptr(w0r), _ptr(w1r), _ptr(wcc), _ptr(xh),
+            C.byref(plan), _ptr(gz), _ptr(xk), ctx.kact, _ptr(zpre), _ptr(w0r), _ptr(w1r), _ptr(wcc), _ptr(xh),
             _ptr(g_in), _ptr(torch.view_as_real(dw0)) if dw0 is not None else None,
             _ptr(torch.view_as_real(dw1)) if dw1 is not None else None, _ptr(dwc), _ptr(dbc),
             _ptr(ws), ws.numel(), _stream()), "fnm_fourier_layer_bwd")
-        return g_in, dw0, dw1, dwc, dbc, None, None
+        return g_in, None, dw0, dw1, dwc, dbc, None, None, None
 
 
 class LinearFunctionalFn(torch.autograd.Function):
-    """out[b, o] = F2V functional of f(xin) (LinearFunctionals1d/2d)."""
+    """out[b, o] = F2V functional of f(zin) (LinearFunctionals1d/2d); ``xact`` = optional cached GELU(zin)."""
 
     @staticmethod
-    def forward(ctx, xin, w, tables, act_in):
-        _need_cuda(xin, w)
-        xin = _f32c(xin)
-        B, P1, P2, Ci = xin.shape
+    def forward(ctx, zin, xact, w, tables, act_in):
+        _need_cuda(zin, xact, w)
+        cached = bool(act_in) and xact is not None
+        xk = _f32c(xact) if cached else _f32c(zin)
+        kact = 0 if cached else int(bool(act_in))
+        B, P1, P2, Ci = xk.shape
         Co = w.shape[1]
         if (P1, P2) != (tables.P1, tables.P2) or w.shape[0] != Ci:
-            raise ValueError(f"input {tuple(xin.shape)} does not match the plan / weights")
-        plan = tables.c_plan(xin.device, B, Ci, Co, _MODE)
-        cc = tables.device(xin.device)["cc"]
-        out = torch.empty((B, Co), dtype=torch.float32, device=xin.device)
-        xh = torch.empty((tables.R, tables.NY, 2, B, Ci), dtype=torch.float32, device=xin.device)
+            raise ValueError(f"input {tuple(xk.shape)} does not match the plan / weights")
+        plan = tables.c_plan(xk.device, B, Ci, Co, _MODE)
+        cc = tables.device(xk.device)["cc"]
+        out = torch.empty((B, Co), dtype=torch.float32, device=xk.device)
+        xh = torch.empty((tables.R, tables.NY, 2, B, Ci), dtype=torch.float32, device=xk.device)
         L = lib()
-        ws = _workspace(xin.device, L.fnm_lfunc_workspace_bytes(C.byref(plan)))
-        check(L.fnm_lfunc_fwd(C.byref(plan), _ptr(xin), int(act_in), _ptr(_cplx(w)), _ptr(cc), _ptr(out), _ptr(xh),
+        ws = _workspace(xk.device, L.fnm_lfunc_workspace_bytes(C.byref(plan)))
+        check(L.fnm_lfunc_fwd(C.byref(plan), _ptr(xk), kact, _ptr(_cplx(w)), _ptr(cc), _ptr(out), _ptr(xh),
                               _ptr(ws), ws.numel(), _stream()), "fnm_lfunc_fwd")
-        ctx.save_for_backward(xin, w, xh)
-        ctx.tables, ctx.act_in = tables, bool(act_in)
+        ctx.save_for_backward(xk, _f32c(zin) if cached else None, w, xh)
+        ctx.tables, ctx.kact = tables, kact
         return out
 
     @staticmethod
     def backward(ctx, g):
-        xin, w, xh = ctx.saved_tensors
+        xk, zpre, w, xh = ctx.saved_tensors
         tables = ctx.tables
         g = _f32c(g)
-        B, _, _, Ci = xin.shape
+        B, _, _, Ci = xk.shape
         Co = w.shape[1]
-        plan = tables.c_plan(xin.device, B, Ci, Co, _MODE)
-        cc = tables.device(xin.device)["cc"]
-        g_in = torch.empty_like(xin) if ctx.needs_input_grad[0] else None
-        dw = torch.empty_like(w) if ctx.needs_input_grad[1] else None
+        plan = tables.c_plan(xk.device, B, Ci, Co, _MODE)
+        cc = tables.device(xk.device)["cc"]
+        g_in = torch.empty_like(xk) if ctx.needs_input_grad[0] else None
+        dw = torch.empty_like(w) if ctx.needs_input_grad[2] else None
         L = lib()
-        ws = _workspace(xin.device, L.fnm_lfunc_workspace_bytes(C.byref(plan)))
-        check(L.fnm_lfunc_bwd(C.byref(plan), _ptr(g), _ptr(xin), int(ctx.act_in), _ptr(_cplx(w)), _ptr(cc), _ptr(xh),
+        ws = _workspace(xk.device, L.fnm_lfunc_workspace_bytes(C.byref(plan)))
+        check(L.fnm_lfunc_bwd(C.byref(plan), _ptr(g), _ptr(xk), ctx.kact, _ptr(zpre), _ptr(_cplx(w)), _ptr(cc), _ptr(xh),
                               _ptr(g_in), _ptr(torch.view_as_real(dw)) if dw is not None else None,
                               _ptr(ws), ws.numel(), _stream()), "fnm_lfunc_bwd")
-        return g_in, dw, None, None
+        return g_in, None, dw, None, None
 
 
 class LinearDecoderFn(torch.autograd.Function):
@@ -228,12 +240,13 @@ class GeluFn(torch.autograd.Function):
         return gz
 
 
-def fourier_layer(xin, w0, w1, wc, bc, tables, act_in=False):
-    return FourierLayerFn.apply(xin, w0, w1, wc, bc, tables, act_in)
+def fourier_layer(zin, w0, w1, wc, bc, tables, act_in=False, xact=None, want_act_out=False):
+    """Returns (z, GELU(z) or None).  ``zin`` is the layer input (pre-activation if act_in)."""
+    return FourierLayerFn.apply(zin, xact, w0, w1, wc, bc, tables, act_in, want_act_out)
 
 
-def linear_functional(xin, w, tables, act_in=False):
-    return LinearFunctionalFn.apply(xin, w, tables, act_in)
+def linear_functional(zin, w, tables, act_in=False, xact=None):
+    return LinearFunctionalFn.apply(zin, xact, w, tables, act_in)
 
 
 def linear_decoder(v, w, tables):

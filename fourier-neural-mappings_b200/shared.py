@@ -158,7 +158,7 @@ class SpectralConv1d(nn.Module):
 
     def forward(self, x, s=None):
         x, info = _fold_extra_dims(x, 1)
-        y = ops.fourier_layer(_to_cl(x), self.weights1, None, None, None, self.tables(x.shape[-1], s))
+        y, _ = ops.fourier_layer(_to_cl(x), self.weights1, None, None, None, self.tables(x.shape[-1], s))
         return _unfold_extra_dims(_from_cl(y, True), info, 1)
 
 
@@ -179,8 +179,8 @@ class SpectralConv2d(nn.Module):
 
     def forward(self, x, s=None):
         x, info = _fold_extra_dims(x, 2)
-        y = ops.fourier_layer(_to_cl(x), self.weights1, self.weights2, None, None,
-                              self.tables(x.shape[-2], x.shape[-1], s))
+        y, _ = ops.fourier_layer(_to_cl(x), self.weights1, self.weights2, None, None,
+                                 self.tables(x.shape[-2], x.shape[-1], s))
         return _unfold_extra_dims(_from_cl(y, False), info, 2)
 
 

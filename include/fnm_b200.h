@@ -93,18 +93,24 @@ size_t fnm_profile_end(char* buf, size_t n);
  *      F.gelu (shared.py:13-14) folded into the consumer's load.
  *        z[b,x,y,o] = sum_i wc[o,i] f(xin[b,x,y,i]) + bc[o] + SpectralConv(f(xin))[b,x,y,o]
  *      f = GELU(erf) if act_in else identity.  wc == NULL drops the pointwise branch (bare
- *      SpectralConv*).  xh_save [R][NY][2][B][Ci] receives the input spectrum for backward.      */
+ *      SpectralConv*).  xh_save [R][NY][2][B][Ci] receives the input spectrum for backward.
+ *      x_act_out (may be NULL) additionally receives GELU(z): the activation is evaluated ONCE, in
+ *      the epilogue of the layer that produces z, and the next layer is then called with that
+ *      tensor as xin and act_in = 0 (measured on B200: GELU-on-load in every consumer costs more
+ *      issue slots than the extra write costs HBM time).                                          */
 size_t fnm_fourier_layer_workspace_bytes(const fnm_plan* plan);
 int fnm_fourier_layer_fwd(const fnm_plan* plan, const float* xin, int act_in,
                           const float* w0, const float* w1,          /* complex (Ci,Co,rows_per_w,NY) */
                           const float* wc, const float* bc,          /* (Co,Ci), (Co) or NULL */
-                          float* z_out, float* xh_save,
+                          float* z_out, float* x_act_out, float* xh_save,
                           void* workspace, size_t workspace_bytes, fnm_stream_t stream);
-/* backward of the above (autograd of the same reference lines).  g_z = dL/dz.  Outputs:
- *   g_in = dL/d xin (already multiplied by GELU'(xin) when act_in), dw0/dw1 complex grads in the
- *   reference layout, dwc (Co,Ci), dbc (Co).  Any of g_in / dw0 / dwc may be NULL to skip it.      */
+/* backward of the above (autograd of the same reference lines).  g_z = dL/dz.  xin / act_in as
+ * given to forward.  zin_pre (may be NULL): when forward was fed a cached GELU(zin_pre) as xin, the
+ * pre-activation it came from; g_in is then dL/d zin_pre = dL/d xin * GELU'(zin_pre).  Outputs:
+ *   g_in (times GELU'(xin) when act_in), dw0/dw1 complex grads in the reference layout, dwc (Co,Ci),
+ *   dbc (Co).  Any of g_in / dw0 / dwc may be NULL to skip it.                                      */
 int fnm_fourier_layer_bwd(const fnm_plan* plan, const float* g_z, const float* xin, int act_in,
-                          const float* w0, const float* w1, const float* wc, const float* xh_save,
+                          const float* zin_pre, const float* w0, const float* w1, const float* wc, const float* xh_save,
                           float* g_in, float* dw0, float* dw1, float* dwc, float* dbc,
                           void* workspace, size_t workspace_bytes, fnm_stream_t stream);
 
@@ -116,7 +122,7 @@ size_t fnm_lfunc_workspace_bytes(const fnm_plan* plan);
 int fnm_lfunc_fwd(const fnm_plan* plan, const float* xin, int act_in, const float* w, const float* cc,
                   float* out, float* xh_save, void* workspace, size_t workspace_bytes, fnm_stream_t stream);
 int fnm_lfunc_bwd(const fnm_plan* plan, const float* g_out, const float* xin, int act_in,
-                  const float* w, const float* cc, const float* xh_save,
+                  const float* zin_pre, const float* w, const float* cc, const float* xh_save,
                   float* g_in, float* dw, void* workspace, size_t workspace_bytes, fnm_stream_t stream);
 
 /* ---- V2F: LinearDecoder{1,2}d.forward (shared.py:276-289, 406-419).
@@ -167,10 +173,11 @@ int fnm_mix_bwd_w(const float* Xh, const float* Gh, float* dw0, float* dw1, int 
  * GELU' of the backward pass):
  *   out[row][y][n] = ( sum_k f(x[row][y][k]) Wk[k][n] + sum_l' by[y][l'] Z[row][l'][n] + bias[n] )
  *                    * ( mul_gelu_grad_of ? GELU'(mul_gelu_grad_of[row][y][n]) : 1 )
+ *   out_act[row][y][n] = GELU(out[row][y][n])      (only when out_act != NULL)
  *   Wk[k][n] = wc[n][k] (wc_is_kn == 0: forward, wc is (Co,Ci)) or wc[k][n] (wc_is_kn != 0: backward).
  *   x == NULL (or K == 0) drops the pointwise term; bias may be NULL.                               */
 int fnm_pointwise_ysyn(const float* x, int act_in, const float* wc, int wc_is_kn, const float* bias,
-                       const float* Z, const float* by, const float* mul_gelu_grad_of, float* out,
+                       const float* Z, const float* by, const float* mul_gelu_grad_of, float* out, float* out_act,
                        int64_t rows, int S2, int LY, int K, int N, int mode, fnm_stream_t stream);
 /* dwc[o][i] = sum_pos g[pos][o] f(x[pos][i]);  dbc[o] = sum_pos g[pos][o]   (conv weight/bias grads) */
 size_t fnm_conv_wgrad_workspace_bytes(int64_t npos, int Ci, int Co);

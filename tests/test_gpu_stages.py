@@ -1,0 +1,123 @@
+"""GPU tests of individual C-ABI stages against float64 torch formulas (no model around them).
+These pin each kernel -- in particular the tcgen05 fused pass -- independently of the layer chain."""
+import ctypes as C
+
+import pytest
+import torch
+
+from tests.helpers import TOL_FP32, TOL_TF32, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+import fnm_b200                                   # noqa: E402
+from fnm_b200._lib import check, lib              # noqa: E402
+
+DEV = "cuda"
+
+
+def _p(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _gelu64(z):
+    return 0.5 * z * (1 + torch.erf(z / 2 ** 0.5))
+
+
+def _gelu_grad64(z):
+    return 0.5 * (1 + torch.erf(z / 2 ** 0.5)) + z * torch.exp(-0.5 * z * z) / (2 * torch.pi) ** 0.5
+
+
+def _pointwise_ysyn_ref(x, act, wc, wc_is_kn, bias, Z, by, mul):
+    """float64 statement of fnm_pointwise_ysyn (include/fnm_b200.h)."""
+    out = torch.einsum("yl,rln->ryn", by.double(), Z.double())
+    if x is not None:
+        xa = _gelu64(x.double()) if act else x.double()
+        wk = wc.double() if wc_is_kn else wc.double().t()        # Wk[k][n]
+        out = out + torch.einsum("ryk,kn->ryn", xa, wk)
+    if bias is not None:
+        out = out + bias.double()
+    if mul is not None:
+        out = out * _gelu_grad64(mul.double())
+    return out
+
+
+CASES = [
+    # rows, S2, LY, K, N, act, wc_is_kn, bias, mul        (tcgen05-eligible shapes first)
+    dict(rows=40, S2=72, LY=24, K=32, N=32, act=1, kn=0, bias=1, mul=0),       # config 1 forward
+    dict(rows=40, S2=72, LY=24, K=32, N=32, act=0, kn=1, bias=0, mul=1),       # config 1 backward
+    dict(rows=300, S2=288, LY=64, K=128, N=128, act=1, kn=0, bias=1, mul=0),   # config 5 forward (TMEM-resident weights)
+    dict(rows=200, S2=288, LY=64, K=128, N=128, act=0, kn=1, bias=0, mul=1),   # config 5 backward
+    dict(rows=7, S2=1152, LY=32, K=64, N=64, act=1, kn=0, bias=1, mul=0),      # config 2 (1-D)
+    dict(rows=33, S2=144, LY=32, K=64, N=64, act=1, kn=0, bias=1, mul=0),      # config 4 trunk
+    dict(rows=50, S2=57, LY=24, K=32, N=32, act=1, kn=0, bias=1, mul=1),       # config 3 trunk: odd row length
+    dict(rows=20, S2=144, LY=34, K=0, N=64, act=0, kn=0, bias=0, mul=0),       # V2F decoder output (no pointwise term)
+    dict(rows=20, S2=57, LY=26, K=0, N=32, act=0, kn=0, bias=0, mul=1),        # F2V backward
+    dict(rows=9, S2=40, LY=10, K=20, N=20, act=1, kn=0, bias=1, mul=0),        # SIMT-only shape (C = 20)
+    dict(rows=5, S2=96, LY=16, K=96, N=96, act=1, kn=0, bias=1, mul=1),        # 64 < C < 128
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: "r{rows}_s{S2}_ly{LY}_k{K}_n{N}_a{act}{kn}{bias}{mul}".format(**c))
+@pytest.mark.parametrize("mode", ["fp32", "tf32"])
+def test_pointwise_ysyn(case, mode):
+    torch.manual_seed(0)
+    rows, S2, LY, K, N = case["rows"], case["S2"], case["LY"], case["K"], case["N"]
+    x = torch.randn(rows, S2, K, device=DEV) if K else None
+    wc = (torch.randn(K, N, device=DEV) if case["kn"] else torch.randn(N, K, device=DEV)) / max(K, 1) ** 0.5 if K else None
+    bias = torch.randn(N, device=DEV) if case["bias"] else None
+    Z = torch.randn(rows, LY, N, device=DEV)
+    by = torch.randn(S2, LY, device=DEV) / LY ** 0.5
+    mul = torch.randn(rows, S2, N, device=DEV) if case["mul"] else None
+    out = torch.full((rows, S2, N), float("nan"), device=DEV)
+    out_act = torch.full((rows, S2, N), float("nan"), device=DEV) if not case["mul"] else None
+    check(lib().fnm_pointwise_ysyn(_p(x), case["act"], _p(wc), case["kn"], _p(bias), _p(Z), _p(by), _p(mul), _p(out),
+                                   _p(out_act), rows, S2, LY, K, N, 0 if mode == "fp32" else 1, _stream()),
+          "fnm_pointwise_ysyn")
+    torch.cuda.synchronize()
+    ref = _pointwise_ysyn_ref(x, case["act"], wc, case["kn"], bias, Z, by, mul)
+    assert torch.isfinite(out).all()
+    err = rel_l2(out, ref)
+    tol = TOL_FP32 if mode == "fp32" else TOL_TF32
+    assert err < tol, err
+    if out_act is not None:                       # the activated copy written by the same epilogue
+        assert rel_l2(out_act, _gelu64(ref)) < tol
+
+
+def test_ydft_xdft_xsyn_roundtrip_stages():
+    """ydft -> xdft -> xsyn -> ysyn with identity mixing reproduces the band-limited projection."""
+    from fnm_b200.plan import spectral_tables
+    torch.manual_seed(1)
+    B, C, P1, P2, m1, m2 = 2, 32, 24, 40, 5, 7
+    tab = spectral_tables(P1, P2, m1, m2)
+    d = tab.device(torch.device(DEV))
+    x = torch.randn(B, P1, P2, C, device=DEV)
+    LY, R, NY = 2 * m2, 2 * m1, m2
+    T = torch.empty(B, P1, LY, C, device=DEV)
+    Xh = torch.empty(R, NY, 2, B, C, device=DEV)
+    Zt = torch.empty(B, P1, LY, C, device=DEV)
+    y = torch.empty(B, P1, P2, C, device=DEV)
+    L = lib()
+    check(L.fnm_ydft(_p(x), _p(d["ay"]), _p(T), B * P1, P2, LY, C, 0, 0, _stream()))
+    check(L.fnm_xdft(_p(T), _p(d["ex"]), _p(Xh), B, P1, R, NY, C, _stream()))
+    check(L.fnm_xsyn(_p(Xh), _p(d["fx"]), _p(Zt), B, P1, R, NY, C, _stream()))
+    check(L.fnm_pointwise_ysyn(None, 0, None, 0, None, _p(Zt), _p(d["by"]), None, _p(y), None, B * P1, P2, LY, 0, C, 0, _stream()))
+    xc = x.permute(0, 3, 1, 2).cpu().double()
+    xh = torch.fft.rfft2(xc)
+    keep = torch.zeros_like(xh)
+    keep[..., :m1, :m2] = xh[..., :m1, :m2]
+    keep[..., P1 - m1:, :m2] = xh[..., P1 - m1:, :m2]
+    ref = torch.fft.irfft2(keep, s=(P1, P2)).permute(0, 2, 3, 1)
+    assert rel_l2(y, ref) < TOL_FP32
+
+
+def test_gelu_kernels():
+    z = torch.randn(100003, device=DEV) * 3
+    g = torch.randn_like(z)
+    assert rel_l2(fnm_b200.ops.gelu(z), _gelu64(z.double())) < 1e-6
+    zz = z.clone().requires_grad_(True)
+    fnm_b200.ops.gelu(zz).backward(g)
+    assert rel_l2(zz.grad, g.double() * _gelu_grad64(z.double())) < 1e-6
