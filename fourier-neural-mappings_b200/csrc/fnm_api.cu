@@ -153,15 +153,19 @@ int fnm_ydft(const float* x, const float* tab, float* T, int64_t rows, int P2, i
     return simt_ydft(x, tab, T, rows, P2, LY, C, act_in, as_stream(stream));
 }
 
-int fnm_xdft(const float* T, const float* ex, float* Xh, int B, int P1, int R, int NY, int C, fnm_stream_t stream) {
+int fnm_xdft(const float* T, const float* ex, float* Xh, int B, int P1, int R, int NY, int C, int mode,
+             fnm_stream_t stream) {
     FNM_REQUIRE(T && ex && Xh, "xdft: NULL pointer");
     FNM_REQUIRE(B > 0 && P1 > 0 && R > 0 && NY > 0 && C > 0, "xdft: bad extents");
+    if (tc_xdft_supported(B, P1, R, NY, C)) return tc_xdft(T, ex, Xh, B, P1, R, NY, C, mode, as_stream(stream));
     return simt_xdft(T, ex, Xh, B, P1, R, NY, C, as_stream(stream));
 }
 
-int fnm_xsyn(const float* Oh, const float* fx, float* Z, int B, int S1, int R, int NY, int C, fnm_stream_t stream) {
+int fnm_xsyn(const float* Oh, const float* fx, float* Z, int B, int S1, int R, int NY, int C, int mode,
+             fnm_stream_t stream) {
     FNM_REQUIRE(Oh && fx && Z, "xsyn: NULL pointer");
     FNM_REQUIRE(B > 0 && S1 > 0 && R > 0 && NY > 0 && C > 0, "xsyn: bad extents");
+    if (tc_xsyn_supported(B, S1, R, NY, C)) return tc_xsyn(Oh, fx, Z, B, S1, R, NY, C, mode, as_stream(stream));
     return simt_xsyn(Oh, fx, Z, B, S1, R, NY, C, as_stream(stream));
 }
 
@@ -262,9 +266,9 @@ int fnm_fourier_layer_fwd(const fnm_plan* p, const float* xin, int act_in, const
     float* Z = cv.take(w.Z);
     const int LY = 2 * p->NY;
     FNM_TRY(fnm_ydft(xin, p->ay, T, (int64_t)p->B * p->P1, p->P2, LY, p->Ci, act_in, p->mode, stream));
-    FNM_TRY(simt_xdft(T, p->ex, xh_save, p->B, p->P1, p->R, p->NY, p->Ci, st));
+    FNM_TRY(fnm_xdft(T, p->ex, xh_save, p->B, p->P1, p->R, p->NY, p->Ci, p->mode, stream));
     FNM_TRY(simt_mix_fwd(xh_save, w0, w1, p->rows_per_w, Oh, p->B, p->R, p->NY, p->Ci, p->Co, st));
-    FNM_TRY(simt_xsyn(Oh, p->fx, Z, p->B, p->S1, p->R, p->NY, p->Co, st));
+    FNM_TRY(fnm_xsyn(Oh, p->fx, Z, p->B, p->S1, p->R, p->NY, p->Co, p->mode, stream));
     return fnm_pointwise_ysyn(wc ? xin : nullptr, act_in, wc, 0, bc, Z, p->by, nullptr, z_out, x_act_out,
                               (int64_t)p->B * p->S1, p->S2, LY, p->Ci, p->Co, p->mode, stream);
 }
@@ -289,13 +293,13 @@ int fnm_fourier_layer_bwd(const fnm_plan* p, const float* g_z, const float* xin,
     const int LY = 2 * p->NY;
     // analysis of g_z (c_l/N folded into byT), A.2 first line
     FNM_TRY(fnm_ydft(g_z, p->byT, Tg, (int64_t)p->B * p->S1, p->S2, LY, p->Co, 0, p->mode, stream));
-    FNM_TRY(simt_xdft(Tg, p->exb, Gh, p->B, p->S1, p->R, p->NY, p->Co, st));
+    FNM_TRY(fnm_xdft(Tg, p->exb, Gh, p->B, p->S1, p->R, p->NY, p->Co, p->mode, stream));
     if (dw0) FNM_TRY(simt_mix_bwd_w(xh_save, Gh, dw0, dw1, p->rows_per_w, p->B, p->R, p->NY, p->Ci, p->Co, st));
     if (wc && (dwc || dbc))
         FNM_TRY(simt_conv_wgrad(g_z, xin, act_in, dwc, dbc, (int64_t)p->B * p->S1 * p->S2, p->Ci, p->Co, partial, st));
     if (g_in) {
         FNM_TRY(simt_mix_bwd_x(Gh, w0, w1, p->rows_per_w, Gxh, p->B, p->R, p->NY, p->Ci, p->Co, st));
-        FNM_TRY(simt_xsyn(Gxh, p->fxb, Zg, p->B, p->P1, p->R, p->NY, p->Ci, st));
+        FNM_TRY(fnm_xsyn(Gxh, p->fxb, Zg, p->B, p->P1, p->R, p->NY, p->Ci, p->mode, stream));
         const float* mul = zin_pre ? zin_pre : (act_in ? xin : nullptr);
         FNM_TRY(fnm_pointwise_ysyn(wc ? g_z : nullptr, 0, wc, 1, nullptr, Zg, p->ayT, mul, g_in, nullptr,
                                    (int64_t)p->B * p->P1, p->P2, LY, p->Co, p->Ci, p->mode, stream));
@@ -326,7 +330,7 @@ int fnm_lfunc_fwd(const fnm_plan* p, const float* xin, int act_in, const float* 
     float* T = cv.take((size_t)p->B * p->P1 * LY * p->Ci);
     float* partial = cv.take(simt_mode_split_workspace(p->R * p->NY, p->B, p->Co) / sizeof(float));
     FNM_TRY(fnm_ydft(xin, p->ay, T, (int64_t)p->B * p->P1, p->P2, LY, p->Ci, act_in, p->mode, stream));
-    FNM_TRY(simt_xdft(T, p->ex, xh_save, p->B, p->P1, p->R, p->NY, p->Ci, st));
+    FNM_TRY(fnm_xdft(T, p->ex, xh_save, p->B, p->P1, p->R, p->NY, p->Ci, p->mode, stream));
     return simt_lfunc_contract(xh_save, w, cc, out, partial, p->B, p->R, p->NY, p->Ci, p->Co, st);
 }
 
@@ -344,7 +348,7 @@ int fnm_lfunc_bwd(const fnm_plan* p, const float* g_out, const float* xin, int a
     if (dw) FNM_TRY(simt_lfunc_bwd_w(g_out, xh_save, cc, dw, p->B, p->R, p->NY, p->Ci, p->Co, st));
     if (g_in) {
         FNM_TRY(simt_lfunc_bwd_x(g_out, w, cc, Gxh, p->B, p->R, p->NY, p->Ci, p->Co, st));
-        FNM_TRY(simt_xsyn(Gxh, p->fxb, Zg, p->B, p->P1, p->R, p->NY, p->Ci, st));
+        FNM_TRY(fnm_xsyn(Gxh, p->fxb, Zg, p->B, p->P1, p->R, p->NY, p->Ci, p->mode, stream));
         const float* mul = zin_pre ? zin_pre : (act_in ? xin : nullptr);
         FNM_TRY(fnm_pointwise_ysyn(nullptr, 0, nullptr, 0, nullptr, Zg, p->ayT, mul, g_in, nullptr,
                                    (int64_t)p->B * p->P1, p->P2, LY, 0, p->Ci, p->mode, stream));
@@ -374,7 +378,7 @@ int fnm_ldec_fwd(const fnm_plan* p, const float* v, const float* w, float* y_out
     float* Z = cv.take((size_t)p->B * p->S1 * LY * p->Co);
     float* Oh = cv.take((size_t)p->R * p->NY * 2 * p->B * p->Co);
     FNM_TRY(simt_ldec_mix(v, w, Oh, p->B, p->R, p->NY, p->Ci, p->Co, st));
-    FNM_TRY(simt_xsyn(Oh, p->fx, Z, p->B, p->S1, p->R, p->NY, p->Co, st));
+    FNM_TRY(fnm_xsyn(Oh, p->fx, Z, p->B, p->S1, p->R, p->NY, p->Co, p->mode, stream));
     return fnm_pointwise_ysyn(nullptr, 0, nullptr, 0, nullptr, Z, p->by, nullptr, y_out, nullptr, (int64_t)p->B * p->S1,
                               p->S2, LY, 0, p->Co, p->mode, stream);
 }
@@ -391,7 +395,7 @@ int fnm_ldec_bwd(const fnm_plan* p, const float* g_y, const float* v, const floa
     float* Gh = cv.take((size_t)p->R * p->NY * 2 * p->B * p->Co);
     float* partial = cv.take(simt_mode_split_workspace(p->R * p->NY, p->B, p->Ci) / sizeof(float));
     FNM_TRY(fnm_ydft(g_y, p->byT, Tg, (int64_t)p->B * p->S1, p->S2, LY, p->Co, 0, p->mode, stream));
-    FNM_TRY(simt_xdft(Tg, p->exb, Gh, p->B, p->S1, p->R, p->NY, p->Co, st));
+    FNM_TRY(fnm_xdft(Tg, p->exb, Gh, p->B, p->S1, p->R, p->NY, p->Co, p->mode, stream));
     if (dw) FNM_TRY(simt_ldec_bwd_w(v, Gh, dw, p->B, p->R, p->NY, p->Ci, p->Co, st));
     if (g_v) FNM_TRY(simt_ldec_bwd_v(Gh, w, g_v, partial, p->B, p->R, p->NY, p->Ci, p->Co, st));
     return FNM_OK;

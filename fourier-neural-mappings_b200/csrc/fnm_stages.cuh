@@ -44,6 +44,10 @@ int tc_available();
 bool tc_ydft_supported(int64_t rows, int P2, int LY, int C);
 int tc_ydft(const float* x, const float* tab, float* T, int64_t rows, int P2, int LY, int C, int act, int mode,
             cudaStream_t st);
+bool tc_xdft_supported(int B, int P1, int R, int NY, int C);
+int tc_xdft(const float* T, const float* ex, float* Xh, int B, int P1, int R, int NY, int C, int mode, cudaStream_t st);
+bool tc_xsyn_supported(int B, int S1, int R, int NY, int C);
+int tc_xsyn(const float* Oh, const float* fx, float* Z, int B, int S1, int R, int NY, int C, int mode, cudaStream_t st);
 bool tc_pointwise_ysyn_supported(int64_t rows, int S2, int LY, int K, int N);
 int tc_pointwise_ysyn(const float* x, int act, const float* wc, int wc_is_kn, const float* bias, const float* Z,
                       const float* by, const float* mul, float* out, float* out_act, int64_t rows, int S2, int LY,

@@ -1,0 +1,383 @@
+// tc_tabgemm -- "apply a small dense table along one axis of a channels-innermost tensor" on tcgen05:
+//
+//     Out[g][m][c] = sum_k tab[m][k] * f(In[g][k][c])          g < G groups, m < Mt, k < Kt, c < C
+//
+// This one kernel is the truncated DFT along y (ydft: g = grid row, k = y, m = (re|im, ky)), the
+// truncated C2C DFT along x (xdft: g = (sample, ky), k = (x, re|im), m = (re|im, kx)) and its inverse
+// (xsyn), forward and backward -- they only differ in the strides of g, k and m (two-level strides
+// cover the (re|im, kx) / (sample, ky) index pairs).
+//
+// Formulation: channels are the MMA M dimension (128 TMEM lanes; C < 128 packs 128/C groups side
+// by side, C > 128 splits into 128-channel blocks), the table rows are N, k is K:
+//     D[lane = (g_local, c)][m] = sum_k A[lane][k] * tab[m][k]
+//   A : activations, read with coalesced 128-byte warp loads (lane = channel), converted in REGISTERS
+//       (optional GELU, hi/lo TF32 split) and written to TMEM with tcgen05.st -- they never touch
+//       shared memory;
+//   B : table slabs [m][32 k] in the canonical K-major SWIZZLE_128B layout, hi and lo parts, either
+//       resident for the whole kernel (ydft) or streamed through a ring (xdft / xsyn);
+//   D : fp32 accumulator in TMEM; epilogue warps tcgen05.ld it and store 128 contiguous bytes per
+//       warp and table row.
+// fp32 parity mode is 3xTF32 (A_hi*B_hi + A_lo*B_hi + A_hi*B_lo); FNM_MODE_TF32 issues A_hi*B_hi only.
+//
+// Warp roles (544 threads, persistent, one CTA per SM):
+//   warps 0-3   epilogue                         warp 4      TMEM allocator + MMA issuer
+//   warps 5-8   table loaders                    warps 9-16  two A-loader warpgroups
+#include "fnm_tc_ptx.cuh"
+
+namespace fnm {
+namespace tc {
+
+constexpr int kTgNwg = 2;                                 // A-loader warpgroups
+constexpr int kTgFirstA = 9;                              // first A-loader warp
+constexpr int kTgThreads = (kTgFirstA + 4 * kTgNwg) * 32;
+constexpr int kTgMaxSlots = 64;
+constexpr int kTgMaxBuf = 8;
+constexpr uint32_t kTgSmemBudget = 200 * 1024;
+
+struct TgArgs {
+    const float* in; const float* tab; float* out;
+    long long gin_s1, gin_s0, k_s1, k_s0, gout_s1, gout_s0, m_s1, m_s0;
+    int gin_div, kin_div, gout_div, mout_div;
+    int C, G, GL, CB, items;
+    int Kt, Mt, nchunks, NT, ntiles, dbl, nbuf, reuse, resident, slots;
+    int act, single_pass, tab_vec4;
+};
+
+__device__ __forceinline__ float ld_stream1(const float* p) {
+    float v;
+    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
+
+__global__ void __launch_bounds__(kTgThreads, 1) tabgemm_tc(const TgArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const uint32_t slot_bytes = (uint32_t)a.NT * 256u;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)a.slots * slot_bytes);
+    uint64_t* tab_full = bars;                                 // [kTgMaxSlots]
+    uint64_t* tab_empty = bars + kTgMaxSlots;                  // [kTgMaxSlots]
+    uint64_t* a_full = bars + 2 * kTgMaxSlots;                 // [kTgMaxBuf]
+    uint64_t* a_empty = a_full + kTgMaxBuf;                    // [kTgMaxBuf]
+    uint64_t* d_full = a_empty + kTgMaxBuf;                    // [2]
+    uint64_t* d_empty = d_full + 2;                            // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d_empty + 2);
+
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < a.slots; ++s) { mbar_init(&tab_full[s], 4); mbar_init(&tab_empty[s], 1); }
+        for (int s = 0; s < a.nbuf; ++s) { mbar_init(&a_full[s], 4); mbar_init(&a_empty[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&d_full[s], 1); mbar_init(&d_empty[s], 4); }
+        fence_barrier_init();
+    }
+    if (warp == 4) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+    const uint32_t dcol0 = (uint32_t)a.nbuf * 64u;
+
+    const int my_items = (a.items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+    if (warp < 4) {
+        // =========================================================================== epilogue
+        const int L = warp * 32 + lane;
+        uint32_t dcount = 0;
+        for (int it = 0; it < my_items; ++it) {
+            const int item = (int)blockIdx.x + it * (int)gridDim.x;
+            int g, c;
+            if (a.C >= 128) { g = item / a.CB; c = (item - g * a.CB) * 128 + L; }
+            else { g = item * a.GL + L / a.C; c = L % a.C; }
+            const bool valid = g < a.G && c < a.C;
+            const int gq = valid ? g / a.gout_div : 0, gr = valid ? g - gq * a.gout_div : 0;
+            float* obase = a.out + (size_t)gq * a.gout_s1 + (size_t)gr * a.gout_s0 + c;
+            for (int nt = 0; nt < a.ntiles; ++nt, ++dcount) {
+                const int dbuf = a.dbl ? (int)(dcount & 1) : 0;
+                const uint32_t dpar = a.dbl ? ((dcount >> 1) & 1) : (dcount & 1);
+                mbar_wait(&d_full[dbuf], dpar);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + dcol0 + (uint32_t)(dbuf * a.NT);
+                const int mlim = min(a.NT, a.Mt - nt * a.NT);
+                for (int c0 = 0; c0 < mlim; c0 += 16) {
+                    uint32_t r[16];
+                    tmem_ld16(taddr + c0, r);
+                    tmem_ld_wait();
+                    if (valid) {
+                        const int m0 = nt * a.NT + c0;
+                        int mq = m0 / a.mout_div, mr = m0 - mq * a.mout_div;
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            if (c0 + j < mlim) obase[(size_t)mq * a.m_s1 + (size_t)mr * a.m_s0] = __uint_as_float(r[j]);
+                            if (++mr == a.mout_div) { mr = 0; ++mq; }
+                        }
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&d_empty[dbuf]);
+            }
+        }
+    } else if (warp == 4) {
+        // =========================================================================== MMA issuer
+        const uint32_t sbase = smem_u32(smem);
+        const uint32_t idesc = make_idesc(128, a.NT);
+        uint32_t qa = 0, qs = 0, dcount = 0;
+        for (int it = 0; it < my_items; ++it) {
+            const uint32_t qa_item = qa;
+            for (int nt = 0; nt < a.ntiles; ++nt, ++dcount) {
+                const int dbuf = a.dbl ? (int)(dcount & 1) : 0;
+                const uint32_t dpar = a.dbl ? ((dcount >> 1) & 1) : (dcount & 1);
+                mbar_wait(&d_empty[dbuf], dpar ^ 1);
+                const uint32_t d = tmem_base + dcol0 + (uint32_t)(dbuf * a.NT);
+                uint32_t accum = 0;
+                for (int ch = 0; ch < a.nchunks; ++ch) {
+                    uint32_t q;
+                    bool first_use, last_use;
+                    if (a.reuse) { q = qa_item + ch; first_use = nt == 0; last_use = nt == a.ntiles - 1; }
+                    else { q = qa++; first_use = last_use = true; }
+                    const uint32_t ab = q % (uint32_t)a.nbuf;
+                    if (first_use) mbar_wait(&a_full[ab], (q / (uint32_t)a.nbuf) & 1);
+                    uint32_t slot, spar;
+                    if (a.resident) { slot = (uint32_t)(nt * a.nchunks + ch); spar = 0; }
+                    else { slot = qs % (uint32_t)a.slots; spar = (qs / (uint32_t)a.slots) & 1; ++qs; }
+                    mbar_wait(&tab_full[slot], spar);
+                    tc_fence_after();
+                    const uint32_t a_hi = tmem_base + ab * 64u, a_lo = a_hi + 32u;
+                    const uint32_t sb = sbase + slot * slot_bytes;
+                    const uint64_t bhi = make_desc(sb), blo = make_desc(sb + (uint32_t)a.NT * 128u);
+                    const int nks = min(4, (a.Kt - ch * 32 + 7) / 8);
+                    for (int ks = 0; ks < nks; ++ks) {
+                        umma_ts(d, a_hi + ks * 8, bhi + 2 * ks, idesc, accum);
+                        accum = 1;
+                        if (!a.single_pass) {
+                            umma_ts(d, a_lo + ks * 8, bhi + 2 * ks, idesc, 1);
+                            umma_ts(d, a_hi + ks * 8, blo + 2 * ks, idesc, 1);
+                        }
+                    }
+                    if (last_use) umma_commit(&a_empty[ab]);
+                    if (!a.resident) umma_commit(&tab_empty[slot]);
+                }
+                umma_commit(&d_full[dbuf]);
+                __syncwarp();
+            }
+            if (a.reuse) qa += (uint32_t)a.nchunks;
+        }
+    } else if (warp < kTgFirstA) {
+        // =========================================================================== table loaders
+        const int tt = threadIdx.x - 5 * 32;                      // 0..127
+        auto fill = [&](int nt, int ch, uint8_t* dst) {
+            uint8_t* hi = dst;
+            uint8_t* lo = dst + (size_t)a.NT * 128;
+            const int k0 = ch * 32;
+            for (int u = tt; u < a.NT * 8; u += 128) {
+                const int r = u >> 3, c4 = u & 7;
+                const int m = nt * a.NT + r, k = k0 + c4 * 4;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (m < a.Mt) {
+                    const float* src = a.tab + (size_t)m * a.Kt + k;
+                    if (a.tab_vec4 && k + 3 < a.Kt) v = __ldg(reinterpret_cast<const float4*>(src));
+                    else {
+                        if (k + 0 < a.Kt) v.x = __ldg(src + 0);
+                        if (k + 1 < a.Kt) v.y = __ldg(src + 1);
+                        if (k + 2 < a.Kt) v.z = __ldg(src + 2);
+                        if (k + 3 < a.Kt) v.w = __ldg(src + 3);
+                    }
+                }
+                store_split4(hi, lo, r, c4, v);
+            }
+            fence_proxy_async();
+            __syncwarp();
+        };
+        if (a.resident) {
+            for (int nt = 0; nt < a.ntiles; ++nt)
+                for (int ch = 0; ch < a.nchunks; ++ch) {
+                    const int slot = nt * a.nchunks + ch;
+                    fill(nt, ch, smem + (size_t)slot * slot_bytes);
+                    if (lane == 0) mbar_arrive(&tab_full[slot]);
+                }
+        } else {
+            uint32_t qs = 0;
+            for (int it = 0; it < my_items; ++it)
+                for (int nt = 0; nt < a.ntiles; ++nt)
+                    for (int ch = 0; ch < a.nchunks; ++ch, ++qs) {
+                        const uint32_t slot = qs % (uint32_t)a.slots;
+                        mbar_wait(&tab_empty[slot], ((qs / (uint32_t)a.slots) & 1) ^ 1);
+                        fill(nt, ch, smem + (size_t)slot * slot_bytes);
+                        if (lane == 0) mbar_arrive(&tab_full[slot]);
+                    }
+        }
+    } else {
+        // =========================================================================== A loaders
+        const int wg = (warp - kTgFirstA) >> 2;
+        const int q4 = warp & 3;                                  // TMEM lane quarter this warp may access
+        const int L = q4 * 32 + lane;
+        const uint32_t lane_base = tmem_base + ((uint32_t)(q4 * 32) << 16);
+        const int npass = a.reuse ? 1 : a.ntiles;
+        uint32_t q = 0;
+        for (int it = 0; it < my_items; ++it) {
+            const int item = (int)blockIdx.x + it * (int)gridDim.x;
+            int g, c;
+            if (a.C >= 128) { g = item / a.CB; c = (item - g * a.CB) * 128 + L; }
+            else { g = item * a.GL + L / a.C; c = L % a.C; }
+            const bool valid = g < a.G && c < a.C;
+            const int gq = valid ? g / a.gin_div : 0, gr = valid ? g - gq * a.gin_div : 0;
+            const float* ibase = a.in + (size_t)gq * a.gin_s1 + (size_t)gr * a.gin_s0 + c;
+            for (int pass = 0; pass < npass; ++pass)
+                for (int ch = 0; ch < a.nchunks; ++ch, ++q) {
+                    if ((int)(q % kTgNwg) != wg) continue;
+                    float v[32];
+                    const int k0 = ch * 32;
+                    int kq = k0 / a.kin_div, kr = k0 - kq * a.kin_div;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        v[j] = (valid && k0 + j < a.Kt) ? ld_stream1(ibase + (size_t)kq * a.k_s1 + (size_t)kr * a.k_s0) : 0.f;
+                        if (++kr == a.kin_div) { kr = 0; ++kq; }
+                    }
+                    const uint32_t ab = q % (uint32_t)a.nbuf;
+                    mbar_wait(&a_empty[ab], ((q / (uint32_t)a.nbuf) & 1) ^ 1);
+                    tc_fence_after();
+                    if (a.act) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = gelu_fast(v[j]);
+                    }
+                    uint32_t w[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        float h, l;
+                        split_tf32(v[j], h, l);
+                        w[j] = __float_as_uint(h);
+                        v[j] = l;
+                    }
+                    tmem_st32(lane_base + ab * 64u, w);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) w[j] = __float_as_uint(v[j]);
+                    tmem_st32(lane_base + ab * 64u + 32u, w);
+                    tmem_st_wait();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&a_full[ab]);
+                }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4) tmem_dealloc(tmem_base, 512);
+}
+
+// tile / buffer configuration; returns false when the shape is outside what the kernel serves
+static bool tg_configure(TgArgs& a) {
+    if (a.Kt < 1 || a.Mt < 1 || a.G < 1) return false;
+    if (!(a.C == 16 || a.C == 32 || a.C == 64 || (a.C >= 128 && a.C % 128 == 0))) return false;
+    a.GL = a.C >= 128 ? 1 : 128 / a.C;
+    a.CB = a.C >= 128 ? a.C / 128 : 1;
+    a.items = a.C >= 128 ? a.G * a.CB : (a.G + a.GL - 1) / a.GL;
+    a.nchunks = (a.Kt + 31) / 32;
+    // pass 0 insists that the A chunks of an item are converted once (reuse); pass 1 accepts re-loading
+    // them for every table tile
+    for (int pass = 0; pass < 2; ++pass)
+        for (int ntiles = 1; ntiles <= 8; ++ntiles) {
+            const int NT = ((a.Mt + ntiles - 1) / ntiles + 15) / 16 * 16;
+            if (NT > 256) continue;
+            for (int dbl = 1; dbl >= 0; --dbl) {
+                const int dcols = NT * (dbl ? 2 : 1);
+                int nbuf = (512 - dcols) / 64;
+                if (nbuf > kTgMaxBuf) nbuf = kTgMaxBuf;
+                if (nbuf < (dbl ? 3 : 2)) continue;
+                const bool reuse = ntiles == 1 || a.nchunks <= nbuf;
+                if (!reuse && pass == 0) continue;
+                const uint32_t slot_bytes = (uint32_t)NT * 256u;
+                const int total = a.nchunks * ntiles;
+                const bool resident = (uint64_t)total * slot_bytes <= kTgSmemBudget && total <= kTgMaxSlots;
+                int slots = total;
+                if (!resident) {
+                    slots = (int)(kTgSmemBudget / slot_bytes);
+                    if (slots > kTgMaxSlots) slots = kTgMaxSlots;
+                    if (slots < 2) continue;
+                }
+                a.NT = NT; a.ntiles = ntiles; a.dbl = dbl; a.nbuf = nbuf; a.reuse = reuse ? 1 : 0;
+                a.resident = resident ? 1 : 0; a.slots = slots;
+                return true;
+            }
+        }
+    return false;
+}
+
+static int tg_launch(TgArgs& a, const char* what, cudaStream_t st) {
+    if (!tg_configure(a)) return fail(FNM_ENOTSUP, "%s: shape not served by the tcgen05 table GEMM", what);
+    a.tab_vec4 = (a.Kt % 4 == 0 && (reinterpret_cast<uintptr_t>(a.tab) & 15) == 0) ? 1 : 0;
+    size_t smem = (size_t)a.slots * a.NT * 256 + 1024 + (2 * kTgMaxSlots + 2 * kTgMaxBuf + 4) * 8 + 16;
+    if (smem < 120 * 1024) smem = 120 * 1024;                    // one CTA per SM (each owns all 512 TMEM columns)
+    static bool attr_set = false;
+    if (!attr_set) {
+        const cudaError_t e = cudaFuncSetAttribute(tabgemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return fail(FNM_ECUDA, "%s: smem attribute: %s", what, cudaGetErrorString(e));
+        attr_set = true;
+    }
+    const int grid = a.items < sm_count() ? a.items : sm_count();
+    {
+        LaunchScope ls(what, st);
+        tabgemm_tc<<<grid, kTgThreads, smem, st>>>(a);
+    }
+    return check_launch(what);
+}
+
+static bool tg_probe(int C, int G, int Kt, int Mt) {
+    if (!tc_enabled()) return false;
+    TgArgs a{};
+    a.C = C; a.G = G; a.Kt = Kt; a.Mt = Mt;
+    return tg_configure(a);
+}
+
+}  // namespace tc
+
+using namespace tc;
+
+bool tc_ydft_supported(int64_t rows, int P2, int LY, int C) {
+    return rows > 0 && rows < (1LL << 30) && tg_probe(C, (int)rows, P2, LY);
+}
+
+int tc_ydft(const float* x, const float* tab, float* T, int64_t rows, int P2, int LY, int C, int act, int mode,
+            cudaStream_t st) {
+    TgArgs a{};
+    a.in = x; a.tab = tab; a.out = T;
+    a.C = C; a.G = (int)rows; a.Kt = P2; a.Mt = LY;
+    a.gin_div = 1 << 30; a.gin_s1 = 0; a.gin_s0 = (long long)P2 * C;
+    a.kin_div = 1 << 30; a.k_s1 = 0; a.k_s0 = C;
+    a.gout_div = 1 << 30; a.gout_s1 = 0; a.gout_s0 = (long long)LY * C;
+    a.mout_div = 1 << 30; a.m_s1 = 0; a.m_s0 = C;
+    a.act = act; a.single_pass = mode == FNM_MODE_TF32;
+    return tg_launch(a, "ydft", st);
+}
+
+// Xh[r][l][ro][b][c] = sum_{x,ri} ex[(ro,r)][(x,ri)] T[b][x][ri][l][c]:  g = (b,l), k = (x,ri), m = (ro,r)
+bool tc_xdft_supported(int B, int P1, int R, int NY, int C) { return tg_probe(C, B * NY, 2 * P1, 2 * R); }
+
+int tc_xdft(const float* T, const float* ex, float* Xh, int B, int P1, int R, int NY, int C, int mode, cudaStream_t st) {
+    TgArgs a{};
+    a.in = T; a.tab = ex; a.out = Xh;
+    a.C = C; a.G = B * NY; a.Kt = 2 * P1; a.Mt = 2 * R;
+    a.gin_div = NY; a.gin_s1 = (long long)P1 * 2 * NY * C; a.gin_s0 = C;          // g = b*NY + l
+    a.kin_div = 1 << 30; a.k_s1 = 0; a.k_s0 = (long long)NY * C;
+    a.gout_div = NY; a.gout_s1 = C; a.gout_s0 = (long long)2 * B * C;
+    a.mout_div = R; a.m_s1 = (long long)B * C; a.m_s0 = (long long)NY * 2 * B * C;   // m = ro*R + r
+    a.act = 0; a.single_pass = mode == FNM_MODE_TF32;
+    return tg_launch(a, "xdft", st);
+}
+
+// Z[b][x][ro][l][c] = sum_{ri,r} fx[(x,ro)][(ri,r)] Oh[r][l][ri][b][c]:  g = (b,l), k = (ri,r), m = (x,ro)
+bool tc_xsyn_supported(int B, int S1, int R, int NY, int C) { return tg_probe(C, B * NY, 2 * R, 2 * S1); }
+
+int tc_xsyn(const float* Oh, const float* fx, float* Z, int B, int S1, int R, int NY, int C, int mode, cudaStream_t st) {
+    TgArgs a{};
+    a.in = Oh; a.tab = fx; a.out = Z;
+    a.C = C; a.G = B * NY; a.Kt = 2 * R; a.Mt = 2 * S1;
+    a.gin_div = NY; a.gin_s1 = C; a.gin_s0 = (long long)2 * B * C;                 // g = b*NY + l
+    a.kin_div = R; a.k_s1 = (long long)B * C; a.k_s0 = (long long)NY * 2 * B * C;   // k = ri*R + r
+    a.gout_div = NY; a.gout_s1 = (long long)S1 * 2 * NY * C; a.gout_s0 = C;
+    a.mout_div = 1 << 30; a.m_s1 = 0; a.m_s0 = (long long)NY * C;
+    a.act = 0; a.single_pass = mode == FNM_MODE_TF32;
+    return tg_launch(a, "xsyn", st);
+}
+
+}  // namespace fnm

@@ -157,9 +157,11 @@ int fnm_counter_inc(int32_t* counter, fnm_stream_t stream);
 int fnm_ydft(const float* x, const float* tab, float* T, int64_t rows, int P2, int LY, int C, int act_in,
              int mode, fnm_stream_t stream);
 /* Xh[r][l][ro][b][c] = sum_{x,ri} ex[(ro,r)][(x,ri)] T[b][x][ri][l][c]   (C2C along x, truncated)   */
-int fnm_xdft(const float* T, const float* ex, float* Xh, int B, int P1, int R, int NY, int C, fnm_stream_t stream);
+int fnm_xdft(const float* T, const float* ex, float* Xh, int B, int P1, int R, int NY, int C, int mode,
+             fnm_stream_t stream);
 /* Z[b][x][ro][l][c] = sum_{ri,r} fx[(x,ro)][(ri,r)] Oh[r][l][ri][b][c]   (inverse C2C along x)       */
-int fnm_xsyn(const float* Oh, const float* fx, float* Z, int B, int S1, int R, int NY, int C, fnm_stream_t stream);
+int fnm_xsyn(const float* Oh, const float* fx, float* Z, int B, int S1, int R, int NY, int C, int mode,
+             fnm_stream_t stream);
 /* compl_mul (shared.py:48-53): Oh[m][.][b][o] = sum_i Xh[m][.][b][i] W[i][o][m]  (complex)           */
 int fnm_mix_fwd(const float* Xh, const float* w0, const float* w1, int rows_per_w, float* Oh,
                 int B, int R, int NY, int Ci, int Co, fnm_stream_t stream);

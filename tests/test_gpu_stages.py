@@ -102,8 +102,8 @@ def test_ydft_xdft_xsyn_roundtrip_stages():
     y = torch.empty(B, P1, P2, C, device=DEV)
     L = lib()
     check(L.fnm_ydft(_p(x), _p(d["ay"]), _p(T), B * P1, P2, LY, C, 0, 0, _stream()))
-    check(L.fnm_xdft(_p(T), _p(d["ex"]), _p(Xh), B, P1, R, NY, C, _stream()))
-    check(L.fnm_xsyn(_p(Xh), _p(d["fx"]), _p(Zt), B, P1, R, NY, C, _stream()))
+    check(L.fnm_xdft(_p(T), _p(d["ex"]), _p(Xh), B, P1, R, NY, C, 0, _stream()))
+    check(L.fnm_xsyn(_p(Xh), _p(d["fx"]), _p(Zt), B, P1, R, NY, C, 0, _stream()))
     check(L.fnm_pointwise_ysyn(None, 0, None, 0, None, _p(Zt), _p(d["by"]), None, _p(y), None, B * P1, P2, LY, 0, C, 0, _stream()))
     xc = x.permute(0, 3, 1, 2).cpu().double()
     xh = torch.fft.rfft2(xc)
@@ -112,6 +112,53 @@ def test_ydft_xdft_xsyn_roundtrip_stages():
     keep[..., P1 - m1:, :m2] = xh[..., P1 - m1:, :m2]
     ref = torch.fft.irfft2(keep, s=(P1, P2)).permute(0, 2, 3, 1)
     assert rel_l2(y, ref) < TOL_FP32
+
+
+TAB_CASES = [
+    # B, P1, P2, R, NY, C                      (table-GEMM stages: ydft / xdft / xsyn)
+    dict(B=3, P1=72, P2=72, R=24, NY=12, C=32),          # config 1
+    dict(B=2, P1=288, P2=288, R=64, NY=32, C=128),       # config 5 (two samples)
+    dict(B=5, P1=1, P2=1152, R=1, NY=16, C=64),          # config 2 (1-D)
+    dict(B=3, P1=248, P2=57, R=24, NY=12, C=32),         # config 3: odd row length, table rows not 16-byte aligned
+    dict(B=2, P1=144, P2=144, R=32, NY=17, C=64),        # config 4 decoder (m2 + 1 columns)
+    dict(B=2, P1=24, P2=40, R=10, NY=7, C=16),           # smoke-test width
+    dict(B=2, P1=20, P2=36, R=6, NY=5, C=20),            # SIMT-only channel count
+    dict(B=1, P1=16, P2=24, R=8, NY=4, C=256),           # two 128-channel blocks
+]
+
+
+@pytest.mark.parametrize("case", TAB_CASES, ids=lambda c: "b{B}_p{P1}x{P2}_r{R}_ny{NY}_c{C}".format(**c))
+@pytest.mark.parametrize("mode", ["fp32", "tf32"])
+def test_table_stages(case, mode):
+    """ydft, xdft and xsyn, each against the float64 contraction its header comment states, with random tables."""
+    torch.manual_seed(2)
+    B, P1, P2, R, NY, C_ = (case[k] for k in ("B", "P1", "P2", "R", "NY", "C"))
+    LY, m = 2 * NY, 0 if mode == "fp32" else 1
+    tol = TOL_FP32 if mode == "fp32" else TOL_TF32
+    L = lib()
+    # ydft, with the GELU on load
+    x = torch.randn(B * P1, P2, C_, device=DEV)
+    tab = torch.randn(LY, P2, device=DEV) / P2 ** 0.5
+    T = torch.full((B * P1, LY, C_), float("nan"), device=DEV)
+    for act in (0, 1):
+        check(L.fnm_ydft(_p(x), _p(tab), _p(T), B * P1, P2, LY, C_, act, m, _stream()), "fnm_ydft")
+        xa = _gelu64(x.double()) if act else x.double()
+        assert rel_l2(T, torch.einsum("ly,ryc->rlc", tab.double(), xa)) < tol
+    # xdft: Xh[r][l][ro][b][c] = sum_{x,ri} ex[(ro,r)][(x,ri)] T[b][x][ri][l][c]
+    T5 = torch.randn(B, P1, 2, NY, C_, device=DEV)
+    ex = torch.randn(2 * R, 2 * P1, device=DEV) / (2 * P1) ** 0.5
+    Xh = torch.full((R, NY, 2, B, C_), float("nan"), device=DEV)
+    check(L.fnm_xdft(_p(T5), _p(ex), _p(Xh), B, P1, R, NY, C_, m, _stream()), "fnm_xdft")
+    ref = torch.einsum("orxi,bxilc->rlobc", ex.double().view(2, R, P1, 2), T5.double())
+    assert rel_l2(Xh, ref) < tol
+    # xsyn: Z[b][x][ro][l][c] = sum_{ri,r} fx[(x,ro)][(ri,r)] Oh[r][l][ri][b][c]
+    S1 = P1 + 3 if P1 > 1 else 1
+    Oh = torch.randn(R, NY, 2, B, C_, device=DEV)
+    fx = torch.randn(2 * S1, 2 * R, device=DEV) / (2 * R) ** 0.5
+    Z = torch.full((B, S1, 2, NY, C_), float("nan"), device=DEV)
+    check(L.fnm_xsyn(_p(Oh), _p(fx), _p(Z), B, S1, R, NY, C_, m, _stream()), "fnm_xsyn")
+    ref = torch.einsum("xoir,rlibc->bxolc", fx.double().view(S1, 2, 2, R), Oh.double())
+    assert rel_l2(Z, ref) < tol
 
 
 def test_gelu_kernels():

@@ -54,6 +54,11 @@ out2 = torch.empty_like(x)
 timeit("pointwise_ysyn fwd +act out (3A)", lambda: check(L.fnm_pointwise_ysyn(p(x), 0, p(wc), 0, p(bias), p(Z), p(tab["by"]), None, p(out), p(out2), rows, P2, LY, C_, C_, 0, st)), 3 * A)
 timeit("pointwise_ysyn bwd (3A)", lambda: check(L.fnm_pointwise_ysyn(p(g), 0, p(wc), 1, None, p(Z), p(tab["ayT"]), p(x), p(out), None, rows, P2, LY, C_, C_, 0, st)), 3 * A)
 timeit("ydft (A + T)", lambda: check(L.fnm_ydft(p(x), p(tab["ay"]), p(T), rows, P2, LY, C_, 1, 0, st)), A + T.numel() * 4)
+timeit("ydft noact (A + T)", lambda: check(L.fnm_ydft(p(x), p(tab["ay"]), p(T), rows, P2, LY, C_, 0, 0, st)), A + T.numel() * 4)
+timeit("ydft noact tf32", lambda: check(L.fnm_ydft(p(x), p(tab["ay"]), p(T), rows, P2, LY, C_, 0, 1, st)), A + T.numel() * 4)
+Xh = torch.empty(R, NY, 2, B, C_, device=dev)
+timeit("xdft (T + Xh)", lambda: check(L.fnm_xdft(p(T), p(tab["ex"]), p(Xh), B, P1, R, NY, C_, 0, st)), (T.numel() + Xh.numel()) * 4)
+timeit("xsyn (Xh + Z)", lambda: check(L.fnm_xsyn(p(Xh), p(tab["fx"]), p(Z), B, P1, R, NY, C_, 0, st)), (Z.numel() + Xh.numel()) * 4)
 ws = torch.empty(L.fnm_conv_wgrad_workspace_bytes(rows * P2, C_, C_), dtype=torch.uint8, device=dev)
 dwc, dbc = torch.empty(C_, C_, device=dev), torch.empty(C_, device=dev)
 timeit("conv_wgrad (2A)", lambda: check(L.fnm_conv_wgrad(p(g), p(x), 1, p(dwc), p(dbc), rows * P2, C_, C_, p(ws), ws.numel(), 0, st)), 2 * A)
