@@ -76,6 +76,18 @@ static int check_plan(const fnm_plan* p, bool need_in, bool need_out) {
     return FNM_OK;
 }
 
+static size_t conv_wgrad_workspace(int64_t npos, int Ci, int Co) {
+    const size_t a = simt_conv_wgrad_workspace(npos, Ci, Co);
+    const size_t b = tc_conv_wgrad_supported(npos, Ci, Co) ? tc_conv_wgrad_workspace(npos, Ci, Co) : 0;
+    return a > b ? a : b;
+}
+
+static int conv_wgrad(const float* g, const float* x, int act, float* dwc, float* dbc, int64_t npos, int Ci, int Co,
+                      float* partial, int mode, cudaStream_t st) {
+    if (tc_conv_wgrad_supported(npos, Ci, Co)) return tc_conv_wgrad(g, x, act, dwc, dbc, npos, Ci, Co, partial, mode, st);
+    return simt_conv_wgrad(g, x, act, dwc, dbc, npos, Ci, Co, partial, st);
+}
+
 struct LayerWs {
     size_t T, Oh, Z, Gh, partial;      // float counts
 };
@@ -89,7 +101,7 @@ static LayerWs layer_ws(const fnm_plan* p) {
     w.Oh = (size_t)p->R * p->NY * 2 * p->B * cmax;        // Oh / Gxh
     w.Z = rows * LY * cmax;
     w.Gh = (size_t)p->R * p->NY * 2 * p->B * cmax;
-    w.partial = simt_conv_wgrad_workspace((int64_t)p->B * p->S1 * p->S2, p->Ci, p->Co) / sizeof(float);
+    w.partial = conv_wgrad_workspace((int64_t)p->B * p->S1 * p->S2, p->Ci, p->Co) / sizeof(float);
     return w;
 }
 
@@ -203,14 +215,13 @@ int fnm_pointwise_ysyn(const float* x, int act_in, const float* wc, int wc_is_kn
                                as_stream(stream));
 }
 
-size_t fnm_conv_wgrad_workspace_bytes(int64_t npos, int Ci, int Co) { return simt_conv_wgrad_workspace(npos, Ci, Co); }
+size_t fnm_conv_wgrad_workspace_bytes(int64_t npos, int Ci, int Co) { return conv_wgrad_workspace(npos, Ci, Co); }
 
 int fnm_conv_wgrad(const float* g, const float* x, int act_in, float* dwc, float* dbc, int64_t npos, int Ci, int Co,
                    void* workspace, size_t workspace_bytes, int mode, fnm_stream_t stream) {
-    (void)mode;
     FNM_REQUIRE(g && x && workspace, "conv_wgrad: NULL pointer");
-    if (workspace_bytes < simt_conv_wgrad_workspace(npos, Ci, Co)) return fail(FNM_EWORKSPACE, "conv_wgrad: workspace too small");
-    return simt_conv_wgrad(g, x, act_in, dwc, dbc, npos, Ci, Co, static_cast<float*>(workspace), as_stream(stream));
+    if (workspace_bytes < conv_wgrad_workspace(npos, Ci, Co)) return fail(FNM_EWORKSPACE, "conv_wgrad: workspace too small");
+    return conv_wgrad(g, x, act_in, dwc, dbc, npos, Ci, Co, static_cast<float*>(workspace), mode, as_stream(stream));
 }
 
 int fnm_gelu_fwd(const float* z, float* y, int64_t n, fnm_stream_t stream) {
@@ -296,7 +307,7 @@ int fnm_fourier_layer_bwd(const fnm_plan* p, const float* g_z, const float* xin,
     FNM_TRY(fnm_xdft(Tg, p->exb, Gh, p->B, p->S1, p->R, p->NY, p->Co, p->mode, stream));
     if (dw0) FNM_TRY(simt_mix_bwd_w(xh_save, Gh, dw0, dw1, p->rows_per_w, p->B, p->R, p->NY, p->Ci, p->Co, st));
     if (wc && (dwc || dbc))
-        FNM_TRY(simt_conv_wgrad(g_z, xin, act_in, dwc, dbc, (int64_t)p->B * p->S1 * p->S2, p->Ci, p->Co, partial, st));
+        FNM_TRY(conv_wgrad(g_z, xin, act_in, dwc, dbc, (int64_t)p->B * p->S1 * p->S2, p->Ci, p->Co, partial, p->mode, st));
     if (g_in) {
         FNM_TRY(simt_mix_bwd_x(Gh, w0, w1, p->rows_per_w, Gxh, p->B, p->R, p->NY, p->Ci, p->Co, st));
         FNM_TRY(fnm_xsyn(Gxh, p->fxb, Zg, p->B, p->P1, p->R, p->NY, p->Ci, p->mode, stream));

@@ -48,6 +48,10 @@ bool tc_xdft_supported(int B, int P1, int R, int NY, int C);
 int tc_xdft(const float* T, const float* ex, float* Xh, int B, int P1, int R, int NY, int C, int mode, cudaStream_t st);
 bool tc_xsyn_supported(int B, int S1, int R, int NY, int C);
 int tc_xsyn(const float* Oh, const float* fx, float* Z, int B, int S1, int R, int NY, int C, int mode, cudaStream_t st);
+bool tc_conv_wgrad_supported(int64_t npos, int Ci, int Co);
+size_t tc_conv_wgrad_workspace(int64_t npos, int Ci, int Co);
+int tc_conv_wgrad(const float* g, const float* x, int act, float* dwc, float* dbc, int64_t npos, int Ci, int Co,
+                  float* partial, int mode, cudaStream_t st);
 bool tc_pointwise_ysyn_supported(int64_t rows, int S2, int LY, int K, int N);
 int tc_pointwise_ysyn(const float* x, int act, const float* wc, int wc_is_kn, const float* bias, const float* Z,
                       const float* by, const float* mul, float* out, float* out_act, int64_t rows, int S2, int LY,

@@ -98,6 +98,30 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32
         "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
         : "memory");
 }
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+        "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+        : "memory");
+}
+// hi/lo TF32 split of 16 values straight into TMEM: hi -> columns [col, col+16), lo -> [col+lo_off, ...)
+__device__ __forceinline__ void split_to_tmem16(uint32_t taddr_hi, uint32_t taddr_lo, const float* v, bool want_lo) {
+    uint32_t w[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        uint32_t h;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(v[j]));
+        w[j] = h;
+    }
+    tmem_st16(taddr_hi, w);
+    if (want_lo) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) w[j] = __float_as_uint(v[j] - __uint_as_float(w[j]));
+        tmem_st16(taddr_lo, w);
+    }
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, version 1):

@@ -19,16 +19,17 @@
 //       warp and table row.
 // fp32 parity mode is 3xTF32 (A_hi*B_hi + A_lo*B_hi + A_hi*B_lo); FNM_MODE_TF32 issues A_hi*B_hi only.
 //
-// Warp roles (544 threads, persistent, one CTA per SM):
+// Warp roles (512 threads = 4 warps per SM sub-partition -> 128 registers; persistent, one CTA per SM):
 //   warps 0-3   epilogue                         warp 4      TMEM allocator + MMA issuer
-//   warps 5-8   table loaders                    warps 9-16  two A-loader warpgroups
+//   warps 5-7   table loaders                    warps 8-15  two A-loader warpgroups
 #include "fnm_tc_ptx.cuh"
 
 namespace fnm {
 namespace tc {
 
-constexpr int kTgNwg = 2;                                 // A-loader warpgroups
-constexpr int kTgFirstA = 9;                              // first A-loader warp
+constexpr int kTgNwg = 2;                                 // A-loader warpgroups, two chunks each: needs nbuf >= 4
+constexpr int kTgTabWarps = 3;
+constexpr int kTgFirstA = 5 + kTgTabWarps;                // first A-loader warp (multiple of 4: TMEM lane quarters)
 constexpr int kTgThreads = (kTgFirstA + 4 * kTgNwg) * 32;
 constexpr int kTgMaxSlots = 64;
 constexpr int kTgMaxBuf = 8;
@@ -65,7 +66,7 @@ __global__ void __launch_bounds__(kTgThreads, 1) tabgemm_tc(const TgArgs a) {
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < a.slots; ++s) { mbar_init(&tab_full[s], 4); mbar_init(&tab_empty[s], 1); }
+        for (int s = 0; s < a.slots; ++s) { mbar_init(&tab_full[s], kTgTabWarps); mbar_init(&tab_empty[s], 1); }
         for (int s = 0; s < a.nbuf; ++s) { mbar_init(&a_full[s], 4); mbar_init(&a_empty[s], 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(&d_full[s], 1); mbar_init(&d_empty[s], 4); }
         fence_barrier_init();
@@ -91,24 +92,45 @@ __global__ void __launch_bounds__(kTgThreads, 1) tabgemm_tc(const TgArgs a) {
             const bool valid = g < a.G && c < a.C;
             const int gq = valid ? g / a.gout_div : 0, gr = valid ? g - gq * a.gout_div : 0;
             float* obase = a.out + (size_t)gq * a.gout_s1 + (size_t)gr * a.gout_s0 + c;
+            const long long m_wrap = a.m_s1 - (long long)a.mout_div * a.m_s0;
             for (int nt = 0; nt < a.ntiles; ++nt, ++dcount) {
                 const int dbuf = a.dbl ? (int)(dcount & 1) : 0;
                 const uint32_t dpar = a.dbl ? ((dcount >> 1) & 1) : (dcount & 1);
                 mbar_wait(&d_full[dbuf], dpar);
                 tc_fence_after();
-                const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + dcol0 + (uint32_t)(dbuf * a.NT);
+                const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + dcol0 + (uint32_t)(dbuf * 2 * a.NT);
                 const int mlim = min(a.NT, a.Mt - nt * a.NT);
                 for (int c0 = 0; c0 < mlim; c0 += 16) {
                     uint32_t r[16];
                     tmem_ld16(taddr + c0, r);
+                    if (!a.single_pass) {                         // + the separately accumulated correction terms
+                        uint32_t rc[16];
+                        tmem_ld16(taddr + a.NT + c0, rc);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(rc[j]));
+                    }
                     tmem_ld_wait();
                     if (valid) {
+                        // pointer walk over the (two-level) m strides: one add per store, no multiplies
                         const int m0 = nt * a.NT + c0;
-                        int mq = m0 / a.mout_div, mr = m0 - mq * a.mout_div;
+                        const int mq = m0 / a.mout_div;
+                        int mr = m0 - mq * a.mout_div;
+                        float* op = obase + (size_t)mq * a.m_s1 + (size_t)mr * a.m_s0;
+                        const int cnt = mlim - c0;
+                        if (a.mout_div >= a.Mt) {
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            if (c0 + j < mlim) obase[(size_t)mq * a.m_s1 + (size_t)mr * a.m_s0] = __uint_as_float(r[j]);
-                            if (++mr == a.mout_div) { mr = 0; ++mq; }
+                            for (int j = 0; j < 16; ++j) {
+                                if (j < cnt) *op = __uint_as_float(r[j]);
+                                op += a.m_s0;
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) {
+                                if (j < cnt) *op = __uint_as_float(r[j]);
+                                op += a.m_s0;
+                                if (++mr == a.mout_div) { mr = 0; op += m_wrap; }
+                            }
                         }
                     }
                 }
@@ -128,7 +150,10 @@ __global__ void __launch_bounds__(kTgThreads, 1) tabgemm_tc(const TgArgs a) {
                 const int dbuf = a.dbl ? (int)(dcount & 1) : 0;
                 const uint32_t dpar = a.dbl ? ((dcount >> 1) & 1) : (dcount & 1);
                 mbar_wait(&d_empty[dbuf], dpar ^ 1);
-                const uint32_t d = tmem_base + dcol0 + (uint32_t)(dbuf * a.NT);
+                // the tensor core accumulates with truncation (measured: ~1.9e-8 relative error per MMA added
+                // to an accumulator), so the hi*hi products go to their own accumulator and the two
+                // correction passes, 2^-11 smaller, to a second one: the long chain is three times shorter
+                const uint32_t d = tmem_base + dcol0 + (uint32_t)(dbuf * 2 * a.NT), dc = d + (uint32_t)a.NT;
                 uint32_t accum = 0;
                 for (int ch = 0; ch < a.nchunks; ++ch) {
                     uint32_t q;
@@ -148,11 +173,11 @@ __global__ void __launch_bounds__(kTgThreads, 1) tabgemm_tc(const TgArgs a) {
                     const int nks = min(4, (a.Kt - ch * 32 + 7) / 8);
                     for (int ks = 0; ks < nks; ++ks) {
                         umma_ts(d, a_hi + ks * 8, bhi + 2 * ks, idesc, accum);
-                        accum = 1;
                         if (!a.single_pass) {
-                            umma_ts(d, a_lo + ks * 8, bhi + 2 * ks, idesc, 1);
-                            umma_ts(d, a_hi + ks * 8, blo + 2 * ks, idesc, 1);
+                            umma_ts(dc, a_lo + ks * 8, bhi + 2 * ks, idesc, accum);
+                            umma_ts(dc, a_hi + ks * 8, blo + 2 * ks, idesc, 1);
                         }
+                        accum = 1;
                     }
                     if (last_use) umma_commit(&a_empty[ab]);
                     if (!a.resident) umma_commit(&tab_empty[slot]);
@@ -164,26 +189,37 @@ __global__ void __launch_bounds__(kTgThreads, 1) tabgemm_tc(const TgArgs a) {
         }
     } else if (warp < kTgFirstA) {
         // =========================================================================== table loaders
-        const int tt = threadIdx.x - 5 * 32;                      // 0..127
+        const int tt = threadIdx.x - 5 * 32;                      // 0..95
         auto fill = [&](int nt, int ch, uint8_t* dst) {
             uint8_t* hi = dst;
             uint8_t* lo = dst + (size_t)a.NT * 128;
             const int k0 = ch * 32;
-            for (int u = tt; u < a.NT * 8; u += 128) {
-                const int r = u >> 3, c4 = u & 7;
-                const int m = nt * a.NT + r, k = k0 + c4 * 4;
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (m < a.Mt) {
-                    const float* src = a.tab + (size_t)m * a.Kt + k;
-                    if (a.tab_vec4 && k + 3 < a.Kt) v = __ldg(reinterpret_cast<const float4*>(src));
-                    else {
-                        if (k + 0 < a.Kt) v.x = __ldg(src + 0);
-                        if (k + 1 < a.Kt) v.y = __ldg(src + 1);
-                        if (k + 2 < a.Kt) v.z = __ldg(src + 2);
-                        if (k + 3 < a.Kt) v.w = __ldg(src + 3);
+            // batches of 8 independent 16-byte loads per thread (the table is L2 resident: latency, not
+            // bandwidth, is what a one-load-at-a-time loop would pay)
+            for (int u0 = 0; u0 < a.NT * 8; u0 += kTgTabWarps * 32 * 8) {
+                float4 v[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int u = u0 + tt + j * kTgTabWarps * 32;
+                    const int r = u >> 3, c4 = u & 7;
+                    const int m = nt * a.NT + r, k = k0 + c4 * 4;
+                    v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (u < a.NT * 8 && m < a.Mt) {
+                        const float* src = a.tab + (size_t)m * a.Kt + k;
+                        if (a.tab_vec4 && k + 3 < a.Kt) v[j] = __ldg(reinterpret_cast<const float4*>(src));
+                        else {
+                            if (k + 0 < a.Kt) v[j].x = __ldg(src + 0);
+                            if (k + 1 < a.Kt) v[j].y = __ldg(src + 1);
+                            if (k + 2 < a.Kt) v[j].z = __ldg(src + 2);
+                            if (k + 3 < a.Kt) v[j].w = __ldg(src + 3);
+                        }
                     }
                 }
-                store_split4(hi, lo, r, c4, v);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int u = u0 + tt + j * kTgTabWarps * 32;
+                    if (u < a.NT * 8) store_split4(hi, lo, u >> 3, u & 7, v[j]);
+                }
             }
             fence_proxy_async();
             __syncwarp();
@@ -212,9 +248,14 @@ __global__ void __launch_bounds__(kTgThreads, 1) tabgemm_tc(const TgArgs a) {
         const int q4 = warp & 3;                                  // TMEM lane quarter this warp may access
         const int L = q4 * 32 + lane;
         const uint32_t lane_base = tmem_base + ((uint32_t)(q4 * 32) << 16);
-        const int npass = a.reuse ? 1 : a.ntiles;
-        uint32_t q = 0;
-        for (int it = 0; it < my_items; ++it) {
+        const int per_item = (a.reuse ? 1 : a.ntiles) * a.nchunks;
+        const uint32_t total = (uint32_t)my_items * (uint32_t)per_item;
+        const long long k_wrap = a.k_s1 - (long long)a.kin_div * a.k_s0;
+
+        // chunk q of this CTA's sequence -> 32 streaming loads (lane = channel, register = k)
+        auto load = [&](float (&v)[32], uint32_t q) {
+            const int it = (int)(q / (uint32_t)per_item);
+            const int ch = (int)(q - (uint32_t)it * per_item) % a.nchunks;
             const int item = (int)blockIdx.x + it * (int)gridDim.x;
             int g, c;
             if (a.C >= 128) { g = item / a.CB; c = (item - g * a.CB) * 128 + L; }
@@ -222,41 +263,54 @@ __global__ void __launch_bounds__(kTgThreads, 1) tabgemm_tc(const TgArgs a) {
             const bool valid = g < a.G && c < a.C;
             const int gq = valid ? g / a.gin_div : 0, gr = valid ? g - gq * a.gin_div : 0;
             const float* ibase = a.in + (size_t)gq * a.gin_s1 + (size_t)gr * a.gin_s0 + c;
-            for (int pass = 0; pass < npass; ++pass)
-                for (int ch = 0; ch < a.nchunks; ++ch, ++q) {
-                    if ((int)(q % kTgNwg) != wg) continue;
-                    float v[32];
-                    const int k0 = ch * 32;
-                    int kq = k0 / a.kin_div, kr = k0 - kq * a.kin_div;
+            const int k0 = ch * 32;
+            const int kq = k0 / a.kin_div;
+            int kr = k0 - kq * a.kin_div;
+            const float* p = ibase + (size_t)kq * a.k_s1 + (size_t)kr * a.k_s0;
+            const int klim = valid ? a.Kt - k0 : 0;
+            if (a.kin_div >= a.Kt) {                              // uniform stride: one add per load
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        v[j] = (valid && k0 + j < a.Kt) ? ld_stream1(ibase + (size_t)kq * a.k_s1 + (size_t)kr * a.k_s0) : 0.f;
-                        if (++kr == a.kin_div) { kr = 0; ++kq; }
-                    }
-                    const uint32_t ab = q % (uint32_t)a.nbuf;
-                    mbar_wait(&a_empty[ab], ((q / (uint32_t)a.nbuf) & 1) ^ 1);
-                    tc_fence_after();
-                    if (a.act) {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] = gelu_fast(v[j]);
-                    }
-                    uint32_t w[32];
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        float h, l;
-                        split_tf32(v[j], h, l);
-                        w[j] = __float_as_uint(h);
-                        v[j] = l;
-                    }
-                    tmem_st32(lane_base + ab * 64u, w);
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) w[j] = __float_as_uint(v[j]);
-                    tmem_st32(lane_base + ab * 64u + 32u, w);
-                    tmem_st_wait();
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&a_full[ab]);
+                for (int j = 0; j < 32; ++j) {
+                    v[j] = j < klim ? ld_stream1(p) : 0.f;
+                    p += a.k_s0;
                 }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    v[j] = j < klim ? ld_stream1(p) : 0.f;
+                    p += a.k_s0;
+                    if (++kr == a.kin_div) { kr = 0; p += k_wrap; }
+                }
+            }
+        };
+        auto process = [&](float (&v)[32], uint32_t q) {
+            const uint32_t ab = q % (uint32_t)a.nbuf;
+            mbar_wait(&a_empty[ab], ((q / (uint32_t)a.nbuf) & 1) ^ 1);
+            tc_fence_after();
+            if (a.act) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = gelu_fast(v[j]);
+            }
+            const uint32_t tb = lane_base + ab * 64u;
+            split_to_tmem16(tb, tb + 32u, v, !a.single_pass);
+            split_to_tmem16(tb + 16u, tb + 48u, v + 16, !a.single_pass);
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&a_full[ab]);
+        };
+
+        // each warpgroup takes PAIRS of consecutive chunks: 64 loads per thread are issued in one batch
+        // (2 warpgroups x 128 threads x 256 B = 64 KB in flight per SM), then both chunks are converted.
+        // (Prefetching across loop iterations instead makes the consumer wait on the scoreboard that also
+        // tracks the younger loads, which serialises everything -- measured 1.6x slower.)
+        float va[32], vb[32];
+        for (uint32_t q = 2u * (uint32_t)wg; q < total; q += 2u * kTgNwg) {
+            load(va, q);
+            const bool two = q + 1 < total;
+            if (two) load(vb, q + 1);
+            process(va, q);
+            if (two) process(vb, q + 1);
         }
     }
 
@@ -276,14 +330,14 @@ static bool tg_configure(TgArgs& a) {
     // pass 0 insists that the A chunks of an item are converted once (reuse); pass 1 accepts re-loading
     // them for every table tile
     for (int pass = 0; pass < 2; ++pass)
-        for (int ntiles = 1; ntiles <= 8; ++ntiles) {
+        for (int ntiles = 1; ntiles <= 16; ++ntiles) {
             const int NT = ((a.Mt + ntiles - 1) / ntiles + 15) / 16 * 16;
-            if (NT > 256) continue;
+            if (NT > 128) continue;
             for (int dbl = 1; dbl >= 0; --dbl) {
-                const int dcols = NT * (dbl ? 2 : 1);
+                const int dcols = 2 * NT * (dbl ? 2 : 1);          // main + correction accumulator
                 int nbuf = (512 - dcols) / 64;
                 if (nbuf > kTgMaxBuf) nbuf = kTgMaxBuf;
-                if (nbuf < (dbl ? 3 : 2)) continue;
+                if (nbuf < 2 * kTgNwg) continue;                  // mbarrier parity safety of the pair schedule
                 const bool reuse = ntiles == 1 || a.nchunks <= nbuf;
                 if (!reuse && pass == 0) continue;
                 const uint32_t slot_bytes = (uint32_t)NT * 256u;

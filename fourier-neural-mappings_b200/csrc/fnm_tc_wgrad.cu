@@ -1,0 +1,295 @@
+// tc_conv_wgrad -- gradient of the 1x1 "w" convolution on tcgen05 (3xTF32):
+//
+//     dWc[o][i] = sum_pos g[pos][o] * f(x[pos][i])        dbc[o] = sum_pos g[pos][o]
+//
+// Both operands are activation-sized and arrive as [pos][channel] (channel contiguous), so either
+// becomes a K-major operand through ONE thread per channel that reads 32 consecutive positions with
+// coalesced warp loads: the 32 registers are that channel's K-row.
+//     A = g^T  : hi/lo TF32 split in registers, written to TMEM with tcgen05.st (lanes = o)
+//     B = x^T  : row i of a SWIZZLE_128B K-major slab, written twice: raw and x_lo = x - trunc(x)
+//     D[o][i] += g_hi*x_raw   (main)        Dc[o][i] += g_lo*x_raw + g_hi*x_lo   (corrections)
+// The tensor core reads an fp32 shared-memory operand as TF32 by ignoring its low 13 mantissa bits,
+// so the raw slab IS trunc(x) and no conversion pass over x is needed.  dbc falls out of the same
+// registers (running sum per channel).
+//
+// Accuracy: the tensor core adds into its fp32 accumulator with truncation; measured on B200 the
+// relative error grows by ~1.9e-8 per MMA accumulated, i.e. 1.3e-4 over the 6 700 MMAs a CTA would
+// chain at config 5.  So (a) the correction passes, 2^-11 smaller, have their own accumulator, and
+// (b) the main accumulator is double-buffered and FLUSHED every kCwSegChunks chunks: the epilogue
+// warpgroup adds it (round-to-nearest FADD) into an fp32 accumulator in shared memory while the next
+// segment accumulates into the other TMEM buffer.  Chains are 4*kCwSegChunks = 64 MMAs (1.2e-6).
+//
+// Every CTA owns a contiguous range of 32-position chunks and writes its partial D / db to the
+// workspace; conv_wgrad_tc_reduce adds the partials up (deterministic).
+//
+// Warps: 0-7 two loader warpgroups (each thread holds the g AND x K-rows of its channel: 64 KB in
+// flight per SM), 8-11 flush/epilogue warpgroup, 12 MMA issuer.  13 warps -> 128 registers.
+#include "fnm_tc_ptx.cuh"
+
+namespace fnm {
+namespace tc {
+
+constexpr int kCwLoaderWgs = 2;
+constexpr int kCwStages = 2;                               // >= loader warpgroups (mbarrier parity safety)
+constexpr int kCwSegChunks = 16;
+constexpr int kCwMmaWarp = 12;
+constexpr int kCwThreads = 13 * 32;
+constexpr uint32_t kCwStageBytes = 32768;                  // raw slab 16 KB + lo slab 16 KB
+constexpr uint32_t kCwAccBytes = 65536;                    // fp32 [128 cols][128 lanes]
+
+struct CwArgs {
+    const float* g; const float* x; float* part;
+    long long npos;
+    int Ci, Co, act, single_pass;
+    long long nchunks;            // total 32-position chunks
+    long long per;                // chunks per CTA
+};
+
+__device__ __forceinline__ float ld_stream_f(const float* p) {
+    float v;
+    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
+
+// per-CTA partial layout (floats): D[Co][Ci], db[kCwLoaderWgs][Co]
+__host__ __device__ inline size_t cw_part_floats(int Ci, int Co) { return (size_t)Ci * Co + (size_t)kCwLoaderWgs * Co; }
+
+__global__ void __launch_bounds__(kCwThreads, 1) conv_wgrad_tc(const CwArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    float* acc = reinterpret_cast<float*>(smem + kCwStages * kCwStageBytes);            // [col i][lane o]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kCwStages * kCwStageBytes + kCwAccBytes);
+    uint64_t* full = bars;                         // [kCwStages]  the 4 warps of the loading warpgroup
+    uint64_t* empty = bars + kCwStages;            // [kCwStages]
+    uint64_t* seg_full = bars + 2 * kCwStages;     // [2]  main accumulator buffer ready to flush
+    uint64_t* seg_empty = seg_full + 2;            // [2]  flushed (4 epilogue warps)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(seg_empty + 2);
+
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kCwStages; ++s) { mbar_init(&full[s], 4); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&seg_full[s], 1); mbar_init(&seg_empty[s], 4); }
+        fence_barrier_init();
+    }
+    if (warp == kCwMmaWarp) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+    // TMEM columns: [0,128) main buffer 0, [128,256) main buffer 1, [256,384) corrections, [384,512) g stages
+    const uint32_t kCorr = 256u, kStage0 = 384u;
+
+    const long long c_begin = (long long)blockIdx.x * a.per;
+    long long c_end = c_begin + a.per;
+    if (c_end > a.nchunks) c_end = a.nchunks;
+    const int n = c_end > c_begin ? (int)(c_end - c_begin) : 0;
+    const int nseg = (n + kCwSegChunks - 1) / kCwSegChunks;
+    float* part = a.part + (size_t)blockIdx.x * cw_part_floats(a.Ci, a.Co);
+
+    if (warp == kCwMmaWarp) {
+        // ======================================================================= MMA issuer
+        const uint32_t sbase = smem_u32(smem);
+        const uint32_t idesc = make_idesc(128, a.Ci);
+        for (int q = 0; q < n; ++q) {
+            const int s = q % kCwStages;
+            const int seg = q / kCwSegChunks, qs = q - seg * kCwSegChunks, db = seg & 1;
+            if (qs == 0) {
+                mbar_wait(&seg_empty[db], (uint32_t)(((seg >> 1) & 1) ^ 1));
+                tc_fence_after();
+            }
+            mbar_wait(&full[s], (uint32_t)((q / kCwStages) & 1));
+            tc_fence_after();
+            const uint32_t dmain = tmem_base + 128u * db, dcorr = tmem_base + kCorr;
+            const uint32_t g_hi = tmem_base + kStage0 + 64u * s, g_lo = g_hi + 32u;
+            const uint64_t bx = make_desc(sbase + s * kCwStageBytes), bxl = make_desc(sbase + s * kCwStageBytes + 16384u);
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+                umma_ts(dmain, g_hi + ks * 8, bx + 2 * ks, idesc, (qs > 0 || ks > 0) ? 1u : 0u);
+                if (!a.single_pass) {
+                    umma_ts(dcorr, g_lo + ks * 8, bx + 2 * ks, idesc, (q > 0 || ks > 0) ? 1u : 0u);
+                    umma_ts(dcorr, g_hi + ks * 8, bxl + 2 * ks, idesc, 1);
+                }
+            }
+            umma_commit(&empty[s]);
+            if (qs == kCwSegChunks - 1 || q == n - 1) umma_commit(&seg_full[db]);
+            __syncwarp();
+        }
+    } else if (warp < 4 * kCwLoaderWgs) {
+        // ======================================================================= loaders: warpgroup wg takes chunks q = wg, wg+2, ...
+        const int wg = warp >> 2;
+        const int q4 = warp & 3;
+        const int ch = q4 * 32 + lane;                             // channel = TMEM lane (g) = smem row (x)
+        const bool g_ok = ch < a.Co, x_ok = ch < a.Ci;
+        const uint32_t lane_base = tmem_base + ((uint32_t)(q4 * 32) << 16) + kStage0;
+        float dbsum = 0.f;
+
+        for (int q = wg; q < n; q += kCwLoaderWgs) {
+            const int s = q % kCwStages;
+            const long long pos0 = (c_begin + q) * 32;
+            float vg[32], vx[32];
+            {
+                const float* gs = a.g + (size_t)pos0 * a.Co + ch;
+                const float* xs = a.x + (size_t)pos0 * a.Ci + ch;
+                const int lim = (int)((a.npos - pos0) < 32 ? (a.npos - pos0) : 32);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) vg[j] = (g_ok && j < lim) ? ld_stream_f(gs + (size_t)j * a.Co) : 0.f;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) vx[j] = (x_ok && j < lim) ? ld_stream_f(xs + (size_t)j * a.Ci) : 0.f;
+            }
+            mbar_wait(&empty[s], (uint32_t)(((q / kCwStages) & 1) ^ 1));
+            tc_fence_after();
+            uint8_t* bx = smem + s * kCwStageBytes;
+            const uint32_t tb = lane_base + 64u * s;
+            // g: running bias-gradient sum, hi/lo split to TMEM
+#pragma unroll
+            for (int j = 0; j < 32; ++j) dbsum += vg[j];
+            split_to_tmem16(tb, tb + 32u, vg, !a.single_pass);
+            split_to_tmem16(tb + 16u, tb + 48u, vg + 16, !a.single_pass);
+            // x: optional GELU, then the raw K-row and its truncation remainder
+            if (a.act) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) vx[j] = gelu_fast(vx[j]);
+            }
+            if (x_ok) {
+#pragma unroll
+                for (int c4 = 0; c4 < 8; ++c4) {
+                    const uint32_t off = swz(ch, c4);
+                    const float4 v = make_float4(vx[4 * c4], vx[4 * c4 + 1], vx[4 * c4 + 2], vx[4 * c4 + 3]);
+                    *reinterpret_cast<float4*>(bx + off) = v;
+                    if (!a.single_pass) {
+                        float4 l;
+                        l.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
+                        l.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
+                        l.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xffffe000u);
+                        l.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
+                        *reinterpret_cast<float4*>(bx + 16384 + off) = l;
+                    }
+                }
+            }
+            tmem_st_wait();
+            tc_fence_before();
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&full[s]);
+        }
+        if (g_ok) part[(size_t)a.Ci * a.Co + (size_t)wg * a.Co + ch] = dbsum;
+    } else {
+        // ======================================================================= flush / epilogue warpgroup
+        const int q4 = warp & 3;
+        const int o = q4 * 32 + lane;                              // TMEM lane = output channel
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(q4 * 32) << 16);
+        for (int seg = 0; seg < nseg; ++seg) {
+            const int db = seg & 1;
+            mbar_wait(&seg_full[db], (uint32_t)((seg >> 1) & 1));
+            tc_fence_after();
+            const bool last = seg == nseg - 1;
+            for (int c0 = 0; c0 < a.Ci; c0 += 16) {
+                uint32_t r[16];
+                tmem_ld16(lane_addr + 128u * db + c0, r);
+                tmem_ld_wait();
+                float v[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+                if (seg > 0) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] += acc[(c0 + j) * 128 + o];
+                }
+                if (!last) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) acc[(c0 + j) * 128 + o] = v[j];
+                } else {
+                    if (!a.single_pass) {
+                        tmem_ld16(lane_addr + kCorr + c0, r);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) v[j] += __uint_as_float(r[j]);
+                    }
+                    if (o < a.Co) {
+#pragma unroll
+                        for (int j4 = 0; j4 < 4; ++j4)
+                            *reinterpret_cast<float4*>(part + (size_t)o * a.Ci + c0 + 4 * j4) =
+                                make_float4(v[4 * j4], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]);
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&seg_empty[db]);
+        }
+        if (nseg == 0 && o < a.Co) {
+            for (int c0 = 0; c0 < a.Ci; c0 += 4)
+                *reinterpret_cast<float4*>(part + (size_t)o * a.Ci + c0) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == kCwMmaWarp) tmem_dealloc(tmem_base, 512);
+}
+
+__global__ void conv_wgrad_tc_reduce(const float* __restrict__ part, int nparts, int Ci, int Co, float* __restrict__ dwc,
+                                     float* __restrict__ dbc) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = cw_part_floats(Ci, Co);
+    if (j < Co * Ci) {
+        float s = 0.f;
+        for (int k = 0; k < nparts; ++k) s += part[(size_t)k * stride + j];
+        if (dwc) dwc[j] = s;
+    } else if (j < Co * Ci + Co) {
+        const int o = j - Co * Ci;
+        float s = 0.f;
+        for (int k = 0; k < nparts; ++k) {
+            const float* p = part + (size_t)k * stride + (size_t)Ci * Co;
+            for (int w = 0; w < kCwLoaderWgs; ++w) s += p[(size_t)w * Co + o];
+        }
+        if (dbc) dbc[o] = s;
+    }
+}
+
+static int cw_grid(int64_t npos) {
+    const int64_t chunks = (npos + 31) / 32;
+    return (int)(chunks < sm_count() ? chunks : sm_count());
+}
+
+}  // namespace tc
+
+using namespace tc;
+
+bool tc_conv_wgrad_supported(int64_t npos, int Ci, int Co) {
+    if (!tc_enabled()) return false;
+    return npos >= 4096 && Ci % 16 == 0 && Co % 16 == 0 && Ci >= 16 && Co >= 16 && Ci <= 128 && Co <= 128;
+}
+
+size_t tc_conv_wgrad_workspace(int64_t npos, int Ci, int Co) {
+    return align_up((size_t)cw_grid(npos) * cw_part_floats(Ci, Co) * sizeof(float), 256);
+}
+
+int tc_conv_wgrad(const float* g, const float* x, int act, float* dwc, float* dbc, int64_t npos, int Ci, int Co,
+                  float* partial, int mode, cudaStream_t st) {
+    CwArgs a{};
+    a.g = g; a.x = x; a.part = partial; a.npos = npos; a.Ci = Ci; a.Co = Co; a.act = act;
+    a.single_pass = mode == FNM_MODE_TF32;
+    a.nchunks = (npos + 31) / 32;
+    const int grid = cw_grid(npos);
+    a.per = (a.nchunks + grid - 1) / grid;
+    static bool attr_set = false;
+    const size_t smem = kCwStages * kCwStageBytes + kCwAccBytes + 2048;   // > half the SM: one CTA per SM owns the TMEM
+    if (!attr_set) {
+        const cudaError_t e = cudaFuncSetAttribute(conv_wgrad_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return fail(FNM_ECUDA, "conv_wgrad: smem attribute: %s", cudaGetErrorString(e));
+        attr_set = true;
+    }
+    {
+        LaunchScope ls("conv_wgrad", st);
+        conv_wgrad_tc<<<grid, kCwThreads, smem, st>>>(a);
+    }
+    FNM_TRY(check_launch("conv_wgrad"));
+    const int count = Co * Ci + Co;
+    {
+        LaunchScope ls("conv_wgrad_reduce", st);
+        conv_wgrad_tc_reduce<<<(count + 255) / 256, 256, 0, st>>>(partial, grid, Ci, Co, dwc, dbc);
+    }
+    return check_launch("conv_wgrad_reduce");
+}
+
+}  // namespace fnm

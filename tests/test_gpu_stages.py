@@ -161,6 +161,26 @@ def test_table_stages(case, mode):
     assert rel_l2(Z, ref) < tol
 
 
+@pytest.mark.parametrize("npos,Ci,Co,act", [(72 * 72 * 3, 32, 32, 1), (288 * 150, 128, 128, 0), (288 * 37 + 5, 128, 128, 1),
+                                            (1152 * 9, 64, 64, 1), (57 * 248, 32, 48, 0), (3000, 20, 20, 1)])
+@pytest.mark.parametrize("mode", ["fp32", "tf32"])
+def test_conv_wgrad(npos, Ci, Co, act, mode):
+    """dWc[o][i] = sum_pos g[pos][o] f(x[pos][i]), dbc[o] = sum_pos g[pos][o] against float64."""
+    torch.manual_seed(3)
+    g = torch.randn(npos, Co, device=DEV)
+    x = torch.randn(npos, Ci, device=DEV) + 0.3
+    L = lib()
+    ws = torch.empty(L.fnm_conv_wgrad_workspace_bytes(npos, Ci, Co), dtype=torch.uint8, device=DEV)
+    dwc = torch.full((Co, Ci), float("nan"), device=DEV)
+    dbc = torch.full((Co,), float("nan"), device=DEV)
+    check(L.fnm_conv_wgrad(_p(g), _p(x), act, _p(dwc), _p(dbc), npos, Ci, Co, _p(ws), ws.numel(),
+                           0 if mode == "fp32" else 1, _stream()), "fnm_conv_wgrad")
+    xa = _gelu64(x.double()) if act else x.double()
+    tol = TOL_FP32 if mode == "fp32" else TOL_TF32
+    assert rel_l2(dwc, g.double().t() @ xa) < tol
+    assert rel_l2(dbc, g.double().sum(0)) < 1e-5
+
+
 def test_gelu_kernels():
     z = torch.randn(100003, device=DEV) * 3
     g = torch.randn_like(z)

@@ -61,6 +61,7 @@ timeit("xdft (T + Xh)", lambda: check(L.fnm_xdft(p(T), p(tab["ex"]), p(Xh), B, P
 timeit("xsyn (Xh + Z)", lambda: check(L.fnm_xsyn(p(Xh), p(tab["fx"]), p(Z), B, P1, R, NY, C_, 0, st)), (Z.numel() + Xh.numel()) * 4)
 ws = torch.empty(L.fnm_conv_wgrad_workspace_bytes(rows * P2, C_, C_), dtype=torch.uint8, device=dev)
 dwc, dbc = torch.empty(C_, C_, device=dev), torch.empty(C_, device=dev)
+timeit("conv_wgrad noact (2A)", lambda: check(L.fnm_conv_wgrad(p(g), p(x), 0, p(dwc), p(dbc), rows * P2, C_, C_, p(ws), ws.numel(), 0, st)), 2 * A)
 timeit("conv_wgrad (2A)", lambda: check(L.fnm_conv_wgrad(p(g), p(x), 1, p(dwc), p(dbc), rows * P2, C_, C_, p(ws), ws.numel(), 0, st)), 2 * A)
 y = torch.empty_like(x)
 timeit("torch copy (2A) reference", lambda: y.copy_(x), 2 * A)
