@@ -208,6 +208,8 @@ int fnm_pointwise_ysyn(const float* x, int act_in, const float* wc, int wc_is_kn
     FNM_REQUIRE(Z && by && out, "pointwise_ysyn: NULL pointer");
     FNM_REQUIRE(rows >= 0 && S2 > 0 && LY > 0 && N > 0 && K >= 0, "pointwise_ysyn: bad extents");
     FNM_REQUIRE((x == nullptr) == (wc == nullptr) || K == 0, "pointwise_ysyn: x and wc must be given together");
+    if (tc_pw2_supported(rows, S2, LY, (x && wc) ? K : 0, N, (x && wc) ? act_in : 0, (x && wc) ? x : nullptr, Z, by))
+        return tc_pw2(x, wc, wc_is_kn, bias, Z, by, mul_gelu_grad_of, out, out_act, rows, S2, LY, K, N, mode, as_stream(stream));
     if (tc_pointwise_ysyn_supported(rows, S2, LY, (x && wc) ? K : 0, N))
         return tc_pointwise_ysyn(x, act_in, wc, wc_is_kn, bias, Z, by, mul_gelu_grad_of, out, out_act, rows, S2, LY, K, N,
                                  mode, as_stream(stream));

@@ -151,9 +151,14 @@ __device__ __forceinline__ float4 ld_stream4(const float* p) {
 // exact-erf GELU to ~1e-7 absolute: erf via Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7) on the MUFU
 // pipe (one rcp, one ex2) -- the libdevice erff costs ~3x the instructions and is branchy.  The
 // absolute error of x*Phi(x) stays below 1e-7*|x|, two orders under the 1e-5 parity budget.
+__device__ __forceinline__ float rcp_fast(float x) {          // MUFU.RCP (1 ulp); __frcp_rn expands to a fix-up sequence with a slow-path call
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
 __device__ __forceinline__ float gelu_fast(float x) {
     const float z = fabsf(x) * 0.70710678118654752440f;
-    const float tt = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+    const float tt = rcp_fast(fmaf(0.3275911f, z, 1.0f));
     float p = fmaf(1.061405429f, tt, -1.453152027f);
     p = fmaf(p, tt, 1.421413741f);
     p = fmaf(p, tt, -0.284496736f);
@@ -166,7 +171,7 @@ __device__ __forceinline__ float gelu_fast(float x) {
 // GELU'(x) = Phi(x) + x phi(x) with the same erf approximation; exp(-x^2/2) is shared by both terms
 __device__ __forceinline__ float gelu_grad_fast(float x) {
     const float z = fabsf(x) * 0.70710678118654752440f;
-    const float tt = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+    const float tt = rcp_fast(fmaf(0.3275911f, z, 1.0f));
     float p = fmaf(1.061405429f, tt, -1.453152027f);
     p = fmaf(p, tt, 1.421413741f);
     p = fmaf(p, tt, -0.284496736f);

@@ -1,0 +1,524 @@
+// tc_pw2 -- the fused "1x1 conv + inverse DFT along y + bias (+ GELU' multiply) (+ GELU copy)" pass on
+// TMA + tcgen05 (3xTF32).  It reads an activation once and writes one once:
+//
+//   out[row][y][n] = ( sum_k X[row][y][k] Wk[k][n] + sum_l by[y][l] Z[row][l][n] + bias[n] ) * GELU'(mul[row][y][n])
+//   out_act        = GELU(out)                                                   (optional second output)
+//
+// Transposed formulation: output channels are the MMA M dimension (TMEM lanes), the positions of one
+// grid-row tile are N:      D[n][y] = [Wk^T | Z[row]^T] (A, TMEM)  x  [X | by] (B, shared memory, K-major)
+//   A1 = Wk^T  hi/lo : written to TMEM once per CTA (constant)
+//   A2 = Z^T   hi/lo : per grid row; the row's Z tile is TMA-loaded, transposed through registers by the
+//                      Z warpgroup (lane = channel) and written to TMEM with tcgen05.st
+//   B1 = X tile, B2 = by tile : TMA (SWIZZLE_128B) straight into MMA-ready slabs.  The tensor core reads
+//                      fp32 smem operands as TF32 by ignoring 13 mantissa bits, so the RAW tile is the
+//                      hi operand; converter warps add the remainder tile lo = v - trunc(v) (smem -> smem)
+//   D  : 2 x NT fp32 columns in TMEM; 8 epilogue warps (lane = channel, 128-byte coalesced stores)
+// Per tile: D = A_hi*B_raw + A_lo*B_raw + A_hi*B_lo.  FNM_MODE_TF32 issues A_hi*B_raw only.
+//
+// Warps (18 -> 5 per SM sub-partition, 96 registers):
+//   0 TMA producer | 1 TMEM allocator + MMA issuer | 2-5 Z warpgroup | 6-9 converters | 10-17 epilogue
+#include "fnm_tc_ptx.cuh"
+
+#include <cuda.h>
+#include <cstdlib>
+
+namespace fnm {
+namespace tc {
+
+constexpr int kPwThreads = 18 * 32;
+constexpr int kPwMaxStages = 6;
+constexpr uint32_t kPwSmemBudget = 226 * 1024;
+
+struct PwArgs2 {
+    const float* wc; const float* bias; const float* mul; float* out; float* out_act;
+    long long rows;
+    int S2, LY, CI, CO, wc_is_kn, single_pass;
+    int NT, tiles_per_row, seg_tiles, nseg, units;
+    int K1slabs, K2slabs, LYp, stages, nlo, debug;
+    uint32_t stage_bytes, x_bytes, z_bytes;
+};
+
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+
+// TMEM column map
+constexpr uint32_t kA1Hi = 0, kA1Lo = 128, kA2Hi = 256, kA2Lo = 320, kD0 = 384;
+
+
+// ---- MMA issue: the issuing warp is latency bound on its scalar (uniform-datapath) instruction stream,
+// so the per-tile sequence is fully unrolled for the common (channel slabs, mode k-steps) shapes: one
+// 32-bit add per descriptor / TMEM address, no loop control, no descriptor re-assembly.  The high word of
+// a K-major SWIZZLE_128B descriptor is constant; k-steps and slabs only move the 14-bit start address.
+constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr) { return ((saddr >> 4) & 0x3fffu) | (1u << 16); }
+__device__ __forceinline__ void umma_ts32(uint32_t d, uint32_t a_tmem, uint32_t bdesc_lo, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t.reg .b64 bd;\n\tmov.b64 bd, {%2, %5};\n\telect.sync _|q, 0xffffffff;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], bd, %3, p;\n\t}" ::"r"(d),
+        "r"(a_tmem), "r"(bdesc_lo), "r"(idesc), "r"(accum), "r"(kDescHi)
+        : "memory");
+}
+
+// raw passes of one tile: D = (A_hi [+ A_lo]) * B_raw over K1S channel slabs and NKS2 mode k-steps.
+// K1S / NKS2 < 0: runtime extents (generic shapes).
+template <int K1S, int NKS2, bool SINGLE>
+__device__ __forceinline__ void pw2_issue_raw(uint32_t d, uint32_t tb, uint32_t x_lo, uint32_t by_lo, uint32_t slab16,
+                                              uint32_t idesc, int k1s_rt, int nks2_rt) {
+    const int k1s = K1S >= 0 ? K1S : k1s_rt, nks2 = NKS2 >= 0 ? NKS2 : nks2_rt;
+    uint32_t accum = 0;
+#pragma unroll
+    for (int kb = 0; kb < (K1S >= 0 ? K1S : 4); ++kb) {
+        if (kb < k1s) {
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+                const uint32_t b = x_lo + kb * slab16 + 2 * ks;
+                umma_ts32(d, tb + kA1Hi + kb * 32 + ks * 8, b, idesc, accum);
+                accum = 1;
+                if (!SINGLE) umma_ts32(d, tb + kA1Lo + kb * 32 + ks * 8, b, idesc, 1);
+            }
+        }
+    }
+#pragma unroll
+    for (int k8 = 0; k8 < (NKS2 >= 0 ? NKS2 : 8); ++k8) {
+        if (k8 < nks2) {
+            const uint32_t b = by_lo + (k8 >> 2) * slab16 + 2 * (k8 & 3);
+            umma_ts32(d, tb + kA2Hi + k8 * 8, b, idesc, accum);
+            accum = 1;
+            if (!SINGLE) umma_ts32(d, tb + kA2Lo + k8 * 8, b, idesc, 1);
+        }
+    }
+}
+
+// remainder pass of one tile: D += A_hi * B_lo
+template <int K1S, int NKS2>
+__device__ __forceinline__ void pw2_issue_lo(uint32_t d, uint32_t tb, uint32_t x_lo, uint32_t by_lo, uint32_t slab16,
+                                             uint32_t idesc, int k1s_rt, int nks2_rt) {
+    const int k1s = K1S >= 0 ? K1S : k1s_rt, nks2 = NKS2 >= 0 ? NKS2 : nks2_rt;
+#pragma unroll
+    for (int kb = 0; kb < (K1S >= 0 ? K1S : 4); ++kb) {
+        if (kb < k1s) {
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) umma_ts32(d, tb + kA1Hi + kb * 32 + ks * 8, x_lo + kb * slab16 + 2 * ks, idesc, 1);
+        }
+    }
+#pragma unroll
+    for (int k8 = 0; k8 < (NKS2 >= 0 ? NKS2 : 8); ++k8) {
+        if (k8 < nks2) umma_ts32(d, tb + kA2Hi + k8 * 8, by_lo + (k8 >> 2) * slab16 + 2 * (k8 & 3), idesc, 1);
+    }
+}
+
+#define PW2_SHAPES(X) X(4, 8) X(2, 4) X(1, 3) X(4, 4) X(2, 8) X(1, 4)
+
+__global__ void __launch_bounds__(kPwThreads, 1)
+pw2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapBy,
+           const __grid_constant__ CUtensorMap mapZ, const PwArgs2 a) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    // [stages x {X raw slabs, by raw slabs}] [lo copy of one stage] [Z staging] [barriers]
+    uint8_t* lo_buf = smem + (size_t)a.stages * a.stage_bytes;
+    float* zs = reinterpret_cast<float*>(lo_buf + (size_t)a.nlo * a.stage_bytes);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(zs) + a.z_bytes);
+    uint64_t* full = bars;                          // [kPwMaxStages]
+    uint64_t* empty = bars + kPwMaxStages;          // [kPwMaxStages]
+    uint64_t* lo_full = bars + 2 * kPwMaxStages;    // [2]
+    uint64_t* lo_empty = lo_full + 2;               // [2]
+    uint64_t* z_full = lo_full + 4;
+    uint64_t* z_empty = lo_full + 5;
+    uint64_t* a2_full = lo_full + 6;
+    uint64_t* a2_empty = lo_full + 7;
+    uint64_t* acc_full = lo_full + 8;               // [2]
+    uint64_t* acc_empty = lo_full + 10;             // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(lo_full + 12);
+
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+    const bool has_x = a.CI > 0;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < a.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], a.single_pass ? 1 : 5); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&lo_full[s], 4); mbar_init(&lo_empty[s], 1); }
+        mbar_init(z_full, 1); mbar_init(z_empty, 4);
+        mbar_init(a2_full, 4); mbar_init(a2_empty, 1);
+        for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 8); }
+        fence_barrier_init();
+        tma_prefetch_desc(&mapX); tma_prefetch_desc(&mapBy); tma_prefetch_desc(&mapZ);
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+
+    // ---- A1: constant pointwise weights, Wk^T[o][k], hi/lo -> TMEM (epilogue warps 10-13, lane = o)
+    if (has_x && warp >= 10 && warp < 14) {
+        const int q4 = warp & 3, o = q4 * 32 + lane;
+        const uint32_t lane_base = tmem_base + ((uint32_t)(q4 * 32) << 16);
+        for (int k0 = 0; k0 < a.K1slabs * 32; k0 += 16) {
+            float v[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const int k = k0 + j;
+                v[j] = 0.f;
+                if (o < a.CO && k < a.CI) v[j] = a.wc_is_kn ? __ldg(a.wc + (size_t)k * a.CO + o) : __ldg(a.wc + (size_t)o * a.CI + k);
+            }
+            split_to_tmem16(lane_base + kA1Hi + k0, lane_base + kA1Lo + k0, v, !a.single_pass);
+        }
+        tmem_st_wait();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+
+    const int my_units = (a.units - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    auto unit_tiles = [&](int u, int& row, int& t0, int& t1) {
+        const int unit = (int)blockIdx.x + u * (int)gridDim.x;
+        row = unit / a.nseg;
+        const int seg = unit - row * a.nseg;
+        t0 = seg * a.seg_tiles;
+        t1 = min(a.tiles_per_row, t0 + a.seg_tiles);
+    };
+
+    if (warp == 0) {
+        // =========================================================================== TMA producer
+        if (lane == 0) {
+            uint32_t t = 0;
+            for (int u = 0; u < my_units; ++u) {
+                int row, t0, t1;
+                unit_tiles(u, row, t0, t1);
+                mbar_wait(z_empty, (uint32_t)((u & 1) ^ 1));
+                mbar_expect_tx(z_full, a.z_bytes);
+                tma_load_2d(&mapZ, z_full, zs, 0, row * a.LY);
+                for (int tile = t0; tile < t1; ++tile, ++t) {
+                    const uint32_t s = t % (uint32_t)a.stages;
+                    mbar_wait(&empty[s], ((t / (uint32_t)a.stages) & 1) ^ 1);
+                    mbar_expect_tx(&full[s], a.stage_bytes);
+                    uint8_t* st = smem + (size_t)s * a.stage_bytes;
+                    const int y0 = tile * a.NT;
+                    for (int kb = 0; kb < a.K1slabs; ++kb)
+                        tma_load_3d(&mapX, &full[s], st + (size_t)kb * a.NT * 128, kb * 32, y0, row);
+                    for (int kb = 0; kb < a.K2slabs; ++kb)
+                        tma_load_2d(&mapBy, &full[s], st + a.x_bytes + (size_t)kb * a.NT * 128, kb * 32, y0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // =========================================================================== MMA issuer
+        const uint32_t sbase = smem_u32(smem);
+        const uint32_t lo_base0 = smem_u32(lo_buf);
+        const uint32_t idesc = make_idesc(128, a.NT);
+        const int nks2 = a.LYp / 8;                                   // k-steps over the (padded) mode axis
+        const uint32_t slab16 = (uint32_t)a.NT * 8u;                  // slab stride in 16-byte descriptor units
+        const uint32_t xb16 = a.x_bytes >> 4;
+        uint32_t t = 0;
+        for (int u = 0; u < my_units; ++u) {
+            int row, t0, t1;
+            unit_tiles(u, row, t0, t1);
+            mbar_wait(a2_full, (uint32_t)(u & 1));
+            for (int tile = t0; tile < t1; ++tile, ++t) {
+                const uint32_t s = t % (uint32_t)a.stages, acc = t & 1;
+                mbar_wait(&acc_empty[acc], ((t >> 1) & 1) ^ 1);
+                mbar_wait(&full[s], (t / (uint32_t)a.stages) & 1);
+                tc_fence_after();
+                const uint32_t d = tmem_base + kD0 + acc * 64u;
+                const uint32_t x_lo = desc_lo(sbase + s * a.stage_bytes), by_lo = x_lo + xb16;
+                // raw passes: (A_hi + A_lo) * B_raw
+                bool done = false;
+#define PW2_RAW(K1, K2)                                                                                                  \
+                if (!done && a.K1slabs == K1 && nks2 == K2) {                                                            \
+                    if (a.single_pass) pw2_issue_raw<K1, K2, true>(d, tmem_base, x_lo, by_lo, slab16, idesc, 0, 0);      \
+                    else pw2_issue_raw<K1, K2, false>(d, tmem_base, x_lo, by_lo, slab16, idesc, 0, 0);                   \
+                    done = true;                                                                                         \
+                }
+                PW2_SHAPES(PW2_RAW)
+#undef PW2_RAW
+                if (!done) {
+                    if (a.single_pass) pw2_issue_raw<-1, -1, true>(d, tmem_base, x_lo, by_lo, slab16, idesc, a.K1slabs, nks2);
+                    else pw2_issue_raw<-1, -1, false>(d, tmem_base, x_lo, by_lo, slab16, idesc, a.K1slabs, nks2);
+                }
+                umma_commit(&empty[s]);                              // the raw tile is free once the raw passes retire
+                if (!a.single_pass) {
+                    // remainder pass: A_hi * B_lo
+                    const uint32_t lb = a.nlo == 2 ? (t & 1) : 0u;
+                    const uint32_t xl_lo = desc_lo(lo_base0 + lb * a.stage_bytes), byl_lo = xl_lo + xb16;
+                    mbar_wait(&lo_full[lb], a.nlo == 2 ? ((t >> 1) & 1) : (t & 1));
+                    tc_fence_after();
+                    done = false;
+#define PW2_LO(K1, K2)                                                                                                   \
+                    if (!done && a.K1slabs == K1 && nks2 == K2) {                                                        \
+                        pw2_issue_lo<K1, K2>(d, tmem_base, xl_lo, byl_lo, slab16, idesc, 0, 0);                          \
+                        done = true;                                                                                     \
+                    }
+                    PW2_SHAPES(PW2_LO)
+#undef PW2_LO
+                    if (!done) pw2_issue_lo<-1, -1>(d, tmem_base, xl_lo, byl_lo, slab16, idesc, a.K1slabs, nks2);
+                    umma_commit(&lo_empty[lb]);
+                }
+                umma_commit(&acc_full[acc]);
+                if (tile == t1 - 1) umma_commit(a2_empty);
+                __syncwarp();
+            }
+        }
+    } else if (warp < 6) {
+        // =========================================================================== Z warpgroup: Z[row] (smem) -> A2 hi/lo (TMEM)
+        const int q4 = warp & 3, c = q4 * 32 + lane;
+        const uint32_t lane_base = tmem_base + ((uint32_t)(q4 * 32) << 16);
+        const bool c_ok = c < a.CO;
+        for (int u = 0; u < my_units; ++u) {
+            mbar_wait(z_full, (uint32_t)(u & 1));
+            mbar_wait(a2_empty, (uint32_t)((u & 1) ^ 1));
+            tc_fence_after();
+            for (int l0 = 0; l0 < a.LYp; l0 += 16) {
+                float v[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = (c_ok && l0 + j < a.LY) ? zs[(l0 + j) * a.CO + c] : 0.f;
+                split_to_tmem16(lane_base + kA2Hi + l0, lane_base + kA2Lo + l0, v, !a.single_pass);
+            }
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) { mbar_arrive(z_empty); mbar_arrive(a2_full); }
+        }
+    } else if (warp < 10) {
+        // =========================================================================== converters: lo = raw - trunc(raw)
+        if (!a.single_pass) {
+            const int ct = threadIdx.x - 6 * 32;                       // 0..127
+            uint32_t t = 0;
+            for (int u = 0; u < my_units; ++u) {
+                int row, t0, t1;
+                unit_tiles(u, row, t0, t1);
+                for (int tile = t0; tile < t1; ++tile, ++t) {
+                    const uint32_t s = t % (uint32_t)a.stages;
+                    mbar_wait(&full[s], (t / (uint32_t)a.stages) & 1);
+                    const uint32_t lb = a.nlo == 2 ? (t & 1) : 0u;
+                    mbar_wait(&lo_empty[lb], (a.nlo == 2 ? ((t >> 1) & 1) : (t & 1)) ^ 1);
+                    const uint32_t src = smem_u32(smem) + s * a.stage_bytes + (uint32_t)ct * 16u;
+                    const uint32_t dst = smem_u32(lo_buf) + lb * a.stage_bytes + (uint32_t)ct * 16u;
+                    // linear copy (the remainder tile has the raw tile's swizzled layout, so offsets are identical):
+                    // stage_bytes is a multiple of 4 KB; 2 KB per pass of the 128 threads, two passes per iteration
+                    uint32_t off = 0;
+                    for (; off + 4096u <= a.stage_bytes; off += 4096u) {
+                        float4 v0, v1;
+                        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v0.x), "=f"(v0.y), "=f"(v0.z), "=f"(v0.w) : "r"(src + off));
+                        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v1.x), "=f"(v1.y), "=f"(v1.z), "=f"(v1.w) : "r"(src + off + 2048u));
+                        v0.x -= __uint_as_float(__float_as_uint(v0.x) & 0xffffe000u); v0.y -= __uint_as_float(__float_as_uint(v0.y) & 0xffffe000u);
+                        v0.z -= __uint_as_float(__float_as_uint(v0.z) & 0xffffe000u); v0.w -= __uint_as_float(__float_as_uint(v0.w) & 0xffffe000u);
+                        v1.x -= __uint_as_float(__float_as_uint(v1.x) & 0xffffe000u); v1.y -= __uint_as_float(__float_as_uint(v1.y) & 0xffffe000u);
+                        v1.z -= __uint_as_float(__float_as_uint(v1.z) & 0xffffe000u); v1.w -= __uint_as_float(__float_as_uint(v1.w) & 0xffffe000u);
+                        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst + off), "f"(v0.x), "f"(v0.y), "f"(v0.z), "f"(v0.w) : "memory");
+                        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst + off + 2048u), "f"(v1.x), "f"(v1.y), "f"(v1.z), "f"(v1.w) : "memory");
+                    }
+                    if (off < a.stage_bytes) {                        // odd number of 2 KB passes
+                        float4 v0;
+                        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v0.x), "=f"(v0.y), "=f"(v0.z), "=f"(v0.w) : "r"(src + off));
+                        v0.x -= __uint_as_float(__float_as_uint(v0.x) & 0xffffe000u); v0.y -= __uint_as_float(__float_as_uint(v0.y) & 0xffffe000u);
+                        v0.z -= __uint_as_float(__float_as_uint(v0.z) & 0xffffe000u); v0.w -= __uint_as_float(__float_as_uint(v0.w) & 0xffffe000u);
+                        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst + off), "f"(v0.x), "f"(v0.y), "f"(v0.z), "f"(v0.w) : "memory");
+                    }
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) { mbar_arrive(&lo_full[lb]); mbar_arrive(&empty[s]); }
+                }
+            }
+        }
+    } else {
+        // =========================================================================== epilogue (8 warps)
+        const int q4 = warp & 3, o = q4 * 32 + lane;
+        const int half = (warp - 10) >> 2;
+        const int hc = a.NT / 2;                                       // columns per half: 16, 24 or 32
+        const bool o_ok = o < a.CO;
+        const float bias = (o_ok && a.bias) ? __ldg(a.bias + o) : 0.f;
+        const uint32_t lane_base = tmem_base + ((uint32_t)(q4 * 32) << 16) + kD0;
+        uint32_t t = 0;
+        for (int u = 0; u < my_units; ++u) {
+            int row, t0, t1;
+            unit_tiles(u, row, t0, t1);
+            for (int tile = t0; tile < t1; ++tile, ++t) {
+                const uint32_t acc = t & 1;
+                const int yb = tile * a.NT + half * hc;                 // first position of this warp's columns
+                const int nv = max(0, min(hc, a.S2 - yb));              // valid positions
+                const size_t base = ((size_t)row * a.S2 + yb) * a.CO + o;
+                float m[32];
+                if (a.mul) {                                          // issued before the accumulator wait: overlaps the MMAs
+                    const float* mp = a.mul + base;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) m[j] = (o_ok && j < nv) ? __ldg(mp + (size_t)j * a.CO) : 0.f;
+                }
+                mbar_wait(&acc_full[acc], (t >> 1) & 1);
+                tc_fence_after();
+                const uint32_t taddr = lane_base + acc * 64u + (uint32_t)(half * hc);
+#pragma unroll
+                for (int g = 0; g < 2; ++g) {
+                    if (g * 16 < hc) {
+                        uint32_t r[16];
+                        tmem_ld16(taddr + g * 16, r);
+                        tmem_ld_wait();
+                        if (o_ok) {
+                            float* op = a.out + base + (size_t)(g * 16) * a.CO;
+                            float* ap = a.out_act ? a.out_act + base + (size_t)(g * 16) * a.CO : nullptr;
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) {
+                                if (g * 16 + j < nv) {
+                                    float v = __uint_as_float(r[j]) + bias;
+                                    if (a.mul) v *= gelu_grad_fast(m[g * 16 + j]);
+                                    op[(size_t)j * a.CO] = v;
+                                    if (ap) ap[(size_t)j * a.CO] = gelu_fast(v);
+                                }
+                            }
+                        }
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&acc_empty[acc]);
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// ---------------------------------------------------------------------------------------------- host
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+static bool make_map(CUtensorMap* m, const float* ptr, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+                     const cuuint32_t* box, bool swizzle128) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return false;
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<float*>(ptr), dims, strides_bytes,
+                          box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
+static bool pw2_configure(PwArgs2& a, int64_t rows, int S2, int LY, int CI, int CO) {
+    if (rows < 1 || rows > (1LL << 28) || S2 < 1 || LY < 4 || LY > 64 || LY % 4 != 0) return false;
+    if (CO < 4 || CO > 128 || CO % 4 != 0) return false;
+    if (CI != 0 && (CI < 4 || CI > 128 || CI % 4 != 0)) return false;
+    a.rows = rows; a.S2 = S2; a.LY = LY; a.CI = CI; a.CO = CO;
+    a.LYp = (LY + 7) / 8 * 8;
+    a.K1slabs = (CI + 31) / 32;
+    a.K2slabs = (a.LYp + 31) / 32;
+    a.z_bytes = (uint32_t)LY * CO * 4u;
+    int best = 0, best_cost = 1 << 30;
+    for (int nt = 64; nt >= 32; nt -= 16) {                    // padded positions + a per-tile overhead worth ~32 positions
+        const int tiles = (S2 + nt - 1) / nt;                  // (measured at config 5: 5 x 64 beats 6 x 48); ties -> wider tile
+        const int cost = tiles * (nt + 32);
+        if (cost < best_cost) { best_cost = cost; best = nt; }
+    }
+    a.NT = best;
+    { const char* e = getenv("FNM_PW2_NT"); if (e && (atoi(e) == 32 || atoi(e) == 48 || atoi(e) == 64)) a.NT = atoi(e); }
+    a.tiles_per_row = (S2 + a.NT - 1) / a.NT;
+    a.x_bytes = (uint32_t)a.K1slabs * a.NT * 128u;
+    a.stage_bytes = a.x_bytes + (uint32_t)a.K2slabs * a.NT * 128u;
+    const uint32_t fixed = a.z_bytes + 1024 /*align*/ + 256 /*barriers*/;
+    if (fixed + 3 * a.stage_bytes > kPwSmemBudget) return false;             // 2 raw stages + 1 remainder buffer at least
+    const int slots = (int)((kPwSmemBudget - fixed) / a.stage_bytes);        // raw stages + remainder buffers
+    // bytes in flight are what hides HBM latency (~90 KB per SM): every slot beyond one remainder buffer is a raw stage
+    a.nlo = slots >= 4 ? 2 : 1;
+    { const char* e = getenv("FNM_PW2_NLO"); if (e && slots >= 4) a.nlo = atoi(e) == 2 ? 2 : 1; }
+    a.stages = slots - a.nlo > kPwMaxStages ? kPwMaxStages : slots - a.nlo;
+    { const char* e = getenv("FNM_PW2_STAGES"); if (e && atoi(e) >= 2 && atoi(e) <= a.stages) a.stages = atoi(e); }
+    // units: whole rows when there are enough of them, otherwise row segments (1-D problems have few rows)
+    int nseg = 1;
+    const int want = 2 * sm_count();
+    if (rows < want) nseg = (int)((want + rows - 1) / rows);
+    if (nseg > a.tiles_per_row) nseg = a.tiles_per_row;
+    a.seg_tiles = (a.tiles_per_row + nseg - 1) / nseg;
+    a.nseg = (a.tiles_per_row + a.seg_tiles - 1) / a.seg_tiles;
+    const long long units = rows * a.nseg;
+    if (units > (1LL << 30)) return false;
+    a.units = (int)units;
+    return true;
+}
+
+}  // namespace tc
+
+using namespace tc;
+
+bool tc_pw2_supported(int64_t rows, int S2, int LY, int K, int N, int act, const void* x, const void* Z, const void* by) {
+    if (!tc_enabled() || act != 0 || !encode_fn()) return false;
+    { const char* e = getenv("FNM_DISABLE_PW2"); if (e && e[0] == '1') return false; }
+    if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(Z) | reinterpret_cast<uintptr_t>(by)) & 15) return false;
+    PwArgs2 a{};
+    return pw2_configure(a, rows, S2, LY, K, N);
+}
+
+int tc_pw2(const float* x, const float* wc, int wc_is_kn, const float* bias, const float* Z, const float* by,
+           const float* mul, float* out, float* out_act, int64_t rows, int S2, int LY, int K, int N, int mode,
+           cudaStream_t st) {
+    PwArgs2 a{};
+    const int CI = (x && wc) ? K : 0;
+    if (!pw2_configure(a, rows, S2, LY, CI, N)) return fail(FNM_ENOTSUP, "pointwise_ysyn: shape not served by the TMA kernel");
+    a.wc = wc; a.bias = bias; a.mul = mul; a.out = out; a.out_act = out_act; a.wc_is_kn = wc_is_kn;
+    a.single_pass = mode == FNM_MODE_TF32;
+    { const char* e = getenv("FNM_PW2_DEBUG"); a.debug = e ? atoi(e) : 0; }
+    CUtensorMap mx, mb, mz;
+    {
+        const cuuint64_t dims[2] = {(cuuint64_t)LY, (cuuint64_t)S2};
+        const cuuint64_t str[1] = {(cuuint64_t)LY * 4};
+        const cuuint32_t box[2] = {32, (cuuint32_t)a.NT};
+        if (!make_map(&mb, by, 2, dims, str, box, true)) return fail(FNM_ECUDA, "pointwise_ysyn: tensor map (by) failed");
+    }
+    {
+        const cuuint64_t dims[2] = {(cuuint64_t)N, (cuuint64_t)rows * LY};
+        const cuuint64_t str[1] = {(cuuint64_t)N * 4};
+        const cuuint32_t box[2] = {(cuuint32_t)N, (cuuint32_t)LY};
+        if (!make_map(&mz, Z, 2, dims, str, box, false)) return fail(FNM_ECUDA, "pointwise_ysyn: tensor map (Z) failed");
+    }
+    if (CI > 0) {
+        const cuuint64_t dims[3] = {(cuuint64_t)CI, (cuuint64_t)S2, (cuuint64_t)rows};
+        const cuuint64_t str[2] = {(cuuint64_t)CI * 4, (cuuint64_t)S2 * CI * 4};
+        const cuuint32_t box[3] = {32, (cuuint32_t)a.NT, 1};
+        if (!make_map(&mx, x, 3, dims, str, box, true)) return fail(FNM_ECUDA, "pointwise_ysyn: tensor map (x) failed");
+    } else {
+        mx = mb;
+    }
+    const size_t smem = (size_t)(a.stages + a.nlo) * a.stage_bytes + a.z_bytes + 1024 + 256;
+    static bool attr_set = false;
+    if (!attr_set) {
+        const cudaError_t e = cudaFuncSetAttribute(pw2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return fail(FNM_ECUDA, "pointwise_ysyn: smem attribute: %s", cudaGetErrorString(e));
+        attr_set = true;
+    }
+    const int grid = a.units < sm_count() ? a.units : sm_count();
+    {
+        LaunchScope ls("pointwise_ysyn", st);
+        pw2_kernel<<<grid, kPwThreads, smem < 120 * 1024 ? 120 * 1024 : smem, st>>>(mx, mb, mz, a);
+    }
+    return check_launch("pointwise_ysyn");
+}
+
+}  // namespace fnm

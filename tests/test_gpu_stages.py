@@ -56,6 +56,14 @@ CASES = [
     dict(rows=50, S2=57, LY=24, K=32, N=32, act=1, kn=0, bias=1, mul=1),       # config 3 trunk: odd row length
     dict(rows=20, S2=144, LY=34, K=0, N=64, act=0, kn=0, bias=0, mul=0),       # V2F decoder output (no pointwise term)
     dict(rows=20, S2=57, LY=26, K=0, N=32, act=0, kn=0, bias=0, mul=1),        # F2V backward
+    # no activation on load (the trunk's normal case: the producer already wrote GELU(z)) -> TMA kernel
+    dict(rows=40, S2=72, LY=24, K=32, N=32, act=0, kn=0, bias=1, mul=0),       # config 1 forward
+    dict(rows=300, S2=288, LY=64, K=128, N=128, act=0, kn=0, bias=1, mul=0),   # config 5 forward (+ GELU copy)
+    dict(rows=450, S2=288, LY=64, K=128, N=128, act=0, kn=1, bias=0, mul=1),   # config 5 backward, > 3 rows per CTA
+    dict(rows=7, S2=1152, LY=32, K=64, N=64, act=0, kn=0, bias=1, mul=0),      # config 2 (1-D): rows split in segments
+    dict(rows=33, S2=144, LY=32, K=64, N=64, act=0, kn=1, bias=0, mul=1),      # config 4 trunk backward
+    dict(rows=50, S2=57, LY=24, K=32, N=32, act=0, kn=0, bias=1, mul=1),       # config 3 trunk: odd row length
+    dict(rows=21, S2=100, LY=20, K=48, N=48, act=0, kn=0, bias=1, mul=0),      # channel count that is no multiple of 32
     dict(rows=9, S2=40, LY=10, K=20, N=20, act=1, kn=0, bias=1, mul=0),        # SIMT-only shape (C = 20)
     dict(rows=5, S2=96, LY=16, K=96, N=96, act=1, kn=0, bias=1, mul=1),        # 64 < C < 128
 ]
