@@ -281,13 +281,15 @@ def run_ours(args, rank, world):
     ms_e2e = max_over_ranks(max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3 if world == 1 else 0.0))
 
     # ---- per-kernel device time of the same step (CUDA events around every launch, separate pass)
+    # (every rank runs the steps -- they contain the all-reduce -- but only rank 0 records events)
     prof = None
+    nprof = 2
     if rank == 0:
-        nprof = 2
         _lib.profile_begin()
-        for _ in range(nprof):
-            step(x, y)
-        torch.cuda.synchronize()
+    for _ in range(nprof):
+        step(x, y)
+    torch.cuda.synchronize()
+    if rank == 0:
         prof = {k: (c / nprof, t / nprof) for k, (c, t) in _lib.profile_end().items()}
     barrier()
 

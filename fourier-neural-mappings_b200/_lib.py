@@ -53,9 +53,10 @@ PROTOTYPES = {
     "fnm_ydft": (_i32, [_vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _vp]),
     "fnm_xdft": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     "fnm_xsyn": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
-    "fnm_mix_fwd": (_i32, [_vp, _vp, _vp, _i32, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
-    "fnm_mix_bwd_x": (_i32, [_vp, _vp, _vp, _i32, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
-    "fnm_mix_bwd_w": (_i32, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "fnm_mix_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32, _i32]),
+    "fnm_mix_fwd": (_i32, [_vp, _vp, _vp, _i32, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _sz, _i32, _vp]),
+    "fnm_mix_bwd_x": (_i32, [_vp, _vp, _vp, _i32, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _sz, _i32, _vp]),
+    "fnm_mix_bwd_w": (_i32, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _sz, _i32, _vp]),
     "fnm_pointwise_ysyn": (_i32, [_vp, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32,
                                   _i32, _vp]),
     "fnm_conv_wgrad_workspace_bytes": (_sz, [_i64, _i32, _i32]),

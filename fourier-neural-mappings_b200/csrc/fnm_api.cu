@@ -89,7 +89,7 @@ static int conv_wgrad(const float* g, const float* x, int act, float* dwc, float
 }
 
 struct LayerWs {
-    size_t T, Oh, Z, Gh, partial;      // float counts
+    size_t T, Oh, Z, Gh, partial, shadow;      // float counts (shadow: one mode-major weight copy, 0 = SIMT mixing)
 };
 
 static LayerWs layer_ws(const fnm_plan* p) {
@@ -102,6 +102,7 @@ static LayerWs layer_ws(const fnm_plan* p) {
     w.Z = rows * LY * cmax;
     w.Gh = (size_t)p->R * p->NY * 2 * p->B * cmax;
     w.partial = conv_wgrad_workspace((int64_t)p->B * p->S1 * p->S2, p->Ci, p->Co) / sizeof(float);
+    w.shadow = tc_mix_supported(p->B, p->Ci, p->Co) ? tc_mix_shadow_floats(p->R * p->NY, p->Ci, p->Co) : 0;
     return w;
 }
 
@@ -181,24 +182,49 @@ int fnm_xsyn(const float* Oh, const float* fx, float* Z, int B, int S1, int R, i
     return simt_xsyn(Oh, fx, Z, B, S1, R, NY, C, as_stream(stream));
 }
 
+size_t fnm_mix_workspace_bytes(int B, int R, int NY, int Ci, int Co) {
+    return tc_mix_supported(B, Ci, Co) ? tc_mix_shadow_floats(R * NY, Ci, Co) * sizeof(float) + 256 : 0;
+}
+
+// the tcgen05 path needs scratch for the mode-major weight copy; without it (or for shapes it does not
+// serve) the fp32 SIMT kernels run on the reference layout directly
+static bool mix_use_tc(int B, int R, int NY, int Ci, int Co, void* ws, size_t ws_bytes) {
+    return ws && tc_mix_supported(B, Ci, Co) && ws_bytes >= fnm_mix_workspace_bytes(B, R, NY, Ci, Co);
+}
+
 int fnm_mix_fwd(const float* Xh, const float* w0, const float* w1, int rows_per_w, float* Oh, int B, int R, int NY,
-                int Ci, int Co, fnm_stream_t stream) {
+                int Ci, int Co, void* workspace, size_t workspace_bytes, int mode, fnm_stream_t stream) {
     FNM_REQUIRE(Xh && w0 && Oh, "mix_fwd: NULL pointer");
     FNM_REQUIRE(rows_per_w == R || (w1 && 2 * rows_per_w == R), "mix_fwd: weight rows do not cover R");
+    if (mix_use_tc(B, R, NY, Ci, Co, workspace, workspace_bytes)) {
+        float* W1 = static_cast<float*>(workspace);
+        FNM_TRY(tc_mix_pack(w0, w1, rows_per_w, R, NY, Ci, Co, 0, W1, as_stream(stream)));
+        return tc_mix_apply(W1, Xh, Oh, R * NY, B, Ci, Co, 0, mode, "mix_fwd", as_stream(stream));
+    }
     return simt_mix_fwd(Xh, w0, w1, rows_per_w, Oh, B, R, NY, Ci, Co, as_stream(stream));
 }
 
 int fnm_mix_bwd_x(const float* Gh, const float* w0, const float* w1, int rows_per_w, float* Gxh, int B, int R, int NY,
-                  int Ci, int Co, fnm_stream_t stream) {
+                  int Ci, int Co, void* workspace, size_t workspace_bytes, int mode, fnm_stream_t stream) {
     FNM_REQUIRE(Gh && w0 && Gxh, "mix_bwd_x: NULL pointer");
     FNM_REQUIRE(rows_per_w == R || (w1 && 2 * rows_per_w == R), "mix_bwd_x: weight rows do not cover R");
+    if (mix_use_tc(B, R, NY, Ci, Co, workspace, workspace_bytes)) {
+        float* W2 = static_cast<float*>(workspace);
+        FNM_TRY(tc_mix_pack(w0, w1, rows_per_w, R, NY, Ci, Co, 1, W2, as_stream(stream)));
+        return tc_mix_apply(W2, Gh, Gxh, R * NY, B, Co, Ci, 1, mode, "mix_bwd_x", as_stream(stream));
+    }
     return simt_mix_bwd_x(Gh, w0, w1, rows_per_w, Gxh, B, R, NY, Ci, Co, as_stream(stream));
 }
 
 int fnm_mix_bwd_w(const float* Xh, const float* Gh, float* dw0, float* dw1, int rows_per_w, int B, int R, int NY,
-                  int Ci, int Co, fnm_stream_t stream) {
+                  int Ci, int Co, void* workspace, size_t workspace_bytes, int mode, fnm_stream_t stream) {
     FNM_REQUIRE(Xh && Gh && dw0, "mix_bwd_w: NULL pointer");
     FNM_REQUIRE(rows_per_w == R || (dw1 && 2 * rows_per_w == R), "mix_bwd_w: weight rows do not cover R");
+    if (mix_use_tc(B, R, NY, Ci, Co, workspace, workspace_bytes)) {
+        float* dW1 = static_cast<float*>(workspace);
+        FNM_TRY(tc_mix_wgrad(Xh, Gh, dW1, R * NY, B, Ci, Co, mode, as_stream(stream)));
+        return tc_mix_unpack(dW1, dw0, dw1, rows_per_w, R, NY, Ci, Co, as_stream(stream));
+    }
     return simt_mix_bwd_w(Xh, Gh, dw0, dw1, rows_per_w, B, R, NY, Ci, Co, as_stream(stream));
 }
 
@@ -259,7 +285,7 @@ int fnm_counter_inc(int32_t* counter, fnm_stream_t stream) {
 size_t fnm_fourier_layer_workspace_bytes(const fnm_plan* plan) {
     if (!plan) return 0;
     const LayerWs w = layer_ws(plan);
-    return (w.T + w.Oh + w.Z + w.Gh + w.partial) * sizeof(float) + 5 * 256;
+    return (w.T + w.Oh + w.Z + w.Gh + w.partial + 2 * w.shadow) * sizeof(float) + 7 * 256;
 }
 
 int fnm_fourier_layer_fwd(const fnm_plan* p, const float* xin, int act_in, const float* w0, const float* w1,
@@ -280,7 +306,13 @@ int fnm_fourier_layer_fwd(const fnm_plan* p, const float* xin, int act_in, const
     const int LY = 2 * p->NY;
     FNM_TRY(fnm_ydft(xin, p->ay, T, (int64_t)p->B * p->P1, p->P2, LY, p->Ci, act_in, p->mode, stream));
     FNM_TRY(fnm_xdft(T, p->ex, xh_save, p->B, p->P1, p->R, p->NY, p->Ci, p->mode, stream));
-    FNM_TRY(simt_mix_fwd(xh_save, w0, w1, p->rows_per_w, Oh, p->B, p->R, p->NY, p->Ci, p->Co, st));
+    if (w.shadow) {
+        float* W1 = cv.take(w.shadow);
+        FNM_TRY(tc_mix_pack(w0, w1, p->rows_per_w, p->R, p->NY, p->Ci, p->Co, 0, W1, st));
+        FNM_TRY(tc_mix_apply(W1, xh_save, Oh, p->R * p->NY, p->B, p->Ci, p->Co, 0, p->mode, "mix_fwd", st));
+    } else {
+        FNM_TRY(simt_mix_fwd(xh_save, w0, w1, p->rows_per_w, Oh, p->B, p->R, p->NY, p->Ci, p->Co, st));
+    }
     FNM_TRY(fnm_xsyn(Oh, p->fx, Z, p->B, p->S1, p->R, p->NY, p->Co, p->mode, stream));
     return fnm_pointwise_ysyn(wc ? xin : nullptr, act_in, wc, 0, bc, Z, p->by, nullptr, z_out, x_act_out,
                               (int64_t)p->B * p->S1, p->S2, LY, p->Ci, p->Co, p->mode, stream);
@@ -307,11 +339,25 @@ int fnm_fourier_layer_bwd(const fnm_plan* p, const float* g_z, const float* xin,
     // analysis of g_z (c_l/N folded into byT), A.2 first line
     FNM_TRY(fnm_ydft(g_z, p->byT, Tg, (int64_t)p->B * p->S1, p->S2, LY, p->Co, 0, p->mode, stream));
     FNM_TRY(fnm_xdft(Tg, p->exb, Gh, p->B, p->S1, p->R, p->NY, p->Co, p->mode, stream));
-    if (dw0) FNM_TRY(simt_mix_bwd_w(xh_save, Gh, dw0, dw1, p->rows_per_w, p->B, p->R, p->NY, p->Ci, p->Co, st));
+    float* shadowA = w.shadow ? cv.take(w.shadow) : nullptr;
+    float* shadowB = w.shadow ? cv.take(w.shadow) : nullptr;
+    if (dw0) {
+        if (w.shadow) {
+            FNM_TRY(tc_mix_wgrad(xh_save, Gh, shadowA, p->R * p->NY, p->B, p->Ci, p->Co, p->mode, st));
+            FNM_TRY(tc_mix_unpack(shadowA, dw0, dw1, p->rows_per_w, p->R, p->NY, p->Ci, p->Co, st));
+        } else {
+            FNM_TRY(simt_mix_bwd_w(xh_save, Gh, dw0, dw1, p->rows_per_w, p->B, p->R, p->NY, p->Ci, p->Co, st));
+        }
+    }
     if (wc && (dwc || dbc))
         FNM_TRY(conv_wgrad(g_z, xin, act_in, dwc, dbc, (int64_t)p->B * p->S1 * p->S2, p->Ci, p->Co, partial, p->mode, st));
     if (g_in) {
-        FNM_TRY(simt_mix_bwd_x(Gh, w0, w1, p->rows_per_w, Gxh, p->B, p->R, p->NY, p->Ci, p->Co, st));
+        if (w.shadow) {
+            FNM_TRY(tc_mix_pack(w0, w1, p->rows_per_w, p->R, p->NY, p->Ci, p->Co, 1, shadowB, st));
+            FNM_TRY(tc_mix_apply(shadowB, Gh, Gxh, p->R * p->NY, p->B, p->Co, p->Ci, 1, p->mode, "mix_bwd_x", st));
+        } else {
+            FNM_TRY(simt_mix_bwd_x(Gh, w0, w1, p->rows_per_w, Gxh, p->B, p->R, p->NY, p->Ci, p->Co, st));
+        }
         FNM_TRY(fnm_xsyn(Gxh, p->fxb, Zg, p->B, p->P1, p->R, p->NY, p->Ci, p->mode, stream));
         const float* mul = zin_pre ? zin_pre : (act_in ? xin : nullptr);
         FNM_TRY(fnm_pointwise_ysyn(wc ? g_z : nullptr, 0, wc, 1, nullptr, Zg, p->ayT, mul, g_in, nullptr,

@@ -48,6 +48,14 @@ bool tc_xdft_supported(int B, int P1, int R, int NY, int C);
 int tc_xdft(const float* T, const float* ex, float* Xh, int B, int P1, int R, int NY, int C, int mode, cudaStream_t st);
 bool tc_xsyn_supported(int B, int S1, int R, int NY, int C);
 int tc_xsyn(const float* Oh, const float* fx, float* Z, int B, int S1, int R, int NY, int C, int mode, cudaStream_t st);
+bool tc_mix_supported(int B, int Ci, int Co);
+size_t tc_mix_shadow_floats(int nmodes, int Ci, int Co);
+int tc_mix_pack(const float* w0, const float* w1, int rpw, int R, int NY, int Ci, int Co, int which, float* dst,
+                cudaStream_t st);
+int tc_mix_unpack(const float* dW1, float* dw0, float* dw1, int rpw, int R, int NY, int Ci, int Co, cudaStream_t st);
+int tc_mix_apply(const float* Wm, const float* In, float* Out, int nmodes, int B, int Kt, int Lt, int conj, int mode,
+                 const char* what, cudaStream_t st);
+int tc_mix_wgrad(const float* Xh, const float* Gh, float* dW1, int nmodes, int B, int Ci, int Co, int mode, cudaStream_t st);
 bool tc_conv_wgrad_supported(int64_t npos, int Ci, int Co);
 size_t tc_conv_wgrad_workspace(int64_t npos, int Ci, int Co);
 int tc_conv_wgrad(const float* g, const float* x, int act, float* dwc, float* dbc, int64_t npos, int Ci, int Co,

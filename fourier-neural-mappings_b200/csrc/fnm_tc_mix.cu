@@ -1,0 +1,420 @@
+// tc_mix -- the per-mode complex channel mixing (compl_mul, models/shared.py:48-53) and its two
+// backward products on tcgen05 (3xTF32), plus the layout permutation that makes the weights mode-major.
+//
+// The reference keeps spectral weights as (Cin, Cout, kx, ky) complex64: the modes are the FASTEST
+// axis, so the (Cin x Cout) matrix of one mode is scattered with an 8 KB stride.  Each layer call first
+// permutes the weights into mode-major scratch copies (one streaming pass, ~0.1 ms for 268 MB):
+//     W1[m][i][o]   (forward:  lanes = o)          W2[m][o][i]   (backward-x: lanes = i)
+// and the weight gradient is produced mode-major and permuted back into the reference layout.
+//
+// One kernel serves the three products.  Per work item (mode m, tile of 32 "n" rows):
+//     D[l][n] = sum_k A[m][k][l] (*) B[m][n][k]          complex, (*) = a*b  or  conj(a)*b pattern
+//   apply, forward   : A = W1 (k=i, l=o), B = X^ (n=b)          O[b][o]  = sum_i X[b][i] W[i][o]
+//   apply, backward-x: A = W2 (k=o, l=i), B = G^ (n=b), conj    Gx[b][i] = sum_o G[b][o] conj(W[i][o])
+//   wgrad            : A = X^ (k=b, l=i), B = G^ (n=o), conj    dW[i][o] = sum_b conj(X[b][i]) G[b][o]
+// A is read with coalesced warp loads (lane = l), split hi/lo in registers and written to TMEM;
+// B is turned into K-major SWIZZLE_128B rows (raw + truncation remainder) by loader threads; the four
+// real products of the complex multiply go to D_re / D_im (main and correction accumulators, see
+// fnm_tc_tabgemm.cu for why), the sign of the A_im terms is applied with the descriptor's negate bit.
+//
+// Warps (16): 0-3 epilogue | 4 MMA issuer | 5-7 B loaders | 8-15 two A-loader warpgroups.
+#include "fnm_tc_ptx.cuh"
+
+#include <cstdlib>
+
+namespace fnm {
+namespace tc {
+
+constexpr int kMxThreads = 16 * 32;
+constexpr int kMxBWarps = 3;
+constexpr int kMxN = 32;                                   // n rows per item (MMA N)
+
+struct MxArgs {
+    const float* a; const float* b; float* out;
+    long long a_sm, a_sk, a_sl, a_im;                      // A element (m, k, l): a + m*a_sm + k*a_sk + l*a_sl (+ a_im)
+    long long b_sm, b_sn, b_sk, b_im;                      // B element (m, n, k)
+    long long o_sm, o_sn, o_sl, o_im;                      // output element (m, n, l)
+    int Kt, Lt, Nt;                                        // contraction length, lanes (<= 128), n extent
+    int nmodes, ntiles, items, nchunks;
+    int conj, single_pass, a_pair, b_kcontig, o_pair;      // a_pair / o_pair: (re, im) adjacent -> 8-byte accesses
+};
+
+__device__ __forceinline__ float ldf(const float* p) {
+    float v;
+    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ float2 ldf2(const float* p) {
+    float2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+    return v;
+}
+
+// smem per B buffer: [re raw | re lo | im raw | im lo] x nchunks slabs of [32 rows][128 B]
+__global__ void __launch_bounds__(kMxThreads, 1) mixgemm_tc(const MxArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const uint32_t part_bytes = (uint32_t)a.nchunks * 4096u;       // one of the four parts
+    const uint32_t bbuf_bytes = 4u * part_bytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * bbuf_bytes);
+    uint64_t* a_full = bars;             // [2] 4 warps
+    uint64_t* a_empty = bars + 2;        // [2]
+    uint64_t* b_full = bars + 4;         // [2] kMxBWarps
+    uint64_t* b_empty = bars + 6;        // [2]
+    uint64_t* d_full = bars + 8;         // [2]
+    uint64_t* d_empty = bars + 10;       // [2] 4 warps
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&a_full[s], 4); mbar_init(&a_empty[s], 1);
+            mbar_init(&b_full[s], kMxBWarps); mbar_init(&b_empty[s], 1);
+            mbar_init(&d_full[s], 1); mbar_init(&d_empty[s], 4);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 4) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+    // TMEM: A buffer s at 128*s: [re hi | re lo | im hi | im lo] x 32 columns;
+    //       D buffer s at 256 + 128*s: [re main | re corr | im main | im corr] x 32 columns
+    const int my_items = (a.items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+    if (warp < 4) {
+        // =========================================================================== epilogue
+        const int L = warp * 32 + lane;
+        const bool l_ok = L < a.Lt;
+        for (int it = 0; it < my_items; ++it) {
+            const int item = (int)blockIdx.x + it * (int)gridDim.x;
+            const int m = item / a.ntiles, n0 = (item - m * a.ntiles) * kMxN;
+            const int db = it & 1;
+            mbar_wait(&d_full[db], (uint32_t)((it >> 1) & 1));
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + 256u + 128u * db;
+            float* obase = a.out + (size_t)m * a.o_sm + (size_t)L * a.o_sl;
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
+                uint32_t rm[16], rc[16], im[16], ic[16];
+                tmem_ld16(taddr + g * 16, rm);
+                tmem_ld16(taddr + 64 + g * 16, im);
+                if (!a.single_pass) {
+                    tmem_ld16(taddr + 32 + g * 16, rc);
+                    tmem_ld16(taddr + 96 + g * 16, ic);
+                }
+                tmem_ld_wait();
+                if (l_ok) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const int n = n0 + g * 16 + j;
+                        if (n < a.Nt) {
+                            float vr = __uint_as_float(rm[j]), vi = __uint_as_float(im[j]);
+                            if (!a.single_pass) { vr += __uint_as_float(rc[j]); vi += __uint_as_float(ic[j]); }
+                            float* p = obase + (size_t)n * a.o_sn;
+                            if (a.o_pair) *reinterpret_cast<float2*>(p) = make_float2(vr, vi);
+                            else { p[0] = vr; p[a.o_im] = vi; }
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&d_empty[db]);
+        }
+    } else if (warp == 4) {
+        // =========================================================================== MMA issuer
+        const uint32_t sbase = smem_u32(smem);
+        const uint32_t idesc = make_idesc(128, kMxN);
+        const uint32_t ineg = idesc | (1u << 13);                     // negate A
+        // D_re = Ar*Br -/+ Ai*Bi ; D_im = +/- Ai*Br + Ar*Bi     (upper sign: plain product, lower: conj(A))
+        const uint32_t id_re_ai = a.conj ? idesc : ineg;
+        const uint32_t id_im_ai = a.conj ? ineg : idesc;
+        uint32_t q = 0;
+        for (int it = 0; it < my_items; ++it) {
+            const int db = it & 1, bb = it & 1;
+            mbar_wait(&d_empty[db], (uint32_t)(((it >> 1) & 1) ^ 1));
+            mbar_wait(&b_full[bb], (uint32_t)((it >> 1) & 1));
+            const uint32_t d_re = tmem_base + 256u + 128u * db, d_rc = d_re + 32u, d_im = d_re + 64u, d_ic = d_re + 96u;
+            const uint32_t bs = sbase + bb * bbuf_bytes;
+            for (int ch = 0; ch < a.nchunks; ++ch, ++q) {
+                const uint32_t ab = q & 1;
+                mbar_wait(&a_full[ab], (q >> 1) & 1);
+                tc_fence_after();
+                const uint32_t ar = tmem_base + 128u * ab, arl = ar + 32u, ai = ar + 64u, ail = ar + 96u;
+                const uint64_t br = make_desc(bs + (uint32_t)ch * 4096u), brl = make_desc(bs + part_bytes + (uint32_t)ch * 4096u);
+                const uint64_t bi = make_desc(bs + 2 * part_bytes + (uint32_t)ch * 4096u);
+                const uint64_t bil = make_desc(bs + 3 * part_bytes + (uint32_t)ch * 4096u);
+                const int nks = min(4, (a.Kt - ch * 32 + 7) / 8);
+                for (int ks = 0; ks < nks; ++ks) {
+                    const uint32_t first = (ch == 0 && ks == 0) ? 0u : 1u;
+                    const uint32_t k8 = ks * 8;
+                    umma_ts(d_re, ar + k8, br + 2 * ks, idesc, first);
+                    umma_ts(d_re, ai + k8, bi + 2 * ks, id_re_ai, 1);
+                    umma_ts(d_im, ai + k8, br + 2 * ks, id_im_ai, first);
+                    umma_ts(d_im, ar + k8, bi + 2 * ks, idesc, 1);
+                    if (!a.single_pass) {
+                        umma_ts(d_rc, arl + k8, br + 2 * ks, idesc, first);
+                        umma_ts(d_rc, ar + k8, brl + 2 * ks, idesc, 1);
+                        umma_ts(d_rc, ail + k8, bi + 2 * ks, id_re_ai, 1);
+                        umma_ts(d_rc, ai + k8, bil + 2 * ks, id_re_ai, 1);
+                        umma_ts(d_ic, ail + k8, br + 2 * ks, id_im_ai, first);
+                        umma_ts(d_ic, ai + k8, brl + 2 * ks, id_im_ai, 1);
+                        umma_ts(d_ic, arl + k8, bi + 2 * ks, idesc, 1);
+                        umma_ts(d_ic, ar + k8, bil + 2 * ks, idesc, 1);
+                    }
+                }
+                umma_commit(&a_empty[ab]);
+            }
+            umma_commit(&b_empty[bb]);
+            umma_commit(&d_full[db]);
+            __syncwarp();
+        }
+    } else if (warp < 8) {
+        // =========================================================================== B loaders (96 threads)
+        const int bt = threadIdx.x - 5 * 32;
+        for (int it = 0; it < my_items; ++it) {
+            const int item = (int)blockIdx.x + it * (int)gridDim.x;
+            const int m = item / a.ntiles, n0 = (item - m * a.ntiles) * kMxN;
+            const int bb = it & 1;
+            uint8_t* base = smem + (size_t)bb * bbuf_bytes;
+            const float* src = a.b + (size_t)m * a.b_sm;
+            mbar_wait(&b_empty[bb], (uint32_t)(((it >> 1) & 1) ^ 1));
+            if (a.b_kcontig) {
+                // rows n, k contiguous: 16-byte units (part re/im, row, 16-byte chunk over the padded K)
+                const int kc = a.nchunks * 8;
+                const int units = 2 * kMxN * kc;
+                for (int u0 = 0; u0 < units; u0 += kMxBWarps * 32 * 4) {
+                    float4 v[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int u = u0 + bt + j * kMxBWarps * 32;
+                        v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (u < units) {
+                            const int ri = u / (kMxN * kc), r2 = u - ri * kMxN * kc, n = r2 / kc, c = r2 - n * kc, k = c * 4;
+                            if (n0 + n < a.Nt && k < a.Kt) {
+                                const float* p = src + (size_t)ri * a.b_im + (size_t)(n0 + n) * a.b_sn + k;
+                                if (k + 3 < a.Kt && (a.Kt & 3) == 0) v[j] = __ldg(reinterpret_cast<const float4*>(p));
+                                else {
+                                    v[j].x = __ldg(p);
+                                    if (k + 1 < a.Kt) v[j].y = __ldg(p + 1);
+                                    if (k + 2 < a.Kt) v[j].z = __ldg(p + 2);
+                                    if (k + 3 < a.Kt) v[j].w = __ldg(p + 3);
+                                }
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int u = u0 + bt + j * kMxBWarps * 32;
+                        if (u < units) {
+                            const int ri = u / (kMxN * kc), r2 = u - ri * kMxN * kc, n = r2 / kc, c = r2 - n * kc;
+                            uint8_t* dst = base + (size_t)(2 * ri) * part_bytes + (size_t)(c >> 3) * 4096 + swz(n, c & 7);
+                            float4 l;
+                            l.x = v[j].x - __uint_as_float(__float_as_uint(v[j].x) & 0xffffe000u);
+                            l.y = v[j].y - __uint_as_float(__float_as_uint(v[j].y) & 0xffffe000u);
+                            l.z = v[j].z - __uint_as_float(__float_as_uint(v[j].z) & 0xffffe000u);
+                            l.w = v[j].w - __uint_as_float(__float_as_uint(v[j].w) & 0xffffe000u);
+                            *reinterpret_cast<float4*>(dst) = v[j];
+                            *reinterpret_cast<float4*>(dst + part_bytes) = l;
+                        }
+                    }
+                }
+            } else {
+                // k strided (n contiguous): one thread per (part, row n) gathers its K-row 32 values at a time
+                for (int task = bt; task < 2 * kMxN; task += kMxBWarps * 32) {
+                    const int ri = task / kMxN, n = task - ri * kMxN;
+                    const bool n_ok = n0 + n < a.Nt;
+                    const float* p = src + (size_t)ri * a.b_im + (size_t)(n0 + n) * a.b_sn;
+                    for (int ch = 0; ch < a.nchunks; ++ch) {
+                        float v[32];
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const int k = ch * 32 + j;
+                            v[j] = (n_ok && k < a.Kt) ? __ldg(p + (size_t)k * a.b_sk) : 0.f;
+                        }
+                        uint8_t* dst = base + (size_t)(2 * ri) * part_bytes + (size_t)ch * 4096;
+#pragma unroll
+                        for (int c4 = 0; c4 < 8; ++c4) {
+                            const float4 w = make_float4(v[4 * c4], v[4 * c4 + 1], v[4 * c4 + 2], v[4 * c4 + 3]);
+                            float4 l;
+                            l.x = w.x - __uint_as_float(__float_as_uint(w.x) & 0xffffe000u);
+                            l.y = w.y - __uint_as_float(__float_as_uint(w.y) & 0xffffe000u);
+                            l.z = w.z - __uint_as_float(__float_as_uint(w.z) & 0xffffe000u);
+                            l.w = w.w - __uint_as_float(__float_as_uint(w.w) & 0xffffe000u);
+                            *reinterpret_cast<float4*>(dst + swz(n, c4)) = w;
+                            *reinterpret_cast<float4*>(dst + part_bytes + swz(n, c4)) = l;
+                        }
+                    }
+                }
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&b_full[bb]);
+        }
+    } else {
+        // =========================================================================== A loaders (two warpgroups, buffer = warpgroup)
+        const int wg = (warp - 8) >> 2;
+        const int q4 = warp & 3;
+        const int L = q4 * 32 + lane;
+        const bool l_ok = L < a.Lt;
+        const uint32_t tb = tmem_base + ((uint32_t)(q4 * 32) << 16) + 128u * wg;
+        const uint32_t total = (uint32_t)my_items * (uint32_t)a.nchunks;
+        for (uint32_t q = (uint32_t)wg; q < total; q += 2) {
+            const int it = (int)(q / (uint32_t)a.nchunks), ch = (int)(q - (uint32_t)it * a.nchunks);
+            const int item = (int)blockIdx.x + it * (int)gridDim.x;
+            const int m = item / a.ntiles;
+            const float* p = a.a + (size_t)m * a.a_sm + (size_t)(ch * 32) * a.a_sk + (size_t)L * a.a_sl;
+            const int klim = l_ok ? a.Kt - ch * 32 : 0;
+            float vr[32], vi[32];
+            if (a.a_pair) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    float2 v = make_float2(0.f, 0.f);
+                    if (j < klim) v = ldf2(p);
+                    vr[j] = v.x; vi[j] = v.y;
+                    p += a.a_sk;
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    vr[j] = j < klim ? ldf(p) : 0.f;
+                    vi[j] = j < klim ? ldf(p + a.a_im) : 0.f;
+                    p += a.a_sk;
+                }
+            }
+            mbar_wait(&a_empty[wg], ((q >> 1) & 1) ^ 1);
+            tc_fence_after();
+            split_to_tmem16(tb, tb + 32u, vr, !a.single_pass);
+            split_to_tmem16(tb + 16u, tb + 48u, vr + 16, !a.single_pass);
+            split_to_tmem16(tb + 64u, tb + 96u, vi, !a.single_pass);
+            split_to_tmem16(tb + 80u, tb + 112u, vi + 16, !a.single_pass);
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&a_full[wg]);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4) tmem_dealloc(tmem_base, 512);
+}
+
+// out[c][b][a] = in[a][b][c] for 8-byte (complex64) elements; grid (ceil(C/32), ceil(A/32), B)
+__global__ void permute_c64_cba(const float2* __restrict__ in, float2* __restrict__ out, int A, int B, int C,
+                                long long out_c_stride) {
+    __shared__ float2 tile[32][33];
+    const int c0 = blockIdx.x * 32, a0 = blockIdx.y * 32, b = blockIdx.z;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;              // 32 x 8
+    for (int r = ty; r < 32; r += 8) {
+        const int aa = a0 + r, cc = c0 + tx;
+        if (aa < A && cc < C) tile[r][tx] = in[((size_t)aa * B + b) * C + cc];
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {
+        const int cc = c0 + r, aa = a0 + tx;
+        if (aa < A && cc < C) out[(size_t)cc * out_c_stride + (size_t)b * A + aa] = tile[tx][r];
+    }
+}
+
+static int mx_launch(MxArgs& a, const char* what, cudaStream_t st) {
+    a.nchunks = (a.Kt + 31) / 32;
+    a.ntiles = (a.Nt + kMxN - 1) / kMxN;
+    const long long items = (long long)a.nmodes * a.ntiles;
+    if (items > (1LL << 30)) return fail(FNM_EINVAL, "%s: too many work items", what);
+    a.items = (int)items;
+    size_t smem = 2 * 4 * (size_t)a.nchunks * 4096 + 1024 + 256;
+    if (smem < 120 * 1024) smem = 120 * 1024;
+    static bool attr_set = false;
+    if (!attr_set) {
+        const cudaError_t e = cudaFuncSetAttribute(mixgemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return fail(FNM_ECUDA, "%s: smem attribute: %s", what, cudaGetErrorString(e));
+        attr_set = true;
+    }
+    const int grid = a.items < sm_count() ? a.items : sm_count();
+    {
+        LaunchScope ls(what, st);
+        mixgemm_tc<<<grid, kMxThreads, smem, st>>>(a);
+    }
+    return check_launch(what);
+}
+
+}  // namespace tc
+
+using namespace tc;
+
+bool tc_mix_supported(int B, int Ci, int Co) {
+    if (!tc_enabled()) return false;
+    { const char* e = getenv("FNM_DISABLE_TCMIX"); if (e && e[0] == '1') return false; }
+    return B >= 1 && B <= 192 && Ci >= 8 && Co >= 8 && Ci <= 128 && Co <= 128;   // wgrad stages K = B in shared memory
+}
+
+// scratch (floats) for the mode-major copies: W1 + W2 (2 x nm*Ci*Co complex) or dW (nm*Ci*Co complex)
+size_t tc_mix_shadow_floats(int nmodes, int Ci, int Co) { return (size_t)nmodes * Ci * Co * 2; }
+
+// W (Ci,Co,rpw*NY) [x2 tensors] -> W1[m][i][o] (which = 0) or W2[m][o][i] (which = 1)
+int tc_mix_pack(const float* w0, const float* w1, int rpw, int R, int NY, int Ci, int Co, int which, float* dst,
+                cudaStream_t st) {
+    const int nm = rpw * NY;                                    // modes per weight tensor
+    const int ntens = (R == rpw) ? 1 : 2;
+    for (int t = 0; t < ntens; ++t) {
+        const float2* src = reinterpret_cast<const float2*>(t == 0 ? w0 : w1);
+        float2* out = reinterpret_cast<float2*>(dst) + (size_t)t * nm * Ci * Co;
+        LaunchScope ls("mix_pack", st);
+        if (which == 0) {
+            // in[a = (i,o)][b = 1][c = m] -> out[m][(i,o)]
+            dim3 grid((nm + 31) / 32, (Ci * Co + 31) / 32, 1);
+            permute_c64_cba<<<grid, 256, 0, st>>>(src, out, Ci * Co, 1, nm, (long long)Ci * Co);
+        } else {
+            // in[a = i][b = o][c = m] -> out[m][o][i]
+            dim3 grid((nm + 31) / 32, (Ci + 31) / 32, Co);
+            permute_c64_cba<<<grid, 256, 0, st>>>(src, out, Ci, Co, nm, (long long)Ci * Co);
+        }
+    }
+    return check_launch("mix_pack");
+}
+
+// dW1[m][i][o] -> dw (Ci,Co,rpw*NY) [x2 tensors]
+int tc_mix_unpack(const float* dW1, float* dw0, float* dw1, int rpw, int R, int NY, int Ci, int Co, cudaStream_t st) {
+    const int nm = rpw * NY;
+    const int ntens = (R == rpw) ? 1 : 2;
+    for (int t = 0; t < ntens; ++t) {
+        const float2* src = reinterpret_cast<const float2*>(dW1) + (size_t)t * nm * Ci * Co;
+        float2* out = reinterpret_cast<float2*>(t == 0 ? dw0 : dw1);
+        LaunchScope ls("mix_unpack", st);
+        // in[a = m][b = 1][c = (i,o)] -> out[(i,o)][m]
+        dim3 grid((Ci * Co + 31) / 32, (nm + 31) / 32, 1);
+        permute_c64_cba<<<grid, 256, 0, st>>>(src, out, nm, 1, Ci * Co, (long long)nm);
+    }
+    return check_launch("mix_unpack");
+}
+
+// Oh[m][ro][b][o] = sum_i Xh[m][ri][b][i] W1[m][i][o]      (conj = 0, W = W1, Kt = Ci, Lt = Co)
+// Gxh[m][ri][b][i] = sum_o Gh[m][ro][b][o] conj(W2[m][o][i]) (conj = 1, W = W2, Kt = Co, Lt = Ci)
+int tc_mix_apply(const float* Wm, const float* In, float* Out, int nmodes, int B, int Kt, int Lt, int conj, int mode,
+                 const char* what, cudaStream_t st) {
+    MxArgs a{};
+    a.a = Wm; a.b = In; a.out = Out;
+    a.Kt = Kt; a.Lt = Lt; a.Nt = B; a.nmodes = nmodes;
+    a.a_sm = (long long)Kt * Lt * 2; a.a_sk = (long long)Lt * 2; a.a_sl = 2; a.a_im = 1; a.a_pair = 1;
+    a.b_sm = (long long)2 * B * Kt; a.b_sn = Kt; a.b_sk = 1; a.b_im = (long long)B * Kt; a.b_kcontig = 1;
+    a.o_sm = (long long)2 * B * Lt; a.o_sn = Lt; a.o_sl = 1; a.o_im = (long long)B * Lt; a.o_pair = 0;
+    a.conj = conj; a.single_pass = mode == FNM_MODE_TF32;
+    return mx_launch(a, what, st);
+}
+
+// dW1[m][i][o] = sum_b conj(Xh[m][.][b][i]) Gh[m][.][b][o]
+int tc_mix_wgrad(const float* Xh, const float* Gh, float* dW1, int nmodes, int B, int Ci, int Co, int mode, cudaStream_t st) {
+    MxArgs a{};
+    a.a = Xh; a.b = Gh; a.out = dW1;
+    a.Kt = B; a.Lt = Ci; a.Nt = Co; a.nmodes = nmodes;
+    a.a_sm = (long long)2 * B * Ci; a.a_sk = Ci; a.a_sl = 1; a.a_im = (long long)B * Ci; a.a_pair = 0;
+    a.b_sm = (long long)2 * B * Co; a.b_sn = 1; a.b_sk = Co; a.b_im = (long long)B * Co; a.b_kcontig = 0;
+    a.o_sm = (long long)Ci * Co * 2; a.o_sn = 2; a.o_sl = (long long)Co * 2; a.o_im = 1; a.o_pair = 1;
+    a.conj = 1; a.single_pass = mode == FNM_MODE_TF32;
+    return mx_launch(a, "mix_bwd_w", st);
+}
+
+}  // namespace fnm

@@ -162,15 +162,22 @@ int fnm_xdft(const float* T, const float* ex, float* Xh, int B, int P1, int R, i
 /* Z[b][x][ro][l][c] = sum_{ri,r} fx[(x,ro)][(ri,r)] Oh[r][l][ri][b][c]   (inverse C2C along x)       */
 int fnm_xsyn(const float* Oh, const float* fx, float* Z, int B, int S1, int R, int NY, int C, int mode,
              fnm_stream_t stream);
-/* compl_mul (shared.py:48-53): Oh[m][.][b][o] = sum_i Xh[m][.][b][i] W[i][o][m]  (complex)           */
+/* compl_mul (shared.py:48-53) and its two backward products.  `workspace` (fnm_mix_workspace_bytes; may be
+ * NULL) lets the tcgen05 path make a mode-major copy of the weights / of dW; without it the fp32 SIMT
+ * kernels run on the reference layout.
+ *   Oh[m][.][b][o]  = sum_i Xh[m][.][b][i] W[i][o][m]                (complex)
+ *   Gxh[m][.][b][i] = sum_o Gh[m][.][b][o] conj(W[i][o][m])
+ *   dW[i][o][m]     = sum_b conj(Xh[m][.][b][i]) Gh[m][.][b][o]      (written in the reference layout)        */
+size_t fnm_mix_workspace_bytes(int B, int R, int NY, int Ci, int Co);
 int fnm_mix_fwd(const float* Xh, const float* w0, const float* w1, int rows_per_w, float* Oh,
-                int B, int R, int NY, int Ci, int Co, fnm_stream_t stream);
-/* Gxh[m][.][b][i] = sum_o Gh[m][.][b][o] conj(W[i][o][m]) */
+                int B, int R, int NY, int Ci, int Co, void* workspace, size_t workspace_bytes, int mode,
+                fnm_stream_t stream);
 int fnm_mix_bwd_x(const float* Gh, const float* w0, const float* w1, int rows_per_w, float* Gxh,
-                  int B, int R, int NY, int Ci, int Co, fnm_stream_t stream);
-/* dW[i][o][m] = sum_b conj(Xh[m][.][b][i]) Gh[m][.][b][o]  (written in the reference layout)          */
+                  int B, int R, int NY, int Ci, int Co, void* workspace, size_t workspace_bytes, int mode,
+                  fnm_stream_t stream);
 int fnm_mix_bwd_w(const float* Xh, const float* Gh, float* dw0, float* dw1, int rows_per_w,
-                  int B, int R, int NY, int Ci, int Co, fnm_stream_t stream);
+                  int B, int R, int NY, int Ci, int Co, void* workspace, size_t workspace_bytes, int mode,
+                  fnm_stream_t stream);
 /* fused pointwise + y-synthesis + epilogue (irfft along y fused with the 1x1 conv, bias, and the
  * GELU' of the backward pass):
  *   out[row][y][n] = ( sum_k f(x[row][y][k]) Wk[k][n] + sum_l' by[y][l'] Z[row][l'][n] + bias[n] )

@@ -189,6 +189,45 @@ def test_conv_wgrad(npos, Ci, Co, act, mode):
     assert rel_l2(dbc, g.double().sum(0)) < 1e-5
 
 
+@pytest.mark.parametrize("B,R,NY,rpw,Ci,Co", [(20, 24, 12, 12, 32, 32), (32, 8, 32, 4, 128, 128), (64, 1, 16, 1, 64, 64),
+                                              (5, 6, 5, 3, 20, 24), (40, 4, 7, 4, 48, 32), (3, 2, 3, 1, 8, 16)])
+@pytest.mark.parametrize("mode", ["fp32", "tf32"])
+@pytest.mark.parametrize("use_ws", [True, False])
+def test_mix_stages(B, R, NY, rpw, Ci, Co, mode, use_ws):
+    """compl_mul and its two backward products against complex128 einsums; with the scratch buffer the
+    tcgen05 path (mode-major weight copy) runs, without it the SIMT kernels on the reference layout."""
+    torch.manual_seed(4)
+    two = rpw != R
+    w0 = torch.randn(Ci, Co, rpw, NY, dtype=torch.complex64, device=DEV) / Ci ** 0.5
+    w1 = torch.randn(Ci, Co, rpw, NY, dtype=torch.complex64, device=DEV) / Ci ** 0.5 if two else None
+    W = torch.cat([w0, w1], 2) if two else w0                              # (Ci, Co, R, NY)
+    Xh = torch.randn(R, NY, 2, B, Ci, device=DEV)
+    Gh = torch.randn(R, NY, 2, B, Co, device=DEV)
+    Xc = torch.complex(Xh[:, :, 0].double(), Xh[:, :, 1].double())          # (R, NY, B, Ci)
+    Gc = torch.complex(Gh[:, :, 0].double(), Gh[:, :, 1].double())
+    Wc = W.to(torch.complex128)
+    L = lib()
+    m = 0 if mode == "fp32" else 1
+    tol = TOL_FP32 if mode == "fp32" else TOL_TF32
+    nb = L.fnm_mix_workspace_bytes(B, R, NY, Ci, Co) if use_ws else 0
+    ws = torch.empty(max(nb, 16), dtype=torch.uint8, device=DEV) if use_ws else None
+    wr = lambda t: None if t is None else _p(torch.view_as_real(t))
+    Oh = torch.full((R, NY, 2, B, Co), float("nan"), device=DEV)
+    check(L.fnm_mix_fwd(_p(Xh), wr(w0), wr(w1), rpw, _p(Oh), B, R, NY, Ci, Co, _p(ws), nb, m, _stream()), "fnm_mix_fwd")
+    ref = torch.einsum("rlbi,iorl->rlbo", Xc, Wc)
+    assert rel_l2(torch.complex(Oh[:, :, 0], Oh[:, :, 1]), ref) < tol
+    Gx = torch.full((R, NY, 2, B, Ci), float("nan"), device=DEV)
+    check(L.fnm_mix_bwd_x(_p(Gh), wr(w0), wr(w1), rpw, _p(Gx), B, R, NY, Ci, Co, _p(ws), nb, m, _stream()), "fnm_mix_bwd_x")
+    ref = torch.einsum("rlbo,iorl->rlbi", Gc, Wc.conj())
+    assert rel_l2(torch.complex(Gx[:, :, 0], Gx[:, :, 1]), ref) < tol
+    dw0 = torch.full_like(w0, float("nan"))
+    dw1 = torch.full_like(w1, float("nan")) if two else None
+    check(L.fnm_mix_bwd_w(_p(Xh), _p(Gh), wr(dw0), wr(dw1), rpw, B, R, NY, Ci, Co, _p(ws), nb, m, _stream()), "fnm_mix_bwd_w")
+    ref = torch.einsum("rlbi,rlbo->iorl", Xc.conj(), Gc)
+    got = torch.cat([dw0, dw1], 2) if two else dw0
+    assert rel_l2(got, ref) < tol
+
+
 def test_gelu_kernels():
     z = torch.randn(100003, device=DEV) * 3
     g = torch.randn_like(z)

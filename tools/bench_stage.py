@@ -60,6 +60,16 @@ timeit("ydft noact tf32", lambda: check(L.fnm_ydft(p(x), p(tab["ay"]), p(T), row
 Xh = torch.empty(R, NY, 2, B, C_, device=dev)
 timeit("xdft (T + Xh)", lambda: check(L.fnm_xdft(p(T), p(tab["ex"]), p(Xh), B, P1, R, NY, C_, 0, st)), (T.numel() + Xh.numel()) * 4)
 timeit("xsyn (Xh + Z)", lambda: check(L.fnm_xsyn(p(Xh), p(tab["fx"]), p(Z), B, P1, R, NY, C_, 0, st)), (Z.numel() + Xh.numel()) * 4)
+w0 = torch.randn(C_, C_, m1, m2, dtype=torch.complex64, device=dev) / C_
+w1 = torch.randn(C_, C_, m1, m2, dtype=torch.complex64, device=dev) / C_
+w0r, w1r = torch.view_as_real(w0), torch.view_as_real(w1)
+mws = torch.empty(max(L.fnm_mix_workspace_bytes(B, R, NY, C_, C_), 16), dtype=torch.uint8, device=dev)
+Oh = torch.empty_like(Xh)
+WB = w0.numel() * 16
+timeit("mix_fwd (W + 2 spectra)", lambda: check(L.fnm_mix_fwd(p(Xh), p(w0r), p(w1r), m1, p(Oh), B, R, NY, C_, C_, p(mws), mws.numel(), 0, st)), WB + 2 * Xh.numel() * 4)
+timeit("mix_bwd_x", lambda: check(L.fnm_mix_bwd_x(p(Xh), p(w0r), p(w1r), m1, p(Oh), B, R, NY, C_, C_, p(mws), mws.numel(), 0, st)), WB + 2 * Xh.numel() * 4)
+dw0, dw1 = torch.empty_like(w0r), torch.empty_like(w1r)
+timeit("mix_bwd_w", lambda: check(L.fnm_mix_bwd_w(p(Xh), p(Oh), p(dw0), p(dw1), m1, B, R, NY, C_, C_, p(mws), mws.numel(), 0, st)), WB + 2 * Xh.numel() * 4)
 ws = torch.empty(L.fnm_conv_wgrad_workspace_bytes(rows * P2, C_, C_), dtype=torch.uint8, device=dev)
 dwc, dbc = torch.empty(C_, C_, device=dev), torch.empty(C_, device=dev)
 timeit("conv_wgrad noact (2A)", lambda: check(L.fnm_conv_wgrad(p(g), p(x), 0, p(dwc), p(dbc), rows * P2, C_, C_, p(ws), ws.numel(), 0, st)), 2 * A)
