@@ -191,12 +191,15 @@ def kernel_algorithmic_bytes(name, wl, model):
     A = 4*B*C*P1*P2 bytes is one fp32 activation of the trunk."""
     A, L, lyf = wl["A"], wl["layers"], wl["ly_frac"]
     return {
-        "pointwise_ysyn": L * (2 * A + 3 * A),          # fwd: read x, write z; bwd: read g_z, z_prev, write g_in
+        # fwd: read x, write z (2A; the activated copy some launches also write is a design choice, not counted);
+        # bwd: read g_z, z_prev, write g_in (3A; the first layer has no GELU' operand: 2A)
+        "pointwise_ysyn": L * 2 * A + (L - 1) * 3 * A + 2 * A,
         "ydft": 2 * L * A * (1 + lyf),                  # fwd + bwd analysis: read A, write the LY/P2 partial transform
         "conv_wgrad": L * 2 * A,                        # read g_z and x
         "adam": 28 * wl["n_real_params"],               # read p,g,m,v; write p,m,v
         "xdft": 2 * L * A * lyf, "xsyn": 2 * L * A * lyf,
         "mix_fwd": L * wl["w_bytes"], "mix_bwd_x": L * wl["w_bytes"], "mix_bwd_w": L * wl["w_bytes"],
+        "mix_pack": 2 * L * 2 * wl["w_bytes"], "mix_unpack": L * 2 * wl["w_bytes"],
     }.get(name)
 
 
@@ -323,8 +326,15 @@ def run_ours(args, rank, world):
                         "algorithmic_GB_per_step": None if ab is None else round(ab / 1e9, 4),
                         "GBps": None if ab is None or t <= 0 else round(ab / 1e6 / t, 1)})
     top = kernels[0]
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
+    if os.path.exists(tpath):                      # dram read+write bytes per launch from the committed ncu capture
+        tj = json.load(open(tpath))
+        if tj.get("workload") == args.workload:
+            tv = tj["per_launch_bytes"].get(top["name"])
+            traffic = tv.get("step_average") if isinstance(tv, dict) else tv
     roofline = {"kernel": top["name"], "bound": "hbm", "achieved": top["GBps"], "peak": peak, "unit": "GB/s",
-                "frac": None if top["GBps"] is None else round(top["GBps"] / peak, 4), "traffic": None,
+                "frac": None if top["GBps"] is None else round(top["GBps"] / peak, 4), "traffic": traffic,
                 "peak_source": peak_src, "launches_per_step": top["launches_per_step"],
                 "ms_per_launch": round(top["ms_per_step"] / max(top["launches_per_step"], 1), 4),
                 "algorithmic_bytes_per_step": None if top["algorithmic_GB_per_step"] is None else top["algorithmic_GB_per_step"] * 1e9,
