@@ -59,6 +59,12 @@ PROTOTYPES = {
     "fnm_mix_bwd_w": (_i32, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _sz, _i32, _vp]),
     "fnm_pointwise_ysyn": (_i32, [_vp, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32,
                                   _i32, _vp]),
+    "fnm_lift_fwd": (_i32, [_vp, _vp, _vp, _vp] + [_i32] * 8 + [_vp]),
+    "fnm_lift_bwd_workspace_bytes": (_sz, [_i32, _i32]),
+    "fnm_lift_bwd": (_i32, [_vp, _vp, _vp, _vp] + [_i32] * 8 + [_vp, _sz, _vp]),
+    "fnm_mlp_head_fwd": (_i32, [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _vp]),
+    "fnm_mlp_head_bwd_workspace_bytes": (_sz, [_i32, _i32]),
+    "fnm_mlp_head_bwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _vp, _sz, _vp]),
     "fnm_conv_wgrad_workspace_bytes": (_sz, [_i64, _i32, _i32]),
     "fnm_conv_wgrad": (_i32, [_vp, _vp, _i32, _vp, _vp, _i64, _i32, _i32, _vp, _sz, _i32, _vp]),
 }

@@ -231,12 +231,13 @@ int fnm_mix_bwd_w(const float* Xh, const float* Gh, float* dw0, float* dw1, int 
 int fnm_pointwise_ysyn(const float* x, int act_in, const float* wc, int wc_is_kn, const float* bias, const float* Z,
                        const float* by, const float* mul_gelu_grad_of, float* out, float* out_act, int64_t rows, int S2,
                        int LY, int K, int N, int mode, fnm_stream_t stream) {
-    FNM_REQUIRE(Z && by && out, "pointwise_ysyn: NULL pointer");
-    FNM_REQUIRE(rows >= 0 && S2 > 0 && LY > 0 && N > 0 && K >= 0, "pointwise_ysyn: bad extents");
+    FNM_REQUIRE(out && (LY == 0 || (Z && by)), "pointwise_ysyn: NULL pointer");
+    FNM_REQUIRE(rows >= 0 && S2 > 0 && LY >= 0 && N > 0 && K >= 0, "pointwise_ysyn: bad extents");
+    FNM_REQUIRE(LY > 0 || (x && wc && K > 0), "pointwise_ysyn: nothing to compute (no spectral and no pointwise term)");
     FNM_REQUIRE((x == nullptr) == (wc == nullptr) || K == 0, "pointwise_ysyn: x and wc must be given together");
     if (tc_pw2_supported(rows, S2, LY, (x && wc) ? K : 0, N, (x && wc) ? act_in : 0, (x && wc) ? x : nullptr, Z, by))
         return tc_pw2(x, wc, wc_is_kn, bias, Z, by, mul_gelu_grad_of, out, out_act, rows, S2, LY, K, N, mode, as_stream(stream));
-    if (tc_pointwise_ysyn_supported(rows, S2, LY, (x && wc) ? K : 0, N))
+    if (LY > 0 && tc_pointwise_ysyn_supported(rows, S2, LY, (x && wc) ? K : 0, N))
         return tc_pointwise_ysyn(x, act_in, wc, wc_is_kn, bias, Z, by, mul_gelu_grad_of, out, out_act, rows, S2, LY, K, N,
                                  mode, as_stream(stream));
     return simt_pointwise_ysyn(x, act_in, wc, wc_is_kn, bias, Z, by, mul_gelu_grad_of, out, out_act, rows, S2, LY, K, N,

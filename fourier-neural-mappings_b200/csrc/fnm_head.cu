@@ -1,0 +1,343 @@
+// The two ends of the trunk, fused so that no activation-sized temporary is made:
+//
+//   lift      fc0 on [data channels, grid coordinates] + zero padding, written channels-last padded
+//             (models/func_to_func2d.py:79-86, shared.py:111-118,150-159) and its weight gradient
+//   mlp head  fc2(GELU(h1)) of the projection MLP (shared.py:26-45; func_to_func2d.py:104-107) and its
+//             backward "gate"  g_h1 = (g_out w2) * GELU'(h1)  together with dW2 / db2
+//
+// fc1 itself (a 1x1 convolution C -> width_final over every position) runs on the TMA/tcgen05 fused
+// pointwise kernel with no spectral term (fnm_pointwise_ysyn, LY = 0), its weight gradient on
+// conv_wgrad.  These kernels are plain bandwidth-bound SIMT passes.
+#include "fnm_common.cuh"
+#include "fnm_stages.cuh"
+
+namespace fnm {
+
+constexpr int kLiftMaxJ = 8;          // data channels + grid coordinates
+
+struct LiftArgs {
+    const float* x; const float* w; const float* b; float* out;
+    const float* g; float* partial;
+    int B, Din, N1, N2, P1, P2, C, ngrid, J;
+};
+
+__device__ __forceinline__ float lift_feat(const LiftArgs& a, int j, int b, int xx, int yy) {
+    if (j < a.Din) return __ldg(a.x + (((size_t)b * a.Din + j) * a.N1 + xx) * a.N2 + yy);
+    const int gi = j - a.Din;
+    // torch.linspace(0, 1, n): i / (n - 1); 2-D: first coordinate along x, second along y; 1-D: along y
+    if (a.ngrid == 2 && gi == 0) return a.N1 > 1 ? (float)xx / (float)(a.N1 - 1) : 0.f;
+    return a.N2 > 1 ? (float)yy / (float)(a.N2 - 1) : 0.f;
+}
+
+__global__ void lift_fwd_kernel(const LiftArgs a) {
+    extern __shared__ float sw[];                         // [J + 1][C]: weights transposed, then bias
+    const int C4 = a.C / 4;
+    for (int i = threadIdx.x; i < (a.J + 1) * a.C; i += blockDim.x) {
+        const int j = i / a.C, c = i - j * a.C;
+        sw[i] = j < a.J ? __ldg(a.w + (size_t)c * a.J + j) : __ldg(a.b + c);
+    }
+    __syncthreads();
+    const long long total = (long long)a.B * a.P1 * a.P2 * C4;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c4 = (int)(i % C4);
+        const long long pos = i / C4;
+        const int yy = (int)(pos % a.P2);
+        const long long r = pos / a.P2;
+        const int xx = (int)(r % a.P1), b = (int)(r / a.P1);
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (xx < a.N1 && yy < a.N2) {
+            v = *reinterpret_cast<const float4*>(sw + a.J * a.C + c4 * 4);
+            for (int j = 0; j < a.J; ++j) {
+                const float f = lift_feat(a, j, b, xx, yy);
+                const float4 w = *reinterpret_cast<const float4*>(sw + j * a.C + c4 * 4);
+                v.x = fmaf(f, w.x, v.x); v.y = fmaf(f, w.y, v.y); v.z = fmaf(f, w.z, v.z); v.w = fmaf(f, w.w, v.w);
+            }
+        }
+        *reinterpret_cast<float4*>(a.out + pos * a.C + c4 * 4) = v;
+    }
+}
+
+// partial[block][j][c] = sum over the block's positions of g[pos][c] * feat_j(pos)   (j == J: bias)
+__global__ void lift_bwd_kernel(const LiftArgs a) {
+    extern __shared__ float red[];                        // [slots][(J+1)][C]
+    const int C4 = a.C / 4;
+    const int slots = blockDim.x / C4;
+    const int c4 = threadIdx.x % C4, slot = threadIdx.x / C4;
+    float4 acc[kLiftMaxJ + 1];
+#pragma unroll
+    for (int j = 0; j <= kLiftMaxJ; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const long long npos = (long long)a.B * a.N1 * a.N2;      // un-padded positions only
+    if (slot < slots) {
+        for (long long q = (long long)blockIdx.x * slots + slot; q < npos; q += (long long)gridDim.x * slots) {
+            const int yy = (int)(q % a.N2);
+            const long long r = q / a.N2;
+            const int xx = (int)(r % a.N1), b = (int)(r / a.N1);
+            const float4 g = __ldg(reinterpret_cast<const float4*>(a.g + (((size_t)b * a.P1 + xx) * a.P2 + yy) * a.C + c4 * 4));
+#pragma unroll
+            for (int j = 0; j < kLiftMaxJ; ++j) {
+                if (j < a.J) {
+                    const float f = lift_feat(a, j, b, xx, yy);
+                    acc[j].x = fmaf(f, g.x, acc[j].x); acc[j].y = fmaf(f, g.y, acc[j].y);
+                    acc[j].z = fmaf(f, g.z, acc[j].z); acc[j].w = fmaf(f, g.w, acc[j].w);
+                }
+            }
+            acc[kLiftMaxJ].x += g.x; acc[kLiftMaxJ].y += g.y; acc[kLiftMaxJ].z += g.z; acc[kLiftMaxJ].w += g.w;
+        }
+        for (int j = 0; j <= a.J; ++j) {
+            const float4 v = j < a.J ? acc[j] : acc[kLiftMaxJ];
+            *reinterpret_cast<float4*>(red + ((size_t)slot * (a.J + 1) + j) * a.C + c4 * 4) = v;
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < (a.J + 1) * a.C; i += blockDim.x) {
+        float s = 0.f;
+        for (int k = 0; k < slots; ++k) s += red[(size_t)k * (a.J + 1) * a.C + i];
+        a.partial[(size_t)blockIdx.x * (a.J + 1) * a.C + i] = s;
+    }
+}
+
+__global__ void lift_bwd_reduce(const float* __restrict__ partial, int nblocks, int J, int C, float* __restrict__ dw,
+                                float* __restrict__ db) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (J + 1) * C) return;
+    float s = 0.f;
+    for (int k = 0; k < nblocks; ++k) s += partial[(size_t)k * (J + 1) * C + i];
+    const int j = i / C, c = i - j * C;
+    if (j < J) { if (dw) dw[(size_t)c * J + j] = s; }
+    else if (db) db[c] = s;
+}
+
+// ---- projection head: out[pos][d] = sum_h w2[d][h] GELU(h1[pos][h]) + b2[d]
+constexpr int kHeadMaxD = 4;
+constexpr int kHeadMaxH4 = 1;         // H <= 128: one float4 group per lane (wider heads fall back to torch)
+
+struct HeadArgs {
+    const float* h1; const float* g_out; const float* w2; const float* b2;
+    float* out; float* g_h1; float* partial;
+    long long npos;
+    int H, D;
+};
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+
+__global__ void head_fwd_kernel(const HeadArgs a) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int H4 = a.H / 4;
+    float4 w[kHeadMaxD][kHeadMaxH4];
+#pragma unroll
+    for (int d = 0; d < kHeadMaxD; ++d)
+#pragma unroll
+        for (int k = 0; k < kHeadMaxH4; ++k) {
+            const int h4 = lane + 32 * k;
+            w[d][k] = (d < a.D && h4 < H4) ? __ldg(reinterpret_cast<const float4*>(a.w2 + (size_t)d * a.H) + h4)
+                                           : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    for (long long pos = (long long)blockIdx.x * nw + warp; pos < a.npos; pos += (long long)gridDim.x * nw) {
+        float s[kHeadMaxD];
+#pragma unroll
+        for (int d = 0; d < kHeadMaxD; ++d) s[d] = 0.f;
+#pragma unroll
+        for (int k = 0; k < kHeadMaxH4; ++k) {
+            const int h4 = lane + 32 * k;
+            if (h4 < H4) {
+                float4 v = __ldg(reinterpret_cast<const float4*>(a.h1 + pos * a.H) + h4);
+                v.x = gelu_erf(v.x); v.y = gelu_erf(v.y); v.z = gelu_erf(v.z); v.w = gelu_erf(v.w);
+#pragma unroll
+                for (int d = 0; d < kHeadMaxD; ++d)
+                    s[d] += v.x * w[d][k].x + v.y * w[d][k].y + v.z * w[d][k].z + v.w * w[d][k].w;
+            }
+        }
+#pragma unroll
+        for (int d = 0; d < kHeadMaxD; ++d)
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) s[d] += __shfl_xor_sync(0xffffffffu, s[d], o);
+        if (lane == 0)
+            for (int d = 0; d < a.D; ++d) a.out[pos * a.D + d] = s[d] + (a.b2 ? __ldg(a.b2 + d) : 0.f);
+    }
+}
+
+// g_h1[pos][h] = (sum_d g_out[pos][d] w2[d][h]) * GELU'(h1[pos][h]);  partial sums of
+// dW2[d][h] = sum_pos g_out[pos][d] GELU(h1[pos][h]) and db2[d] = sum_pos g_out[pos][d]
+__global__ void head_bwd_kernel(const HeadArgs a) {
+    extern __shared__ float red[];                        // [warps][D][H] + [warps][D]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int H4 = a.H / 4;
+    float4 w[kHeadMaxD][kHeadMaxH4], dw[kHeadMaxD][kHeadMaxH4];
+    float dbs[kHeadMaxD];
+#pragma unroll
+    for (int d = 0; d < kHeadMaxD; ++d) {
+        dbs[d] = 0.f;
+#pragma unroll
+        for (int k = 0; k < kHeadMaxH4; ++k) {
+            const int h4 = lane + 32 * k;
+            w[d][k] = (d < a.D && h4 < H4) ? __ldg(reinterpret_cast<const float4*>(a.w2 + (size_t)d * a.H) + h4)
+                                           : make_float4(0.f, 0.f, 0.f, 0.f);
+            dw[d][k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
+    for (long long pos = (long long)blockIdx.x * nw + warp; pos < a.npos; pos += (long long)gridDim.x * nw) {
+        float g[kHeadMaxD];
+#pragma unroll
+        for (int d = 0; d < kHeadMaxD; ++d) {
+            g[d] = d < a.D ? __ldg(a.g_out + pos * a.D + d) : 0.f;
+            dbs[d] += g[d];
+        }
+#pragma unroll
+        for (int k = 0; k < kHeadMaxH4; ++k) {
+            const int h4 = lane + 32 * k;
+            if (h4 < H4) {
+                const float4 v = __ldg(reinterpret_cast<const float4*>(a.h1 + pos * a.H) + h4);
+                float4 gg = make_float4(0.f, 0.f, 0.f, 0.f);
+                const float4 act = make_float4(gelu_erf(v.x), gelu_erf(v.y), gelu_erf(v.z), gelu_erf(v.w));
+#pragma unroll
+                for (int d = 0; d < kHeadMaxD; ++d) {
+                    gg.x = fmaf(g[d], w[d][k].x, gg.x); gg.y = fmaf(g[d], w[d][k].y, gg.y);
+                    gg.z = fmaf(g[d], w[d][k].z, gg.z); gg.w = fmaf(g[d], w[d][k].w, gg.w);
+                    dw[d][k].x = fmaf(g[d], act.x, dw[d][k].x); dw[d][k].y = fmaf(g[d], act.y, dw[d][k].y);
+                    dw[d][k].z = fmaf(g[d], act.z, dw[d][k].z); dw[d][k].w = fmaf(g[d], act.w, dw[d][k].w);
+                }
+                gg.x *= gelu_grad_f(v.x); gg.y *= gelu_grad_f(v.y); gg.z *= gelu_grad_f(v.z); gg.w *= gelu_grad_f(v.w);
+                *(reinterpret_cast<float4*>(a.g_h1 + pos * a.H) + h4) = gg;
+            }
+        }
+    }
+    // block reduction of dW2 / db2 partials
+    float* rw = red;                                       // [nw][D][H]
+    float* rb = red + (size_t)nw * a.D * a.H;              // [nw][D]
+    for (int d = 0; d < a.D; ++d) {
+#pragma unroll
+        for (int k = 0; k < kHeadMaxH4; ++k) {
+            const int h4 = lane + 32 * k;
+            if (h4 < H4) *reinterpret_cast<float4*>(rw + ((size_t)warp * a.D + d) * a.H + h4 * 4) = dw[d][k];
+        }
+        if (lane == 0) rb[warp * a.D + d] = dbs[d];
+    }
+    __syncthreads();
+    const int per = a.D * a.H + a.D;
+    for (int i = threadIdx.x; i < per; i += blockDim.x) {
+        float s = 0.f;
+        if (i < a.D * a.H) { for (int k = 0; k < nw; ++k) s += rw[(size_t)k * a.D * a.H + i]; }
+        else { for (int k = 0; k < nw; ++k) s += rb[k * a.D + (i - a.D * a.H)]; }
+        a.partial[(size_t)blockIdx.x * per + i] = s;
+    }
+}
+
+__global__ void head_bwd_reduce(const float* __restrict__ partial, int nblocks, int H, int D, float* __restrict__ dw2,
+                                float* __restrict__ db2) {
+    const int per = D * H + D;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= per) return;
+    float s = 0.f;
+    for (int k = 0; k < nblocks; ++k) s += partial[(size_t)k * per + i];
+    if (i < D * H) { if (dw2) dw2[i] = s; }
+    else if (db2) db2[i - D * H] = s;
+}
+
+constexpr int kEndBlocks = 148 * 4;
+
+static bool lift_ok(int Din, int C, int ngrid) { return Din >= 0 && Din + ngrid >= 1 && Din + ngrid <= kLiftMaxJ && C % 4 == 0 && C >= 4 && C <= 1024; }
+
+}  // namespace fnm
+
+using namespace fnm;
+
+extern "C" {
+
+int fnm_lift_fwd(const float* x, const float* w, const float* b, float* out, int B, int Din, int N1, int N2, int P1,
+                 int P2, int C, int ngrid, fnm_stream_t stream) {
+    FNM_REQUIRE(x && w && b && out, "lift_fwd: NULL pointer");
+    FNM_REQUIRE(B > 0 && N1 > 0 && N2 > 0 && P1 >= N1 && P2 >= N2 && ngrid >= 0 && ngrid <= 2, "lift_fwd: bad extents");
+    if (!lift_ok(Din, C, ngrid)) return fail(FNM_ENOTSUP, "lift_fwd: unsupported channel counts");
+    LiftArgs a{};
+    a.x = x; a.w = w; a.b = b; a.out = out; a.B = B; a.Din = Din; a.N1 = N1; a.N2 = N2; a.P1 = P1; a.P2 = P2; a.C = C;
+    a.ngrid = ngrid; a.J = Din + ngrid;
+    const long long total = (long long)B * P1 * P2 * (C / 4);
+    const int grid = (int)((total + 255) / 256 < kEndBlocks * 4 ? (total + 255) / 256 : kEndBlocks * 4);
+    {
+        LaunchScope ls("lift_fwd", as_stream(stream));
+        lift_fwd_kernel<<<grid, 256, (a.J + 1) * C * sizeof(float), as_stream(stream)>>>(a);
+    }
+    return check_launch("lift_fwd");
+}
+
+size_t fnm_lift_bwd_workspace_bytes(int C, int J) { return align_up((size_t)kEndBlocks * (J + 1) * C * sizeof(float), 256); }
+
+int fnm_lift_bwd(const float* g, const float* x, float* dw, float* db, int B, int Din, int N1, int N2, int P1, int P2,
+                 int C, int ngrid, void* workspace, size_t workspace_bytes, fnm_stream_t stream) {
+    FNM_REQUIRE(g && x && workspace, "lift_bwd: NULL pointer");
+    if (!lift_ok(Din, C, ngrid) || C > 512) return fail(FNM_ENOTSUP, "lift_bwd: unsupported channel counts");
+    const int J = Din + ngrid;
+    if (workspace_bytes < fnm_lift_bwd_workspace_bytes(C, J)) return fail(FNM_EWORKSPACE, "lift_bwd: workspace too small");
+    LiftArgs a{};
+    a.g = g; a.x = x; a.partial = static_cast<float*>(workspace);
+    a.B = B; a.Din = Din; a.N1 = N1; a.N2 = N2; a.P1 = P1; a.P2 = P2; a.C = C; a.ngrid = ngrid; a.J = J;
+    const int C4 = C / 4;
+    int threads = 256;
+    if (threads < C4) threads = (C4 + 31) / 32 * 32;
+    const int slots = threads / C4;
+    const size_t smem = (size_t)slots * (J + 1) * C * sizeof(float);
+    if (smem > 200 * 1024) return fail(FNM_ENOTSUP, "lift_bwd: reduction tile too large");
+    cudaStream_t st = as_stream(stream);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(lift_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        attr_set = true;
+    }
+    {
+        LaunchScope ls("lift_bwd", st);
+        lift_bwd_kernel<<<kEndBlocks, threads, smem, st>>>(a);
+    }
+    FNM_TRY(check_launch("lift_bwd"));
+    {
+        LaunchScope ls("lift_bwd_reduce", st);
+        lift_bwd_reduce<<<((J + 1) * C + 255) / 256, 256, 0, st>>>(a.partial, kEndBlocks, J, C, dw, db);
+    }
+    return check_launch("lift_bwd_reduce");
+}
+
+int fnm_mlp_head_fwd(const float* h1, const float* w2, const float* b2, float* out, int64_t npos, int H, int D,
+                     fnm_stream_t stream) {
+    FNM_REQUIRE(h1 && w2 && out, "mlp_head_fwd: NULL pointer");
+    if (H % 4 != 0 || H < 4 || H > 128 * kHeadMaxH4 || D < 1 || D > kHeadMaxD) return fail(FNM_ENOTSUP, "mlp_head_fwd: unsupported widths");
+    HeadArgs a{};
+    a.h1 = h1; a.w2 = w2; a.b2 = b2; a.out = out; a.npos = npos; a.H = H; a.D = D;
+    if (npos <= 0) return FNM_OK;
+    const long long want = (npos + 7) / 8;
+    const int grid = (int)(want < kEndBlocks * 4 ? want : kEndBlocks * 4);
+    {
+        LaunchScope ls("mlp_head_fwd", as_stream(stream));
+        head_fwd_kernel<<<grid, 256, 0, as_stream(stream)>>>(a);
+    }
+    return check_launch("mlp_head_fwd");
+}
+
+size_t fnm_mlp_head_bwd_workspace_bytes(int H, int D) { return align_up((size_t)kEndBlocks * (D * H + D) * sizeof(float), 256); }
+
+int fnm_mlp_head_bwd(const float* h1, const float* g_out, const float* w2, float* g_h1, float* dw2, float* db2,
+                     int64_t npos, int H, int D, void* workspace, size_t workspace_bytes, fnm_stream_t stream) {
+    FNM_REQUIRE(h1 && g_out && w2 && g_h1 && workspace, "mlp_head_bwd: NULL pointer");
+    if (H % 4 != 0 || H < 4 || H > 128 * kHeadMaxH4 || D < 1 || D > kHeadMaxD) return fail(FNM_ENOTSUP, "mlp_head_bwd: unsupported widths");
+    if (workspace_bytes < fnm_mlp_head_bwd_workspace_bytes(H, D)) return fail(FNM_EWORKSPACE, "mlp_head_bwd: workspace too small");
+    HeadArgs a{};
+    a.h1 = h1; a.g_out = g_out; a.w2 = w2; a.g_h1 = g_h1; a.partial = static_cast<float*>(workspace);
+    a.npos = npos; a.H = H; a.D = D;
+    cudaStream_t st = as_stream(stream);
+    const size_t smem = (size_t)8 * (D * H + D) * sizeof(float);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(head_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+        attr_set = true;
+    }
+    {
+        LaunchScope ls("mlp_head_bwd", st);
+        head_bwd_kernel<<<kEndBlocks, 256, smem, st>>>(a);
+    }
+    FNM_TRY(check_launch("mlp_head_bwd"));
+    {
+        LaunchScope ls("mlp_head_bwd_reduce", st);
+        head_bwd_reduce<<<(D * H + D + 255) / 256, 256, 0, st>>>(a.partial, kEndBlocks, H, D, dw2, db2);
+    }
+    return check_launch("mlp_head_bwd_reduce");
+}
+
+}  // extern "C"

@@ -121,7 +121,7 @@ __device__ __forceinline__ void pw2_issue_lo(uint32_t d, uint32_t tb, uint32_t x
     }
 }
 
-#define PW2_SHAPES(X) X(4, 8) X(2, 4) X(1, 3) X(4, 4) X(2, 8) X(1, 4)
+#define PW2_SHAPES(X) X(4, 8) X(2, 4) X(1, 3) X(4, 4) X(2, 8) X(1, 4) X(4, 0) X(2, 0) X(1, 0)
 
 __global__ void __launch_bounds__(kPwThreads, 1)
 pw2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapBy,
@@ -145,7 +145,7 @@ pw2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUt
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(lo_full + 12);
 
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
-    const bool has_x = a.CI > 0;
+    const bool has_x = a.CI > 0, has_z = a.LY > 0;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < a.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], a.single_pass ? 1 : 5); }
@@ -198,9 +198,11 @@ pw2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUt
             for (int u = 0; u < my_units; ++u) {
                 int row, t0, t1;
                 unit_tiles(u, row, t0, t1);
-                mbar_wait(z_empty, (uint32_t)((u & 1) ^ 1));
-                mbar_expect_tx(z_full, a.z_bytes);
-                tma_load_2d(&mapZ, z_full, zs, 0, row * a.LY);
+                if (has_z) {
+                    mbar_wait(z_empty, (uint32_t)((u & 1) ^ 1));
+                    mbar_expect_tx(z_full, a.z_bytes);
+                    tma_load_2d(&mapZ, z_full, zs, 0, row * a.LY);
+                }
                 for (int tile = t0; tile < t1; ++tile, ++t) {
                     const uint32_t s = t % (uint32_t)a.stages;
                     mbar_wait(&empty[s], ((t / (uint32_t)a.stages) & 1) ^ 1);
@@ -226,7 +228,7 @@ pw2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUt
         for (int u = 0; u < my_units; ++u) {
             int row, t0, t1;
             unit_tiles(u, row, t0, t1);
-            mbar_wait(a2_full, (uint32_t)(u & 1));
+            if (has_z) mbar_wait(a2_full, (uint32_t)(u & 1));
             for (int tile = t0; tile < t1; ++tile, ++t) {
                 const uint32_t s = t % (uint32_t)a.stages, acc = t & 1;
                 mbar_wait(&acc_empty[acc], ((t >> 1) & 1) ^ 1);
@@ -267,7 +269,7 @@ pw2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUt
                     umma_commit(&lo_empty[lb]);
                 }
                 umma_commit(&acc_full[acc]);
-                if (tile == t1 - 1) umma_commit(a2_empty);
+                if (has_z && tile == t1 - 1) umma_commit(a2_empty);
                 __syncwarp();
             }
         }
@@ -276,7 +278,7 @@ pw2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUt
         const int q4 = warp & 3, c = q4 * 32 + lane;
         const uint32_t lane_base = tmem_base + ((uint32_t)(q4 * 32) << 16);
         const bool c_ok = c < a.CO;
-        for (int u = 0; u < my_units; ++u) {
+        for (int u = 0; u < (has_z ? my_units : 0); ++u) {
             mbar_wait(z_full, (uint32_t)(u & 1));
             mbar_wait(a2_empty, (uint32_t)((u & 1) ^ 1));
             tc_fence_after();
@@ -424,7 +426,8 @@ static bool make_map(CUtensorMap* m, const float* ptr, int rank, const cuuint64_
 }
 
 static bool pw2_configure(PwArgs2& a, int64_t rows, int S2, int LY, int CI, int CO) {
-    if (rows < 1 || rows > (1LL << 28) || S2 < 1 || LY < 4 || LY > 64 || LY % 4 != 0) return false;
+    if (rows < 1 || rows > (1LL << 28) || S2 < 1 || LY < 0 || LY > 64 || LY % 4 != 0) return false;
+    if (LY == 0 && CI == 0) return false;
     if (CO < 4 || CO > 128 || CO % 4 != 0) return false;
     if (CI != 0 && (CI < 4 || CI > 128 || CI % 4 != 0)) return false;
     a.rows = rows; a.S2 = S2; a.LY = LY; a.CI = CI; a.CO = CO;
@@ -486,13 +489,13 @@ int tc_pw2(const float* x, const float* wc, int wc_is_kn, const float* bias, con
     a.single_pass = mode == FNM_MODE_TF32;
     { const char* e = getenv("FNM_PW2_DEBUG"); a.debug = e ? atoi(e) : 0; }
     CUtensorMap mx, mb, mz;
-    {
+    if (LY > 0) {
         const cuuint64_t dims[2] = {(cuuint64_t)LY, (cuuint64_t)S2};
         const cuuint64_t str[1] = {(cuuint64_t)LY * 4};
         const cuuint32_t box[2] = {32, (cuuint32_t)a.NT};
         if (!make_map(&mb, by, 2, dims, str, box, true)) return fail(FNM_ECUDA, "pointwise_ysyn: tensor map (by) failed");
     }
-    {
+    if (LY > 0) {
         const cuuint64_t dims[2] = {(cuuint64_t)N, (cuuint64_t)rows * LY};
         const cuuint64_t str[1] = {(cuuint64_t)N * 4};
         const cuuint32_t box[2] = {(cuuint32_t)N, (cuuint32_t)LY};
@@ -506,6 +509,7 @@ int tc_pw2(const float* x, const float* wc, int wc_is_kn, const float* bias, con
     } else {
         mx = mb;
     }
+    if (LY == 0) { mb = mx; mz = mx; }                          // never dereferenced without a spectral term
     const size_t smem = (size_t)(a.stages + a.nlo) * a.stage_bytes + a.z_bytes + 1024 + 256;
     static bool attr_set = false;
     if (!attr_set) {

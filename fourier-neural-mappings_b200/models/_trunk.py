@@ -81,10 +81,24 @@ def run_layers(state, speconvs, ws, act_name, act_flags, one_d, last_s=None):
     return state
 
 
+def _fused_ends_ok(*tensors):
+    return all(t.is_cuda and t.dtype == torch.float32 for t in tensors)
+
+
 def lift(x, fc0, padding, get_grid, one_d):
     """Lifting + zero padding at the END of each axis (func_to_func2d.py:79-86) -> channels-last
-    (B, P1, P2, C) (P1 = 1 in 1-D).  Adjacent op: plain torch."""
+    (B, P1, P2, C) (P1 = 1 in 1-D).  On CUDA one fused kernel (fc0 on data + grid coordinates, written
+    padded); otherwise, or when the input itself needs a gradient, the plain torch statement."""
     from ..shared import get_grid1d, get_grid2d
+    ngrid = (1 if one_d else 2) if get_grid else 0
+    C = fc0.out_features
+    if (_fused_ends_ok(x, fc0.weight) and not x.requires_grad and fc0.bias is not None and C % 4 == 0 and C <= 512
+            and 1 <= x.shape[1] + ngrid <= 8 and x.shape[1] + ngrid == fc0.in_features):
+        if one_d:
+            n = x.shape[-1]
+            return ops.lift(x.unsqueeze(2), fc0.weight, fc0.bias, 1, n + n // padding, ngrid), (n,)
+        n1, n2 = x.shape[-2:]
+        return ops.lift(x, fc0.weight, fc0.bias, n1 + n1 // padding, n2 + n2 // padding, ngrid), (n1, n2)
     if one_d:
         n = x.shape[-1]
         x = x.permute(0, 2, 1)
@@ -109,6 +123,20 @@ def crop(x, cut, one_d):
         return x[:, :, :-cut[0], :] if cut[0] != 0 else x[:, :, :0, :]
     x = x[:, :-cut[0], :, :] if cut[0] != 0 else x[:, :0, :, :]
     return x[:, :, :-cut[1], :] if cut[1] != 0 else x[:, :, :0, :]
+
+
+def project(x, cut, mlp, one_d):
+    """Crop + pointwise MLP (func_to_func2d.py:98-107) on a channels-last (B, P1, P2, C) tensor.  With
+    GELU on CUDA: fc1 runs on the fused tcgen05 pointwise kernel over the PADDED grid (no crop copy; the
+    padded positions get zero gradient from the crop's backward), GELU + fc2 in one pass that never
+    stores the hidden activation; the crop is a view of the small result."""
+    fc1, fc2 = mlp.fc1, mlp.fc2
+    if (getattr(mlp, "act_name", None) == "gelu" and _fused_ends_ok(x, fc1.weight, fc2.weight)
+            and fc1.in_features % 4 == 0 and fc1.in_features <= 128 and fc1.out_features % 4 == 0
+            and fc1.out_features <= 128 and fc2.out_features <= 4 and min(cut) > 0):
+        h1 = ops.pointwise_conv(x, fc1.weight, fc1.bias)
+        return crop(ops.mlp_head(h1, fc2.weight, fc2.bias), cut, one_d)
+    return mlp(crop(x, cut, one_d))
 
 
 def functional_end(state, lfunc0, mlpfunc0, head, one_d):

@@ -2,7 +2,7 @@
 import torch.nn as nn
 
 from ..shared import MLP, SpectralConv1d, SpectralConv2d, _get_act
-from ._trunk import Pending, crop, lift, run_layers
+from ._trunk import Pending, lift, project, run_layers
 
 
 class FNO2d(nn.Module):
@@ -30,8 +30,7 @@ class FNO2d(nn.Module):
         flags = [True] * (self.n_layers - 1) + [False]
         state = run_layers(Pending(x), self.speconvs, self.ws, self.act_name, flags, False, self.s_outputspace)
         cut = self.num_pad_outputspace if self.s_outputspace is not None else tuple(r // self.padding for r in res)
-        x = crop(state.value(), cut, one_d=False)
-        return self.mlp0(x).permute(0, 3, 1, 2)
+        return project(state.value(), cut, self.mlp0, one_d=False).permute(0, 3, 1, 2)
 
     def set_outputspace_resolution(self, s=None):
         if s is None:
@@ -66,8 +65,7 @@ class FNO1d(nn.Module):
         flags = [True] * (self.n_layers - 1) + [False]
         state = run_layers(Pending(x), self.speconvs, self.ws, self.act_name, flags, True, self.s_outputspace)
         cut = (self.num_pad_outputspace,) if self.s_outputspace is not None else (res[0] // self.padding,)
-        x = crop(state.value(), cut, one_d=True)
-        return self.mlp0(x.squeeze(1)).permute(0, 2, 1)
+        return project(state.value(), cut, self.mlp0, one_d=True).squeeze(1).permute(0, 2, 1)
 
     def set_outputspace_resolution(self, s=None):
         if s is None:

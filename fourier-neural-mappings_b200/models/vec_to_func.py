@@ -3,7 +3,7 @@ import torch.nn as nn
 
 from .. import ops
 from ..shared import MLP, LinearDecoder1d, LinearDecoder2d, SpectralConv1d, SpectralConv2d, _get_act
-from ._trunk import Pending, crop, run_layers
+from ._trunk import Pending, project, run_layers
 
 
 class FND2d(nn.Module):
@@ -35,8 +35,7 @@ class FND2d(nn.Module):
         y = ops.linear_decoder(v, self.ldec0.weights, self.ldec0.tables(self.s_outputspace))
         n = len(self.ws)
         state = run_layers(Pending(y), self.speconvs, self.ws, self.act_name, [True] * (n - 1) + [False], False)
-        y = crop(state.value(), self.num_pad_outputspace, one_d=False)
-        return self.mlp1(y).permute(0, 3, 1, 2)
+        return project(state.value(), self.num_pad_outputspace, self.mlp1, one_d=False).permute(0, 3, 1, 2)
 
     def set_outputspace_resolution(self, s):
         self.s_outputspace = tuple(r + r // self.padding for r in list(s))
@@ -72,8 +71,7 @@ class FND1d(nn.Module):
         y = ops.linear_decoder(v, self.ldec0.weights, self.ldec0.tables(self.s_outputspace))
         n = len(self.ws)
         state = run_layers(Pending(y), self.speconvs, self.ws, self.act_name, [True] * (n - 1) + [False], True)
-        y = crop(state.value(), (self.num_pad_outputspace,), one_d=True)
-        return self.mlp1(y.squeeze(1)).permute(0, 2, 1)
+        return project(state.value(), (self.num_pad_outputspace,), self.mlp1, one_d=True).squeeze(1).permute(0, 2, 1)
 
     def set_outputspace_resolution(self, s):
         self.s_outputspace = s + s // self.padding

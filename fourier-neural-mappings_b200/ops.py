@@ -240,6 +240,124 @@ class GeluFn(torch.autograd.Function):
         return gz
 
 
+class LiftFn(torch.autograd.Function):
+    """Lifting: fc0 on [data channels | grid coordinates] + zero padding -> channels-last (B, P1, P2, C)
+    (reference: func_to_func2d.py:79-86).  ``x`` is (B, Din, N1, N2) (1-D: N1 = 1); it gets no gradient."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, P1, P2, ngrid):
+        _need_cuda(x, w, b)
+        x, w, b = _f32c(x), _f32c(w), _f32c(b)
+        B, Din, N1, N2 = x.shape
+        Cw = w.shape[0]
+        out = torch.empty((B, P1, P2, Cw), dtype=torch.float32, device=x.device)
+        check(lib().fnm_lift_fwd(_ptr(x), _ptr(w), _ptr(b), _ptr(out), B, Din, N1, N2, P1, P2, Cw, ngrid, _stream()),
+              "fnm_lift_fwd")
+        ctx.save_for_backward(x)
+        ctx.dims = (B, Din, N1, N2, P1, P2, Cw, ngrid)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (x,) = ctx.saved_tensors
+        B, Din, N1, N2, P1, P2, Cw, ngrid = ctx.dims
+        g = _f32c(g)
+        J = Din + ngrid
+        dw = torch.empty((Cw, J), dtype=torch.float32, device=g.device)
+        db = torch.empty((Cw,), dtype=torch.float32, device=g.device)
+        L = lib()
+        ws = _workspace(g.device, L.fnm_lift_bwd_workspace_bytes(Cw, J))
+        check(L.fnm_lift_bwd(_ptr(g), _ptr(x), _ptr(dw), _ptr(db), B, Din, N1, N2, P1, P2, Cw, ngrid,
+                             _ptr(ws), ws.numel(), _stream()), "fnm_lift_bwd")
+        return None, dw, db, None, None, None
+
+
+class PointwiseConvFn(torch.autograd.Function):
+    """h[..., o] = sum_i x[..., i] w[o, i] + b[o] on a channels-last (B, P1, P2, Ci) tensor: the fused
+    pointwise kernel without a spectral term (forward and input gradient) + conv_wgrad (dW, db)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b):
+        _need_cuda(x, w, b)
+        x, w = _f32c(x), _f32c(w)
+        B, P1, P2, Ci = x.shape
+        Co = w.shape[0]
+        out = torch.empty((B, P1, P2, Co), dtype=torch.float32, device=x.device)
+        check(lib().fnm_pointwise_ysyn(_ptr(x), 0, _ptr(w), 0, _ptr(_f32c(b)) if b is not None else None, None, None, None,
+                                       _ptr(out), None, B * P1, P2, 0, Ci, Co, _MODE, _stream()), "fnm_pointwise_ysyn")
+        ctx.save_for_backward(x, w)
+        ctx.has_bias = b is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x, w = ctx.saved_tensors
+        g = _f32c(g)
+        B, P1, P2, Ci = x.shape
+        Co = w.shape[0]
+        L = lib()
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty_like(x)
+            check(L.fnm_pointwise_ysyn(_ptr(g), 0, _ptr(w), 1, None, None, None, None, _ptr(dx), None, B * P1, P2, 0,
+                                       Co, Ci, _MODE, _stream()), "fnm_pointwise_ysyn")
+        if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
+            npos = B * P1 * P2
+            dw = torch.empty_like(w)
+            db = torch.empty((Co,), dtype=torch.float32, device=g.device)
+            ws = _workspace(g.device, L.fnm_conv_wgrad_workspace_bytes(npos, Ci, Co))
+            check(L.fnm_conv_wgrad(_ptr(g), _ptr(x), 0, _ptr(dw), _ptr(db), npos, Ci, Co, _ptr(ws), ws.numel(), _MODE,
+                                   _stream()), "fnm_conv_wgrad")
+            if not ctx.has_bias:
+                db = None
+        return dx, dw, db
+
+
+class MlpHeadFn(torch.autograd.Function):
+    """out[..., d] = sum_h w2[d, h] GELU(h1[..., h]) + b2[d] (the activation and second layer of the
+    reference MLP, shared.py:26-45) without materialising GELU(h1)."""
+
+    @staticmethod
+    def forward(ctx, h1, w2, b2):
+        _need_cuda(h1, w2, b2)
+        h1, w2 = _f32c(h1), _f32c(w2)
+        H, D = h1.shape[-1], w2.shape[0]
+        npos = h1.numel() // H
+        out = torch.empty(h1.shape[:-1] + (D,), dtype=torch.float32, device=h1.device)
+        check(lib().fnm_mlp_head_fwd(_ptr(h1), _ptr(w2), _ptr(_f32c(b2)) if b2 is not None else None, _ptr(out), npos, H, D,
+                                     _stream()), "fnm_mlp_head_fwd")
+        ctx.save_for_backward(h1, w2)
+        ctx.has_bias = b2 is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        h1, w2 = ctx.saved_tensors
+        g = _f32c(g)
+        H, D = h1.shape[-1], w2.shape[0]
+        npos = h1.numel() // H
+        g_h1 = torch.empty_like(h1)
+        dw2 = torch.empty_like(w2)
+        db2 = torch.empty((D,), dtype=torch.float32, device=g.device)
+        L = lib()
+        ws = _workspace(g.device, L.fnm_mlp_head_bwd_workspace_bytes(H, D))
+        check(L.fnm_mlp_head_bwd(_ptr(h1), _ptr(g), _ptr(w2), _ptr(g_h1), _ptr(dw2), _ptr(db2), npos, H, D,
+                                 _ptr(ws), ws.numel(), _stream()), "fnm_mlp_head_bwd")
+        return g_h1, dw2, (db2 if ctx.has_bias else None)
+
+
+def lift(x, w, b, P1, P2, ngrid):
+    return LiftFn.apply(x, w, b, P1, P2, ngrid)
+
+
+def pointwise_conv(x, w, b):
+    return PointwiseConvFn.apply(x, w, b)
+
+
+def mlp_head(h1, w2, b2):
+    return MlpHeadFn.apply(h1, w2, b2)
+
+
 def fourier_layer(zin, w0, w1, wc, bc, tables, act_in=False, xact=None, want_act_out=False):
     """Returns (z, GELU(z) or None).  ``zin`` is the layer input (pre-activation if act_in)."""
     return FourierLayerFn.apply(zin, xact, w0, w1, wc, bc, tables, act_in, want_act_out)

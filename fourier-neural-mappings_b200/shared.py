@@ -31,6 +31,7 @@ class MLP(nn.Module):
     def __init__(self, channels_in, channels_hid, channels_out, act="gelu"):
         super().__init__()
         self.fc1 = nn.Linear(channels_in, channels_hid)
+        self.act_name = act
         self.act = _get_act(act)
         self.fc2 = nn.Linear(channels_hid, channels_out)
 

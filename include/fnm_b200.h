@@ -193,6 +193,26 @@ size_t fnm_conv_wgrad_workspace_bytes(int64_t npos, int Ci, int Co);
 int fnm_conv_wgrad(const float* g, const float* x, int act_in, float* dwc, float* dbc, int64_t npos,
                    int Ci, int Co, void* workspace, size_t workspace_bytes, int mode, fnm_stream_t stream);
 
+/* ---- the two ends of the trunk (adjacent ops) -----------------------------------
+ * lift: fc0 applied to [data channels | grid coordinates] + zero padding at the end of each axis
+ *   (models/func_to_func2d.py:79-86; grid = torch.linspace(0, 1, n), shared.py:111-118, 150-159):
+ *     out[b][x][y][c] = sum_j w[c][j] feat_j(b, x, y) + bias[c]   for x < N1, y < N2, else 0
+ *   x is the reference's (B, Din, N1, N2) tensor (1-D: N1 = P1 = 1); ngrid = 0 (get_grid=False), 1 or 2.
+ * lift_bwd: dw[c][j], db[c] from g = dL/d out (the un-padded region).                                   */
+int fnm_lift_fwd(const float* x, const float* w, const float* b, float* out, int B, int Din, int N1, int N2, int P1,
+                 int P2, int C, int ngrid, fnm_stream_t stream);
+size_t fnm_lift_bwd_workspace_bytes(int C, int J);
+int fnm_lift_bwd(const float* g, const float* x, float* dw, float* db, int B, int Din, int N1, int N2, int P1, int P2,
+                 int C, int ngrid, void* workspace, size_t workspace_bytes, fnm_stream_t stream);
+/* projection head of MLP (shared.py:26-45 with act = gelu): out[pos][d] = sum_h w2[d][h] GELU(h1[pos][h]) + b2[d];
+ * backward: g_h1 = (g_out w2) * GELU'(h1), dw2[d][h] = sum_pos g_out[pos][d] GELU(h1[pos][h]), db2[d].
+ * (fc1 itself is fnm_pointwise_ysyn with LY = 0 and its gradient fnm_conv_wgrad.)                        */
+int fnm_mlp_head_fwd(const float* h1, const float* w2, const float* b2, float* out, int64_t npos, int H, int D,
+                     fnm_stream_t stream);
+size_t fnm_mlp_head_bwd_workspace_bytes(int H, int D);
+int fnm_mlp_head_bwd(const float* h1, const float* g_out, const float* w2, float* g_h1, float* dw2, float* db2,
+                     int64_t npos, int H, int D, void* workspace, size_t workspace_bytes, fnm_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -228,6 +228,55 @@ def test_mix_stages(B, R, NY, rpw, Ci, Co, mode, use_ws):
     assert rel_l2(got, ref) < tol
 
 
+@pytest.mark.parametrize("B,Din,N1,N2,pad,C,ngrid", [(3, 1, 16, 24, 8, 32, 2), (2, 2, 13, 9, 4, 20, 2), (4, 1, 1, 40, 8, 64, 1),
+                                                     (2, 3, 8, 8, 8, 16, 0), (2, 1, 64, 64, 8, 128, 2)])
+def test_lift_kernels(B, Din, N1, N2, pad, C, ngrid):
+    """fc0 on [data | grid coordinates] + zero padding, forward and weight gradients, against the torch
+    statement of func_to_func2d.py:79-86 in float64."""
+    torch.manual_seed(5)
+    P1, P2 = (N1 + N1 // pad if N1 > 1 else 1), N2 + N2 // pad
+    x = torch.randn(B, Din, N1, N2, device=DEV)
+    fc0 = torch.nn.Linear(Din + ngrid, C).to(DEV)
+    out = fnm_b200.ops.lift(x, fc0.weight, fc0.bias, P1, P2, ngrid)
+    g = torch.randn_like(out)
+    out.backward(g)
+    got_dw, got_db = fc0.weight.grad.clone(), fc0.bias.grad.clone()
+    fc0.zero_grad()
+    feats = [x.double().permute(0, 2, 3, 1)]
+    if ngrid == 2:
+        feats.append(torch.linspace(0, 1, N1, device=DEV, dtype=torch.float64).view(1, N1, 1, 1).expand(B, N1, N2, 1))
+    if ngrid >= 1:
+        feats.append(torch.linspace(0, 1, N2, device=DEV, dtype=torch.float64).view(1, 1, N2, 1).expand(B, N1, N2, 1))
+    f = torch.cat(feats, -1)
+    w64, b64 = fc0.weight.detach().double().requires_grad_(True), fc0.bias.detach().double().requires_grad_(True)
+    ref = torch.nn.functional.pad(f @ w64.t() + b64, [0, 0, 0, P2 - N2, 0, P1 - N1])
+    ref.backward(g.double())
+    assert rel_l2(out, ref) < 1e-6
+    assert rel_l2(got_dw, w64.grad) < TOL_FP32 and rel_l2(got_db, b64.grad) < TOL_FP32
+
+
+@pytest.mark.parametrize("shape,Ci,H,D", [((2, 20, 24), 32, 128, 1), ((3, 1, 50), 64, 128, 2), ((2, 72, 72), 128, 128, 1),
+                                          ((2, 9, 11), 20, 64, 3)])
+def test_projection_kernels(shape, Ci, H, D):
+    """fc1 (fused pointwise kernel without spectral term) -> GELU -> fc2 (head kernel), forward and all
+    gradients, against torch in float64."""
+    torch.manual_seed(6)
+    B, P1, P2 = shape
+    x = torch.randn(B, P1, P2, Ci, device=DEV, requires_grad=True)
+    fc1, fc2 = torch.nn.Linear(Ci, H).to(DEV), torch.nn.Linear(H, D).to(DEV)
+    out = fnm_b200.ops.mlp_head(fnm_b200.ops.pointwise_conv(x, fc1.weight, fc1.bias), fc2.weight, fc2.bias)
+    g = torch.randn_like(out)
+    out.backward(g)
+    got = [x.grad, fc1.weight.grad, fc1.bias.grad, fc2.weight.grad, fc2.bias.grad]
+    p64 = [t.detach().double().requires_grad_(True) for t in (x, fc1.weight, fc1.bias, fc2.weight, fc2.bias)]
+    h = p64[0] @ p64[1].t() + p64[2]
+    ref = _gelu64(h) @ p64[3].t() + p64[4]
+    ref.backward(g.double())
+    assert rel_l2(out, ref) < TOL_FP32
+    for a, b in zip(got, p64):
+        assert rel_l2(a, b.grad) < TOL_FP32
+
+
 def test_gelu_kernels():
     z = torch.randn(100003, device=DEV) * 3
     g = torch.randn_like(z)
