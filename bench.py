@@ -186,7 +186,7 @@ def cpu_baseline(workload, budget_s=25.0):
 
 
 # ------------------------------------------------------------------------------------------------
-def kernel_algorithmic_bytes(name, wl, model):
+def kernel_algorithmic_bytes(name, wl, model, launches=None):
     """ALGORITHMIC bytes one train step moves through kernel `name`:
     A = 4*B*C*P1*P2 bytes is one fp32 activation of the trunk."""
     A, L, lyf = wl["A"], wl["layers"], wl["ly_frac"]
@@ -195,7 +195,9 @@ def kernel_algorithmic_bytes(name, wl, model):
         # bwd: read g_z, z_prev, write g_in (3A; the first layer has no GELU' operand: 2A)
         "pointwise_ysyn": L * 2 * A + (L - 1) * 3 * A + 2 * A,
         "ydft": 2 * L * A * (1 + lyf),                  # fwd + bwd analysis: read A, write the LY/P2 partial transform
-        "conv_wgrad": L * 2 * A,                        # read g_z and x
+        "conv_wgrad": (launches or L) * 2 * A,          # read g and x (one more launch for the projection's fc1)
+        "pointwise_conv": 2 * 2 * A,                    # projection fc1 forward + its input gradient
+        "lift_fwd": A, "lift_bwd": A, "mlp_head_fwd": A, "mlp_head_bwd": 2 * A,
         "adam": 28 * wl["n_real_params"],               # read p,g,m,v; write p,m,v
         "xdft": 2 * L * A * lyf, "xsyn": 2 * L * A * lyf,
         "mix_fwd": L * wl["w_bytes"], "mix_bwd_x": L * wl["w_bytes"], "mix_bwd_w": L * wl["w_bytes"],
@@ -204,6 +206,7 @@ def kernel_algorithmic_bytes(name, wl, model):
 
 
 def run_ours(args, rank, world):
+    os.environ["NCCL_DEBUG"] = "WARN"              # keep NCCL's version banner off stdout (one JSON line only)
     import torch.distributed as dist
     import fnm_b200
     from fnm_b200 import _lib
@@ -218,7 +221,7 @@ def run_ours(args, rank, world):
     torch.manual_seed(0)
     model = build_model(family, kw).to(dev)
     fnm_b200.parallel.broadcast_parameters(model)
-    opt = fnm_b200.Adam(model.parameters(), lr=1e-3, weight_decay=1e-4)
+    opt = fnm_b200.Adam(model.parameters(), lr=1e-3, weight_decay=1e-4, capturable=args.graph)
     grads = FlatGradients(model.parameters())
 
     x_host = synth((batch,) + xshape, 1234 + rank).pin_memory()
@@ -249,6 +252,18 @@ def run_ours(args, rank, world):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return t.item()
 
+    eager_step = step
+    graphed = None
+    if args.graph:
+        # the step recorded once in a CUDA graph; every timed step below is one replay of the full step
+        try:
+            graphed = fnm_b200.parallel.GraphedTrainStep(model, opt, grads, rel_l2_sum, x, y, warmup=args.warmup)
+        except Exception as e:                             # noqa: BLE001 -- e.g. a collective that cannot be captured
+            sys.stderr.write(f"[bench] CUDA-graph capture failed ({type(e).__name__}: {e}); running eagerly\n")
+            graphed, args.graph = None, False
+    if graphed is not None:
+        def step(xd, yd):                                  # noqa: F811
+            return graphed(xd, yd)
     for _ in range(args.warmup):
         step(x, y)
     # ---- timed region: K steps, inputs resident in HBM
@@ -265,20 +280,26 @@ def run_ours(args, rank, world):
     barrier()
     ms = max_over_ranks(e0.elapsed_time(e1))
     launches = _lib.launch_count() - launches0
+    if graphed is not None:
+        launches = graphed.launches_per_step * args.steps    # kernels recorded in the graph, replayed K times
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- end to end: host batch -> device, step, loss -> host, every step
     xd, yd = torch.empty_like(x), torch.empty_like(y)
+    def e2e_step():
+        if graphed is not None:                            # pinned host -> the graph's static input buffers
+            return step(x_host, y_host).item()
+        xd.copy_(x_host, non_blocking=True)
+        yd.copy_(y_host, non_blocking=True)
+        return step(xd, yd).item()
+
     for _ in range(2):
-        xd.copy_(x_host, non_blocking=True); yd.copy_(y_host, non_blocking=True)
-        step(xd, yd).item()
+        e2e_step()
     barrier()
     t0 = time.perf_counter()
     e0.record()
     for _ in range(args.steps):
-        xd.copy_(x_host, non_blocking=True)
-        yd.copy_(y_host, non_blocking=True)
-        loss_val = step(xd, yd).item()
+        loss_val = e2e_step()
     e1.record()
     barrier()
     ms_e2e = max_over_ranks(max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3 if world == 1 else 0.0))
@@ -290,7 +311,7 @@ def run_ours(args, rank, world):
     if rank == 0:
         _lib.profile_begin()
     for _ in range(nprof):
-        step(x, y)
+        eager_step(x, y)                                   # eager: events are recorded around every launch
     torch.cuda.synchronize()
     if rank == 0:
         prof = {k: (c / nprof, t / nprof) for k, (c, t) in _lib.profile_end().items()}
@@ -320,7 +341,7 @@ def run_ours(args, rank, world):
     kernels = []
     total_ms = sum(t for _, t in prof.values()) or 1.0
     for name, (cnt, t) in sorted(prof.items(), key=lambda kv: -kv[1][1]):
-        ab = kernel_algorithmic_bytes(name, wl, model)
+        ab = kernel_algorithmic_bytes(name, wl, model, cnt)
         kernels.append({"name": name, "launches_per_step": cnt, "ms_per_step": round(t, 4),
                         "share": round(t / total_ms, 4),
                         "algorithmic_GB_per_step": None if ab is None else round(ab / 1e9, 4),
@@ -347,7 +368,7 @@ def run_ours(args, rank, world):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{args.workload}: {desc}", "batch_per_gpu": batch, "global_batch": batch * world,
-                   "parallelism": f"dp{world}", "compute_mode": fnm_b200.get_compute_mode(),
+                   "parallelism": f"dp{world}", "compute_mode": fnm_b200.get_compute_mode(), "cuda_graph": bool(args.graph),
                    "tcgen05": bool(_lib.lib().fnm_has_tcgen05()),
                    "l2": ("working set %.0f MB per activation, larger than the 126 MB L2" % (wl["A"] / 1e6))
                    if wl["A"] > 126e6 else "working set fits L2 (back-to-back steps, no flush)",
@@ -374,6 +395,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg5", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--graph", dest="graph", action="store_true", default=True,
+                    help="replay the step from one CUDA graph (default)")
+    ap.add_argument("--no-graph", dest="graph", action="store_false")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))

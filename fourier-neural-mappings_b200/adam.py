@@ -20,7 +20,10 @@ def _as_float_view(t):
 
 
 class Adam(Optimizer):
-    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0, amsgrad=False):
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0, amsgrad=False,
+                 capturable=False):
+        """``capturable=True`` (extension; the reference has no such flag) keeps the step count in a device
+        counter that the kernel reads, so ``step()`` can be recorded in a CUDA graph and replayed."""
         if not 0.0 <= lr:
             raise ValueError("Invalid learning rate: {}".format(lr))
         if not 0.0 <= eps:
@@ -32,6 +35,8 @@ class Adam(Optimizer):
         if not 0.0 <= weight_decay:
             raise ValueError("Invalid weight_decay value: {}".format(weight_decay))
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, amsgrad=amsgrad))
+        self.capturable = bool(capturable)
+        self._step_dev = {}
 
     def __setstate__(self, state):
         super().__setstate__(state)
@@ -44,6 +49,7 @@ class Adam(Optimizer):
         if closure is not None:
             with torch.enable_grad():
                 loss = closure()
+        self._ctr_bumped = False
         for group in self.param_groups:
             beta1, beta2 = group["betas"]
             by_step = {}
@@ -91,7 +97,18 @@ class Adam(Optimizer):
         numel = (C.c_int64 * n)(*[p.numel() * (2 if p.is_complex() else 1) for p in plist])
         cplx = (C.c_uint8 * n)(*[1 if p.is_complex() else 0 for p in plist])
         stream = C.c_void_p(torch.cuda.current_stream(plist[0].device).cuda_stream)
+        step_dev = None
+        if self.capturable:
+            # one device counter shared by all parameters (they are stepped together); bumped once per step()
+            ctr = self._step_dev.get("ctr")
+            if ctr is None:
+                ctr = torch.full((1,), step - 1, dtype=torch.int32, device=plist[0].device)
+                self._step_dev["ctr"] = ctr
+            if not self._ctr_bumped:
+                check(lib().fnm_counter_inc(C.c_void_p(ctr.data_ptr()), stream), "fnm_counter_inc")
+                self._ctr_bumped = True
+            step_dev = C.c_void_p(ctr.data_ptr())
         check(lib().fnm_adam_multi_tensor(n, p_tab, g_tab, m_tab, v_tab, x_tab, numel, cplx,
                                           float(group["lr"]), float(beta1), float(beta2), float(group["eps"]),
-                                          float(group["weight_decay"]), int(bool(group["amsgrad"])), int(step), None,
+                                          float(group["weight_decay"]), int(bool(group["amsgrad"])), int(step), step_dev,
                                           stream), "fnm_adam_multi_tensor")

@@ -519,7 +519,7 @@ int tc_pw2(const float* x, const float* wc, int wc_is_kn, const float* bias, con
     }
     const int grid = a.units < sm_count() ? a.units : sm_count();
     {
-        LaunchScope ls("pointwise_ysyn", st);
+        LaunchScope ls(LY > 0 ? "pointwise_ysyn" : "pointwise_conv", st);
         pw2_kernel<<<grid, kPwThreads, smem < 120 * 1024 ? 120 * 1024 : smem, st>>>(mx, mb, mz, a);
     }
     return check_launch("pointwise_ysyn");

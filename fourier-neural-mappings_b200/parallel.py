@@ -83,6 +83,38 @@ def train_step(model, optimizer, grads, loss_fn, x, y, group=None):
     return loss
 
 
+class GraphedTrainStep:
+    """The whole train step (zero_grad -> forward -> loss -> backward -> all-reduce -> Adam) captured in ONE
+    CUDA graph and replayed: ~500 kernel launches per step become one graph launch, which is what the
+    launch-bound small configurations need.  ``optimizer`` must be
+    ``fnm_b200.Adam(..., capturable=True)``.  Inputs are copied into static buffers before each replay; the
+    returned loss tensor is overwritten by every replay."""
+
+    def __init__(self, model, optimizer, grads, loss_fn, x, y, group=None, warmup=3):
+        if not getattr(optimizer, "capturable", False):
+            raise ValueError("GraphedTrainStep needs Adam(capturable=True): the step count must live on the device")
+        self.x, self.y = x.clone(), y.clone()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):                          # allocator / workspace / Adam-state warm-up
+            for _ in range(warmup):
+                train_step(model, optimizer, grads, loss_fn, self.x, self.y, group)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        from ._lib import launch_count
+        self.graph = torch.cuda.CUDAGraph()
+        n0 = launch_count()
+        with torch.cuda.graph(self.graph):
+            self.loss = train_step(model, optimizer, grads, loss_fn, self.x, self.y, group)
+        self.launches_per_step = launch_count() - n0
+
+    def __call__(self, x, y):
+        self.x.copy_(x, non_blocking=True)
+        self.y.copy_(y, non_blocking=True)
+        self.graph.replay()
+        return self.loss
+
+
 def rel_l2_sum(out, y, eps=1e-6):
     """The reference's training loss: LpLoss(size_average=False) (utilities_module.py:188-204)."""
     b = out.shape[0]
