@@ -8,8 +8,7 @@
 // fc1 itself (a 1x1 convolution C -> width_final over every position) runs on the TMA/tcgen05 fused
 // pointwise kernel with no spectral term (fnm_pointwise_ysyn, LY = 0), its weight gradient on
 // conv_wgrad.  These kernels are plain bandwidth-bound SIMT passes.
-#include "fnm_common.cuh"
-#include "fnm_stages.cuh"
+#include "fnm_tc_ptx.cuh"
 
 namespace fnm {
 
@@ -37,54 +36,68 @@ __global__ void lift_fwd_kernel(const LiftArgs a) {
         sw[i] = j < a.J ? __ldg(a.w + (size_t)c * a.J + j) : __ldg(a.b + c);
     }
     __syncthreads();
-    const long long total = (long long)a.B * a.P1 * a.P2 * C4;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int c4 = (int)(i % C4);
-        const long long pos = i / C4;
-        const int yy = (int)(pos % a.P2);
-        const long long r = pos / a.P2;
-        const int xx = (int)(r % a.P1), b = (int)(r / a.P1);
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (xx < a.N1 && yy < a.N2) {
-            v = *reinterpret_cast<const float4*>(sw + a.J * a.C + c4 * 4);
-            for (int j = 0; j < a.J; ++j) {
-                const float f = lift_feat(a, j, b, xx, yy);
-                const float4 w = *reinterpret_cast<const float4*>(sw + j * a.C + c4 * 4);
-                v.x = fmaf(f, w.x, v.x); v.y = fmaf(f, w.y, v.y); v.z = fmaf(f, w.z, v.z); v.w = fmaf(f, w.w, v.w);
+    const int nrows = a.B * a.P1;
+    for (int row = blockIdx.x; row < nrows; row += gridDim.x) {          // row = (b, x) of the padded grid
+        const int b = row / a.P1, xx = row - b * a.P1;
+        float4* orow = reinterpret_cast<float4*>(a.out + (size_t)row * a.P2 * a.C);
+        const bool x_in = xx < a.N1;
+        for (int i = threadIdx.x; i < a.P2 * C4; i += blockDim.x) {
+            const int yy = i / C4, c4 = i - yy * C4;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (x_in && yy < a.N2) {
+                v = *reinterpret_cast<const float4*>(sw + a.J * a.C + c4 * 4);
+                for (int j = 0; j < a.J; ++j) {
+                    const float f = lift_feat(a, j, b, xx, yy);
+                    const float4 w = *reinterpret_cast<const float4*>(sw + j * a.C + c4 * 4);
+                    v.x = fmaf(f, w.x, v.x); v.y = fmaf(f, w.y, v.y); v.z = fmaf(f, w.z, v.z); v.w = fmaf(f, w.w, v.w);
+                }
             }
+            orow[i] = v;
         }
-        *reinterpret_cast<float4*>(a.out + pos * a.C + c4 * 4) = v;
     }
 }
 
 // partial[block][j][c] = sum over the block's positions of g[pos][c] * feat_j(pos)   (j == J: bias)
-__global__ void lift_bwd_kernel(const LiftArgs a) {
+template <int MAXJ>
+__global__ void __launch_bounds__(256, 2) lift_bwd_kernel(const LiftArgs a) {
     extern __shared__ float red[];                        // [slots][(J+1)][C]
     const int C4 = a.C / 4;
     const int slots = blockDim.x / C4;
     const int c4 = threadIdx.x % C4, slot = threadIdx.x / C4;
-    float4 acc[kLiftMaxJ + 1];
+    float4 acc[MAXJ + 1];
 #pragma unroll
-    for (int j = 0; j <= kLiftMaxJ; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-    const long long npos = (long long)a.B * a.N1 * a.N2;      // un-padded positions only
+    for (int j = 0; j <= MAXJ; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int nrows = a.B * a.N1;                         // un-padded rows (b, x < N1)
     if (slot < slots) {
-        for (long long q = (long long)blockIdx.x * slots + slot; q < npos; q += (long long)gridDim.x * slots) {
-            const int yy = (int)(q % a.N2);
-            const long long r = q / a.N2;
-            const int xx = (int)(r % a.N1), b = (int)(r / a.N1);
-            const float4 g = __ldg(reinterpret_cast<const float4*>(a.g + (((size_t)b * a.P1 + xx) * a.P2 + yy) * a.C + c4 * 4));
+        for (int row = blockIdx.x; row < nrows; row += gridDim.x) {
+            const int b = row / a.N1, xx = row - b * a.N1;
+            const float4* grow = reinterpret_cast<const float4*>(a.g + ((size_t)b * a.P1 + xx) * a.P2 * a.C) + c4;
+            for (int y0 = slot; y0 < a.N2; y0 += 4 * slots) {           // four independent loads in flight
+                float4 g[4];
 #pragma unroll
-            for (int j = 0; j < kLiftMaxJ; ++j) {
-                if (j < a.J) {
-                    const float f = lift_feat(a, j, b, xx, yy);
-                    acc[j].x = fmaf(f, g.x, acc[j].x); acc[j].y = fmaf(f, g.y, acc[j].y);
-                    acc[j].z = fmaf(f, g.z, acc[j].z); acc[j].w = fmaf(f, g.w, acc[j].w);
+                for (int u = 0; u < 4; ++u) {
+                    const int yy = y0 + u * slots;
+                    g[u] = yy < a.N2 ? __ldg(grow + (size_t)yy * C4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int yy = y0 + u * slots;
+                    if (yy < a.N2) {
+#pragma unroll
+                        for (int j = 0; j < MAXJ; ++j) {
+                            if (j < a.J) {
+                                const float f = lift_feat(a, j, b, xx, yy);
+                                acc[j].x = fmaf(f, g[u].x, acc[j].x); acc[j].y = fmaf(f, g[u].y, acc[j].y);
+                                acc[j].z = fmaf(f, g[u].z, acc[j].z); acc[j].w = fmaf(f, g[u].w, acc[j].w);
+                            }
+                        }
+                        acc[MAXJ].x += g[u].x; acc[MAXJ].y += g[u].y; acc[MAXJ].z += g[u].z; acc[MAXJ].w += g[u].w;
+                    }
                 }
             }
-            acc[kLiftMaxJ].x += g.x; acc[kLiftMaxJ].y += g.y; acc[kLiftMaxJ].z += g.z; acc[kLiftMaxJ].w += g.w;
         }
         for (int j = 0; j <= a.J; ++j) {
-            const float4 v = j < a.J ? acc[j] : acc[kLiftMaxJ];
+            const float4 v = j < a.J ? acc[j] : acc[MAXJ];
             *reinterpret_cast<float4*>(red + ((size_t)slot * (a.J + 1) + j) * a.C + c4 * 4) = v;
         }
     }
@@ -118,7 +131,9 @@ struct HeadArgs {
     int H, D;
 };
 
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+// exact-erf GELU to ~1e-7 (Abramowitz-Stegun 7.1.26 on the MUFU pipe), as in the fused tcgen05 epilogues
+__device__ __forceinline__ float gelu_erf(float x) { return tc::gelu_fast(x); }
+__device__ __forceinline__ float gelu_erf_grad(float x) { return tc::gelu_grad_fast(x); }
 
 __global__ void head_fwd_kernel(const HeadArgs a) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
@@ -132,27 +147,26 @@ __global__ void head_fwd_kernel(const HeadArgs a) {
             w[d][k] = (d < a.D && h4 < H4) ? __ldg(reinterpret_cast<const float4*>(a.w2 + (size_t)d * a.H) + h4)
                                            : make_float4(0.f, 0.f, 0.f, 0.f);
         }
-    for (long long pos = (long long)blockIdx.x * nw + warp; pos < a.npos; pos += (long long)gridDim.x * nw) {
-        float s[kHeadMaxD];
+    const bool lane_ok = lane < H4;
+    for (long long p0 = ((long long)blockIdx.x * nw + warp) * 4; p0 < a.npos; p0 += (long long)gridDim.x * nw * 4) {
+        float4 v[4];
 #pragma unroll
-        for (int d = 0; d < kHeadMaxD; ++d) s[d] = 0.f;
+        for (int u = 0; u < 4; ++u)
+            v[u] = (lane_ok && p0 + u < a.npos) ? __ldg(reinterpret_cast<const float4*>(a.h1 + (p0 + u) * a.H) + lane)
+                                                : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-        for (int k = 0; k < kHeadMaxH4; ++k) {
-            const int h4 = lane + 32 * k;
-            if (h4 < H4) {
-                float4 v = __ldg(reinterpret_cast<const float4*>(a.h1 + pos * a.H) + h4);
-                v.x = gelu_erf(v.x); v.y = gelu_erf(v.y); v.z = gelu_erf(v.z); v.w = gelu_erf(v.w);
+        for (int u = 0; u < 4; ++u) {
+            float s[kHeadMaxD];
+            const float4 t = make_float4(gelu_erf(v[u].x), gelu_erf(v[u].y), gelu_erf(v[u].z), gelu_erf(v[u].w));
 #pragma unroll
-                for (int d = 0; d < kHeadMaxD; ++d)
-                    s[d] += v.x * w[d][k].x + v.y * w[d][k].y + v.z * w[d][k].z + v.w * w[d][k].w;
-            }
+            for (int d = 0; d < kHeadMaxD; ++d) s[d] = t.x * w[d][0].x + t.y * w[d][0].y + t.z * w[d][0].z + t.w * w[d][0].w;
+#pragma unroll
+            for (int d = 0; d < kHeadMaxD; ++d)
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) s[d] += __shfl_xor_sync(0xffffffffu, s[d], o);
+            if (lane == 0 && p0 + u < a.npos)
+                for (int d = 0; d < a.D; ++d) a.out[(p0 + u) * a.D + d] = s[d] + (a.b2 ? __ldg(a.b2 + d) : 0.f);
         }
-#pragma unroll
-        for (int d = 0; d < kHeadMaxD; ++d)
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) s[d] += __shfl_xor_sync(0xffffffffu, s[d], o);
-        if (lane == 0)
-            for (int d = 0; d < a.D; ++d) a.out[pos * a.D + d] = s[d] + (a.b2 ? __ldg(a.b2 + d) : 0.f);
     }
 }
 
@@ -175,29 +189,34 @@ __global__ void head_bwd_kernel(const HeadArgs a) {
             dw[d][k] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
     }
-    for (long long pos = (long long)blockIdx.x * nw + warp; pos < a.npos; pos += (long long)gridDim.x * nw) {
-        float g[kHeadMaxD];
+    const bool lane_ok = lane < H4;
+    for (long long p0 = ((long long)blockIdx.x * nw + warp) * 4; p0 < a.npos; p0 += (long long)gridDim.x * nw * 4) {
+        float4 v[4];
+        float g[4][kHeadMaxD];
 #pragma unroll
-        for (int d = 0; d < kHeadMaxD; ++d) {
-            g[d] = d < a.D ? __ldg(a.g_out + pos * a.D + d) : 0.f;
-            dbs[d] += g[d];
+        for (int u = 0; u < 4; ++u) {
+            const bool ok = p0 + u < a.npos;
+            v[u] = (lane_ok && ok) ? __ldg(reinterpret_cast<const float4*>(a.h1 + (p0 + u) * a.H) + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int d = 0; d < kHeadMaxD; ++d) g[u][d] = (ok && d < a.D) ? __ldg(a.g_out + (p0 + u) * a.D + d) : 0.f;
         }
 #pragma unroll
-        for (int k = 0; k < kHeadMaxH4; ++k) {
-            const int h4 = lane + 32 * k;
-            if (h4 < H4) {
-                const float4 v = __ldg(reinterpret_cast<const float4*>(a.h1 + pos * a.H) + h4);
+        for (int u = 0; u < 4; ++u) {
+            if (p0 + u < a.npos) {
                 float4 gg = make_float4(0.f, 0.f, 0.f, 0.f);
-                const float4 act = make_float4(gelu_erf(v.x), gelu_erf(v.y), gelu_erf(v.z), gelu_erf(v.w));
+                const float4 act = make_float4(gelu_erf(v[u].x), gelu_erf(v[u].y), gelu_erf(v[u].z), gelu_erf(v[u].w));
 #pragma unroll
                 for (int d = 0; d < kHeadMaxD; ++d) {
-                    gg.x = fmaf(g[d], w[d][k].x, gg.x); gg.y = fmaf(g[d], w[d][k].y, gg.y);
-                    gg.z = fmaf(g[d], w[d][k].z, gg.z); gg.w = fmaf(g[d], w[d][k].w, gg.w);
-                    dw[d][k].x = fmaf(g[d], act.x, dw[d][k].x); dw[d][k].y = fmaf(g[d], act.y, dw[d][k].y);
-                    dw[d][k].z = fmaf(g[d], act.z, dw[d][k].z); dw[d][k].w = fmaf(g[d], act.w, dw[d][k].w);
+                    const float gd = g[u][d];
+                    dbs[d] += gd;
+                    gg.x = fmaf(gd, w[d][0].x, gg.x); gg.y = fmaf(gd, w[d][0].y, gg.y);
+                    gg.z = fmaf(gd, w[d][0].z, gg.z); gg.w = fmaf(gd, w[d][0].w, gg.w);
+                    dw[d][0].x = fmaf(gd, act.x, dw[d][0].x); dw[d][0].y = fmaf(gd, act.y, dw[d][0].y);
+                    dw[d][0].z = fmaf(gd, act.z, dw[d][0].z); dw[d][0].w = fmaf(gd, act.w, dw[d][0].w);
                 }
-                gg.x *= gelu_grad_f(v.x); gg.y *= gelu_grad_f(v.y); gg.z *= gelu_grad_f(v.z); gg.w *= gelu_grad_f(v.w);
-                *(reinterpret_cast<float4*>(a.g_h1 + pos * a.H) + h4) = gg;
+                gg.x *= gelu_erf_grad(v[u].x); gg.y *= gelu_erf_grad(v[u].y);
+                gg.z *= gelu_erf_grad(v[u].z); gg.w *= gelu_erf_grad(v[u].w);
+                if (lane_ok) *(reinterpret_cast<float4*>(a.g_h1 + (p0 + u) * a.H) + lane) = gg;
             }
         }
     }
@@ -251,8 +270,8 @@ int fnm_lift_fwd(const float* x, const float* w, const float* b, float* out, int
     LiftArgs a{};
     a.x = x; a.w = w; a.b = b; a.out = out; a.B = B; a.Din = Din; a.N1 = N1; a.N2 = N2; a.P1 = P1; a.P2 = P2; a.C = C;
     a.ngrid = ngrid; a.J = Din + ngrid;
-    const long long total = (long long)B * P1 * P2 * (C / 4);
-    const int grid = (int)((total + 255) / 256 < kEndBlocks * 4 ? (total + 255) / 256 : kEndBlocks * 4);
+    const int nrows = B * P1;
+    const int grid = nrows < kEndBlocks * 8 ? nrows : kEndBlocks * 8;
     {
         LaunchScope ls("lift_fwd", as_stream(stream));
         lift_fwd_kernel<<<grid, 256, (a.J + 1) * C * sizeof(float), as_stream(stream)>>>(a);
@@ -276,16 +295,18 @@ int fnm_lift_bwd(const float* g, const float* x, float* dw, float* db, int B, in
     if (threads < C4) threads = (C4 + 31) / 32 * 32;
     const int slots = threads / C4;
     const size_t smem = (size_t)slots * (J + 1) * C * sizeof(float);
-    if (smem > 200 * 1024) return fail(FNM_ENOTSUP, "lift_bwd: reduction tile too large");
+    if (smem > 100 * 1024 || threads > 256) return fail(FNM_ENOTSUP, "lift_bwd: reduction tile too large");
     cudaStream_t st = as_stream(stream);
     static bool attr_set = false;
     if (!attr_set) {
-        cudaFuncSetAttribute(lift_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(lift_bwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+        cudaFuncSetAttribute(lift_bwd_kernel<kLiftMaxJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
         attr_set = true;
     }
     {
         LaunchScope ls("lift_bwd", st);
-        lift_bwd_kernel<<<kEndBlocks, threads, smem, st>>>(a);
+        if (J <= 4) lift_bwd_kernel<4><<<kEndBlocks, threads, smem, st>>>(a);
+        else lift_bwd_kernel<kLiftMaxJ><<<kEndBlocks, threads, smem, st>>>(a);
     }
     FNM_TRY(check_launch("lift_bwd"));
     {
@@ -302,7 +323,7 @@ int fnm_mlp_head_fwd(const float* h1, const float* w2, const float* b2, float* o
     HeadArgs a{};
     a.h1 = h1; a.w2 = w2; a.b2 = b2; a.out = out; a.npos = npos; a.H = H; a.D = D;
     if (npos <= 0) return FNM_OK;
-    const long long want = (npos + 7) / 8;
+    const long long want = (npos + 31) / 32;
     const int grid = (int)(want < kEndBlocks * 4 ? want : kEndBlocks * 4);
     {
         LaunchScope ls("mlp_head_fwd", as_stream(stream));
