@@ -66,7 +66,10 @@ __global__ void __launch_bounds__(kTgThreads, 1) tabgemm_tc(const TgArgs a) {
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < a.slots; ++s) { mbar_init(&tab_full[s], kTgTabWarps); mbar_init(&tab_empty[s], 1); }
+        for (int s = 0; s < a.slots; ++s) {
+            mbar_init(&tab_full[s], a.resident ? kTgTabWarps : ((s & 1) ? 4 : kTgTabWarps));
+            mbar_init(&tab_empty[s], 1);
+        }
         for (int s = 0; s < a.nbuf; ++s) { mbar_init(&a_full[s], 4); mbar_init(&a_empty[s], 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(&d_full[s], 1); mbar_init(&d_empty[s], 4); }
         fence_barrier_init();
@@ -187,20 +190,25 @@ __global__ void __launch_bounds__(kTgThreads, 1) tabgemm_tc(const TgArgs a) {
             }
             if (a.reuse) qa += (uint32_t)a.nchunks;
         }
-    } else if (warp < kTgFirstA) {
+    } else if (warp < kTgFirstA || (!a.resident && warp >= kTgFirstA + 4)) {
         // =========================================================================== table loaders
-        const int tt = threadIdx.x - 5 * 32;                      // 0..95
+        // resident table (ydft): warps 5-7 fill every slab once.  Streamed table (xdft / xsyn): the table is
+        // what bounds the kernel, so the second A-loader warpgroup joins in -- group 0 (warps 5-7) takes the
+        // even slabs, group 1 (warps 12-15) the odd ones, two slabs are in flight at any time.
+        const int grp = warp < kTgFirstA ? 0 : 1;
+        const int gthreads = grp == 0 ? kTgTabWarps * 32 : 128;
+        const int tt = grp == 0 ? (int)threadIdx.x - 5 * 32 : (int)threadIdx.x - (kTgFirstA + 4) * 32;
         auto fill = [&](int nt, int ch, uint8_t* dst) {
             uint8_t* hi = dst;
             uint8_t* lo = dst + (size_t)a.NT * 128;
             const int k0 = ch * 32;
             // batches of 8 independent 16-byte loads per thread (the table is L2 resident: latency, not
             // bandwidth, is what a one-load-at-a-time loop would pay)
-            for (int u0 = 0; u0 < a.NT * 8; u0 += kTgTabWarps * 32 * 8) {
+            for (int u0 = 0; u0 < a.NT * 8; u0 += gthreads * 8) {
                 float4 v[8];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    const int u = u0 + tt + j * kTgTabWarps * 32;
+                    const int u = u0 + tt + j * gthreads;
                     const int r = u >> 3, c4 = u & 7;
                     const int m = nt * a.NT + r, k = k0 + c4 * 4;
                     v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -217,7 +225,7 @@ __global__ void __launch_bounds__(kTgThreads, 1) tabgemm_tc(const TgArgs a) {
                 }
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    const int u = u0 + tt + j * kTgTabWarps * 32;
+                    const int u = u0 + tt + j * gthreads;
                     if (u < a.NT * 8) store_split4(hi, lo, u >> 3, u & 7, v[j]);
                 }
             }
@@ -236,6 +244,7 @@ __global__ void __launch_bounds__(kTgThreads, 1) tabgemm_tc(const TgArgs a) {
             for (int it = 0; it < my_items; ++it)
                 for (int nt = 0; nt < a.ntiles; ++nt)
                     for (int ch = 0; ch < a.nchunks; ++ch, ++qs) {
+                        if ((int)(qs & 1) != grp) continue;       // slots is even: slab parity == slot parity
                         const uint32_t slot = qs % (uint32_t)a.slots;
                         mbar_wait(&tab_empty[slot], ((qs / (uint32_t)a.slots) & 1) ^ 1);
                         fill(nt, ch, smem + (size_t)slot * slot_bytes);
@@ -245,6 +254,7 @@ __global__ void __launch_bounds__(kTgThreads, 1) tabgemm_tc(const TgArgs a) {
     } else {
         // =========================================================================== A loaders
         const int wg = (warp - kTgFirstA) >> 2;
+        const uint32_t nwg = a.resident ? kTgNwg : 1;
         const int q4 = warp & 3;                                  // TMEM lane quarter this warp may access
         const int L = q4 * 32 + lane;
         const uint32_t lane_base = tmem_base + ((uint32_t)(q4 * 32) << 16);
@@ -305,7 +315,7 @@ __global__ void __launch_bounds__(kTgThreads, 1) tabgemm_tc(const TgArgs a) {
         // (Prefetching across loop iterations instead makes the consumer wait on the scoreboard that also
         // tracks the younger loads, which serialises everything -- measured 1.6x slower.)
         float va[32], vb[32];
-        for (uint32_t q = 2u * (uint32_t)wg; q < total; q += 2u * kTgNwg) {
+        for (uint32_t q = 2u * (uint32_t)wg; q < total; q += 2u * nwg) {
             load(va, q);
             const bool two = q + 1 < total;
             if (two) load(vb, q + 1);
@@ -347,6 +357,7 @@ static bool tg_configure(TgArgs& a) {
                 if (!resident) {
                     slots = (int)(kTgSmemBudget / slot_bytes);
                     if (slots > kTgMaxSlots) slots = kTgMaxSlots;
+                    slots &= ~1;                                  // even: the two loader groups alternate slabs
                     if (slots < 2) continue;
                 }
                 a.NT = NT; a.ntiles = ntiles; a.dbl = dbl; a.nbuf = nbuf; a.reuse = reuse ? 1 : 0;
