@@ -34,7 +34,7 @@ struct PwArgs2 {
     long long rows;
     int S2, LY, CI, CO, wc_is_kn, single_pass;
     int NT, tiles_per_row, seg_tiles, nseg, units;
-    int K1slabs, K2slabs, LYp, stages, nlo, debug;
+    int K1slabs, K2slabs, LYp, stages, nlo, nz, debug;
     uint32_t stage_bytes, x_bytes, z_bytes;
 };
 
@@ -76,8 +76,8 @@ __device__ __forceinline__ void umma_ts32(uint32_t d, uint32_t a_tmem, uint32_t 
 // raw passes of one tile: D = (A_hi [+ A_lo]) * B_raw over K1S channel slabs and NKS2 mode k-steps.
 // K1S / NKS2 < 0: runtime extents (generic shapes).
 template <int K1S, int NKS2, bool SINGLE>
-__device__ __forceinline__ void pw2_issue_raw(uint32_t d, uint32_t tb, uint32_t x_lo, uint32_t by_lo, uint32_t slab16,
-                                              uint32_t idesc, int k1s_rt, int nks2_rt) {
+__device__ __forceinline__ void pw2_issue_raw(uint32_t d, uint32_t tb, uint32_t a2hi, uint32_t a2lo, uint32_t x_lo,
+                                              uint32_t by_lo, uint32_t slab16, uint32_t idesc, int k1s_rt, int nks2_rt) {
     const int k1s = K1S >= 0 ? K1S : k1s_rt, nks2 = NKS2 >= 0 ? NKS2 : nks2_rt;
     uint32_t accum = 0;
 #pragma unroll
@@ -96,17 +96,17 @@ __device__ __forceinline__ void pw2_issue_raw(uint32_t d, uint32_t tb, uint32_t 
     for (int k8 = 0; k8 < (NKS2 >= 0 ? NKS2 : 8); ++k8) {
         if (k8 < nks2) {
             const uint32_t b = by_lo + (k8 >> 2) * slab16 + 2 * (k8 & 3);
-            umma_ts32(d, tb + kA2Hi + k8 * 8, b, idesc, accum);
+            umma_ts32(d, a2hi + k8 * 8, b, idesc, accum);
             accum = 1;
-            if (!SINGLE) umma_ts32(d, tb + kA2Lo + k8 * 8, b, idesc, 1);
+            if (!SINGLE) umma_ts32(d, a2lo + k8 * 8, b, idesc, 1);
         }
     }
 }
 
 // remainder pass of one tile: D += A_hi * B_lo
 template <int K1S, int NKS2>
-__device__ __forceinline__ void pw2_issue_lo(uint32_t d, uint32_t tb, uint32_t x_lo, uint32_t by_lo, uint32_t slab16,
-                                             uint32_t idesc, int k1s_rt, int nks2_rt) {
+__device__ __forceinline__ void pw2_issue_lo(uint32_t d, uint32_t tb, uint32_t a2hi, uint32_t x_lo, uint32_t by_lo,
+                                             uint32_t slab16, uint32_t idesc, int k1s_rt, int nks2_rt) {
     const int k1s = K1S >= 0 ? K1S : k1s_rt, nks2 = NKS2 >= 0 ? NKS2 : nks2_rt;
 #pragma unroll
     for (int kb = 0; kb < (K1S >= 0 ? K1S : 4); ++kb) {
@@ -117,11 +117,68 @@ __device__ __forceinline__ void pw2_issue_lo(uint32_t d, uint32_t tb, uint32_t x
     }
 #pragma unroll
     for (int k8 = 0; k8 < (NKS2 >= 0 ? NKS2 : 8); ++k8) {
-        if (k8 < nks2) umma_ts32(d, tb + kA2Hi + k8 * 8, by_lo + (k8 >> 2) * slab16 + 2 * (k8 & 3), idesc, 1);
+        if (k8 < nks2) umma_ts32(d, a2hi + k8 * 8, by_lo + (k8 >> 2) * slab16 + 2 * (k8 & 3), idesc, 1);
     }
 }
 
 #define PW2_SHAPES(X) X(4, 8) X(2, 4) X(1, 3) X(4, 4) X(2, 8) X(1, 4) X(4, 0) X(2, 0) X(1, 0)
+
+
+template <bool HAS_MUL, bool HAS_ACT>
+__device__ __forceinline__ void pw2_epilogue(const PwArgs2& a, int warp, int lane, uint32_t tmem_base, int my_units,
+                                             uint64_t* acc_full, uint64_t* acc_empty) {
+    const int q4 = warp & 3, o = q4 * 32 + lane;
+    const int half = (warp - 10) >> 2;
+    const int hc = a.NT / 2;                                       // columns per half: 16, 24 or 32
+    const bool o_ok = o < a.CO;
+    const float bias = (o_ok && a.bias) ? __ldg(a.bias + o) : 0.f;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(q4 * 32) << 16) + kD0;
+    uint32_t t = 0;
+    for (int u = 0; u < my_units; ++u) {
+        const int unit = (int)blockIdx.x + u * (int)gridDim.x;
+        const int row = unit / a.nseg, seg = unit - row * a.nseg;
+        const int t0 = seg * a.seg_tiles, t1 = min(a.tiles_per_row, t0 + a.seg_tiles);
+        for (int tile = t0; tile < t1; ++tile, ++t) {
+            const uint32_t acc = t & 1;
+            const int yb = tile * a.NT + half * hc;                 // first position of this warp's columns
+            const int nv = max(0, min(hc, a.S2 - yb));              // valid positions
+            const size_t base = ((size_t)row * a.S2 + yb) * a.CO + o;
+            float m[32];
+            if (HAS_MUL) {                                        // issued before the accumulator wait: overlaps the MMAs
+                const float* mp = a.mul + base;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) m[j] = (o_ok && j < nv) ? __ldg(mp + (size_t)j * a.CO) : 0.f;
+            }
+            mbar_wait(&acc_full[acc], (t >> 1) & 1);
+            tc_fence_after();
+            const uint32_t taddr = lane_base + acc * 64u + (uint32_t)(half * hc);
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
+                if (g * 16 < hc) {
+                    uint32_t r[16];
+                    tmem_ld16(taddr + g * 16, r);
+                    tmem_ld_wait();
+                    if (o_ok) {
+                        float* op = a.out + base + (size_t)(g * 16) * a.CO;
+                        float* ap = HAS_ACT ? a.out_act + base + (size_t)(g * 16) * a.CO : nullptr;
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            if (g * 16 + j < nv) {
+                                float v = __uint_as_float(r[j]) + bias;
+                                if (HAS_MUL) v *= gelu_grad_fast(m[g * 16 + j]);
+                                op[(size_t)j * a.CO] = v;
+                                if (HAS_ACT) ap[(size_t)j * a.CO] = gelu_fast(v);
+                            }
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[acc]);
+        }
+    }
+}
 
 __global__ void __launch_bounds__(kPwThreads, 1)
 pw2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapBy,
@@ -131,27 +188,30 @@ pw2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUt
     // [stages x {X raw slabs, by raw slabs}] [lo copy of one stage] [Z staging] [barriers]
     uint8_t* lo_buf = smem + (size_t)a.stages * a.stage_bytes;
     float* zs = reinterpret_cast<float*>(lo_buf + (size_t)a.nlo * a.stage_bytes);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(zs) + a.z_bytes);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(zs) + (size_t)a.nz * a.z_bytes);
     uint64_t* full = bars;                          // [kPwMaxStages]
     uint64_t* empty = bars + kPwMaxStages;          // [kPwMaxStages]
     uint64_t* lo_full = bars + 2 * kPwMaxStages;    // [2]
     uint64_t* lo_empty = lo_full + 2;               // [2]
-    uint64_t* z_full = lo_full + 4;
-    uint64_t* z_empty = lo_full + 5;
-    uint64_t* a2_full = lo_full + 6;
-    uint64_t* a2_empty = lo_full + 7;
-    uint64_t* acc_full = lo_full + 8;               // [2]
-    uint64_t* acc_empty = lo_full + 10;             // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(lo_full + 12);
+    uint64_t* z_full = lo_full + 4;                 // [4]
+    uint64_t* z_empty = lo_full + 8;                // [4]
+    uint64_t* a2_full = lo_full + 12;               // [2]
+    uint64_t* a2_empty = lo_full + 14;              // [2]
+    uint64_t* acc_full = lo_full + 16;              // [2]
+    uint64_t* acc_empty = lo_full + 18;             // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(lo_full + 20);
 
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     const bool has_x = a.CI > 0, has_z = a.LY > 0;
+    // Z^T hi/lo (A2): one 128-column buffer for up to 64 mode columns, or -- when LYp <= 32 -- two 64-column
+    // buffers so that the next grid row's Z is converted while the current row is still being multiplied
+    const uint32_t na2 = a.LYp <= 32 ? 2u : 1u;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < a.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], a.single_pass ? 1 : 5); }
         for (int s = 0; s < 2; ++s) { mbar_init(&lo_full[s], 4); mbar_init(&lo_empty[s], 1); }
-        mbar_init(z_full, 1); mbar_init(z_empty, 4);
-        mbar_init(a2_full, 4); mbar_init(a2_empty, 1);
+        for (int s = 0; s < 4; ++s) { mbar_init(&z_full[s], 1); mbar_init(&z_empty[s], 4); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&a2_full[s], 4); mbar_init(&a2_empty[s], 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 8); }
         fence_barrier_init();
         tma_prefetch_desc(&mapX); tma_prefetch_desc(&mapBy); tma_prefetch_desc(&mapZ);
@@ -198,10 +258,11 @@ pw2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUt
             for (int u = 0; u < my_units; ++u) {
                 int row, t0, t1;
                 unit_tiles(u, row, t0, t1);
-                if (has_z) {
-                    mbar_wait(z_empty, (uint32_t)((u & 1) ^ 1));
-                    mbar_expect_tx(z_full, a.z_bytes);
-                    tma_load_2d(&mapZ, z_full, zs, 0, row * a.LY);
+                if (has_z) {                                       // ring of nz staging buffers for the rows' Z tiles
+                    const uint32_t zb = (uint32_t)u % (uint32_t)a.nz, zpar = ((uint32_t)u / (uint32_t)a.nz) & 1;
+                    mbar_wait(&z_empty[zb], zpar ^ 1);
+                    mbar_expect_tx(&z_full[zb], a.z_bytes);
+                    tma_load_2d(&mapZ, &z_full[zb], reinterpret_cast<uint8_t*>(zs) + (size_t)zb * a.z_bytes, 0, row * a.LY);
                 }
                 for (int tile = t0; tile < t1; ++tile, ++t) {
                     const uint32_t s = t % (uint32_t)a.stages;
@@ -228,7 +289,9 @@ pw2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUt
         for (int u = 0; u < my_units; ++u) {
             int row, t0, t1;
             unit_tiles(u, row, t0, t1);
-            if (has_z) mbar_wait(a2_full, (uint32_t)(u & 1));
+            const uint32_t ub = (uint32_t)u % na2, upar = ((uint32_t)u / na2) & 1;
+            const uint32_t a2hi = tmem_base + kA2Hi + (na2 == 2 ? 64u * ub : 0u), a2lo = a2hi + (na2 == 2 ? 32u : 64u);
+            if (has_z) mbar_wait(&a2_full[ub], upar);
             for (int tile = t0; tile < t1; ++tile, ++t) {
                 const uint32_t s = t % (uint32_t)a.stages, acc = t & 1;
                 mbar_wait(&acc_empty[acc], ((t >> 1) & 1) ^ 1);
@@ -240,15 +303,15 @@ pw2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUt
                 bool done = false;
 #define PW2_RAW(K1, K2)                                                                                                  \
                 if (!done && a.K1slabs == K1 && nks2 == K2) {                                                            \
-                    if (a.single_pass) pw2_issue_raw<K1, K2, true>(d, tmem_base, x_lo, by_lo, slab16, idesc, 0, 0);      \
-                    else pw2_issue_raw<K1, K2, false>(d, tmem_base, x_lo, by_lo, slab16, idesc, 0, 0);                   \
+                    if (a.single_pass) pw2_issue_raw<K1, K2, true>(d, tmem_base, a2hi, a2lo, x_lo, by_lo, slab16, idesc, 0, 0);      \
+                    else pw2_issue_raw<K1, K2, false>(d, tmem_base, a2hi, a2lo, x_lo, by_lo, slab16, idesc, 0, 0);                   \
                     done = true;                                                                                         \
                 }
                 PW2_SHAPES(PW2_RAW)
 #undef PW2_RAW
                 if (!done) {
-                    if (a.single_pass) pw2_issue_raw<-1, -1, true>(d, tmem_base, x_lo, by_lo, slab16, idesc, a.K1slabs, nks2);
-                    else pw2_issue_raw<-1, -1, false>(d, tmem_base, x_lo, by_lo, slab16, idesc, a.K1slabs, nks2);
+                    if (a.single_pass) pw2_issue_raw<-1, -1, true>(d, tmem_base, a2hi, a2lo, x_lo, by_lo, slab16, idesc, a.K1slabs, nks2);
+                    else pw2_issue_raw<-1, -1, false>(d, tmem_base, a2hi, a2lo, x_lo, by_lo, slab16, idesc, a.K1slabs, nks2);
                 }
                 umma_commit(&empty[s]);                              // the raw tile is free once the raw passes retire
                 if (!a.single_pass) {
@@ -260,16 +323,16 @@ pw2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUt
                     done = false;
 #define PW2_LO(K1, K2)                                                                                                   \
                     if (!done && a.K1slabs == K1 && nks2 == K2) {                                                        \
-                        pw2_issue_lo<K1, K2>(d, tmem_base, xl_lo, byl_lo, slab16, idesc, 0, 0);                          \
+                        pw2_issue_lo<K1, K2>(d, tmem_base, a2hi, xl_lo, byl_lo, slab16, idesc, 0, 0);                          \
                         done = true;                                                                                     \
                     }
                     PW2_SHAPES(PW2_LO)
 #undef PW2_LO
-                    if (!done) pw2_issue_lo<-1, -1>(d, tmem_base, xl_lo, byl_lo, slab16, idesc, a.K1slabs, nks2);
+                    if (!done) pw2_issue_lo<-1, -1>(d, tmem_base, a2hi, xl_lo, byl_lo, slab16, idesc, a.K1slabs, nks2);
                     umma_commit(&lo_empty[lb]);
                 }
                 umma_commit(&acc_full[acc]);
-                if (has_z && tile == t1 - 1) umma_commit(a2_empty);
+                if (has_z && tile == t1 - 1) umma_commit(&a2_empty[ub]);
                 __syncwarp();
             }
         }
@@ -279,19 +342,23 @@ pw2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUt
         const uint32_t lane_base = tmem_base + ((uint32_t)(q4 * 32) << 16);
         const bool c_ok = c < a.CO;
         for (int u = 0; u < (has_z ? my_units : 0); ++u) {
-            mbar_wait(z_full, (uint32_t)(u & 1));
-            mbar_wait(a2_empty, (uint32_t)((u & 1) ^ 1));
+            const uint32_t ub = (uint32_t)u % na2, upar = ((uint32_t)u / na2) & 1;
+            const uint32_t a2hi = kA2Hi + (na2 == 2 ? 64u * ub : 0u), a2lo = a2hi + (na2 == 2 ? 32u : 64u);
+            const uint32_t zb = (uint32_t)u % (uint32_t)a.nz, zpar = ((uint32_t)u / (uint32_t)a.nz) & 1;
+            const float* zsb = reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(zs) + (size_t)zb * a.z_bytes);
+            mbar_wait(&z_full[zb], zpar);
+            mbar_wait(&a2_empty[ub], upar ^ 1);
             tc_fence_after();
             for (int l0 = 0; l0 < a.LYp; l0 += 16) {
                 float v[16];
 #pragma unroll
-                for (int j = 0; j < 16; ++j) v[j] = (c_ok && l0 + j < a.LY) ? zs[(l0 + j) * a.CO + c] : 0.f;
-                split_to_tmem16(lane_base + kA2Hi + l0, lane_base + kA2Lo + l0, v, !a.single_pass);
+                for (int j = 0; j < 16; ++j) v[j] = (c_ok && l0 + j < a.LY) ? zsb[(l0 + j) * a.CO + c] : 0.f;
+                split_to_tmem16(lane_base + a2hi + l0, lane_base + a2lo + l0, v, !a.single_pass);
             }
             tmem_st_wait();
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) { mbar_arrive(z_empty); mbar_arrive(a2_full); }
+            if (lane == 0) { mbar_arrive(&z_empty[zb]); mbar_arrive(&a2_full[ub]); }
         }
     } else if (warp < 10) {
         // =========================================================================== converters: lo = raw - trunc(raw)
@@ -337,56 +404,12 @@ pw2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUt
         }
     } else {
         // =========================================================================== epilogue (8 warps)
-        const int q4 = warp & 3, o = q4 * 32 + lane;
-        const int half = (warp - 10) >> 2;
-        const int hc = a.NT / 2;                                       // columns per half: 16, 24 or 32
-        const bool o_ok = o < a.CO;
-        const float bias = (o_ok && a.bias) ? __ldg(a.bias + o) : 0.f;
-        const uint32_t lane_base = tmem_base + ((uint32_t)(q4 * 32) << 16) + kD0;
-        uint32_t t = 0;
-        for (int u = 0; u < my_units; ++u) {
-            int row, t0, t1;
-            unit_tiles(u, row, t0, t1);
-            for (int tile = t0; tile < t1; ++tile, ++t) {
-                const uint32_t acc = t & 1;
-                const int yb = tile * a.NT + half * hc;                 // first position of this warp's columns
-                const int nv = max(0, min(hc, a.S2 - yb));              // valid positions
-                const size_t base = ((size_t)row * a.S2 + yb) * a.CO + o;
-                float m[32];
-                if (a.mul) {                                          // issued before the accumulator wait: overlaps the MMAs
-                    const float* mp = a.mul + base;
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) m[j] = (o_ok && j < nv) ? __ldg(mp + (size_t)j * a.CO) : 0.f;
-                }
-                mbar_wait(&acc_full[acc], (t >> 1) & 1);
-                tc_fence_after();
-                const uint32_t taddr = lane_base + acc * 64u + (uint32_t)(half * hc);
-#pragma unroll
-                for (int g = 0; g < 2; ++g) {
-                    if (g * 16 < hc) {
-                        uint32_t r[16];
-                        tmem_ld16(taddr + g * 16, r);
-                        tmem_ld_wait();
-                        if (o_ok) {
-                            float* op = a.out + base + (size_t)(g * 16) * a.CO;
-                            float* ap = a.out_act ? a.out_act + base + (size_t)(g * 16) * a.CO : nullptr;
-#pragma unroll
-                            for (int j = 0; j < 16; ++j) {
-                                if (g * 16 + j < nv) {
-                                    float v = __uint_as_float(r[j]) + bias;
-                                    if (a.mul) v *= gelu_grad_fast(m[g * 16 + j]);
-                                    op[(size_t)j * a.CO] = v;
-                                    if (ap) ap[(size_t)j * a.CO] = gelu_fast(v);
-                                }
-                            }
-                        }
-                    }
-                }
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&acc_empty[acc]);
-            }
-        }
+        // explicitly specialised on (GELU' operand, GELU copy): with the flags tested per element the loop is
+        // 2x slower, and whether ptxas unswitches it on its own changes with unrelated edits (measured)
+        if (a.mul && a.out_act) pw2_epilogue<true, true>(a, warp, lane, tmem_base, my_units, acc_full, acc_empty);
+        else if (a.mul) pw2_epilogue<true, false>(a, warp, lane, tmem_base, my_units, acc_full, acc_empty);
+        else if (a.out_act) pw2_epilogue<false, true>(a, warp, lane, tmem_base, my_units, acc_full, acc_empty);
+        else pw2_epilogue<false, false>(a, warp, lane, tmem_base, my_units, acc_full, acc_empty);
     }
 
     tc_fence_before();
@@ -446,7 +469,10 @@ static bool pw2_configure(PwArgs2& a, int64_t rows, int S2, int LY, int CI, int 
     a.tiles_per_row = (S2 + a.NT - 1) / a.NT;
     a.x_bytes = (uint32_t)a.K1slabs * a.NT * 128u;
     a.stage_bytes = a.x_bytes + (uint32_t)a.K2slabs * a.NT * 128u;
-    const uint32_t fixed = a.z_bytes + 1024 /*align*/ + 256 /*barriers*/;
+    // Z staging: a ring when the tiles are small (few tiles per row: the row-to-row hand-over must pipeline)
+    a.nz = 1;
+    if (a.z_bytes > 0 && a.z_bytes % 128 == 0) { a.nz = (int)(32768u / a.z_bytes); a.nz = a.nz < 1 ? 1 : (a.nz > 4 ? 4 : a.nz); }
+    const uint32_t fixed = (uint32_t)a.nz * a.z_bytes + 1024 /*align*/ + 512 /*barriers*/;
     if (fixed + 3 * a.stage_bytes > kPwSmemBudget) return false;             // 2 raw stages + 1 remainder buffer at least
     const int slots = (int)((kPwSmemBudget - fixed) / a.stage_bytes);        // raw stages + remainder buffers
     // bytes in flight are what hides HBM latency (~90 KB per SM): every slot beyond one remainder buffer is a raw stage
@@ -510,7 +536,7 @@ int tc_pw2(const float* x, const float* wc, int wc_is_kn, const float* bias, con
         mx = mb;
     }
     if (LY == 0) { mb = mx; mz = mx; }                          // never dereferenced without a spectral term
-    const size_t smem = (size_t)(a.stages + a.nlo) * a.stage_bytes + a.z_bytes + 1024 + 256;
+    const size_t smem = (size_t)(a.stages + a.nlo) * a.stage_bytes + (size_t)a.nz * a.z_bytes + 1024 + 512;
     static bool attr_set = false;
     if (!attr_set) {
         const cudaError_t e = cudaFuncSetAttribute(pw2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);

@@ -227,22 +227,36 @@ __global__ void __launch_bounds__(kCwThreads, 1) conv_wgrad_tc(const CwArgs a) {
     if (warp == kCwMmaWarp) tmem_dealloc(tmem_base, 512);
 }
 
-__global__ void conv_wgrad_tc_reduce(const float* __restrict__ part, int nparts, int Ci, int Co, float* __restrict__ dwc,
-                                     float* __restrict__ dbc) {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    const size_t stride = cw_part_floats(Ci, Co);
+// dwc / dbc = sum of the per-CTA partials.  fold > 1: the kernel ran on a folded problem -- `fold` consecutive
+// positions of a C-channel tensor viewed as ONE position of a (fold*C)-channel tensor, which is the same
+// memory -- so all 128 TMEM lanes and loader threads are busy for C = 32 / 64; the wanted C x C products are
+// the `fold` diagonal blocks of the (fold*C) x (fold*C) result.
+__global__ void conv_wgrad_tc_reduce(const float* __restrict__ part, int nparts, int Ci, int Co, int fold,
+                                     float* __restrict__ dwc, float* __restrict__ dbc) {
+    // one warp per output element; lanes stride over (partial, diagonal block) and shuffle-reduce
+    const int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    const int Cif = Ci * fold, Cof = Co * fold;
+    const size_t stride = cw_part_floats(Cif, Cof);
+    if (j >= Co * Ci + Co) return;
+    float s = 0.f;
     if (j < Co * Ci) {
-        float s = 0.f;
-        for (int k = 0; k < nparts; ++k) s += part[(size_t)k * stride + j];
-        if (dwc) dwc[j] = s;
-    } else if (j < Co * Ci + Co) {
-        const int o = j - Co * Ci;
-        float s = 0.f;
-        for (int k = 0; k < nparts; ++k) {
-            const float* p = part + (size_t)k * stride + (size_t)Ci * Co;
-            for (int w = 0; w < kCwLoaderWgs; ++w) s += p[(size_t)w * Co + o];
+        const int o = j / Ci, i = j - o * Ci;
+        for (int t = lane; t < nparts * fold; t += 32) {
+            const int k = t / fold, r = t - k * fold;
+            s += part[(size_t)k * stride + (size_t)(r * Co + o) * Cif + (r * Ci + i)];
         }
-        if (dbc) dbc[o] = s;
+    } else {
+        const int o = j - Co * Ci;
+        for (int t = lane; t < nparts * fold * kCwLoaderWgs; t += 32) {
+            const int k = t / (fold * kCwLoaderWgs), rem = t - k * fold * kCwLoaderWgs, w = rem / fold, r = rem - w * fold;
+            s += part[(size_t)k * stride + (size_t)Cif * Cof + (size_t)w * Cof + r * Co + o];
+        }
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+    if (lane == 0) {
+        if (j < Co * Ci) { if (dwc) dwc[j] = s; }
+        else if (dbc) dbc[j - Co * Ci] = s;
     }
 }
 
@@ -260,17 +274,25 @@ bool tc_conv_wgrad_supported(int64_t npos, int Ci, int Co) {
     return npos >= 4096 && Ci % 16 == 0 && Co % 16 == 0 && Ci >= 16 && Co >= 16 && Ci <= 128 && Co <= 128;
 }
 
+static int cw_fold(int64_t npos, int Ci, int Co) {
+    if (Ci != Co || (Ci != 32 && Ci != 64)) return 1;
+    const int fold = 128 / Ci;
+    return npos % fold == 0 ? fold : 1;
+}
+
 size_t tc_conv_wgrad_workspace(int64_t npos, int Ci, int Co) {
-    return align_up((size_t)cw_grid(npos) * cw_part_floats(Ci, Co) * sizeof(float), 256);
+    const int fold = cw_fold(npos, Ci, Co);
+    return align_up((size_t)cw_grid(npos / fold) * cw_part_floats(Ci * fold, Co * fold) * sizeof(float), 256);
 }
 
 int tc_conv_wgrad(const float* g, const float* x, int act, float* dwc, float* dbc, int64_t npos, int Ci, int Co,
                   float* partial, int mode, cudaStream_t st) {
     CwArgs a{};
-    a.g = g; a.x = x; a.part = partial; a.npos = npos; a.Ci = Ci; a.Co = Co; a.act = act;
+    const int fold = cw_fold(npos, Ci, Co);
+    a.g = g; a.x = x; a.part = partial; a.npos = npos / fold; a.Ci = Ci * fold; a.Co = Co * fold; a.act = act;
     a.single_pass = mode == FNM_MODE_TF32;
-    a.nchunks = (npos + 31) / 32;
-    const int grid = cw_grid(npos);
+    a.nchunks = (a.npos + 31) / 32;
+    const int grid = cw_grid(a.npos);
     a.per = (a.nchunks + grid - 1) / grid;
     static bool attr_set = false;
     const size_t smem = kCwStages * kCwStageBytes + kCwAccBytes + 2048;   // > half the SM: one CTA per SM owns the TMEM
@@ -287,7 +309,7 @@ int tc_conv_wgrad(const float* g, const float* x, int act, float* dwc, float* db
     const int count = Co * Ci + Co;
     {
         LaunchScope ls("conv_wgrad_reduce", st);
-        conv_wgrad_tc_reduce<<<(count + 255) / 256, 256, 0, st>>>(partial, grid, Ci, Co, dwc, dbc);
+        conv_wgrad_tc_reduce<<<(count * 32 + 255) / 256, 256, 0, st>>>(partial, grid, Ci, Co, fold, dwc, dbc);
     }
     return check_launch("conv_wgrad_reduce");
 }
