@@ -13,7 +13,8 @@ from fnm_b200.plan import spectral_tables
 cfg = sys.argv[1] if len(sys.argv) > 1 else "cfg5"
 iters = int(sys.argv[2]) if len(sys.argv) > 2 else 5
 B, C_, P1, P2, m1, m2 = {"cfg5": (32, 128, 288, 288, 32, 32), "cfg1": (20, 32, 72, 72, 12, 12),
-                         "cfg4": (20, 64, 144, 144, 16, 16)}[cfg]
+                         "cfg4": (20, 64, 144, 144, 16, 16), "cfg3": (128, 32, 248, 57, 12, 12),
+                         "cfg3b": (128, 32, 248, 64, 12, 16), "cfg3c": (128, 32, 248, 64, 12, 12), "cfg3d": (128, 64, 248, 57, 12, 12)}[cfg]
 dev = torch.device("cuda")
 tab = spectral_tables(P1, P2, m1, m2).device(dev)
 LY, R, NY = 2 * m2, 2 * m1, m2
