@@ -317,9 +317,16 @@ def run_ours(args, rank, world):
         prof = {k: (c / nprof, t / nprof) for k, (c, t) in _lib.profile_end().items()}
     barrier()
 
-    if rank != 0:
+    def leave():
+        """Multi-rank exit: tearing an NCCL communicator down while a CUDA graph that captured its kernels is
+        alive hung on the B200 box, so after a last barrier every rank flushes and exits without the teardown."""
         if world > 1:
-            dist.destroy_process_group()
+            sys.stdout.flush()
+            sys.stderr.flush()
+            os._exit(0)
+
+    if rank != 0:
+        leave()
         return
 
     # ---- roofline of the dominant kernel
@@ -383,8 +390,7 @@ def run_ours(args, rank, world):
         "cpu_baseline": cpu,
     }
     print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    leave()
 
 
 def main():
