@@ -40,7 +40,7 @@ struct TgArgs {
     long long gin_s1, gin_s0, k_s1, k_s0, gout_s1, gout_s0, m_s1, m_s0;
     int gin_div, kin_div, gout_div, mout_div;
     int C, G, GL, CB, items;
-    int Kt, Mt, nchunks, NT, ntiles, dbl, nbuf, reuse, resident, slots;
+    int Kt, Mt, nchunks, NT, ntiles, dbl, nbuf, reuse, resident, slots, nmain;
     int act, single_pass, tab_vec4;
 };
 
@@ -101,14 +101,16 @@ __global__ void __launch_bounds__(kTgThreads, 1) tabgemm_tc(const TgArgs a) {
                 const uint32_t dpar = a.dbl ? ((dcount >> 1) & 1) : (dcount & 1);
                 mbar_wait(&d_full[dbuf], dpar);
                 tc_fence_after();
-                const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + dcol0 + (uint32_t)(dbuf * 2 * a.NT);
+                const uint32_t dstride = (uint32_t)((a.nmain + 1) * a.NT);       // nmain main accumulators + corrections
+                const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + dcol0 + (uint32_t)dbuf * dstride;
                 const int mlim = min(a.NT, a.Mt - nt * a.NT);
                 for (int c0 = 0; c0 < mlim; c0 += 16) {
                     uint32_t r[16];
                     tmem_ld16(taddr + c0, r);
-                    if (!a.single_pass) {                         // + the separately accumulated correction terms
+                    // + the other main accumulator(s) and the separately accumulated correction terms
+                    for (int e = 1; e < a.nmain + (a.single_pass ? 0 : 1); ++e) {
                         uint32_t rc[16];
-                        tmem_ld16(taddr + a.NT + c0, rc);
+                        tmem_ld16(taddr + (uint32_t)(e * a.NT) + c0, rc);
                         tmem_ld_wait();
 #pragma unroll
                         for (int j = 0; j < 16; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(rc[j]));
@@ -156,8 +158,11 @@ __global__ void __launch_bounds__(kTgThreads, 1) tabgemm_tc(const TgArgs a) {
                 // the tensor core accumulates with truncation (measured: ~1.9e-8 relative error per MMA added
                 // to an accumulator), so the hi*hi products go to their own accumulator and the two
                 // correction passes, 2^-11 smaller, to a second one: the long chain is three times shorter
-                const uint32_t d = tmem_base + dcol0 + (uint32_t)(dbuf * 2 * a.NT), dc = d + (uint32_t)a.NT;
-                uint32_t accum = 0;
+                // With nmain = 2 the chunks alternate between two main accumulators (chains half as long again);
+                // the epilogue adds them with round-to-nearest.
+                const uint32_t dstride = (uint32_t)((a.nmain + 1) * a.NT);
+                const uint32_t d0 = tmem_base + dcol0 + (uint32_t)dbuf * dstride, dc = d0 + (uint32_t)(a.nmain * a.NT);
+                uint32_t accum = 0, accum_m[2] = {0u, 0u};
                 for (int ch = 0; ch < a.nchunks; ++ch) {
                     uint32_t q;
                     bool first_use, last_use;
@@ -175,7 +180,9 @@ __global__ void __launch_bounds__(kTgThreads, 1) tabgemm_tc(const TgArgs a) {
                     const uint64_t bhi = make_desc(sb), blo = make_desc(sb + (uint32_t)a.NT * 128u);
                     const int nks = min(4, (a.Kt - ch * 32 + 7) / 8);
                     for (int ks = 0; ks < nks; ++ks) {
-                        umma_ts(d, a_hi + ks * 8, bhi + 2 * ks, idesc, accum);
+                        const int mi = a.nmain == 2 ? (ch & 1) : 0;
+                        umma_ts(d0 + (uint32_t)(mi * a.NT), a_hi + ks * 8, bhi + 2 * ks, idesc, accum_m[mi]);
+                        accum_m[mi] = 1;
                         if (!a.single_pass) {
                             umma_ts(dc, a_lo + ks * 8, bhi + 2 * ks, idesc, accum);
                             umma_ts(dc, a_hi + ks * 8, blo + 2 * ks, idesc, 1);
@@ -344,10 +351,15 @@ static bool tg_configure(TgArgs& a) {
             const int NT = ((a.Mt + ntiles - 1) / ntiles + 15) / 16 * 16;
             if (NT > 128) continue;
             for (int dbl = 1; dbl >= 0; --dbl) {
-                const int dcols = 2 * NT * (dbl ? 2 : 1);          // main + correction accumulator
+                const bool will_stream = (uint64_t)a.nchunks * ntiles * NT * 256u > kTgSmemBudget || a.nchunks * ntiles > kTgMaxSlots;
+                const int nwg_a = will_stream ? 1 : kTgNwg;        // the second A warpgroup streams table slabs instead
+                // long contractions split the main chain over two accumulators when TMEM allows (truncation bias)
+                int nmain = (a.nchunks >= 8 && 3 * NT * (dbl ? 2 : 1) + 64 * 2 * nwg_a <= 512) ? 2 : 1;
+                if (dbl && nmain == 1 && a.nchunks >= 8 && 3 * NT + 64 * 2 * nwg_a <= 512) continue;   // accuracy first: single-buffered D with two chains
+                const int dcols = (nmain + 1) * NT * (dbl ? 2 : 1);  // main accumulator(s) + correction accumulator
                 int nbuf = (512 - dcols) / 64;
                 if (nbuf > kTgMaxBuf) nbuf = kTgMaxBuf;
-                if (nbuf < 2 * kTgNwg) continue;                  // mbarrier parity safety of the pair schedule
+                if (nbuf < 2 * nwg_a) continue;                   // mbarrier parity safety of the pair schedule
                 const bool reuse = ntiles == 1 || a.nchunks <= nbuf;
                 if (!reuse && pass == 0) continue;
                 const uint32_t slot_bytes = (uint32_t)NT * 256u;
@@ -360,7 +372,7 @@ static bool tg_configure(TgArgs& a) {
                     slots &= ~1;                                  // even: the two loader groups alternate slabs
                     if (slots < 2) continue;
                 }
-                a.NT = NT; a.ntiles = ntiles; a.dbl = dbl; a.nbuf = nbuf; a.reuse = reuse ? 1 : 0;
+                a.NT = NT; a.ntiles = ntiles; a.dbl = dbl; a.nbuf = nbuf; a.reuse = reuse ? 1 : 0; a.nmain = nmain;
                 a.resident = resident ? 1 : 0; a.slots = slots;
                 return true;
             }
