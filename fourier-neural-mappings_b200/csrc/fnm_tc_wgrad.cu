@@ -29,11 +29,16 @@
 namespace fnm {
 namespace tc {
 
-constexpr int kCwLoaderWgs = 2;
-constexpr int kCwStages = 2;                               // >= loader warpgroups (mbarrier parity safety)
-constexpr int kCwSegChunks = 16;
-constexpr int kCwMmaWarp = 12;
-constexpr int kCwThreads = 13 * 32;
+constexpr int kCwLoaderWgs = 3;
+constexpr int kCwStages = 3;                               // >= loader warpgroups (mbarrier parity safety)
+constexpr int kCwSegChunks = 8;                            // 8 chunks x 12 MMAs per chain (main and corrections share it)
+constexpr int kCwEpiWarp0 = 4 * kCwLoaderWgs;              // warps 12-15: flush / epilogue warpgroup
+constexpr int kCwMmaWarp = kCwEpiWarp0 + 4;                // warp 16
+constexpr int kCwThreads = (kCwMmaWarp + 4) * 32;          // 20 warps (5 per SM sub-partition): 96 registers each at launch.
+// setmaxnreg re-balances them: the register pool a warpgroup can grow from holds only what OTHER warps of the
+// same CTA released, so the MMA warp's three idle siblings (warps 17-19) exist to donate theirs:
+//   released: epilogue 4 x 32 x (96-64) + MMA warp and its 3 donor siblings 4 x 32 x (96-32) = 12 288
+//   claimed : loaders 12 x 32 x (120-96)                                              =  9 216
 constexpr uint32_t kCwStageBytes = 32768;                  // raw slab 16 KB + lo slab 16 KB
 constexpr uint32_t kCwAccBytes = 65536;                    // fp32 [128 cols][128 lanes]
 
@@ -76,8 +81,10 @@ __global__ void __launch_bounds__(kCwThreads, 1) conv_wgrad_tc(const CwArgs a) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
-    // TMEM columns: [0,128) main buffer 0, [128,256) main buffer 1, [256,384) corrections, [384,512) g stages
-    const uint32_t kCorr = 256u, kStage0 = 384u;
+    // TMEM columns: [0,128) accumulator buffer 0, [128,256) buffer 1, [256,448) three g stages (hi 32 | lo 32)
+    const uint32_t kStage0 = 256u;
+    // register re-balancing: the loaders hold 64 loads in flight per thread, the other roles need few
+
 
     const long long c_begin = (long long)blockIdx.x * a.per;
     long long c_end = c_begin + a.per;
@@ -86,8 +93,11 @@ __global__ void __launch_bounds__(kCwThreads, 1) conv_wgrad_tc(const CwArgs a) {
     const int nseg = (n + kCwSegChunks - 1) / kCwSegChunks;
     float* part = a.part + (size_t)blockIdx.x * cw_part_floats(a.Ci, a.Co);
 
-    if (warp == kCwMmaWarp) {
+    if (warp > kCwMmaWarp) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 32;\n");      // register donors (same value as the MMA warp: one warpgroup), nothing else to do
+    } else if (warp == kCwMmaWarp) {
         // ======================================================================= MMA issuer
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 32;\n");
         const uint32_t sbase = smem_u32(smem);
         const uint32_t idesc = make_idesc(128, a.Ci);
         for (int q = 0; q < n; ++q) {
@@ -99,23 +109,24 @@ __global__ void __launch_bounds__(kCwThreads, 1) conv_wgrad_tc(const CwArgs a) {
             }
             mbar_wait(&full[s], (uint32_t)((q / kCwStages) & 1));
             tc_fence_after();
-            const uint32_t dmain = tmem_base + 128u * db, dcorr = tmem_base + kCorr;
+            const uint32_t dmain = tmem_base + 128u * db;
             const uint32_t g_hi = tmem_base + kStage0 + 64u * s, g_lo = g_hi + 32u;
             const uint64_t bx = make_desc(sbase + s * kCwStageBytes), bxl = make_desc(sbase + s * kCwStageBytes + 16384u);
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks) {
                 umma_ts(dmain, g_hi + ks * 8, bx + 2 * ks, idesc, (qs > 0 || ks > 0) ? 1u : 0u);
                 if (!a.single_pass) {
-                    umma_ts(dcorr, g_lo + ks * 8, bx + 2 * ks, idesc, (q > 0 || ks > 0) ? 1u : 0u);
-                    umma_ts(dcorr, g_hi + ks * 8, bxl + 2 * ks, idesc, 1);
+                    umma_ts(dmain, g_lo + ks * 8, bx + 2 * ks, idesc, 1);
+                    umma_ts(dmain, g_hi + ks * 8, bxl + 2 * ks, idesc, 1);
                 }
             }
             umma_commit(&empty[s]);
             if (qs == kCwSegChunks - 1 || q == n - 1) umma_commit(&seg_full[db]);
             __syncwarp();
         }
-    } else if (warp < 4 * kCwLoaderWgs) {
-        // ======================================================================= loaders: warpgroup wg takes chunks q = wg, wg+2, ...
+    } else if (warp < kCwEpiWarp0) {
+        // ======================================================================= loaders: warpgroup wg takes chunks q = wg, wg+3, ...
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 120;\n");
         const int wg = warp >> 2;
         const int q4 = warp & 3;
         const int ch = q4 * 32 + lane;                             // channel = TMEM lane (g) = smem row (x)
@@ -175,6 +186,7 @@ __global__ void __launch_bounds__(kCwThreads, 1) conv_wgrad_tc(const CwArgs a) {
         if (g_ok) part[(size_t)a.Ci * a.Co + (size_t)wg * a.Co + ch] = dbsum;
     } else {
         // ======================================================================= flush / epilogue warpgroup
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 64;\n");
         const int q4 = warp & 3;
         const int o = q4 * 32 + lane;                              // TMEM lane = output channel
         const uint32_t lane_addr = tmem_base + ((uint32_t)(q4 * 32) << 16);
@@ -198,12 +210,6 @@ __global__ void __launch_bounds__(kCwThreads, 1) conv_wgrad_tc(const CwArgs a) {
 #pragma unroll
                     for (int j = 0; j < 16; ++j) acc[(c0 + j) * 128 + o] = v[j];
                 } else {
-                    if (!a.single_pass) {
-                        tmem_ld16(lane_addr + kCorr + c0, r);
-                        tmem_ld_wait();
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) v[j] += __uint_as_float(r[j]);
-                    }
                     if (o < a.Co) {
 #pragma unroll
                         for (int j4 = 0; j4 < 4; ++j4)
