@@ -19,9 +19,11 @@
 //       warp and table row.
 // fp32 parity mode is 3xTF32 (A_hi*B_hi + A_lo*B_hi + A_hi*B_lo); FNM_MODE_TF32 issues A_hi*B_hi only.
 //
-// Warp roles (512 threads = 4 warps per SM sub-partition -> 128 registers; persistent, one CTA per SM):
-//   warps 0-3   epilogue                         warp 4      TMEM allocator + MMA issuer
-//   warps 5-7   table loaders                    warps 8-15  two A-loader warpgroups
+// Warp roles (640 threads, persistent, one CTA per SM; 96 registers at launch, setmaxnreg gives the A loaders
+// 128 from what the other warpgroups release):
+//   warps 0-3   epilogue                         warp 4       TMEM allocator + MMA issuer
+//   warps 5-7   table loaders (group 0)          warps 8-15   two A-loader warpgroups
+//   warps 16-19 table loaders (group 1) when the table is streamed, otherwise idle register donors
 #include "fnm_tc_ptx.cuh"
 
 namespace fnm {
@@ -30,7 +32,7 @@ namespace tc {
 constexpr int kTgNwg = 2;                                 // A-loader warpgroups, two chunks each: needs nbuf >= 4
 constexpr int kTgTabWarps = 3;
 constexpr int kTgFirstA = 5 + kTgTabWarps;                // first A-loader warp (multiple of 4: TMEM lane quarters)
-constexpr int kTgThreads = (kTgFirstA + 4 * kTgNwg) * 32;
+constexpr int kTgThreads = (kTgFirstA + 4 * kTgNwg + 4) * 32;   // 20 warps: + table group 1 (streamed table) / register donors
 constexpr int kTgMaxSlots = 64;
 constexpr int kTgMaxBuf = 8;
 constexpr uint32_t kTgSmemBudget = 200 * 1024;
@@ -85,6 +87,7 @@ __global__ void __launch_bounds__(kTgThreads, 1) tabgemm_tc(const TgArgs a) {
 
     if (warp < 4) {
         // =========================================================================== epilogue
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 72;\n");
         const int L = warp * 32 + lane;
         uint32_t dcount = 0;
         for (int it = 0; it < my_items; ++it) {
@@ -146,6 +149,7 @@ __global__ void __launch_bounds__(kTgThreads, 1) tabgemm_tc(const TgArgs a) {
         }
     } else if (warp == 4) {
         // =========================================================================== MMA issuer
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 72;\n");
         const uint32_t sbase = smem_u32(smem);
         const uint32_t idesc = make_idesc(128, a.NT);
         uint32_t qa = 0, qs = 0, dcount = 0;
@@ -197,14 +201,15 @@ __global__ void __launch_bounds__(kTgThreads, 1) tabgemm_tc(const TgArgs a) {
             }
             if (a.reuse) qa += (uint32_t)a.nchunks;
         }
-    } else if (warp < kTgFirstA || (!a.resident && warp >= kTgFirstA + 4)) {
+    } else if (warp < kTgFirstA || warp >= kTgFirstA + 4 * kTgNwg) {
         // =========================================================================== table loaders
         // resident table (ydft): warps 5-7 fill every slab once.  Streamed table (xdft / xsyn): the table is
         // what bounds the kernel, so the second A-loader warpgroup joins in -- group 0 (warps 5-7) takes the
         // even slabs, group 1 (warps 12-15) the odd ones, two slabs are in flight at any time.
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 72;\n");
         const int grp = warp < kTgFirstA ? 0 : 1;
         const int gthreads = grp == 0 ? kTgTabWarps * 32 : 128;
-        const int tt = grp == 0 ? (int)threadIdx.x - 5 * 32 : (int)threadIdx.x - (kTgFirstA + 4) * 32;
+        const int tt = grp == 0 ? (int)threadIdx.x - 5 * 32 : (int)threadIdx.x - (kTgFirstA + 4 * kTgNwg) * 32;
         auto fill = [&](int nt, int ch, uint8_t* dst) {
             uint8_t* hi = dst;
             uint8_t* lo = dst + (size_t)a.NT * 128;
@@ -240,7 +245,7 @@ __global__ void __launch_bounds__(kTgThreads, 1) tabgemm_tc(const TgArgs a) {
             __syncwarp();
         };
         if (a.resident) {
-            for (int nt = 0; nt < a.ntiles; ++nt)
+            for (int nt = 0; nt < (grp == 0 ? a.ntiles : 0); ++nt)
                 for (int ch = 0; ch < a.nchunks; ++ch) {
                     const int slot = nt * a.nchunks + ch;
                     fill(nt, ch, smem + (size_t)slot * slot_bytes);
@@ -260,8 +265,8 @@ __global__ void __launch_bounds__(kTgThreads, 1) tabgemm_tc(const TgArgs a) {
         }
     } else {
         // =========================================================================== A loaders
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 128;\n");
         const int wg = (warp - kTgFirstA) >> 2;
-        const uint32_t nwg = a.resident ? kTgNwg : 1;
         const int q4 = warp & 3;                                  // TMEM lane quarter this warp may access
         const int L = q4 * 32 + lane;
         const uint32_t lane_base = tmem_base + ((uint32_t)(q4 * 32) << 16);
@@ -321,13 +326,22 @@ __global__ void __launch_bounds__(kTgThreads, 1) tabgemm_tc(const TgArgs a) {
         // (2 warpgroups x 128 threads x 256 B = 64 KB in flight per SM), then both chunks are converted.
         // (Prefetching across loop iterations instead makes the consumer wait on the scoreboard that also
         // tracks the younger loads, which serialises everything -- measured 1.6x slower.)
+        // With a streamed table TMEM only has room for two A buffers (three accumulators): each warpgroup
+        // then takes single chunks, alternating, so one warpgroup's loads fly while the other converts.
         float va[32], vb[32];
-        for (uint32_t q = 2u * (uint32_t)wg; q < total; q += 2u * nwg) {
-            load(va, q);
-            const bool two = q + 1 < total;
-            if (two) load(vb, q + 1);
-            process(va, q);
-            if (two) process(vb, q + 1);
+        if (a.resident) {
+            for (uint32_t q = 2u * (uint32_t)wg; q < total; q += 2u * kTgNwg) {
+                load(va, q);
+                const bool two = q + 1 < total;
+                if (two) load(vb, q + 1);
+                process(va, q);
+                if (two) process(vb, q + 1);
+            }
+        } else {
+            for (uint32_t q = (uint32_t)wg; q < total; q += kTgNwg) {
+                load(va, q);
+                process(va, q);
+            }
         }
     }
 
@@ -352,7 +366,7 @@ static bool tg_configure(TgArgs& a) {
             if (NT > 128) continue;
             for (int dbl = 1; dbl >= 0; --dbl) {
                 const bool will_stream = (uint64_t)a.nchunks * ntiles * NT * 256u > kTgSmemBudget || a.nchunks * ntiles > kTgMaxSlots;
-                const int nwg_a = will_stream ? 1 : kTgNwg;        // the second A warpgroup streams table slabs instead
+                const int nwg_a = will_stream ? 1 : kTgNwg;        // buffers needed: 2 per warpgroup (pairs), or 1 each when streaming
                 // long contractions split the main chain over two accumulators when TMEM allows (truncation bias)
                 int nmain = (a.nchunks >= 8 && 3 * NT * (dbl ? 2 : 1) + 64 * 2 * nwg_a <= 512) ? 2 : 1;
                 if (dbl && nmain == 1 && a.nchunks >= 8 && 3 * NT + 64 * 2 * nwg_a <= 512) continue;   // accuracy first: single-buffered D with two chains
