@@ -94,6 +94,9 @@ class GraphedTrainStep:
         if not getattr(optimizer, "capturable", False):
             raise ValueError("GraphedTrainStep needs Adam(capturable=True): the step count must live on the device")
         self.x, self.y = x.clone(), y.clone()
+        # the capture stream differs from the stream the AccumulateGrad nodes were created on: expected here
+        if hasattr(torch.autograd.graph, "set_warn_on_accumulate_grad_stream_mismatch"):
+            torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):                          # allocator / workspace / Adam-state warm-up

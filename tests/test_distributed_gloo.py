@@ -1,0 +1,98 @@
+"""The data-parallel host logic (fnm_b200/parallel.py) on CPU with world_size 2 over gloo: batch sharding, the
+flat gradient buffer and its ONE SUM all-reduce, parameter broadcast.  The kernels need a GPU, so the model here
+is a small torch stand-in with the same ingredients (real + complex64 parameters, a loss that SUMS over the
+batch); what is checked is that the two-rank step reproduces the single-process global-batch gradients exactly
+as the reference's summed loss requires."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import fnm_b200
+from fnm_b200.parallel import FlatGradients, broadcast_parameters, rel_l2_sum, shard_batch
+
+
+class Toy(torch.nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.lin = torch.nn.Linear(6, 5)
+        self.w = torch.nn.Parameter(torch.rand(5, 5, 3, dtype=torch.cfloat) / 5)      # a complex "spectral" weight
+
+    def forward(self, x):                                   # x: (B, 6, 8)
+        h = self.lin(x.transpose(1, 2)).transpose(1, 2)     # (B, 5, 8)
+        hf = torch.fft.rfft(h)[..., :3]
+        y = torch.fft.irfft(torch.einsum("bix,iox->box", hf, self.w), n=8)
+        return torch.tanh(h) + y
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, x, y, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.manual_seed(100 + rank)                       # ranks start from DIFFERENT weights ...
+        model = Toy()
+        broadcast_parameters(model)                         # ... and must end up with rank 0's
+        grads = FlatGradients(model.parameters())
+        grads.zero_()
+        loss = rel_l2_sum(model(shard_batch(x, rank, world)), shard_batch(y, rank, world))
+        loss.backward()
+        handle = grads.all_reduce()
+        assert handle is None or handle.wait() is not False
+        if rank == 0:
+            out.put({"flat": grads.flat.clone(), "params": [p.detach().clone() for p in model.parameters()],
+                     "views_alias_flat": all(p.grad.data_ptr() >= grads.flat.data_ptr() for p in model.parameters())})
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_two_rank_sum_allreduce_equals_global_batch_gradient():
+    world = 2
+    torch.manual_seed(7)
+    x, y = torch.randn(6, 6, 8), torch.randn(6, 5, 8)
+    ctx = mp.get_context("spawn")
+    out = ctx.SimpleQueue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, x, y, out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = out.get()
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    # single-process reference: rank 0's weights (seed 100), the WHOLE batch, summed loss
+    torch.manual_seed(100)
+    model = Toy()
+    for p, q in zip(model.parameters(), res["params"]):
+        assert torch.equal(p.detach(), q)                   # broadcast_parameters delivered rank 0's weights
+    grads = FlatGradients(model.parameters())
+    grads.zero_()
+    rel_l2_sum(model(x), y).backward()
+    assert res["views_alias_flat"]
+    assert torch.allclose(res["flat"], grads.flat, rtol=1e-5, atol=1e-7)
+
+
+def test_shard_batch_and_flat_layout():
+    x = torch.arange(24.0).reshape(8, 3)
+    assert torch.equal(shard_batch(x, 1, 4), x[2:4])
+    with pytest.raises(ValueError):
+        shard_batch(x, 0, 3)
+    m = Toy()
+    g = FlatGradients(m.parameters())
+    n = sum(p.numel() * (2 if p.is_complex() else 1) for p in m.parameters())
+    assert g.flat.numel() >= n and all(off % 64 == 0 for off, _ in g.offsets)
+    g.flat.fill_(1.0)
+    assert all(torch.all(torch.view_as_real(p.grad) == 1) if p.is_complex() else torch.all(p.grad == 1)
+               for p in m.parameters())
+    g.zero_()
+    assert float(g.flat.abs().sum()) == 0.0
+    assert fnm_b200.parallel.GraphedTrainStep is not None
