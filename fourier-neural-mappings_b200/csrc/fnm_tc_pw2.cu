@@ -32,7 +32,8 @@ constexpr uint32_t kPwSmemBudget = 226 * 1024;
 struct PwArgs2 {
     const float* wc; const float* bias; const float* mul; float* out; float* out_act;
     long long rows;
-    int S2, LY, CI, CO, wc_is_kn, single_pass;
+    int S2, LY, CI, CO, wc_is_kn, single_pass;       // FOLDED extents (see pw2_fold): what the kernel tiles over
+    int CIo, COo, LYo;                               // the caller's channel / mode counts (== folded ones when fold = 1)
     int NT, tiles_per_row, seg_tiles, nseg, units;
     int K1slabs, K2slabs, LYp, stages, nlo, nz, debug;
     uint32_t stage_bytes, x_bytes, z_bytes;
@@ -131,7 +132,7 @@ __device__ __forceinline__ void pw2_epilogue(const PwArgs2& a, int warp, int lan
     const int half = (warp - 10) >> 2;
     const int hc = a.NT / 2;                                       // columns per half: 16, 24 or 32
     const bool o_ok = o < a.CO;
-    const float bias = (o_ok && a.bias) ? __ldg(a.bias + o) : 0.f;
+    const float bias = (o_ok && a.bias) ? __ldg(a.bias + o % a.COo) : 0.f;
     const uint32_t lane_base = tmem_base + ((uint32_t)(q4 * 32) << 16) + kD0;
     uint32_t t = 0;
     for (int u = 0; u < my_units; ++u) {
@@ -232,7 +233,10 @@ pw2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUt
             for (int j = 0; j < 16; ++j) {
                 const int k = k0 + j;
                 v[j] = 0.f;
-                if (o < a.CO && k < a.CI) v[j] = a.wc_is_kn ? __ldg(a.wc + (size_t)k * a.CO + o) : __ldg(a.wc + (size_t)o * a.CI + k);
+                // folded problem: block-diagonal weights, lane = (sub-position, out channel), k = (sub-position, in channel)
+                const int ro = o / a.COo, oo = o - ro * a.COo, rk = k / a.CIo, ii = k - rk * a.CIo;
+                if (o < a.CO && k < a.CI && ro == rk)
+                    v[j] = a.wc_is_kn ? __ldg(a.wc + (size_t)ii * a.COo + oo) : __ldg(a.wc + (size_t)oo * a.CIo + ii);
             }
             split_to_tmem16(lane_base + kA1Hi + k0, lane_base + kA1Lo + k0, v, !a.single_pass);
         }
@@ -262,7 +266,7 @@ pw2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUt
                     const uint32_t zb = (uint32_t)u % (uint32_t)a.nz, zpar = ((uint32_t)u / (uint32_t)a.nz) & 1;
                     mbar_wait(&z_empty[zb], zpar ^ 1);
                     mbar_expect_tx(&z_full[zb], a.z_bytes);
-                    tma_load_2d(&mapZ, &z_full[zb], reinterpret_cast<uint8_t*>(zs) + (size_t)zb * a.z_bytes, 0, row * a.LY);
+                    tma_load_2d(&mapZ, &z_full[zb], reinterpret_cast<uint8_t*>(zs) + (size_t)zb * a.z_bytes, 0, row * a.LYo);
                 }
                 for (int tile = t0; tile < t1; ++tile, ++t) {
                     const uint32_t s = t % (uint32_t)a.stages;
@@ -341,6 +345,7 @@ pw2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUt
         const int q4 = warp & 3, c = q4 * 32 + lane;
         const uint32_t lane_base = tmem_base + ((uint32_t)(q4 * 32) << 16);
         const bool c_ok = c < a.CO;
+        const int zr = c / a.COo, zo = c - zr * a.COo;                  // folded: lane = (sub-position, channel)
         for (int u = 0; u < (has_z ? my_units : 0); ++u) {
             const uint32_t ub = (uint32_t)u % na2, upar = ((uint32_t)u / na2) & 1;
             const uint32_t a2hi = kA2Hi + (na2 == 2 ? 64u * ub : 0u), a2lo = a2hi + (na2 == 2 ? 32u : 64u);
@@ -352,7 +357,10 @@ pw2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUt
             for (int l0 = 0; l0 < a.LYp; l0 += 16) {
                 float v[16];
 #pragma unroll
-                for (int j = 0; j < 16; ++j) v[j] = (c_ok && l0 + j < a.LY) ? zsb[(l0 + j) * a.CO + c] : 0.f;
+                for (int j = 0; j < 16; ++j) {
+                    const int kk = l0 + j, kr = kk / a.LYo, ll = kk - kr * a.LYo;   // block-diagonal Z^T when folded
+                    v[j] = (c_ok && kk < a.LY && kr == zr) ? zsb[ll * a.COo + zo] : 0.f;
+                }
                 split_to_tmem16(lane_base + a2hi + l0, lane_base + a2lo + l0, v, !a.single_pass);
             }
             tmem_st_wait();
@@ -448,7 +456,26 @@ static bool make_map(CUtensorMap* m, const float* ptr, int rank, const cuuint64_
     return r == CUDA_SUCCESS;
 }
 
+// Position folding for narrow layers: F consecutive positions of a C-channel row are ONE position of an
+// (F*C)-channel row (same memory), the pointwise weights / Z^T become block-diagonal, and all 128 TMEM lanes,
+// the full 128-byte operand rows and F-times fewer tiles are used.  Needs F | S2, no padding of the mode axis.
+static int pw2_fold(int S2, int LY, int CI, int CO) {
+    if ((CI != 0 && CI != CO) || CO % 4 != 0) return 1;       // (the un-folded checks reject what TMA cannot address)
+    for (int F = 4; F >= 2; F >>= 1) {
+        if (CO * F > 128 || S2 % F != 0 || S2 / F < 8) continue;
+        if (LY != 0 && (LY % 8 != 0 || LY * F > 64)) continue;
+        return F;
+    }
+    return 1;
+}
+
 static bool pw2_configure(PwArgs2& a, int64_t rows, int S2, int LY, int CI, int CO) {
+    a.CIo = CI > 0 ? CI : 1; a.COo = CO; a.LYo = LY > 0 ? LY : 1;
+    {
+        const char* e = getenv("FNM_PW2_NOFOLD");
+        const int F = (e && e[0] == '1') ? 1 : pw2_fold(S2, LY, CI, CO);
+        S2 /= F; LY *= F; CI *= F; CO *= F;
+    }
     if (rows < 1 || rows > (1LL << 28) || S2 < 1 || LY < 0 || LY > 64 || LY % 4 != 0) return false;
     if (LY == 0 && CI == 0) return false;
     if (CO < 4 || CO > 128 || CO % 4 != 0) return false;
@@ -457,7 +484,7 @@ static bool pw2_configure(PwArgs2& a, int64_t rows, int S2, int LY, int CI, int 
     a.LYp = (LY + 7) / 8 * 8;
     a.K1slabs = (CI + 31) / 32;
     a.K2slabs = (a.LYp + 31) / 32;
-    a.z_bytes = (uint32_t)LY * CO * 4u;
+    a.z_bytes = (uint32_t)a.LYo * a.COo * 4u * (LY > 0 ? 1u : 0u);
     int best = 0, best_cost = 1 << 30;
     for (int nt = 64; nt >= 32; nt -= 16) {                    // padded positions + a per-tile overhead worth ~32 positions
         const int tiles = (S2 + nt - 1) / nt;                  // (measured at config 5: 5 x 64 beats 6 x 48); ties -> wider tile
@@ -516,20 +543,20 @@ int tc_pw2(const float* x, const float* wc, int wc_is_kn, const float* bias, con
     { const char* e = getenv("FNM_PW2_DEBUG"); a.debug = e ? atoi(e) : 0; }
     CUtensorMap mx, mb, mz;
     if (LY > 0) {
-        const cuuint64_t dims[2] = {(cuuint64_t)LY, (cuuint64_t)S2};
-        const cuuint64_t str[1] = {(cuuint64_t)LY * 4};
+        const cuuint64_t dims[2] = {(cuuint64_t)a.LY, (cuuint64_t)a.S2};          // folded view of by[S2][LY]
+        const cuuint64_t str[1] = {(cuuint64_t)a.LY * 4};
         const cuuint32_t box[2] = {32, (cuuint32_t)a.NT};
         if (!make_map(&mb, by, 2, dims, str, box, true)) return fail(FNM_ECUDA, "pointwise_ysyn: tensor map (by) failed");
     }
     if (LY > 0) {
-        const cuuint64_t dims[2] = {(cuuint64_t)N, (cuuint64_t)rows * LY};
-        const cuuint64_t str[1] = {(cuuint64_t)N * 4};
-        const cuuint32_t box[2] = {(cuuint32_t)N, (cuuint32_t)LY};
+        const cuuint64_t dims[2] = {(cuuint64_t)a.COo, (cuuint64_t)rows * a.LYo};  // Z[row][l][o]: never folded
+        const cuuint64_t str[1] = {(cuuint64_t)a.COo * 4};
+        const cuuint32_t box[2] = {(cuuint32_t)a.COo, (cuuint32_t)a.LYo};
         if (!make_map(&mz, Z, 2, dims, str, box, false)) return fail(FNM_ECUDA, "pointwise_ysyn: tensor map (Z) failed");
     }
     if (CI > 0) {
-        const cuuint64_t dims[3] = {(cuuint64_t)CI, (cuuint64_t)S2, (cuuint64_t)rows};
-        const cuuint64_t str[2] = {(cuuint64_t)CI * 4, (cuuint64_t)S2 * CI * 4};
+        const cuuint64_t dims[3] = {(cuuint64_t)a.CI, (cuuint64_t)a.S2, (cuuint64_t)rows};   // folded view of x[rows][S2][CI]
+        const cuuint64_t str[2] = {(cuuint64_t)a.CI * 4, (cuuint64_t)a.S2 * a.CI * 4};
         const cuuint32_t box[3] = {32, (cuuint32_t)a.NT, 1};
         if (!make_map(&mx, x, 3, dims, str, box, true)) return fail(FNM_ECUDA, "pointwise_ysyn: tensor map (x) failed");
     } else {

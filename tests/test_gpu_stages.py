@@ -31,9 +31,12 @@ def _gelu_grad64(z):
     return 0.5 * (1 + torch.erf(z / 2 ** 0.5)) + z * torch.exp(-0.5 * z * z) / (2 * torch.pi) ** 0.5
 
 
+LY_ACTIVE = [True]
+
+
 def _pointwise_ysyn_ref(x, act, wc, wc_is_kn, bias, Z, by, mul):
     """float64 statement of fnm_pointwise_ysyn (include/fnm_b200.h)."""
-    out = torch.einsum("yl,rln->ryn", by.double(), Z.double())
+    out = torch.einsum("yl,rln->ryn", by.double(), Z.double()) if LY_ACTIVE[0] else 0
     if x is not None:
         xa = _gelu64(x.double()) if act else x.double()
         wk = wc.double() if wc_is_kn else wc.double().t()        # Wk[k][n]
@@ -64,6 +67,9 @@ CASES = [
     dict(rows=33, S2=144, LY=32, K=64, N=64, act=0, kn=1, bias=0, mul=1),      # config 4 trunk backward
     dict(rows=50, S2=57, LY=24, K=32, N=32, act=0, kn=0, bias=1, mul=1),       # config 3 trunk: odd row length
     dict(rows=21, S2=100, LY=20, K=48, N=48, act=0, kn=0, bias=1, mul=0),      # channel count that is no multiple of 32
+    dict(rows=64, S2=72, LY=24, K=32, N=32, act=0, kn=1, bias=0, mul=1),       # config 1 backward: two positions folded per lane row
+    dict(rows=12, S2=64, LY=16, K=32, N=32, act=0, kn=0, bias=1, mul=0),       # four positions folded (C = 32, 4 x 16 mode columns)
+    dict(rows=12, S2=64, LY=0, K=32, N=32, act=0, kn=0, bias=1, mul=0),        # pointwise term only, folded
     dict(rows=9, S2=40, LY=10, K=20, N=20, act=1, kn=0, bias=1, mul=0),        # SIMT-only shape (C = 20)
     dict(rows=5, S2=96, LY=16, K=96, N=96, act=1, kn=0, bias=1, mul=1),        # 64 < C < 128
 ]
@@ -77,8 +83,8 @@ def test_pointwise_ysyn(case, mode):
     x = torch.randn(rows, S2, K, device=DEV) if K else None
     wc = (torch.randn(K, N, device=DEV) if case["kn"] else torch.randn(N, K, device=DEV)) / max(K, 1) ** 0.5 if K else None
     bias = torch.randn(N, device=DEV) if case["bias"] else None
-    Z = torch.randn(rows, LY, N, device=DEV)
-    by = torch.randn(S2, LY, device=DEV) / LY ** 0.5
+    Z = torch.randn(rows, max(LY, 1), N, device=DEV)
+    by = torch.randn(S2, max(LY, 1), device=DEV) / max(LY, 1) ** 0.5
     mul = torch.randn(rows, S2, N, device=DEV) if case["mul"] else None
     out = torch.full((rows, S2, N), float("nan"), device=DEV)
     out_act = torch.full((rows, S2, N), float("nan"), device=DEV) if not case["mul"] else None
@@ -86,7 +92,9 @@ def test_pointwise_ysyn(case, mode):
                                    _p(out_act), rows, S2, LY, K, N, 0 if mode == "fp32" else 1, _stream()),
           "fnm_pointwise_ysyn")
     torch.cuda.synchronize()
+    LY_ACTIVE[0] = LY > 0
     ref = _pointwise_ysyn_ref(x, case["act"], wc, case["kn"], bias, Z, by, mul)
+    LY_ACTIVE[0] = True
     assert torch.isfinite(out).all()
     err = rel_l2(out, ref)
     tol = TOL_FP32 if mode == "fp32" else TOL_TF32
