@@ -252,6 +252,83 @@ __global__ void head_bwd_reduce(const float* __restrict__ partial, int nblocks, 
     else if (db2) db2[i - D * H] = s;
 }
 
+
+// ---- F2V local branch: the reference applies mlpfunc0 pointwise and integrates with
+// two torch.trapz calls (func_to_vec2d.py:100-104).  fc2 is linear, so trapz(fc2(GELU(h1))) =
+// fc2(sum_pos wt[pos] GELU(h1[pos])): only the weighted GELU sum S[b][h] touches the field.
+//   S[b][h] = sum_{x,y} wx[x] wy[y] GELU(h1[b][x][y][h])          g_h1 = gS[b][h] wx[x] wy[y] GELU'(h1)
+struct WsumArgs {
+    const float* h1; const float* wx; const float* wy; const float* gS;
+    float* partial; float* g_h1;
+    int B, P1, P2, H, nchunk;
+};
+
+__global__ void wsum_fwd_kernel(const WsumArgs a) {
+    extern __shared__ float red[];                        // [warps][H]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int H4 = a.H / 4, b = blockIdx.y, chunk = blockIdx.x;
+    const int npos = a.P1 * a.P2;
+    const int per = (npos + a.nchunk - 1) / a.nchunk;
+    const int p_end = min(npos, (chunk + 1) * per);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float* base = a.h1 + (size_t)b * npos * a.H;
+    if (lane < H4) {
+        for (int p0 = chunk * per + warp * 4; p0 < p_end; p0 += nw * 4) {
+            float4 v[4];
+            float w[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int p = p0 + u;
+                const bool ok = p < p_end;
+                v[u] = ok ? __ldg(reinterpret_cast<const float4*>(base + (size_t)p * a.H) + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+                w[u] = ok ? __ldg(a.wx + p / a.P2) * __ldg(a.wy + p % a.P2) : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                acc.x = fmaf(w[u], gelu_erf(v[u].x), acc.x); acc.y = fmaf(w[u], gelu_erf(v[u].y), acc.y);
+                acc.z = fmaf(w[u], gelu_erf(v[u].z), acc.z); acc.w = fmaf(w[u], gelu_erf(v[u].w), acc.w);
+            }
+        }
+        *reinterpret_cast<float4*>(red + (size_t)warp * a.H + lane * 4) = acc;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < a.H; i += blockDim.x) {
+        float s = 0.f;
+        for (int k = 0; k < nw; ++k) s += red[(size_t)k * a.H + i];
+        a.partial[((size_t)b * a.nchunk + chunk) * a.H + i] = s;
+    }
+}
+
+__global__ void wsum_reduce_kernel(const float* __restrict__ partial, int nchunk, int BH, int H, float* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= BH) return;
+    const int b = i / H, h = i - b * H;
+    float s = 0.f;
+    for (int k = 0; k < nchunk; ++k) s += partial[((size_t)b * nchunk + k) * H + h];
+    out[i] = s;
+}
+
+__global__ void wsum_bwd_kernel(const WsumArgs a) {
+    const int H4 = a.H / 4;
+    const int npos = a.P1 * a.P2;
+    const int b = blockIdx.y;
+    const float* base = a.h1 + (size_t)b * npos * a.H;
+    float* gbase = a.g_h1 + (size_t)b * npos * a.H;
+    const int total = npos * H4;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int p = i / H4, h4 = i - p * H4;
+        const float w = __ldg(a.wx + p / a.P2) * __ldg(a.wy + p % a.P2);
+        const float4 v = __ldg(reinterpret_cast<const float4*>(base + (size_t)p * a.H) + h4);
+        const float4 g = __ldg(reinterpret_cast<const float4*>(a.gS + (size_t)b * a.H) + h4);
+        float4 o;
+        o.x = w * g.x * gelu_erf_grad(v.x); o.y = w * g.y * gelu_erf_grad(v.y);
+        o.z = w * g.z * gelu_erf_grad(v.z); o.w = w * g.w * gelu_erf_grad(v.w);
+        *(reinterpret_cast<float4*>(gbase + (size_t)p * a.H) + h4) = o;
+    }
+}
+
+constexpr int kWsumChunks = 64;
+
 constexpr int kEndBlocks = 148 * 4;
 
 static bool lift_ok(int Din, int C, int ngrid) { return Din >= 0 && Din + ngrid >= 1 && Din + ngrid <= kLiftMaxJ && C % 4 == 0 && C >= 4 && C <= 1024; }
@@ -359,6 +436,46 @@ int fnm_mlp_head_bwd(const float* h1, const float* g_out, const float* w2, float
         head_bwd_reduce<<<(D * H + D + 255) / 256, 256, 0, st>>>(a.partial, kEndBlocks, H, D, dw2, db2);
     }
     return check_launch("mlp_head_bwd_reduce");
+}
+
+size_t fnm_wsum_gelu_workspace_bytes(int B, int H) { return align_up((size_t)B * kWsumChunks * H * sizeof(float), 256); }
+
+int fnm_wsum_gelu_fwd(const float* h1, const float* wx, const float* wy, float* S, int B, int P1, int P2, int H,
+                      void* workspace, size_t workspace_bytes, fnm_stream_t stream) {
+    FNM_REQUIRE(h1 && wx && wy && S && workspace, "wsum_gelu_fwd: NULL pointer");
+    if (H % 4 != 0 || H < 4 || H > 128 || B < 1 || B > 65535) return fail(FNM_ENOTSUP, "wsum_gelu_fwd: unsupported widths");
+    if (workspace_bytes < fnm_wsum_gelu_workspace_bytes(B, H)) return fail(FNM_EWORKSPACE, "wsum_gelu_fwd: workspace too small");
+    WsumArgs a{};
+    a.h1 = h1; a.wx = wx; a.wy = wy; a.partial = static_cast<float*>(workspace);
+    a.B = B; a.P1 = P1; a.P2 = P2; a.H = H; a.nchunk = kWsumChunks;
+    cudaStream_t st = as_stream(stream);
+    {
+        LaunchScope ls("wsum_gelu_fwd", st);
+        wsum_fwd_kernel<<<dim3(kWsumChunks, B), 256, 8 * H * sizeof(float), st>>>(a);
+    }
+    FNM_TRY(check_launch("wsum_gelu_fwd"));
+    {
+        LaunchScope ls("wsum_gelu_reduce", st);
+        wsum_reduce_kernel<<<(B * H + 255) / 256, 256, 0, st>>>(a.partial, kWsumChunks, B * H, H, S);
+    }
+    return check_launch("wsum_gelu_reduce");
+}
+
+int fnm_wsum_gelu_bwd(const float* h1, const float* wx, const float* wy, const float* gS, float* g_h1, int B, int P1,
+                      int P2, int H, fnm_stream_t stream) {
+    FNM_REQUIRE(h1 && wx && wy && gS && g_h1, "wsum_gelu_bwd: NULL pointer");
+    if (H % 4 != 0 || H < 4 || B < 1 || B > 65535) return fail(FNM_ENOTSUP, "wsum_gelu_bwd: unsupported widths");
+    WsumArgs a{};
+    a.h1 = h1; a.wx = wx; a.wy = wy; a.gS = gS; a.g_h1 = g_h1; a.B = B; a.P1 = P1; a.P2 = P2; a.H = H;
+    const long long per_b = (long long)P1 * P2 * (H / 4);
+    int gx = (int)((per_b + 255) / 256);
+    const int cap = (kEndBlocks * 8 + B - 1) / B;
+    if (gx > cap) gx = cap < 1 ? 1 : cap;
+    {
+        LaunchScope ls("wsum_gelu_bwd", as_stream(stream));
+        wsum_bwd_kernel<<<dim3(gx, B), 256, 0, as_stream(stream)>>>(a);
+    }
+    return check_launch("wsum_gelu_bwd");
 }
 
 }  // extern "C"

@@ -146,7 +146,34 @@ def functional_end(state, lfunc0, mlpfunc0, head, one_d):
     tables = lfunc0.tables(P2) if one_d else lfunc0.tables(P1, P2)
     xv = state.value()                                        # differentiable GELU(z) for the pointwise branch
     nonlocal_feats = ops.linear_functional(z, lfunc0.weights, tables, act_in=state.act, xact=state.x)
-    h = mlpfunc0(xv)                                          # (B, P1, P2, width_lfunc)
-    h = torch.trapz(h, dx=1.0 / P2, dim=2)
-    h = h.squeeze(1) if one_d else torch.trapz(h, dx=1.0 / P1, dim=1)
+    fc1, fc2 = mlpfunc0.fc1, mlpfunc0.fc2
+    if (getattr(mlpfunc0, "act_name", None) == "gelu" and _fused_ends_ok(xv, fc1.weight, fc2.weight)
+            and fc1.in_features % 4 == 0 and fc1.in_features <= 128 and fc1.out_features % 4 == 0
+            and fc1.out_features <= 128 and P2 >= 2 and (one_d or P1 >= 2)):
+        # local branch without the (B, P1, P2, width_lfunc) tensors: fc1 on the fused pointwise kernel, then the
+        # trapezoid-weighted GELU sum; fc2 is linear, so it commutes with the integration and acts on (B, H)
+        wy = _trapz_weights(P2, xv.device)
+        wx = _trapz_weights(P1, xv.device) if not one_d else torch.ones(1, device=xv.device)
+        S = ops.weighted_gelu_sum(ops.pointwise_conv(xv, fc1.weight, fc1.bias), wx, wy)
+        h = F.linear(S, fc2.weight)
+        if fc2.bias is not None:
+            h = h + fc2.bias * (((P2 - 1.0) / P2) * (1.0 if one_d else (P1 - 1.0) / P1))   # integral of the constant
+    else:
+        h = mlpfunc0(xv)                                      # (B, P1, P2, width_lfunc)
+        h = torch.trapz(h, dx=1.0 / P2, dim=2)
+        h = h.squeeze(1) if one_d else torch.trapz(h, dx=1.0 / P1, dim=1)
     return head(torch.cat((nonlocal_feats, h), dim=1))
+
+
+_TRAPZ = {}
+
+
+def _trapz_weights(P, device):
+    """torch.trapz(., dx=1/P) over P points as a weight vector: dx * (1/2, 1, ..., 1, 1/2)."""
+    key = (P, str(device))
+    if key not in _TRAPZ:
+        w = torch.full((P,), 1.0 / P, dtype=torch.float32)
+        w[0] *= 0.5
+        w[-1] *= 0.5
+        _TRAPZ[key] = w.to(device)
+    return _TRAPZ[key]

@@ -346,6 +346,37 @@ class MlpHeadFn(torch.autograd.Function):
         return g_h1, dw2, (db2 if ctx.has_bias else None)
 
 
+class WeightedGeluSumFn(torch.autograd.Function):
+    """S[b, h] = sum_{x,y} wx[x] wy[y] GELU(h1[b, x, y, h]): the field-sized part of mlpfunc0 + double trapz
+    (func_to_vec2d.py:100-104); fc2 is linear and is applied to S afterwards."""
+
+    @staticmethod
+    def forward(ctx, h1, wx, wy):
+        _need_cuda(h1, wx, wy)
+        h1, wx, wy = _f32c(h1), _f32c(wx), _f32c(wy)
+        B, P1, P2, H = h1.shape
+        S = torch.empty((B, H), dtype=torch.float32, device=h1.device)
+        L = lib()
+        ws = _workspace(h1.device, L.fnm_wsum_gelu_workspace_bytes(B, H))
+        check(L.fnm_wsum_gelu_fwd(_ptr(h1), _ptr(wx), _ptr(wy), _ptr(S), B, P1, P2, H, _ptr(ws), ws.numel(), _stream()),
+              "fnm_wsum_gelu_fwd")
+        ctx.save_for_backward(h1, wx, wy)
+        return S
+
+    @staticmethod
+    def backward(ctx, gS):
+        h1, wx, wy = ctx.saved_tensors
+        B, P1, P2, H = h1.shape
+        g = torch.empty_like(h1)
+        check(lib().fnm_wsum_gelu_bwd(_ptr(h1), _ptr(wx), _ptr(wy), _ptr(_f32c(gS)), _ptr(g), B, P1, P2, H, _stream()),
+              "fnm_wsum_gelu_bwd")
+        return g, None, None
+
+
+def weighted_gelu_sum(h1, wx, wy):
+    return WeightedGeluSumFn.apply(h1, wx, wy)
+
+
 def lift(x, w, b, P1, P2, ngrid):
     return LiftFn.apply(x, w, b, P1, P2, ngrid)
 

@@ -213,6 +213,16 @@ size_t fnm_mlp_head_bwd_workspace_bytes(int H, int D);
 int fnm_mlp_head_bwd(const float* h1, const float* g_out, const float* w2, float* g_h1, float* dw2, float* db2,
                      int64_t npos, int H, int D, void* workspace, size_t workspace_bytes, fnm_stream_t stream);
 
+/* ---- F2V local branch (func_to_vec2d.py:100-104, vec_to_vec2d.py:107-111): mlpfunc0 then two
+ *      torch.trapz.  fc2 is linear, so only S[b][h] = sum_{x,y} wx[x] wy[y] GELU(h1[b][x][y][h]) touches the field
+ *      (h1 = fc1 output, fnm_pointwise_ysyn with LY = 0); wx / wy hold the trapezoid weights dx*(1/2, 1, ..., 1, 1/2).
+ *      backward: g_h1 = gS[b][h] wx[x] wy[y] GELU'(h1).                                                           */
+size_t fnm_wsum_gelu_workspace_bytes(int B, int H);
+int fnm_wsum_gelu_fwd(const float* h1, const float* wx, const float* wy, float* S, int B, int P1, int P2, int H,
+                      void* workspace, size_t workspace_bytes, fnm_stream_t stream);
+int fnm_wsum_gelu_bwd(const float* h1, const float* wx, const float* wy, const float* gS, float* g_h1, int B, int P1,
+                      int P2, int H, fnm_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

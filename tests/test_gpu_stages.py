@@ -285,6 +285,23 @@ def test_projection_kernels(shape, Ci, H, D):
         assert rel_l2(a, b.grad) < TOL_FP32
 
 
+@pytest.mark.parametrize("B,P1,P2,H", [(3, 20, 24, 128), (2, 1, 50, 64), (5, 9, 11, 32)])
+def test_weighted_gelu_sum(B, P1, P2, H):
+    """S[b,h] = sum wx[x] wy[y] GELU(h1) and its backward against float64 torch (the field-sized part of
+    mlpfunc0 + double trapz)."""
+    torch.manual_seed(8)
+    h1 = torch.randn(B, P1, P2, H, device=DEV, requires_grad=True)
+    wx, wy = torch.rand(P1, device=DEV), torch.rand(P2, device=DEV)
+    S = fnm_b200.ops.weighted_gelu_sum(h1, wx, wy)
+    g = torch.randn_like(S)
+    S.backward(g)
+    h64 = h1.detach().double().requires_grad_(True)
+    ref = torch.einsum("x,y,bxyh->bh", wx.double(), wy.double(), _gelu64(h64))
+    ref.backward(g.double())
+    assert rel_l2(S, ref) < 1e-6
+    assert rel_l2(h1.grad, h64.grad) < 1e-6
+
+
 def test_gelu_kernels():
     z = torch.randn(100003, device=DEV) * 3
     g = torch.randn_like(z)
