@@ -32,8 +32,8 @@ constexpr uint32_t kPwSmemBudget = 226 * 1024;
 struct PwArgs2 {
     const float* wc; const float* bias; const float* mul; float* out; float* out_act;
     long long rows;
-    int S2, LY, CI, CO, wc_is_kn, single_pass;       // FOLDED extents (see pw2_fold): what the kernel tiles over
-    int CIo, COo, LYo;                               // the caller's channel / mode counts (== folded ones when fold = 1)
+    int S2, LY, CI, CO, wc_is_kn, single_pass;       // CI / CO: FOLDED channel extents F*CIo / F*COo (see pw2_fold)
+    int CIo, COo, F;                                 // the caller's channel counts; F grid rows share one lane set
     int NT, tiles_per_row, seg_tiles, nseg, units;
     int K1slabs, K2slabs, LYp, stages, nlo, nz, debug;
     uint32_t stage_bytes, x_bytes, z_bytes;
@@ -131,24 +131,26 @@ __device__ __forceinline__ void pw2_epilogue(const PwArgs2& a, int warp, int lan
     const int q4 = warp & 3, o = q4 * 32 + lane;
     const int half = (warp - 10) >> 2;
     const int hc = a.NT / 2;                                       // columns per half: 16, 24 or 32
-    const bool o_ok = o < a.CO;
-    const float bias = (o_ok && a.bias) ? __ldg(a.bias + o % a.COo) : 0.f;
+    const int fr = o / a.COo, oo = o - fr * a.COo;              // lane = (row within the group, out channel)
+    const float bias = (o < a.CO && a.bias) ? __ldg(a.bias + oo) : 0.f;
     const uint32_t lane_base = tmem_base + ((uint32_t)(q4 * 32) << 16) + kD0;
     uint32_t t = 0;
     for (int u = 0; u < my_units; ++u) {
         const int unit = (int)blockIdx.x + u * (int)gridDim.x;
-        const int row = unit / a.nseg, seg = unit - row * a.nseg;
+        const int rg = unit / a.nseg, seg = unit - rg * a.nseg;
         const int t0 = seg * a.seg_tiles, t1 = min(a.tiles_per_row, t0 + a.seg_tiles);
+        const long long row = (long long)rg * a.F + fr;
+        const bool o_ok = o < a.CO && row < a.rows;
         for (int tile = t0; tile < t1; ++tile, ++t) {
             const uint32_t acc = t & 1;
             const int yb = tile * a.NT + half * hc;                 // first position of this warp's columns
             const int nv = max(0, min(hc, a.S2 - yb));              // valid positions
-            const size_t base = ((size_t)row * a.S2 + yb) * a.CO + o;
+            const size_t base = ((size_t)row * a.S2 + yb) * a.COo + oo;
             float m[32];
             if (HAS_MUL) {                                        // issued before the accumulator wait: overlaps the MMAs
                 const float* mp = a.mul + base;
 #pragma unroll
-                for (int j = 0; j < 32; ++j) m[j] = (o_ok && j < nv) ? __ldg(mp + (size_t)j * a.CO) : 0.f;
+                for (int j = 0; j < 32; ++j) m[j] = (o_ok && j < nv) ? __ldg(mp + (size_t)j * a.COo) : 0.f;
             }
             mbar_wait(&acc_full[acc], (t >> 1) & 1);
             tc_fence_after();
@@ -160,15 +162,15 @@ __device__ __forceinline__ void pw2_epilogue(const PwArgs2& a, int warp, int lan
                     tmem_ld16(taddr + g * 16, r);
                     tmem_ld_wait();
                     if (o_ok) {
-                        float* op = a.out + base + (size_t)(g * 16) * a.CO;
-                        float* ap = HAS_ACT ? a.out_act + base + (size_t)(g * 16) * a.CO : nullptr;
+                        float* op = a.out + base + (size_t)(g * 16) * a.COo;
+                        float* ap = HAS_ACT ? a.out_act + base + (size_t)(g * 16) * a.COo : nullptr;
 #pragma unroll
                         for (int j = 0; j < 16; ++j) {
                             if (g * 16 + j < nv) {
                                 float v = __uint_as_float(r[j]) + bias;
                                 if (HAS_MUL) v *= gelu_grad_fast(m[g * 16 + j]);
-                                op[(size_t)j * a.CO] = v;
-                                if (HAS_ACT) ap[(size_t)j * a.CO] = gelu_fast(v);
+                                op[(size_t)j * a.COo] = v;
+                                if (HAS_ACT) ap[(size_t)j * a.COo] = gelu_fast(v);
                             }
                         }
                     }
@@ -266,7 +268,7 @@ pw2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUt
                     const uint32_t zb = (uint32_t)u % (uint32_t)a.nz, zpar = ((uint32_t)u / (uint32_t)a.nz) & 1;
                     mbar_wait(&z_empty[zb], zpar ^ 1);
                     mbar_expect_tx(&z_full[zb], a.z_bytes);
-                    tma_load_2d(&mapZ, &z_full[zb], reinterpret_cast<uint8_t*>(zs) + (size_t)zb * a.z_bytes, 0, row * a.LYo);
+                    tma_load_2d(&mapZ, &z_full[zb], reinterpret_cast<uint8_t*>(zs) + (size_t)zb * a.z_bytes, 0, row * a.F * a.LY);
                 }
                 for (int tile = t0; tile < t1; ++tile, ++t) {
                     const uint32_t s = t % (uint32_t)a.stages;
@@ -274,8 +276,10 @@ pw2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUt
                     mbar_expect_tx(&full[s], a.stage_bytes);
                     uint8_t* st = smem + (size_t)s * a.stage_bytes;
                     const int y0 = tile * a.NT;
+                    // K-slab kb of the X tile: 32 channels of grid row (row group * F + kb / slabs per row)
+                    const int spr = a.F > 1 ? a.CIo / 32 : a.K1slabs;
                     for (int kb = 0; kb < a.K1slabs; ++kb)
-                        tma_load_3d(&mapX, &full[s], st + (size_t)kb * a.NT * 128, kb * 32, y0, row);
+                        tma_load_3d(&mapX, &full[s], st + (size_t)kb * a.NT * 128, (kb % spr) * 32, y0, row * a.F + kb / spr);
                     for (int kb = 0; kb < a.K2slabs; ++kb)
                         tma_load_2d(&mapBy, &full[s], st + a.x_bytes + (size_t)kb * a.NT * 128, kb * 32, y0);
                 }
@@ -345,7 +349,7 @@ pw2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUt
         const int q4 = warp & 3, c = q4 * 32 + lane;
         const uint32_t lane_base = tmem_base + ((uint32_t)(q4 * 32) << 16);
         const bool c_ok = c < a.CO;
-        const int zr = c / a.COo, zo = c - zr * a.COo;                  // folded: lane = (sub-position, channel)
+        const int zr = c / a.COo, zo = c - zr * a.COo;                  // lane = (row within the group, channel)
         for (int u = 0; u < (has_z ? my_units : 0); ++u) {
             const uint32_t ub = (uint32_t)u % na2, upar = ((uint32_t)u / na2) & 1;
             const uint32_t a2hi = kA2Hi + (na2 == 2 ? 64u * ub : 0u), a2lo = a2hi + (na2 == 2 ? 32u : 64u);
@@ -358,8 +362,8 @@ pw2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUt
                 float v[16];
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
-                    const int kk = l0 + j, kr = kk / a.LYo, ll = kk - kr * a.LYo;   // block-diagonal Z^T when folded
-                    v[j] = (c_ok && kk < a.LY && kr == zr) ? zsb[ll * a.COo + zo] : 0.f;
+                    const int kk = l0 + j;                                        // each row of the group brings its own Z tile
+                    v[j] = (c_ok && kk < a.LY) ? zsb[(zr * a.LY + kk) * a.COo + zo] : 0.f;
                 }
                 split_to_tmem16(lane_base + a2hi + l0, lane_base + a2lo + l0, v, !a.single_pass);
             }
@@ -456,35 +460,36 @@ static bool make_map(CUtensorMap* m, const float* ptr, int rank, const cuuint64_
     return r == CUDA_SUCCESS;
 }
 
-// Position folding for narrow layers: F consecutive positions of a C-channel row are ONE position of an
-// (F*C)-channel row (same memory), the pointwise weights / Z^T become block-diagonal, and all 128 TMEM lanes,
-// the full 128-byte operand rows and F-times fewer tiles are used.  Needs F | S2, no padding of the mode axis.
-static int pw2_fold(int S2, int LY, int CI, int CO) {
-    if ((CI != 0 && CI != CO) || CO % 4 != 0) return 1;       // (the un-folded checks reject what TMA cannot address)
-    for (int F = 4; F >= 2; F >>= 1) {
-        if (CO * F > 128 || S2 % F != 0 || S2 / F < 8) continue;
-        if (LY != 0 && (LY % 8 != 0 || LY * F > 64)) continue;
-        return F;
-    }
+// Row folding for narrow layers: F consecutive grid rows share one CTA pass.  TMEM lane = (row in group, out
+// channel), the K axis of the pointwise term is (row in group, in channel) with block-diagonal weights -- K-slab
+// kb of the X tile is simply TMA-loaded from grid row kb / (C/32) -- and every row of the group contributes its own
+// Z^T rows while the twiddle tile `by` is shared.  All 128 lanes, full MMA K and F times fewer tiles for C = 32 / 64,
+// for any row length and mode count.
+static int pw2_fold(int64_t rows, int CI, int CO) {
+    if ((CI != 0 && CI != CO) || CO % 32 != 0) return 1;
+    for (int F = 4; F >= 2; F >>= 1)
+        if (CO * F <= 128 && rows >= 2 * F) return F;
     return 1;
 }
 
 static bool pw2_configure(PwArgs2& a, int64_t rows, int S2, int LY, int CI, int CO) {
-    a.CIo = CI > 0 ? CI : 1; a.COo = CO; a.LYo = LY > 0 ? LY : 1;
-    {
-        const char* e = getenv("FNM_PW2_NOFOLD");
-        const int F = (e && e[0] == '1') ? 1 : pw2_fold(S2, LY, CI, CO);
-        S2 /= F; LY *= F; CI *= F; CO *= F;
-    }
+    // what TMA can address (16-byte strides) and what the TMEM map holds (128 lanes, 64 mode columns)
     if (rows < 1 || rows > (1LL << 28) || S2 < 1 || LY < 0 || LY > 64 || LY % 4 != 0) return false;
     if (LY == 0 && CI == 0) return false;
     if (CO < 4 || CO > 128 || CO % 4 != 0) return false;
     if (CI != 0 && (CI < 4 || CI > 128 || CI % 4 != 0)) return false;
+    a.CIo = CI > 0 ? CI : 1; a.COo = CO;
+    {
+        const char* e = getenv("FNM_PW2_NOFOLD");
+        a.F = (e && e[0] == '1') ? 1 : pw2_fold(rows, CI, CO);
+        CI *= a.F; CO *= a.F;
+    }
+    if (a.F > 1 && (uint64_t)a.F * LY * a.COo * 4u > 32768u) return false;
     a.rows = rows; a.S2 = S2; a.LY = LY; a.CI = CI; a.CO = CO;
     a.LYp = (LY + 7) / 8 * 8;
     a.K1slabs = (CI + 31) / 32;
     a.K2slabs = (a.LYp + 31) / 32;
-    a.z_bytes = (uint32_t)a.LYo * a.COo * 4u * (LY > 0 ? 1u : 0u);
+    a.z_bytes = (uint32_t)a.F * LY * a.COo * 4u;
     int best = 0, best_cost = 1 << 30;
     for (int nt = 64; nt >= 32; nt -= 16) {                    // padded positions + a per-tile overhead worth ~32 positions
         const int tiles = (S2 + nt - 1) / nt;                  // (measured at config 5: 5 x 64 beats 6 x 48); ties -> wider tile
@@ -510,11 +515,12 @@ static bool pw2_configure(PwArgs2& a, int64_t rows, int S2, int LY, int CI, int 
     // units: whole rows when there are enough of them, otherwise row segments (1-D problems have few rows)
     int nseg = 1;
     const int want = 2 * sm_count();
-    if (rows < want) nseg = (int)((want + rows - 1) / rows);
+    const int64_t grows = (rows + a.F - 1) / a.F;               // row groups
+    if (grows < want) nseg = (int)((want + grows - 1) / grows);
     if (nseg > a.tiles_per_row) nseg = a.tiles_per_row;
     a.seg_tiles = (a.tiles_per_row + nseg - 1) / nseg;
     a.nseg = (a.tiles_per_row + a.seg_tiles - 1) / a.seg_tiles;
-    const long long units = rows * a.nseg;
+    const long long units = grows * a.nseg;
     if (units > (1LL << 30)) return false;
     a.units = (int)units;
     return true;
@@ -543,20 +549,20 @@ int tc_pw2(const float* x, const float* wc, int wc_is_kn, const float* bias, con
     { const char* e = getenv("FNM_PW2_DEBUG"); a.debug = e ? atoi(e) : 0; }
     CUtensorMap mx, mb, mz;
     if (LY > 0) {
-        const cuuint64_t dims[2] = {(cuuint64_t)a.LY, (cuuint64_t)a.S2};          // folded view of by[S2][LY]
+        const cuuint64_t dims[2] = {(cuuint64_t)a.LY, (cuuint64_t)a.S2};
         const cuuint64_t str[1] = {(cuuint64_t)a.LY * 4};
         const cuuint32_t box[2] = {32, (cuuint32_t)a.NT};
         if (!make_map(&mb, by, 2, dims, str, box, true)) return fail(FNM_ECUDA, "pointwise_ysyn: tensor map (by) failed");
     }
     if (LY > 0) {
-        const cuuint64_t dims[2] = {(cuuint64_t)a.COo, (cuuint64_t)rows * a.LYo};  // Z[row][l][o]: never folded
+        const cuuint64_t dims[2] = {(cuuint64_t)a.COo, (cuuint64_t)rows * a.LY};   // Z[row][l][o]; one box = the F rows of a group
         const cuuint64_t str[1] = {(cuuint64_t)a.COo * 4};
-        const cuuint32_t box[2] = {(cuuint32_t)a.COo, (cuuint32_t)a.LYo};
+        const cuuint32_t box[2] = {(cuuint32_t)a.COo, (cuuint32_t)(a.F * a.LY)};
         if (!make_map(&mz, Z, 2, dims, str, box, false)) return fail(FNM_ECUDA, "pointwise_ysyn: tensor map (Z) failed");
     }
     if (CI > 0) {
-        const cuuint64_t dims[3] = {(cuuint64_t)a.CI, (cuuint64_t)a.S2, (cuuint64_t)rows};   // folded view of x[rows][S2][CI]
-        const cuuint64_t str[2] = {(cuuint64_t)a.CI * 4, (cuuint64_t)a.S2 * a.CI * 4};
+        const cuuint64_t dims[3] = {(cuuint64_t)a.CIo, (cuuint64_t)a.S2, (cuuint64_t)rows};
+        const cuuint64_t str[2] = {(cuuint64_t)a.CIo * 4, (cuuint64_t)a.S2 * a.CIo * 4};
         const cuuint32_t box[3] = {32, (cuuint32_t)a.NT, 1};
         if (!make_map(&mx, x, 3, dims, str, box, true)) return fail(FNM_ECUDA, "pointwise_ysyn: tensor map (x) failed");
     } else {
