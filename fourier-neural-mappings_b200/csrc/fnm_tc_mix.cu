@@ -302,11 +302,15 @@ __global__ void __launch_bounds__(kMxThreads, 1) mixgemm_tc(const MxArgs a) {
     if (warp == 4) tmem_dealloc(tmem_base, 512);
 }
 
-// out[c][b][a] = in[a][b][c] for 8-byte (complex64) elements; grid (ceil(C/32), ceil(A/32), B)
-__global__ void permute_c64_cba(const float2* __restrict__ in, float2* __restrict__ out, int A, int B, int C,
-                                long long out_c_stride) {
+// out[c][b][a] = in[a][b][c] for 8-byte (complex64) elements; grid (ceil(C/32), ceil(A/32), B * ntens): the
+// two weight tensors of a SpectralConv2d (weights1 | weights2) are permuted by ONE launch (blockIdx.z / B picks it)
+__global__ void permute_c64_cba(const float2* __restrict__ in0, const float2* __restrict__ in1, float2* __restrict__ out0,
+                                float2* __restrict__ out1, int A, int B, int C, long long out_c_stride) {
     __shared__ float2 tile[32][33];
-    const int c0 = blockIdx.x * 32, a0 = blockIdx.y * 32, b = blockIdx.z;
+    const int t = blockIdx.z / B, b = blockIdx.z - t * B;
+    const float2* in = t ? in1 : in0;
+    float2* out = t ? out1 : out0;
+    const int c0 = blockIdx.x * 32, a0 = blockIdx.y * 32;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;              // 32 x 8
     for (int r = ty; r < 32; r += 8) {
         const int aa = a0 + r, cc = c0 + tx;
@@ -359,18 +363,20 @@ int tc_mix_pack(const float* w0, const float* w1, int rpw, int R, int NY, int Ci
                 cudaStream_t st) {
     const int nm = rpw * NY;                                    // modes per weight tensor
     const int ntens = (R == rpw) ? 1 : 2;
-    for (int t = 0; t < ntens; ++t) {
-        const float2* src = reinterpret_cast<const float2*>(t == 0 ? w0 : w1);
-        float2* out = reinterpret_cast<float2*>(dst) + (size_t)t * nm * Ci * Co;
+    const float2* s0 = reinterpret_cast<const float2*>(w0);
+    const float2* s1 = reinterpret_cast<const float2*>(w1 ? w1 : w0);
+    float2* o0 = reinterpret_cast<float2*>(dst);
+    float2* o1 = o0 + (size_t)nm * Ci * Co;
+    {
         LaunchScope ls("mix_pack", st);
         if (which == 0) {
             // in[a = (i,o)][b = 1][c = m] -> out[m][(i,o)]
-            dim3 grid((nm + 31) / 32, (Ci * Co + 31) / 32, 1);
-            permute_c64_cba<<<grid, 256, 0, st>>>(src, out, Ci * Co, 1, nm, (long long)Ci * Co);
+            dim3 grid((nm + 31) / 32, (Ci * Co + 31) / 32, ntens);
+            permute_c64_cba<<<grid, 256, 0, st>>>(s0, s1, o0, o1, Ci * Co, 1, nm, (long long)Ci * Co);
         } else {
             // in[a = i][b = o][c = m] -> out[m][o][i]
-            dim3 grid((nm + 31) / 32, (Ci + 31) / 32, Co);
-            permute_c64_cba<<<grid, 256, 0, st>>>(src, out, Ci, Co, nm, (long long)Ci * Co);
+            dim3 grid((nm + 31) / 32, (Ci + 31) / 32, Co * ntens);
+            permute_c64_cba<<<grid, 256, 0, st>>>(s0, s1, o0, o1, Ci, Co, nm, (long long)Ci * Co);
         }
     }
     return check_launch("mix_pack");
@@ -380,13 +386,14 @@ int tc_mix_pack(const float* w0, const float* w1, int rpw, int R, int NY, int Ci
 int tc_mix_unpack(const float* dW1, float* dw0, float* dw1, int rpw, int R, int NY, int Ci, int Co, cudaStream_t st) {
     const int nm = rpw * NY;
     const int ntens = (R == rpw) ? 1 : 2;
-    for (int t = 0; t < ntens; ++t) {
-        const float2* src = reinterpret_cast<const float2*>(dW1) + (size_t)t * nm * Ci * Co;
-        float2* out = reinterpret_cast<float2*>(t == 0 ? dw0 : dw1);
+    const float2* s0 = reinterpret_cast<const float2*>(dW1);
+    const float2* s1 = s0 + (size_t)nm * Ci * Co;
+    {
         LaunchScope ls("mix_unpack", st);
         // in[a = m][b = 1][c = (i,o)] -> out[(i,o)][m]
-        dim3 grid((Ci * Co + 31) / 32, (nm + 31) / 32, 1);
-        permute_c64_cba<<<grid, 256, 0, st>>>(src, out, nm, 1, Ci * Co, (long long)nm);
+        dim3 grid((Ci * Co + 31) / 32, (nm + 31) / 32, ntens);
+        permute_c64_cba<<<grid, 256, 0, st>>>(s0, s1, reinterpret_cast<float2*>(dw0),
+                                                 reinterpret_cast<float2*>(dw1 ? dw1 : dw0), nm, 1, Ci * Co, (long long)nm);
     }
     return check_launch("mix_unpack");
 }
