@@ -53,6 +53,7 @@ PROTOTYPES = {
     "fnm_ydft": (_i32, [_vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _vp]),
     "fnm_xdft": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     "fnm_xsyn": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "fnm_resample": (_i32, [_vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _vp]),
     "fnm_mix_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32, _i32]),
     "fnm_mix_fwd": (_i32, [_vp, _vp, _vp, _i32, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _sz, _i32, _vp]),
     "fnm_mix_bwd_x": (_i32, [_vp, _vp, _vp, _i32, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _sz, _i32, _vp]),

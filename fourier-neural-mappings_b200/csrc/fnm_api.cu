@@ -182,6 +182,18 @@ int fnm_xsyn(const float* Oh, const float* fx, float* Z, int B, int S1, int R, i
     return simt_xsyn(Oh, fx, Z, B, S1, R, NY, C, as_stream(stream));
 }
 
+int fnm_resample(const float* in, const float* tab, float* out, int64_t G, int K, int M, int inner, int C, int mode,
+                 fnm_stream_t stream) {
+    FNM_REQUIRE(in && tab && out, "resample: NULL pointer");
+    FNM_REQUIRE(G >= 0 && K > 0 && M > 0 && inner > 0 && C > 0, "resample: bad extents");
+    if (G == 0) return FNM_OK;
+    if (tc_resample_supported(G, K, M, inner, C))
+        return tc_resample(in, tab, out, G, K, M, inner, C, mode, as_stream(stream));
+    // same contraction with the trailing (inner, C) extent taken as one channel axis
+    FNM_REQUIRE((int64_t)inner * C < (1LL << 30), "resample: trailing extent too large");
+    return simt_ydft(in, tab, out, G, K, M, inner * C, 0, as_stream(stream));
+}
+
 size_t fnm_mix_workspace_bytes(int B, int R, int NY, int Ci, int Co) {
     return tc_mix_supported(B, Ci, Co) ? tc_mix_shadow_floats(R * NY, Ci, Co) * sizeof(float) + 256 : 0;
 }

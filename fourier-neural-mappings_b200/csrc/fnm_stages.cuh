@@ -46,6 +46,9 @@ int tc_ydft(const float* x, const float* tab, float* T, int64_t rows, int P2, in
             cudaStream_t st);
 bool tc_xdft_supported(int B, int P1, int R, int NY, int C);
 int tc_xdft(const float* T, const float* ex, float* Xh, int B, int P1, int R, int NY, int C, int mode, cudaStream_t st);
+bool tc_resample_supported(int64_t G, int K, int M, int inner, int C);
+int tc_resample(const float* in, const float* tab, float* out, int64_t G, int K, int M, int inner, int C, int mode,
+                cudaStream_t st);
 bool tc_xsyn_supported(int B, int S1, int R, int NY, int C);
 int tc_xsyn(const float* Oh, const float* fx, float* Z, int B, int S1, int R, int NY, int C, int mode, cudaStream_t st);
 bool tc_mix_supported(int B, int Ci, int Co);

@@ -471,4 +471,23 @@ int tc_xsyn(const float* Oh, const float* fx, float* Z, int B, int S1, int R, in
     return tg_launch(a, "xsyn", st);
 }
 
+// out[g][m][j][c] = sum_k tab[m][k] in[g][k][j][c]:  item = (g, j), the table along one axis of a
+// channels-last tensor whose trailing extent is inner*C
+bool tc_resample_supported(int64_t G, int K, int M, int inner, int C) {
+    return G > 0 && inner > 0 && G * inner < (1LL << 30) && tg_probe(C, (int)(G * inner), K, M);
+}
+
+int tc_resample(const float* in, const float* tab, float* out, int64_t G, int K, int M, int inner, int C, int mode,
+                cudaStream_t st) {
+    TgArgs a{};
+    a.in = in; a.tab = tab; a.out = out;
+    a.C = C; a.G = (int)(G * inner); a.Kt = K; a.Mt = M;
+    a.gin_div = inner; a.gin_s1 = (long long)K * inner * C; a.gin_s0 = C;           // item = g*inner + j
+    a.kin_div = 1 << 30; a.k_s1 = 0; a.k_s0 = (long long)inner * C;
+    a.gout_div = inner; a.gout_s1 = (long long)M * inner * C; a.gout_s0 = C;
+    a.mout_div = 1 << 30; a.m_s1 = 0; a.m_s0 = (long long)inner * C;
+    a.act = 0; a.single_pass = mode == FNM_MODE_TF32;
+    return tg_launch(a, "resample", st);
+}
+
 }  // namespace fnm

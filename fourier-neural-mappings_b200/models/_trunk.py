@@ -59,8 +59,13 @@ def run_layers(state, speconvs, ws, act_name, act_flags, one_d, last_s=None):
         if change:
             x = state.value()
             z, _ = ops.fourier_layer(x, sc.weights1, w1, None, None, _layer_tables(sc, P1, P2, one_d, last_s))
-            # the pointwise branch acts on the Fourier-resampled input: adjacent op
-            if one_d:
+            # the pointwise branch acts on the Fourier-resampled input: one table GEMM per axis,
+            # then the 1x1 conv on the (small) output grid
+            if _fused_ends_ok(x) and w.in_channels % 4 == 0 and w.out_channels % 4 == 0 and \
+                    max(w.in_channels, w.out_channels) <= 128:
+                xc = ops.project_resolution(x, last_s, one_d)
+                z = z + ops.pointwise_conv(xc, w.weight.view(w.out_channels, w.in_channels), w.bias)
+            elif one_d:
                 xc = projector1d(x.squeeze(1).permute(0, 2, 1), last_s)
                 z = z + w(xc).permute(0, 2, 1).unsqueeze(1)
             else:

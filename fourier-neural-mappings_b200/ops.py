@@ -313,6 +313,53 @@ class PointwiseConvFn(torch.autograd.Function):
         return dx, dw, db
 
 
+class ResampleFn(torch.autograd.Function):
+    """out[g, m, j, c] = sum_k tab[m, k] x[g, k, j, c]: one axis of the reference's Fourier projector
+    (shared.py:121-128, 162-169) as a table contraction; backward is the same kernel with the transposed
+    table.  ``x`` is viewed as (G, K, inner, C)."""
+
+    @staticmethod
+    def forward(ctx, x, tab, tabT, G, K, M, inner):
+        _need_cuda(x, tab)
+        x = _f32c(x)
+        Cc = x.shape[-1]
+        out = torch.empty((G, M, inner, Cc), dtype=torch.float32, device=x.device)
+        check(lib().fnm_resample(_ptr(x), _ptr(tab), _ptr(out), G, K, M, inner, Cc, _MODE, _stream()), "fnm_resample")
+        ctx.tabT, ctx.dims, ctx.in_shape = tabT, (G, K, M, inner, Cc), x.shape
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        G, K, M, inner, Cc = ctx.dims
+        g = _f32c(g)
+        dx = torch.empty((G, K, inner, Cc), dtype=torch.float32, device=g.device)
+        check(lib().fnm_resample(_ptr(g), _ptr(ctx.tabT), _ptr(dx), G, M, K, inner, Cc, _MODE, _stream()), "fnm_resample")
+        return dx.view(ctx.in_shape), None, None, None, None, None, None
+
+
+def project_resolution(x, s, one_d):
+    """``projector1d`` / ``projector2d`` on a channels-last (B, P1, P2, C) tensor (P1 = 1 in 1-D): one table
+    contraction per axis (two stacked ones where the reference's resize keeps a non-Hermitian bin set, see
+    plan.ResampleTables)."""
+    from .plan import resample_tables
+    B, P1, P2, Cc = x.shape
+    if one_d:
+        S2 = int(s)
+        d = resample_tables(None, P2, None, S2).device(x.device)
+        return ResampleFn.apply(x, d["ty"], d["tyT"], B, P2, S2, 1).view(B, 1, S2, Cc)
+    S1, S2 = int(s[0]), int(s[1])
+    t = resample_tables(P1, P2, S1, S2)
+    d = t.device(x.device)
+    if t.separable:
+        if S2 != P2:
+            x = ResampleFn.apply(x, d["ty"], d["tyT"], B * P1, P2, S2, 1)
+        if S1 != P1:
+            x = ResampleFn.apply(x, d["tx"], d["txT"], B, P1, S1, S2)
+        return x.view(B, S1, S2, Cc)
+    x = ResampleFn.apply(x, d["ty"], d["tyT"], B * P1, P2, 2 * S2, 1)             # (B, P1, (re/im, S2), C)
+    return ResampleFn.apply(x, d["tx"], d["txT"], B, 2 * P1, S1, S2).view(B, S1, S2, Cc)
+
+
 class MlpHeadFn(torch.autograd.Function):
     """out[..., d] = sum_h w2[d, h] GELU(h1[..., h]) + b2[d] (the activation and second layer of the
     reference MLP, shared.py:26-45) without materialising GELU(h1)."""

@@ -196,3 +196,67 @@ def decoder_tables(S1, S2, m1, m2, one_d=False):
         rows_out = _destination(twosided_source(2 * m1, S1), 2 * m1)
     return ModeTables("decoder", S1, S2, S1, S2, None, rows_out, None, cols_out,
                       0.0, 1.0 / (S1 * S2), len(rows_out))
+
+
+class ResampleTables:
+    """``projector1d`` / ``projector2d`` (shared.py:121-128, 162-169: rfft -> resize_rfft[2] -> irfft) as real
+    resampling matrices, obtained by pushing the identity through the reference's own index rules in
+    float64.  ``ty`` (S2 x P2) acts along the last axis (one-sided resize), ``tx`` (S1 x P1) along the first
+    axis of a 2-D field (two-sided resize).
+
+    The two-sided rule does not always keep Hermitian-symmetric bins (an even target keeps the Nyquist bin
+    on the negative side only, shared.py:104-108; an odd-length spectrum is split at N // 2 when zero
+    padding, shared.py:94-96).  The x-axis operator is then complex, A = Ar + i Ai, and with Y = rfft_y(x)
+        out = Ar (x R^T) + Ai (x H^T),   R = irfft_y(resized Y),  H = irfft_y(i * resized Y).
+    ``separable`` False selects that two-term form: ``ty`` is then [R; H] (2 S2 x P2) and ``tx`` holds
+    (Ar, Ai) interleaved along its columns (S1 x 2 P1), matching the (x, re/im) order of the intermediate."""
+
+    def __init__(self, P1, P2, S1, S2):
+        self.P1, self.P2, self.S1, self.S2 = P1, P2, S1, S2
+        spec = np.fft.rfft(np.eye(P2), axis=-1) / P2
+        src = onesided_source(spec.shape[-1], S2)
+        res = np.where(src >= 0, spec[:, np.clip(src, 0, None)], 0.0)
+        ty = (np.fft.irfft(res, n=S2, axis=-1) * S2).T                            # [y'][y]
+        self.separable = True
+        tx = None
+        if P1 is not None:
+            spec1 = np.fft.fft(np.eye(P1), axis=-1) / P1
+            src1 = twosided_source(P1, S1)
+            res1 = np.where(src1 >= 0, spec1[:, np.clip(src1, 0, None)], 0.0)
+            txc = (np.fft.ifft(res1, n=S1, axis=-1) * S1).T                       # [x'][x], complex in general
+            self.separable = bool(np.abs(txc.imag).max() <= 1e-12 * max(1.0, np.abs(txc.real).max()))
+            if self.separable:
+                tx = txc.real
+            else:
+                hy = (np.fft.irfft(1j * res, n=S2, axis=-1) * S2).T
+                ty = np.concatenate([ty, hy], axis=0)                             # [(ri, y')][y]
+                tx = np.stack([txc.real, txc.imag], axis=-1).reshape(S1, 2 * P1)  # [x'][(x, ri)]
+        host = {"ty": ty, "tyT": ty.T}
+        if tx is not None:
+            host["tx"], host["txT"] = tx, tx.T
+        self.host = {k: np.ascontiguousarray(v, dtype=np.float32) for k, v in host.items()}
+        self._dev = {}
+
+    def device(self, device):
+        key = str(device)
+        if key not in self._dev:
+            self._dev[key] = {k: torch.from_numpy(v).to(device) for k, v in self.host.items()}
+        return self._dev[key]
+
+    def apply_host(self, x):
+        """float64 evaluation on a (..., P1, P2) (or (..., P2)) torch tensor: the definition the CUDA path is
+        tested against besides the golden vectors."""
+        ty = torch.from_numpy(self.host["ty"]).to(x.dtype)
+        if self.P1 is None:
+            return torch.einsum("dy,...y->...d", ty, x)
+        tx = torch.from_numpy(self.host["tx"]).to(x.dtype)
+        if self.separable:
+            return torch.einsum("ax,...xy,dy->...ad", tx, x, ty)
+        t = torch.einsum("rdy,...xy->...xrd", ty.view(2, self.S2, self.P2), x)
+        return torch.einsum("axr,...xrd->...ad", tx.view(self.S1, self.P1, 2), t)
+
+
+@lru_cache(maxsize=64)
+def resample_tables(P1, P2, S1, S2):
+    """P1 = S1 = None for the 1-D projector."""
+    return ResampleTables(P1, P2, S1, S2)

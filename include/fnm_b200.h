@@ -162,6 +162,11 @@ int fnm_xdft(const float* T, const float* ex, float* Xh, int B, int P1, int R, i
 /* Z[b][x][ro][l][c] = sum_{ri,r} fx[(x,ro)][(ri,r)] Oh[r][l][ri][b][c]   (inverse C2C along x)       */
 int fnm_xsyn(const float* Oh, const float* fx, float* Z, int B, int S1, int R, int NY, int C, int mode,
              fnm_stream_t stream);
+/* one axis of projector1d / projector2d (shared.py:121-128, 162-169: rfft -> resize -> irfft) as a real
+ * (M x K) resampling table applied to a channels-last tensor with trailing extent inner*C:
+ *   out[g][m][j][c] = sum_k tab[m][k] in[g][k][j][c]      (backward: the same call with tab^T)              */
+int fnm_resample(const float* in, const float* tab, float* out, int64_t G, int K, int M, int inner, int C, int mode,
+                 fnm_stream_t stream);
 /* compl_mul (shared.py:48-53) and its two backward products.  `workspace` (fnm_mix_workspace_bytes; may be
  * NULL) lets the tcgen05 path make a mode-major copy of the weights / of dW; without it the fp32 SIMT
  * kernels run on the reference layout.

@@ -320,6 +320,45 @@ def v2v_forward(p, v, s_latentspace, act="gelu", nonlinear_first=True):
     return _functional_end(x, p, a, d, "mlp1")
 
 
+def f1d_to_f2d_forward(p, x, padding=8, act="gelu", s_outputspace=None, get_grid=True):
+    """FNO1d2 (func1d_to_func2d.py:78-121): lift a 1-D function, decode every grid point's channel vector into a
+    function of a second axis of the UNPADDED input length (:97), 2-D trunk whose last layer changes resolution."""
+    a = activation(act)
+    x, res = _lift(x, p, padding, get_grid)
+    n = res[0]
+    x = linear_decoder1d(x, p["ldec0.weights"], n)                      # (B, width, P, n)
+    s_pad, cut = None, (n // padding, n // padding)
+    if s_outputspace is not None:
+        s_pad = tuple(r + r // padding for r in s_outputspace)
+        cut = tuple(r // padding for r in s_outputspace)
+    nl = _count(p, "ws")
+    for i in range(nl):
+        last = i == nl - 1
+        x = fourier_layer(x, p, i, None if last else a, s_pad if last else None)
+    x = _crop(x, cut)
+    return mlp(x.movedim(1, -1), p, "mlp0", a).movedim(-1, 1)
+
+
+def f2d_to_f1d_forward(p, x, padding=8, act="gelu", s_outputspace=None, get_grid=True):
+    """FNO2d1 (func2d_to_func1d.py:78-128): 2-D trunk (activation after every layer), functionals of the LAST axis
+    for every x (:103-111), 1-D resolution change, crop (by ny // padding when no output resolution is set,
+    :120), pointwise MLP."""
+    a = activation(act)
+    x, res = _lift(x, p, padding, get_grid)
+    for i in range(_count(p, "ws")):
+        x = fourier_layer(x, p, i, a)
+    nonlocal_feats = linear_functionals1d(x, p["lfunc0.weights"])       # (B, width1d, P1)
+    loc = mlp(x.movedim(1, -1), p, "mlpfunc0", a).movedim(-1, 1)
+    loc = torch.trapz(loc, dx=1.0 / loc.shape[-1])
+    x = torch.cat((nonlocal_feats, loc), dim=1)
+    cut = res[-1] // padding
+    if s_outputspace is not None:
+        x = project1d(x, s_outputspace + s_outputspace // padding)
+        cut = s_outputspace // padding
+    x = _crop(x, (cut,))
+    return mlp(x.movedim(1, -1), p, "mlp0", a).movedim(-1, 1)
+
+
 # --------------------------------------------------------------------------------------
 # loss and optimiser
 # --------------------------------------------------------------------------------------

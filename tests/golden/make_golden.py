@@ -176,6 +176,43 @@ def model_cases():
                                              width_final=16, n_layers=3), (2, 5))
 
 
+def _fno2d1(*a, **kw):
+    """The reference's FNO2d1 never stores ``get_grid`` (func2d_to_func1d.py:8-75) and its forward reads it
+    (:90), so the stock class raises AttributeError; the attribute is set here, nothing else is touched."""
+    m = models.FNO2d1(*a, **kw)
+    m.get_grid = True
+    return m
+
+
+def cross_dim_cases():
+    """Cross-dimension models and extra resolution-change cases; kept in their own
+    files so that the fixtures above stay byte-identical."""
+    model_case("fno1d2", lambda: models.FNO1d2(4, 12, 3, 3, 8, width_final=16, n_layers=3), (2, 1, 32))
+    model_case("fno1d2_res", lambda: models.FNO1d2(4, 12, 3, 3, 8, s_outputspace=(16, 11), width_final=16, n_layers=3,
+                                                   d_in=2, d_out=2), (2, 2, 32))
+    model_case("fno2d1", lambda: _fno2d1(4, 12, 3, 3, 8, width_final=16, n_layers=3), (2, 1, 16, 16))
+    model_case("fno2d1_res", lambda: _fno2d1(4, 12, 3, 3, 8, s_outputspace=24, width_final=16, n_layers=3, d_in=2,
+                                             d_out=2), (2, 2, 16, 14))
+    model_case("fno1d_res", lambda: models.FNO1d(5, 8, s_outputspace=21, n_layers=3, width_final=16), (3, 1, 32))
+    model_case("fno2d_res_odd", lambda: models.FNO2d(3, 3, 8, s_outputspace=(11, 23), n_layers=2, width_final=16),
+               (2, 1, 17, 16))
+    d = {}
+    for tag, (shape, s) in {"p2_odd_up": ((2, 3, 9, 7), (14, 11)), "p2_odd_down": ((2, 3, 19, 17), (5, 7)),
+                            "p2_even_down": ((2, 2, 16, 16), (10, 16)), "p2_mixed": ((2, 2, 8, 9), (16, 4))}.items():
+        x = randn(*shape, seed=11)
+        d[f"{tag}.x"], d[f"{tag}.y"], d[f"{tag}.s"] = x, shared.projector2d(x, s), np.array(s)
+    for tag, (shape, s) in {"p1_odd_up": ((2, 3, 9), 14), "p1_odd_down": ((2, 3, 19), 5)}.items():
+        x = randn(*shape, seed=12)
+        d[f"{tag}.x"], d[f"{tag}.y"], d[f"{tag}.s"] = x, shared.projector1d(x, s), np.array([s])
+    npz("projectors.npz", **d)
+    import json
+    lay = {}
+    for name, c in {"FNO1d2": lambda: models.FNO1d2(), "FNO2d1": lambda: models.FNO2d1()}.items():
+        lay[name] = {k: [list(v.shape), str(v.dtype)] for k, v in c().state_dict().items()}
+    with open(os.path.join(HERE, "state_dict_layouts_cross_dim.json"), "w") as f:
+        json.dump(lay, f, indent=1)
+
+
 def adam_cases():
     """NB: the reference's amsgrad branch calls torch.maximum on the complex second moment and
     raises for complex parameters (Adam.py:43), so the amsgrad case holds a real parameter only."""
@@ -226,7 +263,11 @@ def state_dict_layouts():
 
 if __name__ == "__main__":
     torch.set_num_threads(4)
+    if sys.argv[1:] == ["cross_dim"]:
+        cross_dim_cases()
+        sys.exit(0)
     blocks()
     model_cases()
     adam_cases()
     state_dict_layouts()
+    cross_dim_cases()

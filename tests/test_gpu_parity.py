@@ -102,6 +102,15 @@ MODELS = {
                                     width_final=16, n_layers=4),
     "fnn1d": lambda: fnm_b200.FNN1d(5, 3, s_latentspace=32, modes1=5, width=8, width_initial=16, width_final=16,
                                     n_layers=3),
+    # resolution change at odd sizes and the cross-dimension models
+    "fno1d_res": lambda: fnm_b200.FNO1d(5, 8, s_outputspace=21, n_layers=3, width_final=16),
+    "fno2d_res_odd": lambda: fnm_b200.FNO2d(3, 3, 8, s_outputspace=(11, 23), n_layers=2, width_final=16),
+    "fno1d2": lambda: fnm_b200.FNO1d2(4, 12, 3, 3, 8, width_final=16, n_layers=3),
+    "fno1d2_res": lambda: fnm_b200.FNO1d2(4, 12, 3, 3, 8, s_outputspace=(16, 11), width_final=16, n_layers=3, d_in=2,
+                                          d_out=2),
+    "fno2d1": lambda: fnm_b200.FNO2d1(4, 12, 3, 3, 8, width_final=16, n_layers=3),
+    "fno2d1_res": lambda: fnm_b200.FNO2d1(4, 12, 3, 3, 8, s_outputspace=24, width_final=16, n_layers=3, d_in=2,
+                                          d_out=2),
 }
 
 
@@ -115,6 +124,12 @@ ORACLE_FWD = {
     "fnd1d": lambda p, x: O.v2f_forward(p, x, 32),
     "fnn2d": lambda p, x: O.v2v_forward(p, x, (16, 16)),
     "fnn1d": lambda p, x: O.v2v_forward(p, x, 32),
+    "fno1d_res": lambda p, x: O.f2f_forward(p, x, s_outputspace=21),
+    "fno2d_res_odd": lambda p, x: O.f2f_forward(p, x, s_outputspace=(11, 23)),
+    "fno1d2": lambda p, x: O.f1d_to_f2d_forward(p, x),
+    "fno1d2_res": lambda p, x: O.f1d_to_f2d_forward(p, x, s_outputspace=(16, 11)),
+    "fno2d1": lambda p, x: O.f2d_to_f1d_forward(p, x),
+    "fno2d1_res": lambda p, x: O.f2d_to_f1d_forward(p, x, s_outputspace=24),
 }
 
 

@@ -302,6 +302,52 @@ def test_weighted_gelu_sum(B, P1, P2, H):
     assert rel_l2(h1.grad, h64.grad) < 1e-6
 
 
+@pytest.mark.parametrize("B,P1,P2,C,s", [
+    (3, 24, 20, 32, (12, 10)),     # even -> even: two-term form (Nyquist bin kept on one side), tcgen05 table GEMM
+    (2, 29, 29, 64, (13, 13)),     # odd -> odd: one real table per axis
+    (2, 145, 145, 32, (37, 37)),   # the paper's F2F grids (train_fno.py:45-46)
+    (2, 16, 12, 128, (24, 18)),    # upsampling
+    (2, 9, 11, 8, (14, 7)),        # odd upsampling (resize_fft's N // 2 split) on the SIMT engine
+    (2, 1, 48, 32, 20),            # 1-D
+    (3, 1, 21, 12, 30)])
+def test_project_resolution(B, P1, P2, C, s):
+    """projector1d / projector2d (shared.py:121-128, 162-169) on channels-last tensors: forward against the FFT
+    statement in float64, backward against its autograd."""
+    torch.manual_seed(9)
+    one_d = not isinstance(s, tuple)
+    x = torch.randn(B, P1, P2, C, device=DEV, requires_grad=True)
+    out = fnm_b200.ops.project_resolution(x, s, one_d)
+    g = torch.randn_like(out)
+    out.backward(g)
+    x64 = x.detach().double().requires_grad_(True)
+    if one_d:
+        ref = fnm_b200.shared.projector1d(x64.squeeze(1).permute(0, 2, 1), s).permute(0, 2, 1).unsqueeze(1)
+    else:
+        ref = fnm_b200.shared.projector2d(x64.permute(0, 3, 1, 2), s).permute(0, 2, 3, 1)
+    ref.backward(g.double())
+    assert out.shape == ref.shape
+    assert rel_l2(out, ref) < TOL_FP32
+    assert rel_l2(x.grad, x64.grad) < TOL_FP32
+
+
+def test_project_resolution_vs_reference_fixtures():
+    """Outputs of the reference's own projector1d / projector2d (tests/golden/projectors.npz, blocks.npz)."""
+    from tests.helpers import load_npz
+    g = load_npz("projectors.npz")
+    b = load_npz("blocks.npz")
+    g.update({"b2d.x": b["proj2.x"], "b2d.y": b["proj2.down"], "b2d.s": [8, 6], "b2u.x": b["proj2.x"], "b2u.y": b["proj2.up"],
+              "b2u.s": [16, 14], "b1d.x": b["proj1.x"], "b1d.y": b["proj1.down"], "b1d.s": [7], "b1u.x": b["proj1.x"],
+              "b1u.y": b["proj1.up"], "b1u.s": [20]})
+    for tag in sorted({k.split(".")[0] for k in g}):
+        x, y, s = torch.from_numpy(g[f"{tag}.x"]).to(DEV), g[f"{tag}.y"], [int(v) for v in g[f"{tag}.s"]]
+        if x.dim() == 4:
+            got = fnm_b200.ops.project_resolution(x.permute(0, 2, 3, 1).contiguous(), tuple(s), False).permute(0, 3, 1, 2)
+        else:
+            got = fnm_b200.ops.project_resolution(x.permute(0, 2, 1).unsqueeze(1).contiguous(), s[0], True)
+            got = got.squeeze(1).permute(0, 2, 1)
+        assert rel_l2(got, y) < TOL_FP32, tag
+
+
 def test_gelu_kernels():
     z = torch.randn(100003, device=DEV) * 3
     g = torch.randn_like(z)

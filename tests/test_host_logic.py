@@ -167,6 +167,47 @@ def test_resize_helpers_match_oracle():
         assert torch.equal(fnm_b200.shared.resize_rfft2(a, s), O.keep_spectrum2(a, s))
 
 
+@pytest.mark.parametrize("P1,P2,S1,S2", [(12, 10, 8, 6), (12, 10, 16, 14), (9, 7, 14, 11), (9, 9, 5, 5), (145, 145, 37, 37),
+                                         (8, 9, 16, 18), (7, 8, 3, 1), (16, 16, 10, 16), (6, 1, 4, 3)])
+def test_resample_tables_2d(P1, P2, S1, S2):
+    """projector2d as table contractions (one real table per axis, or the two-term form where the two-sided
+    resize keeps a non-Hermitian bin set) against the FFT statement, including the golden vectors."""
+    tab = P.resample_tables(P1, P2, S1, S2)
+    x = torch.randn(2, 3, P1, P2, dtype=torch.float64, generator=torch.Generator().manual_seed(3))
+    assert rel_l2(tab.apply_host(x), fnm_b200.shared.projector2d(x, (S1, S2))) < 5e-7
+    if (P1, P2) == (12, 10):
+        g = np.load(os.path.join(GOLDEN, "blocks.npz"))
+        xg = torch.from_numpy(g["proj2.x"]).double()
+        assert rel_l2(tab.apply_host(xg), g["proj2.down" if S1 == 8 else "proj2.up"]) < 5e-7
+    if P1 % 2 == 1 and S1 % 2 == 1 and S1 <= P1:
+        assert tab.separable            # odd -> odd truncation keeps a symmetric bin set
+    if S1 % 2 == 0 and 1 < S1 < P1:
+        assert not tab.separable        # an even target keeps its Nyquist bin on the negative side only
+
+
+def test_resample_tables_vs_reference_projector_fixtures():
+    """projectors.npz holds outputs of the reference's projector1d / projector2d at odd and mixed sizes (the
+    N // 2 split of resize_fft, one-sided Nyquist bins)."""
+    g = np.load(os.path.join(GOLDEN, "projectors.npz"))
+    for tag in sorted({k.split(".")[0] for k in g.files}):
+        x, y, s = torch.from_numpy(g[f"{tag}.x"]).double(), g[f"{tag}.y"], g[f"{tag}.s"]
+        if tag.startswith("p2"):
+            tab = P.resample_tables(x.shape[-2], x.shape[-1], int(s[0]), int(s[1]))
+        else:
+            tab = P.resample_tables(None, x.shape[-1], None, int(s[0]))
+        assert rel_l2(tab.apply_host(x), y) < 5e-7, tag
+
+
+@pytest.mark.parametrize("Pn,s", [(12, 7), (12, 20), (9, 14), (16, 16), (5, 1)])
+def test_resample_tables_1d(Pn, s):
+    tab = P.resample_tables(None, Pn, None, s)
+    x = torch.randn(2, 3, Pn, dtype=torch.float64, generator=torch.Generator().manual_seed(4))
+    assert rel_l2(tab.apply_host(x), fnm_b200.shared.projector1d(x, s)) < 5e-7
+    if Pn == 12:
+        g = np.load(os.path.join(GOLDEN, "blocks.npz"))
+        assert rel_l2(tab.apply_host(torch.from_numpy(g["proj1.x"]).double()), g["proj1.down" if s == 7 else "proj1.up"]) < 5e-7
+
+
 # ---------------------------------------------------------------- no CPU fallback --------------
 def test_cpu_tensors_fail_loudly():
     m = fnm_b200.FNO2d(3, 3, 8, n_layers=2, width_final=16)
@@ -210,7 +251,10 @@ def test_c_abi_rejects_bad_arguments_without_gpu():
 # ---------------------------------------------------------------- state_dict contract ----------
 def test_state_dict_layout_matches_reference():
     ref = json.load(open(os.path.join(GOLDEN, "state_dict_layouts.json")))
+    ref.update(json.load(open(os.path.join(GOLDEN, "state_dict_layouts_cross_dim.json"))))
     ctors = {
+        "FNO1d2": lambda: fnm_b200.FNO1d2(),
+        "FNO2d1": lambda: fnm_b200.FNO2d1(),
         "FNO2d": lambda: fnm_b200.FNO2d(12, 12, 32),
         "FNO1d": lambda: fnm_b200.FNO1d(16, 64),
         "FNF2d": lambda: fnm_b200.FNF2d(12, 12, 32, d_in=2, d_out=2),

@@ -139,6 +139,14 @@ def test_projectors():
     assert rel_l2(O.project1d(t(BLOCKS["proj1.x"]), 20), BLOCKS["proj1.up"]) < TIGHT
 
 
+def test_projectors_odd_and_mixed_sizes():
+    g = load_npz("projectors.npz")
+    for tag in sorted({k.split(".")[0] for k in g}):
+        x, s = t(g[f"{tag}.x"]), g[f"{tag}.s"]
+        got = O.project2d(x, tuple(int(v) for v in s)) if tag.startswith("p2") else O.project1d(x, int(s[0]))
+        assert rel_l2(got, g[f"{tag}.y"]) < TIGHT, tag
+
+
 def test_errors_match_reference():
     with pytest.raises(ValueError):
         O.activation("swish")                      # shared.py:22
@@ -159,6 +167,12 @@ MODEL_FWD = {
     "fnd1d": lambda p, x: O.v2f_forward(p, x, 32),
     "fnn2d": lambda p, x: O.v2v_forward(p, x, (16, 16)),
     "fnn1d": lambda p, x: O.v2v_forward(p, x, 32),
+    "fno1d_res": lambda p, x: O.f2f_forward(p, x, s_outputspace=21),
+    "fno2d_res_odd": lambda p, x: O.f2f_forward(p, x, s_outputspace=(11, 23)),
+    "fno1d2": lambda p, x: O.f1d_to_f2d_forward(p, x),
+    "fno1d2_res": lambda p, x: O.f1d_to_f2d_forward(p, x, s_outputspace=(16, 11)),
+    "fno2d1": lambda p, x: O.f2d_to_f1d_forward(p, x),
+    "fno2d1_res": lambda p, x: O.f2d_to_f1d_forward(p, x, s_outputspace=24),
 }
 
 
