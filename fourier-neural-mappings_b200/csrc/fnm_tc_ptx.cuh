@@ -86,6 +86,12 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
         : "r"(taddr)
         : "memory");
 }
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr)
+                 : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
     asm volatile(
@@ -156,6 +162,13 @@ __device__ __forceinline__ float rcp_fast(float x) {          // MUFU.RCP (1 ulp
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
 }
+// exp(-z^2) for the GELU formulas: MUFU.EX2 with flush-to-zero (results below 2^-126 only occur for |x| > 13, where
+// erfc is 0 to fp32 anyway); __expf adds a denormal-range fix-up (compare + two multiplies) per element
+__device__ __forceinline__ float exp_neg_sq(float z) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(z * z * -1.4426950408889634074f));
+    return r;
+}
 __device__ __forceinline__ float gelu_fast(float x) {
     const float z = fabsf(x) * 0.70710678118654752440f;
     const float tt = rcp_fast(fmaf(0.3275911f, z, 1.0f));
@@ -163,7 +176,7 @@ __device__ __forceinline__ float gelu_fast(float x) {
     p = fmaf(p, tt, 1.421413741f);
     p = fmaf(p, tt, -0.284496736f);
     p = fmaf(p, tt, 0.254829592f);
-    const float e = p * tt * __expf(-z * z);          // erfc(z) for z >= 0
+    const float e = p * tt * exp_neg_sq(z);           // erfc(z) for z >= 0
     const float cdf = x >= 0.f ? 1.0f - 0.5f * e : 0.5f * e;
     return x * cdf;
 }
@@ -176,7 +189,7 @@ __device__ __forceinline__ float gelu_grad_fast(float x) {
     p = fmaf(p, tt, 1.421413741f);
     p = fmaf(p, tt, -0.284496736f);
     p = fmaf(p, tt, 0.254829592f);
-    const float ex = __expf(-z * z);
+    const float ex = exp_neg_sq(z);
     const float e = p * tt * ex;
     const float cdf = x >= 0.f ? 1.0f - 0.5f * e : 0.5f * e;
     return fmaf(x * 0.39894228040143267794f, ex, cdf);

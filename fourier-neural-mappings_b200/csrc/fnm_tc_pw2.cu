@@ -56,6 +56,19 @@ __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
 
+// Optional per-role timeline of CTA 0 (build with -DFNM_PW2_TRACE; tools/pw2_trace.py reads it).  Never in the product build.
+#ifdef FNM_PW2_TRACE
+constexpr int kTraceTiles = 96, kTraceEv = 12;
+__device__ long long g_pw2_trace[kTraceTiles * kTraceEv];
+#define PW2_TRACE(tile_idx, ev)                                                                     \
+    do {                                                                                            \
+        if (blockIdx.x == 0 && (tile_idx) < (uint32_t)kTraceTiles && (threadIdx.x & 31) == 0)       \
+            g_pw2_trace[(tile_idx) * kTraceEv + (ev)] = clock64();                                  \
+    } while (0)
+#else
+#define PW2_TRACE(tile_idx, ev) do { } while (0)
+#endif
+
 // TMEM column map
 constexpr uint32_t kA1Hi = 0, kA1Lo = 128, kA2Hi = 256, kA2Lo = 320, kD0 = 384;
 
@@ -76,9 +89,12 @@ __device__ __forceinline__ void umma_ts32(uint32_t d, uint32_t a_tmem, uint32_t 
 
 // raw passes of one tile: D = (A_hi [+ A_lo]) * B_raw over K1S channel slabs and NKS2 mode k-steps.
 // K1S / NKS2 < 0: runtime extents (generic shapes).
+// The Z^T operand (A2) of a new grid row is awaited only after the channel part has been issued (a2_bar != nullptr
+// on the row's first tile): the Z warpgroup converts the next row while those MMAs keep the tensor pipe busy.
 template <int K1S, int NKS2, bool SINGLE>
 __device__ __forceinline__ void pw2_issue_raw(uint32_t d, uint32_t tb, uint32_t a2hi, uint32_t a2lo, uint32_t x_lo,
-                                              uint32_t by_lo, uint32_t slab16, uint32_t idesc, int k1s_rt, int nks2_rt) {
+                                              uint32_t by_lo, uint32_t slab16, uint32_t idesc, int k1s_rt, int nks2_rt,
+                                              uint64_t* a2_bar, uint32_t a2_par) {
     const int k1s = K1S >= 0 ? K1S : k1s_rt, nks2 = NKS2 >= 0 ? NKS2 : nks2_rt;
     uint32_t accum = 0;
 #pragma unroll
@@ -92,6 +108,10 @@ __device__ __forceinline__ void pw2_issue_raw(uint32_t d, uint32_t tb, uint32_t 
                 if (!SINGLE) umma_ts32(d, tb + kA1Lo + kb * 32 + ks * 8, b, idesc, 1);
             }
         }
+    }
+    if (a2_bar) {
+        mbar_wait(a2_bar, a2_par);
+        tc_fence_after();
     }
 #pragma unroll
     for (int k8 = 0; k8 < (NKS2 >= 0 ? NKS2 : 8); ++k8) {
@@ -125,15 +145,21 @@ __device__ __forceinline__ void pw2_issue_lo(uint32_t d, uint32_t tb, uint32_t a
 #define PW2_SHAPES(X) X(4, 8) X(2, 4) X(1, 3) X(4, 4) X(2, 8) X(1, 4) X(4, 0) X(2, 0) X(1, 0)
 
 
+// Epilogue of one warp: lane = output channel, 8 positions per step.  The loop is deliberately NOT unrolled over the
+// tile: a fully unrolled 32-position body (with GELU / GELU' inline) is ~50 KB of code that every epilogue warp
+// streams through once per tile, and ncu showed those warps stalled on instruction fetch for 40 % of their samples
+// while pacing the whole kernel.  The GELU' operand of step c+1 is loaded while step c is computed.
 template <bool HAS_MUL, bool HAS_ACT>
 __device__ __forceinline__ void pw2_epilogue(const PwArgs2& a, int warp, int lane, uint32_t tmem_base, int my_units,
                                              uint64_t* acc_full, uint64_t* acc_empty) {
     const int q4 = warp & 3, o = q4 * 32 + lane;
     const int half = (warp - 10) >> 2;
     const int hc = a.NT / 2;                                       // columns per half: 16, 24 or 32
+    const int nsteps = hc >> 3;
     const int fr = o / a.COo, oo = o - fr * a.COo;              // lane = (row within the group, out channel)
     const float bias = (o < a.CO && a.bias) ? __ldg(a.bias + oo) : 0.f;
     const uint32_t lane_base = tmem_base + ((uint32_t)(q4 * 32) << 16) + kD0;
+    const size_t cstride = (size_t)a.COo;
     uint32_t t = 0;
     for (int u = 0; u < my_units; ++u) {
         const int unit = (int)blockIdx.x + u * (int)gridDim.x;
@@ -144,34 +170,89 @@ __device__ __forceinline__ void pw2_epilogue(const PwArgs2& a, int warp, int lan
         for (int tile = t0; tile < t1; ++tile, ++t) {
             const uint32_t acc = t & 1;
             const int yb = tile * a.NT + half * hc;                 // first position of this warp's columns
-            const int nv = max(0, min(hc, a.S2 - yb));              // valid positions
-            const size_t base = ((size_t)row * a.S2 + yb) * a.COo + oo;
-            float m[32];
-            if (HAS_MUL) {                                        // issued before the accumulator wait: overlaps the MMAs
+            const int nv = o_ok ? max(0, min(hc, a.S2 - yb)) : 0;   // valid positions of this lane
+            const size_t base = ((size_t)row * a.S2 + yb) * cstride + oo;
+            float mn[8];
+            if (HAS_MUL) {
+                // pull the NEXT tile's operand lines into L2 (lane j: the 128-byte channel slice of position j) ...
+                int ntile = tile + 1, nrg = rg;
+                if (ntile == t1) {                                  // first tile of this CTA's next unit
+                    const int nunit = unit + (int)gridDim.x;
+                    nrg = nunit / a.nseg;
+                    ntile = nunit < a.units ? (nunit - nrg * a.nseg) * a.seg_tiles : -1;
+                }
+                const int frw = (q4 * 32) / a.COo, sb = q4 * 32 - frw * a.COo;      // warp-uniform (row in group, channel slice)
+                const long long nrow = (long long)nrg * a.F + frw;
+                const int ny = ntile * a.NT + half * hc + lane;
+                if (ntile >= 0 && lane < hc && ny < a.S2 && nrow < a.rows && q4 * 32 < a.CO)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(a.mul + ((size_t)nrow * a.S2 + ny) * cstride + sb));
+                // ... and this tile's first step into registers before the accumulator wait
                 const float* mp = a.mul + base;
+                if (__all_sync(0xffffffffu, 8 <= nv)) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) m[j] = (o_ok && j < nv) ? __ldg(mp + (size_t)j * a.COo) : 0.f;
+                    for (int j = 0; j < 8; ++j) mn[j] = __ldg(mp + j * a.COo);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) mn[j] = j < nv ? __ldg(mp + j * a.COo) : 0.f;
+                }
             }
+            if (warp == 10) PW2_TRACE(t, 7);
             mbar_wait(&acc_full[acc], (t >> 1) & 1);
             tc_fence_after();
+            if (warp == 10) PW2_TRACE(t, 8);
             const uint32_t taddr = lane_base + acc * 64u + (uint32_t)(half * hc);
+            // element offsets of the 8 positions of a step (shared by the operand, the output and the GELU copy)
+            uint32_t offs[8];                                       // in bytes
 #pragma unroll
-            for (int g = 0; g < 2; ++g) {
-                if (g * 16 < hc) {
-                    uint32_t r[16];
-                    tmem_ld16(taddr + g * 16, r);
-                    tmem_ld_wait();
-                    if (o_ok) {
-                        float* op = a.out + base + (size_t)(g * 16) * a.COo;
-                        float* ap = HAS_ACT ? a.out_act + base + (size_t)(g * 16) * a.COo : nullptr;
+            for (int j = 0; j < 8; ++j) offs[j] = (uint32_t)(j * a.COo) * 4u;
+            auto at = [](const float* p0, uint32_t byte_off) {
+                return reinterpret_cast<const float*>(reinterpret_cast<const char*>(p0) + byte_off);
+            };
+            auto at_w = [](float* p0, uint32_t byte_off) { return reinterpret_cast<float*>(reinterpret_cast<char*>(p0) + byte_off); };
+#pragma unroll 1
+            for (int c = 0; c < nsteps; ++c) {
+                uint32_t r[8];
+                tmem_ld8(taddr + c * 8, r);
+                // warp-uniform fast path (all 8 positions valid in every lane): no per-element predicates or branches,
+                // so the eight GELU chains interleave
+                const bool full = __all_sync(0xffffffffu, (c + 1) * 8 <= nv);
+                float m[8];
+                if (HAS_MUL) {
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            if (g * 16 + j < nv) {
-                                float v = __uint_as_float(r[j]) + bias;
-                                if (HAS_MUL) v *= gelu_grad_fast(m[g * 16 + j]);
-                                op[(size_t)j * a.COo] = v;
-                                if (HAS_ACT) ap[(size_t)j * a.COo] = gelu_fast(v);
-                            }
+                    for (int j = 0; j < 8; ++j) m[j] = mn[j];
+                    if (c + 1 < nsteps) {
+                        const float* mp = a.mul + base + (size_t)((c + 1) * 8) * cstride;
+                        if (__all_sync(0xffffffffu, (c + 2) * 8 <= nv)) {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) mn[j] = __ldg(at(mp, offs[j]));
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) mn[j] = (c + 1) * 8 + j < nv ? __ldg(at(mp, offs[j])) : 0.f;
+                        }
+                    }
+                }
+                tmem_ld_wait();
+                float* op = a.out + base + (size_t)(c * 8) * cstride;
+                float* ap = HAS_ACT ? a.out_act + base + (size_t)(c * 8) * cstride : nullptr;
+                float v[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    v[j] = __uint_as_float(r[j]) + bias;
+                    if (HAS_MUL) v[j] *= gelu_grad_fast(m[j]);
+                }
+                if (full) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) *at_w(op, offs[j]) = v[j];
+                    if (HAS_ACT) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) *at_w(ap, offs[j]) = gelu_fast(v[j]);
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        if (c * 8 + j < nv) {
+                            *at_w(op, offs[j]) = v[j];
+                            if (HAS_ACT) *at_w(ap, offs[j]) = gelu_fast(v[j]);
                         }
                     }
                 }
@@ -179,6 +260,7 @@ __device__ __forceinline__ void pw2_epilogue(const PwArgs2& a, int warp, int lan
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&acc_empty[acc]);
+            if (warp == 10) PW2_TRACE(t, 9);
         }
     }
 }
@@ -273,6 +355,7 @@ pw2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUt
                 for (int tile = t0; tile < t1; ++tile, ++t) {
                     const uint32_t s = t % (uint32_t)a.stages;
                     mbar_wait(&empty[s], ((t / (uint32_t)a.stages) & 1) ^ 1);
+                    PW2_TRACE(t, 10);
                     mbar_expect_tx(&full[s], a.stage_bytes);
                     uint8_t* st = smem + (size_t)s * a.stage_bytes;
                     const int y0 = tile * a.NT;
@@ -299,35 +382,39 @@ pw2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUt
             unit_tiles(u, row, t0, t1);
             const uint32_t ub = (uint32_t)u % na2, upar = ((uint32_t)u / na2) & 1;
             const uint32_t a2hi = tmem_base + kA2Hi + (na2 == 2 ? 64u * ub : 0u), a2lo = a2hi + (na2 == 2 ? 32u : 64u);
-            if (has_z) mbar_wait(&a2_full[ub], upar);
             for (int tile = t0; tile < t1; ++tile, ++t) {
+                uint64_t* a2_bar = (has_z && tile == t0) ? &a2_full[ub] : nullptr;
                 const uint32_t s = t % (uint32_t)a.stages, acc = t & 1;
                 mbar_wait(&acc_empty[acc], ((t >> 1) & 1) ^ 1);
+                PW2_TRACE(t, 0);
                 mbar_wait(&full[s], (t / (uint32_t)a.stages) & 1);
                 tc_fence_after();
+                PW2_TRACE(t, 1);
                 const uint32_t d = tmem_base + kD0 + acc * 64u;
                 const uint32_t x_lo = desc_lo(sbase + s * a.stage_bytes), by_lo = x_lo + xb16;
                 // raw passes: (A_hi + A_lo) * B_raw
                 bool done = false;
 #define PW2_RAW(K1, K2)                                                                                                  \
                 if (!done && a.K1slabs == K1 && nks2 == K2) {                                                            \
-                    if (a.single_pass) pw2_issue_raw<K1, K2, true>(d, tmem_base, a2hi, a2lo, x_lo, by_lo, slab16, idesc, 0, 0);      \
-                    else pw2_issue_raw<K1, K2, false>(d, tmem_base, a2hi, a2lo, x_lo, by_lo, slab16, idesc, 0, 0);                   \
+                    if (a.single_pass) pw2_issue_raw<K1, K2, true>(d, tmem_base, a2hi, a2lo, x_lo, by_lo, slab16, idesc, 0, 0, a2_bar, upar);  \
+                    else pw2_issue_raw<K1, K2, false>(d, tmem_base, a2hi, a2lo, x_lo, by_lo, slab16, idesc, 0, 0, a2_bar, upar);               \
                     done = true;                                                                                         \
                 }
                 PW2_SHAPES(PW2_RAW)
 #undef PW2_RAW
                 if (!done) {
-                    if (a.single_pass) pw2_issue_raw<-1, -1, true>(d, tmem_base, a2hi, a2lo, x_lo, by_lo, slab16, idesc, a.K1slabs, nks2);
-                    else pw2_issue_raw<-1, -1, false>(d, tmem_base, a2hi, a2lo, x_lo, by_lo, slab16, idesc, a.K1slabs, nks2);
+                    if (a.single_pass) pw2_issue_raw<-1, -1, true>(d, tmem_base, a2hi, a2lo, x_lo, by_lo, slab16, idesc, a.K1slabs, nks2, a2_bar, upar);
+                    else pw2_issue_raw<-1, -1, false>(d, tmem_base, a2hi, a2lo, x_lo, by_lo, slab16, idesc, a.K1slabs, nks2, a2_bar, upar);
                 }
                 umma_commit(&empty[s]);                              // the raw tile is free once the raw passes retire
+                PW2_TRACE(t, 2);
                 if (!a.single_pass) {
                     // remainder pass: A_hi * B_lo
                     const uint32_t lb = a.nlo == 2 ? (t & 1) : 0u;
                     const uint32_t xl_lo = desc_lo(lo_base0 + lb * a.stage_bytes), byl_lo = xl_lo + xb16;
                     mbar_wait(&lo_full[lb], a.nlo == 2 ? ((t >> 1) & 1) : (t & 1));
                     tc_fence_after();
+                    PW2_TRACE(t, 3);
                     done = false;
 #define PW2_LO(K1, K2)                                                                                                   \
                     if (!done && a.K1slabs == K1 && nks2 == K2) {                                                        \
@@ -340,6 +427,7 @@ pw2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUt
                     umma_commit(&lo_empty[lb]);
                 }
                 umma_commit(&acc_full[acc]);
+                PW2_TRACE(t, 4);
                 if (has_z && tile == t1 - 1) umma_commit(&a2_empty[ub]);
                 __syncwarp();
             }
@@ -385,6 +473,7 @@ pw2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUt
                     mbar_wait(&full[s], (t / (uint32_t)a.stages) & 1);
                     const uint32_t lb = a.nlo == 2 ? (t & 1) : 0u;
                     mbar_wait(&lo_empty[lb], (a.nlo == 2 ? ((t >> 1) & 1) : (t & 1)) ^ 1);
+                    if (warp == 6) PW2_TRACE(t, 5);
                     const uint32_t src = smem_u32(smem) + s * a.stage_bytes + (uint32_t)ct * 16u;
                     const uint32_t dst = smem_u32(lo_buf) + lb * a.stage_bytes + (uint32_t)ct * 16u;
                     // linear copy (the remainder tile has the raw tile's swizzled layout, so offsets are identical):
@@ -411,6 +500,7 @@ pw2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUt
                     fence_proxy_async();
                     __syncwarp();
                     if (lane == 0) { mbar_arrive(&lo_full[lb]); mbar_arrive(&empty[s]); }
+                    if (warp == 6) PW2_TRACE(t, 6);
                 }
             }
         }
@@ -585,3 +675,11 @@ int tc_pw2(const float* x, const float* wc, int wc_is_kn, const float* bias, con
 }
 
 }  // namespace fnm
+
+#ifdef FNM_PW2_TRACE
+extern "C" int fnm_debug_pw2_trace(long long* host, int n) {
+    const int total = fnm::tc::kTraceTiles * fnm::tc::kTraceEv;
+    if (n > total) n = total;
+    return (int)cudaMemcpyFromSymbol(host, fnm::tc::g_pw2_trace, sizeof(long long) * n);
+}
+#endif
