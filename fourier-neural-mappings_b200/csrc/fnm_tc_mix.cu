@@ -13,9 +13,13 @@
 //   apply, backward-x: A = W2 (k=o, l=i), B = G^ (n=b), conj    Gx[b][i] = sum_o G[b][o] conj(W[i][o])
 //   wgrad            : A = X^ (k=b, l=i), B = G^ (n=o), conj    dW[i][o] = sum_b conj(X[b][i]) G[b][o]
 // A is read with coalesced warp loads (lane = l), split hi/lo in registers and written to TMEM;
-// B is turned into K-major SWIZZLE_128B rows (raw + truncation remainder) by loader threads; the four
-// real products of the complex multiply go to D_re / D_im (main and correction accumulators, see
-// fnm_tc_tabgemm.cu for why), the sign of the A_im terms is applied with the descriptor's negate bit.
+// B is turned into K-major SWIZZLE_128B rows (raw + truncation remainder) by loader threads, the real rows
+// of the tile stacked on its imaginary rows: B' = [B_re ; B_im] is ONE 64-row operand, so the complex
+// product takes two accumulators F = A_re B' = [A_re B_re | A_re B_im] and E = A_im B' = [A_im B_re | A_im B_im]
+// (6 MMAs with N = 64 per k-step in 3xTF32 instead of 12 with N = 32: the cost of a tf32 MMA does not depend
+// on N at this size) and the epilogue forms D_re = F_re -/+ E_im, D_im = F_im +/- E_re (lower sign: conj(A)).
+// The contraction is short (K = Cin <= 128 or K = batch), so the 2^-11-sized correction products share the
+// accumulator of the main product (see fnm_tc_tabgemm.cu for when they must not).
 //
 // Warps (16): 0-3 epilogue | 4 MMA issuer | 5-7 B loaders | 8-15 two A-loader warpgroups.
 #include "fnm_tc_ptx.cuh"
@@ -37,6 +41,8 @@ struct MxArgs {
     int Kt, Lt, Nt;                                        // contraction length, lanes (<= 128), n extent
     int nmodes, ntiles, items, nchunks;
     int conj, single_pass, a_pair, b_kcontig, o_pair;      // a_pair / o_pair: (re, im) adjacent -> 8-byte accesses
+    int a_reuse;                                           // one A chunk per mode, kept in TMEM across the mode's n tiles
+    int b_tma;                                             // B rows are K-contiguous and 16-byte aligned: TMA brings the raw tile
 };
 
 __device__ __forceinline__ float ldf(const float* p) {
@@ -50,12 +56,12 @@ __device__ __forceinline__ float2 ldf2(const float* p) {
     return v;
 }
 
-// smem per B buffer: [re raw | re lo | im raw | im lo] x nchunks slabs of [32 rows][128 B]
-__global__ void __launch_bounds__(kMxThreads, 1) mixgemm_tc(const MxArgs a) {
+// smem per B buffer: [raw | lo] x nchunks slabs of [64 rows = 32 re + 32 im][128 B]
+__global__ void __launch_bounds__(kMxThreads, 1) mixgemm_tc(const __grid_constant__ CUtensorMap mapB, const MxArgs a) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    const uint32_t part_bytes = (uint32_t)a.nchunks * 4096u;       // one of the four parts
-    const uint32_t bbuf_bytes = 4u * part_bytes;
+    const uint32_t half_bytes = (uint32_t)a.nchunks * 8192u;       // raw tile | remainder tile, 64 rows per k-chunk slab
+    const uint32_t bbuf_bytes = 2u * half_bytes;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * bbuf_bytes);
     uint64_t* a_full = bars;             // [2] 4 warps
     uint64_t* a_empty = bars + 2;        // [2]
@@ -63,7 +69,8 @@ __global__ void __launch_bounds__(kMxThreads, 1) mixgemm_tc(const MxArgs a) {
     uint64_t* b_empty = bars + 6;        // [2]
     uint64_t* d_full = bars + 8;         // [2]
     uint64_t* d_empty = bars + 10;       // [2] 4 warps
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+    uint64_t* braw_full = bars + 12;     // [2] TMA transaction barrier of the raw B tile
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
 
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
@@ -71,8 +78,10 @@ __global__ void __launch_bounds__(kMxThreads, 1) mixgemm_tc(const MxArgs a) {
             mbar_init(&a_full[s], 4); mbar_init(&a_empty[s], 1);
             mbar_init(&b_full[s], kMxBWarps); mbar_init(&b_empty[s], 1);
             mbar_init(&d_full[s], 1); mbar_init(&d_empty[s], 4);
+            mbar_init(&braw_full[s], 1);
         }
         fence_barrier_init();
+        if (a.b_tma) tma_prefetch_desc(&mapB);
     }
     if (warp == 4) tmem_alloc(tmem_slot, 512);
     tc_fence_before();
@@ -80,16 +89,24 @@ __global__ void __launch_bounds__(kMxThreads, 1) mixgemm_tc(const MxArgs a) {
     tc_fence_after();
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
     // TMEM: A buffer s at 128*s: [re hi | re lo | im hi | im lo] x 32 columns;
-    //       D buffer s at 256 + 128*s: [re main | re corr | im main | im corr] x 32 columns
-    const int my_items = (a.items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    //       D buffer s at 256 + 128*s: F = [A_re B_re | A_re B_im], E = [A_im B_re | A_im B_im], 32 columns each
+    // a CTA owns whole modes and runs their n tiles back to back; when the contraction fits one A chunk (weight
+    // gradient: K = batch) the A operand of a mode stays in TMEM for all its n tiles (a_reuse)
+    const int my_modes = (a.nmodes - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int my_items = my_modes * a.ntiles;
+    auto item_of = [&](int it, int& m, int& n0) {
+        const int mi = it / a.ntiles;
+        m = (int)blockIdx.x + mi * (int)gridDim.x;
+        n0 = (it - mi * a.ntiles) * kMxN;
+    };
 
     if (warp < 4) {
         // =========================================================================== epilogue
         const int L = warp * 32 + lane;
         const bool l_ok = L < a.Lt;
         for (int it = 0; it < my_items; ++it) {
-            const int item = (int)blockIdx.x + it * (int)gridDim.x;
-            const int m = item / a.ntiles, n0 = (item - m * a.ntiles) * kMxN;
+            int m, n0;
+            item_of(it, m, n0);
             const int db = it & 1;
             mbar_wait(&d_full[db], (uint32_t)((it >> 1) & 1));
             tc_fence_after();
@@ -97,21 +114,22 @@ __global__ void __launch_bounds__(kMxThreads, 1) mixgemm_tc(const MxArgs a) {
             float* obase = a.out + (size_t)m * a.o_sm + (size_t)L * a.o_sl;
 #pragma unroll
             for (int g = 0; g < 2; ++g) {
-                uint32_t rm[16], rc[16], im[16], ic[16];
-                tmem_ld16(taddr + g * 16, rm);
-                tmem_ld16(taddr + 64 + g * 16, im);
-                if (!a.single_pass) {
-                    tmem_ld16(taddr + 32 + g * 16, rc);
-                    tmem_ld16(taddr + 96 + g * 16, ic);
-                }
+                uint32_t fr[16], fi[16], er[16], ei[16];
+                tmem_ld16(taddr + g * 16, fr);
+                tmem_ld16(taddr + 32 + g * 16, fi);
+                tmem_ld16(taddr + 64 + g * 16, er);
+                tmem_ld16(taddr + 96 + g * 16, ei);
                 tmem_ld_wait();
                 if (l_ok) {
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
                         const int n = n0 + g * 16 + j;
                         if (n < a.Nt) {
-                            float vr = __uint_as_float(rm[j]), vi = __uint_as_float(im[j]);
-                            if (!a.single_pass) { vr += __uint_as_float(rc[j]); vi += __uint_as_float(ic[j]); }
+                            // conj: 0 = A B, 1 = conj(A) B, 2 = A conj(B)
+                            const float s = a.conj ? 1.f : -1.f;
+                            const float vr = fmaf(s, __uint_as_float(ei[j]), __uint_as_float(fr[j]));
+                            float vi = fmaf(-s, __uint_as_float(er[j]), __uint_as_float(fi[j]));
+                            if (a.conj == 2) vi = -vi;
                             float* p = obase + (size_t)n * a.o_sn;
                             if (a.o_pair) *reinterpret_cast<float2*>(p) = make_float2(vr, vi);
                             else { p[0] = vr; p[a.o_im] = vi; }
@@ -126,46 +144,44 @@ __global__ void __launch_bounds__(kMxThreads, 1) mixgemm_tc(const MxArgs a) {
     } else if (warp == 4) {
         // =========================================================================== MMA issuer
         const uint32_t sbase = smem_u32(smem);
-        const uint32_t idesc = make_idesc(128, kMxN);
-        const uint32_t ineg = idesc | (1u << 13);                     // negate A
-        // D_re = Ar*Br -/+ Ai*Bi ; D_im = +/- Ai*Br + Ar*Bi     (upper sign: plain product, lower: conj(A))
-        const uint32_t id_re_ai = a.conj ? idesc : ineg;
-        const uint32_t id_im_ai = a.conj ? ineg : idesc;
+        const uint32_t idesc = make_idesc(128, 2 * kMxN);
         uint32_t q = 0;
         for (int it = 0; it < my_items; ++it) {
             const int db = it & 1, bb = it & 1;
             mbar_wait(&d_empty[db], (uint32_t)(((it >> 1) & 1) ^ 1));
             mbar_wait(&b_full[bb], (uint32_t)((it >> 1) & 1));
-            const uint32_t d_re = tmem_base + 256u + 128u * db, d_rc = d_re + 32u, d_im = d_re + 64u, d_ic = d_re + 96u;
+            const uint32_t d_f = tmem_base + 256u + 128u * db, d_e = d_f + 64u;
             const uint32_t bs = sbase + bb * bbuf_bytes;
-            for (int ch = 0; ch < a.nchunks; ++ch, ++q) {
+            const int tile = it % a.ntiles;
+            for (int ch = 0; ch < a.nchunks; ++ch) {
                 const uint32_t ab = q & 1;
-                mbar_wait(&a_full[ab], (q >> 1) & 1);
-                tc_fence_after();
+                if (!a.a_reuse || tile == 0) {
+                    mbar_wait(&a_full[ab], (q >> 1) & 1);
+                    tc_fence_after();
+                }
                 const uint32_t ar = tmem_base + 128u * ab, arl = ar + 32u, ai = ar + 64u, ail = ar + 96u;
-                const uint64_t br = make_desc(bs + (uint32_t)ch * 4096u), brl = make_desc(bs + part_bytes + (uint32_t)ch * 4096u);
-                const uint64_t bi = make_desc(bs + 2 * part_bytes + (uint32_t)ch * 4096u);
-                const uint64_t bil = make_desc(bs + 3 * part_bytes + (uint32_t)ch * 4096u);
+                const uint64_t braw = make_desc(bs + (uint32_t)ch * 8192u), blo = make_desc(bs + half_bytes + (uint32_t)ch * 8192u);
                 const int nks = min(4, (a.Kt - ch * 32 + 7) / 8);
-                for (int ks = 0; ks < nks; ++ks) {
-                    const uint32_t first = (ch == 0 && ks == 0) ? 0u : 1u;
-                    const uint32_t k8 = ks * 8;
-                    umma_ts(d_re, ar + k8, br + 2 * ks, idesc, first);
-                    umma_ts(d_re, ai + k8, bi + 2 * ks, id_re_ai, 1);
-                    umma_ts(d_im, ai + k8, br + 2 * ks, id_im_ai, first);
-                    umma_ts(d_im, ar + k8, bi + 2 * ks, idesc, 1);
-                    if (!a.single_pass) {
-                        umma_ts(d_rc, arl + k8, br + 2 * ks, idesc, first);
-                        umma_ts(d_rc, ar + k8, brl + 2 * ks, idesc, 1);
-                        umma_ts(d_rc, ail + k8, bi + 2 * ks, id_re_ai, 1);
-                        umma_ts(d_rc, ai + k8, bil + 2 * ks, id_re_ai, 1);
-                        umma_ts(d_ic, ail + k8, br + 2 * ks, id_im_ai, first);
-                        umma_ts(d_ic, ai + k8, brl + 2 * ks, id_im_ai, 1);
-                        umma_ts(d_ic, arl + k8, bi + 2 * ks, idesc, 1);
-                        umma_ts(d_ic, ar + k8, bil + 2 * ks, idesc, 1);
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) {
+                    if (ks < nks) {
+                        const uint32_t first = (ch == 0 && ks == 0) ? 0u : 1u;
+                        const uint32_t k8 = ks * 8;
+                        const uint64_t br = braw + 2 * ks, bl = blo + 2 * ks;
+                        umma_ts(d_f, ar + k8, br, idesc, first);
+                        umma_ts(d_e, ai + k8, br, idesc, first);
+                        if (!a.single_pass) {
+                            umma_ts(d_f, arl + k8, br, idesc, 1);
+                            umma_ts(d_e, ail + k8, br, idesc, 1);
+                            umma_ts(d_f, ar + k8, bl, idesc, 1);
+                            umma_ts(d_e, ai + k8, bl, idesc, 1);
+                        }
                     }
                 }
-                umma_commit(&a_empty[ab]);
+                if (!a.a_reuse || tile == a.ntiles - 1) {
+                    umma_commit(&a_empty[ab]);
+                    ++q;
+                }
             }
             umma_commit(&b_empty[bb]);
             umma_commit(&d_full[db]);
@@ -174,12 +190,50 @@ __global__ void __launch_bounds__(kMxThreads, 1) mixgemm_tc(const MxArgs a) {
     } else if (warp < 8) {
         // =========================================================================== B loaders (96 threads)
         const int bt = threadIdx.x - 5 * 32;
+        // TMA variant: one thread streams the raw [re ; im] rows of an item (SWIZZLE_128B boxes of 32 k x 32 rows) one
+        // item ahead; the three warps only derive the remainder tile, smem -> smem
+        auto tma_item = [&](int it) {
+            int m, n0;
+            item_of(it, m, n0);
+            const int bb = it & 1;
+            uint8_t* base = smem + (size_t)bb * bbuf_bytes;
+            mbar_wait(&b_empty[bb], (uint32_t)(((it >> 1) & 1) ^ 1));
+            mbar_expect_tx(&braw_full[bb], half_bytes);
+            for (int ch = 0; ch < a.nchunks; ++ch)
+                for (int ri = 0; ri < 2; ++ri) {
+                    tma_load_2d(&mapB, &braw_full[bb], base + (size_t)ch * 8192 + (size_t)ri * 4096, ch * 32,
+                                (m * 2 + ri) * a.Nt + n0);
+                }
+        };
+        if (a.b_tma && warp == 5 && lane == 0 && my_items > 0) tma_item(0);
         for (int it = 0; it < my_items; ++it) {
-            const int item = (int)blockIdx.x + it * (int)gridDim.x;
-            const int m = item / a.ntiles, n0 = (item - m * a.ntiles) * kMxN;
+            int m, n0;
+            item_of(it, m, n0);
             const int bb = it & 1;
             uint8_t* base = smem + (size_t)bb * bbuf_bytes;
             const float* src = a.b + (size_t)m * a.b_sm;
+            if (a.b_tma) {
+                mbar_wait(&braw_full[bb], (uint32_t)((it >> 1) & 1));
+                const uint32_t raw0 = smem_u32(base) + (uint32_t)bt * 16u;
+                for (uint32_t off = 0; off < half_bytes; off += kMxBWarps * 32 * 16 * 2) {
+                    float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
+                    const uint32_t o1 = off + kMxBWarps * 32 * 16;
+                    const bool ok0 = off + (uint32_t)bt * 16u < half_bytes, ok1 = o1 + (uint32_t)bt * 16u < half_bytes;
+                    if (ok0) asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v0.x), "=f"(v0.y), "=f"(v0.z), "=f"(v0.w) : "r"(raw0 + off));
+                    if (ok1) asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v1.x), "=f"(v1.y), "=f"(v1.z), "=f"(v1.w) : "r"(raw0 + o1));
+                    v0.x -= __uint_as_float(__float_as_uint(v0.x) & 0xffffe000u); v0.y -= __uint_as_float(__float_as_uint(v0.y) & 0xffffe000u);
+                    v0.z -= __uint_as_float(__float_as_uint(v0.z) & 0xffffe000u); v0.w -= __uint_as_float(__float_as_uint(v0.w) & 0xffffe000u);
+                    v1.x -= __uint_as_float(__float_as_uint(v1.x) & 0xffffe000u); v1.y -= __uint_as_float(__float_as_uint(v1.y) & 0xffffe000u);
+                    v1.z -= __uint_as_float(__float_as_uint(v1.z) & 0xffffe000u); v1.w -= __uint_as_float(__float_as_uint(v1.w) & 0xffffe000u);
+                    if (ok0) asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(raw0 + half_bytes + off), "f"(v0.x), "f"(v0.y), "f"(v0.z), "f"(v0.w) : "memory");
+                    if (ok1) asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(raw0 + half_bytes + o1), "f"(v1.x), "f"(v1.y), "f"(v1.z), "f"(v1.w) : "memory");
+                }
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&b_full[bb]);
+                if (warp == 5 && lane == 0 && it + 1 < my_items) tma_item(it + 1);
+                continue;
+            }
             mbar_wait(&b_empty[bb], (uint32_t)(((it >> 1) & 1) ^ 1));
             if (a.b_kcontig) {
                 // rows n, k contiguous: 16-byte units (part re/im, row, 16-byte chunk over the padded K)
@@ -210,14 +264,14 @@ __global__ void __launch_bounds__(kMxThreads, 1) mixgemm_tc(const MxArgs a) {
                         const int u = u0 + bt + j * kMxBWarps * 32;
                         if (u < units) {
                             const int ri = u / (kMxN * kc), r2 = u - ri * kMxN * kc, n = r2 / kc, c = r2 - n * kc;
-                            uint8_t* dst = base + (size_t)(2 * ri) * part_bytes + (size_t)(c >> 3) * 4096 + swz(n, c & 7);
+                            uint8_t* dst = base + (size_t)(c >> 3) * 8192 + (size_t)ri * 4096 + swz(n, c & 7);
                             float4 l;
                             l.x = v[j].x - __uint_as_float(__float_as_uint(v[j].x) & 0xffffe000u);
                             l.y = v[j].y - __uint_as_float(__float_as_uint(v[j].y) & 0xffffe000u);
                             l.z = v[j].z - __uint_as_float(__float_as_uint(v[j].z) & 0xffffe000u);
                             l.w = v[j].w - __uint_as_float(__float_as_uint(v[j].w) & 0xffffe000u);
                             *reinterpret_cast<float4*>(dst) = v[j];
-                            *reinterpret_cast<float4*>(dst + part_bytes) = l;
+                            *reinterpret_cast<float4*>(dst + half_bytes) = l;
                         }
                     }
                 }
@@ -234,7 +288,7 @@ __global__ void __launch_bounds__(kMxThreads, 1) mixgemm_tc(const MxArgs a) {
                             const int k = ch * 32 + j;
                             v[j] = (n_ok && k < a.Kt) ? __ldg(p + (size_t)k * a.b_sk) : 0.f;
                         }
-                        uint8_t* dst = base + (size_t)(2 * ri) * part_bytes + (size_t)ch * 4096;
+                        uint8_t* dst = base + (size_t)ch * 8192 + (size_t)ri * 4096;
 #pragma unroll
                         for (int c4 = 0; c4 < 8; ++c4) {
                             const float4 w = make_float4(v[4 * c4], v[4 * c4 + 1], v[4 * c4 + 2], v[4 * c4 + 3]);
@@ -244,7 +298,7 @@ __global__ void __launch_bounds__(kMxThreads, 1) mixgemm_tc(const MxArgs a) {
                             l.z = w.z - __uint_as_float(__float_as_uint(w.z) & 0xffffe000u);
                             l.w = w.w - __uint_as_float(__float_as_uint(w.w) & 0xffffe000u);
                             *reinterpret_cast<float4*>(dst + swz(n, c4)) = w;
-                            *reinterpret_cast<float4*>(dst + part_bytes + swz(n, c4)) = l;
+                            *reinterpret_cast<float4*>(dst + half_bytes + swz(n, c4)) = l;
                         }
                     }
                 }
@@ -260,11 +314,12 @@ __global__ void __launch_bounds__(kMxThreads, 1) mixgemm_tc(const MxArgs a) {
         const int L = q4 * 32 + lane;
         const bool l_ok = L < a.Lt;
         const uint32_t tb = tmem_base + ((uint32_t)(q4 * 32) << 16) + 128u * wg;
-        const uint32_t total = (uint32_t)my_items * (uint32_t)a.nchunks;
+        const uint32_t total = a.a_reuse ? (uint32_t)my_modes : (uint32_t)my_items * (uint32_t)a.nchunks;
         for (uint32_t q = (uint32_t)wg; q < total; q += 2) {
-            const int it = (int)(q / (uint32_t)a.nchunks), ch = (int)(q - (uint32_t)it * a.nchunks);
-            const int item = (int)blockIdx.x + it * (int)gridDim.x;
-            const int m = item / a.ntiles;
+            const int it = a.a_reuse ? (int)q * a.ntiles : (int)(q / (uint32_t)a.nchunks);
+            const int ch = a.a_reuse ? 0 : (int)(q - (uint32_t)it * a.nchunks);
+            int m, n0_unused;
+            item_of(it, m, n0_unused);
             const float* p = a.a + (size_t)m * a.a_sm + (size_t)(ch * 32) * a.a_sk + (size_t)L * a.a_sl;
             const int klim = l_ok ? a.Kt - ch * 32 : 0;
             float vr[32], vi[32];
@@ -329,6 +384,7 @@ static int mx_launch(MxArgs& a, const char* what, cudaStream_t st) {
     const long long items = (long long)a.nmodes * a.ntiles;
     if (items > (1LL << 30)) return fail(FNM_EINVAL, "%s: too many work items", what);
     a.items = (int)items;
+    a.a_reuse = (a.nchunks == 1 && a.ntiles > 1) ? 1 : 0;
     size_t smem = 2 * 4 * (size_t)a.nchunks * 4096 + 1024 + 256;
     if (smem < 120 * 1024) smem = 120 * 1024;
     static bool attr_set = false;
@@ -337,10 +393,20 @@ static int mx_launch(MxArgs& a, const char* what, cudaStream_t st) {
         if (e != cudaSuccess) return fail(FNM_ECUDA, "%s: smem attribute: %s", what, cudaGetErrorString(e));
         attr_set = true;
     }
-    const int grid = a.items < sm_count() ? a.items : sm_count();
+    // raw B tile by TMA when its rows are K-contiguous: tensor [nmodes * 2 * Nt rows][Kt], box 32 x 32
+    CUtensorMap mapB{};
+    a.b_tma = 0;
+    if (a.b_kcontig && a.Kt % 4 == 0 && (reinterpret_cast<uintptr_t>(a.b) & 15) == 0 && a.b_sn == a.Kt &&
+        a.b_im == (long long)a.Nt * a.Kt && a.b_sm == 2 * a.b_im) {
+        const cuuint64_t dims[2] = {(cuuint64_t)a.Kt, (cuuint64_t)a.nmodes * 2 * (cuuint64_t)a.Nt};
+        const cuuint64_t str[1] = {(cuuint64_t)a.Kt * 4};
+        const cuuint32_t box[2] = {32, (cuuint32_t)kMxN};
+        if (tc_make_map(&mapB, a.b, 2, dims, str, box, true)) a.b_tma = 1;
+    }
+    const int grid = a.nmodes < sm_count() ? a.nmodes : sm_count();
     {
         LaunchScope ls(what, st);
-        mixgemm_tc<<<grid, kMxThreads, smem, st>>>(a);
+        mixgemm_tc<<<grid, kMxThreads, smem, st>>>(mapB, a);
     }
     return check_launch(what);
 }
@@ -412,15 +478,17 @@ int tc_mix_apply(const float* Wm, const float* In, float* Out, int nmodes, int B
     return mx_launch(a, what, st);
 }
 
-// dW1[m][i][o] = sum_b conj(Xh[m][.][b][i]) Gh[m][.][b][o]
+// dW1[m][i][o] = sum_b conj(Xh[m][.][b][i]) Gh[m][.][b][o].  The output-gradient spectrum is the TMEM operand
+// (lanes = o) so that the epilogue's warp stores run along o, the contiguous axis of dW1 (with lanes = i every
+// 8-byte store of a warp hit a different 1 KB row); the conjugate then sits on the shared-memory operand.
 int tc_mix_wgrad(const float* Xh, const float* Gh, float* dW1, int nmodes, int B, int Ci, int Co, int mode, cudaStream_t st) {
     MxArgs a{};
-    a.a = Xh; a.b = Gh; a.out = dW1;
-    a.Kt = B; a.Lt = Ci; a.Nt = Co; a.nmodes = nmodes;
-    a.a_sm = (long long)2 * B * Ci; a.a_sk = Ci; a.a_sl = 1; a.a_im = (long long)B * Ci; a.a_pair = 0;
-    a.b_sm = (long long)2 * B * Co; a.b_sn = 1; a.b_sk = Co; a.b_im = (long long)B * Co; a.b_kcontig = 0;
-    a.o_sm = (long long)Ci * Co * 2; a.o_sn = 2; a.o_sl = (long long)Co * 2; a.o_im = 1; a.o_pair = 1;
-    a.conj = 1; a.single_pass = mode == FNM_MODE_TF32;
+    a.a = Gh; a.b = Xh; a.out = dW1;
+    a.Kt = B; a.Lt = Co; a.Nt = Ci; a.nmodes = nmodes;
+    a.a_sm = (long long)2 * B * Co; a.a_sk = Co; a.a_sl = 1; a.a_im = (long long)B * Co; a.a_pair = 0;
+    a.b_sm = (long long)2 * B * Ci; a.b_sn = 1; a.b_sk = Ci; a.b_im = (long long)B * Ci; a.b_kcontig = 0;
+    a.o_sm = (long long)Ci * Co * 2; a.o_sn = (long long)Co * 2; a.o_sl = 2; a.o_im = 1; a.o_pair = 1;
+    a.conj = 2; a.single_pass = mode == FNM_MODE_TF32;
     return mx_launch(a, "mix_bwd_w", st);
 }
 

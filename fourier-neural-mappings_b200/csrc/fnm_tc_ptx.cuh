@@ -1,5 +1,6 @@
 // PTX wrappers shared by the tcgen05 / TMEM kernels of libfnm_b200 (sm_100a only).
 #pragma once
+#include <cuda.h>
 #include "fnm_stages.cuh"
 
 namespace fnm {
@@ -213,9 +214,29 @@ __device__ __forceinline__ void store_split4(uint8_t* hi_slab, uint8_t* lo_slab,
 }
 
 
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+
 // PTX wrappers below are shared helpers -------------------------------------------------------------
 __device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&r)[32]) { tmem_ld32(taddr, r); }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point (fnm_tc_pw2.cu); fp32 elements, strides in bytes
+bool tc_make_map(CUtensorMap* m, const float* ptr, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+                 const cuuint32_t* box, bool swizzle128);
 int sm_count();
 bool tc_enabled();
 

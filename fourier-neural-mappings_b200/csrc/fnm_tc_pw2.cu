@@ -19,7 +19,6 @@
 //   0 TMA producer | 1 TMEM allocator + MMA issuer | 2-5 Z warpgroup | 6-9 converters | 10-17 epilogue
 #include "fnm_tc_ptx.cuh"
 
-#include <cuda.h>
 #include <cstdlib>
 
 namespace fnm {
@@ -38,23 +37,6 @@ struct PwArgs2 {
     int K1slabs, K2slabs, LYp, stages, nlo, nz, debug;
     uint32_t stage_bytes, x_bytes, z_bytes;
 };
-
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
-    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-                 ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-                 : "memory");
-}
-__device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2) {
-    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-                 ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
-                 : "memory");
-}
-__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
-}
 
 // Optional per-role timeline of CTA 0 (build with -DFNM_PW2_TRACE; tools/pw2_trace.py reads it).  Never in the product build.
 #ifdef FNM_PW2_TRACE
@@ -538,7 +520,7 @@ static EncodeTiledFn encode_fn() {
     return fn;
 }
 
-static bool make_map(CUtensorMap* m, const float* ptr, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+bool tc_make_map(CUtensorMap* m, const float* ptr, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
                      const cuuint32_t* box, bool swizzle128) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return false;
@@ -642,19 +624,19 @@ int tc_pw2(const float* x, const float* wc, int wc_is_kn, const float* bias, con
         const cuuint64_t dims[2] = {(cuuint64_t)a.LY, (cuuint64_t)a.S2};
         const cuuint64_t str[1] = {(cuuint64_t)a.LY * 4};
         const cuuint32_t box[2] = {32, (cuuint32_t)a.NT};
-        if (!make_map(&mb, by, 2, dims, str, box, true)) return fail(FNM_ECUDA, "pointwise_ysyn: tensor map (by) failed");
+        if (!tc_make_map(&mb, by, 2, dims, str, box, true)) return fail(FNM_ECUDA, "pointwise_ysyn: tensor map (by) failed");
     }
     if (LY > 0) {
         const cuuint64_t dims[2] = {(cuuint64_t)a.COo, (cuuint64_t)rows * a.LY};   // Z[row][l][o]; one box = the F rows of a group
         const cuuint64_t str[1] = {(cuuint64_t)a.COo * 4};
         const cuuint32_t box[2] = {(cuuint32_t)a.COo, (cuuint32_t)(a.F * a.LY)};
-        if (!make_map(&mz, Z, 2, dims, str, box, false)) return fail(FNM_ECUDA, "pointwise_ysyn: tensor map (Z) failed");
+        if (!tc_make_map(&mz, Z, 2, dims, str, box, false)) return fail(FNM_ECUDA, "pointwise_ysyn: tensor map (Z) failed");
     }
     if (CI > 0) {
         const cuuint64_t dims[3] = {(cuuint64_t)a.CIo, (cuuint64_t)a.S2, (cuuint64_t)rows};
         const cuuint64_t str[2] = {(cuuint64_t)a.CIo * 4, (cuuint64_t)a.S2 * a.CIo * 4};
         const cuuint32_t box[3] = {32, (cuuint32_t)a.NT, 1};
-        if (!make_map(&mx, x, 3, dims, str, box, true)) return fail(FNM_ECUDA, "pointwise_ysyn: tensor map (x) failed");
+        if (!tc_make_map(&mx, x, 3, dims, str, box, true)) return fail(FNM_ECUDA, "pointwise_ysyn: tensor map (x) failed");
     } else {
         mx = mb;
     }

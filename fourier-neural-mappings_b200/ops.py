@@ -55,6 +55,20 @@ def _cplx(t):
     return torch.view_as_real(t.contiguous())
 
 
+def _grad_sink(w):
+    """The slot a FlatGradients(direct_spectral=True) registered for this weight, or None.  Called by the
+    wrappers at the bottom of this file BEFORE Function.apply (inside forward grad mode is always off), with
+    the module's Parameter object itself."""
+    sink = getattr(w, "_fnm_grad_sink", None) if w is not None else None
+    if sink is None or not (torch.is_grad_enabled() and w.requires_grad):
+        return None
+    if w._fnm_sink_uses:
+        raise RuntimeError("direct gradient sinks need every spectral weight to enter one autograd Function per "
+                           "step (and FlatGradients.zero_() before each backward)")
+    w._fnm_sink_uses = 1
+    return sink
+
+
 _WS = {}
 
 
@@ -78,7 +92,7 @@ class FourierLayerFn(torch.autograd.Function):
     (bare SpectralConv)."""
 
     @staticmethod
-    def forward(ctx, zin, xact, w0, w1, wc, bc, tables, act_in, want_act_out):
+    def forward(ctx, zin, xact, w0, w1, wc, bc, tables, act_in, want_act_out, sinks=(None, None)):
         _need_cuda(zin, xact, w0, w1, wc, bc)
         cached = bool(act_in) and xact is not None
         xk = _f32c(xact) if cached else _f32c(zin)
@@ -103,6 +117,7 @@ class FourierLayerFn(torch.autograd.Function):
               "fnm_fourier_layer_fwd")
         ctx.save_for_backward(xk, _f32c(zin) if cached else None, w0, w1, wc, xh)
         ctx.tables, ctx.kact, ctx.has_bias = tables, kact, bc is not None
+        ctx.sinks = sinks
         if xo is not None:
             ctx.mark_non_differentiable(xo)
         return z, xo
@@ -118,8 +133,9 @@ class FourierLayerFn(torch.autograd.Function):
         need_x, _, need_w0, need_w1, need_wc, need_bc = ctx.needs_input_grad[:6]
         g_in = torch.empty_like(xk) if need_x else None
         want_w = need_w0 or (w1 is not None and need_w1)
-        dw0 = torch.empty_like(w0) if want_w else None
-        dw1 = torch.empty_like(w1) if (want_w and w1 is not None) else None
+        s0, s1 = ctx.sinks
+        dw0 = (s0 if s0 is not None else torch.empty_like(w0)) if want_w else None
+        dw1 = (s1 if s1 is not None else torch.empty_like(w1)) if (want_w and w1 is not None) else None
         dwc = torch.empty_like(wc) if (wc is not None and need_wc) else None
         dbc = torch.empty((Co,), dtype=torch.float32, device=xk.device) if (ctx.has_bias and need_bc) else None
         w0r = _cplx(w0)
@@ -133,14 +149,15 @@ class FourierLayerFn(torch.autograd.Function):
             _ptr(g_in), _ptr(torch.view_as_real(dw0)) if dw0 is not None else None,
             _ptr(torch.view_as_real(dw1)) if dw1 is not None else None, _ptr(dwc), _ptr(dbc),
             _ptr(ws), ws.numel(), _stream()), "fnm_fourier_layer_bwd")
-        return g_in, None, dw0, dw1, dwc, dbc, None, None, None
+        # a sink already holds the gradient: autograd gets None and runs no AccumulateGrad for that weight
+        return (g_in, None, None if s0 is not None else dw0, None if s1 is not None else dw1, dwc, dbc, None, None, None, None)
 
 
 class LinearFunctionalFn(torch.autograd.Function):
     """out[b, o] = F2V functional of f(zin) (LinearFunctionals1d/2d); ``xact`` = optional cached GELU(zin)."""
 
     @staticmethod
-    def forward(ctx, zin, xact, w, tables, act_in):
+    def forward(ctx, zin, xact, w, tables, act_in, sink=None):
         _need_cuda(zin, xact, w)
         cached = bool(act_in) and xact is not None
         xk = _f32c(xact) if cached else _f32c(zin)
@@ -159,6 +176,7 @@ class LinearFunctionalFn(torch.autograd.Function):
                               _ptr(ws), ws.numel(), _stream()), "fnm_lfunc_fwd")
         ctx.save_for_backward(xk, _f32c(zin) if cached else None, w, xh)
         ctx.tables, ctx.kact = tables, kact
+        ctx.sink = sink
         return out
 
     @staticmethod
@@ -171,20 +189,20 @@ class LinearFunctionalFn(torch.autograd.Function):
         plan = tables.c_plan(xk.device, B, Ci, Co, _MODE)
         cc = tables.device(xk.device)["cc"]
         g_in = torch.empty_like(xk) if ctx.needs_input_grad[0] else None
-        dw = torch.empty_like(w) if ctx.needs_input_grad[2] else None
+        dw = (ctx.sink if ctx.sink is not None else torch.empty_like(w)) if ctx.needs_input_grad[2] else None
         L = lib()
         ws = _workspace(xk.device, L.fnm_lfunc_workspace_bytes(C.byref(plan)))
         check(L.fnm_lfunc_bwd(C.byref(plan), _ptr(g), _ptr(xk), ctx.kact, _ptr(zpre), _ptr(_cplx(w)), _ptr(cc), _ptr(xh),
                               _ptr(g_in), _ptr(torch.view_as_real(dw)) if dw is not None else None,
                               _ptr(ws), ws.numel(), _stream()), "fnm_lfunc_bwd")
-        return g_in, None, dw, None, None
+        return g_in, None, None if ctx.sink is not None else dw, None, None, None
 
 
 class LinearDecoderFn(torch.autograd.Function):
     """y[b, x, y, o] = V2F decoder of the vector v[b, i] (LinearDecoder1d/2d)."""
 
     @staticmethod
-    def forward(ctx, v, w, tables):
+    def forward(ctx, v, w, tables, sink=None):
         _need_cuda(v, w)
         v = _f32c(v)
         B, Ci = v.shape
@@ -199,6 +217,7 @@ class LinearDecoderFn(torch.autograd.Function):
               "fnm_ldec_fwd")
         ctx.save_for_backward(v, w)
         ctx.tables = tables
+        ctx.sink = sink
         return y
 
     @staticmethod
@@ -210,13 +229,13 @@ class LinearDecoderFn(torch.autograd.Function):
         Co = w.shape[1]
         plan = tables.c_plan(v.device, B, Ci, Co, _MODE)
         gv = torch.empty_like(v) if ctx.needs_input_grad[0] else None
-        dw = torch.empty_like(w) if ctx.needs_input_grad[1] else None
+        dw = (ctx.sink if ctx.sink is not None else torch.empty_like(w)) if ctx.needs_input_grad[1] else None
         L = lib()
         ws = _workspace(v.device, L.fnm_ldec_workspace_bytes(C.byref(plan)))
         check(L.fnm_ldec_bwd(C.byref(plan), _ptr(gy), _ptr(v), _ptr(_cplx(w)), _ptr(gv),
                              _ptr(torch.view_as_real(dw)) if dw is not None else None,
                              _ptr(ws), ws.numel(), _stream()), "fnm_ldec_bwd")
-        return gv, dw, None
+        return gv, None if ctx.sink is not None else dw, None, None
 
 
 class GeluFn(torch.autograd.Function):
@@ -438,15 +457,15 @@ def mlp_head(h1, w2, b2):
 
 def fourier_layer(zin, w0, w1, wc, bc, tables, act_in=False, xact=None, want_act_out=False):
     """Returns (z, GELU(z) or None).  ``zin`` is the layer input (pre-activation if act_in)."""
-    return FourierLayerFn.apply(zin, xact, w0, w1, wc, bc, tables, act_in, want_act_out)
+    return FourierLayerFn.apply(zin, xact, w0, w1, wc, bc, tables, act_in, want_act_out, (_grad_sink(w0), _grad_sink(w1)))
 
 
 def linear_functional(zin, w, tables, act_in=False, xact=None):
-    return LinearFunctionalFn.apply(zin, xact, w, tables, act_in)
+    return LinearFunctionalFn.apply(zin, xact, w, tables, act_in, _grad_sink(w))
 
 
 def linear_decoder(v, w, tables):
-    return LinearDecoderFn.apply(v, w, tables)
+    return LinearDecoderFn.apply(v, w, tables, _grad_sink(w))
 
 
 def gelu(z):

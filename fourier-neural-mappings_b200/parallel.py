@@ -16,12 +16,21 @@ import torch.distributed as dist
 
 
 class FlatGradients:
-    """Owns the flat gradient buffer of ``params`` and keeps ``p.grad`` pointing into it."""
+    """Owns the flat gradient buffer of ``params`` and keeps ``p.grad`` pointing into it.
 
-    def __init__(self, params):
+    ``direct_spectral=True`` additionally makes the complex (spectral) weights' slots *gradient sinks*: the
+    backward kernels of ops.py write dW straight into the slot and hand autograd no gradient, which removes
+    the AccumulateGrad pass (read dW, read grad, write grad: 3 x 1.07 GB at config 5) and lets ``zero_`` skip
+    those slots.  It assumes what holds for every model here: each spectral weight enters exactly one
+    autograd Function per step and ``zero_()`` is called before every backward (a second use raises)."""
+
+    def __init__(self, params, direct_spectral=False):
         self.params = [p for p in params if p.requires_grad]
         if not self.params:
             raise ValueError("no trainable parameters")
+        self.direct = bool(direct_spectral)
+        if self.direct:                                        # sinks last: zero_ is one memset of the head
+            self.params.sort(key=lambda p: p.is_complex())
         dev = self.params[0].device
         self.offsets, total = [], 0
         for p in self.params:
@@ -31,6 +40,8 @@ class FlatGradients:
             self.offsets.append((total, n))
             total += (n + 63) // 64 * 64                     # 256-byte aligned slots
         self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
+        firsts = [off for p, (off, _) in zip(self.params, self.offsets) if p.is_complex()]
+        self.head = firsts[0] if (self.direct and firsts) else total      # floats that zero_ clears
         self.attach()
 
     def attach(self):
@@ -38,14 +49,20 @@ class FlatGradients:
             chunk = self.flat[off:off + n]
             view = torch.view_as_complex(chunk.view(-1, 2)).view(p.shape) if p.is_complex() else chunk.view(p.shape)
             p.grad = view
+            if self.direct and p.is_complex():
+                p._fnm_grad_sink, p._fnm_sink_uses = view, 0
 
     def zero_(self):
         """Replacement for ``optimizer.zero_grad()``: keeps the views alive (set_to_none would drop them)."""
-        self.flat.zero_()
+        self.flat[:self.head].zero_()
         for p in self.params:
             if p.grad is None:
                 self.attach()
                 break
+        if self.direct:
+            for p in self.params:
+                if p.is_complex():
+                    p._fnm_sink_uses = 0
 
     def all_reduce(self, group=None, async_op=False):
         """SUM over ranks; no-op in a single-process run."""

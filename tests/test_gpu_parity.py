@@ -366,3 +366,44 @@ def test_config5_full_size_train_step_vs_oracle():
         grads = dict(model.named_parameters())
         for k in late:
             assert_parity(grads[k].grad, p[k].grad, p64[k].grad, what=k)
+
+
+@pytest.mark.parametrize("family", ["fno2d", "fnf2d", "fnd2d"])
+def test_direct_gradient_sinks_match_autograd_accumulation(family):
+    """FlatGradients(direct_spectral=True): the backward kernels write the spectral-weight gradients straight into
+    the flat buffer (no AccumulateGrad pass).  Gradients and parameters after two Adam steps must be bit-identical
+    to the default path, and a second use of a weight without zero_() must raise."""
+    ctor = {"fno2d": lambda: fnm_b200.FNO2d(4, 4, 32, n_layers=3, width_final=32),
+            "fnf2d": lambda: fnm_b200.FNF2d(4, 4, 32, width_final=32, d_out=3, n_layers=3),
+            "fnd2d": lambda: fnm_b200.FND2d(6, (24, 24), modes1=4, modes2=4, width=32, width_initial=32, width_final=32,
+                                            n_layers=3)}[family]
+    torch.manual_seed(3)
+    x = torch.randn(3, 6, device=DEV) if family == "fnd2d" else torch.randn(3, 1, 24, 24, device=DEV)
+    results = []
+    for direct in (False, True):
+        torch.manual_seed(11)
+        model = ctor().to(DEV)
+        opt = fnm_b200.Adam(model.parameters(), lr=1e-3, weight_decay=1e-4)
+        grads = fnm_b200.parallel.FlatGradients(model.parameters(), direct_spectral=direct)
+        y = None
+        for _ in range(2):
+            grads.zero_()
+            out = model(x)
+            y = torch.ones_like(out) if y is None else y
+            fnm_b200.parallel.rel_l2_sum(out, y).backward()
+            g = {k: p.grad.clone() for k, p in model.named_parameters()}
+            opt.step()
+        results.append((g, {k: v.clone() for k, v in model.state_dict().items()}))
+        if direct:
+            assert all(p._fnm_sink_uses == 1 for p in model.parameters() if p.is_complex())   # the sinks were used
+            with pytest.raises(RuntimeError):
+                model(x)                                       # second use without zero_()
+            with torch.no_grad():
+                model(x)                                       # inference does not touch the sinks
+    (g0, w0), (g1, w1) = results
+    for k in g0:
+        assert torch.equal(torch.view_as_real(g0[k]) if g0[k].is_complex() else g0[k],
+                           torch.view_as_real(g1[k]) if g1[k].is_complex() else g1[k]), k
+    for k in w0:
+        assert torch.equal(torch.view_as_real(w0[k]) if w0[k].is_complex() else w0[k],
+                           torch.view_as_real(w1[k]) if w1[k].is_complex() else w1[k]), k
