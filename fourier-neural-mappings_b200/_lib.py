@@ -23,7 +23,7 @@ class FnmPlan(C.Structure):
                 ("R", C.c_int32), ("NY", C.c_int32), ("Ci", C.c_int32), ("Co", C.c_int32),
                 ("rows_per_w", C.c_int32), ("mode", C.c_int32), ("reserved", C.c_int32),
                 ("ay", _vp), ("ayT", _vp), ("by", _vp), ("byT", _vp),
-                ("ex", _vp), ("fx", _vp), ("exb", _vp), ("fxb", _vp)]
+                ("ex", _vp), ("fx", _vp), ("exb", _vp), ("fxb", _vp), ("w_shadow", _vp)]
 
 
 _PP = C.POINTER(FnmPlan)
@@ -37,6 +37,7 @@ PROTOTYPES = {
     "fnm_profile_begin": (_i32, []),
     "fnm_profile_end": (_sz, [C.c_char_p, _sz]),
     "fnm_fourier_layer_workspace_bytes": (_sz, [_PP]),
+    "fnm_fourier_layer_shadow_bytes": (_sz, [_PP]),
     "fnm_fourier_layer_fwd": (_i32, [_PP, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "fnm_fourier_layer_bwd": (_i32, [_PP, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "fnm_lfunc_workspace_bytes": (_sz, [_PP]),

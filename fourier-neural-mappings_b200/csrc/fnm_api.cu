@@ -211,7 +211,7 @@ int fnm_mix_fwd(const float* Xh, const float* w0, const float* w1, int rows_per_
     if (mix_use_tc(B, R, NY, Ci, Co, workspace, workspace_bytes)) {
         float* W1 = static_cast<float*>(workspace);
         FNM_TRY(tc_mix_pack(w0, w1, rows_per_w, R, NY, Ci, Co, 0, W1, as_stream(stream)));
-        return tc_mix_apply(W1, Xh, Oh, R * NY, B, Ci, Co, 0, mode, "mix_fwd", as_stream(stream));
+        return tc_mix_apply(W1, Xh, Oh, R * NY, B, Ci, Co, 0, 0, mode, "mix_fwd", as_stream(stream));
     }
     return simt_mix_fwd(Xh, w0, w1, rows_per_w, Oh, B, R, NY, Ci, Co, as_stream(stream));
 }
@@ -221,9 +221,11 @@ int fnm_mix_bwd_x(const float* Gh, const float* w0, const float* w1, int rows_pe
     FNM_REQUIRE(Gh && w0 && Gxh, "mix_bwd_x: NULL pointer");
     FNM_REQUIRE(rows_per_w == R || (w1 && 2 * rows_per_w == R), "mix_bwd_x: weight rows do not cover R");
     if (mix_use_tc(B, R, NY, Ci, Co, workspace, workspace_bytes)) {
-        float* W2 = static_cast<float*>(workspace);
-        FNM_TRY(tc_mix_pack(w0, w1, rows_per_w, R, NY, Ci, Co, 1, W2, as_stream(stream)));
-        return tc_mix_apply(W2, Gh, Gxh, R * NY, B, Co, Ci, 1, mode, "mix_bwd_x", as_stream(stream));
+        // the same mode-major copy W1[m][i][o] as the forward when its rows can be read with 16-byte loads
+        const int w1_layout = Co % 2 == 0 ? 1 : 0;
+        float* Wm = static_cast<float*>(workspace);
+        FNM_TRY(tc_mix_pack(w0, w1, rows_per_w, R, NY, Ci, Co, w1_layout ? 0 : 1, Wm, as_stream(stream)));
+        return tc_mix_apply(Wm, Gh, Gxh, R * NY, B, Co, Ci, 1, w1_layout, mode, "mix_bwd_x", as_stream(stream));
     }
     return simt_mix_bwd_x(Gh, w0, w1, rows_per_w, Gxh, B, R, NY, Ci, Co, as_stream(stream));
 }
@@ -295,6 +297,11 @@ int fnm_counter_inc(int32_t* counter, fnm_stream_t stream) {
 // ------------------------------------------------------------------------------------------------
 // fused Fourier layer
 // ------------------------------------------------------------------------------------------------
+size_t fnm_fourier_layer_shadow_bytes(const fnm_plan* plan) {
+    if (!plan || plan->Co % 2 != 0) return 0;
+    return layer_ws(plan).shadow * sizeof(float);
+}
+
 size_t fnm_fourier_layer_workspace_bytes(const fnm_plan* plan) {
     if (!plan) return 0;
     const LayerWs w = layer_ws(plan);
@@ -320,9 +327,10 @@ int fnm_fourier_layer_fwd(const fnm_plan* p, const float* xin, int act_in, const
     FNM_TRY(fnm_ydft(xin, p->ay, T, (int64_t)p->B * p->P1, p->P2, LY, p->Ci, act_in, p->mode, stream));
     FNM_TRY(fnm_xdft(T, p->ex, xh_save, p->B, p->P1, p->R, p->NY, p->Ci, p->mode, stream));
     if (w.shadow) {
-        float* W1 = cv.take(w.shadow);
+        // mode-major weight copy: into the caller's persistent buffer when given (backward then reuses it)
+        float* W1 = p->w_shadow ? p->w_shadow : cv.take(w.shadow);
         FNM_TRY(tc_mix_pack(w0, w1, p->rows_per_w, p->R, p->NY, p->Ci, p->Co, 0, W1, st));
-        FNM_TRY(tc_mix_apply(W1, xh_save, Oh, p->R * p->NY, p->B, p->Ci, p->Co, 0, p->mode, "mix_fwd", st));
+        FNM_TRY(tc_mix_apply(W1, xh_save, Oh, p->R * p->NY, p->B, p->Ci, p->Co, 0, 0, p->mode, "mix_fwd", st));
     } else {
         FNM_TRY(simt_mix_fwd(xh_save, w0, w1, p->rows_per_w, Oh, p->B, p->R, p->NY, p->Ci, p->Co, st));
     }
@@ -366,8 +374,11 @@ int fnm_fourier_layer_bwd(const fnm_plan* p, const float* g_z, const float* xin,
         FNM_TRY(conv_wgrad(g_z, xin, act_in, dwc, dbc, (int64_t)p->B * p->S1 * p->S2, p->Ci, p->Co, partial, p->mode, st));
     if (g_in) {
         if (w.shadow) {
-            FNM_TRY(tc_mix_pack(w0, w1, p->rows_per_w, p->R, p->NY, p->Ci, p->Co, 1, shadowB, st));
-            FNM_TRY(tc_mix_apply(shadowB, Gh, Gxh, p->R * p->NY, p->B, p->Co, p->Ci, 1, p->mode, "mix_bwd_x", st));
+            const int w1_layout = p->Co % 2 == 0 ? 1 : 0;
+            const float* Wm = shadowB;
+            if (w1_layout && p->w_shadow) Wm = p->w_shadow;       // the forward's copy, still valid: no second permute
+            else FNM_TRY(tc_mix_pack(w0, w1, p->rows_per_w, p->R, p->NY, p->Ci, p->Co, w1_layout ? 0 : 1, shadowB, st));
+            FNM_TRY(tc_mix_apply(Wm, Gh, Gxh, p->R * p->NY, p->B, p->Co, p->Ci, 1, w1_layout, p->mode, "mix_bwd_x", st));
         } else {
             FNM_TRY(simt_mix_bwd_x(Gh, w0, w1, p->rows_per_w, Gxh, p->B, p->R, p->NY, p->Ci, p->Co, st));
         }

@@ -56,7 +56,7 @@ size_t tc_mix_shadow_floats(int nmodes, int Ci, int Co);
 int tc_mix_pack(const float* w0, const float* w1, int rpw, int R, int NY, int Ci, int Co, int which, float* dst,
                 cudaStream_t st);
 int tc_mix_unpack(const float* dW1, float* dw0, float* dw1, int rpw, int R, int NY, int Ci, int Co, cudaStream_t st);
-int tc_mix_apply(const float* Wm, const float* In, float* Out, int nmodes, int B, int Kt, int Lt, int conj, int mode,
+int tc_mix_apply(const float* Wm, const float* In, float* Out, int nmodes, int B, int Kt, int Lt, int conj, int w_is_w1, int mode,
                  const char* what, cudaStream_t st);
 int tc_mix_wgrad(const float* Xh, const float* Gh, float* dW1, int nmodes, int B, int Ci, int Co, int mode, cudaStream_t st);
 bool tc_conv_wgrad_supported(int64_t npos, int Ci, int Co);

@@ -41,6 +41,7 @@ struct MxArgs {
     int Kt, Lt, Nt;                                        // contraction length, lanes (<= 128), n extent
     int nmodes, ntiles, items, nchunks;
     int conj, single_pass, a_pair, b_kcontig, o_pair;      // a_pair / o_pair: (re, im) adjacent -> 8-byte accesses
+    int a_kc;                                              // A element (m, k, l) has k contiguous as (re, im) pairs: each lane reads its own 256-byte row
     int a_reuse;                                           // one A chunk per mode, kept in TMEM across the mode's n tiles
     int b_tma;                                             // B rows are K-contiguous and 16-byte aligned: TMA brings the raw tile
 };
@@ -323,7 +324,18 @@ __global__ void __launch_bounds__(kMxThreads, 1) mixgemm_tc(const __grid_constan
             const float* p = a.a + (size_t)m * a.a_sm + (size_t)(ch * 32) * a.a_sk + (size_t)L * a.a_sl;
             const int klim = l_ok ? a.Kt - ch * 32 : 0;
             float vr[32], vi[32];
-            if (a.a_pair) {
+            if (a.a_kc) {
+                // backward-x on the FORWARD's mode-major copy W1[m][i][o] (lanes = i, k = o): a lane's 32 (re, im) pairs
+                // are one 256-byte run; L1 keeps the sectors between the two 16-byte loads that share them
+                const float4* p4 = reinterpret_cast<const float4*>(a.a + (size_t)m * a.a_sm + (size_t)L * a.a_sl + (size_t)(ch * 32) * 2);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (2 * j < klim) v = __ldg(p4 + j);
+                    vr[2 * j] = v.x; vi[2 * j] = v.y;
+                    vr[2 * j + 1] = 2 * j + 1 < klim ? v.z : 0.f; vi[2 * j + 1] = 2 * j + 1 < klim ? v.w : 0.f;
+                }
+            } else if (a.a_pair) {
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
                     float2 v = make_float2(0.f, 0.f);
@@ -464,14 +476,16 @@ int tc_mix_unpack(const float* dW1, float* dw0, float* dw1, int rpw, int R, int 
     return check_launch("mix_unpack");
 }
 
-// Oh[m][ro][b][o] = sum_i Xh[m][ri][b][i] W1[m][i][o]      (conj = 0, W = W1, Kt = Ci, Lt = Co)
-// Gxh[m][ri][b][i] = sum_o Gh[m][ro][b][o] conj(W2[m][o][i]) (conj = 1, W = W2, Kt = Co, Lt = Ci)
-int tc_mix_apply(const float* Wm, const float* In, float* Out, int nmodes, int B, int Kt, int Lt, int conj, int mode,
-                 const char* what, cudaStream_t st) {
+// Oh[m][ro][b][o] = sum_i Xh[m][ri][b][i] W1[m][i][o]        (conj = 0, W = W1, Kt = Ci, Lt = Co)
+// Gxh[m][ri][b][i] = sum_o Gh[m][ro][b][o] conj(W[i][o][m])   (conj = 1, Kt = Co, Lt = Ci) with W given either as
+//   W2[m][o][i] (w_is_w1 = 0) or as the forward's copy W1[m][i][o] (w_is_w1 = 1: lanes read k-contiguous rows)
+int tc_mix_apply(const float* Wm, const float* In, float* Out, int nmodes, int B, int Kt, int Lt, int conj, int w_is_w1,
+                 int mode, const char* what, cudaStream_t st) {
     MxArgs a{};
     a.a = Wm; a.b = In; a.out = Out;
     a.Kt = Kt; a.Lt = Lt; a.Nt = B; a.nmodes = nmodes;
     a.a_sm = (long long)Kt * Lt * 2; a.a_sk = (long long)Lt * 2; a.a_sl = 2; a.a_im = 1; a.a_pair = 1;
+    if (conj && w_is_w1) { a.a_sk = 2; a.a_sl = (long long)Kt * 2; a.a_kc = 1; }
     a.b_sm = (long long)2 * B * Kt; a.b_sn = Kt; a.b_sk = 1; a.b_im = (long long)B * Kt; a.b_kcontig = 1;
     a.o_sm = (long long)2 * B * Lt; a.o_sn = Lt; a.o_sl = 1; a.o_im = (long long)B * Lt; a.o_pair = 0;
     a.conj = conj; a.single_pass = mode == FNM_MODE_TF32;

@@ -112,12 +112,24 @@ class FourierLayerFn(torch.autograd.Function):
         L = lib()
         nbytes = L.fnm_fourier_layer_workspace_bytes(C.byref(plan))
         ws = _workspace(xk.device, nbytes)
+        # training: the mode-major weight copy made here is kept for backward (one permute per layer and step)
+        wsh = None
+        if any(ctx.needs_input_grad[:6]):
+            nsh = L.fnm_fourier_layer_shadow_bytes(C.byref(plan))
+            if nsh:
+                wsh = torch.empty(nsh, dtype=torch.uint8, device=xk.device)
+                plan.w_shadow = wsh.data_ptr()
+        ctx.wsh = wsh
         check(L.fnm_fourier_layer_fwd(C.byref(plan), _ptr(xk), kact, _ptr(w0r), _ptr(w1r), _ptr(wcc), _ptr(bcc),
                                       _ptr(z), _ptr(xo), _ptr(xh), _ptr(ws), ws.numel(), _stream()),
               "fnm_fourier_layer_fwd")
         ctx.save_for_backward(xk, _f32c(zin) if cached else None, w0, w1, wc, xh)
         ctx.tables, ctx.kact, ctx.has_bias = tables, kact, bc is not None
         ctx.sinks = sinks
+        ctx.w_version = (w0._version, w1._version if w1 is not None else 0)
+        # the GELU copy carries no gradient: without this autograd would MATERIALISE a zero tensor of its size
+        # (one activation-sized fill per layer) just to hand it to backward
+        ctx.set_materialize_grads(False)
         if xo is not None:
             ctx.mark_non_differentiable(xo)
         return z, xo
@@ -126,10 +138,17 @@ class FourierLayerFn(torch.autograd.Function):
     def backward(ctx, gz, _gxo=None):
         xk, zpre, w0, w1, wc, xh = ctx.saved_tensors
         tables = ctx.tables
+        if gz is None:                                          # z did not reach the loss
+            for sink in ctx.sinks:
+                if sink is not None:
+                    sink.zero_()                                # a sink must not keep the previous step's gradient
+            return (None,) * 10
         gz = _f32c(gz)
         B, P1, P2, Ci = xk.shape
         Co = w0.shape[1]
         plan = tables.c_plan(xk.device, B, Ci, Co, _MODE)
+        if ctx.wsh is not None and (w0._version, w1._version if w1 is not None else 0) == ctx.w_version:      # weights not modified in place since forward
+            plan.w_shadow = ctx.wsh.data_ptr()
         need_x, _, need_w0, need_w1, need_wc, need_bc = ctx.needs_input_grad[:6]
         g_in = torch.empty_like(xk) if need_x else None
         want_w = need_w0 or (w1 is not None and need_w1)

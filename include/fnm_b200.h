@@ -70,6 +70,11 @@ typedef struct fnm_plan {
     int32_t mode;                           /* FNM_MODE_* */
     int32_t reserved;
     const float *ay, *ayT, *by, *byT, *ex, *fx, *exb, *fxb;
+    float* w_shadow;                        /* optional (fused Fourier layer only): caller-owned buffer of
+                                               fnm_fourier_layer_shadow_bytes() that receives the mode-major copy of
+                                               the spectral weights in forward; handing the SAME buffer (untouched,
+                                               weights unchanged) to backward saves its weight permute.  NULL: both
+                                               passes permute into the workspace. */
 } fnm_plan;
 
 const char* fnm_version(void);
@@ -99,6 +104,7 @@ size_t fnm_profile_end(char* buf, size_t n);
  *      tensor as xin and act_in = 0 (measured on B200: GELU-on-load in every consumer costs more
  *      issue slots than the extra write costs HBM time).                                          */
 size_t fnm_fourier_layer_workspace_bytes(const fnm_plan* plan);
+size_t fnm_fourier_layer_shadow_bytes(const fnm_plan* plan);      /* 0: this shape does not use a weight copy */
 int fnm_fourier_layer_fwd(const fnm_plan* plan, const float* xin, int act_in,
                           const float* w0, const float* w1,          /* complex (Ci,Co,rows_per_w,NY) */
                           const float* wc, const float* bc,          /* (Co,Ci), (Co) or NULL */

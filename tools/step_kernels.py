@@ -13,7 +13,7 @@ dev = torch.device("cuda")
 torch.manual_seed(0)
 model = fnm_b200.FNO2d(32, 32, 128).to(dev)
 opt = fnm_b200.Adam(model.parameters(), lr=1e-3, weight_decay=1e-4)
-grads = FlatGradients(model.parameters())
+grads = FlatGradients(model.parameters(), direct_spectral=True)
 x = torch.randn(32, 1, 256, 256, device=dev)
 y = torch.randn(32, 1, 256, 256, device=dev)
 
@@ -29,7 +29,7 @@ def step():
 for _ in range(3):
     step()
 torch.cuda.synchronize()
-with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU], record_shapes=True, with_stack=False) as prof:
     step()
     torch.cuda.synchronize()
 rows = [(e.key, e.count, e.device_time_total / 1e3) for e in prof.key_averages() if e.device_time_total > 0 and e.device_type.name == "CUDA"]
@@ -38,3 +38,8 @@ tot = sum(r[2] for r in rows)
 print(f"total kernel time {tot:.2f} ms")
 for k, n, ms in rows[:40]:
     print(f"{ms:8.3f} ms  x{n:<3d} {k[:110]}")
+
+print("fills / zeros / adds by input shape:")
+for e in prof.key_averages(group_by_input_shape=True):
+    if e.key in ("aten::fill_", "aten::zero_", "aten::zeros", "aten::zeros_like", "aten::add_", "aten::add", "aten::copy_") and e.device_time_total > 5:
+        print(f"  {e.key:18s} x{e.count:<3d} {e.device_time_total / 1e3:7.3f} ms  {e.input_shapes}")
