@@ -11,6 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libfnm_b200.so")
 CSRC_DIR = os.path.join(_HERE, "csrc")
 
+FNM_W_REFERENCE, FNM_W_MODE_MAJOR = 0, 1
 FNM_MODE_FP32 = 0
 FNM_MODE_TF32 = 1
 ADAM_MAX_TENSORS = 48
@@ -21,7 +22,7 @@ _vp, _i32, _i64, _sz, _dbl = C.c_void_p, C.c_int, C.c_int64, C.c_size_t, C.c_dou
 class FnmPlan(C.Structure):
     _fields_ = [("B", C.c_int32), ("P1", C.c_int32), ("P2", C.c_int32), ("S1", C.c_int32), ("S2", C.c_int32),
                 ("R", C.c_int32), ("NY", C.c_int32), ("Ci", C.c_int32), ("Co", C.c_int32),
-                ("rows_per_w", C.c_int32), ("mode", C.c_int32), ("reserved", C.c_int32),
+                ("rows_per_w", C.c_int32), ("mode", C.c_int32), ("w_layout", C.c_int32),
                 ("ay", _vp), ("ayT", _vp), ("by", _vp), ("byT", _vp),
                 ("ex", _vp), ("fx", _vp), ("exb", _vp), ("fxb", _vp), ("w_shadow", _vp)]
 

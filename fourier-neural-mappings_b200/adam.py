@@ -12,6 +12,7 @@ import ctypes as C
 import torch
 from torch.optim.optimizer import Optimizer
 
+from .parallel import _dense
 from ._lib import FnmError, check, lib
 
 
@@ -81,16 +82,24 @@ class Adam(Optimizer):
         keep = []                      # float views must outlive the launch call
 
         def table(tensors):
+            # the update is elementwise over STORAGE: parameter, gradient and state must be dense and share one memory
+            # order (the spectral weights are stored mode-major, their state is created with preserve_format)
             views = []
-            for t in tensors:
-                if not t.is_contiguous():
-                    raise FnmError("fnm_b200.Adam needs contiguous parameters, gradients and state")
+            for t, p in zip(tensors, plist):
+                if t.stride() != p.stride() or not _dense(p):
+                    raise FnmError("fnm_b200.Adam needs dense parameters whose gradients and state share their memory order")
                 views.append(_as_float_view(t))
             keep.extend(views)
             return vp(*[v.data_ptr() for v in views])
 
+        def grad_of(p):
+            g = p.grad if p.grad.dtype == p.dtype else p.grad.to(p.dtype)
+            if g.stride() != p.stride():                       # e.g. a contiguous gradient for a mode-major weight
+                g = torch.empty_like(p, memory_format=torch.preserve_format).copy_(g)
+            return g
+
         p_tab = table([p.data for p in plist])
-        g_tab = table([p.grad if p.grad.dtype == p.dtype else p.grad.to(p.dtype) for p in plist])
+        g_tab = table([grad_of(p) for p in plist])
         m_tab = table([self.state[p]["exp_avg"] for p in plist])
         v_tab = table([self.state[p]["exp_avg_sq"] for p in plist])
         x_tab = table([self.state[p]["max_exp_avg_sq"] for p in plist]) if group["amsgrad"] else None

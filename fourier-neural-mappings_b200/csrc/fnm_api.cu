@@ -211,7 +211,7 @@ int fnm_mix_fwd(const float* Xh, const float* w0, const float* w1, int rows_per_
     if (mix_use_tc(B, R, NY, Ci, Co, workspace, workspace_bytes)) {
         float* W1 = static_cast<float*>(workspace);
         FNM_TRY(tc_mix_pack(w0, w1, rows_per_w, R, NY, Ci, Co, 0, W1, as_stream(stream)));
-        return tc_mix_apply(W1, Xh, Oh, R * NY, B, Ci, Co, 0, 0, mode, "mix_fwd", as_stream(stream));
+        return tc_mix_apply(W1, nullptr, 0, Xh, Oh, R * NY, B, Ci, Co, 0, 0, mode, "mix_fwd", as_stream(stream));
     }
     return simt_mix_fwd(Xh, w0, w1, rows_per_w, Oh, B, R, NY, Ci, Co, as_stream(stream));
 }
@@ -225,7 +225,7 @@ int fnm_mix_bwd_x(const float* Gh, const float* w0, const float* w1, int rows_pe
         const int w1_layout = Co % 2 == 0 ? 1 : 0;
         float* Wm = static_cast<float*>(workspace);
         FNM_TRY(tc_mix_pack(w0, w1, rows_per_w, R, NY, Ci, Co, w1_layout ? 0 : 1, Wm, as_stream(stream)));
-        return tc_mix_apply(Wm, Gh, Gxh, R * NY, B, Co, Ci, 1, w1_layout, mode, "mix_bwd_x", as_stream(stream));
+        return tc_mix_apply(Wm, nullptr, 0, Gh, Gxh, R * NY, B, Co, Ci, 1, w1_layout, mode, "mix_bwd_x", as_stream(stream));
     }
     return simt_mix_bwd_x(Gh, w0, w1, rows_per_w, Gxh, B, R, NY, Ci, Co, as_stream(stream));
 }
@@ -236,7 +236,7 @@ int fnm_mix_bwd_w(const float* Xh, const float* Gh, float* dw0, float* dw1, int 
     FNM_REQUIRE(rows_per_w == R || (dw1 && 2 * rows_per_w == R), "mix_bwd_w: weight rows do not cover R");
     if (mix_use_tc(B, R, NY, Ci, Co, workspace, workspace_bytes)) {
         float* dW1 = static_cast<float*>(workspace);
-        FNM_TRY(tc_mix_wgrad(Xh, Gh, dW1, R * NY, B, Ci, Co, mode, as_stream(stream)));
+        FNM_TRY(tc_mix_wgrad(Xh, Gh, dW1, nullptr, 0, R * NY, B, Ci, Co, mode, as_stream(stream)));
         return tc_mix_unpack(dW1, dw0, dw1, rows_per_w, R, NY, Ci, Co, as_stream(stream));
     }
     return simt_mix_bwd_w(Xh, Gh, dw0, dw1, rows_per_w, B, R, NY, Ci, Co, as_stream(stream));
@@ -298,7 +298,7 @@ int fnm_counter_inc(int32_t* counter, fnm_stream_t stream) {
 // fused Fourier layer
 // ------------------------------------------------------------------------------------------------
 size_t fnm_fourier_layer_shadow_bytes(const fnm_plan* plan) {
-    if (!plan || plan->Co % 2 != 0) return 0;
+    if (!plan || plan->Co % 2 != 0 || plan->w_layout == FNM_W_MODE_MAJOR) return 0;
     return layer_ws(plan).shadow * sizeof(float);
 }
 
@@ -326,13 +326,18 @@ int fnm_fourier_layer_fwd(const fnm_plan* p, const float* xin, int act_in, const
     const int LY = 2 * p->NY;
     FNM_TRY(fnm_ydft(xin, p->ay, T, (int64_t)p->B * p->P1, p->P2, LY, p->Ci, act_in, p->mode, stream));
     FNM_TRY(fnm_xdft(T, p->ex, xh_save, p->B, p->P1, p->R, p->NY, p->Ci, p->mode, stream));
-    if (w.shadow) {
+    const int mm = p->w_layout == FNM_W_MODE_MAJOR;
+    const int nmodes = p->R * p->NY, m_split = p->rows_per_w * p->NY;
+    if (w.shadow && mm) {
+        // parameters already mode-major: the kernel reads them in place (weights1 | weights2 = two arrays)
+        FNM_TRY(tc_mix_apply(w0, w1, m_split, xh_save, Oh, nmodes, p->B, p->Ci, p->Co, 0, 0, p->mode, "mix_fwd", st));
+    } else if (w.shadow) {
         // mode-major weight copy: into the caller's persistent buffer when given (backward then reuses it)
         float* W1 = p->w_shadow ? p->w_shadow : cv.take(w.shadow);
         FNM_TRY(tc_mix_pack(w0, w1, p->rows_per_w, p->R, p->NY, p->Ci, p->Co, 0, W1, st));
-        FNM_TRY(tc_mix_apply(W1, xh_save, Oh, p->R * p->NY, p->B, p->Ci, p->Co, 0, 0, p->mode, "mix_fwd", st));
+        FNM_TRY(tc_mix_apply(W1, nullptr, 0, xh_save, Oh, nmodes, p->B, p->Ci, p->Co, 0, 0, p->mode, "mix_fwd", st));
     } else {
-        FNM_TRY(simt_mix_fwd(xh_save, w0, w1, p->rows_per_w, Oh, p->B, p->R, p->NY, p->Ci, p->Co, st));
+        FNM_TRY(simt_mix_fwd(xh_save, w0, w1, p->rows_per_w, Oh, p->B, p->R, p->NY, p->Ci, p->Co, st, mm));
     }
     FNM_TRY(fnm_xsyn(Oh, p->fx, Z, p->B, p->S1, p->R, p->NY, p->Co, p->mode, stream));
     return fnm_pointwise_ysyn(wc ? xin : nullptr, act_in, wc, 0, bc, Z, p->by, nullptr, z_out, x_act_out,
@@ -362,25 +367,31 @@ int fnm_fourier_layer_bwd(const fnm_plan* p, const float* g_z, const float* xin,
     FNM_TRY(fnm_xdft(Tg, p->exb, Gh, p->B, p->S1, p->R, p->NY, p->Co, p->mode, stream));
     float* shadowA = w.shadow ? cv.take(w.shadow) : nullptr;
     float* shadowB = w.shadow ? cv.take(w.shadow) : nullptr;
+    const int mm = p->w_layout == FNM_W_MODE_MAJOR;
+    const int nmodes = p->R * p->NY, m_split = p->rows_per_w * p->NY;
     if (dw0) {
-        if (w.shadow) {
-            FNM_TRY(tc_mix_wgrad(xh_save, Gh, shadowA, p->R * p->NY, p->B, p->Ci, p->Co, p->mode, st));
+        if (w.shadow && mm) {
+            FNM_TRY(tc_mix_wgrad(xh_save, Gh, dw0, dw1, m_split, nmodes, p->B, p->Ci, p->Co, p->mode, st));   // written in place
+        } else if (w.shadow) {
+            FNM_TRY(tc_mix_wgrad(xh_save, Gh, shadowA, nullptr, 0, nmodes, p->B, p->Ci, p->Co, p->mode, st));
             FNM_TRY(tc_mix_unpack(shadowA, dw0, dw1, p->rows_per_w, p->R, p->NY, p->Ci, p->Co, st));
         } else {
-            FNM_TRY(simt_mix_bwd_w(xh_save, Gh, dw0, dw1, p->rows_per_w, p->B, p->R, p->NY, p->Ci, p->Co, st));
+            FNM_TRY(simt_mix_bwd_w(xh_save, Gh, dw0, dw1, p->rows_per_w, p->B, p->R, p->NY, p->Ci, p->Co, st, mm));
         }
     }
     if (wc && (dwc || dbc))
         FNM_TRY(conv_wgrad(g_z, xin, act_in, dwc, dbc, (int64_t)p->B * p->S1 * p->S2, p->Ci, p->Co, partial, p->mode, st));
     if (g_in) {
-        if (w.shadow) {
-            const int w1_layout = p->Co % 2 == 0 ? 1 : 0;
+        const int w1_layout = p->Co % 2 == 0 ? 1 : 0;                  // W1[m][i][o] rows readable with 16-byte loads
+        if (w.shadow && mm && w1_layout) {
+            FNM_TRY(tc_mix_apply(w0, w1, m_split, Gh, Gxh, nmodes, p->B, p->Co, p->Ci, 1, 1, p->mode, "mix_bwd_x", st));
+        } else if (w.shadow && !mm) {
             const float* Wm = shadowB;
             if (w1_layout && p->w_shadow) Wm = p->w_shadow;       // the forward's copy, still valid: no second permute
             else FNM_TRY(tc_mix_pack(w0, w1, p->rows_per_w, p->R, p->NY, p->Ci, p->Co, w1_layout ? 0 : 1, shadowB, st));
-            FNM_TRY(tc_mix_apply(Wm, Gh, Gxh, p->R * p->NY, p->B, p->Co, p->Ci, 1, w1_layout, p->mode, "mix_bwd_x", st));
+            FNM_TRY(tc_mix_apply(Wm, nullptr, 0, Gh, Gxh, nmodes, p->B, p->Co, p->Ci, 1, w1_layout, p->mode, "mix_bwd_x", st));
         } else {
-            FNM_TRY(simt_mix_bwd_x(Gh, w0, w1, p->rows_per_w, Gxh, p->B, p->R, p->NY, p->Ci, p->Co, st));
+            FNM_TRY(simt_mix_bwd_x(Gh, w0, w1, p->rows_per_w, Gxh, p->B, p->R, p->NY, p->Ci, p->Co, st, mm));
         }
         FNM_TRY(fnm_xsyn(Gxh, p->fxb, Zg, p->B, p->P1, p->R, p->NY, p->Ci, p->mode, stream));
         const float* mul = zin_pre ? zin_pre : (act_in ? xin : nullptr);

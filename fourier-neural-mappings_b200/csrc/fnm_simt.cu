@@ -162,11 +162,12 @@ struct FullK {
 struct WeightRef {
     const float2* w0;
     const float2* w1;
-    int rpw, NY, Co;
+    int rpw, NY, Co, Ci, mm;                   // mm: the tensors are held mode-major, (rows, NY, Ci, Co)
     __device__ __forceinline__ size_t index(int i, int o, int mode, bool& second) const {
         const int r = mode / NY, l = mode - r * NY;
         second = r >= rpw;
         const int rr = second ? r - rpw : r;
+        if (mm) return (((size_t)rr * NY + l) * Ci + i) * Co + o;
         return (((size_t)i * Co + o) * rpw + rr) * NY + l;
     }
     __device__ __forceinline__ float2 load(int i, int o, int mode) const {
@@ -258,7 +259,7 @@ struct MixBwdXP : FullK {
 // dW = sum_b conj(xh) gh:  dWr = xr gr + xi gi, dWi = xr gi - xi gr      M = Ci, K = 2B, N = 2Co
 struct MixBwdWP : FullK {
     const float* Xh; const float* Gh; float2* dw0; float2* dw1;
-    int M, N, B, Co, rpw, NY;
+    int M, N, B, Co, rpw, NY, mm;
     static constexpr bool A_MFAST = true, B_NFAST = true;
     __device__ __forceinline__ float a(int mode, int i, int k) const {
         const int ri = k / B, b = k - ri * B;
@@ -274,8 +275,8 @@ struct MixBwdWP : FullK {
         const int r = mode / NY, l = mode - r * NY;
         const bool second = r >= rpw;
         const int rr = second ? r - rpw : r;
-        float* dst = reinterpret_cast<float*>((second ? dw1 : dw0) + ((((size_t)i * Co + o) * rpw + rr) * NY + l));
-        dst[ro] = v;
+        const size_t idx = mm ? (((size_t)rr * NY + l) * M + i) * Co + o : (((size_t)i * Co + o) * rpw + rr) * NY + l;
+        reinterpret_cast<float*>((second ? dw1 : dw0) + idx)[ro] = v;
     }
 };
 
@@ -479,31 +480,32 @@ int simt_xsyn(const float* Oh, const float* fx, float* Z, int B, int S1, int R, 
     return launch_auto(p, B, st, "xsyn");
 }
 
-static WeightRef make_w(const float* w0, const float* w1, int rpw, int NY, int Co) {
+static WeightRef make_w(const float* w0, const float* w1, int rpw, int NY, int Co, int Ci = 0, int mm = 0) {
     WeightRef w;
     w.w0 = reinterpret_cast<const float2*>(w0);
     w.w1 = reinterpret_cast<const float2*>(w1 ? w1 : w0);
-    w.rpw = rpw; w.NY = NY; w.Co = Co;
+    w.rpw = rpw; w.NY = NY; w.Co = Co; w.Ci = Ci; w.mm = mm;
     return w;
 }
 
 int simt_mix_fwd(const float* Xh, const float* w0, const float* w1, int rpw, float* Oh, int B, int R, int NY, int Ci,
-                 int Co, cudaStream_t st) {
+                 int Co, cudaStream_t st, int mode_major) {
     MixFwdP p;
-    p.K = 2 * Ci; p.Xh = Xh; p.Oh = Oh; p.w = make_w(w0, w1, rpw, NY, Co); p.M = B; p.N = 2 * Co; p.Ci = Ci; p.Co = Co;
+    p.K = 2 * Ci; p.Xh = Xh; p.Oh = Oh; p.w = make_w(w0, w1, rpw, NY, Co, Ci, mode_major); p.M = B; p.N = 2 * Co; p.Ci = Ci; p.Co = Co;
     return launch_auto(p, (int64_t)R * NY, st, "mix_fwd");
 }
 
 int simt_mix_bwd_x(const float* Gh, const float* w0, const float* w1, int rpw, float* Gxh, int B, int R, int NY, int Ci,
-                   int Co, cudaStream_t st) {
+                   int Co, cudaStream_t st, int mode_major) {
     MixBwdXP p;
-    p.K = 2 * Co; p.Gh = Gh; p.Gxh = Gxh; p.w = make_w(w0, w1, rpw, NY, Co); p.M = B; p.N = 2 * Ci; p.Ci = Ci; p.Co = Co;
+    p.K = 2 * Co; p.Gh = Gh; p.Gxh = Gxh; p.w = make_w(w0, w1, rpw, NY, Co, Ci, mode_major); p.M = B; p.N = 2 * Ci; p.Ci = Ci; p.Co = Co;
     return launch_auto(p, (int64_t)R * NY, st, "mix_bwd_x");
 }
 
 int simt_mix_bwd_w(const float* Xh, const float* Gh, float* dw0, float* dw1, int rpw, int B, int R, int NY, int Ci,
-                   int Co, cudaStream_t st) {
+                   int Co, cudaStream_t st, int mode_major) {
     MixBwdWP p;
+    p.mm = mode_major;
     p.K = 2 * B; p.Xh = Xh; p.Gh = Gh;
     p.dw0 = reinterpret_cast<float2*>(dw0); p.dw1 = reinterpret_cast<float2*>(dw1 ? dw1 : dw0);
     p.M = Ci; p.N = 2 * Co; p.B = B; p.Co = Co; p.rpw = rpw; p.NY = NY;

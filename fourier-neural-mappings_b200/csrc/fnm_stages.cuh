@@ -9,11 +9,11 @@ int simt_ydft(const float* x, const float* tab, float* T, int64_t rows, int P2, 
 int simt_xdft(const float* T, const float* ex, float* Xh, int B, int P1, int R, int NY, int C, cudaStream_t st);
 int simt_xsyn(const float* Oh, const float* fx, float* Z, int B, int S1, int R, int NY, int C, cudaStream_t st);
 int simt_mix_fwd(const float* Xh, const float* w0, const float* w1, int rpw, float* Oh, int B, int R, int NY, int Ci,
-                 int Co, cudaStream_t st);
+                 int Co, cudaStream_t st, int mode_major = 0);
 int simt_mix_bwd_x(const float* Gh, const float* w0, const float* w1, int rpw, float* Gxh, int B, int R, int NY, int Ci,
-                   int Co, cudaStream_t st);
+                   int Co, cudaStream_t st, int mode_major = 0);
 int simt_mix_bwd_w(const float* Xh, const float* Gh, float* dw0, float* dw1, int rpw, int B, int R, int NY, int Ci,
-                   int Co, cudaStream_t st);
+                   int Co, cudaStream_t st, int mode_major = 0);
 int simt_pointwise_ysyn(const float* x, int act, const float* wc, int wc_is_kn, const float* bias, const float* Z,
                         const float* by, const float* mul, float* out, float* out_act, int64_t rows, int S2, int LY,
                         int K, int N, cudaStream_t st);
@@ -56,9 +56,10 @@ size_t tc_mix_shadow_floats(int nmodes, int Ci, int Co);
 int tc_mix_pack(const float* w0, const float* w1, int rpw, int R, int NY, int Ci, int Co, int which, float* dst,
                 cudaStream_t st);
 int tc_mix_unpack(const float* dW1, float* dw0, float* dw1, int rpw, int R, int NY, int Ci, int Co, cudaStream_t st);
-int tc_mix_apply(const float* Wm, const float* In, float* Out, int nmodes, int B, int Kt, int Lt, int conj, int w_is_w1, int mode,
-                 const char* what, cudaStream_t st);
-int tc_mix_wgrad(const float* Xh, const float* Gh, float* dW1, int nmodes, int B, int Ci, int Co, int mode, cudaStream_t st);
+int tc_mix_apply(const float* Wm, const float* Wm1, int m_split, const float* In, float* Out, int nmodes, int B, int Kt,
+                 int Lt, int conj, int w_is_w1, int mode, const char* what, cudaStream_t st);
+int tc_mix_wgrad(const float* Xh, const float* Gh, float* dW1, float* dW1b, int m_split, int nmodes, int B, int Ci, int Co,
+                 int mode, cudaStream_t st);
 bool tc_conv_wgrad_supported(int64_t npos, int Ci, int Co);
 size_t tc_conv_wgrad_workspace(int64_t npos, int Ci, int Co);
 int tc_conv_wgrad(const float* g, const float* x, int act, float* dwc, float* dbc, int64_t npos, int Ci, int Co,

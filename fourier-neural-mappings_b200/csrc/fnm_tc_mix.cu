@@ -35,6 +35,7 @@ constexpr int kMxN = 32;                                   // n rows per item (M
 
 struct MxArgs {
     const float* a; const float* b; float* out;
+    const float* a1; float* out1; int a_split, o_split;    // modes >= a_split read a1, modes >= o_split write out1 (weights1 | weights2 held mode-major)
     long long a_sm, a_sk, a_sl, a_im;                      // A element (m, k, l): a + m*a_sm + k*a_sk + l*a_sl (+ a_im)
     long long b_sm, b_sn, b_sk, b_im;                      // B element (m, n, k)
     long long o_sm, o_sn, o_sl, o_im;                      // output element (m, n, l)
@@ -112,7 +113,7 @@ __global__ void __launch_bounds__(kMxThreads, 1) mixgemm_tc(const __grid_constan
             mbar_wait(&d_full[db], (uint32_t)((it >> 1) & 1));
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + 256u + 128u * db;
-            float* obase = a.out + (size_t)m * a.o_sm + (size_t)L * a.o_sl;
+            float* obase = (m < a.o_split ? a.out + (size_t)m * a.o_sm : a.out1 + (size_t)(m - a.o_split) * a.o_sm) + (size_t)L * a.o_sl;
 #pragma unroll
             for (int g = 0; g < 2; ++g) {
                 uint32_t fr[16], fi[16], er[16], ei[16];
@@ -321,13 +322,14 @@ __global__ void __launch_bounds__(kMxThreads, 1) mixgemm_tc(const __grid_constan
             const int ch = a.a_reuse ? 0 : (int)(q - (uint32_t)it * a.nchunks);
             int m, n0_unused;
             item_of(it, m, n0_unused);
-            const float* p = a.a + (size_t)m * a.a_sm + (size_t)(ch * 32) * a.a_sk + (size_t)L * a.a_sl;
+            const float* amode = m < a.a_split ? a.a + (size_t)m * a.a_sm : a.a1 + (size_t)(m - a.a_split) * a.a_sm;
+            const float* p = amode + (size_t)(ch * 32) * a.a_sk + (size_t)L * a.a_sl;
             const int klim = l_ok ? a.Kt - ch * 32 : 0;
             float vr[32], vi[32];
             if (a.a_kc) {
                 // backward-x on the FORWARD's mode-major copy W1[m][i][o] (lanes = i, k = o): a lane's 32 (re, im) pairs
                 // are one 256-byte run; L1 keeps the sectors between the two 16-byte loads that share them
-                const float4* p4 = reinterpret_cast<const float4*>(a.a + (size_t)m * a.a_sm + (size_t)L * a.a_sl + (size_t)(ch * 32) * 2);
+                const float4* p4 = reinterpret_cast<const float4*>(amode + (size_t)L * a.a_sl + (size_t)(ch * 32) * 2);
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
                     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -479,10 +481,12 @@ int tc_mix_unpack(const float* dW1, float* dw0, float* dw1, int rpw, int R, int 
 // Oh[m][ro][b][o] = sum_i Xh[m][ri][b][i] W1[m][i][o]        (conj = 0, W = W1, Kt = Ci, Lt = Co)
 // Gxh[m][ri][b][i] = sum_o Gh[m][ro][b][o] conj(W[i][o][m])   (conj = 1, Kt = Co, Lt = Ci) with W given either as
 //   W2[m][o][i] (w_is_w1 = 0) or as the forward's copy W1[m][i][o] (w_is_w1 = 1: lanes read k-contiguous rows)
-int tc_mix_apply(const float* Wm, const float* In, float* Out, int nmodes, int B, int Kt, int Lt, int conj, int w_is_w1,
-                 int mode, const char* what, cudaStream_t st) {
+//   Wm1 / m_split: modes >= m_split are read from Wm1 (mode-major parameters: weights1 | weights2 are two arrays)
+int tc_mix_apply(const float* Wm, const float* Wm1, int m_split, const float* In, float* Out, int nmodes, int B, int Kt,
+                 int Lt, int conj, int w_is_w1, int mode, const char* what, cudaStream_t st) {
     MxArgs a{};
     a.a = Wm; a.b = In; a.out = Out;
+    a.a1 = Wm1 ? Wm1 : Wm; a.a_split = Wm1 ? m_split : nmodes; a.out1 = Out; a.o_split = nmodes;
     a.Kt = Kt; a.Lt = Lt; a.Nt = B; a.nmodes = nmodes;
     a.a_sm = (long long)Kt * Lt * 2; a.a_sk = (long long)Lt * 2; a.a_sl = 2; a.a_im = 1; a.a_pair = 1;
     if (conj && w_is_w1) { a.a_sk = 2; a.a_sl = (long long)Kt * 2; a.a_kc = 1; }
@@ -495,9 +499,11 @@ int tc_mix_apply(const float* Wm, const float* In, float* Out, int nmodes, int B
 // dW1[m][i][o] = sum_b conj(Xh[m][.][b][i]) Gh[m][.][b][o].  The output-gradient spectrum is the TMEM operand
 // (lanes = o) so that the epilogue's warp stores run along o, the contiguous axis of dW1 (with lanes = i every
 // 8-byte store of a warp hit a different 1 KB row); the conjugate then sits on the shared-memory operand.
-int tc_mix_wgrad(const float* Xh, const float* Gh, float* dW1, int nmodes, int B, int Ci, int Co, int mode, cudaStream_t st) {
+int tc_mix_wgrad(const float* Xh, const float* Gh, float* dW1, float* dW1b, int m_split, int nmodes, int B, int Ci, int Co,
+                 int mode, cudaStream_t st) {
     MxArgs a{};
     a.a = Gh; a.b = Xh; a.out = dW1;
+    a.a1 = Gh; a.a_split = nmodes; a.out1 = dW1b ? dW1b : dW1; a.o_split = dW1b ? m_split : nmodes;
     a.Kt = B; a.Lt = Co; a.Nt = Ci; a.nmodes = nmodes;
     a.a_sm = (long long)2 * B * Co; a.a_sk = Co; a.a_sl = 1; a.a_im = (long long)B * Co; a.a_pair = 0;
     a.b_sm = (long long)2 * B * Ci; a.b_sn = 1; a.b_sk = Ci; a.b_im = (long long)B * Ci; a.b_kcontig = 0;

@@ -69,6 +69,22 @@ def _grad_sink(w):
     return sink
 
 
+def _is_mode_major(t):
+    """(in, out, modes...) tensor whose memory order is (modes..., in, out), dense."""
+    n = t.dim()
+    return n >= 3 and t.permute(tuple(range(2, n)) + (0, 1)).is_contiguous()
+
+
+def _spectral_weights(w0, w1):
+    """-> (float view of w0, of w1 or None, FNM_W_* layout).  Both tensors must share the layout; anything that is
+    neither the reference order nor mode-major is copied into the reference order."""
+    if w0.dtype != torch.complex64 or (w1 is not None and w1.dtype != torch.complex64):
+        raise TypeError("expected complex64 weights")
+    if _is_mode_major(w0) and not w0.is_contiguous() and (w1 is None or (_is_mode_major(w1) and not w1.is_contiguous())):
+        return torch.view_as_real(w0), (torch.view_as_real(w1) if w1 is not None else None), _lib.FNM_W_MODE_MAJOR
+    return _cplx(w0), (_cplx(w1) if w1 is not None else None), _lib.FNM_W_REFERENCE
+
+
 _WS = {}
 
 
@@ -102,8 +118,7 @@ class FourierLayerFn(torch.autograd.Function):
         if (P1, P2) != (tables.P1, tables.P2) or w0.shape[0] != Ci:
             raise ValueError(f"input {tuple(xk.shape)} does not match the plan / weights")
         plan = tables.c_plan(xk.device, B, Ci, Co, _MODE)
-        w0r = _cplx(w0)
-        w1r = _cplx(w1) if w1 is not None else None
+        w0r, w1r, plan.w_layout = _spectral_weights(w0, w1)
         wcc = _f32c(wc.reshape(Co, Ci)) if wc is not None else None
         bcc = _f32c(bc) if bc is not None else None
         z = torch.empty((B, tables.S1, tables.S2, Co), dtype=torch.float32, device=xk.device)
@@ -153,12 +168,20 @@ class FourierLayerFn(torch.autograd.Function):
         g_in = torch.empty_like(xk) if need_x else None
         want_w = need_w0 or (w1 is not None and need_w1)
         s0, s1 = ctx.sinks
-        dw0 = (s0 if s0 is not None else torch.empty_like(w0)) if want_w else None
-        dw1 = (s1 if s1 is not None else torch.empty_like(w1)) if (want_w and w1 is not None) else None
+        w0r, w1r, plan.w_layout = _spectral_weights(w0, w1)
+        # gradients in the memory order the kernels were told the weights have; a sink in another order gets a copy
+        mm = plan.w_layout == _lib.FNM_W_MODE_MAJOR
+
+        def grad_buffer(sink, w):
+            if w is None or not want_w:
+                return None
+            if sink is not None and (sink.stride() == w.stride() if mm else sink.is_contiguous()):
+                return sink
+            return torch.empty_like(w, memory_format=torch.preserve_format if mm else torch.contiguous_format)
+
+        dw0, dw1 = grad_buffer(s0, w0), grad_buffer(s1, w1)
         dwc = torch.empty_like(wc) if (wc is not None and need_wc) else None
         dbc = torch.empty((Co,), dtype=torch.float32, device=xk.device) if (ctx.has_bias and need_bc) else None
-        w0r = _cplx(w0)
-        w1r = _cplx(w1) if w1 is not None else None
         wcc = _f32c(wc.reshape(Co, Ci)) if wc is not None else None
         L = lib()
         nbytes = L.fnm_fourier_layer_workspace_bytes(C.byref(plan))
@@ -169,6 +192,9 @@ class FourierLayerFn(torch.autograd.Function):
             _ptr(torch.view_as_real(dw1)) if dw1 is not None else None, _ptr(dwc), _ptr(dbc),
             _ptr(ws), ws.numel(), _stream()), "fnm_fourier_layer_bwd")
         # a sink already holds the gradient: autograd gets None and runs no AccumulateGrad for that weight
+        for sink, dw in ((s0, dw0), (s1, dw1)):
+            if sink is not None and dw is not None and dw is not sink:
+                sink.copy_(dw)
         return (g_in, None, None if s0 is not None else dw0, None if s1 is not None else dw1, dwc, dbc, None, None, None, None)
 
 

@@ -47,7 +47,10 @@ class FlatGradients:
     def attach(self):
         for p, (off, n) in zip(self.params, self.offsets):
             chunk = self.flat[off:off + n]
-            view = torch.view_as_complex(chunk.view(-1, 2)).view(p.shape) if p.is_complex() else chunk.view(p.shape)
+            flat = torch.view_as_complex(chunk.view(-1, 2)) if p.is_complex() else chunk
+            # same memory order as the parameter (the spectral weights are stored mode-major): Adam and the dW kernels
+            # address parameter and gradient storage element by element
+            view = torch.as_strided(flat, p.shape, p.stride()) if _dense(p) else flat.view(p.shape)
             p.grad = view
             if self.direct and p.is_complex():
                 p._fnm_grad_sink, p._fnm_sink_uses = view, 0
@@ -71,6 +74,17 @@ class FlatGradients:
         return dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
 
 
+def _dense(t):
+    """Non-overlapping and dense (any permutation of a contiguous tensor): numel == storage span."""
+    span = 1 + sum((n - 1) * st for n, st in zip(t.shape, t.stride())) if t.numel() else 0
+    return span == t.numel()
+
+
+def storage_order_view(t):
+    """1-D contiguous view over the storage of a dense tensor (collectives need contiguous buffers)."""
+    return torch.as_strided(t, (t.numel(),), (1,)) if _dense(t) else t.contiguous().view(-1)
+
+
 def shard_batch(x, rank, world):
     """Rank r trains on samples [r*B/G, (r+1)*B/G)."""
     b = x.shape[0]
@@ -84,8 +98,8 @@ def broadcast_parameters(module, src=0):
     """Make every rank start from rank ``src``'s weights."""
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
         for t in list(module.parameters()) + list(module.buffers()):
-            data = torch.view_as_real(t.data) if t.is_complex() else t.data
-            dist.broadcast(data, src)
+            data = storage_order_view(t.data)
+            dist.broadcast(torch.view_as_real(data) if data.is_complex() else data, src)
 
 
 def train_step(model, optimizer, grads, loss_fn, x, y, group=None):

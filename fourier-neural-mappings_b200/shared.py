@@ -80,8 +80,18 @@ def _from_cl(y, one_d):
     return y.squeeze(1).permute(0, 2, 1) if one_d else y.permute(0, 3, 1, 2)
 
 
-def _complex_param(scale, *shape):
-    return nn.Parameter(scale * torch.rand(*shape, dtype=torch.cfloat))
+def _complex_param(scale, *shape, mode_major=False):
+    """scale * U[0,1) on real and imaginary parts (shared.py:311-313).  ``mode_major``: same logical shape
+    (in, out, modes...) and values, but stored with the mode axes slowest -- the order the mixing kernels
+    contract against (include/fnm_b200.h: FNM_W_MODE_MAJOR), so no per-call layout copies are needed.
+    state_dict / load_state_dict / checkpoints see the reference's shapes and values; only strides differ."""
+    w = scale * torch.rand(*shape, dtype=torch.cfloat)
+    if mode_major:
+        n = len(shape)
+        fwd = tuple(range(2, n)) + (0, 1)                     # (modes..., in, out)
+        inv = (n - 2, n - 1) + tuple(range(0, n - 2))
+        w = w.permute(fwd).contiguous().permute(inv)
+    return nn.Parameter(w)
 
 
 # ------------------------------------------------------------------------------------------
@@ -152,7 +162,7 @@ class SpectralConv1d(nn.Module):
         super().__init__()
         self.in_channels, self.out_channels, self.modes1 = in_channels, out_channels, modes1
         self.scale = 1.0 / (in_channels * out_channels)
-        self.weights1 = _complex_param(self.scale, in_channels, out_channels, modes1)
+        self.weights1 = _complex_param(self.scale, in_channels, out_channels, modes1, mode_major=True)
 
     def tables(self, P, s=None):
         return spectral_tables(1, P, 0, self.modes1, 1, P if s is None else int(s), one_d=True)
@@ -171,8 +181,8 @@ class SpectralConv2d(nn.Module):
         self.in_channels, self.out_channels = in_channels, out_channels
         self.modes1, self.modes2 = modes1, modes2
         self.scale = 1.0 / (in_channels * out_channels)
-        self.weights1 = _complex_param(self.scale, in_channels, out_channels, modes1, modes2)
-        self.weights2 = _complex_param(self.scale, in_channels, out_channels, modes1, modes2)
+        self.weights1 = _complex_param(self.scale, in_channels, out_channels, modes1, modes2, mode_major=True)
+        self.weights2 = _complex_param(self.scale, in_channels, out_channels, modes1, modes2, mode_major=True)
 
     def tables(self, P1, P2, s=None):
         S1, S2 = (P1, P2) if s is None else (int(s[0]), int(s[1]))

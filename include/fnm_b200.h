@@ -59,6 +59,15 @@ enum {
     FNM_MODE_TF32 = 1                       /* single-pass TF32 tensor cores, looser stated tolerance */
 };
 
+/* memory order of the complex spectral weights w0 / w1 (and dw0 / dw1) of the fused Fourier layer */
+enum {
+    FNM_W_REFERENCE = 0,                    /* the reference's (Cin, Cout, kx, ky): modes fastest; each call makes a
+                                               mode-major scratch copy (and permutes dW back) */
+    FNM_W_MODE_MAJOR = 1                    /* (kx, ky, Cin, Cout): what the kernels contract against -- read and
+                                               written in place, no copies.  The drop-in modules keep their
+                                               parameters in this order behind the reference's logical shape. */
+};
+
 typedef struct fnm_plan {
     int32_t B;                              /* batch (samples on this rank) */
     int32_t P1, P2;                         /* input grid  (P1 = 1 for 1-D) */
@@ -68,7 +77,8 @@ typedef struct fnm_plan {
     int32_t rows_per_w;                     /* weight rows held by ONE weight tensor: m1 for
                                                SpectralConv2d (weights1|weights2), R otherwise */
     int32_t mode;                           /* FNM_MODE_* */
-    int32_t reserved;
+    int32_t w_layout;                       /* FNM_W_* : memory order of the spectral weights AND their gradients
+                                               (fused Fourier layer only; F2V / V2F weights are always FNM_W_REFERENCE) */
     const float *ay, *ayT, *by, *byT, *ex, *fx, *exb, *fxb;
     float* w_shadow;                        /* optional (fused Fourier layer only): caller-owned buffer of
                                                fnm_fourier_layer_shadow_bytes() that receives the mode-major copy of

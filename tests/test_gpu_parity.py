@@ -407,3 +407,46 @@ def test_direct_gradient_sinks_match_autograd_accumulation(family):
     for k in w0:
         assert torch.equal(torch.view_as_real(w0[k]) if w0[k].is_complex() else w0[k],
                            torch.view_as_real(w1[k]) if w1[k].is_complex() else w1[k]), k
+
+
+def test_spectral_weights_live_mode_major_and_skip_the_layout_copies():
+    """The drop-in modules keep weights1 / weights2 in (kx, ky, Cin, Cout) memory order behind the reference's
+    logical shape: a train step launches no weight permutes, gradients and Adam state share the order, and the
+    results equal those of the same model with reference-ordered (contiguous) parameters, which take the
+    pack / unpack path of the C ABI."""
+    from fnm_b200 import _lib
+    from fnm_b200.ops import _is_mode_major
+    torch.manual_seed(5)
+    ref_sd = fnm_b200.FNO2d(4, 4, 32, n_layers=3, width_final=32).state_dict()
+    x = torch.randn(3, 1, 24, 24, device=DEV)
+    y = torch.randn(3, 1, 24, 24, device=DEV)
+    outs = {}
+    for order in ("mode_major", "reference"):
+        model = fnm_b200.FNO2d(4, 4, 32, n_layers=3, width_final=32)
+        model.load_state_dict(ref_sd)
+        model = model.to(DEV)
+        spectral = [p for p in model.parameters() if p.is_complex()]
+        if order == "reference":
+            for sc in model.speconvs:
+                sc.weights1 = torch.nn.Parameter(sc.weights1.detach().contiguous())
+                sc.weights2 = torch.nn.Parameter(sc.weights2.detach().contiguous())
+        else:
+            assert all(_is_mode_major(p) and not p.is_contiguous() for p in spectral)     # survives load + .to()
+        opt = fnm_b200.Adam(model.parameters(), lr=1e-3, weight_decay=1e-4)
+        _lib.profile_begin()
+        for _ in range(2):
+            opt.zero_grad()
+            out = model(x)
+            fnm_b200.parallel.rel_l2_sum(out, y).backward()
+            opt.step()
+        prof = _lib.profile_end()
+        packs = sum(v[0] for k, v in prof.items() if k in ("mix_pack", "mix_unpack"))
+        assert (packs == 0) == (order == "mode_major"), prof
+        for p in model.parameters():
+            if p.is_complex():
+                assert p.grad.stride() == p.stride() and opt.state[p]["exp_avg"].stride() == p.stride()
+        outs[order] = (out.detach().clone(), {k: v.detach().clone() for k, v in model.state_dict().items()})
+    assert rel_l2(outs["mode_major"][0], outs["reference"][0]) < 1e-6
+    for k, v in outs["mode_major"][1].items():
+        assert v.shape == outs["reference"][1][k].shape
+        assert rel_l2(v, outs["reference"][1][k]) < 1e-6, k
