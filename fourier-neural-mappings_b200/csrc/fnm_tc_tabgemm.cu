@@ -26,6 +26,8 @@
 //   warps 16-19 table loaders (group 1) when the table is streamed, otherwise idle register donors
 #include "fnm_tc_ptx.cuh"
 
+#include <cstdlib>
+
 namespace fnm {
 namespace tc {
 
@@ -42,8 +44,9 @@ struct TgArgs {
     long long gin_s1, gin_s0, k_s1, k_s0, gout_s1, gout_s0, m_s1, m_s0;
     int gin_div, kin_div, gout_div, mout_div;
     int C, G, GL, CB, items;
-    int Kt, Mt, nchunks, NT, ntiles, dbl, nbuf, reuse, resident, slots, nmain;
+    int Kt, Mt, nchunks, NT, ntiles, dbl, nbuf, reuse, resident, slots, nmain, ncorr;
     int act, single_pass, tab_vec4;
+    int tab_tma;                                           // streamed table: raw slabs arrive by TMA, the table warps only derive the remainder
 };
 
 __device__ __forceinline__ float ld_stream1(const float* p) {
@@ -52,14 +55,15 @@ __device__ __forceinline__ float ld_stream1(const float* p) {
     return v;
 }
 
-__global__ void __launch_bounds__(kTgThreads, 1) tabgemm_tc(const TgArgs a) {
+__global__ void __launch_bounds__(kTgThreads, 1) tabgemm_tc(const __grid_constant__ CUtensorMap mapT, const TgArgs a) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const uint32_t slot_bytes = (uint32_t)a.NT * 256u;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)a.slots * slot_bytes);
     uint64_t* tab_full = bars;                                 // [kTgMaxSlots]
     uint64_t* tab_empty = bars + kTgMaxSlots;                  // [kTgMaxSlots]
-    uint64_t* a_full = bars + 2 * kTgMaxSlots;                 // [kTgMaxBuf]
+    uint64_t* tab_raw = bars + 2 * kTgMaxSlots;                // [kTgMaxSlots] TMA transaction barriers (tab_tma)
+    uint64_t* a_full = bars + 3 * kTgMaxSlots;                 // [kTgMaxBuf]
     uint64_t* a_empty = a_full + kTgMaxBuf;                    // [kTgMaxBuf]
     uint64_t* d_full = a_empty + kTgMaxBuf;                    // [2]
     uint64_t* d_empty = d_full + 2;                            // [2]
@@ -71,10 +75,12 @@ __global__ void __launch_bounds__(kTgThreads, 1) tabgemm_tc(const TgArgs a) {
         for (int s = 0; s < a.slots; ++s) {
             mbar_init(&tab_full[s], a.resident ? kTgTabWarps : ((s & 1) ? 4 : kTgTabWarps));
             mbar_init(&tab_empty[s], 1);
+            mbar_init(&tab_raw[s], 1);
         }
         for (int s = 0; s < a.nbuf; ++s) { mbar_init(&a_full[s], 4); mbar_init(&a_empty[s], 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(&d_full[s], 1); mbar_init(&d_empty[s], 4); }
         fence_barrier_init();
+        if (a.tab_tma) tma_prefetch_desc(&mapT);
     }
     if (warp == 4) tmem_alloc(tmem_slot, 512);
     tc_fence_before();
@@ -104,14 +110,14 @@ __global__ void __launch_bounds__(kTgThreads, 1) tabgemm_tc(const TgArgs a) {
                 const uint32_t dpar = a.dbl ? ((dcount >> 1) & 1) : (dcount & 1);
                 mbar_wait(&d_full[dbuf], dpar);
                 tc_fence_after();
-                const uint32_t dstride = (uint32_t)((a.nmain + 1) * a.NT);       // nmain main accumulators + corrections
+                const uint32_t dstride = (uint32_t)((a.nmain + a.ncorr) * a.NT);  // nmain main accumulators + corrections
                 const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + dcol0 + (uint32_t)dbuf * dstride;
                 const int mlim = min(a.NT, a.Mt - nt * a.NT);
                 for (int c0 = 0; c0 < mlim; c0 += 16) {
                     uint32_t r[16];
                     tmem_ld16(taddr + c0, r);
                     // + the other main accumulator(s) and the separately accumulated correction terms
-                    for (int e = 1; e < a.nmain + (a.single_pass ? 0 : 1); ++e) {
+                    for (int e = 1; e < a.nmain + (a.single_pass ? 0 : a.ncorr); ++e) {
                         uint32_t rc[16];
                         tmem_ld16(taddr + (uint32_t)(e * a.NT) + c0, rc);
                         tmem_ld_wait();
@@ -164,8 +170,11 @@ __global__ void __launch_bounds__(kTgThreads, 1) tabgemm_tc(const TgArgs a) {
                 // correction passes, 2^-11 smaller, to a second one: the long chain is three times shorter
                 // With nmain = 2 the chunks alternate between two main accumulators (chains half as long again);
                 // the epilogue adds them with round-to-nearest.
-                const uint32_t dstride = (uint32_t)((a.nmain + 1) * a.NT);
-                const uint32_t d0 = tmem_base + dcol0 + (uint32_t)dbuf * dstride, dc = d0 + (uint32_t)(a.nmain * a.NT);
+                // Short contractions (<= 4 chunks, ncorr = 0) put the corrections into the main accumulator instead: the
+                // chain stays under 50 MMAs and the freed columns double-buffer D, so the epilogue of a tile overlaps the
+                // MMAs of the next one.
+                const uint32_t dstride = (uint32_t)((a.nmain + a.ncorr) * a.NT);
+                const uint32_t d0 = tmem_base + dcol0 + (uint32_t)dbuf * dstride, dc = a.ncorr ? d0 + (uint32_t)(a.nmain * a.NT) : d0;
                 uint32_t accum = 0, accum_m[2] = {0u, 0u};
                 for (int ch = 0; ch < a.nchunks; ++ch) {
                     uint32_t q;
@@ -188,7 +197,7 @@ __global__ void __launch_bounds__(kTgThreads, 1) tabgemm_tc(const TgArgs a) {
                         umma_ts(d0 + (uint32_t)(mi * a.NT), a_hi + ks * 8, bhi + 2 * ks, idesc, accum_m[mi]);
                         accum_m[mi] = 1;
                         if (!a.single_pass) {
-                            umma_ts(dc, a_lo + ks * 8, bhi + 2 * ks, idesc, accum);
+                            umma_ts(dc, a_lo + ks * 8, bhi + 2 * ks, idesc, a.ncorr ? accum : 1u);
                             umma_ts(dc, a_hi + ks * 8, blo + 2 * ks, idesc, 1);
                         }
                         accum = 1;
@@ -251,6 +260,45 @@ __global__ void __launch_bounds__(kTgThreads, 1) tabgemm_tc(const TgArgs a) {
                     fill(nt, ch, smem + (size_t)slot * slot_bytes);
                     if (lane == 0) mbar_arrive(&tab_full[slot]);
                 }
+        } else if (a.tab_tma) {
+            // Streamed table by TMA.  The slab sequence of this CTA is q = 0, 1, ... (item, tile, chunk); group g owns the
+            // slabs of its parity and the ring slots of its parity.  One thread of the group issues the raw [NT x 32 k] box
+            // of slab q + 2*ahead (once the MMAs of the slot's previous tenant have retired), all its threads then turn the
+            // raw slab q -- which IS the hi operand -- into the remainder slab, shared memory to shared memory.
+            const uint32_t per_item = (uint32_t)(a.ntiles * a.nchunks);
+            const uint32_t total = (uint32_t)my_items * per_item;
+            const uint32_t ahead = (uint32_t)a.slots / 2u - 1u;            // slabs of this group in flight beyond the current one
+            const bool issuer = (grp == 0 ? warp == 5 : warp == kTgFirstA + 4 * kTgNwg) && lane == 0;
+            auto issue = [&](uint32_t q) {
+                const uint32_t slot = q % (uint32_t)a.slots;
+                const uint32_t r = q % per_item;
+                const int nt = (int)(r / (uint32_t)a.nchunks), ch = (int)(r - (uint32_t)nt * a.nchunks);
+                mbar_wait(&tab_empty[slot], ((q / (uint32_t)a.slots) & 1) ^ 1);
+                mbar_expect_tx(&tab_raw[slot], (uint32_t)a.NT * 128u);
+                tma_load_2d(&mapT, &tab_raw[slot], smem + (size_t)slot * slot_bytes, ch * 32, nt * a.NT);
+            };
+            if (issuer)
+                for (uint32_t q = (uint32_t)grp; q < total && q < (uint32_t)grp + 2u * ahead; q += 2) issue(q);   // slots empty: no wait
+            for (uint32_t q = (uint32_t)grp; q < total; q += 2) {
+                const uint32_t slot = q % (uint32_t)a.slots;
+                mbar_wait(&tab_raw[slot], (q / (uint32_t)a.slots) & 1);
+                const uint32_t raw0 = smem_u32(smem) + slot * slot_bytes + (uint32_t)tt * 16u;
+                const uint32_t half = (uint32_t)a.NT * 128u;
+                for (uint32_t off = (uint32_t)tt * 16u; off < half; off += (uint32_t)gthreads * 16u) {
+                    float4 v;
+                    const uint32_t src = raw0 + (off - (uint32_t)tt * 16u);
+                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(src));
+                    v.x -= __uint_as_float(__float_as_uint(v.x) & 0xffffe000u); v.y -= __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
+                    v.z -= __uint_as_float(__float_as_uint(v.z) & 0xffffe000u); v.w -= __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
+                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(src + half), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+                }
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tab_full[slot]);
+                // refill the ring AFTER handing slab q over: the slot wanted is the one slab q - 2 occupied, whose MMAs
+                // have usually retired by now, so the conversion above never waits behind this
+                if (issuer && q + 2u * ahead < total) issue(q + 2u * ahead);
+            }
         } else {
             uint32_t qs = 0;
             for (int it = 0; it < my_items; ++it)
@@ -370,7 +418,12 @@ static bool tg_configure(TgArgs& a) {
                 // long contractions split the main chain over two accumulators when TMEM allows (truncation bias)
                 int nmain = (a.nchunks >= 8 && 3 * NT * (dbl ? 2 : 1) + 64 * 2 * nwg_a <= 512) ? 2 : 1;
                 if (dbl && nmain == 1 && a.nchunks >= 8 && 3 * NT + 64 * 2 * nwg_a <= 512) continue;   // accuracy first: single-buffered D with two chains
-                const int dcols = (nmain + 1) * NT * (dbl ? 2 : 1);  // main accumulator(s) + correction accumulator
+                int ncorr = 1;
+                int dcols = (nmain + ncorr) * NT * (dbl ? 2 : 1);    // main accumulator(s) + correction accumulator
+                if (dbl && a.nchunks <= 4 && (512 - dcols) / 64 < 2 * nwg_a) {
+                    ncorr = 0;                                     // short chain: corrections share the main accumulator
+                    dcols = nmain * NT * 2;
+                }
                 int nbuf = (512 - dcols) / 64;
                 if (nbuf > kTgMaxBuf) nbuf = kTgMaxBuf;
                 if (nbuf < 2 * nwg_a) continue;                   // mbarrier parity safety of the pair schedule
@@ -386,7 +439,7 @@ static bool tg_configure(TgArgs& a) {
                     slots &= ~1;                                  // even: the two loader groups alternate slabs
                     if (slots < 2) continue;
                 }
-                a.NT = NT; a.ntiles = ntiles; a.dbl = dbl; a.nbuf = nbuf; a.reuse = reuse ? 1 : 0; a.nmain = nmain;
+                a.NT = NT; a.ntiles = ntiles; a.dbl = dbl; a.nbuf = nbuf; a.reuse = reuse ? 1 : 0; a.nmain = nmain; a.ncorr = ncorr;
                 a.resident = resident ? 1 : 0; a.slots = slots;
                 return true;
             }
@@ -394,10 +447,15 @@ static bool tg_configure(TgArgs& a) {
     return false;
 }
 
+static bool tab_tma_enabled() {
+    const char* e = getenv("FNM_TAB_NO_TMA");
+    return !(e && e[0] == '1');
+}
+
 static int tg_launch(TgArgs& a, const char* what, cudaStream_t st) {
     if (!tg_configure(a)) return fail(FNM_ENOTSUP, "%s: shape not served by the tcgen05 table GEMM", what);
     a.tab_vec4 = (a.Kt % 4 == 0 && (reinterpret_cast<uintptr_t>(a.tab) & 15) == 0) ? 1 : 0;
-    size_t smem = (size_t)a.slots * a.NT * 256 + 1024 + (2 * kTgMaxSlots + 2 * kTgMaxBuf + 4) * 8 + 16;
+    size_t smem = (size_t)a.slots * a.NT * 256 + 1024 + (3 * kTgMaxSlots + 2 * kTgMaxBuf + 4) * 8 + 16;
     if (smem < 120 * 1024) smem = 120 * 1024;                    // one CTA per SM (each owns all 512 TMEM columns)
     static bool attr_set = false;
     if (!attr_set) {
@@ -405,10 +463,19 @@ static int tg_launch(TgArgs& a, const char* what, cudaStream_t st) {
         if (e != cudaSuccess) return fail(FNM_ECUDA, "%s: smem attribute: %s", what, cudaGetErrorString(e));
         attr_set = true;
     }
+    // streamed table: TMA the raw slabs when the rows are 16-byte aligned and each group can keep a slab ahead
+    CUtensorMap mapT{};
+    a.tab_tma = 0;
+    if (!a.resident && a.slots >= 4 && a.Kt % 4 == 0 && (reinterpret_cast<uintptr_t>(a.tab) & 15) == 0 && tab_tma_enabled()) {
+        const cuuint64_t dims[2] = {(cuuint64_t)a.Kt, (cuuint64_t)a.Mt};
+        const cuuint64_t str[1] = {(cuuint64_t)a.Kt * 4};
+        const cuuint32_t box[2] = {32, (cuuint32_t)a.NT};
+        if (tc_make_map(&mapT, a.tab, 2, dims, str, box, true)) a.tab_tma = 1;
+    }
     const int grid = a.items < sm_count() ? a.items : sm_count();
     {
         LaunchScope ls(what, st);
-        tabgemm_tc<<<grid, kTgThreads, smem, st>>>(a);
+        tabgemm_tc<<<grid, kTgThreads, smem, st>>>(mapT, a);
     }
     return check_launch(what);
 }
