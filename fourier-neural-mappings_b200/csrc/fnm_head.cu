@@ -28,38 +28,49 @@ __device__ __forceinline__ float lift_feat(const LiftArgs& a, int j, int b, int 
     return a.N2 > 1 ? (float)yy / (float)(a.N2 - 1) : 0.f;
 }
 
-__global__ void lift_fwd_kernel(const LiftArgs a) {
-    extern __shared__ float sw[];                         // [J + 1][C]: weights transposed, then bias
+// thread = (position slot, 4-channel group): its weight columns live in registers, the features of a position are
+// evaluated once per thread (no per-element index division), one 16-byte store per position
+template <int MAXJ>
+__global__ void __launch_bounds__(256) lift_fwd_kernel(const LiftArgs a) {
     const int C4 = a.C / 4;
-    for (int i = threadIdx.x; i < (a.J + 1) * a.C; i += blockDim.x) {
-        const int j = i / a.C, c = i - j * a.C;
-        sw[i] = j < a.J ? __ldg(a.w + (size_t)c * a.J + j) : __ldg(a.b + c);
+    const int slots = blockDim.x / C4;
+    const int c4 = threadIdx.x % C4, slot = threadIdx.x / C4;
+    if (slot >= slots) return;
+    float4 w[MAXJ], bias = __ldg(reinterpret_cast<const float4*>(a.b) + c4);
+#pragma unroll
+    for (int j = 0; j < MAXJ; ++j) {
+        w[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (j < a.J) {
+            w[j].x = __ldg(a.w + (size_t)(c4 * 4 + 0) * a.J + j); w[j].y = __ldg(a.w + (size_t)(c4 * 4 + 1) * a.J + j);
+            w[j].z = __ldg(a.w + (size_t)(c4 * 4 + 2) * a.J + j); w[j].w = __ldg(a.w + (size_t)(c4 * 4 + 3) * a.J + j);
+        }
     }
-    __syncthreads();
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
     const int nrows = a.B * a.P1;
     for (int row = blockIdx.x; row < nrows; row += gridDim.x) {          // row = (b, x) of the padded grid
         const int b = row / a.P1, xx = row - b * a.P1;
-        float4* orow = reinterpret_cast<float4*>(a.out + (size_t)row * a.P2 * a.C);
+        float4* orow = reinterpret_cast<float4*>(a.out + (size_t)row * a.P2 * a.C) + c4;
         const bool x_in = xx < a.N1;
-        for (int i = threadIdx.x; i < a.P2 * C4; i += blockDim.x) {
-            const int yy = i / C4, c4 = i - yy * C4;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int yy = slot; yy < a.P2; yy += slots) {
+            float4 v = zero;
             if (x_in && yy < a.N2) {
-                v = *reinterpret_cast<const float4*>(sw + a.J * a.C + c4 * 4);
-                for (int j = 0; j < a.J; ++j) {
-                    const float f = lift_feat(a, j, b, xx, yy);
-                    const float4 w = *reinterpret_cast<const float4*>(sw + j * a.C + c4 * 4);
-                    v.x = fmaf(f, w.x, v.x); v.y = fmaf(f, w.y, v.y); v.z = fmaf(f, w.z, v.z); v.w = fmaf(f, w.w, v.w);
+                v = bias;
+#pragma unroll
+                for (int j = 0; j < MAXJ; ++j) {
+                    if (j < a.J) {
+                        const float f = lift_feat(a, j, b, xx, yy);
+                        v.x = fmaf(f, w[j].x, v.x); v.y = fmaf(f, w[j].y, v.y); v.z = fmaf(f, w[j].z, v.z); v.w = fmaf(f, w[j].w, v.w);
+                    }
                 }
             }
-            orow[i] = v;
+            orow[(size_t)yy * C4] = v;
         }
     }
 }
 
 // partial[block][j][c] = sum over the block's positions of g[pos][c] * feat_j(pos)   (j == J: bias)
 template <int MAXJ>
-__global__ void __launch_bounds__(256, 2) lift_bwd_kernel(const LiftArgs a) {
+__global__ void __launch_bounds__(256, 3) lift_bwd_kernel(const LiftArgs a) {
     extern __shared__ float red[];                        // [slots][(J+1)][C]
     const int C4 = a.C / 4;
     const int slots = blockDim.x / C4;
@@ -72,7 +83,7 @@ __global__ void __launch_bounds__(256, 2) lift_bwd_kernel(const LiftArgs a) {
         for (int row = blockIdx.x; row < nrows; row += gridDim.x) {
             const int b = row / a.N1, xx = row - b * a.N1;
             const float4* grow = reinterpret_cast<const float4*>(a.g + ((size_t)b * a.P1 + xx) * a.P2 * a.C) + c4;
-            for (int y0 = slot; y0 < a.N2; y0 += 4 * slots) {           // four independent loads in flight
+            for (int y0 = slot; y0 < a.N2; y0 += 4 * slots) {           // four independent loads in flight (eight spill at 128 registers)
                 float4 g[4];
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
@@ -135,37 +146,59 @@ struct HeadArgs {
 __device__ __forceinline__ float gelu_erf(float x) { return tc::gelu_fast(x); }
 __device__ __forceinline__ float gelu_erf_grad(float x) { return tc::gelu_grad_fast(x); }
 
-__global__ void head_fwd_kernel(const HeadArgs a) {
+// One warp per 8 positions: lane = 4 hidden channels, eight 16-byte loads in flight per lane.  The 8 (x D) per-lane
+// partial dot products are summed over the warp with a halving butterfly -- lanes trade half of their values at each of
+// the first three steps -- 9 shuffles instead of 40; lane 4*v then holds the total of position v.
+template <int D>
+__global__ void __launch_bounds__(256) head_fwd_kernel(const HeadArgs a) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
     const int H4 = a.H / 4;
-    float4 w[kHeadMaxD][kHeadMaxH4];
-#pragma unroll
-    for (int d = 0; d < kHeadMaxD; ++d)
-#pragma unroll
-        for (int k = 0; k < kHeadMaxH4; ++k) {
-            const int h4 = lane + 32 * k;
-            w[d][k] = (d < a.D && h4 < H4) ? __ldg(reinterpret_cast<const float4*>(a.w2 + (size_t)d * a.H) + h4)
-                                           : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
     const bool lane_ok = lane < H4;
-    for (long long p0 = ((long long)blockIdx.x * nw + warp) * 4; p0 < a.npos; p0 += (long long)gridDim.x * nw * 4) {
-        float4 v[4];
+    float4 w[D];
+    float bias[D];
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
-            v[u] = (lane_ok && p0 + u < a.npos) ? __ldg(reinterpret_cast<const float4*>(a.h1 + (p0 + u) * a.H) + lane)
-                                                : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int d = 0; d < D; ++d) {
+        w[d] = lane_ok ? __ldg(reinterpret_cast<const float4*>(a.w2 + (size_t)d * a.H) + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+        bias[d] = a.b2 ? __ldg(a.b2 + d) : 0.f;
+    }
+    const int vsel = ((lane >> 2) & 1) + 2 * ((lane >> 3) & 1) + 4 * ((lane >> 4) & 1);   // position this lane ends up owning
+    for (long long p0 = ((long long)blockIdx.x * nw + warp) * 8; p0 < a.npos; p0 += (long long)gridDim.x * nw * 8) {
+        float4 v[8];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            float s[kHeadMaxD];
+        for (int u = 0; u < 8; ++u)
+            v[u] = (lane_ok && p0 + u < a.npos) ? tc::ld_stream4(a.h1 + (p0 + u) * a.H + lane * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        float s[D][8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
             const float4 t = make_float4(gelu_erf(v[u].x), gelu_erf(v[u].y), gelu_erf(v[u].z), gelu_erf(v[u].w));
 #pragma unroll
-            for (int d = 0; d < kHeadMaxD; ++d) s[d] = t.x * w[d][0].x + t.y * w[d][0].y + t.z * w[d][0].z + t.w * w[d][0].w;
+            for (int d = 0; d < D; ++d) s[d][u] = t.x * w[d].x + t.y * w[d].y + t.z * w[d].z + t.w * w[d].w;
+        }
 #pragma unroll
-            for (int d = 0; d < kHeadMaxD; ++d)
+        for (int d = 0; d < D; ++d) {
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) s[d] += __shfl_xor_sync(0xffffffffu, s[d], o);
-            if (lane == 0 && p0 + u < a.npos)
-                for (int d = 0; d < a.D; ++d) a.out[(p0 + u) * a.D + d] = s[d] + (a.b2 ? __ldg(a.b2 + d) : 0.f);
+            for (int i = 0; i < 4; ++i) {                       // lanes with bit 4 set keep positions 4..7
+                const bool hi = lane & 16;
+                const float recv = __shfl_xor_sync(0xffffffffu, hi ? s[d][i] : s[d][i + 4], 16);
+                s[d][i] = (hi ? s[d][i + 4] : s[d][i]) + recv;
+            }
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const bool hi = lane & 8;
+                const float recv = __shfl_xor_sync(0xffffffffu, hi ? s[d][i] : s[d][i + 2], 8);
+                s[d][i] = (hi ? s[d][i + 2] : s[d][i]) + recv;
+            }
+            {
+                const bool hi = lane & 4;
+                const float recv = __shfl_xor_sync(0xffffffffu, hi ? s[d][0] : s[d][1], 4);
+                s[d][0] = (hi ? s[d][1] : s[d][0]) + recv;
+            }
+            s[d][0] += __shfl_xor_sync(0xffffffffu, s[d][0], 2);
+            s[d][0] += __shfl_xor_sync(0xffffffffu, s[d][0], 1);
+        }
+        if ((lane & 3) == 0 && p0 + vsel < a.npos) {
+#pragma unroll
+            for (int d = 0; d < D; ++d) a.out[(p0 + vsel) * a.D + d] = s[d][0] + bias[d];
         }
     }
 }
@@ -351,7 +384,10 @@ int fnm_lift_fwd(const float* x, const float* w, const float* b, float* out, int
     const int grid = nrows < kEndBlocks * 8 ? nrows : kEndBlocks * 8;
     {
         LaunchScope ls("lift_fwd", as_stream(stream));
-        lift_fwd_kernel<<<grid, 256, (a.J + 1) * C * sizeof(float), as_stream(stream)>>>(a);
+        int threads = 256;
+        if (threads < C / 4) threads = (C / 4 + 31) / 32 * 32;              // C <= 512 (lift_ok): at most 128 groups
+        if (a.J <= 4) lift_fwd_kernel<4><<<grid, threads, 0, as_stream(stream)>>>(a);
+        else lift_fwd_kernel<kLiftMaxJ><<<grid, threads, 0, as_stream(stream)>>>(a);
     }
     return check_launch("lift_fwd");
 }
@@ -400,11 +436,16 @@ int fnm_mlp_head_fwd(const float* h1, const float* w2, const float* b2, float* o
     HeadArgs a{};
     a.h1 = h1; a.w2 = w2; a.b2 = b2; a.out = out; a.npos = npos; a.H = H; a.D = D;
     if (npos <= 0) return FNM_OK;
-    const long long want = (npos + 31) / 32;
+    const long long want = (npos + 63) / 64;                          // 8 warps x 8 positions per block iteration
     const int grid = (int)(want < kEndBlocks * 4 ? want : kEndBlocks * 4);
     {
         LaunchScope ls("mlp_head_fwd", as_stream(stream));
-        head_fwd_kernel<<<grid, 256, 0, as_stream(stream)>>>(a);
+        switch (D) {
+            case 1: head_fwd_kernel<1><<<grid, 256, 0, as_stream(stream)>>>(a); break;
+            case 2: head_fwd_kernel<2><<<grid, 256, 0, as_stream(stream)>>>(a); break;
+            case 3: head_fwd_kernel<3><<<grid, 256, 0, as_stream(stream)>>>(a); break;
+            default: head_fwd_kernel<4><<<grid, 256, 0, as_stream(stream)>>>(a); break;
+        }
     }
     return check_launch("mlp_head_fwd");
 }
