@@ -223,7 +223,8 @@ def run_ours(args, rank, world):
     model = build_model(family, kw).to(dev)
     fnm_b200.parallel.broadcast_parameters(model)
     opt = fnm_b200.Adam(model.parameters(), lr=1e-3, weight_decay=1e-4, capturable=args.graph)
-    grads = FlatGradients(model.parameters(), direct_spectral=True)   # dW kernels write into the flat buffer
+    grads = FlatGradients(model.parameters(), direct_spectral=True,       # dW kernels write into the flat buffer
+                          overlap=os.environ.get("FNM_BENCH_OVERLAP", "1") == "1")   # slots exchanged as backward fills them (N > 1)
 
     x_host = synth((batch,) + xshape, 1234 + rank).pin_memory()
     x = x_host.to(dev)

@@ -195,6 +195,9 @@ class FourierLayerFn(torch.autograd.Function):
         for sink, dw in ((s0, dw0), (s1, dw1)):
             if sink is not None and dw is not None and dw is not sink:
                 sink.copy_(dw)
+            ready = getattr(sink, "_fnm_on_ready", None) if sink is not None else None
+            if ready is not None:
+                ready()                                             # FlatGradients(overlap=True): start this slot's exchange
         return (g_in, None, None if s0 is not None else dw0, None if s1 is not None else dw1, dwc, dbc, None, None, None, None)
 
 

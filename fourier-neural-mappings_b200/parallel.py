@@ -24,8 +24,13 @@ class FlatGradients:
     those slots.  It assumes what holds for every model here: each spectral weight enters exactly one
     autograd Function per step and ``zero_()`` is called before every backward (a second use raises)."""
 
-    def __init__(self, params, direct_spectral=False):
+    def __init__(self, params, direct_spectral=False, overlap=False):
         self.params = [p for p in params if p.requires_grad]
+        # overlap (needs direct_spectral): each spectral weight's slot is all-reduced as soon as the backward kernel
+        # that fills it has been enqueued (asynchronously, on the process group's stream), so the exchange of the deep
+        # layers runs under the backward pass of the shallow ones; all_reduce() then handles the rest and joins.
+        self.overlap = bool(overlap and direct_spectral)
+        self._pending = []
         if not self.params:
             raise ValueError("no trainable parameters")
         self.direct = bool(direct_spectral)
@@ -54,6 +59,7 @@ class FlatGradients:
             p.grad = view
             if self.direct and p.is_complex():
                 p._fnm_grad_sink, p._fnm_sink_uses = view, 0
+                view._fnm_on_ready = (lambda c=chunk: self._sink_ready(c)) if self.overlap else None
 
     def zero_(self):
         """Replacement for ``optimizer.zero_grad()``: keeps the views alive (set_to_none would drop them)."""
@@ -67,9 +73,21 @@ class FlatGradients:
                 if p.is_complex():
                     p._fnm_sink_uses = 0
 
+    def _sink_ready(self, chunk):
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            self._pending.append(dist.all_reduce(chunk, op=dist.ReduceOp.SUM, async_op=True))
+
     def all_reduce(self, group=None, async_op=False):
         """SUM over ranks; no-op in a single-process run."""
         if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+            return None
+        if self.overlap and self._pending:
+            # the sinks are already in flight: exchange the head (everything that is not a sink), then join
+            work = dist.all_reduce(self.flat[:self.head], op=dist.ReduceOp.SUM, group=group, async_op=True)
+            for w in self._pending:
+                w.wait()
+            self._pending = []
+            work.wait()
             return None
         return dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
 
