@@ -226,12 +226,19 @@ def _oracle_layer(x, w1, w2, wc, bc, act):
     dict(B=2, C=20, P=(24, 20), m=(5, 7)),            # channel count that is no multiple of 16
     dict(B=4, C=64, P=(1152,), m=(16,)),              # config 2 layer (1-D)
     dict(B=2, C=24, P=(45,), m=(9,)),                 # odd 1-D grid
+    dict(B=5, C=128, P=(20, 33), m=(4, 9)),           # batch / mode counts that are no multiples of 4 on the tcgen05 kernels
+    dict(B=1, C=16, P=(17, 30), m=(3, 5)),            # single sample, 16 channels (8 rows folded into the 128 lanes)
+    dict(B=3, C=96, P=(18, 24), m=(7, 6)),            # 96 channels: not a power of two, above 64
 ])
 def test_fused_layers_vs_oracle(shape):
     """Two chained fused layers (GELU between them is applied on load) + trailing GELU, forward and
     all gradients, against the CPU oracle."""
-    torch.manual_seed(5)
-    B, C, P, m = shape["B"], shape["C"], shape["P"], shape["m"]
+    check_fused_layers(shape["B"], shape["C"], shape["P"], shape["m"], seed=5)
+
+
+def check_fused_layers(B, C, P, m, seed=5):
+    """Shared by the test above and tools/shape_sweep.py (random shapes)."""
+    torch.manual_seed(seed)
     one_d = len(P) == 1
     Sc = (lambda: S.SpectralConv1d(C, C, m[0])) if one_d else (lambda: S.SpectralConv2d(C, C, m[0], m[1]))
     Conv = torch.nn.Conv1d if one_d else torch.nn.Conv2d
