@@ -354,6 +354,8 @@ pw2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUt
         // =========================================================================== MMA issuer
         const uint32_t sbase = smem_u32(smem);
         const uint32_t lo_base0 = smem_u32(lo_buf);
+        // One MMA shape for every tile.  Issuing the half-empty last tile of a row with a narrower N (idesc N = 32) was
+        // measured 10-14 % SLOWER overall: alternating instruction shapes costs more than the columns it saves.
         const uint32_t idesc = make_idesc(128, a.NT);
         const int nks2 = a.LYp / 8;                                   // k-steps over the (padded) mode axis
         const uint32_t slab16 = (uint32_t)a.NT * 8u;                  // slab stride in 16-byte descriptor units
