@@ -46,6 +46,7 @@ struct TgArgs {
     int C, G, GL, CB, items;
     int Kt, Mt, nchunks, NT, ntiles, dbl, nbuf, reuse, resident, slots, nmain, ncorr;
     int act, single_pass, tab_vec4;
+    int pairs;                                             // A loaders take pairs of chunks (needs 4 A buffers) instead of single chunks
     int tab_tma;                                           // streamed table: raw slabs arrive by TMA, the table warps only derive the remainder
 };
 
@@ -377,7 +378,7 @@ __global__ void __launch_bounds__(kTgThreads, 1) tabgemm_tc(const __grid_constan
         // With a streamed table TMEM only has room for two A buffers (three accumulators): each warpgroup
         // then takes single chunks, alternating, so one warpgroup's loads fly while the other converts.
         float va[32], vb[32];
-        if (a.resident) {
+        if (a.pairs) {
             for (uint32_t q = 2u * (uint32_t)wg; q < total; q += 2u * kTgNwg) {
                 load(va, q);
                 const bool two = q + 1 < total;
@@ -398,6 +399,11 @@ __global__ void __launch_bounds__(kTgThreads, 1) tabgemm_tc(const __grid_constan
     if (warp == 4) tmem_dealloc(tmem_base, 512);
 }
 
+static bool tg_force_singles() {
+    const char* e = getenv("FNM_TG_SINGLES");
+    return e && e[0] == '1';
+}
+
 // tile / buffer configuration; returns false when the shape is outside what the kernel serves
 static bool tg_configure(TgArgs& a) {
     if (a.Kt < 1 || a.Mt < 1 || a.G < 1) return false;
@@ -414,7 +420,8 @@ static bool tg_configure(TgArgs& a) {
             if (NT > 128) continue;
             for (int dbl = 1; dbl >= 0; --dbl) {
                 const bool will_stream = (uint64_t)a.nchunks * ntiles * NT * 256u > kTgSmemBudget || a.nchunks * ntiles > kTgMaxSlots;
-                const int nwg_a = will_stream ? 1 : kTgNwg;        // buffers needed: 2 per warpgroup (pairs), or 1 each when streaming
+                const bool singles = will_stream || tg_force_singles();
+                const int nwg_a = singles ? 1 : kTgNwg;            // buffers needed: 2 per warpgroup (pairs), or 1 each (single chunks)
                 // long contractions split the main chain over two accumulators when TMEM allows (truncation bias)
                 int nmain = (a.nchunks >= 8 && 3 * NT * (dbl ? 2 : 1) + 64 * 2 * nwg_a <= 512) ? 2 : 1;
                 if (dbl && nmain == 1 && a.nchunks >= 8 && 3 * NT + 64 * 2 * nwg_a <= 512) continue;   // accuracy first: single-buffered D with two chains
@@ -440,7 +447,7 @@ static bool tg_configure(TgArgs& a) {
                     if (slots < 2) continue;
                 }
                 a.NT = NT; a.ntiles = ntiles; a.dbl = dbl; a.nbuf = nbuf; a.reuse = reuse ? 1 : 0; a.nmain = nmain; a.ncorr = ncorr;
-                a.resident = resident ? 1 : 0; a.slots = slots;
+                a.resident = resident ? 1 : 0; a.slots = slots; a.pairs = (resident && !singles) ? 1 : 0;
                 return true;
             }
         }
