@@ -81,6 +81,48 @@ def test_two_rank_sum_allreduce_equals_global_batch_gradient():
     assert torch.allclose(res["flat"], grads.flat, rtol=1e-5, atol=1e-7)
 
 
+def _worker_overlap(rank, world, port, out):
+    """Sink slots exchanged one by one (what the CUDA backward triggers through ``_fnm_on_ready``), the rest after:
+    the result must be the plain flat SUM.  The spectral weight is stored mode-major like the drop-in modules' own."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.manual_seed(3)
+        model = Toy()
+        model.w = torch.nn.Parameter(model.w.detach().permute(2, 0, 1).contiguous().permute(1, 2, 0))   # mode-major storage
+        broadcast_parameters(model)                          # storage-order view of a non-contiguous parameter
+        grads = FlatGradients(model.parameters(), direct_spectral=True, overlap=True)
+        assert model.w.grad.stride() == model.w.stride() and grads.head < grads.flat.numel()
+        grads.zero_()
+        grads.flat.copy_(torch.arange(grads.flat.numel(), dtype=torch.float32) * (rank + 1))
+        model.w._fnm_grad_sink._fnm_on_ready()               # the backward kernel would do this after writing the slot
+        assert len(grads._pending) == 1
+        grads.all_reduce()
+        assert not grads._pending
+        if rank == 0:
+            out.put((grads.flat.clone(), list(grads.offsets)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_two_rank_overlapped_slot_exchange_equals_flat_sum():
+    world = 2
+    ctx = mp.get_context("spawn")
+    out = ctx.SimpleQueue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_overlap, args=(r, world, port, out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    flat, offsets = out.get()
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    want = torch.arange(flat.numel(), dtype=torch.float32) * 3          # rank 0 held 1x, rank 1 held 2x
+    for off, n in offsets:                                                # every parameter's slot (alignment gaps are unused)
+        assert torch.equal(flat[off:off + n], want[off:off + n])
+
+
 def test_shard_batch_and_flat_layout():
     x = torch.arange(24.0).reshape(8, 3)
     assert torch.equal(shard_batch(x, 1, 4), x[2:4])
