@@ -237,6 +237,8 @@ __device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&r)[3
 // cuTensorMapEncodeTiled through the runtime's driver entry point (fnm_tc_pw2.cu); fp32 elements, strides in bytes
 bool tc_make_map(CUtensorMap* m, const float* ptr, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
                  const cuuint32_t* box, bool swizzle128);
+bool tc_make_map_swz(CUtensorMap* m, const float* ptr, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+                     const cuuint32_t* box, CUtensorMapSwizzle swizzle);
 int sm_count();
 bool tc_enabled();
 

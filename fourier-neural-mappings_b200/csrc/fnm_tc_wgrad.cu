@@ -26,6 +26,8 @@
 // flight per SM), 8-11 flush/epilogue warpgroup, 12 MMA issuer.  13 warps -> 128 registers.
 #include "fnm_tc_ptx.cuh"
 
+#include <cstdlib>
+
 namespace fnm {
 namespace tc {
 
@@ -266,6 +268,189 @@ __global__ void conv_wgrad_tc_reduce(const float* __restrict__ part, int nparts,
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// TMA variant for 128 (folded) channels without an activation on load.  Both operands are [pos][channel] with the
+// channel contiguous, i.e. MN-major for a contraction over positions: g is the A operand (M = o), x the B operand
+// (N = i), both straight from TMA boxes of 32 positions x 32 channels -- no register staging, no transposition.
+// kind::tf32 accepts MN-major shared-memory operands only in the SWIZZLE_128B_BASE32B layout (128-byte rows whose 32-byte
+// chunks are XORed with row & 3; TMA: CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B); with the ordinary 128-byte swizzle the
+// instruction returns zeros (tools/probes/mn_major_probe.cu).  Descriptor: LBO = distance of two 32-channel blocks,
+// SBO = distance of two 4-row k groups (512 B), one k-step of 8 positions = 1024 B.
+//   main  D += g_raw * x_raw        corrections  D += g_lo * x_raw + g_raw * x_lo   (lo tiles: converter warps, smem -> smem)
+// The accumulator is flushed every kCwSegChunks chunks into REGISTERS of the 8 flush warps (64 columns each).
+// Warps: 0 TMA producer | 1 MMA issuer | 2-5 converters (+ column sums of g for db) | 6-13 flush / epilogue.
+constexpr int kW2Raw = 4, kW2Lo = 2;
+constexpr uint32_t kW2Tile = 32768;                        // g: 4 channel blocks x [32 pos][128 B] | x: the same
+constexpr int kW2Threads = 14 * 32;
+
+__device__ __forceinline__ uint64_t desc_mn32(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3fff);
+    d |= (uint64_t)(4096 >> 4) << 16;                      // LBO: next 32-channel block
+    d |= (uint64_t)(512 >> 4) << 32;                       // SBO: next group of 4 positions
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)1 << 61;                                // SWIZZLE_128B_BASE32B
+    return d;
+}
+
+__global__ void __launch_bounds__(kW2Threads, 1)
+conv_wgrad_tma(const __grid_constant__ CUtensorMap mapG, const __grid_constant__ CUtensorMap mapX, const CwArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* lo_ring = smem + kW2Raw * kW2Tile;
+    float* dbs = reinterpret_cast<float*>(lo_ring + kW2Lo * kW2Tile);                    // [128] column sums of g
+    uint64_t* bars = reinterpret_cast<uint64_t*>(dbs + 128);
+    uint64_t* raw_full = bars;                     // [kW2Raw] TMA transaction barriers
+    uint64_t* raw_empty = bars + kW2Raw;           // [kW2Raw] MMA commit + 4 converter warps (they read the tile for db in every mode)
+    uint64_t* lo_full = bars + 2 * kW2Raw;         // [kW2Lo]  4 converter warps
+    uint64_t* lo_empty = lo_full + kW2Lo;          // [kW2Lo]  MMA commit
+    uint64_t* seg_full = lo_empty + kW2Lo;         // [2]
+    uint64_t* seg_empty = seg_full + 2;            // [2] 8 flush warps
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(seg_empty + 2);
+
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kW2Raw; ++s) { mbar_init(&raw_full[s], 1); mbar_init(&raw_empty[s], 5); }
+        for (int s = 0; s < kW2Lo; ++s) { mbar_init(&lo_full[s], 4); mbar_init(&lo_empty[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&seg_full[s], 1); mbar_init(&seg_empty[s], 8); }
+        fence_barrier_init();
+        tma_prefetch_desc(&mapG); tma_prefetch_desc(&mapX);
+    }
+    if (threadIdx.x < 128) dbs[threadIdx.x] = 0.f;
+    if (warp == 1) tmem_alloc(tmem_slot, 256);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+
+    const long long c0 = (long long)blockIdx.x * a.per;
+    const long long c1 = c0 + a.per < a.nchunks ? c0 + a.per : a.nchunks;
+    const uint32_t n = c1 > c0 ? (uint32_t)(c1 - c0) : 0u;
+    const uint32_t nseg = (n + kCwSegChunks - 1) / kCwSegChunks;
+
+    if (warp == 0) {
+        // =========================================================================== TMA producer
+        if (lane == 0) {
+            for (uint32_t q = 0; q < n; ++q) {
+                const uint32_t s = q % kW2Raw;
+                mbar_wait(&raw_empty[s], ((q / kW2Raw) & 1) ^ 1);
+                mbar_expect_tx(&raw_full[s], kW2Tile);
+                uint8_t* st = smem + (size_t)s * kW2Tile;
+                const int row = (int)((c0 + q) * 32);
+                for (int j = 0; j < 4; ++j) {
+                    tma_load_2d(&mapG, &raw_full[s], st + j * 4096, j * 32, row);
+                    tma_load_2d(&mapX, &raw_full[s], st + 16384 + j * 4096, j * 32, row);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // =========================================================================== MMA issuer
+        const uint32_t sbase = smem_u32(smem), lbase = smem_u32(lo_ring);
+        const uint32_t idesc = make_idesc(128, 128) | (1u << 15) | (1u << 16);          // A and B MN-major
+        for (uint32_t q = 0; q < n; ++q) {
+            const uint32_t seg = q / kCwSegChunks, buf = seg & 1, first = (q % kCwSegChunks) == 0;
+            if (first) mbar_wait(&seg_empty[buf], ((seg >> 1) & 1) ^ 1);
+            const uint32_t s = q % kW2Raw, l = q % kW2Lo;
+            const uint32_t d = tmem_base + buf * 128u;
+            mbar_wait(&raw_full[s], (q / kW2Raw) & 1);
+            tc_fence_after();
+            const uint32_t g_raw = sbase + s * kW2Tile, x_raw = g_raw + 16384u;
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks)
+                umma_ss(d, desc_mn32(g_raw + ks * 1024u), desc_mn32(x_raw + ks * 1024u), idesc, (first && ks == 0) ? 0u : 1u);
+            if (!a.single_pass) {
+                mbar_wait(&lo_full[l], (q / kW2Lo) & 1);
+                tc_fence_after();
+                const uint32_t g_lo = lbase + l * kW2Tile, x_lo = g_lo + 16384u;
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) {
+                    umma_ss(d, desc_mn32(g_lo + ks * 1024u), desc_mn32(x_raw + ks * 1024u), idesc, 1u);
+                    umma_ss(d, desc_mn32(g_raw + ks * 1024u), desc_mn32(x_lo + ks * 1024u), idesc, 1u);
+                }
+                umma_commit(&lo_empty[l]);
+            }
+            umma_commit(&raw_empty[s]);
+            if ((q % kCwSegChunks) == kCwSegChunks - 1 || q == n - 1) umma_commit(&seg_full[buf]);
+            __syncwarp();
+        }
+    } else if (warp < 6) {
+        // =========================================================================== converters: lo = raw - trunc(raw), db
+        const int ct = (int)threadIdx.x - 64;                        // 0..127
+        const int pair = ct & 31, rgrp = ct >> 5;                    // (channel block j, 16-byte chunk c) and row group
+        const int j = pair >> 3, c = pair & 7;
+        float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (uint32_t q = 0; q < n; ++q) {
+            const uint32_t s = q % kW2Raw, l = q % kW2Lo;
+            mbar_wait(&raw_full[s], (q / kW2Raw) & 1);
+            const uint32_t src0 = smem_u32(smem) + s * kW2Tile, dst0 = smem_u32(lo_ring) + l * kW2Tile;
+            if (!a.single_pass) mbar_wait(&lo_empty[l], ((q / kW2Lo) & 1) ^ 1);
+#pragma unroll
+            for (int rr = 0; rr < 8; ++rr) {
+                const uint32_t r = (uint32_t)(rgrp + 4 * rr);
+                const uint32_t off = (uint32_t)j * 4096u + r * 128u + ((((uint32_t)c >> 1) ^ (r & 3u)) << 5) + ((uint32_t)c & 1u) * 16u;
+                float4 vg, vx;
+                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(vg.x), "=f"(vg.y), "=f"(vg.z), "=f"(vg.w) : "r"(src0 + off));
+                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(vx.x), "=f"(vx.y), "=f"(vx.z), "=f"(vx.w) : "r"(src0 + 16384u + off));
+                sum.x += vg.x; sum.y += vg.y; sum.z += vg.z; sum.w += vg.w;
+                if (!a.single_pass) {
+                    vg.x -= __uint_as_float(__float_as_uint(vg.x) & 0xffffe000u); vg.y -= __uint_as_float(__float_as_uint(vg.y) & 0xffffe000u);
+                    vg.z -= __uint_as_float(__float_as_uint(vg.z) & 0xffffe000u); vg.w -= __uint_as_float(__float_as_uint(vg.w) & 0xffffe000u);
+                    vx.x -= __uint_as_float(__float_as_uint(vx.x) & 0xffffe000u); vx.y -= __uint_as_float(__float_as_uint(vx.y) & 0xffffe000u);
+                    vx.z -= __uint_as_float(__float_as_uint(vx.z) & 0xffffe000u); vx.w -= __uint_as_float(__float_as_uint(vx.w) & 0xffffe000u);
+                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst0 + off), "f"(vg.x), "f"(vg.y), "f"(vg.z), "f"(vg.w) : "memory");
+                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst0 + 16384u + off), "f"(vx.x), "f"(vx.y), "f"(vx.z), "f"(vx.w) : "memory");
+                }
+            }
+            if (!a.single_pass) fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+                if (!a.single_pass) mbar_arrive(&lo_full[l]);
+                mbar_arrive(&raw_empty[s]);
+            }
+        }
+        // bias gradient: channel 32 j + 4 c + {0..3}; the four row groups meet in shared memory
+        atomicAdd(&dbs[32 * j + 4 * c + 0], sum.x); atomicAdd(&dbs[32 * j + 4 * c + 1], sum.y);
+        atomicAdd(&dbs[32 * j + 4 * c + 2], sum.z); atomicAdd(&dbs[32 * j + 4 * c + 3], sum.w);
+    } else {
+        // =========================================================================== flush / epilogue (8 warps)
+        const int ew = warp - 6, q4 = warp & 3, half = ew >> 2;      // TMEM lane quarter = warp % 4
+        const int o = q4 * 32 + lane;
+        float acc[64];
+#pragma unroll
+        for (int i = 0; i < 64; ++i) acc[i] = 0.f;
+        for (uint32_t seg = 0; seg < nseg; ++seg) {
+            const uint32_t buf = seg & 1;
+            mbar_wait(&seg_full[buf], (seg >> 1) & 1);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) + buf * 128u + (uint32_t)half * 64u;
+#pragma unroll
+            for (int g4 = 0; g4 < 4; ++g4) {
+                uint32_t r[16];
+                tmem_ld16(taddr + g4 * 16, r);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 16; ++i) acc[g4 * 16 + i] += __uint_as_float(r[i]);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&seg_empty[buf]);
+        }
+        float* pd = a.part + (size_t)blockIdx.x * cw_part_floats(a.Ci, a.Co) + (size_t)o * a.Ci + half * 64;
+#pragma unroll
+        for (int i = 0; i < 64; i += 4) *reinterpret_cast<float4*>(pd + i) = make_float4(acc[i], acc[i + 1], acc[i + 2], acc[i + 3]);
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x < 128) {
+        float* pb = a.part + (size_t)blockIdx.x * cw_part_floats(a.Ci, a.Co) + (size_t)a.Ci * a.Co;
+        pb[threadIdx.x] = dbs[threadIdx.x];
+        for (int w = 1; w < kCwLoaderWgs; ++w) pb[w * a.Co + threadIdx.x] = 0.f;
+    }
+    if (warp == 1) tmem_dealloc(tmem_base, 256);
+}
+
 static int cw_grid(int64_t npos) {
     const int64_t chunks = (npos + 31) / 32;
     return (int)(chunks < sm_count() ? chunks : sm_count());
@@ -300,6 +485,38 @@ int tc_conv_wgrad(const float* g, const float* x, int act, float* dwc, float* db
     a.nchunks = (a.npos + 31) / 32;
     const int grid = cw_grid(a.npos);
     a.per = (a.nchunks + grid - 1) / grid;
+    // 128 (folded) channels, no activation on load, aligned: operands straight from TMA (MN-major), no register staging
+    {
+        const char* e = getenv("FNM_WGRAD_NO_TMA");
+        const bool off = e && e[0] == '1';
+        if (!off && act == 0 && a.Ci == 128 && a.Co == 128 && ((reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(x)) & 15) == 0) {
+            CUtensorMap mg, mx;
+            const cuuint64_t dims[2] = {128, (cuuint64_t)a.npos};
+            const cuuint64_t str[1] = {128 * 4};
+            const cuuint32_t box[2] = {32, 32};
+            if (tc_make_map_swz(&mg, g, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B) &&
+                tc_make_map_swz(&mx, x, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) {
+                static bool attr2 = false;
+                const size_t smem2 = (size_t)(kW2Raw + kW2Lo) * kW2Tile + 128 * 4 + 1024 + 512;
+                if (!attr2) {
+                    const cudaError_t e2 = cudaFuncSetAttribute(conv_wgrad_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+                    if (e2 != cudaSuccess) return fail(FNM_ECUDA, "conv_wgrad: smem attribute: %s", cudaGetErrorString(e2));
+                    attr2 = true;
+                }
+                {
+                    LaunchScope ls("conv_wgrad", st);
+                    conv_wgrad_tma<<<grid, kW2Threads, smem2, st>>>(mg, mx, a);
+                }
+                FNM_TRY(check_launch("conv_wgrad"));
+                const int count2 = Co * Ci + Co;
+                {
+                    LaunchScope ls("conv_wgrad_reduce", st);
+                    conv_wgrad_tc_reduce<<<(count2 * 32 + 255) / 256, 256, 0, st>>>(partial, grid, Ci, Co, fold, dwc, dbc);
+                }
+                return check_launch("conv_wgrad_reduce");
+            }
+        }
+    }
     static bool attr_set = false;
     const size_t smem = kCwStages * kCwStageBytes + kCwAccBytes + 2048;   // > half the SM: one CTA per SM owns the TMEM
     if (!attr_set) {

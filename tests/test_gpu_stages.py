@@ -178,7 +178,10 @@ def test_table_stages(case, mode):
 
 
 @pytest.mark.parametrize("npos,Ci,Co,act", [(72 * 72 * 3, 32, 32, 1), (288 * 150, 128, 128, 0), (288 * 37 + 5, 128, 128, 1),
-                                            (1152 * 9, 64, 64, 1), (57 * 248, 32, 48, 0), (3000, 20, 20, 1)])
+                                            (1152 * 9, 64, 64, 1), (57 * 248, 32, 48, 0), (3000, 20, 20, 1),
+                                            # no activation on load: operands straight from TMA as MN-major tiles (128 channels,
+                                            # or 32 / 64 with positions folded into the channel axis); ragged last chunk
+                                            (288 * 37 + 5, 128, 128, 0), (72 * 72 * 4, 32, 32, 0), (1152 * 8 + 2, 64, 64, 0)])
 @pytest.mark.parametrize("mode", ["fp32", "tf32"])
 def test_conv_wgrad(npos, Ci, Co, act, mode):
     """dWc[o][i] = sum_pos g[pos][o] f(x[pos][i]), dbc[o] = sum_pos g[pos][o] against float64."""
