@@ -1,0 +1,244 @@
+// tc_ydft_tma -- the truncated DFT along y of a 128-channel channels-last activation with TMA-fed operands:
+//
+//     T[row][l'][c] = sum_y tab[l'][y] * x[row][y][c]          row = (sample, x) grid row, l' < LY <= 64, c < 128
+//
+// x[row] is [y][c] with c contiguous: MN-major for the contraction over y, so it is the A operand (M = c, lanes = c)
+// straight from TMA boxes of 32 y x 32 c in the SWIZZLE_128B_BASE32B layout (see fnm_tc_wgrad.cu); the table chunk
+// [l'][32 y] is the K-major B operand, also by TMA.  Nothing is staged through registers.  Converter warps derive the
+// remainder tiles (x_lo, tab_lo) shared memory -> shared memory; 3xTF32:
+//     main  D_m += x_raw * tab_raw          corrections  D_c += x_lo * tab_raw + x_raw * tab_lo
+// The table chunk is streamed (it is L2 resident) instead of kept in shared memory, which leaves room for a deep raw ring;
+// an item is a PAIR of grid rows so that each streamed table chunk serves two activation tiles.
+// Accuracy as in fnm_tc_tabgemm.cu: separate correction accumulator, chunks alternate between two main accumulators.
+// TMEM (per row of the pair): main0 | main1 | corr, 64 columns each.
+// Warps: 0 TMA producer | 1 MMA issuer | 2-5 converters | 6-13 epilogue (lane = channel, 128-byte coalesced stores).
+#include "fnm_tc_ptx.cuh"
+
+#include <cstdlib>
+
+namespace fnm {
+namespace tc {
+
+constexpr int kYdRaw = 3, kYdLo = 2;
+constexpr uint32_t kYdATile = 16384;                         // one row: 4 channel blocks x [32 y][128 B]
+constexpr uint32_t kYdStage = 2 * kYdATile + 8192;           // two rows + table chunk [64 l'][128 B]
+constexpr int kYdThreads = 14 * 32;
+
+struct YdArgs {
+    float* out;
+    long long rows;
+    int P2, LY, NT, nch, single_pass;
+    long long pairs;
+};
+
+__device__ __forceinline__ uint64_t yd_desc_mn32(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3fff);
+    d |= (uint64_t)(4096 >> 4) << 16;                      // LBO: next 32-channel block
+    d |= (uint64_t)(512 >> 4) << 32;                       // SBO: next group of 4 y
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)1 << 61;                                // SWIZZLE_128B_BASE32B
+    return d;
+}
+
+__global__ void __launch_bounds__(kYdThreads, 1)
+ydft_tma(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapT, const YdArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* lo_ring = smem + kYdRaw * kYdStage;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(lo_ring + kYdLo * kYdStage);
+    uint64_t* raw_full = bars;                     // [kYdRaw] TMA transaction barriers
+    uint64_t* raw_empty = bars + kYdRaw;           // [kYdRaw] MMA commit + 4 converter warps
+    uint64_t* lo_full = bars + 2 * kYdRaw;         // [kYdLo] 4 converter warps
+    uint64_t* lo_empty = lo_full + kYdLo;          // [kYdLo] MMA commit
+    uint64_t* d_full = lo_empty + kYdLo;           // [1]
+    uint64_t* d_empty = d_full + 1;                // [1] 8 epilogue warps
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d_empty + 1);
+
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+    const int nconv = a.single_pass ? 0 : 4;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kYdRaw; ++s) { mbar_init(&raw_full[s], 1); mbar_init(&raw_empty[s], 1 + nconv); }
+        for (int s = 0; s < kYdLo; ++s) { mbar_init(&lo_full[s], 4); mbar_init(&lo_empty[s], 1); }
+        mbar_init(d_full, 1); mbar_init(d_empty, 8);
+        fence_barrier_init();
+        tma_prefetch_desc(&mapX); tma_prefetch_desc(&mapT);
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+
+    const long long my_pairs = (a.pairs - (long long)blockIdx.x + (long long)gridDim.x - 1) / (long long)gridDim.x;
+    const uint32_t nch = (uint32_t)a.nch;
+    const uint32_t total = (uint32_t)my_pairs * nch;
+
+    if (warp == 0) {
+        // =========================================================================== TMA producer
+        if (lane == 0) {
+            for (uint32_t q = 0; q < total; ++q) {
+                const uint32_t it = q / nch, ch = q - it * nch, s = q % kYdRaw;
+                const long long pair = (long long)blockIdx.x + (long long)it * gridDim.x;
+                mbar_wait(&raw_empty[s], ((q / kYdRaw) & 1) ^ 1);
+                const bool two = pair * 2 + 1 < a.rows;
+                mbar_expect_tx(&raw_full[s], (two ? 2u : 1u) * kYdATile + 8192u);
+                uint8_t* st = smem + (size_t)s * kYdStage;
+                for (int j = 0; j < (two ? 2 : 1); ++j)
+                    for (int cb = 0; cb < 4; ++cb)
+                        tma_load_3d(&mapX, &raw_full[s], st + j * kYdATile + cb * 4096, cb * 32, (int)ch * 32, (int)(pair * 2 + j));
+                tma_load_2d(&mapT, &raw_full[s], st + 2 * kYdATile, (int)ch * 32, 0);
+            }
+        }
+    } else if (warp == 1) {
+        // =========================================================================== MMA issuer
+        const uint32_t sbase = smem_u32(smem), lbase = smem_u32(lo_ring);
+        const uint32_t idesc = make_idesc(128, a.NT) | (1u << 15);                  // A MN-major, B K-major
+        uint32_t q = 0;
+        for (uint32_t it = 0; it < (uint32_t)my_pairs; ++it) {
+            mbar_wait(d_empty, (it & 1) ^ 1);
+            tc_fence_after();
+            for (uint32_t ch = 0; ch < nch; ++ch, ++q) {
+                const uint32_t s = q % kYdRaw, l = q % kYdLo;
+                mbar_wait(&raw_full[s], (q / kYdRaw) & 1);
+                tc_fence_after();
+                const uint32_t st = sbase + s * kYdStage, t_raw = st + 2 * kYdATile;
+                const uint32_t mi = ch & 1u, first_m = ch < 2u ? 0u : 1u, first_c = ch == 0u ? 0u : 1u;
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const uint32_t dm = tmem_base + (uint32_t)j * 192u + mi * 64u;
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks)
+                        umma_ss(dm, yd_desc_mn32(st + j * kYdATile + ks * 1024u), make_desc(t_raw) + 2 * ks, idesc,
+                                (ks == 0) ? first_m : 1u);
+                }
+                if (!a.single_pass) {
+                    mbar_wait(&lo_full[l], (q / kYdLo) & 1);
+                    tc_fence_after();
+                    const uint32_t lt = lbase + l * kYdStage, t_lo = lt + 2 * kYdATile;
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        const uint32_t dc = tmem_base + (uint32_t)j * 192u + 128u;
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks) {
+                            umma_ss(dc, yd_desc_mn32(lt + j * kYdATile + ks * 1024u), make_desc(t_raw) + 2 * ks, idesc,
+                                    (ks == 0) ? first_c : 1u);
+                            umma_ss(dc, yd_desc_mn32(st + j * kYdATile + ks * 1024u), make_desc(t_lo) + 2 * ks, idesc, 1u);
+                        }
+                    }
+                    umma_commit(&lo_empty[l]);
+                }
+                umma_commit(&raw_empty[s]);
+            }
+            umma_commit(d_full);
+            __syncwarp();
+        }
+    } else if (warp < 6) {
+        // =========================================================================== converters: lo = raw - trunc(raw)
+        if (!a.single_pass) {
+            const uint32_t ct = threadIdx.x - 64u;                   // 0..127
+            for (uint32_t q = 0; q < total; ++q) {
+                const uint32_t s = q % kYdRaw, l = q % kYdLo;
+                mbar_wait(&raw_full[s], (q / kYdRaw) & 1);
+                mbar_wait(&lo_empty[l], ((q / kYdLo) & 1) ^ 1);
+                const uint32_t src = smem_u32(smem) + s * kYdStage + ct * 16u, dst = smem_u32(lo_ring) + l * kYdStage + ct * 16u;
+#pragma unroll 4
+                for (uint32_t off = 0; off < kYdStage; off += 2048u) {      // layout-preserving copy: 2 KB per pass of 128 threads
+                    float4 v;
+                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(src + off));
+                    v.x -= __uint_as_float(__float_as_uint(v.x) & 0xffffe000u); v.y -= __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
+                    v.z -= __uint_as_float(__float_as_uint(v.z) & 0xffffe000u); v.w -= __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
+                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst + off), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+                }
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) { mbar_arrive(&lo_full[l]); mbar_arrive(&raw_empty[s]); }
+            }
+        }
+    } else {
+        // =========================================================================== epilogue (8 warps)
+        const int q4 = warp & 3, half = (warp - 6) >> 2;             // TMEM lane quarter, column half of the 64 table rows
+        const int c = q4 * 32 + lane;
+        const int l0 = half * 32;
+        for (uint32_t it = 0; it < (uint32_t)my_pairs; ++it) {
+            const long long pair = (long long)blockIdx.x + (long long)it * gridDim.x;
+            mbar_wait(d_full, it & 1);
+            tc_fence_after();
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const long long row = pair * 2 + j;
+                const uint32_t taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)j * 192u + (uint32_t)l0;
+                uint32_t m0[32], m1[32], cc[32];
+                tmem_ld32(taddr, m0);
+                if (nch > 1) tmem_ld32(taddr + 64u, m1);
+                if (!a.single_pass) tmem_ld32(taddr + 128u, cc);
+                tmem_ld_wait();
+                if (row < a.rows) {
+                    float* op = a.out + ((size_t)row * a.LY + l0) * 128 + c;
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        if (l0 + i < a.LY) {
+                            float v = __uint_as_float(m0[i]);
+                            if (nch > 1) v += __uint_as_float(m1[i]);
+                            if (!a.single_pass) v += __uint_as_float(cc[i]);
+                            op[(size_t)i * 128] = v;
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(d_empty);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+}  // namespace tc
+
+using namespace tc;
+
+bool tc_ydft_tma_supported(const float* x, const float* tab, int64_t rows, int P2, int LY, int C, int act) {
+    if (!tc_enabled() || act != 0 || C != 128 || LY < 8 || LY > 64 || P2 % 4 != 0 || rows < 1 || rows >= (1LL << 30)) return false;
+    if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(tab)) & 15) return false;
+    const char* e = getenv("FNM_YDFT_NO_TMA");
+    return !(e && e[0] == '1');
+}
+
+int tc_ydft_tma(const float* x, const float* tab, float* T, int64_t rows, int P2, int LY, int mode, cudaStream_t st) {
+    YdArgs a{};
+    a.out = T; a.rows = rows; a.P2 = P2; a.LY = LY; a.NT = (LY + 15) / 16 * 16; a.nch = (P2 + 31) / 32;
+    a.single_pass = mode == FNM_MODE_TF32;
+    a.pairs = (rows + 1) / 2;
+    CUtensorMap mx, mt;
+    {
+        const cuuint64_t dims[3] = {128, (cuuint64_t)P2, (cuuint64_t)rows};
+        const cuuint64_t str[2] = {128 * 4, (cuuint64_t)P2 * 128 * 4};
+        const cuuint32_t box[3] = {32, 32, 1};
+        if (!tc_make_map_swz(&mx, x, 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return fail(FNM_ECUDA, "ydft: tensor map (x) failed");
+    }
+    {
+        const cuuint64_t dims[2] = {(cuuint64_t)P2, (cuuint64_t)LY};
+        const cuuint64_t str[1] = {(cuuint64_t)P2 * 4};
+        const cuuint32_t box[2] = {32, 64};
+        if (!tc_make_map(&mt, tab, 2, dims, str, box, true)) return fail(FNM_ECUDA, "ydft: tensor map (table) failed");
+    }
+    const size_t smem = (size_t)(kYdRaw + kYdLo) * kYdStage + 1024 + 256;
+    static bool attr_set = false;
+    if (!attr_set) {
+        const cudaError_t e = cudaFuncSetAttribute(ydft_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return fail(FNM_ECUDA, "ydft: smem attribute: %s", cudaGetErrorString(e));
+        attr_set = true;
+    }
+    const int grid = a.pairs < sm_count() ? (int)a.pairs : sm_count();
+    {
+        LaunchScope ls("ydft", st);
+        ydft_tma<<<grid, kYdThreads, smem, st>>>(mx, mt, a);
+    }
+    return check_launch("ydft");
+}
+
+}  // namespace fnm
