@@ -7,10 +7,13 @@
 // [l'][32 y] is the K-major B operand, also by TMA.  Nothing is staged through registers.  Converter warps derive the
 // remainder tiles (x_lo, tab_lo) shared memory -> shared memory; 3xTF32:
 //     main  D_m += x_raw * tab_raw          corrections  D_c += x_lo * tab_raw + x_raw * tab_lo
+// The table chunk and its remainder are stacked into ONE 128-row operand [tab_raw ; tab_lo], so x_raw * [tab_raw ; tab_lo]
+// is a single N = 128 MMA that feeds the main and the correction accumulator (adjacent TMEM columns) at once: two MMAs
+// and two reads of the activation slice per k-step instead of three.
 // The table chunk is streamed (it is L2 resident) instead of kept in shared memory, which leaves room for a deep raw ring;
 // an item is a PAIR of grid rows so that each streamed table chunk serves two activation tiles.
 // Accuracy as in fnm_tc_tabgemm.cu: separate correction accumulator, chunks alternate between two main accumulators.
-// TMEM (per row of the pair): main0 | main1 | corr, 64 columns each.
+// TMEM (per row of the pair): main0 | corr0 | main1 | corr1, 64 columns each (even / odd chunks).
 // Warps: 0 TMA producer | 1 MMA issuer | 2-5 converters | 6-13 epilogue (lane = channel, 128-byte coalesced stores).
 #include "fnm_tc_ptx.cuh"
 
@@ -21,7 +24,8 @@ namespace tc {
 
 constexpr int kYdRaw = 3, kYdLo = 2;
 constexpr uint32_t kYdATile = 16384;                         // one row: 4 channel blocks x [32 y][128 B]
-constexpr uint32_t kYdStage = 2 * kYdATile + 8192;           // two rows + table chunk [64 l'][128 B]
+constexpr uint32_t kYdStage = 2 * kYdATile + 16384;          // two rows + [table chunk ; its remainder] = [128 rows][128 B]
+constexpr uint32_t kYdLoStage = 2 * kYdATile;                // remainder tiles of the two rows
 constexpr int kYdThreads = 14 * 32;
 
 struct YdArgs {
@@ -46,7 +50,7 @@ ydft_tma(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUten
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t* lo_ring = smem + kYdRaw * kYdStage;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(lo_ring + kYdLo * kYdStage);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(lo_ring + kYdLo * kYdLoStage);
     uint64_t* raw_full = bars;                     // [kYdRaw] TMA transaction barriers
     uint64_t* raw_empty = bars + kYdRaw;           // [kYdRaw] MMA commit + 4 converter warps
     uint64_t* lo_full = bars + 2 * kYdRaw;         // [kYdLo] 4 converter warps
@@ -93,7 +97,8 @@ ydft_tma(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUten
     } else if (warp == 1) {
         // =========================================================================== MMA issuer
         const uint32_t sbase = smem_u32(smem), lbase = smem_u32(lo_ring);
-        const uint32_t idesc = make_idesc(128, a.NT) | (1u << 15);                  // A MN-major, B K-major
+        const uint32_t idesc128 = make_idesc(128, 128) | (1u << 15);                // A MN-major, B K-major
+        const uint32_t idesc64 = make_idesc(128, 64) | (1u << 15);
         uint32_t q = 0;
         for (uint32_t it = 0; it < (uint32_t)my_pairs; ++it) {
             mbar_wait(d_empty, (it & 1) ^ 1);
@@ -101,30 +106,27 @@ ydft_tma(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUten
             for (uint32_t ch = 0; ch < nch; ++ch, ++q) {
                 const uint32_t s = q % kYdRaw, l = q % kYdLo;
                 mbar_wait(&raw_full[s], (q / kYdRaw) & 1);
+                if (!a.single_pass) mbar_wait(&lo_full[l], (q / kYdLo) & 1);
                 tc_fence_after();
                 const uint32_t st = sbase + s * kYdStage, t_raw = st + 2 * kYdATile;
-                const uint32_t mi = ch & 1u, first_m = ch < 2u ? 0u : 1u, first_c = ch == 0u ? 0u : 1u;
+                const uint32_t lt = lbase + l * kYdLoStage;
+                const uint32_t first = ch < 2u ? 0u : 1u;
+                // x_raw * [tab_raw ; tab_lo] -> (main | corr) of this chunk parity, both rows, then x_lo * tab_raw -> corr
 #pragma unroll
                 for (int j = 0; j < 2; ++j) {
-                    const uint32_t dm = tmem_base + (uint32_t)j * 192u + mi * 64u;
+                    const uint32_t d = tmem_base + (uint32_t)j * 256u + (ch & 1u) * 128u;
 #pragma unroll
                     for (int ks = 0; ks < 4; ++ks)
-                        umma_ss(dm, yd_desc_mn32(st + j * kYdATile + ks * 1024u), make_desc(t_raw) + 2 * ks, idesc,
-                                (ks == 0) ? first_m : 1u);
+                        umma_ss(d, yd_desc_mn32(st + j * kYdATile + ks * 1024u), make_desc(t_raw) + 2 * ks,
+                                a.single_pass ? idesc64 : idesc128, (ks == 0) ? first : 1u);
                 }
                 if (!a.single_pass) {
-                    mbar_wait(&lo_full[l], (q / kYdLo) & 1);
-                    tc_fence_after();
-                    const uint32_t lt = lbase + l * kYdStage, t_lo = lt + 2 * kYdATile;
 #pragma unroll
                     for (int j = 0; j < 2; ++j) {
-                        const uint32_t dc = tmem_base + (uint32_t)j * 192u + 128u;
+                        const uint32_t dc = tmem_base + (uint32_t)j * 256u + (ch & 1u) * 128u + 64u;
 #pragma unroll
-                        for (int ks = 0; ks < 4; ++ks) {
-                            umma_ss(dc, yd_desc_mn32(lt + j * kYdATile + ks * 1024u), make_desc(t_raw) + 2 * ks, idesc,
-                                    (ks == 0) ? first_c : 1u);
-                            umma_ss(dc, yd_desc_mn32(st + j * kYdATile + ks * 1024u), make_desc(t_lo) + 2 * ks, idesc, 1u);
-                        }
+                        for (int ks = 0; ks < 4; ++ks)
+                            umma_ss(dc, yd_desc_mn32(lt + j * kYdATile + ks * 1024u), make_desc(t_raw) + 2 * ks, idesc64, 1u);
                     }
                     umma_commit(&lo_empty[l]);
                 }
@@ -141,14 +143,17 @@ ydft_tma(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUten
                 const uint32_t s = q % kYdRaw, l = q % kYdLo;
                 mbar_wait(&raw_full[s], (q / kYdRaw) & 1);
                 mbar_wait(&lo_empty[l], ((q / kYdLo) & 1) ^ 1);
-                const uint32_t src = smem_u32(smem) + s * kYdStage + ct * 16u, dst = smem_u32(lo_ring) + l * kYdStage + ct * 16u;
+                const uint32_t src = smem_u32(smem) + s * kYdStage + ct * 16u, dst = smem_u32(lo_ring) + l * kYdLoStage + ct * 16u;
+                // layout-preserving copies, 2 KB per pass of the 128 threads: the two activation tiles into the lo ring,
+                // the table chunk into the second half of its own stacked slab
 #pragma unroll 4
-                for (uint32_t off = 0; off < kYdStage; off += 2048u) {      // layout-preserving copy: 2 KB per pass of 128 threads
+                for (uint32_t off = 0; off < 2 * kYdATile + 8192u; off += 2048u) {
                     float4 v;
                     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(src + off));
                     v.x -= __uint_as_float(__float_as_uint(v.x) & 0xffffe000u); v.y -= __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
                     v.z -= __uint_as_float(__float_as_uint(v.z) & 0xffffe000u); v.w -= __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
-                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst + off), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+                    const uint32_t to = off < 2 * kYdATile ? dst + off : src + off + 8192u;
+                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(to), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
                 }
                 fence_proxy_async();
                 __syncwarp();
@@ -167,23 +172,26 @@ ydft_tma(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUten
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
                 const long long row = pair * 2 + j;
-                const uint32_t taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)j * 192u + (uint32_t)l0;
-                uint32_t m0[32], m1[32], cc[32];
-                tmem_ld32(taddr, m0);
-                if (nch > 1) tmem_ld32(taddr + 64u, m1);
-                if (!a.single_pass) tmem_ld32(taddr + 128u, cc);
+                const uint32_t taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)j * 256u + (uint32_t)l0;
+                uint32_t m0[32], m1[32];
+                tmem_ld32(taddr, m0);                               // main of the even chunks
+                if (nch > 1) tmem_ld32(taddr + 128u, m1);           // main of the odd chunks
                 tmem_ld_wait();
+                float v[32];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(m0[i]) + (nch > 1 ? __uint_as_float(m1[i]) : 0.f);
+                if (!a.single_pass) {
+                    tmem_ld32(taddr + 64u, m0);                     // corrections, even / odd chunks
+                    if (nch > 1) tmem_ld32(taddr + 192u, m1);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] += __uint_as_float(m0[i]) + (nch > 1 ? __uint_as_float(m1[i]) : 0.f);
+                }
                 if (row < a.rows) {
                     float* op = a.out + ((size_t)row * a.LY + l0) * 128 + c;
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        if (l0 + i < a.LY) {
-                            float v = __uint_as_float(m0[i]);
-                            if (nch > 1) v += __uint_as_float(m1[i]);
-                            if (!a.single_pass) v += __uint_as_float(cc[i]);
-                            op[(size_t)i * 128] = v;
-                        }
-                    }
+                    for (int i = 0; i < 32; ++i)
+                        if (l0 + i < a.LY) op[(size_t)i * 128] = v[i];
                 }
             }
             tc_fence_before();
@@ -226,7 +234,7 @@ int tc_ydft_tma(const float* x, const float* tab, float* T, int64_t rows, int P2
         const cuuint32_t box[2] = {32, 64};
         if (!tc_make_map(&mt, tab, 2, dims, str, box, true)) return fail(FNM_ECUDA, "ydft: tensor map (table) failed");
     }
-    const size_t smem = (size_t)(kYdRaw + kYdLo) * kYdStage + 1024 + 256;
+    const size_t smem = (size_t)kYdRaw * kYdStage + (size_t)kYdLo * kYdLoStage + 1024 + 256;
     static bool attr_set = false;
     if (!attr_set) {
         const cudaError_t e = cudaFuncSetAttribute(ydft_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
