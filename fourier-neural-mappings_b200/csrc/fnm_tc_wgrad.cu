@@ -278,10 +278,14 @@ __global__ void conv_wgrad_tc_reduce(const float* __restrict__ part, int nparts,
 // instruction returns zeros (tools/probes/mn_major_probe.cu).  Descriptor: LBO = distance of two 32-channel blocks,
 // SBO = distance of two 4-row k groups (512 B), one k-step of 8 positions = 1024 B.
 //   main  D += g_raw * x_raw        corrections  D += g_lo * x_raw + g_raw * x_lo   (lo tiles: converter warps, smem -> smem)
+// x_lo sits right behind x_raw, so g_raw * [x_raw ; x_lo] is ONE N = 256 MMA whose 256 accumulator columns are
+// (main | g_raw x_lo); g_lo * x_raw (N = 128) is added to the first half: two MMAs and two reads of the g slice per
+// k-step instead of three.  The epilogue adds the two halves.
 // The accumulator is flushed every kCwSegChunks chunks into REGISTERS of the 8 flush warps (64 columns each).
 // Warps: 0 TMA producer | 1 MMA issuer | 2-5 converters (+ column sums of g for db) | 6-13 flush / epilogue.
 constexpr int kW2Raw = 4, kW2Lo = 2;
-constexpr uint32_t kW2Tile = 32768;                        // g: 4 channel blocks x [32 pos][128 B] | x: the same
+constexpr uint32_t kW2Tile = 49152;                        // g: 4 channel blocks x [32 pos][128 B] | x: the same | x_lo
+constexpr uint32_t kW2LoTile = 16384;                      // g_lo
 constexpr int kW2Threads = 14 * 32;
 
 __device__ __forceinline__ uint64_t desc_mn32(uint32_t saddr) {
@@ -299,7 +303,7 @@ conv_wgrad_tma(const __grid_constant__ CUtensorMap mapG, const __grid_constant__
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t* lo_ring = smem + kW2Raw * kW2Tile;
-    float* dbs = reinterpret_cast<float*>(lo_ring + kW2Lo * kW2Tile);                    // [128] column sums of g
+    float* dbs = reinterpret_cast<float*>(lo_ring + kW2Lo * kW2LoTile);                    // [128] column sums of g
     uint64_t* bars = reinterpret_cast<uint64_t*>(dbs + 128);
     uint64_t* raw_full = bars;                     // [kW2Raw] TMA transaction barriers
     uint64_t* raw_empty = bars + kW2Raw;           // [kW2Raw] MMA commit + 4 converter warps (they read the tile for db in every mode)
@@ -318,7 +322,7 @@ conv_wgrad_tma(const __grid_constant__ CUtensorMap mapG, const __grid_constant__
         tma_prefetch_desc(&mapG); tma_prefetch_desc(&mapX);
     }
     if (threadIdx.x < 128) dbs[threadIdx.x] = 0.f;
-    if (warp == 1) tmem_alloc(tmem_slot, 256);
+    if (warp == 1) tmem_alloc(tmem_slot, 512);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -335,7 +339,7 @@ conv_wgrad_tma(const __grid_constant__ CUtensorMap mapG, const __grid_constant__
             for (uint32_t q = 0; q < n; ++q) {
                 const uint32_t s = q % kW2Raw;
                 mbar_wait(&raw_empty[s], ((q / kW2Raw) & 1) ^ 1);
-                mbar_expect_tx(&raw_full[s], kW2Tile);
+                mbar_expect_tx(&raw_full[s], 32768u);
                 uint8_t* st = smem + (size_t)s * kW2Tile;
                 const int row = (int)((c0 + q) * 32);
                 for (int j = 0; j < 4; ++j) {
@@ -347,27 +351,25 @@ conv_wgrad_tma(const __grid_constant__ CUtensorMap mapG, const __grid_constant__
     } else if (warp == 1) {
         // =========================================================================== MMA issuer
         const uint32_t sbase = smem_u32(smem), lbase = smem_u32(lo_ring);
-        const uint32_t idesc = make_idesc(128, 128) | (1u << 15) | (1u << 16);          // A and B MN-major
+        const uint32_t idesc128 = make_idesc(128, 128) | (1u << 15) | (1u << 16);       // A and B MN-major
+        const uint32_t idesc256 = make_idesc(128, 256) | (1u << 15) | (1u << 16);
         for (uint32_t q = 0; q < n; ++q) {
             const uint32_t seg = q / kCwSegChunks, buf = seg & 1, first = (q % kCwSegChunks) == 0;
             if (first) mbar_wait(&seg_empty[buf], ((seg >> 1) & 1) ^ 1);
             const uint32_t s = q % kW2Raw, l = q % kW2Lo;
-            const uint32_t d = tmem_base + buf * 128u;
+            const uint32_t d = tmem_base + buf * 256u;
             mbar_wait(&raw_full[s], (q / kW2Raw) & 1);
+            if (!a.single_pass) mbar_wait(&lo_full[l], (q / kW2Lo) & 1);
             tc_fence_after();
             const uint32_t g_raw = sbase + s * kW2Tile, x_raw = g_raw + 16384u;
+            const uint32_t g_lo = lbase + l * kW2LoTile;
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks)
-                umma_ss(d, desc_mn32(g_raw + ks * 1024u), desc_mn32(x_raw + ks * 1024u), idesc, (first && ks == 0) ? 0u : 1u);
+            for (int ks = 0; ks < 4; ++ks)          // (main | g_raw x_lo): the x_lo blocks continue x_raw's at the same 4096-byte stride
+                umma_ss(d, desc_mn32(g_raw + ks * 1024u), desc_mn32(x_raw + ks * 1024u), a.single_pass ? idesc128 : idesc256,
+                        (first && ks == 0) ? 0u : 1u);
             if (!a.single_pass) {
-                mbar_wait(&lo_full[l], (q / kW2Lo) & 1);
-                tc_fence_after();
-                const uint32_t g_lo = lbase + l * kW2Tile, x_lo = g_lo + 16384u;
 #pragma unroll
-                for (int ks = 0; ks < 4; ++ks) {
-                    umma_ss(d, desc_mn32(g_lo + ks * 1024u), desc_mn32(x_raw + ks * 1024u), idesc, 1u);
-                    umma_ss(d, desc_mn32(g_raw + ks * 1024u), desc_mn32(x_lo + ks * 1024u), idesc, 1u);
-                }
+                for (int ks = 0; ks < 4; ++ks) umma_ss(d, desc_mn32(g_lo + ks * 1024u), desc_mn32(x_raw + ks * 1024u), idesc128, 1u);
                 umma_commit(&lo_empty[l]);
             }
             umma_commit(&raw_empty[s]);
@@ -383,7 +385,7 @@ conv_wgrad_tma(const __grid_constant__ CUtensorMap mapG, const __grid_constant__
         for (uint32_t q = 0; q < n; ++q) {
             const uint32_t s = q % kW2Raw, l = q % kW2Lo;
             mbar_wait(&raw_full[s], (q / kW2Raw) & 1);
-            const uint32_t src0 = smem_u32(smem) + s * kW2Tile, dst0 = smem_u32(lo_ring) + l * kW2Tile;
+            const uint32_t src0 = smem_u32(smem) + s * kW2Tile, dst0 = smem_u32(lo_ring) + l * kW2LoTile;
             if (!a.single_pass) mbar_wait(&lo_empty[l], ((q / kW2Lo) & 1) ^ 1);
 #pragma unroll
             for (int rr = 0; rr < 8; ++rr) {
@@ -399,7 +401,7 @@ conv_wgrad_tma(const __grid_constant__ CUtensorMap mapG, const __grid_constant__
                     vx.x -= __uint_as_float(__float_as_uint(vx.x) & 0xffffe000u); vx.y -= __uint_as_float(__float_as_uint(vx.y) & 0xffffe000u);
                     vx.z -= __uint_as_float(__float_as_uint(vx.z) & 0xffffe000u); vx.w -= __uint_as_float(__float_as_uint(vx.w) & 0xffffe000u);
                     asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst0 + off), "f"(vg.x), "f"(vg.y), "f"(vg.z), "f"(vg.w) : "memory");
-                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst0 + 16384u + off), "f"(vx.x), "f"(vx.y), "f"(vx.z), "f"(vx.w) : "memory");
+                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(src0 + 32768u + off), "f"(vx.x), "f"(vx.y), "f"(vx.z), "f"(vx.w) : "memory");
                 }
             }
             if (!a.single_pass) fence_proxy_async();
@@ -423,14 +425,16 @@ conv_wgrad_tma(const __grid_constant__ CUtensorMap mapG, const __grid_constant__
             const uint32_t buf = seg & 1;
             mbar_wait(&seg_full[buf], (seg >> 1) & 1);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) + buf * 128u + (uint32_t)half * 64u;
+            const uint32_t taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) + buf * 256u + (uint32_t)half * 64u;
 #pragma unroll
             for (int g4 = 0; g4 < 4; ++g4) {
-                uint32_t r[16];
+                uint32_t r[16], r2[16];
                 tmem_ld16(taddr + g4 * 16, r);
+                if (!a.single_pass) tmem_ld16(taddr + 128u + g4 * 16, r2);          // the g_raw * x_lo half
                 tmem_ld_wait();
 #pragma unroll
-                for (int i = 0; i < 16; ++i) acc[g4 * 16 + i] += __uint_as_float(r[i]);
+                for (int i = 0; i < 16; ++i)
+                    acc[g4 * 16 + i] += __uint_as_float(r[i]) + (a.single_pass ? 0.f : __uint_as_float(r2[i]));
             }
             tc_fence_before();
             __syncwarp();
@@ -448,7 +452,7 @@ conv_wgrad_tma(const __grid_constant__ CUtensorMap mapG, const __grid_constant__
         pb[threadIdx.x] = dbs[threadIdx.x];
         for (int w = 1; w < kCwLoaderWgs; ++w) pb[w * a.Co + threadIdx.x] = 0.f;
     }
-    if (warp == 1) tmem_dealloc(tmem_base, 256);
+    if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
 static int cw_grid(int64_t npos) {
@@ -497,7 +501,7 @@ int tc_conv_wgrad(const float* g, const float* x, int act, float* dwc, float* db
             if (tc_make_map_swz(&mg, g, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B) &&
                 tc_make_map_swz(&mx, x, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) {
                 static bool attr2 = false;
-                const size_t smem2 = (size_t)(kW2Raw + kW2Lo) * kW2Tile + 128 * 4 + 1024 + 512;
+                const size_t smem2 = (size_t)kW2Raw * kW2Tile + (size_t)kW2Lo * kW2LoTile + 128 * 4 + 1024 + 512;
                 if (!attr2) {
                     const cudaError_t e2 = cudaFuncSetAttribute(conv_wgrad_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
                     if (e2 != cudaSuccess) return fail(FNM_ECUDA, "conv_wgrad: smem attribute: %s", cudaGetErrorString(e2));
