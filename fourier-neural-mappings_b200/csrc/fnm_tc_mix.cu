@@ -44,7 +44,8 @@ struct MxArgs {
     int conj, single_pass, a_pair, b_kcontig, o_pair;      // a_pair / o_pair: (re, im) adjacent -> 8-byte accesses
     int a_kc;                                              // A element (m, k, l) has k contiguous as (re, im) pairs: each lane reads its own 256-byte row
     int a_reuse;                                           // one A chunk per mode, kept in TMEM across the mode's n tiles
-    int b_tma;                                             // B rows are K-contiguous and 16-byte aligned: TMA brings the raw tile
+    int b_tma;                                             // TMA brings the raw B tile: 1 = rows K-contiguous (K-major operand), 2 = rows N-contiguous
+                                                           // (MN-major operand, SWIZZLE_128B_BASE32B: the weight gradient's spectra)
 };
 
 __device__ __forceinline__ float ldf(const float* p) {
@@ -56,6 +57,16 @@ __device__ __forceinline__ float2 ldf2(const float* p) {
     float2 v;
     asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
     return v;
+}
+
+__device__ __forceinline__ uint64_t desc_mn32_mix(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3fff);
+    d |= (uint64_t)(4096 >> 4) << 16;                      // LBO: the imaginary half
+    d |= (uint64_t)(512 >> 4) << 32;                       // SBO: next group of 4 k rows
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)1 << 61;                                // SWIZZLE_128B_BASE32B
+    return d;
 }
 
 // smem per B buffer: [raw | lo] x nchunks slabs of [64 rows = 32 re + 32 im][128 B]
@@ -146,7 +157,9 @@ __global__ void __launch_bounds__(kMxThreads, 1) mixgemm_tc(const __grid_constan
     } else if (warp == 4) {
         // =========================================================================== MMA issuer
         const uint32_t sbase = smem_u32(smem);
-        const uint32_t idesc = make_idesc(128, 2 * kMxN);
+        const bool mn = a.b_tma == 2;
+        const uint32_t idesc = make_idesc(128, 2 * kMxN) | (mn ? (1u << 16) : 0u);     // MN-major B for the TMA-fed weight gradient
+        const uint32_t kstep = mn ? 64u : 2u;                          // descriptor start-address units (16 B) per k-step of 8
         uint32_t q = 0;
         for (int it = 0; it < my_items; ++it) {
             const int db = it & 1, bb = it & 1;
@@ -162,14 +175,17 @@ __global__ void __launch_bounds__(kMxThreads, 1) mixgemm_tc(const __grid_constan
                     tc_fence_after();
                 }
                 const uint32_t ar = tmem_base + 128u * ab, arl = ar + 32u, ai = ar + 64u, ail = ar + 96u;
-                const uint64_t braw = make_desc(bs + (uint32_t)ch * 8192u), blo = make_desc(bs + half_bytes + (uint32_t)ch * 8192u);
+                // K-major: 64 rows (re | im) of 128 bytes.  MN-major (SWIZZLE_128B_BASE32B): 32 k rows of 32 n per half, the im
+                // half (second N block) 4096 bytes behind the re half, 4-row k groups 512 bytes apart
+                const uint64_t braw = mn ? desc_mn32_mix(bs + (uint32_t)ch * 8192u) : make_desc(bs + (uint32_t)ch * 8192u);
+                const uint64_t blo = mn ? desc_mn32_mix(bs + half_bytes + (uint32_t)ch * 8192u) : make_desc(bs + half_bytes + (uint32_t)ch * 8192u);
                 const int nks = min(4, (a.Kt - ch * 32 + 7) / 8);
 #pragma unroll
                 for (int ks = 0; ks < 4; ++ks) {
                     if (ks < nks) {
                         const uint32_t first = (ch == 0 && ks == 0) ? 0u : 1u;
                         const uint32_t k8 = ks * 8;
-                        const uint64_t br = braw + 2 * ks, bl = blo + 2 * ks;
+                        const uint64_t br = braw + kstep * ks, bl = blo + kstep * ks;
                         umma_ts(d_f, ar + k8, br, idesc, first);
                         umma_ts(d_e, ai + k8, br, idesc, first);
                         if (!a.single_pass) {
@@ -203,8 +219,9 @@ __global__ void __launch_bounds__(kMxThreads, 1) mixgemm_tc(const __grid_constan
             mbar_expect_tx(&braw_full[bb], half_bytes);
             for (int ch = 0; ch < a.nchunks; ++ch)
                 for (int ri = 0; ri < 2; ++ri) {
-                    tma_load_2d(&mapB, &braw_full[bb], base + (size_t)ch * 8192 + (size_t)ri * 4096, ch * 32,
-                                (m * 2 + ri) * a.Nt + n0);
+                    uint8_t* dst = base + (size_t)ch * 8192 + (size_t)ri * 4096;
+                    if (a.b_tma == 1) tma_load_2d(&mapB, &braw_full[bb], dst, ch * 32, (m * 2 + ri) * a.Nt + n0);
+                    else tma_load_2d(&mapB, &braw_full[bb], dst, n0, (m * 2 + ri) * a.Kt + ch * 32);   // 32 k rows of 32 n
                 }
         };
         if (a.b_tma && warp == 5 && lane == 0 && my_items > 0) tma_item(0);
@@ -416,6 +433,13 @@ static int mx_launch(MxArgs& a, const char* what, cudaStream_t st) {
         const cuuint64_t str[1] = {(cuuint64_t)a.Kt * 4};
         const cuuint32_t box[2] = {32, (cuuint32_t)kMxN};
         if (tc_make_map(&mapB, a.b, 2, dims, str, box, true)) a.b_tma = 1;
+    } else if (!a.b_kcontig && a.Nt % 4 == 0 && (reinterpret_cast<uintptr_t>(a.b) & 15) == 0 && a.b_sn == 1 &&
+               a.b_sk == a.Nt && a.b_im == (long long)a.Kt * a.Nt && a.b_sm == 2 * a.b_im) {
+        // rows are N-contiguous (weight gradient: B = X^[m][.][b][i]): tensor [nmodes * 2 * Kt rows][Nt], boxes of 32 k x 32 n
+        const cuuint64_t dims[2] = {(cuuint64_t)a.Nt, (cuuint64_t)a.nmodes * 2 * (cuuint64_t)a.Kt};
+        const cuuint64_t str[1] = {(cuuint64_t)a.Nt * 4};
+        const cuuint32_t box[2] = {32, 32};
+        if (tc_make_map_swz(&mapB, a.b, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) a.b_tma = 2;
     }
     const int grid = a.nmodes < sm_count() ? a.nmodes : sm_count();
     {
