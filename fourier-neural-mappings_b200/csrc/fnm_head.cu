@@ -18,14 +18,21 @@ struct LiftArgs {
     const float* x; const float* w; const float* b; float* out;
     const float* g; float* partial;
     int B, Din, N1, N2, P1, P2, C, ngrid, J;
+    float step1, step2;                   // torch.linspace(0, 1, n) step 1 / (n - 1) in fp32
 };
+
+// torch.linspace(0, 1, n) as ATen evaluates it in fp32: start + i * step in the first half, end - (n - 1 - i) * step in
+// the second (no division per element)
+__device__ __forceinline__ float linspace01(int i, int n, float step) {
+    return i < n / 2 ? (float)i * step : 1.0f - (float)(n - 1 - i) * step;
+}
 
 __device__ __forceinline__ float lift_feat(const LiftArgs& a, int j, int b, int xx, int yy) {
     if (j < a.Din) return __ldg(a.x + (((size_t)b * a.Din + j) * a.N1 + xx) * a.N2 + yy);
     const int gi = j - a.Din;
-    // torch.linspace(0, 1, n): i / (n - 1); 2-D: first coordinate along x, second along y; 1-D: along y
-    if (a.ngrid == 2 && gi == 0) return a.N1 > 1 ? (float)xx / (float)(a.N1 - 1) : 0.f;
-    return a.N2 > 1 ? (float)yy / (float)(a.N2 - 1) : 0.f;
+    // 2-D: first coordinate along x, second along y; 1-D: along y
+    if (a.ngrid == 2 && gi == 0) return a.N1 > 1 ? linspace01(xx, a.N1, a.step1) : 0.f;
+    return a.N2 > 1 ? linspace01(yy, a.N2, a.step2) : 0.f;
 }
 
 // thread = (position slot, 4-channel group): its weight columns live in registers, the features of a position are
@@ -380,6 +387,7 @@ int fnm_lift_fwd(const float* x, const float* w, const float* b, float* out, int
     LiftArgs a{};
     a.x = x; a.w = w; a.b = b; a.out = out; a.B = B; a.Din = Din; a.N1 = N1; a.N2 = N2; a.P1 = P1; a.P2 = P2; a.C = C;
     a.ngrid = ngrid; a.J = Din + ngrid;
+    a.step1 = N1 > 1 ? 1.0f / (float)(N1 - 1) : 0.f; a.step2 = N2 > 1 ? 1.0f / (float)(N2 - 1) : 0.f;
     const int nrows = B * P1;
     const int grid = nrows < kEndBlocks * 8 ? nrows : kEndBlocks * 8;
     {
@@ -403,6 +411,7 @@ int fnm_lift_bwd(const float* g, const float* x, float* dw, float* db, int B, in
     LiftArgs a{};
     a.g = g; a.x = x; a.partial = static_cast<float*>(workspace);
     a.B = B; a.Din = Din; a.N1 = N1; a.N2 = N2; a.P1 = P1; a.P2 = P2; a.C = C; a.ngrid = ngrid; a.J = J;
+    a.step1 = N1 > 1 ? 1.0f / (float)(N1 - 1) : 0.f; a.step2 = N2 > 1 ? 1.0f / (float)(N2 - 1) : 0.f;
     const int C4 = C / 4;
     int threads = 256;
     if (threads < C4) threads = (C4 + 31) / 32 * 32;
