@@ -140,6 +140,11 @@ TAB_CASES = [
     dict(B=2, P1=24, P2=40, R=10, NY=7, C=16),           # smoke-test width
     dict(B=2, P1=20, P2=36, R=6, NY=5, C=20),            # SIMT-only channel count
     dict(B=1, P1=16, P2=24, R=8, NY=4, C=256),           # two 128-channel blocks
+    # 128 channels: the TMA-fed ydft (MN-major operand) -- odd number of grid rows (last pair half empty), row length that is
+    # no multiple of 32 (ragged last chunk), fewer than 64 table rows, a single chunk
+    dict(B=3, P1=7, P2=100, R=6, NY=12, C=128),
+    dict(B=1, P1=5, P2=36, R=4, NY=5, C=128),
+    dict(B=2, P1=9, P2=28, R=2, NY=3, C=128),
 ]
 
 

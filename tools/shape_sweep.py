@@ -11,13 +11,13 @@ n = int(sys.argv[1]) if len(sys.argv) > 1 else 30
 rng = random.Random(int(sys.argv[2]) if len(sys.argv) > 2 else 0)
 bad = 0
 for i in range(n):
-    C = rng.choice([8, 12, 16, 20, 32, 40, 48, 64, 96, 128])
+    C = rng.choice([8, 12, 16, 20, 32, 40, 48, 64, 96, 128, 128, 128])          # 128: the TMA / MN-major kernels
     B = rng.choice([1, 2, 3, 4, 5, 7, 20, 33])
     if rng.random() < 0.3:
         Pn = rng.randint(9, 200)
         P, m = (Pn,), (rng.randint(1, Pn // 2),)
     else:
-        P1, P2 = rng.randint(6, 48), rng.randint(6, 48)
+        P1, P2 = rng.randint(6, 48), rng.randint(6, 72)
         P, m = (P1, P2), (rng.randint(1, P1 // 2), rng.randint(1, P2 // 2))
     try:
         check_fused_layers(B, C, P, m, seed=100 + i)
