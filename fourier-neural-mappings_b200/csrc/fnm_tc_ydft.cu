@@ -250,3 +250,9 @@ int tc_ydft_tma(const float* x, const float* tab, float* T, int64_t rows, int P2
 }
 
 }  // namespace fnm
+
+// Measured and dropped: the same operand path for xdft (item = (sample, ky), K = 2 P1, table 2R x 2 P1 streamed per item).
+// There the streamed table chunk is as large as the activation chunk, which doubles the L2 -> shared-memory traffic, and
+// the 3xTF32 pass ran at 0.17 ms against 0.14 ms for the register-staged table GEMM with its TMA-streamed table ring
+// (single-pass TF32: 0.12 vs 0.13 ms).  Sharing one table chunk between several items would need more than the 512 TMEM
+// columns that two alternating (main | correction) accumulator pairs of 128 table rows already take.

@@ -145,6 +145,9 @@ TAB_CASES = [
     dict(B=3, P1=7, P2=100, R=6, NY=12, C=128),
     dict(B=1, P1=5, P2=36, R=4, NY=5, C=128),
     dict(B=2, P1=9, P2=28, R=2, NY=3, C=128),
+    # ... and the TMA-fed xdft (even P1): one ragged chunk, two chunks, rows of the next sample behind the last chunk
+    dict(B=3, P1=10, P2=24, R=6, NY=4, C=128),
+    dict(B=2, P1=22, P2=32, R=8, NY=5, C=128),
 ]
 
 
