@@ -457,3 +457,27 @@ def test_spectral_weights_live_mode_major_and_skip_the_layout_copies():
     for k, v in outs["mode_major"][1].items():
         assert v.shape == outs["reference"][1][k].shape
         assert rel_l2(v, outs["reference"][1][k]) < 1e-6, k
+
+
+def test_edge_inputs_like_reference():
+    """Grid smaller than ``padding`` (no padding is added and the reference's ``:-0`` crop yields an EMPTY output,
+    func_to_func2d.py:101 -- kept), batch of one, and a 1-D model on the shortest grid the modes allow."""
+    torch.manual_seed(2)
+    model = fnm_b200.FNO2d(2, 2, 8, n_layers=2, width_final=16)
+    p = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    model = model.to(DEV)
+    x = torch.randn(1, 1, 6, 6)
+    ref = O.f2f_forward(p, x)
+    out = model(x.to(DEV))
+    assert tuple(out.shape) == tuple(ref.shape) and out.numel() == 0          # (1, 1, 0, 0) like the reference
+    x = torch.randn(1, 1, 9, 10)                                               # batch 1, padded to 10 x 11
+    ref = O.f2f_forward(p, x)
+    out = model(x.to(DEV))
+    assert tuple(out.shape) == tuple(ref.shape) == (1, 1, 9, 10)
+    assert rel_l2(out, ref) < TOL_FP32
+    m1 = fnm_b200.FNO1d(4, 8, n_layers=2, width_final=16)
+    p1 = {k: v.detach().clone() for k, v in m1.state_dict().items()}
+    x1 = torch.randn(2, 1, 8)                                                  # padded to 9 points: modes 4 = floor(9 / 2)
+    ref1 = O.f2f_forward(p1, x1)
+    out1 = m1.to(DEV)(x1.to(DEV))
+    assert rel_l2(out1, ref1) < TOL_FP32
