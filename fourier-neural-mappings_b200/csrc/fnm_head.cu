@@ -212,41 +212,42 @@ __global__ void __launch_bounds__(256) head_fwd_kernel(const HeadArgs a) {
 
 // g_h1[pos][h] = (sum_d g_out[pos][d] w2[d][h]) * GELU'(h1[pos][h]);  partial sums of
 // dW2[d][h] = sum_pos g_out[pos][d] GELU(h1[pos][h]) and db2[d] = sum_pos g_out[pos][d]
-__global__ void head_bwd_kernel(const HeadArgs a) {
+template <int D>
+__global__ void __launch_bounds__(256) head_bwd_kernel(const HeadArgs a) {
     extern __shared__ float red[];                        // [warps][D][H] + [warps][D]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
     const int H4 = a.H / 4;
-    float4 w[kHeadMaxD][kHeadMaxH4], dw[kHeadMaxD][kHeadMaxH4];
-    float dbs[kHeadMaxD];
+    float4 w[D][kHeadMaxH4], dw[D][kHeadMaxH4];
+    float dbs[D];
 #pragma unroll
-    for (int d = 0; d < kHeadMaxD; ++d) {
+    for (int d = 0; d < D; ++d) {
         dbs[d] = 0.f;
 #pragma unroll
         for (int k = 0; k < kHeadMaxH4; ++k) {
             const int h4 = lane + 32 * k;
-            w[d][k] = (d < a.D && h4 < H4) ? __ldg(reinterpret_cast<const float4*>(a.w2 + (size_t)d * a.H) + h4)
-                                           : make_float4(0.f, 0.f, 0.f, 0.f);
+            w[d][k] = h4 < H4 ? __ldg(reinterpret_cast<const float4*>(a.w2 + (size_t)d * a.H) + h4) : make_float4(0.f, 0.f, 0.f, 0.f);
             dw[d][k] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
     }
     const bool lane_ok = lane < H4;
-    for (long long p0 = ((long long)blockIdx.x * nw + warp) * 4; p0 < a.npos; p0 += (long long)gridDim.x * nw * 4) {
-        float4 v[4];
-        float g[4][kHeadMaxD];
+    for (long long p0 = ((long long)blockIdx.x * nw + warp) * 8; p0 < a.npos; p0 += (long long)gridDim.x * nw * 8) {
+        float4 v[8];
+        float g[8][D];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < 8; ++u) {                     // eight 16-byte loads in flight per lane
             const bool ok = p0 + u < a.npos;
-            v[u] = (lane_ok && ok) ? __ldg(reinterpret_cast<const float4*>(a.h1 + (p0 + u) * a.H) + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+            v[u] = (lane_ok && ok) ? tc::ld_stream4(a.h1 + (p0 + u) * a.H + lane * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-            for (int d = 0; d < kHeadMaxD; ++d) g[u][d] = (ok && d < a.D) ? __ldg(a.g_out + (p0 + u) * a.D + d) : 0.f;
+            for (int d = 0; d < D; ++d) g[u][d] = ok ? __ldg(a.g_out + (p0 + u) * D + d) : 0.f;
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < 8; ++u) {
             if (p0 + u < a.npos) {
-                float4 gg = make_float4(0.f, 0.f, 0.f, 0.f);
-                const float4 act = make_float4(gelu_erf(v[u].x), gelu_erf(v[u].y), gelu_erf(v[u].z), gelu_erf(v[u].w));
+                float4 act, dact, gg = make_float4(0.f, 0.f, 0.f, 0.f);
+                tc::gelu_both_fast(v[u].x, act.x, dact.x); tc::gelu_both_fast(v[u].y, act.y, dact.y);
+                tc::gelu_both_fast(v[u].z, act.z, dact.z); tc::gelu_both_fast(v[u].w, act.w, dact.w);
 #pragma unroll
-                for (int d = 0; d < kHeadMaxD; ++d) {
+                for (int d = 0; d < D; ++d) {
                     const float gd = g[u][d];
                     dbs[d] += gd;
                     gg.x = fmaf(gd, w[d][0].x, gg.x); gg.y = fmaf(gd, w[d][0].y, gg.y);
@@ -254,8 +255,7 @@ __global__ void head_bwd_kernel(const HeadArgs a) {
                     dw[d][0].x = fmaf(gd, act.x, dw[d][0].x); dw[d][0].y = fmaf(gd, act.y, dw[d][0].y);
                     dw[d][0].z = fmaf(gd, act.z, dw[d][0].z); dw[d][0].w = fmaf(gd, act.w, dw[d][0].w);
                 }
-                gg.x *= gelu_erf_grad(v[u].x); gg.y *= gelu_erf_grad(v[u].y);
-                gg.z *= gelu_erf_grad(v[u].z); gg.w *= gelu_erf_grad(v[u].w);
+                gg.x *= dact.x; gg.y *= dact.y; gg.z *= dact.z; gg.w *= dact.w;
                 if (lane_ok) *(reinterpret_cast<float4*>(a.g_h1 + (p0 + u) * a.H) + lane) = gg;
             }
         }
@@ -263,7 +263,8 @@ __global__ void head_bwd_kernel(const HeadArgs a) {
     // block reduction of dW2 / db2 partials
     float* rw = red;                                       // [nw][D][H]
     float* rb = red + (size_t)nw * a.D * a.H;              // [nw][D]
-    for (int d = 0; d < a.D; ++d) {
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
 #pragma unroll
         for (int k = 0; k < kHeadMaxH4; ++k) {
             const int h4 = lane + 32 * k;
@@ -473,12 +474,20 @@ int fnm_mlp_head_bwd(const float* h1, const float* g_out, const float* w2, float
     const size_t smem = (size_t)8 * (D * H + D) * sizeof(float);
     static bool attr_set = false;
     if (!attr_set) {
-        cudaFuncSetAttribute(head_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+        cudaFuncSetAttribute(head_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+        cudaFuncSetAttribute(head_bwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+        cudaFuncSetAttribute(head_bwd_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+        cudaFuncSetAttribute(head_bwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
         attr_set = true;
     }
     {
         LaunchScope ls("mlp_head_bwd", st);
-        head_bwd_kernel<<<kEndBlocks, 256, smem, st>>>(a);
+        switch (D) {
+            case 1: head_bwd_kernel<1><<<kEndBlocks, 256, smem, st>>>(a); break;
+            case 2: head_bwd_kernel<2><<<kEndBlocks, 256, smem, st>>>(a); break;
+            case 3: head_bwd_kernel<3><<<kEndBlocks, 256, smem, st>>>(a); break;
+            default: head_bwd_kernel<4><<<kEndBlocks, 256, smem, st>>>(a); break;
+        }
     }
     FNM_TRY(check_launch("mlp_head_bwd"));
     {

@@ -196,6 +196,21 @@ __device__ __forceinline__ float gelu_grad_fast(float x) {
     return fmaf(x * 0.39894228040143267794f, ex, cdf);
 }
 
+// GELU(x) and GELU'(x) from ONE rcp / ex2 pair (the head's backward needs both of the same element)
+__device__ __forceinline__ void gelu_both_fast(float x, float& g, float& dg) {
+    const float z = fabsf(x) * 0.70710678118654752440f;
+    const float tt = rcp_fast(fmaf(0.3275911f, z, 1.0f));
+    float p = fmaf(1.061405429f, tt, -1.453152027f);
+    p = fmaf(p, tt, 1.421413741f);
+    p = fmaf(p, tt, -0.284496736f);
+    p = fmaf(p, tt, 0.254829592f);
+    const float ex = exp_neg_sq(z);
+    const float e = p * tt * ex;
+    const float cdf = x >= 0.f ? 1.0f - 0.5f * e : 0.5f * e;
+    g = x * cdf;
+    dg = fmaf(x * 0.39894228040143267794f, ex, cdf);
+}
+
 __device__ __forceinline__ void split_tf32(float v, float& hi, float& lo) {
     uint32_t h;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(v));
