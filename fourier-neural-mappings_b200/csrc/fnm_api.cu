@@ -259,6 +259,34 @@ int fnm_pointwise_ysyn(const float* x, int act_in, const float* wc, int wc_is_kn
                                as_stream(stream));
 }
 
+// The F2V / V2F ends keep m2 + 1 columns, so their y-synthesis has LY = 2 (m2 + 1) table columns -- usually no multiple
+// of 4, which the TMA kernel's table map (16-byte row stride) cannot address.  With scratch at hand the table is copied
+// once per call into a zero-padded [S2][round4(LY)] buffer (a few KB) so that these launches run on the tcgen05 kernel
+// too instead of the fp32 SIMT engine.
+__global__ void pad_table_kernel(const float* __restrict__ src, float* __restrict__ dst, int rows, int ld, int ld_pad) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * ld_pad) return;
+    const int r = i / ld_pad, c = i - r * ld_pad;
+    dst[i] = c < ld ? src[(size_t)r * ld + c] : 0.f;
+}
+
+static size_t padded_table_bytes(int S2, int LY) { return LY % 4 == 0 ? 0 : align_up((size_t)S2 * ((LY + 3) / 4 * 4) * sizeof(float), 256); }
+
+static int ysyn_only(const float* Z, const float* by, const float* mul, float* out, int64_t rows, int S2, int LY, int N, int mode,
+                     float* tab_scratch, fnm_stream_t stream) {
+    const int ld = (LY + 3) / 4 * 4;
+    if (LY % 4 != 0 && tab_scratch && tc_pw2_supported(rows, S2, LY, 0, N, 0, nullptr, Z, tab_scratch, ld)) {
+        cudaStream_t st = as_stream(stream);
+        {
+            LaunchScope ls("pad_table", st);
+            pad_table_kernel<<<(S2 * ld + 255) / 256, 256, 0, st>>>(by, tab_scratch, S2, LY, ld);
+        }
+        FNM_TRY(check_launch("pad_table"));
+        return tc_pw2(nullptr, nullptr, 0, nullptr, Z, tab_scratch, mul, out, nullptr, rows, S2, LY, 0, N, mode, st, ld);
+    }
+    return fnm_pointwise_ysyn(nullptr, 0, nullptr, 0, nullptr, Z, by, mul, out, nullptr, rows, S2, LY, 0, N, mode, stream);
+}
+
 size_t fnm_conv_wgrad_workspace_bytes(int64_t npos, int Ci, int Co) { return conv_wgrad_workspace(npos, Ci, Co); }
 
 int fnm_conv_wgrad(const float* g, const float* x, int act_in, float* dwc, float* dbc, int64_t npos, int Ci, int Co,
@@ -411,7 +439,8 @@ size_t fnm_lfunc_workspace_bytes(const fnm_plan* p) {
     const size_t T = (size_t)p->B * p->P1 * LY * p->Ci;
     const size_t Gxh = (size_t)p->R * p->NY * 2 * p->B * p->Ci;
     const size_t cmax = p->Ci > p->Co ? p->Ci : p->Co;
-    return (T + Gxh) * sizeof(float) + simt_mode_split_workspace(p->R * p->NY, p->B, (int)cmax) + 4 * 256;
+    return (T + Gxh) * sizeof(float) + simt_mode_split_workspace(p->R * p->NY, p->B, (int)cmax) + 4 * 256 +
+           padded_table_bytes(p->P2, (int)LY);
 }
 
 int fnm_lfunc_fwd(const fnm_plan* p, const float* xin, int act_in, const float* w, const float* cc, float* out,
@@ -440,13 +469,13 @@ int fnm_lfunc_bwd(const fnm_plan* p, const float* g_out, const float* xin, int a
     const int LY = 2 * p->NY;
     float* Zg = cv.take((size_t)p->B * p->P1 * LY * p->Ci);
     float* Gxh = cv.take((size_t)p->R * p->NY * 2 * p->B * p->Ci);
+    float* tabpad = LY % 4 ? cv.take(padded_table_bytes(p->P2, LY) / sizeof(float)) : nullptr;
     if (dw) FNM_TRY(simt_lfunc_bwd_w(g_out, xh_save, cc, dw, p->B, p->R, p->NY, p->Ci, p->Co, st));
     if (g_in) {
         FNM_TRY(simt_lfunc_bwd_x(g_out, w, cc, Gxh, p->B, p->R, p->NY, p->Ci, p->Co, st));
         FNM_TRY(fnm_xsyn(Gxh, p->fxb, Zg, p->B, p->P1, p->R, p->NY, p->Ci, p->mode, stream));
         const float* mul = zin_pre ? zin_pre : (act_in ? xin : nullptr);
-        FNM_TRY(fnm_pointwise_ysyn(nullptr, 0, nullptr, 0, nullptr, Zg, p->ayT, mul, g_in, nullptr,
-                                   (int64_t)p->B * p->P1, p->P2, LY, 0, p->Ci, p->mode, stream));
+        FNM_TRY(ysyn_only(Zg, p->ayT, mul, g_in, (int64_t)p->B * p->P1, p->P2, LY, p->Ci, p->mode, tabpad, stream));
     }
     return FNM_OK;
 }
@@ -459,7 +488,8 @@ size_t fnm_ldec_workspace_bytes(const fnm_plan* p) {
     const size_t LY = 2 * (size_t)p->NY;
     const size_t Z = (size_t)p->B * p->S1 * LY * p->Co;
     const size_t Oh = (size_t)p->R * p->NY * 2 * p->B * p->Co;
-    return (Z + Oh) * sizeof(float) + simt_mode_split_workspace(p->R * p->NY, p->B, p->Ci) + 4 * 256;
+    return (Z + Oh) * sizeof(float) + simt_mode_split_workspace(p->R * p->NY, p->B, p->Ci) + 4 * 256 +
+           padded_table_bytes(p->S2, (int)LY);
 }
 
 int fnm_ldec_fwd(const fnm_plan* p, const float* v, const float* w, float* y_out, void* workspace,
@@ -472,10 +502,10 @@ int fnm_ldec_fwd(const fnm_plan* p, const float* v, const float* w, float* y_out
     const int LY = 2 * p->NY;
     float* Z = cv.take((size_t)p->B * p->S1 * LY * p->Co);
     float* Oh = cv.take((size_t)p->R * p->NY * 2 * p->B * p->Co);
+    float* tabpad = LY % 4 ? cv.take(padded_table_bytes(p->S2, LY) / sizeof(float)) : nullptr;
     FNM_TRY(simt_ldec_mix(v, w, Oh, p->B, p->R, p->NY, p->Ci, p->Co, st));
     FNM_TRY(fnm_xsyn(Oh, p->fx, Z, p->B, p->S1, p->R, p->NY, p->Co, p->mode, stream));
-    return fnm_pointwise_ysyn(nullptr, 0, nullptr, 0, nullptr, Z, p->by, nullptr, y_out, nullptr, (int64_t)p->B * p->S1,
-                              p->S2, LY, 0, p->Co, p->mode, stream);
+    return ysyn_only(Z, p->by, nullptr, y_out, (int64_t)p->B * p->S1, p->S2, LY, p->Co, p->mode, tabpad, stream);
 }
 
 int fnm_ldec_bwd(const fnm_plan* p, const float* g_y, const float* v, const float* w, float* g_v, float* dw,

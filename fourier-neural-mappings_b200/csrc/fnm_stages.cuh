@@ -66,10 +66,11 @@ bool tc_conv_wgrad_supported(int64_t npos, int Ci, int Co);
 size_t tc_conv_wgrad_workspace(int64_t npos, int Ci, int Co);
 int tc_conv_wgrad(const float* g, const float* x, int act, float* dwc, float* dbc, int64_t npos, int Ci, int Co,
                   float* partial, int mode, cudaStream_t st);
-bool tc_pw2_supported(int64_t rows, int S2, int LY, int K, int N, int act, const void* x, const void* Z, const void* by);
+bool tc_pw2_supported(int64_t rows, int S2, int LY, int K, int N, int act, const void* x, const void* Z, const void* by,
+                      int by_ld = 0);
 int tc_pw2(const float* x, const float* wc, int wc_is_kn, const float* bias, const float* Z, const float* by,
            const float* mul, float* out, float* out_act, int64_t rows, int S2, int LY, int K, int N, int mode,
-           cudaStream_t st);
+           cudaStream_t st, int by_ld = 0);
 bool tc_pointwise_ysyn_supported(int64_t rows, int S2, int LY, int K, int N);
 int tc_pointwise_ysyn(const float* x, int act, const float* wc, int wc_is_kn, const float* bias, const float* Z,
                       const float* by, const float* mul, float* out, float* out_act, int64_t rows, int S2, int LY,

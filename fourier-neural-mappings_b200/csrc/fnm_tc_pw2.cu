@@ -550,9 +550,11 @@ static int pw2_fold(int64_t rows, int CI, int CO) {
     return 1;
 }
 
-static bool pw2_configure(PwArgs2& a, int64_t rows, int S2, int LY, int CI, int CO) {
-    // what TMA can address (16-byte strides) and what the TMEM map holds (128 lanes, 64 mode columns)
-    if (rows < 1 || rows > (1LL << 28) || S2 < 1 || LY < 0 || LY > 64 || LY % 4 != 0) return false;
+static bool pw2_configure(PwArgs2& a, int64_t rows, int S2, int LY, int CI, int CO, int by_ld = 0) {
+    // what TMA can address (16-byte strides: the twiddle table's leading dimension by_ld, LY unless the caller padded it)
+    // and what the TMEM map holds (128 lanes, 64 mode columns)
+    if (by_ld == 0) by_ld = LY;
+    if (rows < 1 || rows > (1LL << 28) || S2 < 1 || LY < 0 || LY > 64 || by_ld % 4 != 0 || by_ld < LY) return false;
     if (LY == 0 && CI == 0) return false;
     if (CO < 4 || CO > 128 || CO % 4 != 0) return false;
     if (CI != 0 && (CI < 4 || CI > 128 || CI % 4 != 0)) return false;
@@ -608,27 +610,28 @@ static bool pw2_configure(PwArgs2& a, int64_t rows, int S2, int LY, int CI, int 
 
 using namespace tc;
 
-bool tc_pw2_supported(int64_t rows, int S2, int LY, int K, int N, int act, const void* x, const void* Z, const void* by) {
+bool tc_pw2_supported(int64_t rows, int S2, int LY, int K, int N, int act, const void* x, const void* Z, const void* by, int by_ld) {
     if (!tc_enabled() || act != 0 || !encode_fn()) return false;
     { const char* e = getenv("FNM_DISABLE_PW2"); if (e && e[0] == '1') return false; }
     if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(Z) | reinterpret_cast<uintptr_t>(by)) & 15) return false;
     PwArgs2 a{};
-    return pw2_configure(a, rows, S2, LY, K, N);
+    return pw2_configure(a, rows, S2, LY, K, N, by_ld);
 }
 
 int tc_pw2(const float* x, const float* wc, int wc_is_kn, const float* bias, const float* Z, const float* by,
            const float* mul, float* out, float* out_act, int64_t rows, int S2, int LY, int K, int N, int mode,
-           cudaStream_t st) {
+           cudaStream_t st, int by_ld) {
     PwArgs2 a{};
     const int CI = (x && wc) ? K : 0;
-    if (!pw2_configure(a, rows, S2, LY, CI, N)) return fail(FNM_ENOTSUP, "pointwise_ysyn: shape not served by the TMA kernel");
+    if (by_ld == 0) by_ld = LY;
+    if (!pw2_configure(a, rows, S2, LY, CI, N, by_ld)) return fail(FNM_ENOTSUP, "pointwise_ysyn: shape not served by the TMA kernel");
     a.wc = wc; a.bias = bias; a.mul = mul; a.out = out; a.out_act = out_act; a.wc_is_kn = wc_is_kn;
     a.single_pass = mode == FNM_MODE_TF32;
     { const char* e = getenv("FNM_PW2_DEBUG"); a.debug = e ? atoi(e) : 0; }
     CUtensorMap mx, mb, mz;
     if (LY > 0) {
-        const cuuint64_t dims[2] = {(cuuint64_t)a.LY, (cuuint64_t)a.S2};
-        const cuuint64_t str[1] = {(cuuint64_t)a.LY * 4};
+        const cuuint64_t dims[2] = {(cuuint64_t)by_ld, (cuuint64_t)a.S2};        // columns LY .. by_ld - 1 of a padded table are zero
+        const cuuint64_t str[1] = {(cuuint64_t)by_ld * 4};
         const cuuint32_t box[2] = {32, (cuuint32_t)a.NT};
         if (!tc_make_map(&mb, by, 2, dims, str, box, true)) return fail(FNM_ECUDA, "pointwise_ysyn: tensor map (by) failed");
     }
