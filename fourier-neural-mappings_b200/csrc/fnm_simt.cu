@@ -13,6 +13,8 @@
 // take over the heavy spatial passes for the shapes they support.
 #include "fnm_common.cuh"
 
+#include <cstring>
+
 namespace fnm {
 
 // ------------------------------------------------------------------------------------------------
@@ -125,6 +127,18 @@ __global__ void __launch_bounds__((BM / 4) * (BN / 4)) gemm_engine(const P p, in
     }
 }
 
+// Profile name of a stage when the fp32 SIMT engine serves it: stages that also have a tcgen05 kernel get a ".simt" suffix, so
+// that a fallback shows up as its own line in bench.py's per-kernel list instead of hiding behind the stage name.
+static const char* simt_profile_name(const char* what) {
+    static const char* const names[][2] = {
+        {"ydft", "ydft.simt"}, {"xdft", "xdft.simt"}, {"xsyn", "xsyn.simt"}, {"mix_fwd", "mix_fwd.simt"},
+        {"mix_bwd_x", "mix_bwd_x.simt"}, {"mix_bwd_w", "mix_bwd_w.simt"}, {"pointwise_ysyn", "pointwise_ysyn.simt"},
+        {"conv_wgrad", "conv_wgrad.simt"}};
+    for (const auto& n : names)
+        if (strcmp(what, n[0]) == 0) return n[1];
+    return what;
+}
+
 template <int BM, int BN, class P>
 static int launch_engine(const P& p, int64_t nbatch, cudaStream_t st, const char* what) {
     const int tm = (p.M + BM - 1) / BM, tn = (p.N + BN - 1) / BN;
@@ -132,7 +146,7 @@ static int launch_engine(const P& p, int64_t nbatch, cudaStream_t st, const char
     if (blocks <= 0) return FNM_OK;
     if (blocks > 0x7fffffffLL) return fail(FNM_EINVAL, "%s: grid too large (%lld blocks)", what, (long long)blocks);
     {
-        LaunchScope ls(what, st);
+        LaunchScope ls(simt_profile_name(what), st);
         gemm_engine<BM, BN, P><<<(unsigned)blocks, (BM / 4) * (BN / 4), 0, st>>>(p, tm, tn);
     }
     return check_launch(what);
