@@ -121,19 +121,41 @@ def measured_peaks():
 
 
 # ------------------------------------------------------------------------------------------------
-def run_reference(args, rank):
-    """CPU arm: the oracle port of the reference algorithm on the host cores, bounded sample."""
-    if rank != 0:
-        return
+def _oracle_setup(workload, device="cpu"):
     from oracle import fnm_oracle as O
-    desc, family, kw, batch, xshape, cpu_batch = WORKLOADS[args.workload]
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
+    desc, family, kw, batch, xshape, cpu_batch = WORKLOADS[workload]
     torch.manual_seed(0)
     model = build_model(family, kw)
-    p = {k: v.detach().clone().requires_grad_(True) for k, v in model.state_dict().items()}
+    p = {k: v.detach().clone().to(device).requires_grad_(True) for k, v in model.state_dict().items()}
     del model
-    fwd = oracle_forward(family, kw)
+    return O, desc, family, kw, batch, xshape, cpu_batch, p, oracle_forward(family, kw)
+
+
+def _cpu_pick_batch(O, fwd, p, xshape, batch, start, budget_s, steps_wanted):
+    """Largest batch <= the workload's whose `steps_wanted` steps fit `budget_s`, assuming time linear in the batch
+    (measured with one probe step at `start`; the probe is also the allocator / thread-pool warm-up)."""
+    b0 = max(1, min(start, batch))
+    x = synth((b0,) + xshape, 1234)
+    with torch.no_grad():
+        y = synth(tuple(fwd(p, x).shape), 1235)
+    O.train_step(fwd, p, x, y, O.AdamState(), lr=1e-3, weight_decay=1e-4)          # first call: page-in, not timed
+    t0 = time.perf_counter()
+    O.train_step(fwd, p, x, y, O.AdamState(), lr=1e-3, weight_decay=1e-4)
+    per_sample = (time.perf_counter() - t0) / b0
+    b = int(budget_s / max(per_sample * steps_wanted, 1e-9))
+    return max(1, min(batch, b))
+
+
+def run_reference(args, rank):
+    """CPU arm: the oracle port of the reference algorithm (the same torch.fft / einsum / conv CPU entry points the
+    reference calls) on all host cores, on a bounded sample of the same workload: the largest batch (<= the workload's
+    own) whose K + W steps fit ~100 s."""
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    O, desc, family, kw, batch, xshape, cpu_batch, p, fwd = _oracle_setup(args.workload)
+    cpu_batch = _cpu_pick_batch(O, fwd, p, xshape, batch, 2 if batch >= 2 else 1, 100.0, args.steps + args.warmup)
     x = synth((cpu_batch,) + xshape, 1234)
     with torch.no_grad():
         yshape = fwd(p, x).shape
@@ -146,12 +168,13 @@ def run_reference(args, rank):
         O.train_step(fwd, p, x, y, state, lr=1e-3, weight_decay=1e-4)
     dt = time.perf_counter() - t0
     value = cpu_batch * args.steps / dt
-    sample = f"batch {cpu_batch} of the workload's {batch} per step, {args.steps} steps after {args.warmup} warm-up"
+    sample = (f"batch {cpu_batch} of the workload's {batch} per step (largest batch whose {args.steps}+{args.warmup} steps fit "
+              f"100 s of CPU time), {args.steps} steps after {args.warmup} warm-up")
     print(json.dumps({
         "impl": "reference", "metric": "train_samples_per_sec", "value": value, "unit": "samples/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: {desc}", "device": "cpu", "threads": cores},
+        "config": {"workload": f"{args.workload}: {desc}", "device": "cpu", "threads": cores, "cpu_batch": cpu_batch},
         "cpu_baseline": {"value": value, "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -159,16 +182,12 @@ def run_reference(args, rank):
 
 
 def cpu_baseline(workload, budget_s=25.0):
-    """Bounded CPU sample of the same step with the oracle port (reported baseline, not a target)."""
-    from oracle import fnm_oracle as O
-    desc, family, kw, batch, xshape, cpu_batch = WORKLOADS[workload]
+    """Bounded CPU sample of the same step with the oracle port (reported baseline, not a target): the largest batch
+    whose 1 warm-up + 2 timed steps fit the budget."""
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    torch.manual_seed(0)
-    model = build_model(family, kw)
-    p = {k: v.detach().clone().requires_grad_(True) for k, v in model.state_dict().items()}
-    del model
-    fwd = oracle_forward(family, kw)
+    O, desc, family, kw, batch, xshape, cpu_batch, p, fwd = _oracle_setup(workload)
+    cpu_batch = _cpu_pick_batch(O, fwd, p, xshape, batch, 2 if batch >= 2 else 1, budget_s, 3)
     x = synth((cpu_batch,) + xshape, 1234)
     with torch.no_grad():
         y = synth(tuple(fwd(p, x).shape), 1235)
@@ -182,7 +201,58 @@ def cpu_baseline(workload, budget_s=25.0):
         if dt > budget_s or n >= 20 or (n >= 2 and dt * (n + 1) / n > budget_s):
             break
     return {"value": cpu_batch * n / dt, "unit": "samples/s", "cores": cores, "kind": "port",
-            "sample": f"batch {cpu_batch} of {batch}, {n} steps after 1 warm-up, {dt:.1f} s"}
+            "sample": f"batch {cpu_batch} of {batch} (largest that fits the {budget_s:.0f} s budget), {n} steps after 1 warm-up, {dt:.1f} s"}
+
+
+def gpu_comparator(workload, steps, warmup, allow_tf32, dev):
+    """The reference's OWN GPU path on this box: the oracle port -- the same torch.fft.rfft2 / irfft2
+    (cuFFT), einsum (cuBLAS), 1x1 Conv (cuDNN), F.gelu and reference-semantics Adam calls as /root/reference/models/shared.py:
+    315-341 and func_to_func2d.py:62-65,89-95 -- run on the GPU through stock PyTorch, same batch, loss and optimizer."""
+    O, desc, family, kw, batch, xshape, _, p, fwd = _oracle_setup(workload, dev)
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = bool(allow_tf32)
+    try:
+        x = synth((batch,) + xshape, 1234).to(dev)
+        with torch.no_grad():
+            y = synth(tuple(fwd(p, x).shape), 1235).to(dev)
+        state = O.AdamState()
+        for _ in range(max(warmup, 3)):
+            O.train_step(fwd, p, x, y, state, lr=1e-3, weight_decay=1e-4)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            loss, _ = O.train_step(fwd, p, x, y, state, lr=1e-3, weight_decay=1e-4)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        return {"value": batch / (ms / 1e3), "unit": "samples/s", "ms_per_step": ms, "batch": batch, "steps": steps,
+                "allow_tf32": bool(allow_tf32), "last_loss": float(loss),
+                "what": "stock PyTorch on the same GPU: cuFFT rfft2/irfft2 + cuBLAS einsum + cuDNN 1x1 conv + reference Adam"}
+    except torch.cuda.OutOfMemoryError as e:                       # noqa: PERF203
+        return {"unavailable": f"out of memory: {str(e)[:120]}"}
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+        del p
+        torch.cuda.empty_cache()
+
+
+def run_stock_gpu(args, rank):
+    """`--impl stock-gpu`: only the comparator, as its own JSON line (rank 0)."""
+    if rank != 0:
+        return
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", 0)))
+    torch.cuda.set_device(dev)
+    desc, family, kw, batch, xshape, _ = WORKLOADS[args.workload]
+    res = {tag: gpu_comparator(args.workload, args.steps, args.warmup, tf32, dev) for tag, tf32 in (("fp32", False), ("tf32", True))}
+    main_ = res["fp32"]
+    print(json.dumps({
+        "impl": "stock-gpu", "metric": "train_samples_per_sec", "value": main_.get("value"), "unit": "samples/s", "n_gpus": 1,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": main_.get("ms_per_step"), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {desc}", "batch_per_gpu": batch, "device": "cuda (stock PyTorch)"},
+        "gpu_comparator": res,
+    }))
 
 
 # ------------------------------------------------------------------------------------------------
@@ -206,7 +276,9 @@ def kernel_algorithmic_bytes(name, wl, model, launches=None):
 
 
 def run_ours(args, rank, world):
-    os.environ["NCCL_DEBUG"] = "WARN"              # keep NCCL's version banner off stdout (one JSON line only)
+    # NCCL's log level is the caller's to choose (the driver reads the communicator lines); only a default is set here,
+    # and it is NOT silenced.  The JSON line is the last line of stdout either way.
+    os.environ.setdefault("NCCL_DEBUG", "WARN")
     import torch.distributed as dist
     import fnm_b200
     from fnm_b200 import _lib
@@ -320,12 +392,16 @@ def run_ours(args, rank, world):
     barrier()
 
     def leave():
-        """Multi-rank exit: tearing an NCCL communicator down while a CUDA graph that captured its kernels is
-        alive hung on the B200 box, so after a last barrier every rank flushes and exits without the teardown."""
+        """Multi-rank shutdown in dependency order: the CUDA graph that captured NCCL kernels goes first, then the
+        communicator (tearing the communicator down under a live graph hung on the B200 box)."""
+        nonlocal graphed
+        if graphed is not None:
+            graphed.close()
+            graphed = None
+        torch.cuda.synchronize()
         if world > 1:
-            sys.stdout.flush()
-            sys.stderr.flush()
-            os._exit(0)
+            dist.barrier()
+            dist.destroy_process_group()
 
     if rank != 0:
         leave()
@@ -356,15 +432,22 @@ def run_ours(args, rank, world):
                         "algorithmic_GB_per_step": None if ab is None else round(ab / 1e9, 4),
                         "GBps": None if ab is None or t <= 0 else round(ab / 1e6 / t, 1)})
     top = kernels[0]
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
-    if os.path.exists(tpath):                      # dram read+write bytes per launch from the committed ncu capture
-        tj = json.load(open(tpath))
-        if tj.get("workload") == args.workload:
-            tv = tj["per_launch_bytes"].get(top["name"])
-            traffic = tv.get("step_average") if isinstance(tv, dict) else tv
+    # `traffic` is NOT measured by this run: it is the dram read + write bytes per launch of the same kernel from the
+    # committed `ncu --set full` capture of this workload (profiles/<file>), named in `traffic_source`
+    traffic, traffic_src = None, None
+    for tname in ("r02_ncu_traffic.json", "r01_ncu_traffic.json"):
+        tpath = os.path.join(ROOT, "profiles", tname)
+        if traffic is None and os.path.exists(tpath):
+            tj = json.load(open(tpath))
+            per = tj.get(args.workload) if isinstance(tj.get(args.workload), dict) else (tj if tj.get("workload") == args.workload else None)
+            if per:
+                tv = per.get("per_launch_bytes", {}).get(top["name"])
+                traffic = tv.get("step_average") if isinstance(tv, dict) else tv
+                if traffic is not None:
+                    traffic_src = f"committed ncu capture profiles/{tname} (not measured by this run)"
     roofline = {"kernel": top["name"], "bound": "hbm", "achieved": top["GBps"], "peak": peak, "unit": "GB/s",
                 "frac": None if top["GBps"] is None else round(top["GBps"] / peak, 4), "traffic": traffic,
+                "traffic_source": traffic_src,
                 "peak_source": peak_src, "launches_per_step": top["launches_per_step"],
                 "ms_per_launch": round(top["ms_per_step"] / max(top["launches_per_step"], 1), 4),
                 "algorithmic_bytes_per_step": None if top["algorithmic_GB_per_step"] is None else top["algorithmic_GB_per_step"] * 1e9,
@@ -389,6 +472,16 @@ def run_ours(args, rank, world):
                            "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained / 2 (TF32) / {passes} ({args.mode} mode)",
                            "useful_flops_per_step": flops}
 
+    comparator = None
+    if world == 1 and not args.no_gpu_comparator:
+        # free this arm's step state first: the stock path saves ~10 activation-sized tensors per layer
+        if graphed is not None:
+            graphed.close()
+            graphed = None
+        step = eager_step = None
+        del grads, opt
+        torch.cuda.empty_cache()
+        comparator = {tag: gpu_comparator(args.workload, min(args.steps, 5), 3, tf32, dev) for tag, tf32 in (("fp32", False), ("tf32", True))}
     cpu = cpu_baseline(args.workload) if (world == 1 and not args.no_cpu_baseline) else None
     samples = batch * world * args.steps
     line = {
@@ -410,8 +503,10 @@ def run_ours(args, rank, world):
         "roofline_tensor": roofline_tensor,
         "kernels": kernels,
         "cpu_baseline": cpu,
+        "gpu_comparator": comparator,
     }
     print(json.dumps(line))
+    sys.stdout.flush()
     leave()
 
 
@@ -420,9 +515,11 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "stock-gpu"])
     ap.add_argument("--workload", default="cfg5", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-comparator", action="store_true",
+                    help="skip the stock-PyTorch GPU comparator (cuFFT / cuBLAS / cuDNN path of the reference) at N = 1")
     ap.add_argument("--mode", default="fp32", choices=["fp32", "tf32"],
                     help="fp32: 3xTF32 parity mode (rel-L2 <= 1e-5, the headline); tf32: single tensor-core pass (<= 5e-3)")
     ap.add_argument("--graph", dest="graph", action="store_true", default=True,
@@ -433,6 +530,9 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", 1))
     if args.impl == "reference":
         run_reference(args, rank)
+        return
+    if args.impl == "stock-gpu":
+        run_stock_gpu(args, rank)
         return
     if args.warmup < 3:
         args.warmup = 3

@@ -43,6 +43,74 @@ class Adam(Optimizer):
         super().__setstate__(state)
         for group in self.param_groups:
             group.setdefault("amsgrad", False)
+        self.__dict__.setdefault("capturable", False)
+        self._step_dev = {}                                    # rebuilt from state["step"] at the next step()
+        self._relayout_state()
+
+    # ---- checkpoint compatibility ---------------------------------------------------------------------------------
+    def _relayout_state(self):
+        """Moments loaded from a checkpoint (the reference's util.Adam, or any contiguous save) arrive in the
+        reference's memory order; the drop-in spectral weights are stored mode-major and the fused update runs
+        element by element over STORAGE, so every state tensor is brought into its parameter's memory order."""
+        for group in self.param_groups:
+            for p in group["params"]:
+                st = self.state.get(p)
+                if not st:
+                    continue
+                for key in ("exp_avg", "exp_avg_sq", "max_exp_avg_sq"):
+                    t = st.get(key)
+                    if isinstance(t, torch.Tensor) and (t.stride() != p.stride() or t.dtype != p.dtype or t.device != p.device):
+                        st[key] = torch.empty_like(p, memory_format=torch.preserve_format).copy_(t)
+                if isinstance(st.get("step"), torch.Tensor):    # torch.optim checkpoints keep a tensor step
+                    st["step"] = int(st["step"].item())
+
+    def load_state_dict(self, state_dict):
+        super().load_state_dict(state_dict)
+        self._step_dev = {}
+        self._relayout_state()
+
+    def sync_steps(self):
+        """Capturable mode: CUDA-graph replays advance only the device counter.  ``GraphedTrainStep`` reports every
+        replay (``graph_replayed``); this folds the reported count into ``state[p]["step"]`` so that checkpoints and a
+        later eager step see the true count -- host bookkeeping only, no device synchronisation."""
+        n = self._step_dev.get("pending", 0)
+        if not n:
+            return
+        self._step_dev["pending"] = 0
+        for p in self._step_dev.get("params", ()):
+            if self.state.get(p):
+                self.state[p]["step"] += n
+        if "host" in self._step_dev:
+            self._step_dev["host"] += n
+
+    def graph_captured(self):
+        """Called once after ``step()`` was RECORDED in a CUDA graph: recording bumped the host-side counts although no
+        kernel ran."""
+        for p in self._step_dev.get("params", ()):
+            if self.state.get(p):
+                self.state[p]["step"] -= 1
+        if "host" in self._step_dev:
+            self._step_dev["host"] -= 1
+
+    def graph_replayed(self, n=1):
+        self._step_dev["pending"] = self._step_dev.get("pending", 0) + n
+
+    def reset_step_counter(self):
+        """Re-derive the device counter from ``state[p]["step"]`` (after the states were edited or restored)."""
+        ctr = self._step_dev.get("ctr")
+        if ctr is None:
+            return
+        self._step_dev["pending"] = 0
+        steps = {int(self.state[p]["step"]) for p in self._step_dev.get("params", ()) if self.state.get(p)}
+        if len(steps) > 1:
+            raise FnmError(f"Adam(capturable=True): parameters disagree on the step count ({sorted(steps)})")
+        n = steps.pop() if steps else 0
+        ctr.fill_(n)                                            # in place: a captured graph keeps reading this tensor
+        self._step_dev["host"] = n
+
+    def state_dict(self):
+        self.sync_steps()
+        return super().state_dict()
 
     @torch.no_grad()
     def step(self, closure=None):
@@ -51,6 +119,8 @@ class Adam(Optimizer):
             with torch.enable_grad():
                 loss = closure()
         self._ctr_bumped = False
+        if self.capturable and self._step_dev.get("ctr") is not None and not torch.cuda.is_current_stream_capturing():
+            self.sync_steps()                                  # graph replays since the last eager step moved the counter
         for group in self.param_groups:
             beta1, beta2 = group["betas"]
             by_step = {}
@@ -72,8 +142,12 @@ class Adam(Optimizer):
                         state["max_exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
                 state["step"] += 1
                 by_step.setdefault(state["step"], []).append(p)
+            if self.capturable and len(by_step) > 1:
+                raise FnmError("Adam(capturable=True) keeps ONE device step counter: all parameters must have been "
+                               f"stepped the same number of times (found steps {sorted(by_step)})")
             for step, plist in by_step.items():
-                self._launch(plist, step, group, beta1, beta2)
+                with torch.cuda.device(plist[0].device):          # the library launches on the current device
+                    self._launch(plist, step, group, beta1, beta2)
         return loss
 
     def _launch(self, plist, step, group, beta1, beta2):
@@ -113,9 +187,17 @@ class Adam(Optimizer):
             if ctr is None:
                 ctr = torch.full((1,), step - 1, dtype=torch.int32, device=plist[0].device)
                 self._step_dev["ctr"] = ctr
+                self._step_dev["params"] = []
+                self._step_dev["host"] = step - 1
+            if not self._ctr_bumped and self._step_dev["host"] != step - 1:
+                raise FnmError("Adam(capturable=True): parameter groups disagree on the step count "
+                               f"({self._step_dev['host'] + 1} vs {step})")
+            known = self._step_dev["params"]
+            known.extend(p for p in plist if all(p is not q for q in known))
             if not self._ctr_bumped:
                 check(lib().fnm_counter_inc(C.c_void_p(ctr.data_ptr()), stream), "fnm_counter_inc")
                 self._ctr_bumped = True
+                self._step_dev["host"] = step
             step_dev = C.c_void_p(ctr.data_ptr())
         check(lib().fnm_adam_multi_tensor(n, p_tab, g_tab, m_tab, v_tab, x_tab, numel, cplx,
                                           float(group["lr"]), float(beta1), float(beta2), float(group["eps"]),

@@ -4,6 +4,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <stdarg.h>
+#include <atomic>
 
 #include "../../include/fnm_b200.h"
 
@@ -46,6 +47,15 @@ __device__ __forceinline__ float gelu_grad_f(float x) {
     const float pdf = 0.39894228040143267794f * expf(-0.5f * x * x);
     return cdf + x * pdf;
 }
+
+// Once-per-DEVICE guard for cudaFuncSetAttribute: function attributes belong to the device's context, so a process that
+// touches a second GPU has to set them there too (a plain `static bool` left every kernel with more than 48 KB of dynamic
+// shared memory unlaunchable on the second device).  One bit per device ordinal; a race sets the attribute twice.
+static inline bool once_needed(std::atomic<uint64_t>& mask, int& dev) {
+    if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;
+    return ((mask.load(std::memory_order_acquire) >> (dev & 63)) & 1ull) == 0;
+}
+static inline void once_done(std::atomic<uint64_t>& mask, int dev) { mask.fetch_or(1ull << (dev & 63), std::memory_order_release); }
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 

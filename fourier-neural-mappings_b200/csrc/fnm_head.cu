@@ -420,11 +420,12 @@ int fnm_lift_bwd(const float* g, const float* x, float* dw, float* db, int B, in
     const size_t smem = (size_t)slots * (J + 1) * C * sizeof(float);
     if (smem > 100 * 1024 || threads > 256) return fail(FNM_ENOTSUP, "lift_bwd: reduction tile too large");
     cudaStream_t st = as_stream(stream);
-    static bool attr_set = false;
-    if (!attr_set) {
+    static std::atomic<uint64_t> attr_set{0};
+    int attr_set_dev = 0;
+    if (once_needed(attr_set, attr_set_dev)) {
         cudaFuncSetAttribute(lift_bwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
         cudaFuncSetAttribute(lift_bwd_kernel<kLiftMaxJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-        attr_set = true;
+        once_done(attr_set, attr_set_dev);
     }
     {
         LaunchScope ls("lift_bwd", st);
@@ -472,13 +473,14 @@ int fnm_mlp_head_bwd(const float* h1, const float* g_out, const float* w2, float
     a.npos = npos; a.H = H; a.D = D;
     cudaStream_t st = as_stream(stream);
     const size_t smem = (size_t)8 * (D * H + D) * sizeof(float);
-    static bool attr_set = false;
-    if (!attr_set) {
+    static std::atomic<uint64_t> attr_set{0};
+    int attr_set_dev = 0;
+    if (once_needed(attr_set, attr_set_dev)) {
         cudaFuncSetAttribute(head_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
         cudaFuncSetAttribute(head_bwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
         cudaFuncSetAttribute(head_bwd_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
         cudaFuncSetAttribute(head_bwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-        attr_set = true;
+        once_done(attr_set, attr_set_dev);
     }
     {
         LaunchScope ls("mlp_head_bwd", st);

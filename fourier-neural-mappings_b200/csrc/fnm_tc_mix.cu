@@ -418,11 +418,12 @@ static int mx_launch(MxArgs& a, const char* what, cudaStream_t st) {
     a.a_reuse = (a.nchunks == 1 && a.ntiles > 1) ? 1 : 0;
     size_t smem = 2 * 4 * (size_t)a.nchunks * 4096 + 1024 + 256;
     if (smem < 120 * 1024) smem = 120 * 1024;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static std::atomic<uint64_t> attr_set{0};
+    int attr_set_dev = 0;
+    if (once_needed(attr_set, attr_set_dev)) {
         const cudaError_t e = cudaFuncSetAttribute(mixgemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return fail(FNM_ECUDA, "%s: smem attribute: %s", what, cudaGetErrorString(e));
-        attr_set = true;
+        once_done(attr_set, attr_set_dev);
     }
     // raw B tile by TMA when its rows are K-contiguous: tensor [nmodes * 2 * Nt rows][Kt], box 32 x 32
     CUtensorMap mapB{};

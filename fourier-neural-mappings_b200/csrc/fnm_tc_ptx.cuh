@@ -28,6 +28,35 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "r"(parity)
         : "memory");
 }
+// Warp-uniform wait (ALL 32 lanes must call it converged): the loop branches on a vote, i.e. on a predicate ptxas knows to
+// be uniform, so the code that follows stays in uniform control flow and the MMA issuer's descriptor arithmetic is kept in
+// the uniform datapath (UIADD3 on uniform registers).  After the per-lane loop of mbar_wait the compiler treats the warp as
+// possibly diverged, builds every descriptor in vector registers and moves it over with R2UR right before the MMA that
+// needs it -- ~15 clk of exposed latency each (tools/probes/mma_rate_probe.cu: 30 clk per MMA instead of 16 at N = 32).
+__device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t"
+        "WAITW_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "vote.sync.all.pred q, p, 0xffffffff;\n\t"
+        "@q bra WAITW_DONE;\n\t"
+        "bra WAITW_LOOP;\n\t"
+        "WAITW_DONE:\n\t}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// Non-blocking, warp-uniform test of a phase (ALL 32 lanes converged): true when the phase with `parity` has completed.
+__device__ __forceinline__ bool mbar_test_warp(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "vote.sync.all.pred q, p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, q;\n\t}" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+// warp-uniform value of a (lane-invariant) quantity, produced by REDUX so that ptxas can keep it in a uniform register
+__device__ __forceinline__ uint32_t uniform_u32(uint32_t v) { return __reduce_min_sync(0xffffffffu, v); }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }

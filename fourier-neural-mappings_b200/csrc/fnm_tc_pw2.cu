@@ -25,6 +25,7 @@ namespace fnm {
 namespace tc {
 
 constexpr int kPwThreads = 18 * 32;
+constexpr int kPwMmaWarp = 1;
 constexpr int kPwMaxStages = 6;
 constexpr uint32_t kPwSmemBudget = 226 * 1024;
 
@@ -36,11 +37,12 @@ struct PwArgs2 {
     int NT, tiles_per_row, seg_tiles, nseg, units;
     int K1slabs, K2slabs, LYp, stages, nlo, nz, debug;
     uint32_t stage_bytes, x_bytes, z_bytes;
+    uint32_t tmem0;                                  // always 0: the TMEM base as a kernel parameter (see the MMA issuer)
 };
 
 // Optional per-role timeline of CTA 0 (build with -DFNM_PW2_TRACE; tools/pw2_trace.py reads it).  Never in the product build.
 #ifdef FNM_PW2_TRACE
-constexpr int kTraceTiles = 96, kTraceEv = 12;
+constexpr int kTraceTiles = 96, kTraceEv = 24;
 __device__ long long g_pw2_trace[kTraceTiles * kTraceEv];
 #define PW2_TRACE(tile_idx, ev)                                                                     \
     do {                                                                                            \
@@ -73,17 +75,23 @@ __device__ __forceinline__ void umma_ts32(uint32_t d, uint32_t a_tmem, uint32_t 
 // K1S / NKS2 < 0: runtime extents (generic shapes).
 // The Z^T operand (A2) of a new grid row is awaited only after the channel part has been issued (a2_bar != nullptr
 // on the row's first tile): the Z warpgroup converts the next row while those MMAs keep the tensor pipe busy.
-template <int K1S, int NKS2, bool SINGLE>
+// `early` runs before the last four k-steps: the issuer does there the barrier waits of what it issues NEXT, so that the
+// ~90 clk of each mbarrier wait pass while the tensor pipe still has queued MMAs.  (The MMA queue is only a few
+// instructions deep: with every wait at the top of a tile the pipe idled ~1600 clk per 2304-clk tile -- per-role
+// timeline in DESIGN.md section 4.)
+template <int K1S, int NKS2, bool SINGLE, typename Early>
 __device__ __forceinline__ void pw2_issue_raw(uint32_t d, uint32_t tb, uint32_t a2hi, uint32_t a2lo, uint32_t x_lo,
                                               uint32_t by_lo, uint32_t slab16, uint32_t idesc, int k1s_rt, int nks2_rt,
-                                              uint64_t* a2_bar, uint32_t a2_par) {
+                                              uint64_t* a2_bar, uint32_t a2_par, Early&& early) {
     const int k1s = K1S >= 0 ? K1S : k1s_rt, nks2 = NKS2 >= 0 ? NKS2 : nks2_rt;
+    const int total = 4 * k1s + nks2, e_at = total > 4 ? total - 4 : 0;
     uint32_t accum = 0;
 #pragma unroll
     for (int kb = 0; kb < (K1S >= 0 ? K1S : 4); ++kb) {
         if (kb < k1s) {
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks) {
+                if (4 * kb + ks == e_at) early();
                 const uint32_t b = x_lo + kb * slab16 + 2 * ks;
                 umma_ts32(d, tb + kA1Hi + kb * 32 + ks * 8, b, idesc, accum);
                 accum = 1;
@@ -92,12 +100,13 @@ __device__ __forceinline__ void pw2_issue_raw(uint32_t d, uint32_t tb, uint32_t 
         }
     }
     if (a2_bar) {
-        mbar_wait(a2_bar, a2_par);
+        mbar_wait_warp(a2_bar, a2_par);
         tc_fence_after();
     }
 #pragma unroll
     for (int k8 = 0; k8 < (NKS2 >= 0 ? NKS2 : 8); ++k8) {
         if (k8 < nks2) {
+            if (4 * k1s + k8 == e_at) early();
             const uint32_t b = by_lo + (k8 >> 2) * slab16 + 2 * (k8 & 3);
             umma_ts32(d, a2hi + k8 * 8, b, idesc, accum);
             accum = 1;
@@ -107,20 +116,116 @@ __device__ __forceinline__ void pw2_issue_raw(uint32_t d, uint32_t tb, uint32_t 
 }
 
 // remainder pass of one tile: D += A_hi * B_lo
-template <int K1S, int NKS2>
+template <int K1S, int NKS2, typename Early>
 __device__ __forceinline__ void pw2_issue_lo(uint32_t d, uint32_t tb, uint32_t a2hi, uint32_t x_lo, uint32_t by_lo,
-                                             uint32_t slab16, uint32_t idesc, int k1s_rt, int nks2_rt) {
+                                             uint32_t slab16, uint32_t idesc, int k1s_rt, int nks2_rt, Early&& early) {
     const int k1s = K1S >= 0 ? K1S : k1s_rt, nks2 = NKS2 >= 0 ? NKS2 : nks2_rt;
+    const int total = 4 * k1s + nks2, e_at = total > 8 ? total - 8 : 0;
 #pragma unroll
     for (int kb = 0; kb < (K1S >= 0 ? K1S : 4); ++kb) {
         if (kb < k1s) {
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks) umma_ts32(d, tb + kA1Hi + kb * 32 + ks * 8, x_lo + kb * slab16 + 2 * ks, idesc, 1);
+            for (int ks = 0; ks < 4; ++ks) {
+                if (4 * kb + ks == e_at) early();
+                umma_ts32(d, tb + kA1Hi + kb * 32 + ks * 8, x_lo + kb * slab16 + 2 * ks, idesc, 1);
+            }
         }
     }
 #pragma unroll
     for (int k8 = 0; k8 < (NKS2 >= 0 ? NKS2 : 8); ++k8) {
-        if (k8 < nks2) umma_ts32(d, a2hi + k8 * 8, by_lo + (k8 >> 2) * slab16 + 2 * (k8 & 3), idesc, 1);
+        if (k8 < nks2) {
+            if (4 * k1s + k8 == e_at) early();
+            umma_ts32(d, a2hi + k8 * 8, by_lo + (k8 >> 2) * slab16 + 2 * (k8 & 3), idesc, 1);
+        }
+    }
+}
+
+struct PwBars {
+    uint64_t *full, *empty, *lo_full, *lo_empty, *a2_full, *a2_empty, *acc_full, *acc_empty;
+};
+
+// The MMA issuer's loop over this CTA's tiles, specialised on the shape.  Barrier waits are software pipelined: a tile
+// starts with its accumulator and stage already awaited (by the previous tile's `early` hook), awaits its remainder tile
+// before the last raw k-steps and the NEXT tile's accumulator / stage before the last remainder k-steps.
+template <int K1S, int NKS2, bool SINGLE>
+__device__ __forceinline__ void pw2_mma_loop(const PwArgs2& a, const PwBars& B, uint32_t sbase, uint32_t lo_base0, int my_units,
+                                             uint32_t na2, bool has_z) {
+    const uint32_t idesc = make_idesc(128, a.NT);
+    const int nks2 = a.LYp / 8;                                   // k-steps over the (padded) mode axis
+    const uint32_t slab16 = (uint32_t)a.NT * 8u;                  // slab stride in 16-byte descriptor units
+    const uint32_t xb16 = a.x_bytes >> 4;
+    // tiles of this CTA (for "is there a next tile")
+    uint32_t total = 0;
+    {
+        int unit = (int)blockIdx.x;
+        for (int u = 0; u < my_units; ++u, unit += (int)gridDim.x) {
+            const int row = unit / a.nseg, seg = unit - row * a.nseg;
+            const int t0 = seg * a.seg_tiles;
+            total += (uint32_t)(min(a.tiles_per_row, t0 + a.seg_tiles) - t0);
+        }
+    }
+    // stage / phase counters advance incrementally (a `t % stages` with a run-time divisor is a vector-datapath sequence
+    // and drags every value derived from it out of the uniform registers)
+    uint32_t t = 0, s = 0, sph = 0;
+    bool tile_ready = false;                                      // this tile's accumulator and stage were seen complete early
+    int unit = (int)blockIdx.x;
+    for (int u = 0; u < my_units; ++u, unit += (int)gridDim.x) {
+        int t0, t1;
+        {
+            const int row = unit / a.nseg, seg = unit - row * a.nseg;
+            t0 = seg * a.seg_tiles;
+            t1 = min(a.tiles_per_row, t0 + a.seg_tiles);
+        }
+        const uint32_t ub = na2 == 2 ? ((uint32_t)u & 1u) : 0u, upar = (na2 == 2 ? ((uint32_t)u >> 1) : (uint32_t)u) & 1u;
+        const uint32_t a2off = kA2Hi + (na2 == 2 ? 64u * ub : 0u);
+        for (int tile = t0; tile < t1; ++tile, ++t) {
+            uint64_t* a2_bar = (has_z && tile == t0) ? &B.a2_full[ub] : nullptr;
+            const uint32_t acc = t & 1;
+            if (!tile_ready) {
+                mbar_wait_warp(&B.acc_empty[acc], ((t >> 1) & 1) ^ 1);
+                mbar_wait_warp(&B.full[s], sph);
+            }
+            tc_fence_after();
+            PW2_TRACE(t, 1);
+            // per-tile bases produced by REDUX (destination = a uniform register, defined INSIDE the tile loop so the 48
+            // operand addresses are not hoisted out of it as 48 long-lived values): every MMA operand below is
+            // `uniform base + immediate`, one UIADD3 away from its UTCHMMA
+            const uint32_t tmem_base = uniform_u32(a.tmem0 + (t & 0u));
+            const uint32_t d = tmem_base + kD0 + acc * 64u;
+            const uint32_t a2hi = tmem_base + a2off, a2lo = a2hi + (na2 == 2 ? 32u : 64u);
+            const uint32_t x_lo = uniform_u32(desc_lo(sbase + s * a.stage_bytes)), by_lo = x_lo + xb16;
+            const uint32_t lb = a.nlo == 2 ? (t & 1) : 0u;
+            const uint32_t xl_lo = uniform_u32(desc_lo(lo_base0 + lb * a.stage_bytes)), byl_lo = xl_lo + xb16;
+            // the next tile's stage / accumulator
+            uint32_t s1 = s + 1, sph1 = sph;
+            if (s1 == (uint32_t)a.stages) { s1 = 0; sph1 ^= 1u; }
+            const bool more = t + 1 < total;
+            // The hooks only TEST (non-blocking): a barrier that is not complete yet is awaited where it is needed, as
+            // before -- blocking here would tie this tile's completion to the NEXT tile's data and cost a pipeline stage.
+            bool next_ready = false, lo_ready = false;
+            auto test_next = [&]() {
+                next_ready = more && mbar_test_warp(&B.acc_empty[acc ^ 1u], (((t + 1) >> 1) & 1) ^ 1) && mbar_test_warp(&B.full[s1], sph1);
+            };
+            auto test_lo = [&]() { lo_ready = mbar_test_warp(&B.lo_full[lb], a.nlo == 2 ? ((t >> 1) & 1) : (t & 1)); };
+            // raw passes: (A_hi + A_lo) * B_raw
+            if (SINGLE) pw2_issue_raw<K1S, NKS2, true>(d, tmem_base, a2hi, a2lo, x_lo, by_lo, slab16, idesc, a.K1slabs, nks2, a2_bar, upar, test_next);
+            else pw2_issue_raw<K1S, NKS2, false>(d, tmem_base, a2hi, a2lo, x_lo, by_lo, slab16, idesc, a.K1slabs, nks2, a2_bar, upar, test_lo);
+            umma_commit(&B.empty[s]);                              // the raw tile is free once the raw passes retire
+            PW2_TRACE(t, 2);
+            if (!SINGLE) {
+                // remainder pass: A_hi * B_lo
+                if (!lo_ready) mbar_wait_warp(&B.lo_full[lb], a.nlo == 2 ? ((t >> 1) & 1) : (t & 1));
+                tc_fence_after();
+                pw2_issue_lo<K1S, NKS2>(d, tmem_base, a2hi, xl_lo, byl_lo, slab16, idesc, a.K1slabs, nks2, test_next);
+                umma_commit(&B.lo_empty[lb]);
+            }
+            umma_commit(&B.acc_full[acc]);
+            PW2_TRACE(t, 4);
+            if (has_z && tile == t1 - 1) umma_commit(&B.a2_empty[ub]);
+            s = s1;
+            sph = sph1;
+            tile_ready = next_ready;
+        }
     }
 }
 
@@ -194,6 +299,9 @@ __device__ __forceinline__ void pw2_epilogue(const PwArgs2& a, int warp, int lan
 #pragma unroll 1
             for (int c = 0; c < nsteps; ++c) {
                 uint32_t r[8];
+#ifdef FNM_PW2_DEBUG_SWITCHES
+                if (a.debug & 8) { for (int j = 0; j < 8; ++j) r[j] = 0; } else
+#endif
                 tmem_ld8(taddr + c * 8, r);
                 // warp-uniform fast path (all 8 positions valid in every lane): no per-element predicates or branches,
                 // so the eight GELU chains interleave
@@ -222,6 +330,9 @@ __device__ __forceinline__ void pw2_epilogue(const PwArgs2& a, int warp, int lan
                     v[j] = __uint_as_float(r[j]) + bias;
                     if (HAS_MUL) v[j] *= gelu_grad_fast(m[j]);
                 }
+#ifdef FNM_PW2_DEBUG_SWITCHES
+                if ((a.debug & 1) && v[0] != 123.456f) continue;
+#endif
                 if (full) {
 #pragma unroll
                     for (int j = 0; j < 8; ++j) *at_w(op, offs[j]) = v[j];
@@ -268,7 +379,7 @@ pw2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUt
     uint64_t* acc_empty = lo_full + 18;             // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(lo_full + 20);
 
-    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+    const int warp = (int)uniform_u32(threadIdx.x >> 5), lane = threadIdx.x & 31;
     const bool has_x = a.CI > 0, has_z = a.LY > 0;
     // Z^T hi/lo (A2): one 128-column buffer for up to 64 mode columns, or -- when LYp <= 32 -- two 64-column
     // buffers so that the next grid row's Z is converted while the current row is still being multiplied
@@ -338,6 +449,9 @@ pw2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUt
                     const uint32_t s = t % (uint32_t)a.stages;
                     mbar_wait(&empty[s], ((t / (uint32_t)a.stages) & 1) ^ 1);
                     PW2_TRACE(t, 10);
+#ifdef FNM_PW2_DEBUG_SWITCHES
+                    if ((a.debug & 4) && t >= (uint32_t)a.stages) { mbar_arrive(&full[s]); continue; }
+#endif
                     mbar_expect_tx(&full[s], a.stage_bytes);
                     uint8_t* st = smem + (size_t)s * a.stage_bytes;
                     const int y0 = tile * a.NT;
@@ -350,73 +464,32 @@ pw2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUt
                 }
             }
         }
-    } else if (warp == 1) {
+    } else if (warp == kPwMmaWarp) {
         // =========================================================================== MMA issuer
+        // One CTA per SM owns all 512 TMEM columns, so the allocation starts at lane 0 / column 0; the issue loop takes the
+        // base from a kernel PARAMETER (always 0: a uniform-register source) so that every TMEM operand address stays in
+        // the uniform datapath.
+        if (tmem_base != 0u) __trap();
         const uint32_t sbase = smem_u32(smem);
         const uint32_t lo_base0 = smem_u32(lo_buf);
         // One MMA shape for every tile.  Issuing the half-empty last tile of a row with a narrower N (idesc N = 32) was
         // measured 10-14 % SLOWER overall: alternating instruction shapes costs more than the columns it saves.
-        const uint32_t idesc = make_idesc(128, a.NT);
-        const int nks2 = a.LYp / 8;                                   // k-steps over the (padded) mode axis
-        const uint32_t slab16 = (uint32_t)a.NT * 8u;                  // slab stride in 16-byte descriptor units
-        const uint32_t xb16 = a.x_bytes >> 4;
-        uint32_t t = 0;
-        for (int u = 0; u < my_units; ++u) {
-            int row, t0, t1;
-            unit_tiles(u, row, t0, t1);
-            const uint32_t ub = (uint32_t)u % na2, upar = ((uint32_t)u / na2) & 1;
-            const uint32_t a2hi = tmem_base + kA2Hi + (na2 == 2 ? 64u * ub : 0u), a2lo = a2hi + (na2 == 2 ? 32u : 64u);
-            for (int tile = t0; tile < t1; ++tile, ++t) {
-                uint64_t* a2_bar = (has_z && tile == t0) ? &a2_full[ub] : nullptr;
-                const uint32_t s = t % (uint32_t)a.stages, acc = t & 1;
-                mbar_wait(&acc_empty[acc], ((t >> 1) & 1) ^ 1);
-                PW2_TRACE(t, 0);
-                mbar_wait(&full[s], (t / (uint32_t)a.stages) & 1);
-                tc_fence_after();
-                PW2_TRACE(t, 1);
-                const uint32_t d = tmem_base + kD0 + acc * 64u;
-                const uint32_t x_lo = desc_lo(sbase + s * a.stage_bytes), by_lo = x_lo + xb16;
-                // raw passes: (A_hi + A_lo) * B_raw
-                bool done = false;
-#define PW2_RAW(K1, K2)                                                                                                  \
-                if (!done && a.K1slabs == K1 && nks2 == K2) {                                                            \
-                    if (a.single_pass) pw2_issue_raw<K1, K2, true>(d, tmem_base, a2hi, a2lo, x_lo, by_lo, slab16, idesc, 0, 0, a2_bar, upar);  \
-                    else pw2_issue_raw<K1, K2, false>(d, tmem_base, a2hi, a2lo, x_lo, by_lo, slab16, idesc, 0, 0, a2_bar, upar);               \
-                    done = true;                                                                                         \
-                }
-                PW2_SHAPES(PW2_RAW)
-#undef PW2_RAW
-                if (!done) {
-                    if (a.single_pass) pw2_issue_raw<-1, -1, true>(d, tmem_base, a2hi, a2lo, x_lo, by_lo, slab16, idesc, a.K1slabs, nks2, a2_bar, upar);
-                    else pw2_issue_raw<-1, -1, false>(d, tmem_base, a2hi, a2lo, x_lo, by_lo, slab16, idesc, a.K1slabs, nks2, a2_bar, upar);
-                }
-                umma_commit(&empty[s]);                              // the raw tile is free once the raw passes retire
-                PW2_TRACE(t, 2);
-                if (!a.single_pass) {
-                    // remainder pass: A_hi * B_lo
-                    const uint32_t lb = a.nlo == 2 ? (t & 1) : 0u;
-                    const uint32_t xl_lo = desc_lo(lo_base0 + lb * a.stage_bytes), byl_lo = xl_lo + xb16;
-                    mbar_wait(&lo_full[lb], a.nlo == 2 ? ((t >> 1) & 1) : (t & 1));
-                    tc_fence_after();
-                    PW2_TRACE(t, 3);
-                    done = false;
-#define PW2_LO(K1, K2)                                                                                                   \
-                    if (!done && a.K1slabs == K1 && nks2 == K2) {                                                        \
-                        pw2_issue_lo<K1, K2>(d, tmem_base, a2hi, xl_lo, byl_lo, slab16, idesc, 0, 0);                          \
-                        done = true;                                                                                     \
-                    }
-                    PW2_SHAPES(PW2_LO)
-#undef PW2_LO
-                    if (!done) pw2_issue_lo<-1, -1>(d, tmem_base, a2hi, xl_lo, byl_lo, slab16, idesc, a.K1slabs, nks2);
-                    umma_commit(&lo_empty[lb]);
-                }
-                umma_commit(&acc_full[acc]);
-                PW2_TRACE(t, 4);
-                if (has_z && tile == t1 - 1) umma_commit(&a2_empty[ub]);
-                __syncwarp();
-            }
+        PwBars B{full, empty, lo_full, lo_empty, a2_full, a2_empty, acc_full, acc_empty};
+        const int nks2 = a.LYp / 8;
+        bool done = false;
+#define PW2_LOOP(K1, K2)                                                                                                 \
+        if (!done && a.K1slabs == K1 && nks2 == K2) {                                                                    \
+            if (a.single_pass) pw2_mma_loop<K1, K2, true>(a, B, sbase, lo_base0, my_units, na2, has_z);                  \
+            else pw2_mma_loop<K1, K2, false>(a, B, sbase, lo_base0, my_units, na2, has_z);                               \
+            done = true;                                                                                                 \
         }
-    } else if (warp < 6) {
+        PW2_SHAPES(PW2_LOOP)
+#undef PW2_LOOP
+        if (!done) {
+            if (a.single_pass) pw2_mma_loop<-1, -1, true>(a, B, sbase, lo_base0, my_units, na2, has_z);
+            else pw2_mma_loop<-1, -1, false>(a, B, sbase, lo_base0, my_units, na2, has_z);
+        }
+    } else if (warp >= 2 && warp < 6) {
         // =========================================================================== Z warpgroup: Z[row] (smem) -> A2 hi/lo (TMEM)
         const int q4 = warp & 3, c = q4 * 32 + lane;
         const uint32_t lane_base = tmem_base + ((uint32_t)(q4 * 32) << 16);
@@ -444,7 +517,7 @@ pw2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUt
             __syncwarp();
             if (lane == 0) { mbar_arrive(&z_empty[zb]); mbar_arrive(&a2_full[ub]); }
         }
-    } else if (warp < 10) {
+    } else if (warp >= 6 && warp < 10) {
         // =========================================================================== converters: lo = raw - trunc(raw)
         if (!a.single_pass) {
             const int ct = threadIdx.x - 6 * 32;                       // 0..127
@@ -463,6 +536,9 @@ pw2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUt
                     // linear copy (the remainder tile has the raw tile's swizzled layout, so offsets are identical):
                     // stage_bytes is a multiple of 4 KB; 2 KB per pass of the 128 threads, two passes per iteration
                     uint32_t off = 0;
+#ifdef FNM_PW2_DEBUG_SWITCHES
+                    if (a.debug & 2) off = a.stage_bytes;
+#endif
                     for (; off + 4096u <= a.stage_bytes; off += 4096u) {
                         float4 v0, v1;
                         asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v0.x), "=f"(v0.y), "=f"(v0.z), "=f"(v0.w) : "r"(src + off));
@@ -488,7 +564,7 @@ pw2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUt
                 }
             }
         }
-    } else {
+    } else if (warp >= 10 && warp < 18) {
         // =========================================================================== epilogue (8 warps)
         // explicitly specialised on (GELU' operand, GELU copy): with the flags tested per element the loop is
         // 2x slower, and whether ptxas unswitches it on its own changes with unrelated edits (measured)
@@ -651,11 +727,12 @@ int tc_pw2(const float* x, const float* wc, int wc_is_kn, const float* bias, con
     }
     if (LY == 0) { mb = mx; mz = mx; }                          // never dereferenced without a spectral term
     const size_t smem = (size_t)(a.stages + a.nlo) * a.stage_bytes + (size_t)a.nz * a.z_bytes + 1024 + 512;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static std::atomic<uint64_t> attr_set{0};
+    int attr_set_dev = 0;
+    if (once_needed(attr_set, attr_set_dev)) {
         const cudaError_t e = cudaFuncSetAttribute(pw2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return fail(FNM_ECUDA, "pointwise_ysyn: smem attribute: %s", cudaGetErrorString(e));
-        attr_set = true;
+        once_done(attr_set, attr_set_dev);
     }
     const int grid = a.units < sm_count() ? a.units : sm_count();
     {

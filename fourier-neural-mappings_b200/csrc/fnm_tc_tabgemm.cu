@@ -464,11 +464,12 @@ static int tg_launch(TgArgs& a, const char* what, cudaStream_t st) {
     a.tab_vec4 = (a.Kt % 4 == 0 && (reinterpret_cast<uintptr_t>(a.tab) & 15) == 0) ? 1 : 0;
     size_t smem = (size_t)a.slots * a.NT * 256 + 1024 + (3 * kTgMaxSlots + 2 * kTgMaxBuf + 4) * 8 + 16;
     if (smem < 120 * 1024) smem = 120 * 1024;                    // one CTA per SM (each owns all 512 TMEM columns)
-    static bool attr_set = false;
-    if (!attr_set) {
+    static std::atomic<uint64_t> attr_set{0};
+    int attr_set_dev = 0;
+    if (once_needed(attr_set, attr_set_dev)) {
         const cudaError_t e = cudaFuncSetAttribute(tabgemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return fail(FNM_ECUDA, "%s: smem attribute: %s", what, cudaGetErrorString(e));
-        attr_set = true;
+        once_done(attr_set, attr_set_dev);
     }
     // streamed table: TMA the raw slabs when the rows are 16-byte aligned and each group can keep a slab ahead
     CUtensorMap mapT{};

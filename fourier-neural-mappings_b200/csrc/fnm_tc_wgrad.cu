@@ -500,12 +500,13 @@ int tc_conv_wgrad(const float* g, const float* x, int act, float* dwc, float* db
             const cuuint32_t box[2] = {32, 32};
             if (tc_make_map_swz(&mg, g, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B) &&
                 tc_make_map_swz(&mx, x, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) {
-                static bool attr2 = false;
+                static std::atomic<uint64_t> attr2{0};
+    int attr2_dev = 0;
                 const size_t smem2 = (size_t)kW2Raw * kW2Tile + (size_t)kW2Lo * kW2LoTile + 128 * 4 + 1024 + 512;
-                if (!attr2) {
+                if (once_needed(attr2, attr2_dev)) {
                     const cudaError_t e2 = cudaFuncSetAttribute(conv_wgrad_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
                     if (e2 != cudaSuccess) return fail(FNM_ECUDA, "conv_wgrad: smem attribute: %s", cudaGetErrorString(e2));
-                    attr2 = true;
+                    once_done(attr2, attr2_dev);
                 }
                 {
                     LaunchScope ls("conv_wgrad", st);
@@ -521,12 +522,13 @@ int tc_conv_wgrad(const float* g, const float* x, int act, float* dwc, float* db
             }
         }
     }
-    static bool attr_set = false;
+    static std::atomic<uint64_t> attr_set{0};
+    int attr_set_dev = 0;
     const size_t smem = kCwStages * kCwStageBytes + kCwAccBytes + 2048;   // > half the SM: one CTA per SM owns the TMEM
-    if (!attr_set) {
+    if (once_needed(attr_set, attr_set_dev)) {
         const cudaError_t e = cudaFuncSetAttribute(conv_wgrad_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return fail(FNM_ECUDA, "conv_wgrad: smem attribute: %s", cudaGetErrorString(e));
-        attr_set = true;
+        once_done(attr_set, attr_set_dev);
     }
     {
         LaunchScope ls("conv_wgrad", st);

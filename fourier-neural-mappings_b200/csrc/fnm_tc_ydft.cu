@@ -235,11 +235,12 @@ int tc_ydft_tma(const float* x, const float* tab, float* T, int64_t rows, int P2
         if (!tc_make_map(&mt, tab, 2, dims, str, box, true)) return fail(FNM_ECUDA, "ydft: tensor map (table) failed");
     }
     const size_t smem = (size_t)kYdRaw * kYdStage + (size_t)kYdLo * kYdLoStage + 1024 + 256;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static std::atomic<uint64_t> attr_set{0};
+    int attr_set_dev = 0;
+    if (once_needed(attr_set, attr_set_dev)) {
         const cudaError_t e = cudaFuncSetAttribute(ydft_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return fail(FNM_ECUDA, "ydft: smem attribute: %s", cudaGetErrorString(e));
-        attr_set = true;
+        once_done(attr_set, attr_set_dev);
     }
     const int grid = a.pairs < sm_count() ? (int)a.pairs : sm_count();
     {

@@ -154,7 +154,8 @@ def functional_end(state, lfunc0, mlpfunc0, head, one_d):
     fc1, fc2 = mlpfunc0.fc1, mlpfunc0.fc2
     if (getattr(mlpfunc0, "act_name", None) == "gelu" and _fused_ends_ok(xv, fc1.weight, fc2.weight)
             and fc1.in_features % 4 == 0 and fc1.in_features <= 128 and fc1.out_features % 4 == 0
-            and fc1.out_features <= 128 and P2 >= 2 and (one_d or P1 >= 2)):
+            and fc1.out_features <= 128 and P2 >= 2 and (one_d or P1 >= 2)
+            and xv.shape[0] <= 65535):                                     # wsum kernels put the batch on grid.y
         # local branch without the (B, P1, P2, width_lfunc) tensors: fc1 on the fused pointwise kernel, then the
         # trapezoid-weighted GELU sum; fc2 is linear, so it commutes with the integration and acts on (B, H)
         wy = _trapz_weights(P2, xv.device)

@@ -31,6 +31,24 @@ def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+def _on_tensor_device(fn):
+    """Run an autograd Function's forward / backward with the CUDA device of its first CUDA tensor argument current:
+    the library launches on the current device and `_stream()` is that device's current stream, so a model that
+    lives on cuda:1 while cuda:0 is current must switch first (one process per GPU never notices)."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(ctx, *args):
+        dev = next((a.device for a in args if isinstance(a, torch.Tensor) and a.is_cuda), None)
+        if dev is None:
+            dev = next((t.device for t in getattr(ctx, "saved_tensors", ()) if isinstance(t, torch.Tensor) and t.is_cuda), None)
+        if dev is None or dev.index == torch.cuda.current_device():
+            return fn(ctx, *args)
+        with torch.cuda.device(dev):
+            return fn(ctx, *args)
+    return wrapper
+
+
 def _ptr(t):
     return None if t is None else C.c_void_p(t.data_ptr())
 
@@ -108,6 +126,7 @@ class FourierLayerFn(torch.autograd.Function):
     (bare SpectralConv)."""
 
     @staticmethod
+    @_on_tensor_device
     def forward(ctx, zin, xact, w0, w1, wc, bc, tables, act_in, want_act_out, sinks=(None, None)):
         _need_cuda(zin, xact, w0, w1, wc, bc)
         cached = bool(act_in) and xact is not None
@@ -150,6 +169,7 @@ class FourierLayerFn(torch.autograd.Function):
         return z, xo
 
     @staticmethod
+    @_on_tensor_device
     def backward(ctx, gz, _gxo=None):
         xk, zpre, w0, w1, wc, xh = ctx.saved_tensors
         tables = ctx.tables
@@ -205,6 +225,7 @@ class LinearFunctionalFn(torch.autograd.Function):
     """out[b, o] = F2V functional of f(zin) (LinearFunctionals1d/2d); ``xact`` = optional cached GELU(zin)."""
 
     @staticmethod
+    @_on_tensor_device
     def forward(ctx, zin, xact, w, tables, act_in, sink=None):
         _need_cuda(zin, xact, w)
         cached = bool(act_in) and xact is not None
@@ -228,6 +249,7 @@ class LinearFunctionalFn(torch.autograd.Function):
         return out
 
     @staticmethod
+    @_on_tensor_device
     def backward(ctx, g):
         xk, zpre, w, xh = ctx.saved_tensors
         tables = ctx.tables
@@ -250,6 +272,7 @@ class LinearDecoderFn(torch.autograd.Function):
     """y[b, x, y, o] = V2F decoder of the vector v[b, i] (LinearDecoder1d/2d)."""
 
     @staticmethod
+    @_on_tensor_device
     def forward(ctx, v, w, tables, sink=None):
         _need_cuda(v, w)
         v = _f32c(v)
@@ -269,6 +292,7 @@ class LinearDecoderFn(torch.autograd.Function):
         return y
 
     @staticmethod
+    @_on_tensor_device
     def backward(ctx, gy):
         v, w = ctx.saved_tensors
         tables = ctx.tables
@@ -290,6 +314,7 @@ class GeluFn(torch.autograd.Function):
     """Stand-alone exact GELU for a trunk that ends with an activation."""
 
     @staticmethod
+    @_on_tensor_device
     def forward(ctx, z):
         _need_cuda(z)
         z = _f32c(z)
@@ -299,6 +324,7 @@ class GeluFn(torch.autograd.Function):
         return y
 
     @staticmethod
+    @_on_tensor_device
     def backward(ctx, gy):
         (z,) = ctx.saved_tensors
         gy = _f32c(gy)
@@ -312,6 +338,7 @@ class LiftFn(torch.autograd.Function):
     (reference: func_to_func2d.py:79-86).  ``x`` is (B, Din, N1, N2) (1-D: N1 = 1); it gets no gradient."""
 
     @staticmethod
+    @_on_tensor_device
     def forward(ctx, x, w, b, P1, P2, ngrid):
         _need_cuda(x, w, b)
         x, w, b = _f32c(x), _f32c(w), _f32c(b)
@@ -325,6 +352,7 @@ class LiftFn(torch.autograd.Function):
         return out
 
     @staticmethod
+    @_on_tensor_device
     def backward(ctx, g):
         (x,) = ctx.saved_tensors
         B, Din, N1, N2, P1, P2, Cw, ngrid = ctx.dims
@@ -344,6 +372,7 @@ class PointwiseConvFn(torch.autograd.Function):
     pointwise kernel without a spectral term (forward and input gradient) + conv_wgrad (dW, db)."""
 
     @staticmethod
+    @_on_tensor_device
     def forward(ctx, x, w, b):
         _need_cuda(x, w, b)
         x, w = _f32c(x), _f32c(w)
@@ -357,6 +386,7 @@ class PointwiseConvFn(torch.autograd.Function):
         return out
 
     @staticmethod
+    @_on_tensor_device
     def backward(ctx, g):
         x, w = ctx.saved_tensors
         g = _f32c(g)
@@ -386,6 +416,7 @@ class ResampleFn(torch.autograd.Function):
     table.  ``x`` is viewed as (G, K, inner, C)."""
 
     @staticmethod
+    @_on_tensor_device
     def forward(ctx, x, tab, tabT, G, K, M, inner):
         _need_cuda(x, tab)
         x = _f32c(x)
@@ -396,6 +427,7 @@ class ResampleFn(torch.autograd.Function):
         return out
 
     @staticmethod
+    @_on_tensor_device
     def backward(ctx, g):
         G, K, M, inner, Cc = ctx.dims
         g = _f32c(g)
@@ -432,6 +464,7 @@ class MlpHeadFn(torch.autograd.Function):
     reference MLP, shared.py:26-45) without materialising GELU(h1)."""
 
     @staticmethod
+    @_on_tensor_device
     def forward(ctx, h1, w2, b2):
         _need_cuda(h1, w2, b2)
         h1, w2 = _f32c(h1), _f32c(w2)
@@ -445,6 +478,7 @@ class MlpHeadFn(torch.autograd.Function):
         return out
 
     @staticmethod
+    @_on_tensor_device
     def backward(ctx, g):
         h1, w2 = ctx.saved_tensors
         g = _f32c(g)
@@ -465,6 +499,7 @@ class WeightedGeluSumFn(torch.autograd.Function):
     (func_to_vec2d.py:100-104); fc2 is linear and is applied to S afterwards."""
 
     @staticmethod
+    @_on_tensor_device
     def forward(ctx, h1, wx, wy):
         _need_cuda(h1, wx, wy)
         h1, wx, wy = _f32c(h1), _f32c(wx), _f32c(wy)
@@ -478,6 +513,7 @@ class WeightedGeluSumFn(torch.autograd.Function):
         return S
 
     @staticmethod
+    @_on_tensor_device
     def backward(ctx, gS):
         h1, wx, wy = ctx.saved_tensors
         B, P1, P2, H = h1.shape

@@ -152,9 +152,20 @@ class GraphedTrainStep:
     returned loss tensor is overwritten by every replay."""
 
     def __init__(self, model, optimizer, grads, loss_fn, x, y, group=None, warmup=3):
+        """``warmup`` eager steps run first on a side stream (allocator, workspaces, Adam state).  They are real
+        optimizer updates, so parameters, moments and step counts are snapshotted before and restored after: building
+        the graph leaves the model and the optimizer exactly as they were (moments that did not exist yet are zeroed,
+        which is what lazy creation at the first replay would have produced)."""
         if not getattr(optimizer, "capturable", False):
             raise ValueError("GraphedTrainStep needs Adam(capturable=True): the step count must live on the device")
         self.x, self.y = x.clone(), y.clone()
+        params = [p for g in optimizer.param_groups for p in g["params"]]
+        saved_p = [p.detach().clone(memory_format=torch.preserve_format) for p in params]
+        saved_s = []
+        for p in params:
+            st = optimizer.state.get(p) or {}
+            saved_s.append({k: (v.detach().clone(memory_format=torch.preserve_format) if isinstance(v, torch.Tensor) else v)
+                            for k, v in st.items()})
         # the capture stream differs from the stream the AccumulateGrad nodes were created on: expected here
         if hasattr(torch.autograd.graph, "set_warn_on_accumulate_grad_stream_mismatch"):
             torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)
@@ -165,17 +176,41 @@ class GraphedTrainStep:
                 train_step(model, optimizer, grads, loss_fn, self.x, self.y, group)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
+        with torch.no_grad():                                  # undo the warm-up updates (in place: the graph records addresses)
+            for p, p0, s0 in zip(params, saved_p, saved_s):
+                p.copy_(p0)
+                st = optimizer.state.get(p)
+                if not st:
+                    continue
+                for k, v in st.items():
+                    if isinstance(v, torch.Tensor):
+                        v.copy_(s0[k]) if k in s0 else v.zero_()
+                    else:
+                        st[k] = s0.get(k, 0)
+        if hasattr(optimizer, "reset_step_counter"):
+            optimizer.reset_step_counter()
         from ._lib import launch_count
         self.graph = torch.cuda.CUDAGraph()
         n0 = launch_count()
         with torch.cuda.graph(self.graph):
             self.loss = train_step(model, optimizer, grads, loss_fn, self.x, self.y, group)
         self.launches_per_step = launch_count() - n0
+        self.optimizer = optimizer
+        if hasattr(optimizer, "graph_captured"):
+            optimizer.graph_captured()
+
+    def close(self):
+        """Drop the CUDA graph (call before ``dist.destroy_process_group()``: NCCL cannot tear a communicator down
+        while a graph that captured its kernels is alive)."""
+        self.graph = None
+        self.loss = None
 
     def __call__(self, x, y):
         self.x.copy_(x, non_blocking=True)
         self.y.copy_(y, non_blocking=True)
         self.graph.replay()
+        if hasattr(self.optimizer, "graph_replayed"):
+            self.optimizer.graph_replayed()
         return self.loss
 
 

@@ -155,11 +155,21 @@ def spectral_tables(P1, P2, m1, m2, S1=None, S2=None, one_d=False):
         rows_out = rows_in.copy()
         rows_per_w = 1
     else:
+        if m1 > P1:
+            raise ValueError(f"modes1={m1} exceeds the {P1} points of the x axis (the reference's corner-block "
+                             "assignment fails with a shape mismatch there too)")
+        low = np.arange(m1, dtype=np.int64)
         if 2 * m1 > P1:
-            raise ValueError(f"modes1={m1} needs a grid of at least {2 * m1} points along x (got {P1}): the "
-                             "two corner blocks of the reference would overlap")
-        rows_in = np.concatenate([np.arange(m1), np.arange(P1 - m1, P1)]).astype(np.int64)
-        rows_out = rows_in if S1 == P1 else _destination(twosided_source(P1, S1), P1)[rows_in]
+            # overlapping corner blocks: the reference assigns the weights1 block first and the weights2 block second
+            # (shared.py:330-333), so on the shared rows P1 - m1 .. m1 - 1 the LATER assignment wins and the weights1
+            # rows that produced them are dead (no contribution, zero gradient): zero table rows, like any dropped bin
+            low[P1 - m1:] = -1
+        rows_in = np.concatenate([low, np.arange(P1 - m1, P1)]).astype(np.int64)
+        if S1 == P1:
+            rows_out = rows_in
+        else:
+            dest = _destination(twosided_source(P1, S1), P1)
+            rows_out = np.where(rows_in >= 0, dest[np.maximum(rows_in, 0)], -1)
         rows_per_w = m1
     cols_in = np.arange(m2, dtype=np.int64)
     cols_out = cols_in if S2 == P2 else _destination(onesided_source(P2 // 2 + 1, S2), P2 // 2 + 1)[cols_in]

@@ -13,8 +13,13 @@ TOL_FP32 = 1e-5
 TOL_TF32 = 5e-3
 
 
-# see assert_parity: how much further from the float64 truth than the reference an ill-conditioned quantity may be
-NOISE_FLOOR_FACTOR = 3.0
+# see assert_parity: how much further from the float64 truth than the reference an ill-conditioned quantity may be.
+# fp32-parity mode multiplies as 3xTF32, i.e. with 22 significant bits per product against fp32's 24: where a quantity
+# is pure rounding noise (the reference's own distance from float64 far above 1e-5) the noise floor of this library is
+# up to 2^2 = 4x the reference's.  6 = that factor with a 1.5x margin for the different summation order of a truncated
+# dense DFT against an FFT.  Every use of this branch is recorded in NOISE_FLOOR_LOG and printed at the end of the run.
+NOISE_FLOOR_FACTOR = 6.0
+NOISE_FLOOR_LOG = []
 
 
 def rel_l2(a, b):
@@ -72,4 +77,8 @@ def assert_parity(got, ref32, truth64=None, tol=TOL_FP32, what=""):
     e_got, e_ref = rel_l2(got, truth64), rel_l2(ref32, truth64)
     assert e_got <= max(tol, NOISE_FLOOR_FACTOR * e_ref), \
         f"{what}: rel-L2 vs reference {e:.3e}; vs float64 truth: ours {e_got:.3e}, reference's own {e_ref:.3e}"
+    import os
+    test = os.environ.get("PYTEST_CURRENT_TEST", "?").split(" ")[0]
+    NOISE_FLOOR_LOG.append(f"{test}: {what}: vs reference {e:.2e} (> {tol:.0e}); vs float64: ours {e_got:.2e}, "
+                           f"reference's own {e_ref:.2e} (ratio {e_got / max(e_ref, 1e-300):.2f})")
     return e

@@ -157,7 +157,11 @@ def test_value_errors_like_reference():
     with pytest.raises(ValueError):
         fnm_b200.Adam([torch.nn.Parameter(torch.zeros(1))], lr=-1.0)   # Adam.py:81-82
     with pytest.raises(ValueError):
-        P.spectral_tables(6, 8, 4, 3)                               # corner blocks would overlap
+        P.spectral_tables(3, 8, 4, 3)                               # modes1 > grid: the reference's slice assignment fails too
+    # overlapping corner blocks (modes1 <= P1 < 2 modes1) RUN in the reference: the weights2 block is assigned last
+    # and wins on the shared rows (shared.py:330-333) -> those weights1 rows are dead in the tables
+    tb = P.spectral_tables(6, 8, 4, 3)
+    assert list(tb.rows_in) == [0, 1, -1, -1, 2, 3, 4, 5]
 
 
 def test_resize_helpers_match_oracle():

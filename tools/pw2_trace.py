@@ -26,6 +26,8 @@ bias = torch.randn(C_, device=dev)
 Z = torch.randn(rows, LY, C_, device=dev)
 L = lib()
 mode = 1 if variant == "tf32" else 0
+if len(sys.argv) > 2:
+    os.environ["FNM_PW2_DEBUG"] = sys.argv[2]
 for _ in range(3):
     if variant == "act":
         check(L.fnm_pointwise_ysyn(p(x), 0, p(wc), 0, p(bias), p(Z), p(tab["by"]), None, p(out), p(out2), rows, P2, LY, C_, C_, mode, st))
@@ -38,7 +40,7 @@ raw = C.CDLL(LIB_PATH)
 if not hasattr(raw, "fnm_debug_pw2_trace"):
     print("library built without -DFNM_PW2_TRACE: kernels ran, no timeline")
     sys.exit(0)
-NT, NE = 96, 12
+NT, NE = 96, 24
 buf = (C.c_longlong * (NT * NE))()
 assert raw.fnm_debug_pw2_trace(buf, NT * NE) == 0
 ev = [[buf[t * NE + e] for e in range(NE)] for t in range(NT)]
@@ -49,10 +51,8 @@ for t in range(40, 72):
     print(f"{t:3d}: {r[10]:7d} | {r[0]:7d} {r[1]:7d} {r[2]:7d} {r[3]:7d} {r[4]:7d} | {r[5]:7d} {r[6]:7d} | {r[7]:7d} {r[8]:7d} {r[9]:7d}")
 per = (ev[80][4] - ev[40][4]) / 40.0
 print("steady-state clocks per tile:", per)
-for name, a_, b_ in (("mma wait acc_empty", 4, 0), ("mma wait full", 0, 1), ("mma raw issue", 1, 2), ("mma wait lo", 2, 3), ("mma lo issue", 3, 4),
-                     ("conv work", 5, 6), ("epi wait", 7, 8), ("epi work", 8, 9)):
-    if a_ == 4:
-        d = [ev[t][0] - ev[t - 1][4] for t in range(41, 81)]
-    else:
-        d = [ev[t][b_] - ev[t][a_] for t in range(40, 80)]
-    print(f"{name:22s} mean {sum(d) / len(d):8.1f}")
+for name, a_, b_ in (("mma tile start -> raw issued", 1, 2), ("mma raw issued -> lo issued", 2, 4), ("conv work", 5, 6), ("epi wait", 7, 8), ("epi work", 8, 9)):
+    d = [ev[t][b_] - ev[t][a_] for t in range(40, 80)]
+    print(f"{name:30s} mean {sum(d) / len(d):8.1f}")
+d = [ev[t + 1][1] - ev[t][4] for t in range(40, 80)]
+print(f"{'mma lo issued -> next tile':30s} mean {sum(d) / len(d):8.1f}")
