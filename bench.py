@@ -505,9 +505,13 @@ def run_ours(args, rank, world):
         "cpu_baseline": cpu,
         "gpu_comparator": comparator,
     }
+    # teardown first, the JSON line LAST: with NCCL_DEBUG=INFO the communicator's teardown lines of every rank also go to
+    # stdout, and the one JSON line must stay the last line of the output
+    leave()
+    if world > 1:
+        time.sleep(0.5)
     print(json.dumps(line))
     sys.stdout.flush()
-    leave()
 
 
 def main():

@@ -12,6 +12,8 @@ LIB_PATH = os.path.join(_HERE, "libfnm_b200.so")
 CSRC_DIR = os.path.join(_HERE, "csrc")
 
 FNM_W_REFERENCE, FNM_W_MODE_MAJOR = 0, 1
+FNM_PLAN_ZOUT_IS_GELU_GRAD, FNM_PLAN_PRE_IS_GELU_GRAD = 1, 2
+FNM_PW_MUL_IS_GRAD, FNM_PW_OUT_IS_GRAD = 1, 2
 FNM_MODE_FP32 = 0
 FNM_MODE_TF32 = 1
 ADAM_MAX_TENSORS = 48
@@ -24,7 +26,7 @@ class FnmPlan(C.Structure):
                 ("R", C.c_int32), ("NY", C.c_int32), ("Ci", C.c_int32), ("Co", C.c_int32),
                 ("rows_per_w", C.c_int32), ("mode", C.c_int32), ("w_layout", C.c_int32),
                 ("ay", _vp), ("ayT", _vp), ("by", _vp), ("byT", _vp),
-                ("ex", _vp), ("fx", _vp), ("exb", _vp), ("fxb", _vp), ("w_shadow", _vp)]
+                ("ex", _vp), ("fx", _vp), ("exb", _vp), ("fxb", _vp), ("w_shadow", _vp), ("flags", C.c_int32)]
 
 
 _PP = C.POINTER(FnmPlan)
@@ -62,6 +64,8 @@ PROTOTYPES = {
     "fnm_mix_bwd_w": (_i32, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _sz, _i32, _vp]),
     "fnm_pointwise_ysyn": (_i32, [_vp, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32,
                                   _i32, _vp]),
+    "fnm_pointwise_ysyn_ex": (_i32, [_vp, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32,
+                                     _i32, _i32, _vp]),
     "fnm_lift_fwd": (_i32, [_vp, _vp, _vp, _vp] + [_i32] * 8 + [_vp]),
     "fnm_lift_bwd_workspace_bytes": (_sz, [_i32, _i32]),
     "fnm_lift_bwd": (_i32, [_vp, _vp, _vp, _vp] + [_i32] * 8 + [_vp, _sz, _vp]),

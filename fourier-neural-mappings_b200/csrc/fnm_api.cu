@@ -243,20 +243,29 @@ int fnm_mix_bwd_w(const float* Xh, const float* Gh, float* dw0, float* dw1, int 
     return simt_mix_bwd_w(Xh, Gh, dw0, dw1, rows_per_w, B, R, NY, Ci, Co, as_stream(stream));
 }
 
-int fnm_pointwise_ysyn(const float* x, int act_in, const float* wc, int wc_is_kn, const float* bias, const float* Z,
-                       const float* by, const float* mul_gelu_grad_of, float* out, float* out_act, int64_t rows, int S2,
-                       int LY, int K, int N, int mode, fnm_stream_t stream) {
+int fnm_pointwise_ysyn_ex(const float* x, int act_in, const float* wc, int wc_is_kn, const float* bias, const float* Z,
+                          const float* by, const float* mul, float* out, float* out_act, int64_t rows, int S2,
+                          int LY, int K, int N, int mode, int flags, fnm_stream_t stream) {
     FNM_REQUIRE(out && (LY == 0 || (Z && by)), "pointwise_ysyn: NULL pointer");
     FNM_REQUIRE(rows >= 0 && S2 > 0 && LY >= 0 && N > 0 && K >= 0, "pointwise_ysyn: bad extents");
     FNM_REQUIRE(LY > 0 || (x && wc && K > 0), "pointwise_ysyn: nothing to compute (no spectral and no pointwise term)");
     FNM_REQUIRE((x == nullptr) == (wc == nullptr) || K == 0, "pointwise_ysyn: x and wc must be given together");
+    FNM_REQUIRE(!(flags & FNM_PW_OUT_IS_GRAD) || (out_act && !mul), "pointwise_ysyn: FNM_PW_OUT_IS_GRAD needs out_act and no multiplier");
+    FNM_REQUIRE(!(flags & FNM_PW_MUL_IS_GRAD) || mul, "pointwise_ysyn: FNM_PW_MUL_IS_GRAD without a multiplier");
     if (tc_pw2_supported(rows, S2, LY, (x && wc) ? K : 0, N, (x && wc) ? act_in : 0, (x && wc) ? x : nullptr, Z, by))
-        return tc_pw2(x, wc, wc_is_kn, bias, Z, by, mul_gelu_grad_of, out, out_act, rows, S2, LY, K, N, mode, as_stream(stream));
-    if (LY > 0 && tc_pointwise_ysyn_supported(rows, S2, LY, (x && wc) ? K : 0, N))
-        return tc_pointwise_ysyn(x, act_in, wc, wc_is_kn, bias, Z, by, mul_gelu_grad_of, out, out_act, rows, S2, LY, K, N,
+        return tc_pw2(x, wc, wc_is_kn, bias, Z, by, mul, out, out_act, rows, S2, LY, K, N, mode, as_stream(stream), 0, flags);
+    if (flags == 0 && LY > 0 && tc_pointwise_ysyn_supported(rows, S2, LY, (x && wc) ? K : 0, N))
+        return tc_pointwise_ysyn(x, act_in, wc, wc_is_kn, bias, Z, by, mul, out, out_act, rows, S2, LY, K, N,
                                  mode, as_stream(stream));
-    return simt_pointwise_ysyn(x, act_in, wc, wc_is_kn, bias, Z, by, mul_gelu_grad_of, out, out_act, rows, S2, LY, K, N,
-                               as_stream(stream));
+    return simt_pointwise_ysyn(x, act_in, wc, wc_is_kn, bias, Z, by, mul, out, out_act, rows, S2, LY, K, N,
+                               as_stream(stream), flags);
+}
+
+int fnm_pointwise_ysyn(const float* x, int act_in, const float* wc, int wc_is_kn, const float* bias, const float* Z,
+                       const float* by, const float* mul_gelu_grad_of, float* out, float* out_act, int64_t rows, int S2,
+                       int LY, int K, int N, int mode, fnm_stream_t stream) {
+    return fnm_pointwise_ysyn_ex(x, act_in, wc, wc_is_kn, bias, Z, by, mul_gelu_grad_of, out, out_act, rows, S2, LY, K, N, mode,
+                                 0, stream);
 }
 
 // The F2V / V2F ends keep m2 + 1 columns, so their y-synthesis has LY = 2 (m2 + 1) table columns -- usually no multiple
@@ -369,8 +378,10 @@ int fnm_fourier_layer_fwd(const fnm_plan* p, const float* xin, int act_in, const
         FNM_TRY(simt_mix_fwd(xh_save, w0, w1, p->rows_per_w, Oh, p->B, p->R, p->NY, p->Ci, p->Co, st, mm));
     }
     FNM_TRY(fnm_xsyn(Oh, p->fx, Z, p->B, p->S1, p->R, p->NY, p->Co, p->mode, stream));
-    return fnm_pointwise_ysyn(wc ? xin : nullptr, act_in, wc, 0, bc, Z, p->by, nullptr, z_out, x_act_out,
-                              (int64_t)p->B * p->S1, p->S2, LY, p->Ci, p->Co, p->mode, stream);
+    const int zgrad = (p->flags & FNM_PLAN_ZOUT_IS_GELU_GRAD) ? 1 : 0;
+    FNM_REQUIRE(!zgrad || x_act_out, "layer_fwd: FNM_PLAN_ZOUT_IS_GELU_GRAD needs x_act_out");
+    return fnm_pointwise_ysyn_ex(wc ? xin : nullptr, act_in, wc, 0, bc, Z, p->by, nullptr, z_out, x_act_out,
+                                 (int64_t)p->B * p->S1, p->S2, LY, p->Ci, p->Co, p->mode, zgrad ? FNM_PW_OUT_IS_GRAD : 0, stream);
 }
 
 int fnm_fourier_layer_bwd(const fnm_plan* p, const float* g_z, const float* xin, int act_in, const float* zin_pre,
@@ -424,8 +435,9 @@ int fnm_fourier_layer_bwd(const fnm_plan* p, const float* g_z, const float* xin,
         }
         FNM_TRY(fnm_xsyn(Gxh, p->fxb, Zg, p->B, p->P1, p->R, p->NY, p->Ci, p->mode, stream));
         const float* mul = zin_pre ? zin_pre : (act_in ? xin : nullptr);
-        FNM_TRY(fnm_pointwise_ysyn(wc ? g_z : nullptr, 0, wc, 1, nullptr, Zg, p->ayT, mul, g_in, nullptr,
-                                   (int64_t)p->B * p->P1, p->P2, LY, p->Co, p->Ci, p->mode, stream));
+        const int pre_grad = (zin_pre && (p->flags & FNM_PLAN_PRE_IS_GELU_GRAD)) ? FNM_PW_MUL_IS_GRAD : 0;
+        FNM_TRY(fnm_pointwise_ysyn_ex(wc ? g_z : nullptr, 0, wc, 1, nullptr, Zg, p->ayT, mul, g_in, nullptr,
+                                      (int64_t)p->B * p->P1, p->P2, LY, p->Co, p->Ci, p->mode, pre_grad, stream));
     }
     return FNM_OK;
 }

@@ -298,7 +298,7 @@ struct MixBwdWP : FullK {
 struct PointwiseYsynP : FullK {
     const float* x; const float* wc; const float* bias; const float* Z; const float* by; const float* mul;
     float* out; float* out_act;
-    int M, N, Kc, LY, act, wc_is_kn;
+    int M, N, Kc, LY, act, wc_is_kn, flags;
     static constexpr bool A_MFAST = false, B_NFAST = true;
     __device__ __forceinline__ float a(int row, int y, int k) const {
         if (k < Kc) {
@@ -314,8 +314,8 @@ struct PointwiseYsynP : FullK {
     __device__ __forceinline__ void store(int row, int y, int n, float v) const {
         const size_t idx = ((size_t)row * M + y) * N + n;
         if (bias) v += __ldg(bias + n);
-        if (mul) v *= gelu_grad_f(__ldg(mul + idx));
-        out[idx] = v;
+        if (mul) v *= (flags & FNM_PW_MUL_IS_GRAD) ? __ldg(mul + idx) : gelu_grad_f(__ldg(mul + idx));
+        out[idx] = (out_act && (flags & FNM_PW_OUT_IS_GRAD)) ? gelu_grad_f(v) : v;
         if (out_act) out_act[idx] = gelu_f(v);
     }
 };
@@ -528,8 +528,9 @@ int simt_mix_bwd_w(const float* Xh, const float* Gh, float* dw0, float* dw1, int
 
 int simt_pointwise_ysyn(const float* x, int act, const float* wc, int wc_is_kn, const float* bias, const float* Z,
                         const float* by, const float* mul, float* out, float* out_act, int64_t rows, int S2, int LY,
-                        int K, int N, cudaStream_t st) {
+                        int K, int N, cudaStream_t st, int flags) {
     PointwiseYsynP p;
+    p.flags = flags;
     const int Kc = (x && wc) ? K : 0;
     p.K = Kc + LY; p.x = x; p.wc = wc; p.bias = bias; p.Z = Z; p.by = by; p.mul = mul; p.out = out; p.out_act = out_act;
     p.M = S2; p.N = N; p.Kc = Kc; p.LY = LY; p.act = act; p.wc_is_kn = wc_is_kn;

@@ -16,7 +16,7 @@ int simt_mix_bwd_w(const float* Xh, const float* Gh, float* dw0, float* dw1, int
                    int Co, cudaStream_t st, int mode_major = 0);
 int simt_pointwise_ysyn(const float* x, int act, const float* wc, int wc_is_kn, const float* bias, const float* Z,
                         const float* by, const float* mul, float* out, float* out_act, int64_t rows, int S2, int LY,
-                        int K, int N, cudaStream_t st);
+                        int K, int N, cudaStream_t st, int flags = 0);
 size_t simt_conv_wgrad_workspace(int64_t npos, int Ci, int Co);
 int simt_conv_wgrad(const float* g, const float* x, int act, float* dwc, float* dbc, int64_t npos, int Ci, int Co,
                     float* partial, cudaStream_t st);
@@ -70,7 +70,7 @@ bool tc_pw2_supported(int64_t rows, int S2, int LY, int K, int N, int act, const
                       int by_ld = 0);
 int tc_pw2(const float* x, const float* wc, int wc_is_kn, const float* bias, const float* Z, const float* by,
            const float* mul, float* out, float* out_act, int64_t rows, int S2, int LY, int K, int N, int mode,
-           cudaStream_t st, int by_ld = 0);
+           cudaStream_t st, int by_ld = 0, int flags = 0);
 bool tc_pointwise_ysyn_supported(int64_t rows, int S2, int LY, int K, int N);
 int tc_pointwise_ysyn(const float* x, int act, const float* wc, int wc_is_kn, const float* bias, const float* Z,
                       const float* by, const float* mul, float* out, float* out_act, int64_t rows, int S2, int LY,

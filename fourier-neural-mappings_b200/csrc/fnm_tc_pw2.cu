@@ -37,6 +37,7 @@ struct PwArgs2 {
     int NT, tiles_per_row, seg_tiles, nseg, units;
     int K1slabs, K2slabs, LYp, stages, nlo, nz, debug;
     uint32_t stage_bytes, x_bytes, z_bytes;
+    int mul_raw, out_grad;                           // FNM_PW_MUL_IS_GRAD / FNM_PW_OUT_IS_GRAD (see include/fnm_b200.h)
     uint32_t tmem0;                                  // always 0: the TMEM base as a kernel parameter (see the MMA issuer)
 };
 
@@ -236,7 +237,9 @@ __device__ __forceinline__ void pw2_mma_loop(const PwArgs2& a, const PwBars& B, 
 // tile: a fully unrolled 32-position body (with GELU / GELU' inline) is ~50 KB of code that every epilogue warp
 // streams through once per tile, and ncu showed those warps stalled on instruction fetch for 40 % of their samples
 // while pacing the whole kernel.  The GELU' operand of step c+1 is loaded while step c is computed.
-template <bool HAS_MUL, bool HAS_ACT>
+// HAS_MUL: 0 none, 1 multiply by GELU'(mul), 2 multiply by mul (a cached derivative); HAS_ACT: 0 none, 1 out_act = GELU(out),
+// 2 out = GELU'(v) and out_act = GELU(v) from one rcp / ex2 pair (the next layer's backward then multiplies without any math)
+template <int HAS_MUL, int HAS_ACT>
 __device__ __forceinline__ void pw2_epilogue(const PwArgs2& a, int warp, int lane, uint32_t tmem_base, int my_units,
                                              uint64_t* acc_full, uint64_t* acc_empty) {
     const int q4 = warp & 3, o = q4 * 32 + lane;
@@ -328,24 +331,33 @@ __device__ __forceinline__ void pw2_epilogue(const PwArgs2& a, int warp, int lan
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     v[j] = __uint_as_float(r[j]) + bias;
-                    if (HAS_MUL) v[j] *= gelu_grad_fast(m[j]);
+                    if (HAS_MUL == 1) v[j] *= gelu_grad_fast(m[j]);
+                    if (HAS_MUL == 2) v[j] *= m[j];
                 }
 #ifdef FNM_PW2_DEBUG_SWITCHES
                 if ((a.debug & 1) && v[0] != 123.456f) continue;
 #endif
+                float ga[8];
+                if (HAS_ACT == 2) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) { float g, dg; gelu_both_fast(v[j], g, dg); ga[j] = g; v[j] = dg; }
+                } else if (HAS_ACT == 1) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) ga[j] = gelu_fast(v[j]);
+                }
                 if (full) {
 #pragma unroll
                     for (int j = 0; j < 8; ++j) *at_w(op, offs[j]) = v[j];
                     if (HAS_ACT) {
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) *at_w(ap, offs[j]) = gelu_fast(v[j]);
+                        for (int j = 0; j < 8; ++j) *at_w(ap, offs[j]) = ga[j];
                     }
                 } else {
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         if (c * 8 + j < nv) {
                             *at_w(op, offs[j]) = v[j];
-                            if (HAS_ACT) *at_w(ap, offs[j]) = gelu_fast(v[j]);
+                            if (HAS_ACT) *at_w(ap, offs[j]) = ga[j];
                         }
                     }
                 }
@@ -568,10 +580,14 @@ pw2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUt
         // =========================================================================== epilogue (8 warps)
         // explicitly specialised on (GELU' operand, GELU copy): with the flags tested per element the loop is
         // 2x slower, and whether ptxas unswitches it on its own changes with unrelated edits (measured)
-        if (a.mul && a.out_act) pw2_epilogue<true, true>(a, warp, lane, tmem_base, my_units, acc_full, acc_empty);
-        else if (a.mul) pw2_epilogue<true, false>(a, warp, lane, tmem_base, my_units, acc_full, acc_empty);
-        else if (a.out_act) pw2_epilogue<false, true>(a, warp, lane, tmem_base, my_units, acc_full, acc_empty);
-        else pw2_epilogue<false, false>(a, warp, lane, tmem_base, my_units, acc_full, acc_empty);
+        const int mm = a.mul ? (a.mul_raw ? 2 : 1) : 0, am = a.out_act ? (a.out_grad ? 2 : 1) : 0;
+        if (mm == 0 && am == 0) pw2_epilogue<0, 0>(a, warp, lane, tmem_base, my_units, acc_full, acc_empty);
+        else if (mm == 0 && am == 1) pw2_epilogue<0, 1>(a, warp, lane, tmem_base, my_units, acc_full, acc_empty);
+        else if (mm == 0 && am == 2) pw2_epilogue<0, 2>(a, warp, lane, tmem_base, my_units, acc_full, acc_empty);
+        else if (mm == 1 && am == 0) pw2_epilogue<1, 0>(a, warp, lane, tmem_base, my_units, acc_full, acc_empty);
+        else if (mm == 2 && am == 0) pw2_epilogue<2, 0>(a, warp, lane, tmem_base, my_units, acc_full, acc_empty);
+        else if (mm == 1) pw2_epilogue<1, 1>(a, warp, lane, tmem_base, my_units, acc_full, acc_empty);       // (mul, GELU copy): not used by the layers
+        else pw2_epilogue<2, 1>(a, warp, lane, tmem_base, my_units, acc_full, acc_empty);
     }
 
     tc_fence_before();
@@ -696,13 +712,15 @@ bool tc_pw2_supported(int64_t rows, int S2, int LY, int K, int N, int act, const
 
 int tc_pw2(const float* x, const float* wc, int wc_is_kn, const float* bias, const float* Z, const float* by,
            const float* mul, float* out, float* out_act, int64_t rows, int S2, int LY, int K, int N, int mode,
-           cudaStream_t st, int by_ld) {
+           cudaStream_t st, int by_ld, int flags) {
     PwArgs2 a{};
     const int CI = (x && wc) ? K : 0;
     if (by_ld == 0) by_ld = LY;
     if (!pw2_configure(a, rows, S2, LY, CI, N, by_ld)) return fail(FNM_ENOTSUP, "pointwise_ysyn: shape not served by the TMA kernel");
     a.wc = wc; a.bias = bias; a.mul = mul; a.out = out; a.out_act = out_act; a.wc_is_kn = wc_is_kn;
     a.single_pass = mode == FNM_MODE_TF32;
+    a.mul_raw = (flags & FNM_PW_MUL_IS_GRAD) ? 1 : 0;
+    a.out_grad = (flags & FNM_PW_OUT_IS_GRAD) ? 1 : 0;
     { const char* e = getenv("FNM_PW2_DEBUG"); a.debug = e ? atoi(e) : 0; }
     CUtensorMap mx, mb, mz;
     if (LY > 0) {

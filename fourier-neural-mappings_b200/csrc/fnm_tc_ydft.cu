@@ -59,7 +59,7 @@ ydft_tma(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUten
     uint64_t* d_empty = d_full + 1;                // [1] 8 epilogue warps
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d_empty + 1);
 
-    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+    const int warp = (int)uniform_u32(threadIdx.x >> 5), lane = threadIdx.x & 31;
     const int nconv = a.single_pass ? 0 : 4;
     if (threadIdx.x == 0) {
         for (int s = 0; s < kYdRaw; ++s) { mbar_init(&raw_full[s], 1); mbar_init(&raw_empty[s], 1 + nconv); }
@@ -96,44 +96,72 @@ ydft_tma(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUten
         }
     } else if (warp == 1) {
         // =========================================================================== MMA issuer
+        // Descriptors as (constant high word, 32-bit low word) so that the per-MMA arithmetic is one uniform add; the waits
+        // of the NEXT chunk are tested (non-blocking) before the last four MMAs of the current one, so their ~90 clk pass
+        // while the tensor pipe still has queued work (same scheme as pw2_kernel's issuer).
         const uint32_t sbase = smem_u32(smem), lbase = smem_u32(lo_ring);
         const uint32_t idesc128 = make_idesc(128, 128) | (1u << 15);                // A MN-major, B K-major
         const uint32_t idesc64 = make_idesc(128, 64) | (1u << 15);
-        uint32_t q = 0;
+        constexpr uint32_t kAHi = (512u >> 4) | (1u << 14) | (1u << 29);            // SBO = 4-row k group, version 1, SWIZZLE_128B_BASE32B
+        constexpr uint32_t kALoF = (4096u >> 4) << 16;                              // LBO = next 32-channel block
+        constexpr uint32_t kBHi = (1024u >> 4) | (1u << 14) | (2u << 29);           // K-major SWIZZLE_128B
+        constexpr uint32_t kBLoF = 1u << 16;
+        auto mma = [](uint32_t d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accum) {
+            asm volatile(
+                "{\n\t.reg .pred p, q;\n\t.reg .b64 ad, bd;\n\tmov.b64 ad, {%1, %5};\n\tmov.b64 bd, {%2, %6};\n\t"
+                "elect.sync _|q, 0xffffffff;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], ad, bd, %3, p;\n\t}" ::"r"(d), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accum),
+                "r"(kAHi), "r"(kBHi) : "memory");
+        };
+        uint32_t q = 0, s = 0, sph = 0, l = 0, lph = 0;
+        bool ready = false;
         for (uint32_t it = 0; it < (uint32_t)my_pairs; ++it) {
-            mbar_wait(d_empty, (it & 1) ^ 1);
+            mbar_wait_warp(d_empty, (it & 1) ^ 1);
             tc_fence_after();
             for (uint32_t ch = 0; ch < nch; ++ch, ++q) {
-                const uint32_t s = q % kYdRaw, l = q % kYdLo;
-                mbar_wait(&raw_full[s], (q / kYdRaw) & 1);
-                if (!a.single_pass) mbar_wait(&lo_full[l], (q / kYdLo) & 1);
+                if (!ready) {
+                    mbar_wait_warp(&raw_full[s], sph);
+                    if (!a.single_pass) mbar_wait_warp(&lo_full[l], lph);
+                }
                 tc_fence_after();
-                const uint32_t st = sbase + s * kYdStage, t_raw = st + 2 * kYdATile;
-                const uint32_t lt = lbase + l * kYdLoStage;
+                const uint32_t tb = uniform_u32(tmem_base + (q & 0u));
+                const uint32_t st16 = uniform_u32(((sbase + s * kYdStage) >> 4) & 0x3fffu), lt16 = uniform_u32(((lbase + l * kYdLoStage) >> 4) & 0x3fffu);
+                const uint32_t t16 = st16 + ((2 * kYdATile) >> 4);
                 const uint32_t first = ch < 2u ? 0u : 1u;
+                uint32_t s1 = s + 1, sph1 = sph, l1 = l + 1, lph1 = lph;
+                if (s1 == (uint32_t)kYdRaw) { s1 = 0; sph1 ^= 1u; }
+                if (l1 == (uint32_t)kYdLo) { l1 = 0; lph1 ^= 1u; }
+                const bool more = q + 1 < total;
+                bool next_ready = false;
+                auto test_next = [&]() {
+                    next_ready = more && mbar_test_warp(&raw_full[s1], sph1) && (a.single_pass || mbar_test_warp(&lo_full[l1], lph1));
+                };
                 // x_raw * [tab_raw ; tab_lo] -> (main | corr) of this chunk parity, both rows, then x_lo * tab_raw -> corr
 #pragma unroll
                 for (int j = 0; j < 2; ++j) {
-                    const uint32_t d = tmem_base + (uint32_t)j * 256u + (ch & 1u) * 128u;
+                    const uint32_t d = tb + (uint32_t)j * 256u + (ch & 1u) * 128u;
+                    if (j == 1 && a.single_pass) test_next();
 #pragma unroll
                     for (int ks = 0; ks < 4; ++ks)
-                        umma_ss(d, yd_desc_mn32(st + j * kYdATile + ks * 1024u), make_desc(t_raw) + 2 * ks,
-                                a.single_pass ? idesc64 : idesc128, (ks == 0) ? first : 1u);
+                        mma(d, (st16 + (uint32_t)(j * (kYdATile >> 4) + ks * 64)) | kALoF, (t16 + 2u * ks) | kBLoF,
+                            a.single_pass ? idesc64 : idesc128, (ks == 0) ? first : 1u);
                 }
                 if (!a.single_pass) {
 #pragma unroll
                     for (int j = 0; j < 2; ++j) {
-                        const uint32_t dc = tmem_base + (uint32_t)j * 256u + (ch & 1u) * 128u + 64u;
+                        const uint32_t dc = tb + (uint32_t)j * 256u + (ch & 1u) * 128u + 64u;
+                        if (j == 1) test_next();
 #pragma unroll
                         for (int ks = 0; ks < 4; ++ks)
-                            umma_ss(dc, yd_desc_mn32(lt + j * kYdATile + ks * 1024u), make_desc(t_raw) + 2 * ks, idesc64, 1u);
+                            mma(dc, (lt16 + (uint32_t)(j * (kYdATile >> 4) + ks * 64)) | kALoF, (t16 + 2u * ks) | kBLoF, idesc64, 1u);
                     }
                     umma_commit(&lo_empty[l]);
                 }
                 umma_commit(&raw_empty[s]);
+                s = s1; sph = sph1; l = l1; lph = lph1;
+                ready = next_ready;
             }
             umma_commit(d_full);
-            __syncwarp();
         }
     } else if (warp < 6) {
         // =========================================================================== converters: lo = raw - trunc(raw)

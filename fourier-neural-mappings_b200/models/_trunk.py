@@ -6,11 +6,16 @@ GELU the activation is never materialised between layers: each fused layer kerne
 pre-activation z and the NEXT layer applies GELU while loading ("save only
 the pre-activation"); backward multiplies by GELU'(z) in the producing kernel's epilogue.
 """
+import os
+
 import torch
 import torch.nn.functional as F
 
 from .. import ops
 from ..shared import projector1d, projector2d
+
+# FNM_CACHE_GELU_GRAD=0 keeps z between fused layers (the derivative is then evaluated in the consumer's backward)
+_CACHE_GELU_GRAD = os.environ.get("FNM_CACHE_GELU_GRAD", "1") != "0"
 
 _TORCH_ACTS = {"tanh": torch.tanh, "relu": F.relu, "elu": F.elu, "leaky_relu": F.leaky_relu}
 
@@ -20,13 +25,16 @@ class Pending:
     set its GELU is still pending, and ``x`` may hold GELU(z) already (written by the producing
     kernel's epilogue, detached: gradients flow through ``z``)."""
 
-    __slots__ = ("z", "act", "x")
+    __slots__ = ("z", "act", "x", "zgrad")
 
-    def __init__(self, z, act=False, x=None):
-        self.z, self.act, self.x = z, act, x
+    def __init__(self, z, act=False, x=None, zgrad=False):
+        # zgrad: ``z`` holds GELU'(z) instead of z (ops.fourier_layer(grad_out=True)); only the next fused layer may read it
+        self.z, self.act, self.x, self.zgrad = z, act, x, zgrad
 
     def value(self):
         """The activated tensor as a differentiable value (for consumers outside the fused layers)."""
+        if self.zgrad:
+            raise RuntimeError("this activation carries GELU'(z) for the next fused layer only")
         if not self.act:
             return self.z
         y = ops.gelu(self.z)
@@ -47,15 +55,20 @@ def run_layers(state, speconvs, ws, act_name, act_flags, one_d, last_s=None):
     ``w(projector(x, s)) + speconv(x, s)`` (func_to_func2d.py:95)."""
     n = len(speconvs)
     fused_gelu = act_name == "gelu"
+
+    def changes(P1, P2):
+        if last_s is None:
+            return False
+        target = (int(last_s),) if one_d else tuple(int(v) for v in last_s)
+        return target != ((P2,) if one_d else (P1, P2))
+
     for i, (sc, w) in enumerate(zip(speconvs, ws)):
         z_in = state.z
         _, P1, P2, _ = z_in.shape
         w1 = None if one_d else sc.weights2
         last = i == n - 1
-        change = False
-        if last and last_s is not None:
-            target = (int(last_s),) if one_d else tuple(int(v) for v in last_s)
-            change = target != ((P2,) if one_d else (P1, P2))
+        change = last and changes(P1, P2)
+        zgrad = False
         if change:
             x = state.value()
             z, _ = ops.fourier_layer(x, sc.weights1, w1, None, None, _layer_tables(sc, P1, P2, one_d, last_s))
@@ -75,12 +88,16 @@ def run_layers(state, speconvs, ws, act_name, act_flags, one_d, last_s=None):
             xo = None
             # the activated copy is produced in this layer's epilogue when another fused layer consumes it
             want = bool(act_flags[i]) and fused_gelu and not last
+            # ... and when that layer is a plain fused one (the grid does not change inside the trunk), z itself is never
+            # needed again: the epilogue writes GELU'(z) in its place and the consumer's backward multiplies by it
+            zgrad = want and _CACHE_GELU_GRAD and torch.is_grad_enabled() and not (i + 1 == n - 1 and changes(P1, P2))
             z, xo = ops.fourier_layer(z_in, sc.weights1, w1, w.weight, w.bias, _layer_tables(sc, P1, P2, one_d),
-                                      act_in=state.act, xact=state.x, want_act_out=want)
+                                      act_in=state.act, xact=state.x, want_act_out=want, pre_is_grad=state.zgrad,
+                                      grad_out=zgrad)
         if not act_flags[i]:
             state = Pending(z, False)
         elif fused_gelu:
-            state = Pending(z, True, xo if not change else None)
+            state = Pending(z, True, xo if not change else None, zgrad)
         else:
             state = Pending(_TORCH_ACTS[act_name](z), False)
     return state

@@ -127,9 +127,14 @@ class FourierLayerFn(torch.autograd.Function):
 
     @staticmethod
     @_on_tensor_device
-    def forward(ctx, zin, xact, w0, w1, wc, bc, tables, act_in, want_act_out, sinks=(None, None)):
+    def forward(ctx, zin, xact, w0, w1, wc, bc, tables, act_in, want_act_out, sinks=(None, None), pre_is_grad=False,
+                grad_out=False):
         _need_cuda(zin, xact, w0, w1, wc, bc)
         cached = bool(act_in) and xact is not None
+        if pre_is_grad and not cached:
+            raise ValueError("pre_is_grad: a cached GELU'(z) input needs the cached GELU(z) beside it")
+        if grad_out and not want_act_out:
+            raise ValueError("grad_out: GELU'(z) is written beside the GELU copy only")
         xk = _f32c(xact) if cached else _f32c(zin)
         kact = 0 if cached else int(bool(act_in))
         B, P1, P2, Ci = xk.shape
@@ -154,11 +159,14 @@ class FourierLayerFn(torch.autograd.Function):
                 wsh = torch.empty(nsh, dtype=torch.uint8, device=xk.device)
                 plan.w_shadow = wsh.data_ptr()
         ctx.wsh = wsh
+        if grad_out:
+            plan.flags = _lib.FNM_PLAN_ZOUT_IS_GELU_GRAD
         check(L.fnm_fourier_layer_fwd(C.byref(plan), _ptr(xk), kact, _ptr(w0r), _ptr(w1r), _ptr(wcc), _ptr(bcc),
                                       _ptr(z), _ptr(xo), _ptr(xh), _ptr(ws), ws.numel(), _stream()),
               "fnm_fourier_layer_fwd")
         ctx.save_for_backward(xk, _f32c(zin) if cached else None, w0, w1, wc, xh)
         ctx.tables, ctx.kact, ctx.has_bias = tables, kact, bc is not None
+        ctx.pre_is_grad = bool(pre_is_grad)
         ctx.sinks = sinks
         ctx.w_version = (w0._version, w1._version if w1 is not None else 0)
         # the GELU copy carries no gradient: without this autograd would MATERIALISE a zero tensor of its size
@@ -177,13 +185,15 @@ class FourierLayerFn(torch.autograd.Function):
             for sink in ctx.sinks:
                 if sink is not None:
                     sink.zero_()                                # a sink must not keep the previous step's gradient
-            return (None,) * 10
+            return (None,) * 12
         gz = _f32c(gz)
         B, P1, P2, Ci = xk.shape
         Co = w0.shape[1]
         plan = tables.c_plan(xk.device, B, Ci, Co, _MODE)
         if ctx.wsh is not None and (w0._version, w1._version if w1 is not None else 0) == ctx.w_version:      # weights not modified in place since forward
             plan.w_shadow = ctx.wsh.data_ptr()
+        if ctx.pre_is_grad:
+            plan.flags = _lib.FNM_PLAN_PRE_IS_GELU_GRAD
         need_x, _, need_w0, need_w1, need_wc, need_bc = ctx.needs_input_grad[:6]
         g_in = torch.empty_like(xk) if need_x else None
         want_w = need_w0 or (w1 is not None and need_w1)
@@ -218,7 +228,8 @@ class FourierLayerFn(torch.autograd.Function):
             ready = getattr(sink, "_fnm_on_ready", None) if sink is not None else None
             if ready is not None:
                 ready()                                             # FlatGradients(overlap=True): start this slot's exchange
-        return (g_in, None, None if s0 is not None else dw0, None if s1 is not None else dw1, dwc, dbc, None, None, None, None)
+        return (g_in, None, None if s0 is not None else dw0, None if s1 is not None else dw1, dwc, dbc, None, None, None, None,
+                None, None)
 
 
 class LinearFunctionalFn(torch.autograd.Function):
@@ -539,9 +550,15 @@ def mlp_head(h1, w2, b2):
     return MlpHeadFn.apply(h1, w2, b2)
 
 
-def fourier_layer(zin, w0, w1, wc, bc, tables, act_in=False, xact=None, want_act_out=False):
-    """Returns (z, GELU(z) or None).  ``zin`` is the layer input (pre-activation if act_in)."""
-    return FourierLayerFn.apply(zin, xact, w0, w1, wc, bc, tables, act_in, want_act_out, (_grad_sink(w0), _grad_sink(w1)))
+def fourier_layer(zin, w0, w1, wc, bc, tables, act_in=False, xact=None, want_act_out=False, pre_is_grad=False,
+                  grad_out=False):
+    """Returns (z, GELU(z) or None).  ``zin`` is the layer input (pre-activation if act_in).
+
+    Cached GELU derivative (include/fnm_b200.h, FNM_PLAN_*): with ``grad_out`` (and want_act_out) the first result
+    holds GELU'(z) INSTEAD of z -- only a fused layer called with ``pre_is_grad`` may consume it (it multiplies its
+    outgoing gradient by that buffer instead of evaluating GELU' of it); the gradient it receives is still dL/dz."""
+    return FourierLayerFn.apply(zin, xact, w0, w1, wc, bc, tables, act_in, want_act_out, (_grad_sink(w0), _grad_sink(w1)),
+                                pre_is_grad, grad_out)
 
 
 def linear_functional(zin, w, tables, act_in=False, xact=None):

@@ -85,7 +85,23 @@ typedef struct fnm_plan {
                                                the spectral weights in forward; handing the SAME buffer (untouched,
                                                weights unchanged) to backward saves its weight permute.  NULL: both
                                                passes permute into the workspace. */
+    int32_t flags;                          /* FNM_PLAN_* (fused Fourier layer only), 0 = none */
 } fnm_plan;
+
+/* Cached GELU derivative (fused Fourier layer).  GELU'(z) of a layer's output costs ~25 instructions per element; in the
+ * backward epilogue of the NEXT layer those instructions -- not HBM or the tensor pipe -- paced the kernel.  With
+ * FNM_PLAN_ZOUT_IS_GELU_GRAD the forward pass (when x_act_out is given) writes GELU'(z) into z_out instead of z, computed
+ * from the same rcp / ex2 pair as the GELU copy; the consumer's backward gets that buffer as zin_pre together with
+ * FNM_PLAN_PRE_IS_GELU_GRAD and multiplies by it directly.  z itself is then never stored: nothing else needs it.   */
+enum {
+    FNM_PLAN_ZOUT_IS_GELU_GRAD = 1,         /* forward:  z_out := GELU'(z) (requires x_act_out != NULL) */
+    FNM_PLAN_PRE_IS_GELU_GRAD = 2           /* backward: zin_pre holds GELU'(zin), not zin */
+};
+/* flags of fnm_pointwise_ysyn_ex */
+enum {
+    FNM_PW_MUL_IS_GRAD = 1,                 /* out *= mul[...] instead of GELU'(mul[...]) */
+    FNM_PW_OUT_IS_GRAD = 2                  /* with out_act: out := GELU'(v), out_act := GELU(v), v = the pre-activation */
+};
 
 const char* fnm_version(void);
 const char* fnm_last_error(void);
@@ -209,6 +225,10 @@ int fnm_mix_bwd_w(const float* Xh, const float* Gh, float* dw0, float* dw1, int 
 int fnm_pointwise_ysyn(const float* x, int act_in, const float* wc, int wc_is_kn, const float* bias,
                        const float* Z, const float* by, const float* mul_gelu_grad_of, float* out, float* out_act,
                        int64_t rows, int S2, int LY, int K, int N, int mode, fnm_stream_t stream);
+/* the same with FNM_PW_* flags (cached GELU derivative, see above) */
+int fnm_pointwise_ysyn_ex(const float* x, int act_in, const float* wc, int wc_is_kn, const float* bias,
+                          const float* Z, const float* by, const float* mul, float* out, float* out_act,
+                          int64_t rows, int S2, int LY, int K, int N, int mode, int flags, fnm_stream_t stream);
 /* dwc[o][i] = sum_pos g[pos][o] f(x[pos][i]);  dbc[o] = sum_pos g[pos][o]   (conv weight/bias grads) */
 size_t fnm_conv_wgrad_workspace_bytes(int64_t npos, int Ci, int Co);
 int fnm_conv_wgrad(const float* g, const float* x, int act_in, float* dwc, float* dbc, int64_t npos,

@@ -714,3 +714,35 @@ def test_overlapping_corner_blocks_like_reference():
     assert rel_l2(xg.grad, xo.grad) < TOL_FP32
     assert rel_l2(sc.weights1.grad, w1.grad) < TOL_FP32 and rel_l2(sc.weights2.grad, w2.grad) < TOL_FP32
     assert torch.all(sc.weights1.grad[:, :, 3:, :] == 0)           # rows 8 - 5 = 3 .. 4 of weights1 are overwritten
+
+
+@pytest.mark.parametrize("family", ["fno2d", "fno1d", "fnd2d"])
+def test_cached_gelu_derivative_equals_the_recomputed_one(family):
+    """The trunk's default (a fused layer writes GELU'(z) in place of z for the next fused layer,
+    FNM_PLAN_ZOUT_IS_GELU_GRAD) against the same model with the cache switched off: same formula, evaluated in the
+    producer's epilogue instead of the consumer's backward."""
+    from fnm_b200.models import _trunk
+    torch.manual_seed(3)
+    if family == "fno2d":
+        model = fnm_b200.FNO2d(6, 6, 32, n_layers=4).to(DEV)
+        x = torch.randn(3, 1, 40, 40, device=DEV)
+    elif family == "fno1d":
+        model = fnm_b200.FNO1d(8, 64, n_layers=3).to(DEV)
+        x = torch.randn(3, 1, 128, device=DEV)
+    else:
+        model = fnm_b200.FND2d(5, (24, 24), 6, 6, 32, n_layers=4).to(DEV)
+        x = torch.randn(3, 5, device=DEV)
+    res = {}
+    for on in (True, False):
+        old = _trunk._CACHE_GELU_GRAD
+        _trunk._CACHE_GELU_GRAD = on
+        try:
+            model.zero_grad(set_to_none=True)
+            out = model(x)
+            out.square().sum().backward()
+            res[on] = (out.detach().clone(), {k: p.grad.detach().clone() for k, p in model.named_parameters()})
+        finally:
+            _trunk._CACHE_GELU_GRAD = old
+    assert torch.equal(res[True][0], res[False][0])
+    for k in res[True][1]:
+        assert rel_l2(res[True][1][k], res[False][1][k]) < 2e-6, k

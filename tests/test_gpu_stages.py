@@ -103,6 +103,46 @@ def test_pointwise_ysyn(case, mode):
         assert rel_l2(out_act, _gelu64(ref)) < tol
 
 
+@pytest.mark.parametrize("case", [CASES[0], CASES[9], CASES[10], CASES[12], CASES[14], CASES[19]],
+                         ids=lambda c: "r{rows}_s{S2}_ly{LY}_k{K}_n{N}_a{act}".format(**c))
+@pytest.mark.parametrize("mode", ["fp32", "tf32"])
+def test_pointwise_ysyn_cached_gelu_derivative(case, mode):
+    """fnm_pointwise_ysyn_ex: FNM_PW_OUT_IS_GRAD writes GELU'(v) | GELU(v) (forward of a fused layer), FNM_PW_MUL_IS_GRAD
+    multiplies by the operand itself (backward of the consumer) -- against float64 (include/fnm_b200.h)."""
+    from fnm_b200._lib import FNM_PW_MUL_IS_GRAD, FNM_PW_OUT_IS_GRAD
+    torch.manual_seed(1)
+    rows, S2, LY, K, N = case["rows"], case["S2"], case["LY"], case["K"], case["N"]
+    x = torch.randn(rows, S2, K, device=DEV)
+    wc = torch.randn(N, K, device=DEV) / K ** 0.5
+    bias = torch.randn(N, device=DEV)
+    Z = torch.randn(rows, max(LY, 1), N, device=DEV)
+    by = torch.randn(S2, max(LY, 1), device=DEV) / max(LY, 1) ** 0.5
+    imode = 0 if mode == "fp32" else 1
+    tol = TOL_FP32 if mode == "fp32" else TOL_TF32
+    out = torch.full((rows, S2, N), float("nan"), device=DEV)
+    out_act = torch.full((rows, S2, N), float("nan"), device=DEV)
+    check(lib().fnm_pointwise_ysyn_ex(_p(x), case["act"], _p(wc), 0, _p(bias), _p(Z), _p(by), None, _p(out), _p(out_act),
+                                      rows, S2, LY, K, N, imode, FNM_PW_OUT_IS_GRAD, _stream()), "fnm_pointwise_ysyn_ex")
+    torch.cuda.synchronize()
+    v = _pointwise_ysyn_ref(x, case["act"], wc, 0, bias, Z, by, None)
+    assert rel_l2(out_act, _gelu64(v)) < tol
+    # GELU' is O(1) where v is: the derivative of an input carrying the matmul's error
+    assert rel_l2(out, _gelu_grad64(v)) < tol
+    # consumer side: multiply by the cached derivative
+    dgrad = _gelu_grad64(v).float()
+    g = torch.randn(rows, S2, N, device=DEV)
+    wk = torch.randn(N, K, device=DEV) / N ** 0.5                 # [k = out channel of the layer][n = in channel]
+    ZK = torch.randn(rows, max(LY, 1), K, device=DEV)
+    mulK = torch.randn(rows, S2, K, device=DEV)
+    gin = torch.full((rows, S2, K), float("nan"), device=DEV)
+    check(lib().fnm_pointwise_ysyn_ex(_p(g), 0, _p(wk), 1, None, _p(ZK), _p(by), _p(mulK), _p(gin), None,
+                                      rows, S2, LY, N, K, imode, FNM_PW_MUL_IS_GRAD, _stream()), "fnm_pointwise_ysyn_ex")
+    torch.cuda.synchronize()
+    ref = _pointwise_ysyn_ref(g, 0, wk, 1, None, ZK, by, None) * mulK.double()
+    assert rel_l2(gin, ref) < tol
+    del dgrad
+
+
 def test_ydft_xdft_xsyn_roundtrip_stages():
     """ydft -> xdft -> xsyn -> ysyn with identity mixing reproduces the band-limited projection."""
     from fnm_b200.plan import spectral_tables

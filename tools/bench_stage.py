@@ -55,6 +55,8 @@ out2 = torch.empty_like(x)
 timeit("pointwise_ysyn fwd +act out (3A)", lambda: check(L.fnm_pointwise_ysyn(p(x), 0, p(wc), 0, p(bias), p(Z), p(tab["by"]), None, p(out), p(out2), rows, P2, LY, C_, C_, 0, st)), 3 * A)
 timeit("pointwise_ysyn bwd tf32", lambda: check(L.fnm_pointwise_ysyn(p(g), 0, p(wc), 1, None, p(Z), p(tab["ayT"]), p(x), p(out), None, rows, P2, LY, C_, C_, 1, st)), 3 * A)
 timeit("pointwise_ysyn bwd (3A)", lambda: check(L.fnm_pointwise_ysyn(p(g), 0, p(wc), 1, None, p(Z), p(tab["ayT"]), p(x), p(out), None, rows, P2, LY, C_, C_, 0, st)), 3 * A)
+timeit("pw_ysyn fwd grad|act out (3A)", lambda: check(L.fnm_pointwise_ysyn_ex(p(x), 0, p(wc), 0, p(bias), p(Z), p(tab["by"]), None, p(out), p(out2), rows, P2, LY, C_, C_, 0, 2, st)), 3 * A)
+timeit("pw_ysyn bwd cached grad (3A)", lambda: check(L.fnm_pointwise_ysyn_ex(p(g), 0, p(wc), 1, None, p(Z), p(tab["ayT"]), p(x), p(out), None, rows, P2, LY, C_, C_, 0, 1, st)), 3 * A)
 timeit("ydft (A + T)", lambda: check(L.fnm_ydft(p(x), p(tab["ay"]), p(T), rows, P2, LY, C_, 1, 0, st)), A + T.numel() * 4)
 timeit("ydft noact (A + T)", lambda: check(L.fnm_ydft(p(x), p(tab["ay"]), p(T), rows, P2, LY, C_, 0, 0, st)), A + T.numel() * 4)
 timeit("ydft noact tf32", lambda: check(L.fnm_ydft(p(x), p(tab["ay"]), p(T), rows, P2, LY, C_, 0, 1, st)), A + T.numel() * 4)
