@@ -64,15 +64,46 @@ def synth(shape, seed):
 
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """SM clocks / throttle reasons sampled DURING the timed region: NVML in-process every ~2 ms (the small workloads'
+    timed region is ~10 ms, far below what an `nvidia-smi -lms` subprocess resolves), nvidia-smi as the fallback."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    BITS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown"}
 
     def __init__(self, index):
         self.index, self.proc, self.lines = index, None, []
+        self.nvml, self.handle, self.samples, self.mask, self.mx, self.run = None, None, [], 0, None, False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            try:
+                uuid = str(torch.cuda.get_device_properties(index).uuid)
+                self.handle = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+            except Exception:                              # noqa: BLE001
+                self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+        except Exception:                                  # noqa: BLE001 -- no NVML: nvidia-smi below
+            self.nvml = None
+
+    def _poll(self):
+        nv = self.nvml
+        reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        while self.run:
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM)))
+                self.mask |= int(reasons(self.handle))
+            except Exception:                              # noqa: BLE001
+                pass
+            time.sleep(0.002)
 
     def start(self):
+        if self.nvml is not None:
+            self.run = True
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
@@ -87,6 +118,12 @@ class ClockSampler:
             self.lines.append(line.strip())
 
     def stop(self):
+        if self.nvml is not None:
+            self.run = False
+            self.thread.join(timeout=1)
+            sm = self.samples
+            return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": self.mx, "samples": len(sm),
+                    "reasons": sorted(n for b, n in self.BITS.items() if self.mask & b), "source": "nvml"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -109,7 +146,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(n)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "reasons": sorted(reasons), "source": "nvidia-smi"}
 
 
 def measured_peaks():
@@ -305,14 +342,11 @@ def run_ours(args, rank, world):
     y_host = synth(yshape, 1235 + rank).pin_memory()
     y = y_host.to(dev)
 
+    # SMs the persistent backward kernels leave to the NCCL kernels of the overlapped exchange (N > 1 only)
+    sm_reserve = int(os.environ.get("FNM_DP_SM_RESERVE", "16")) if world > 1 else 0
+
     def step(xd, yd):
-        grads.zero_()
-        out = model(xd)
-        loss = rel_l2_sum(out, yd)
-        loss.backward()
-        grads.all_reduce()
-        opt.step()
-        return loss
+        return fnm_b200.parallel.train_step(model, opt, grads, rel_l2_sum, xd, yd, sm_reserve=sm_reserve)
 
     def barrier():
         if world > 1:
@@ -331,7 +365,8 @@ def run_ours(args, rank, world):
     if args.graph:
         # the step recorded once in a CUDA graph; every timed step below is one replay of the full step
         try:
-            graphed = fnm_b200.parallel.GraphedTrainStep(model, opt, grads, rel_l2_sum, x, y, warmup=args.warmup)
+            graphed = fnm_b200.parallel.GraphedTrainStep(model, opt, grads, rel_l2_sum, x, y, warmup=args.warmup,
+                                                             sm_reserve=sm_reserve)
         except Exception as e:                             # noqa: BLE001 -- e.g. a collective that cannot be captured
             sys.stderr.write(f"[bench] CUDA-graph capture failed ({type(e).__name__}: {e}); running eagerly\n")
             graphed, args.graph = None, False
@@ -489,7 +524,7 @@ def run_ours(args, rank, world):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32" if args.mode == "fp32" else "tf32", "data": "synthetic",
         "config": {"workload": f"{args.workload}: {desc}", "batch_per_gpu": batch, "global_batch": batch * world,
-                   "parallelism": f"dp{world}", "compute_mode": fnm_b200.get_compute_mode(), "cuda_graph": bool(args.graph),
+                   "parallelism": f"dp{world}", "sm_reserve_backward": sm_reserve, "compute_mode": fnm_b200.get_compute_mode(), "cuda_graph": bool(args.graph),
                    "tcgen05": bool(_lib.lib().fnm_has_tcgen05()),
                    "l2": ("working set %.0f MB per activation, larger than the 126 MB L2" % (wl["A"] / 1e6))
                    if wl["A"] > 126e6 else "working set fits L2 (back-to-back steps, no flush)",

@@ -37,6 +37,7 @@ PROTOTYPES = {
     "fnm_last_error": (C.c_char_p, []),
     "fnm_has_tcgen05": (_i32, []),
     "fnm_launch_count": (_i64, []),
+    "fnm_set_sm_limit": (_i32, [_i32]),
     "fnm_profile_begin": (_i32, []),
     "fnm_profile_end": (_sz, [C.c_char_p, _sz]),
     "fnm_fourier_layer_workspace_bytes": (_sz, [_PP]),
@@ -121,6 +122,11 @@ def check(rc, what=""):
 
 def version():
     return lib().fnm_version().decode()
+
+
+def set_sm_limit(n):
+    """Cap the grid of the persistent kernels at ``n`` CTAs (0 = every SM); returns the previous cap."""
+    return int(lib().fnm_set_sm_limit(int(n)))
 
 
 def launch_count():

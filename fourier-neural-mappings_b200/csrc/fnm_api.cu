@@ -118,6 +118,8 @@ int fnm_has_tcgen05(void) { return tc_available(); }
 
 int64_t fnm_launch_count(void) { return g_launches.load(); }
 
+int fnm_set_sm_limit(int n) { return tc_set_sm_limit(n); }
+
 int fnm_profile_begin(void) {
     std::lock_guard<std::mutex> lk(g_prof_mu);
     for (auto& r : g_prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
@@ -282,7 +284,7 @@ __global__ void pad_table_kernel(const float* __restrict__ src, float* __restric
 static size_t padded_table_bytes(int S2, int LY) { return LY % 4 == 0 ? 0 : align_up((size_t)S2 * ((LY + 3) / 4 * 4) * sizeof(float), 256); }
 
 static int ysyn_only(const float* Z, const float* by, const float* mul, float* out, int64_t rows, int S2, int LY, int N, int mode,
-                     float* tab_scratch, fnm_stream_t stream) {
+                     float* tab_scratch, fnm_stream_t stream, int flags = 0) {
     const int ld = (LY + 3) / 4 * 4;
     if (LY % 4 != 0 && tab_scratch && tc_pw2_supported(rows, S2, LY, 0, N, 0, nullptr, Z, tab_scratch, ld)) {
         cudaStream_t st = as_stream(stream);
@@ -291,9 +293,9 @@ static int ysyn_only(const float* Z, const float* by, const float* mul, float* o
             pad_table_kernel<<<(S2 * ld + 255) / 256, 256, 0, st>>>(by, tab_scratch, S2, LY, ld);
         }
         FNM_TRY(check_launch("pad_table"));
-        return tc_pw2(nullptr, nullptr, 0, nullptr, Z, tab_scratch, mul, out, nullptr, rows, S2, LY, 0, N, mode, st, ld);
+        return tc_pw2(nullptr, nullptr, 0, nullptr, Z, tab_scratch, mul, out, nullptr, rows, S2, LY, 0, N, mode, st, ld, flags);
     }
-    return fnm_pointwise_ysyn(nullptr, 0, nullptr, 0, nullptr, Z, by, mul, out, nullptr, rows, S2, LY, 0, N, mode, stream);
+    return fnm_pointwise_ysyn_ex(nullptr, 0, nullptr, 0, nullptr, Z, by, mul, out, nullptr, rows, S2, LY, 0, N, mode, flags, stream);
 }
 
 size_t fnm_conv_wgrad_workspace_bytes(int64_t npos, int Ci, int Co) { return conv_wgrad_workspace(npos, Ci, Co); }
@@ -445,14 +447,29 @@ int fnm_fourier_layer_bwd(const fnm_plan* p, const float* g_z, const float* xin,
 // ------------------------------------------------------------------------------------------------
 // F2V
 // ------------------------------------------------------------------------------------------------
+// The mode contractions of both ends run on the tcgen05 mixing kernels when the weights are held mode-major
+// (FNM_W_MODE_MAJOR, what the drop-in modules store): a vector is the same "spectrum" in every mode, and a functional is
+// the cc-weighted real part of a mixed spectrum summed over modes -- so
+//   F2V: out = reduce_cc( mix_fwd(x^, W) ),   dW = mix_bwd_w(x^, spread_cc(g)),   g^x = mix_bwd_x(spread_cc(g), W)
+//   V2F: o^  = mix_fwd(spread(v), W),         dW = mix_bwd_w(spread(v), g^),      dv  = reduce( mix_bwd_x(g^, W) )
+// Reference-ordered weights (or shapes the mixing kernels do not serve) keep the fp32 SIMT contractions.
+static bool ends_on_mix(const fnm_plan* p) {
+    return p->w_layout == FNM_W_MODE_MAJOR && tc_mix_supported(p->B, p->Ci, p->Co) && p->Co % 2 == 0 &&
+           ((int64_t)p->B * p->Ci) % 4 == 0 && ((int64_t)p->B * p->Co) % 4 == 0;
+}
+static size_t ends_spectrum_floats(const fnm_plan* p) {
+    const size_t cmax = p->Ci > p->Co ? p->Ci : p->Co;
+    return align_up((size_t)p->R * p->NY * 2 * p->B * cmax * sizeof(float), 256) / sizeof(float);
+}
+
 size_t fnm_lfunc_workspace_bytes(const fnm_plan* p) {
     if (!p) return 0;
     const size_t LY = 2 * (size_t)p->NY;
     const size_t T = (size_t)p->B * p->P1 * LY * p->Ci;
     const size_t Gxh = (size_t)p->R * p->NY * 2 * p->B * p->Ci;
     const size_t cmax = p->Ci > p->Co ? p->Ci : p->Co;
-    return (T + Gxh) * sizeof(float) + simt_mode_split_workspace(p->R * p->NY, p->B, (int)cmax) + 4 * 256 +
-           padded_table_bytes(p->P2, (int)LY);
+    return (T + Gxh + 2 * ends_spectrum_floats(p)) * sizeof(float) + simt_mode_split_workspace(p->R * p->NY, p->B, (int)cmax) +
+           6 * 256 + padded_table_bytes(p->P2, (int)LY);
 }
 
 int fnm_lfunc_fwd(const fnm_plan* p, const float* xin, int act_in, const float* w, const float* cc, float* out,
@@ -465,9 +482,15 @@ int fnm_lfunc_fwd(const fnm_plan* p, const float* xin, int act_in, const float* 
     const int LY = 2 * p->NY;
     float* T = cv.take((size_t)p->B * p->P1 * LY * p->Ci);
     float* partial = cv.take(simt_mode_split_workspace(p->R * p->NY, p->B, p->Co) / sizeof(float));
+    float* Oh = cv.take(ends_spectrum_floats(p));
+    const int mm = p->w_layout == FNM_W_MODE_MAJOR, nmodes = p->R * p->NY;
     FNM_TRY(fnm_ydft(xin, p->ay, T, (int64_t)p->B * p->P1, p->P2, LY, p->Ci, act_in, p->mode, stream));
     FNM_TRY(fnm_xdft(T, p->ex, xh_save, p->B, p->P1, p->R, p->NY, p->Ci, p->mode, stream));
-    return simt_lfunc_contract(xh_save, w, cc, out, partial, p->B, p->R, p->NY, p->Ci, p->Co, st);
+    if (ends_on_mix(p)) {
+        FNM_TRY(tc_mix_apply(w, nullptr, 0, xh_save, Oh, nmodes, p->B, p->Ci, p->Co, 0, 0, p->mode, "lfunc_contract", st));
+        return mode_reduce(Oh, cc, out, nmodes, p->B * p->Co, "lfunc_reduce", st);
+    }
+    return simt_lfunc_contract(xh_save, w, cc, out, partial, p->B, p->R, p->NY, p->Ci, p->Co, st, mm);
 }
 
 int fnm_lfunc_bwd(const fnm_plan* p, const float* g_out, const float* xin, int act_in, const float* zin_pre,
@@ -482,12 +505,21 @@ int fnm_lfunc_bwd(const fnm_plan* p, const float* g_out, const float* xin, int a
     float* Zg = cv.take((size_t)p->B * p->P1 * LY * p->Ci);
     float* Gxh = cv.take((size_t)p->R * p->NY * 2 * p->B * p->Ci);
     float* tabpad = LY % 4 ? cv.take(padded_table_bytes(p->P2, LY) / sizeof(float)) : nullptr;
-    if (dw) FNM_TRY(simt_lfunc_bwd_w(g_out, xh_save, cc, dw, p->B, p->R, p->NY, p->Ci, p->Co, st));
+    float* Gh = cv.take(ends_spectrum_floats(p));
+    const int mm = p->w_layout == FNM_W_MODE_MAJOR, nmodes = p->R * p->NY;
+    const bool on_mix = ends_on_mix(p);
+    if (on_mix) FNM_TRY(mode_spread(g_out, cc, Gh, nmodes, p->B * p->Co, "lfunc_spread", st));
+    if (dw) {
+        if (on_mix) FNM_TRY(tc_mix_wgrad(xh_save, Gh, dw, nullptr, 0, nmodes, p->B, p->Ci, p->Co, p->mode, st, "lfunc_bwd_w"));
+        else FNM_TRY(simt_lfunc_bwd_w(g_out, xh_save, cc, dw, p->B, p->R, p->NY, p->Ci, p->Co, st, mm));
+    }
     if (g_in) {
-        FNM_TRY(simt_lfunc_bwd_x(g_out, w, cc, Gxh, p->B, p->R, p->NY, p->Ci, p->Co, st));
+        if (on_mix) FNM_TRY(tc_mix_apply(w, nullptr, 0, Gh, Gxh, nmodes, p->B, p->Co, p->Ci, 1, 1, p->mode, "lfunc_bwd_x", st));
+        else FNM_TRY(simt_lfunc_bwd_x(g_out, w, cc, Gxh, p->B, p->R, p->NY, p->Ci, p->Co, st, mm));
         FNM_TRY(fnm_xsyn(Gxh, p->fxb, Zg, p->B, p->P1, p->R, p->NY, p->Ci, p->mode, stream));
         const float* mul = zin_pre ? zin_pre : (act_in ? xin : nullptr);
-        FNM_TRY(ysyn_only(Zg, p->ayT, mul, g_in, (int64_t)p->B * p->P1, p->P2, LY, p->Ci, p->mode, tabpad, stream));
+        const int pre_grad = (zin_pre && (p->flags & FNM_PLAN_PRE_IS_GELU_GRAD)) ? FNM_PW_MUL_IS_GRAD : 0;
+        FNM_TRY(ysyn_only(Zg, p->ayT, mul, g_in, (int64_t)p->B * p->P1, p->P2, LY, p->Ci, p->mode, tabpad, stream, pre_grad));
     }
     return FNM_OK;
 }
@@ -500,8 +532,8 @@ size_t fnm_ldec_workspace_bytes(const fnm_plan* p) {
     const size_t LY = 2 * (size_t)p->NY;
     const size_t Z = (size_t)p->B * p->S1 * LY * p->Co;
     const size_t Oh = (size_t)p->R * p->NY * 2 * p->B * p->Co;
-    return (Z + Oh) * sizeof(float) + simt_mode_split_workspace(p->R * p->NY, p->B, p->Ci) + 4 * 256 +
-           padded_table_bytes(p->S2, (int)LY);
+    return (Z + Oh + 2 * ends_spectrum_floats(p)) * sizeof(float) + simt_mode_split_workspace(p->R * p->NY, p->B, p->Ci) +
+           6 * 256 + padded_table_bytes(p->S2, (int)LY);
 }
 
 int fnm_ldec_fwd(const fnm_plan* p, const float* v, const float* w, float* y_out, void* workspace,
@@ -515,7 +547,14 @@ int fnm_ldec_fwd(const fnm_plan* p, const float* v, const float* w, float* y_out
     float* Z = cv.take((size_t)p->B * p->S1 * LY * p->Co);
     float* Oh = cv.take((size_t)p->R * p->NY * 2 * p->B * p->Co);
     float* tabpad = LY % 4 ? cv.take(padded_table_bytes(p->S2, LY) / sizeof(float)) : nullptr;
-    FNM_TRY(simt_ldec_mix(v, w, Oh, p->B, p->R, p->NY, p->Ci, p->Co, st));
+    float* Xb = cv.take(ends_spectrum_floats(p));
+    const int mm = p->w_layout == FNM_W_MODE_MAJOR, nmodes = p->R * p->NY;
+    if (ends_on_mix(p)) {
+        FNM_TRY(mode_spread(v, nullptr, Xb, nmodes, p->B * p->Ci, "ldec_spread", st));
+        FNM_TRY(tc_mix_apply(w, nullptr, 0, Xb, Oh, nmodes, p->B, p->Ci, p->Co, 0, 0, p->mode, "ldec_mix", st));
+    } else {
+        FNM_TRY(simt_ldec_mix(v, w, Oh, p->B, p->R, p->NY, p->Ci, p->Co, st, mm));
+    }
     FNM_TRY(fnm_xsyn(Oh, p->fx, Z, p->B, p->S1, p->R, p->NY, p->Co, p->mode, stream));
     return ysyn_only(Z, p->by, nullptr, y_out, (int64_t)p->B * p->S1, p->S2, LY, p->Co, p->mode, tabpad, stream);
 }
@@ -531,10 +570,28 @@ int fnm_ldec_bwd(const fnm_plan* p, const float* g_y, const float* v, const floa
     float* Tg = cv.take((size_t)p->B * p->S1 * LY * p->Co);
     float* Gh = cv.take((size_t)p->R * p->NY * 2 * p->B * p->Co);
     float* partial = cv.take(simt_mode_split_workspace(p->R * p->NY, p->B, p->Ci) / sizeof(float));
+    float* Xb = cv.take(ends_spectrum_floats(p));
+    float* Gxh = cv.take(ends_spectrum_floats(p));
+    const int mm = p->w_layout == FNM_W_MODE_MAJOR, nmodes = p->R * p->NY;
+    const bool on_mix = ends_on_mix(p);
     FNM_TRY(fnm_ydft(g_y, p->byT, Tg, (int64_t)p->B * p->S1, p->S2, LY, p->Co, 0, p->mode, stream));
     FNM_TRY(fnm_xdft(Tg, p->exb, Gh, p->B, p->S1, p->R, p->NY, p->Co, p->mode, stream));
-    if (dw) FNM_TRY(simt_ldec_bwd_w(v, Gh, dw, p->B, p->R, p->NY, p->Ci, p->Co, st));
-    if (g_v) FNM_TRY(simt_ldec_bwd_v(Gh, w, g_v, partial, p->B, p->R, p->NY, p->Ci, p->Co, st));
+    if (dw) {
+        if (on_mix) {
+            FNM_TRY(mode_spread(v, nullptr, Xb, nmodes, p->B * p->Ci, "ldec_spread", st));
+            FNM_TRY(tc_mix_wgrad(Xb, Gh, dw, nullptr, 0, nmodes, p->B, p->Ci, p->Co, p->mode, st, "ldec_bwd_w"));
+        } else {
+            FNM_TRY(simt_ldec_bwd_w(v, Gh, dw, p->B, p->R, p->NY, p->Ci, p->Co, st, mm));
+        }
+    }
+    if (g_v) {
+        if (on_mix) {
+            FNM_TRY(tc_mix_apply(w, nullptr, 0, Gh, Gxh, nmodes, p->B, p->Co, p->Ci, 1, 1, p->mode, "ldec_bwd_v", st));
+            FNM_TRY(mode_reduce(Gxh, nullptr, g_v, nmodes, p->B * p->Ci, "ldec_reduce", st));
+        } else {
+            FNM_TRY(simt_ldec_bwd_v(Gh, w, g_v, partial, p->B, p->R, p->NY, p->Ci, p->Co, st, mm));
+        }
+    }
     return FNM_OK;
 }
 

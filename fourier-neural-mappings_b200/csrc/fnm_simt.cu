@@ -402,7 +402,7 @@ struct LfuncBwdXP : FullK {
 // dW[i,o,mode].ro = cc * sum_b g[b,o] * (ro ? -xi : xr)[b,i]           batch = mode; M = 2Ci, K = B, N = Co
 struct LfuncBwdWP : FullK {
     const float* g; const float* Xh; const float* cc; float2* dw;
-    int M, N, Ci, NYR;                   // NYR = R*NY (modes per (i,o))
+    int M, N, Ci, NYR, mm;               // NYR = R*NY (modes per (i,o)); mm: dw is held mode-major
     static constexpr bool A_MFAST = true, B_NFAST = true;
     __device__ __forceinline__ float a(int mode, int m, int b) const {
         const int ro = m / Ci, i = m - ro * Ci;
@@ -412,7 +412,7 @@ struct LfuncBwdWP : FullK {
     __device__ __forceinline__ float b(int, int b, int o) const { return __ldg(g + (size_t)b * N + o); }
     __device__ __forceinline__ void store(int mode, int m, int o, float v) const {
         const int ro = m / Ci, i = m - ro * Ci;
-        float* dst = reinterpret_cast<float*>(dw + (((size_t)i * N + o) * NYR + mode));
+        float* dst = reinterpret_cast<float*>(dw + (mm ? ((size_t)mode * Ci + i) * N + o : ((size_t)i * N + o) * NYR + mode));
         dst[ro] = __ldg(cc + mode) * v;
     }
 };
@@ -437,7 +437,7 @@ struct LdecFwdP : FullK {
 // dW[i,o,mode].ro = sum_b v[b,i] gh{ro}[b,o]                            batch = mode; M = Ci, K = B, N = 2Co
 struct LdecBwdWP : FullK {
     const float* v; const float* Gh; float2* dw;
-    int M, N, Co, NYR;
+    int M, N, Co, NYR, mm;
     static constexpr bool A_MFAST = true, B_NFAST = true;
     __device__ __forceinline__ float a(int, int i, int b) const { return __ldg(v + (size_t)b * M + i); }
     __device__ __forceinline__ float b(int mode, int b, int n) const {
@@ -446,7 +446,7 @@ struct LdecBwdWP : FullK {
     }
     __device__ __forceinline__ void store(int mode, int i, int n, float val) const {
         const int ro = n / Co, o = n - ro * Co;
-        float* dst = reinterpret_cast<float*>(dw + (((size_t)i * Co + o) * NYR + mode));
+        float* dst = reinterpret_cast<float*>(dw + (mm ? ((size_t)mode * M + i) * Co + o : ((size_t)i * Co + o) * NYR + mode));
         dst[ro] = val;
     }
 };
@@ -579,11 +579,11 @@ size_t simt_mode_split_workspace(int nmodes, int B, int C) {
 }
 
 int simt_lfunc_contract(const float* Xh, const float* w, const float* cc, float* out, float* partial, int B, int R,
-                        int NY, int Ci, int Co, cudaStream_t st) {
+                        int NY, int Ci, int Co, cudaStream_t st, int mm) {
     int per, nsplit;
     mode_split(R * NY, per, nsplit);
     LfuncFwdP p;
-    p.Xh = Xh; p.cc = cc; p.partial = partial; p.w = make_w(w, nullptr, R, NY, Co);
+    p.Xh = Xh; p.cc = cc; p.partial = partial; p.w = make_w(w, nullptr, R, NY, Co, Ci, mm);
     p.M = B; p.N = Co; p.Ci = Ci; p.nmodes = R * NY; p.per = per;
     FNM_TRY(launch_auto(p, nsplit, st, "lfunc_contract"));
     {
@@ -594,38 +594,40 @@ int simt_lfunc_contract(const float* Xh, const float* w, const float* cc, float*
 }
 
 int simt_lfunc_bwd_x(const float* g, const float* w, const float* cc, float* Gxh, int B, int R, int NY, int Ci, int Co,
-                     cudaStream_t st) {
+                     cudaStream_t st, int mm) {
     LfuncBwdXP p;
-    p.K = Co; p.g = g; p.cc = cc; p.Gxh = Gxh; p.w = make_w(w, nullptr, R, NY, Co); p.M = B; p.N = 2 * Ci; p.Ci = Ci;
+    p.K = Co; p.g = g; p.cc = cc; p.Gxh = Gxh; p.w = make_w(w, nullptr, R, NY, Co, Ci, mm); p.M = B; p.N = 2 * Ci; p.Ci = Ci;
     return launch_auto(p, (int64_t)R * NY, st, "lfunc_bwd_x");
 }
 
 int simt_lfunc_bwd_w(const float* g, const float* Xh, const float* cc, float* dw, int B, int R, int NY, int Ci, int Co,
-                     cudaStream_t st) {
+                     cudaStream_t st, int mm) {
     LfuncBwdWP p;
+    p.mm = mm;
     p.K = B; p.g = g; p.Xh = Xh; p.cc = cc; p.dw = reinterpret_cast<float2*>(dw);
     p.M = 2 * Ci; p.N = Co; p.Ci = Ci; p.NYR = R * NY;
     return launch_auto(p, (int64_t)R * NY, st, "lfunc_bwd_w");
 }
 
-int simt_ldec_mix(const float* v, const float* w, float* Oh, int B, int R, int NY, int Ci, int Co, cudaStream_t st) {
+int simt_ldec_mix(const float* v, const float* w, float* Oh, int B, int R, int NY, int Ci, int Co, cudaStream_t st, int mm) {
     LdecFwdP p;
-    p.K = Ci; p.v = v; p.Oh = Oh; p.w = make_w(w, nullptr, R, NY, Co); p.M = B; p.N = 2 * Co; p.Co = Co;
+    p.K = Ci; p.v = v; p.Oh = Oh; p.w = make_w(w, nullptr, R, NY, Co, Ci, mm); p.M = B; p.N = 2 * Co; p.Co = Co;
     return launch_auto(p, (int64_t)R * NY, st, "ldec_mix");
 }
 
-int simt_ldec_bwd_w(const float* v, const float* Gh, float* dw, int B, int R, int NY, int Ci, int Co, cudaStream_t st) {
+int simt_ldec_bwd_w(const float* v, const float* Gh, float* dw, int B, int R, int NY, int Ci, int Co, cudaStream_t st, int mm) {
     LdecBwdWP p;
+    p.mm = mm;
     p.K = B; p.v = v; p.Gh = Gh; p.dw = reinterpret_cast<float2*>(dw); p.M = Ci; p.N = 2 * Co; p.Co = Co; p.NYR = R * NY;
     return launch_auto(p, (int64_t)R * NY, st, "ldec_bwd_w");
 }
 
 int simt_ldec_bwd_v(const float* Gh, const float* w, float* dv, float* partial, int B, int R, int NY, int Ci, int Co,
-                    cudaStream_t st) {
+                    cudaStream_t st, int mm) {
     int per, nsplit;
     mode_split(R * NY, per, nsplit);
     LdecBwdVP p;
-    p.Gh = Gh; p.partial = partial; p.w = make_w(w, nullptr, R, NY, Co);
+    p.Gh = Gh; p.partial = partial; p.w = make_w(w, nullptr, R, NY, Co, Ci, mm);
     p.M = B; p.N = Ci; p.Co = Co; p.nmodes = R * NY; p.per = per;
     FNM_TRY(launch_auto(p, nsplit, st, "ldec_bwd_v"));
     {
@@ -633,6 +635,63 @@ int simt_ldec_bwd_v(const float* Gh, const float* w, float* dv, float* partial, 
         sum_partials<<<(B * Ci + 255) / 256, 256, 0, st>>>(partial, nsplit, B * Ci, dv);
     }
     return check_launch("ldec_reduce");
+}
+
+// ---- F2V / V2F ends on the mixing kernels: a real (B, C) matrix becomes a planar spectrum that is the same in every mode
+// (times cc[mode]), and the real part of a spectrum is summed over modes (times cc[mode]).
+//   spread: dst[mode][0][j] = cc[mode] * src[j], dst[mode][1][j] = 0          (j < n = B * C)
+__global__ void mode_spread_kernel(const float* __restrict__ src, const float* __restrict__ cc, float* __restrict__ dst,
+                                   int nmodes, int n) {
+    const int j4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (j4 >= n) return;
+    const float4 v = *reinterpret_cast<const float4*>(src + j4);
+    for (int m = blockIdx.y; m < nmodes; m += gridDim.y) {
+        const float c = cc ? __ldg(cc + m) : 1.f;
+        float* d = dst + (size_t)m * 2 * n + j4;
+        *reinterpret_cast<float4*>(d) = make_float4(c * v.x, c * v.y, c * v.z, c * v.w);
+        *reinterpret_cast<float4*>(d + n) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+}
+
+//   reduce: out[j] = sum_mode cc[mode] * src[mode][0][j]; 32 outputs x 8 mode groups per CTA, fixed summation order
+__global__ void __launch_bounds__(256) mode_reduce_kernel(const float* __restrict__ src, const float* __restrict__ cc,
+                                                          float* __restrict__ out, int nmodes, int n) {
+    __shared__ float part[8][33];
+    const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
+    const int j = blockIdx.x * 32 + lane;
+    float acc = 0.f;
+    if (j < n)
+        for (int m = grp; m < nmodes; m += 8) acc = fmaf(cc ? __ldg(cc + m) : 1.f, __ldg(src + (size_t)m * 2 * n + j), acc);
+    part[grp][lane] = acc;
+    __syncthreads();
+    if (grp == 0 && j < n) {
+        float s = 0.f;
+#pragma unroll
+        for (int g = 0; g < 8; ++g) s += part[g][lane];
+        out[j] = s;
+    }
+}
+
+int mode_spread(const float* src, const float* cc, float* dst, int nmodes, int n, const char* what, cudaStream_t st) {
+    if (n % 4 != 0) return fail(FNM_ENOTSUP, "%s: extent %d is no multiple of 4", what, n);
+    if (nmodes <= 0 || n <= 0) return FNM_OK;
+    const int bx = (n / 4 + 127) / 128;
+    int by = (4 * 148 + bx - 1) / bx;
+    if (by > nmodes) by = nmodes;
+    {
+        LaunchScope ls(what, st);
+        mode_spread_kernel<<<dim3(bx, by), 128, 0, st>>>(src, cc, dst, nmodes, n);
+    }
+    return check_launch(what);
+}
+
+int mode_reduce(const float* src, const float* cc, float* out, int nmodes, int n, const char* what, cudaStream_t st) {
+    if (n <= 0) return FNM_OK;
+    {
+        LaunchScope ls(what, st);
+        mode_reduce_kernel<<<(n + 31) / 32, 256, 0, st>>>(src, cc, out, nmodes, n);
+    }
+    return check_launch(what);
 }
 
 }  // namespace fnm

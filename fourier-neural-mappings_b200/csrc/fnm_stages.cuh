@@ -21,16 +21,21 @@ size_t simt_conv_wgrad_workspace(int64_t npos, int Ci, int Co);
 int simt_conv_wgrad(const float* g, const float* x, int act, float* dwc, float* dbc, int64_t npos, int Ci, int Co,
                     float* partial, cudaStream_t st);
 size_t simt_mode_split_workspace(int nmodes, int B, int C);
+// mm: the (Ci, Co, R, NY) weight / gradient tensor is held mode-major, memory order (R, NY, Ci, Co)
 int simt_lfunc_contract(const float* Xh, const float* w, const float* cc, float* out, float* partial, int B, int R,
-                        int NY, int Ci, int Co, cudaStream_t st);
+                        int NY, int Ci, int Co, cudaStream_t st, int mm = 0);
 int simt_lfunc_bwd_x(const float* g, const float* w, const float* cc, float* Gxh, int B, int R, int NY, int Ci, int Co,
-                     cudaStream_t st);
+                     cudaStream_t st, int mm = 0);
 int simt_lfunc_bwd_w(const float* g, const float* Xh, const float* cc, float* dw, int B, int R, int NY, int Ci, int Co,
-                     cudaStream_t st);
-int simt_ldec_mix(const float* v, const float* w, float* Oh, int B, int R, int NY, int Ci, int Co, cudaStream_t st);
-int simt_ldec_bwd_w(const float* v, const float* Gh, float* dw, int B, int R, int NY, int Ci, int Co, cudaStream_t st);
+                     cudaStream_t st, int mm = 0);
+int simt_ldec_mix(const float* v, const float* w, float* Oh, int B, int R, int NY, int Ci, int Co, cudaStream_t st, int mm = 0);
+int simt_ldec_bwd_w(const float* v, const float* Gh, float* dw, int B, int R, int NY, int Ci, int Co, cudaStream_t st,
+                    int mm = 0);
 int simt_ldec_bwd_v(const float* Gh, const float* w, float* dv, float* partial, int B, int R, int NY, int Ci, int Co,
-                    cudaStream_t st);
+                    cudaStream_t st, int mm = 0);
+// real (B, C) matrix <-> planar per-mode spectrum (F2V / V2F ends on the mixing kernels)
+int mode_spread(const float* src, const float* cc, float* dst, int nmodes, int n, const char* what, cudaStream_t st);
+int mode_reduce(const float* src, const float* cc, float* out, int nmodes, int n, const char* what, cudaStream_t st);
 
 // ---- optimiser / elementwise (fnm_adam.cu)
 int adam_launch(int n, float* const* p, const float* const* g, float* const* m, float* const* v, float* const* vmax,
@@ -61,7 +66,7 @@ int tc_mix_unpack(const float* dW1, float* dw0, float* dw1, int rpw, int R, int 
 int tc_mix_apply(const float* Wm, const float* Wm1, int m_split, const float* In, float* Out, int nmodes, int B, int Kt,
                  int Lt, int conj, int w_is_w1, int mode, const char* what, cudaStream_t st);
 int tc_mix_wgrad(const float* Xh, const float* Gh, float* dW1, float* dW1b, int m_split, int nmodes, int B, int Ci, int Co,
-                 int mode, cudaStream_t st);
+                 int mode, cudaStream_t st, const char* what = "mix_bwd_w");
 bool tc_conv_wgrad_supported(int64_t npos, int Ci, int Co);
 size_t tc_conv_wgrad_workspace(int64_t npos, int Ci, int Co);
 int tc_conv_wgrad(const float* g, const float* x, int act, float* dwc, float* dbc, int64_t npos, int Ci, int Co,
@@ -71,6 +76,7 @@ bool tc_pw2_supported(int64_t rows, int S2, int LY, int K, int N, int act, const
 int tc_pw2(const float* x, const float* wc, int wc_is_kn, const float* bias, const float* Z, const float* by,
            const float* mul, float* out, float* out_act, int64_t rows, int S2, int LY, int K, int N, int mode,
            cudaStream_t st, int by_ld = 0, int flags = 0);
+int tc_set_sm_limit(int n);                // fnm_set_sm_limit
 bool tc_pointwise_ysyn_supported(int64_t rows, int S2, int LY, int K, int N);
 int tc_pointwise_ysyn(const float* x, int act, const float* wc, int wc_is_kn, const float* bias, const float* Z,
                       const float* by, const float* mul, float* out, float* out_act, int64_t rows, int S2, int LY,

@@ -23,6 +23,8 @@
 // Pipelines: smem stage full/empty (producers <-> MMA), Z-row full/empty, TMEM accumulator full/empty.
 #include "fnm_tc_ptx.cuh"
 
+#include <atomic>
+
 #include <cstdlib>
 
 namespace fnm {
@@ -407,7 +409,8 @@ __global__ void __launch_bounds__(kThreads, 1) pointwise_ysyn_tc(const PwArgs a)
 }
 
 static int g_sm_count = 0;
-int sm_count() {
+static std::atomic<int> g_sm_limit{0};
+int sm_count_max() {
     if (g_sm_count == 0) {
         int dev = 0;
         cudaGetDevice(&dev);
@@ -416,6 +419,12 @@ int sm_count() {
     }
     return g_sm_count;
 }
+// CTAs of a persistent launch: every SM, or the caller's budget (fnm_set_sm_limit: SMs left to a concurrent collective)
+int sm_count() {
+    const int n = sm_count_max(), lim = g_sm_limit.load(std::memory_order_relaxed);
+    return (lim > 0 && lim < n) ? lim : n;
+}
+int sm_limit_exchange(int n) { return g_sm_limit.exchange(n < 0 ? 0 : n); }
 
 bool tc_enabled() {
     static int v = -1;
@@ -444,6 +453,8 @@ static int choose_nt(int S2, int CI, int K2slabs, int M, bool a1_smem) {
 }  // namespace tc
 
 int tc_available() { return 1; }
+
+int tc_set_sm_limit(int n) { return tc::sm_limit_exchange(n); }
 
 bool tc_pointwise_ysyn_supported(int64_t rows, int S2, int LY, int K, int N) {
     if (!tc::tc_enabled()) return false;

@@ -525,7 +525,7 @@ int tc_mix_apply(const float* Wm, const float* Wm1, int m_split, const float* In
 // (lanes = o) so that the epilogue's warp stores run along o, the contiguous axis of dW1 (with lanes = i every
 // 8-byte store of a warp hit a different 1 KB row); the conjugate then sits on the shared-memory operand.
 int tc_mix_wgrad(const float* Xh, const float* Gh, float* dW1, float* dW1b, int m_split, int nmodes, int B, int Ci, int Co,
-                 int mode, cudaStream_t st) {
+                 int mode, cudaStream_t st, const char* what) {
     MxArgs a{};
     a.a = Gh; a.b = Xh; a.out = dW1;
     a.a1 = Gh; a.a_split = nmodes; a.out1 = dW1b ? dW1b : dW1; a.o_split = dW1b ? m_split : nmodes;
@@ -534,7 +534,7 @@ int tc_mix_wgrad(const float* Xh, const float* Gh, float* dW1, float* dW1b, int 
     a.b_sm = (long long)2 * B * Ci; a.b_sn = 1; a.b_sk = Ci; a.b_im = (long long)B * Ci; a.b_kcontig = 0;
     a.o_sm = (long long)Ci * Co * 2; a.o_sn = (long long)Co * 2; a.o_sl = 2; a.o_im = 1; a.o_pair = 1;
     a.conj = 2; a.single_pass = mode == FNM_MODE_TF32;
-    return mx_launch(a, "mix_bwd_w", st);
+    return mx_launch(a, what, st);
 }
 
 }  // namespace fnm

@@ -283,7 +283,9 @@ bool tc_make_map(CUtensorMap* m, const float* ptr, int rank, const cuuint64_t* d
                  const cuuint32_t* box, bool swizzle128);
 bool tc_make_map_swz(CUtensorMap* m, const float* ptr, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
                      const cuuint32_t* box, CUtensorMapSwizzle swizzle);
-int sm_count();
+int sm_count();                           // CTAs of a persistent launch (honours fnm_set_sm_limit)
+int sm_count_max();                       // SMs of the device: workspace sizing
+int sm_limit_exchange(int n);
 bool tc_enabled();
 
 }  // namespace tc

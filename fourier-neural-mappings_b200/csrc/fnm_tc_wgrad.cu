@@ -455,9 +455,10 @@ conv_wgrad_tma(const __grid_constant__ CUtensorMap mapG, const __grid_constant__
     if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
-static int cw_grid(int64_t npos) {
+static int cw_grid(int64_t npos, bool for_workspace = false) {
     const int64_t chunks = (npos + 31) / 32;
-    return (int)(chunks < sm_count() ? chunks : sm_count());
+    const int sms = for_workspace ? sm_count_max() : sm_count();     // the workspace must hold any later SM budget
+    return (int)(chunks < sms ? chunks : sms);
 }
 
 }  // namespace tc
@@ -477,7 +478,7 @@ static int cw_fold(int64_t npos, int Ci, int Co) {
 
 size_t tc_conv_wgrad_workspace(int64_t npos, int Ci, int Co) {
     const int fold = cw_fold(npos, Ci, Co);
-    return align_up((size_t)cw_grid(npos / fold) * cw_part_floats(Ci * fold, Co * fold) * sizeof(float), 256);
+    return align_up((size_t)cw_grid(npos / fold, true) * cw_part_floats(Ci * fold, Co * fold) * sizeof(float), 256);
 }
 
 int tc_conv_wgrad(const float* g, const float* x, int act, float* dwc, float* dbc, int64_t npos, int Ci, int Co,

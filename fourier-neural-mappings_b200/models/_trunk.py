@@ -37,7 +37,7 @@ class Pending:
             raise RuntimeError("this activation carries GELU'(z) for the next fused layer only")
         if not self.act:
             return self.z
-        y = ops.gelu(self.z)
+        y = ops.gelu(self.z, self.x)                          # no forward kernel when the producer already wrote GELU(z)
         self.x = y.detach()
         return y
 
@@ -48,11 +48,13 @@ def _layer_tables(speconv, P1, P2, one_d, s=None):
     return speconv.tables(P1, P2, s)
 
 
-def run_layers(state, speconvs, ws, act_name, act_flags, one_d, last_s=None):
+def run_layers(state, speconvs, ws, act_name, act_flags, one_d, last_s=None, end_takes_grad=False):
     """Apply the Fourier layers to ``state`` (a Pending over a (B, P1, P2, C) tensor; P1 = 1 in 1-D).
     ``act_flags[i]`` says whether layer i is followed by the activation.  ``last_s`` (padded output
     resolution) switches the LAST layer to the resolution-changing form
-    ``w(projector(x, s)) + speconv(x, s)`` (func_to_func2d.py:95)."""
+    ``w(projector(x, s)) + speconv(x, s)`` (func_to_func2d.py:95).  ``end_takes_grad``: what follows the trunk is
+    ``functional_end`` on its fused path (``functional_end_is_fused``), which like a fused layer reads GELU(z) and
+    GELU'(z) only -- so the last layer may write the derivative in place of z too."""
     n = len(speconvs)
     fused_gelu = act_name == "gelu"
 
@@ -87,10 +89,12 @@ def run_layers(state, speconvs, ws, act_name, act_flags, one_d, last_s=None):
         else:
             xo = None
             # the activated copy is produced in this layer's epilogue when another fused layer consumes it
-            want = bool(act_flags[i]) and fused_gelu and not last
-            # ... and when that layer is a plain fused one (the grid does not change inside the trunk), z itself is never
+            # (or, after the last layer, the F2V end: both of its branches read GELU(z))
+            want = bool(act_flags[i]) and fused_gelu
+            # ... and when that consumer is a plain fused one (the grid does not change inside the trunk), z itself is never
             # needed again: the epilogue writes GELU'(z) in its place and the consumer's backward multiplies by it
-            zgrad = want and _CACHE_GELU_GRAD and torch.is_grad_enabled() and not (i + 1 == n - 1 and changes(P1, P2))
+            zgrad = want and _CACHE_GELU_GRAD and torch.is_grad_enabled() and \
+                (end_takes_grad if last else not (i + 1 == n - 1 and changes(P1, P2)))
             z, xo = ops.fourier_layer(z_in, sc.weights1, w1, w.weight, w.bias, _layer_tables(sc, P1, P2, one_d),
                                       act_in=state.act, xact=state.x, want_act_out=want, pre_is_grad=state.zgrad,
                                       grad_out=zgrad)
@@ -161,28 +165,41 @@ def project(x, cut, mlp, one_d):
     return mlp(crop(x, cut, one_d))
 
 
+def functional_end_is_fused(x, mlpfunc0, one_d, rows=None):
+    """Whether ``functional_end`` will take its fused local branch for a trunk state shaped like ``x`` (B, P1, P2, C)
+    (``rows``: the batch extent it will see, when the caller folds an axis into the batch)."""
+    fc1, fc2 = mlpfunc0.fc1, mlpfunc0.fc2
+    _, P1, P2, _ = x.shape
+    return (getattr(mlpfunc0, "act_name", None) == "gelu" and _fused_ends_ok(x, fc1.weight, fc2.weight)
+            and fc1.in_features % 4 == 0 and fc1.in_features <= 128 and fc1.out_features % 4 == 0
+            and fc1.out_features <= 128 and P2 >= 2 and (one_d or P1 >= 2)
+            and (x.shape[0] if rows is None else rows) <= 65535)            # wsum kernels put the batch on grid.y
+
+
 def functional_end(state, lfunc0, mlpfunc0, head, one_d):
     """F2V end (func_to_vec2d.py:97-110): nonlocal functionals || pointwise MLP + trapezoid rule."""
     z = state.z
     _, P1, P2, _ = z.shape
     tables = lfunc0.tables(P2) if one_d else lfunc0.tables(P1, P2)
-    xv = state.value()                                        # differentiable GELU(z) for the pointwise branch
-    nonlocal_feats = ops.linear_functional(z, lfunc0.weights, tables, act_in=state.act, xact=state.x)
+    nonlocal_feats = ops.linear_functional(z, lfunc0.weights, tables, act_in=state.act, xact=state.x,
+                                           pre_is_grad=state.zgrad)
     fc1, fc2 = mlpfunc0.fc1, mlpfunc0.fc2
-    if (getattr(mlpfunc0, "act_name", None) == "gelu" and _fused_ends_ok(xv, fc1.weight, fc2.weight)
-            and fc1.in_features % 4 == 0 and fc1.in_features <= 128 and fc1.out_features % 4 == 0
-            and fc1.out_features <= 128 and P2 >= 2 and (one_d or P1 >= 2)
-            and xv.shape[0] <= 65535):                                     # wsum kernels put the batch on grid.y
+    if functional_end_is_fused(z, mlpfunc0, one_d):
         # local branch without the (B, P1, P2, width_lfunc) tensors: fc1 on the fused pointwise kernel, then the
         # trapezoid-weighted GELU sum; fc2 is linear, so it commutes with the integration and acts on (B, H)
-        wy = _trapz_weights(P2, xv.device)
-        wx = _trapz_weights(P1, xv.device) if not one_d else torch.ones(1, device=xv.device)
-        S = ops.weighted_gelu_sum(ops.pointwise_conv(xv, fc1.weight, fc1.bias), wx, wy)
+        wy = _trapz_weights(P2, z.device)
+        wx = _trapz_weights(P1, z.device) if not one_d else torch.ones(1, device=z.device)
+        if state.act and state.x is not None:
+            # fc1 reads the cached GELU(z); its backward multiplies the input gradient by GELU'(z) in the epilogue
+            h1 = ops.pointwise_conv(state.x, fc1.weight, fc1.bias, zpre=z, zpre_is_grad=state.zgrad)
+        else:
+            h1 = ops.pointwise_conv(state.value(), fc1.weight, fc1.bias)
+        S = ops.weighted_gelu_sum(h1, wx, wy)
         h = F.linear(S, fc2.weight)
         if fc2.bias is not None:
             h = h + fc2.bias * (((P2 - 1.0) / P2) * (1.0 if one_d else (P1 - 1.0) / P1))   # integral of the constant
     else:
-        h = mlpfunc0(xv)                                      # (B, P1, P2, width_lfunc)
+        h = mlpfunc0(state.value())                           # (B, P1, P2, width_lfunc)
         h = torch.trapz(h, dx=1.0 / P2, dim=2)
         h = h.squeeze(1) if one_d else torch.trapz(h, dx=1.0 / P1, dim=1)
     return head(torch.cat((nonlocal_feats, h), dim=1))

@@ -8,7 +8,7 @@ import torch.nn as nn
 
 from .. import ops
 from ..shared import MLP, LinearDecoder1d, LinearFunctionals1d, SpectralConv2d, _get_act
-from ._trunk import Pending, _fused_ends_ok, functional_end, lift, project, run_layers
+from ._trunk import Pending, _fused_ends_ok, functional_end, functional_end_is_fused, lift, project, run_layers
 
 
 class FNO1d2(nn.Module):
@@ -81,11 +81,12 @@ class FNO2d1(nn.Module):
     def forward(self, x):
         """(batch, d_in, nx, ny) -> (batch, d_out, nx_out)"""
         x, (n1, n2) = lift(x, self.fc0, self.padding, self.get_grid, one_d=False)
-        state = run_layers(Pending(x), self.speconvs, self.ws, self.act_name, [True] * len(self.ws), False)
+        state = run_layers(Pending(x), self.speconvs, self.ws, self.act_name, [True] * len(self.ws), False,
+                           end_takes_grad=functional_end_is_fused(x, self.mlpfunc0, True, rows=x.shape[0] * x.shape[1]))
         B, P1, P2, Cw = state.z.shape
         # functionals of the LAST axis for every x: rows (b, x) are a batch of 1-D functions
         rows = Pending(state.z.view(B * P1, 1, P2, Cw), state.act,
-                       None if state.x is None else state.x.view(B * P1, 1, P2, Cw))
+                       None if state.x is None else state.x.view(B * P1, 1, P2, Cw), state.zgrad)
         feats = functional_end(rows, self.lfunc0, self.mlpfunc0, lambda f: f, one_d=True)    # (B*P1, 2*width1d)
         f = feats.view(B, 1, P1, 2 * self.width1d)
         if self.s_outputspace is not None and self.s_outputspace != P1:

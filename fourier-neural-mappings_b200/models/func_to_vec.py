@@ -2,7 +2,7 @@
 import torch.nn as nn
 
 from ..shared import MLP, LinearFunctionals1d, LinearFunctionals2d, SpectralConv1d, SpectralConv2d, _get_act
-from ._trunk import Pending, functional_end, lift, run_layers
+from ._trunk import Pending, functional_end, functional_end_is_fused, lift, run_layers
 
 
 class FNF2d(nn.Module):
@@ -28,7 +28,8 @@ class FNF2d(nn.Module):
     def forward(self, x):
         """(batch, d_in, nx, ny) -> (batch, d_out)"""
         x, _ = lift(x, self.fc0, self.padding, self.get_grid, one_d=False)
-        state = run_layers(Pending(x), self.speconvs, self.ws, self.act_name, [True] * len(self.ws), False)
+        state = run_layers(Pending(x), self.speconvs, self.ws, self.act_name, [True] * len(self.ws), False,
+                           end_takes_grad=functional_end_is_fused(x, self.mlpfunc0, False))
         return functional_end(state, self.lfunc0, self.mlpfunc0, self.mlp0, one_d=False)
 
 
@@ -55,5 +56,6 @@ class FNF1d(nn.Module):
     def forward(self, x):
         """(batch, d_in, nx) -> (batch, d_out)"""
         x, _ = lift(x, self.fc0, self.padding, self.get_grid, one_d=True)
-        state = run_layers(Pending(x), self.speconvs, self.ws, self.act_name, [True] * len(self.ws), True)
+        state = run_layers(Pending(x), self.speconvs, self.ws, self.act_name, [True] * len(self.ws), True,
+                           end_takes_grad=functional_end_is_fused(x, self.mlpfunc0, True))
         return functional_end(state, self.lfunc0, self.mlpfunc0, self.mlp0, one_d=True)

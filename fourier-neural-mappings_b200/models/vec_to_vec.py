@@ -4,7 +4,7 @@ import torch.nn as nn
 from .. import ops
 from ..shared import (MLP, LinearDecoder1d, LinearDecoder2d, LinearFunctionals1d, LinearFunctionals2d,
                       SpectralConv1d, SpectralConv2d, _get_act)
-from ._trunk import Pending, functional_end, run_layers
+from ._trunk import Pending, functional_end, functional_end_is_fused, run_layers
 
 
 class FNN2d(nn.Module):
@@ -38,7 +38,8 @@ class FNN2d(nn.Module):
         """(batch, d_in) -> (batch, d_out)"""
         v = self.mlp0(x)
         y = ops.linear_decoder(v, self.ldec0.weights, self.ldec0.tables(self.s_latentspace))
-        state = run_layers(Pending(y), self.speconvs, self.ws, self.act_name, [True] * len(self.ws), False)
+        state = run_layers(Pending(y), self.speconvs, self.ws, self.act_name, [True] * len(self.ws), False,
+                           end_takes_grad=functional_end_is_fused(y, self.mlpfunc0, False))
         return functional_end(state, self.lfunc0, self.mlpfunc0, self.mlp1, one_d=False)
 
     def set_latentspace_resolution(self, s):
@@ -76,7 +77,8 @@ class FNN1d(nn.Module):
         """(batch, d_in) -> (batch, d_out)"""
         v = self.mlp0(x)
         y = ops.linear_decoder(v, self.ldec0.weights, self.ldec0.tables(self.s_latentspace))
-        state = run_layers(Pending(y), self.speconvs, self.ws, self.act_name, [True] * len(self.ws), True)
+        state = run_layers(Pending(y), self.speconvs, self.ws, self.act_name, [True] * len(self.ws), True,
+                           end_takes_grad=functional_end_is_fused(y, self.mlpfunc0, True))
         return functional_end(state, self.lfunc0, self.mlpfunc0, self.mlp1, one_d=True)
 
     def set_latentspace_resolution(self, s):

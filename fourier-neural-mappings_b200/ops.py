@@ -103,6 +103,15 @@ def _spectral_weights(w0, w1):
     return _cplx(w0), (_cplx(w1) if w1 is not None else None), _lib.FNM_W_REFERENCE
 
 
+def _end_grad_buffer(sink, w, layout):
+    """-> (buffer the F2V / V2F kernels write dW into, whether that buffer IS the sink).  The buffer has the memory order
+    the kernels were told the weights have (``layout``); a sink in another order gets a copy afterwards."""
+    mm = layout == _lib.FNM_W_MODE_MAJOR
+    if sink is not None and (sink.stride() == w.stride() if mm else sink.is_contiguous()):
+        return sink, True
+    return torch.empty_like(w, memory_format=torch.preserve_format if mm else torch.contiguous_format), False
+
+
 _WS = {}
 
 
@@ -237,9 +246,12 @@ class LinearFunctionalFn(torch.autograd.Function):
 
     @staticmethod
     @_on_tensor_device
-    def forward(ctx, zin, xact, w, tables, act_in, sink=None):
+    def forward(ctx, zin, xact, w, tables, act_in, sink=None, pre_is_grad=False):
         _need_cuda(zin, xact, w)
         cached = bool(act_in) and xact is not None
+        if pre_is_grad and not cached:
+            raise ValueError("pre_is_grad: a cached GELU'(z) input needs the cached GELU(z) beside it")
+        ctx.pre_is_grad = bool(pre_is_grad)
         xk = _f32c(xact) if cached else _f32c(zin)
         kact = 0 if cached else int(bool(act_in))
         B, P1, P2, Ci = xk.shape
@@ -252,7 +264,8 @@ class LinearFunctionalFn(torch.autograd.Function):
         xh = torch.empty((tables.R, tables.NY, 2, B, Ci), dtype=torch.float32, device=xk.device)
         L = lib()
         ws = _workspace(xk.device, L.fnm_lfunc_workspace_bytes(C.byref(plan)))
-        check(L.fnm_lfunc_fwd(C.byref(plan), _ptr(xk), kact, _ptr(_cplx(w)), _ptr(cc), _ptr(out), _ptr(xh),
+        wr, _, plan.w_layout = _spectral_weights(w, None)
+        check(L.fnm_lfunc_fwd(C.byref(plan), _ptr(xk), kact, _ptr(wr), _ptr(cc), _ptr(out), _ptr(xh),
                               _ptr(ws), ws.numel(), _stream()), "fnm_lfunc_fwd")
         ctx.save_for_backward(xk, _f32c(zin) if cached else None, w, xh)
         ctx.tables, ctx.kact = tables, kact
@@ -270,13 +283,18 @@ class LinearFunctionalFn(torch.autograd.Function):
         plan = tables.c_plan(xk.device, B, Ci, Co, _MODE)
         cc = tables.device(xk.device)["cc"]
         g_in = torch.empty_like(xk) if ctx.needs_input_grad[0] else None
-        dw = (ctx.sink if ctx.sink is not None else torch.empty_like(w)) if ctx.needs_input_grad[2] else None
+        wr, _, plan.w_layout = _spectral_weights(w, None)
+        if ctx.pre_is_grad:
+            plan.flags = _lib.FNM_PLAN_PRE_IS_GELU_GRAD
+        dw, sunk = _end_grad_buffer(ctx.sink, w, plan.w_layout) if ctx.needs_input_grad[2] else (None, False)
         L = lib()
         ws = _workspace(xk.device, L.fnm_lfunc_workspace_bytes(C.byref(plan)))
-        check(L.fnm_lfunc_bwd(C.byref(plan), _ptr(g), _ptr(xk), ctx.kact, _ptr(zpre), _ptr(_cplx(w)), _ptr(cc), _ptr(xh),
+        check(L.fnm_lfunc_bwd(C.byref(plan), _ptr(g), _ptr(xk), ctx.kact, _ptr(zpre), _ptr(wr), _ptr(cc), _ptr(xh),
                               _ptr(g_in), _ptr(torch.view_as_real(dw)) if dw is not None else None,
                               _ptr(ws), ws.numel(), _stream()), "fnm_lfunc_bwd")
-        return g_in, None, None if ctx.sink is not None else dw, None, None, None
+        if ctx.sink is not None and dw is not None and not sunk:
+            ctx.sink.copy_(dw)
+        return g_in, None, None if ctx.sink is not None else dw, None, None, None, None
 
 
 class LinearDecoderFn(torch.autograd.Function):
@@ -295,7 +313,8 @@ class LinearDecoderFn(torch.autograd.Function):
         y = torch.empty((B, tables.S1, tables.S2, Co), dtype=torch.float32, device=v.device)
         L = lib()
         ws = _workspace(v.device, L.fnm_ldec_workspace_bytes(C.byref(plan)))
-        check(L.fnm_ldec_fwd(C.byref(plan), _ptr(v), _ptr(_cplx(w)), _ptr(y), _ptr(ws), ws.numel(), _stream()),
+        wr, _, plan.w_layout = _spectral_weights(w, None)
+        check(L.fnm_ldec_fwd(C.byref(plan), _ptr(v), _ptr(wr), _ptr(y), _ptr(ws), ws.numel(), _stream()),
               "fnm_ldec_fwd")
         ctx.save_for_backward(v, w)
         ctx.tables = tables
@@ -312,12 +331,15 @@ class LinearDecoderFn(torch.autograd.Function):
         Co = w.shape[1]
         plan = tables.c_plan(v.device, B, Ci, Co, _MODE)
         gv = torch.empty_like(v) if ctx.needs_input_grad[0] else None
-        dw = (ctx.sink if ctx.sink is not None else torch.empty_like(w)) if ctx.needs_input_grad[1] else None
+        wr, _, plan.w_layout = _spectral_weights(w, None)
+        dw, sunk = _end_grad_buffer(ctx.sink, w, plan.w_layout) if ctx.needs_input_grad[1] else (None, False)
         L = lib()
         ws = _workspace(v.device, L.fnm_ldec_workspace_bytes(C.byref(plan)))
-        check(L.fnm_ldec_bwd(C.byref(plan), _ptr(gy), _ptr(v), _ptr(_cplx(w)), _ptr(gv),
+        check(L.fnm_ldec_bwd(C.byref(plan), _ptr(gy), _ptr(v), _ptr(wr), _ptr(gv),
                              _ptr(torch.view_as_real(dw)) if dw is not None else None,
                              _ptr(ws), ws.numel(), _stream()), "fnm_ldec_bwd")
+        if ctx.sink is not None and dw is not None and not sunk:
+            ctx.sink.copy_(dw)
         return gv, None if ctx.sink is not None else dw, None, None
 
 
@@ -380,35 +402,40 @@ class LiftFn(torch.autograd.Function):
 
 class PointwiseConvFn(torch.autograd.Function):
     """h[..., o] = sum_i x[..., i] w[o, i] + b[o] on a channels-last (B, P1, P2, Ci) tensor: the fused
-    pointwise kernel without a spectral term (forward and input gradient) + conv_wgrad (dW, db)."""
+    pointwise kernel without a spectral term (forward and input gradient) + conv_wgrad (dW, db).
+
+    With ``zpre``: ``x`` is the cached GELU(zpre) a fused layer's epilogue wrote (it carries no gradient) and the
+    input gradient is returned for ``zpre``, multiplied by GELU'(zpre) in the same kernel's epilogue."""
 
     @staticmethod
     @_on_tensor_device
-    def forward(ctx, x, w, b):
-        _need_cuda(x, w, b)
+    def forward(ctx, x, w, b, zpre=None, zpre_is_grad=False):
+        _need_cuda(x, w, b, zpre)
+        ctx.zpre_is_grad = bool(zpre_is_grad) and zpre is not None
         x, w = _f32c(x), _f32c(w)
         B, P1, P2, Ci = x.shape
         Co = w.shape[0]
         out = torch.empty((B, P1, P2, Co), dtype=torch.float32, device=x.device)
         check(lib().fnm_pointwise_ysyn(_ptr(x), 0, _ptr(w), 0, _ptr(_f32c(b)) if b is not None else None, None, None, None,
                                        _ptr(out), None, B * P1, P2, 0, Ci, Co, _MODE, _stream()), "fnm_pointwise_ysyn")
-        ctx.save_for_backward(x, w)
+        ctx.save_for_backward(x, w, _f32c(zpre) if zpre is not None else None)
         ctx.has_bias = b is not None
         return out
 
     @staticmethod
     @_on_tensor_device
     def backward(ctx, g):
-        x, w = ctx.saved_tensors
+        x, w, zpre = ctx.saved_tensors
         g = _f32c(g)
         B, P1, P2, Ci = x.shape
         Co = w.shape[0]
         L = lib()
         dx = dw = db = None
-        if ctx.needs_input_grad[0]:
+        if ctx.needs_input_grad[3] if zpre is not None else ctx.needs_input_grad[0]:
             dx = torch.empty_like(x)
-            check(L.fnm_pointwise_ysyn(_ptr(g), 0, _ptr(w), 1, None, None, None, None, _ptr(dx), None, B * P1, P2, 0,
-                                       Co, Ci, _MODE, _stream()), "fnm_pointwise_ysyn")
+            check(L.fnm_pointwise_ysyn_ex(_ptr(g), 0, _ptr(w), 1, None, None, None, _ptr(zpre), _ptr(dx), None, B * P1, P2, 0,
+                                          Co, Ci, _MODE, _lib.FNM_PW_MUL_IS_GRAD if ctx.zpre_is_grad else 0, _stream()),
+                  "fnm_pointwise_ysyn_ex")
         if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
             npos = B * P1 * P2
             dw = torch.empty_like(w)
@@ -418,7 +445,30 @@ class PointwiseConvFn(torch.autograd.Function):
                                    _stream()), "fnm_conv_wgrad")
             if not ctx.has_bias:
                 db = None
-        return dx, dw, db
+        if zpre is not None:
+            return None, dw, db, dx, None
+        return dx, dw, db, None, None
+
+
+class CachedGeluFn(torch.autograd.Function):
+    """GELU(z) whose value already exists (``x``, written by the producing layer's epilogue): no forward kernel; the
+    backward is the stand-alone g * GELU'(z)."""
+
+    @staticmethod
+    @_on_tensor_device
+    def forward(ctx, z, x):
+        _need_cuda(z, x)
+        ctx.save_for_backward(_f32c(z))
+        return x.view_as(x)
+
+    @staticmethod
+    @_on_tensor_device
+    def backward(ctx, gy):
+        (z,) = ctx.saved_tensors
+        gy = _f32c(gy)
+        gz = torch.empty_like(z)
+        check(lib().fnm_gelu_bwd(_ptr(gy), _ptr(z), _ptr(gz), z.numel(), _stream()), "fnm_gelu_bwd")
+        return gz, None
 
 
 class ResampleFn(torch.autograd.Function):
@@ -542,8 +592,8 @@ def lift(x, w, b, P1, P2, ngrid):
     return LiftFn.apply(x, w, b, P1, P2, ngrid)
 
 
-def pointwise_conv(x, w, b):
-    return PointwiseConvFn.apply(x, w, b)
+def pointwise_conv(x, w, b, zpre=None, zpre_is_grad=False):
+    return PointwiseConvFn.apply(x, w, b, zpre, zpre_is_grad)
 
 
 def mlp_head(h1, w2, b2):
@@ -561,13 +611,17 @@ def fourier_layer(zin, w0, w1, wc, bc, tables, act_in=False, xact=None, want_act
                                 pre_is_grad, grad_out)
 
 
-def linear_functional(zin, w, tables, act_in=False, xact=None):
-    return LinearFunctionalFn.apply(zin, xact, w, tables, act_in, _grad_sink(w))
+def linear_functional(zin, w, tables, act_in=False, xact=None, pre_is_grad=False):
+    """``pre_is_grad``: ``zin`` holds GELU'(z) (ops.fourier_layer(grad_out=True)) and ``xact`` GELU(z)."""
+    return LinearFunctionalFn.apply(zin, xact, w, tables, act_in, _grad_sink(w), pre_is_grad)
 
 
 def linear_decoder(v, w, tables):
     return LinearDecoderFn.apply(v, w, tables, _grad_sink(w))
 
 
-def gelu(z):
+def gelu(z, cached=None):
+    """GELU(z); ``cached`` = the value when a fused layer's epilogue already wrote it."""
+    if cached is not None:
+        return CachedGeluFn.apply(z, cached)
     return GeluFn.apply(z)

@@ -130,13 +130,27 @@ def broadcast_parameters(module, src=0):
             dist.broadcast(torch.view_as_real(data) if data.is_complex() else data, src)
 
 
-def train_step(model, optimizer, grads, loss_fn, x, y, group=None):
+def train_step(model, optimizer, grads, loss_fn, x, y, group=None, sm_reserve=0):
     """zero_grad -> forward -> loss -> backward -> SUM all-reduce -> Adam (train_fno.py:187-197 +
-    the exchange).  Returns the LOCAL loss tensor (no host sync)."""
+    the exchange).  Returns the LOCAL loss tensor (no host sync).
+
+    ``sm_reserve`` (overlapped exchange only): SMs the persistent backward kernels leave free, so that the NCCL
+    kernels of the slots already in flight have somewhere to run (include/fnm_b200.h, fnm_set_sm_limit)."""
     grads.zero_()
     out = model(x)
     loss = loss_fn(out, y)
-    loss.backward()
+    reserve = int(sm_reserve) if (grads.overlap and dist.is_available() and dist.is_initialized()
+                                  and dist.get_world_size(group) > 1) else 0
+    if reserve > 0:
+        from ._lib import set_sm_limit
+        sms = torch.cuda.get_device_properties(x.device).multi_processor_count
+        prev = set_sm_limit(max(1, sms - reserve))
+        try:
+            loss.backward()
+        finally:
+            set_sm_limit(prev)
+    else:
+        loss.backward()
     # (Updating each parameter group as soon as ITS exchange has landed -- several Adam launches driven by
     # update_groups() -- was measured at 2 GPUs and is no faster than joining first: 23.5 vs 23.4 ms per step.)
     grads.all_reduce(group)
@@ -151,7 +165,7 @@ class GraphedTrainStep:
     ``fnm_b200.Adam(..., capturable=True)``.  Inputs are copied into static buffers before each replay; the
     returned loss tensor is overwritten by every replay."""
 
-    def __init__(self, model, optimizer, grads, loss_fn, x, y, group=None, warmup=3):
+    def __init__(self, model, optimizer, grads, loss_fn, x, y, group=None, warmup=3, sm_reserve=0):
         """``warmup`` eager steps run first on a side stream (allocator, workspaces, Adam state).  They are real
         optimizer updates, so parameters, moments and step counts are snapshotted before and restored after: building
         the graph leaves the model and the optimizer exactly as they were (moments that did not exist yet are zeroed,
@@ -173,7 +187,7 @@ class GraphedTrainStep:
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):                          # allocator / workspace / Adam-state warm-up
             for _ in range(warmup):
-                train_step(model, optimizer, grads, loss_fn, self.x, self.y, group)
+                train_step(model, optimizer, grads, loss_fn, self.x, self.y, group, sm_reserve)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         with torch.no_grad():                                  # undo the warm-up updates (in place: the graph records addresses)
@@ -193,7 +207,7 @@ class GraphedTrainStep:
         self.graph = torch.cuda.CUDAGraph()
         n0 = launch_count()
         with torch.cuda.graph(self.graph):
-            self.loss = train_step(model, optimizer, grads, loss_fn, self.x, self.y, group)
+            self.loss = train_step(model, optimizer, grads, loss_fn, self.x, self.y, group, sm_reserve)
         self.launches_per_step = launch_count() - n0
         self.optimizer = optimizer
         if hasattr(optimizer, "graph_captured"):

@@ -202,7 +202,7 @@ class LinearFunctionals1d(nn.Module):
         super().__init__()
         self.in_channels, self.out_channels, self.modes1 = in_channels, out_channels, modes1
         self.scale = 1.0 / (in_channels * out_channels)
-        self.weights = _complex_param(self.scale, in_channels, out_channels, modes1 + 1)
+        self.weights = _complex_param(self.scale, in_channels, out_channels, modes1 + 1, mode_major=True)
 
     def tables(self, P):
         return functional_tables(1, P, 0, self.modes1, one_d=True)
@@ -221,7 +221,7 @@ class LinearFunctionals2d(nn.Module):
         self.in_channels, self.out_channels = in_channels, out_channels
         self.modes1, self.modes2 = modes1, modes2
         self.scale = 1.0 / (in_channels * out_channels)
-        self.weights = _complex_param(self.scale, in_channels, out_channels, 2 * modes1, modes2 + 1)
+        self.weights = _complex_param(self.scale, in_channels, out_channels, 2 * modes1, modes2 + 1, mode_major=True)
 
     def tables(self, P1, P2):
         return functional_tables(P1, P2, self.modes1, self.modes2)
@@ -239,7 +239,7 @@ class LinearDecoder1d(nn.Module):
         super().__init__()
         self.in_channels, self.out_channels, self.modes1 = in_channels, out_channels, modes1
         self.scale = 1.0 / (in_channels * out_channels)
-        self.weights = _complex_param(self.scale, in_channels, out_channels, modes1 + 1)
+        self.weights = _complex_param(self.scale, in_channels, out_channels, modes1 + 1, mode_major=True)
 
     def tables(self, s):
         return decoder_tables(1, int(s), 0, self.modes1, one_d=True)
@@ -258,7 +258,7 @@ class LinearDecoder2d(nn.Module):
         self.in_channels, self.out_channels = in_channels, out_channels
         self.modes1, self.modes2 = modes1, modes2
         self.scale = 1.0 / (in_channels * out_channels)
-        self.weights = _complex_param(self.scale, in_channels, out_channels, 2 * modes1, modes2 + 1)
+        self.weights = _complex_param(self.scale, in_channels, out_channels, 2 * modes1, modes2 + 1, mode_major=True)
 
     def tables(self, s):
         return decoder_tables(int(s[0]), int(s[1]), self.modes1, self.modes2)

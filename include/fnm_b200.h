@@ -95,7 +95,7 @@ typedef struct fnm_plan {
  * FNM_PLAN_PRE_IS_GELU_GRAD and multiplies by it directly.  z itself is then never stored: nothing else needs it.   */
 enum {
     FNM_PLAN_ZOUT_IS_GELU_GRAD = 1,         /* forward:  z_out := GELU'(z) (requires x_act_out != NULL) */
-    FNM_PLAN_PRE_IS_GELU_GRAD = 2           /* backward: zin_pre holds GELU'(zin), not zin */
+    FNM_PLAN_PRE_IS_GELU_GRAD = 2           /* backward (fourier_layer_bwd, lfunc_bwd): zin_pre holds GELU'(zin), not zin */
 };
 /* flags of fnm_pointwise_ysyn_ex */
 enum {
@@ -107,6 +107,13 @@ const char* fnm_version(void);
 const char* fnm_last_error(void);
 /* 1 when the library was built with the tcgen05/TMA kernels (sm_100a) */
 int fnm_has_tcgen05(void);
+
+/* ---- SM budget of the persistent kernels.  The tcgen05 kernels launch one CTA per SM and keep it for the whole
+ *      pass, so a collective enqueued on another stream (the NCCL gradient all-reduce of data-parallel training,
+ *      started from inside backward) finds no SM to run on until they drain.  fnm_set_sm_limit(n) caps the grid of
+ *      every later persistent launch of this process at n CTAs (0 = all SMs); it returns the previous value.
+ *      Workspace queries always assume the full device.  Process-wide, takes effect at launch (or capture) time. */
+int fnm_set_sm_limit(int n);
 
 /* ---- instrumentation (used by bench.py; never on by default) --------------------------------------
  * fnm_launch_count(): kernels launched by this library in this process so far.

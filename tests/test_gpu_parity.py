@@ -716,7 +716,7 @@ def test_overlapping_corner_blocks_like_reference():
     assert torch.all(sc.weights1.grad[:, :, 3:, :] == 0)           # rows 8 - 5 = 3 .. 4 of weights1 are overwritten
 
 
-@pytest.mark.parametrize("family", ["fno2d", "fno1d", "fnd2d"])
+@pytest.mark.parametrize("family", ["fno2d", "fno1d", "fnd2d", "fnf2d", "fno2d1"])
 def test_cached_gelu_derivative_equals_the_recomputed_one(family):
     """The trunk's default (a fused layer writes GELU'(z) in place of z for the next fused layer,
     FNM_PLAN_ZOUT_IS_GELU_GRAD) against the same model with the cache switched off: same formula, evaluated in the
@@ -729,6 +729,12 @@ def test_cached_gelu_derivative_equals_the_recomputed_one(family):
     elif family == "fno1d":
         model = fnm_b200.FNO1d(8, 64, n_layers=3).to(DEV)
         x = torch.randn(3, 1, 128, device=DEV)
+    elif family == "fnf2d":                                   # the F2V end consumes GELU(z) | GELU'(z) of the last layer too
+        model = fnm_b200.FNF2d(6, 6, 32, d_in=1, d_out=2, n_layers=3).to(DEV)
+        x = torch.randn(3, 1, 40, 32, device=DEV)
+    elif family == "fno2d1":
+        model = fnm_b200.FNO2d1(4, 16, 4, 4, 16, n_layers=3).to(DEV)
+        x = torch.randn(2, 1, 24, 24, device=DEV)
     else:
         model = fnm_b200.FND2d(5, (24, 24), 6, 6, 32, n_layers=4).to(DEV)
         x = torch.randn(3, 5, device=DEV)
@@ -746,3 +752,43 @@ def test_cached_gelu_derivative_equals_the_recomputed_one(family):
     assert torch.equal(res[True][0], res[False][0])
     for k in res[True][1]:
         assert rel_l2(res[True][1][k], res[False][1][k]) < 2e-6, k
+
+
+@pytest.mark.parametrize("width", [4, 16, 64])
+@pytest.mark.parametrize("end", ["f2v", "v2f"])
+def test_ends_mode_major_weights_match_reference_ordered_weights(end, width):
+    """F2V / V2F weights live mode-major in the drop-in modules (tcgen05 mixing kernels for the mode contractions, SIMT
+    for narrow widths); the C ABI also takes them in the reference's memory order (fp32 SIMT contractions).  Same values,
+    same gradients -- and both against the float64 statement of SURVEY A.3 through the oracle."""
+    from fnm_b200 import ops
+    torch.manual_seed(11)
+    B, P1, P2, m1, m2 = 6, 20, 24, 4, 5
+    if end == "f2v":
+        mod = S.LinearFunctionals2d(width, width, m1, m2).to(DEV)
+        x = torch.randn(B, width, P1, P2, device=DEV, requires_grad=True)
+        run_mod = lambda: mod(x)
+        tables = mod.tables(P1, P2)
+        xcl = x.detach().permute(0, 2, 3, 1).contiguous().requires_grad_(True)
+        wref = mod.weights.detach().contiguous().clone().requires_grad_(True)
+        run_ref = lambda: ops.linear_functional(xcl, wref, tables)
+        ref = O.linear_functionals2d(x.detach().cpu(), mod.weights.detach().cpu().contiguous())
+    else:
+        mod = S.LinearDecoder2d(width, width, m1, m2).to(DEV)
+        x = torch.randn(B, width, device=DEV, requires_grad=True)
+        run_mod = lambda: mod(x, (P1, P2))
+        tables = mod.tables((P1, P2))
+        xcl = x.detach().clone().requires_grad_(True)
+        wref = mod.weights.detach().contiguous().clone().requires_grad_(True)
+        run_ref = lambda: ops.linear_decoder(xcl, wref, tables).permute(0, 3, 1, 2)
+        ref = O.linear_decoder2d(x.detach().cpu(), mod.weights.detach().cpu().contiguous(), (P1, P2))
+    assert not mod.weights.is_contiguous() and wref.is_contiguous()
+    out_m = run_mod()
+    gsel = torch.randn_like(out_m)
+    (out_m * gsel).sum().backward()
+    out_r = run_ref()
+    (out_r * gsel).sum().backward()
+    assert rel_l2(out_m, ref) < TOL_FP32 and rel_l2(out_r, ref) < TOL_FP32
+    assert rel_l2(out_m, out_r) < TOL_FP32
+    assert rel_l2(mod.weights.grad, wref.grad) < TOL_FP32
+    gx_r = xcl.grad.permute(0, 3, 1, 2) if end == "f2v" else xcl.grad
+    assert rel_l2(x.grad, gx_r) < TOL_FP32
