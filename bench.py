@@ -343,7 +343,7 @@ def run_ours(args, rank, world):
     y = y_host.to(dev)
 
     # SMs the persistent backward kernels leave to the NCCL kernels of the overlapped exchange (N > 1 only)
-    sm_reserve = int(os.environ.get("FNM_DP_SM_RESERVE", "16")) if world > 1 else 0
+    sm_reserve = int(os.environ.get("FNM_DP_SM_RESERVE", "0")) if world > 1 else 0
 
     def step(xd, yd):
         return fnm_b200.parallel.train_step(model, opt, grads, rel_l2_sum, xd, yd, sm_reserve=sm_reserve)

@@ -26,7 +26,8 @@ class FnmPlan(C.Structure):
                 ("R", C.c_int32), ("NY", C.c_int32), ("Ci", C.c_int32), ("Co", C.c_int32),
                 ("rows_per_w", C.c_int32), ("mode", C.c_int32), ("w_layout", C.c_int32),
                 ("ay", _vp), ("ayT", _vp), ("by", _vp), ("byT", _vp),
-                ("ex", _vp), ("fx", _vp), ("exb", _vp), ("fxb", _vp), ("w_shadow", _vp), ("flags", C.c_int32)]
+                ("ex", _vp), ("fx", _vp), ("exb", _vp), ("fxb", _vp), ("w_shadow", _vp), ("flags", C.c_int32),
+                ("by16", _vp), ("ayT16", _vp)]
 
 
 _PP = C.POINTER(FnmPlan)
@@ -66,7 +67,7 @@ PROTOTYPES = {
     "fnm_pointwise_ysyn": (_i32, [_vp, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32,
                                   _i32, _vp]),
     "fnm_pointwise_ysyn_ex": (_i32, [_vp, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32,
-                                     _i32, _i32, _vp]),
+                                     _i32, _i32, _vp, _vp]),
     "fnm_lift_fwd": (_i32, [_vp, _vp, _vp, _vp] + [_i32] * 8 + [_vp]),
     "fnm_lift_bwd_workspace_bytes": (_sz, [_i32, _i32]),
     "fnm_lift_bwd": (_i32, [_vp, _vp, _vp, _vp] + [_i32] * 8 + [_vp, _sz, _vp]),

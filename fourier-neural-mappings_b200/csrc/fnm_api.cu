@@ -247,7 +247,7 @@ int fnm_mix_bwd_w(const float* Xh, const float* Gh, float* dw0, float* dw1, int 
 
 int fnm_pointwise_ysyn_ex(const float* x, int act_in, const float* wc, int wc_is_kn, const float* bias, const float* Z,
                           const float* by, const float* mul, float* out, float* out_act, int64_t rows, int S2,
-                          int LY, int K, int N, int mode, int flags, fnm_stream_t stream) {
+                          int LY, int K, int N, int mode, int flags, const void* by16, fnm_stream_t stream) {
     FNM_REQUIRE(out && (LY == 0 || (Z && by)), "pointwise_ysyn: NULL pointer");
     FNM_REQUIRE(rows >= 0 && S2 > 0 && LY >= 0 && N > 0 && K >= 0, "pointwise_ysyn: bad extents");
     FNM_REQUIRE(LY > 0 || (x && wc && K > 0), "pointwise_ysyn: nothing to compute (no spectral and no pointwise term)");
@@ -255,7 +255,7 @@ int fnm_pointwise_ysyn_ex(const float* x, int act_in, const float* wc, int wc_is
     FNM_REQUIRE(!(flags & FNM_PW_OUT_IS_GRAD) || (out_act && !mul), "pointwise_ysyn: FNM_PW_OUT_IS_GRAD needs out_act and no multiplier");
     FNM_REQUIRE(!(flags & FNM_PW_MUL_IS_GRAD) || mul, "pointwise_ysyn: FNM_PW_MUL_IS_GRAD without a multiplier");
     if (tc_pw2_supported(rows, S2, LY, (x && wc) ? K : 0, N, (x && wc) ? act_in : 0, (x && wc) ? x : nullptr, Z, by))
-        return tc_pw2(x, wc, wc_is_kn, bias, Z, by, mul, out, out_act, rows, S2, LY, K, N, mode, as_stream(stream), 0, flags);
+        return tc_pw2(x, wc, wc_is_kn, bias, Z, by, mul, out, out_act, rows, S2, LY, K, N, mode, as_stream(stream), 0, flags, by16);
     if (flags == 0 && LY > 0 && tc_pointwise_ysyn_supported(rows, S2, LY, (x && wc) ? K : 0, N))
         return tc_pointwise_ysyn(x, act_in, wc, wc_is_kn, bias, Z, by, mul, out, out_act, rows, S2, LY, K, N,
                                  mode, as_stream(stream));
@@ -267,7 +267,7 @@ int fnm_pointwise_ysyn(const float* x, int act_in, const float* wc, int wc_is_kn
                        const float* by, const float* mul_gelu_grad_of, float* out, float* out_act, int64_t rows, int S2,
                        int LY, int K, int N, int mode, fnm_stream_t stream) {
     return fnm_pointwise_ysyn_ex(x, act_in, wc, wc_is_kn, bias, Z, by, mul_gelu_grad_of, out, out_act, rows, S2, LY, K, N, mode,
-                                 0, stream);
+                                 0, nullptr, stream);
 }
 
 // The F2V / V2F ends keep m2 + 1 columns, so their y-synthesis has LY = 2 (m2 + 1) table columns -- usually no multiple
@@ -295,7 +295,7 @@ static int ysyn_only(const float* Z, const float* by, const float* mul, float* o
         FNM_TRY(check_launch("pad_table"));
         return tc_pw2(nullptr, nullptr, 0, nullptr, Z, tab_scratch, mul, out, nullptr, rows, S2, LY, 0, N, mode, st, ld, flags);
     }
-    return fnm_pointwise_ysyn_ex(nullptr, 0, nullptr, 0, nullptr, Z, by, mul, out, nullptr, rows, S2, LY, 0, N, mode, flags, stream);
+    return fnm_pointwise_ysyn_ex(nullptr, 0, nullptr, 0, nullptr, Z, by, mul, out, nullptr, rows, S2, LY, 0, N, mode, flags, nullptr, stream);
 }
 
 size_t fnm_conv_wgrad_workspace_bytes(int64_t npos, int Ci, int Co) { return conv_wgrad_workspace(npos, Ci, Co); }
@@ -383,7 +383,7 @@ int fnm_fourier_layer_fwd(const fnm_plan* p, const float* xin, int act_in, const
     const int zgrad = (p->flags & FNM_PLAN_ZOUT_IS_GELU_GRAD) ? 1 : 0;
     FNM_REQUIRE(!zgrad || x_act_out, "layer_fwd: FNM_PLAN_ZOUT_IS_GELU_GRAD needs x_act_out");
     return fnm_pointwise_ysyn_ex(wc ? xin : nullptr, act_in, wc, 0, bc, Z, p->by, nullptr, z_out, x_act_out,
-                                 (int64_t)p->B * p->S1, p->S2, LY, p->Ci, p->Co, p->mode, zgrad ? FNM_PW_OUT_IS_GRAD : 0, stream);
+                                 (int64_t)p->B * p->S1, p->S2, LY, p->Ci, p->Co, p->mode, zgrad ? FNM_PW_OUT_IS_GRAD : 0, p->by16, stream);
 }
 
 int fnm_fourier_layer_bwd(const fnm_plan* p, const float* g_z, const float* xin, int act_in, const float* zin_pre,
@@ -439,7 +439,7 @@ int fnm_fourier_layer_bwd(const fnm_plan* p, const float* g_z, const float* xin,
         const float* mul = zin_pre ? zin_pre : (act_in ? xin : nullptr);
         const int pre_grad = (zin_pre && (p->flags & FNM_PLAN_PRE_IS_GELU_GRAD)) ? FNM_PW_MUL_IS_GRAD : 0;
         FNM_TRY(fnm_pointwise_ysyn_ex(wc ? g_z : nullptr, 0, wc, 1, nullptr, Zg, p->ayT, mul, g_in, nullptr,
-                                      (int64_t)p->B * p->P1, p->P2, LY, p->Co, p->Ci, p->mode, pre_grad, stream));
+                                      (int64_t)p->B * p->P1, p->P2, LY, p->Co, p->Ci, p->mode, pre_grad, p->ayT16, stream));
     }
     return FNM_OK;
 }

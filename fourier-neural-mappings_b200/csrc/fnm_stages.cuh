@@ -75,7 +75,7 @@ bool tc_pw2_supported(int64_t rows, int S2, int LY, int K, int N, int act, const
                       int by_ld = 0);
 int tc_pw2(const float* x, const float* wc, int wc_is_kn, const float* bias, const float* Z, const float* by,
            const float* mul, float* out, float* out_act, int64_t rows, int S2, int LY, int K, int N, int mode,
-           cudaStream_t st, int by_ld = 0, int flags = 0);
+           cudaStream_t st, int by_ld = 0, int flags = 0, const void* by16 = nullptr);
 int tc_set_sm_limit(int n);                // fnm_set_sm_limit
 bool tc_pointwise_ysyn_supported(int64_t rows, int S2, int LY, int K, int N);
 int tc_pointwise_ysyn(const float* x, int act, const float* wc, int wc_is_kn, const float* bias, const float* Z,

@@ -142,6 +142,38 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16
         "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
         : "memory");
 }
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]),
+                 "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+                 : "memory");
+}
+// two floats -> one 32-bit word of bf16 (round to nearest even): `first` in the low half (the lower k index of a
+// kind::f16 operand: 16-bit A elements sit in TMEM two per column, 16-bit B elements two per word of a K-major row)
+__device__ __forceinline__ uint32_t pack_bf16x2(float first, float second) {
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(second), "f"(first));
+    return r;
+}
+// 16 values -> TMEM as the three A operands of the "TF32 main product + bf16 corrections" scheme:
+//   hi  = rna_tf32(v)            16 fp32 columns   (kind::tf32, times the raw B tile)
+//   lo16 = bf16(v - hi)           8 columns of pairs (kind::f16, times bf16(B))
+//   hi16 = bf16(v)                8 columns of pairs (kind::f16, times bf16(B - trunc_tf32(B)))
+__device__ __forceinline__ void split_to_tmem16_corr16(uint32_t taddr_hi, uint32_t taddr_lo16, uint32_t taddr_hi16, const float* v) {
+    uint32_t w[16], q[8];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        uint32_t h;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(v[j]));
+        w[j] = h;
+    }
+    tmem_st16(taddr_hi, w);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) q[j] = pack_bf16x2(v[2 * j] - __uint_as_float(w[2 * j]), v[2 * j + 1] - __uint_as_float(w[2 * j + 1]));
+    tmem_st8(taddr_lo16, q);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) q[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+    tmem_st8(taddr_hi16, q);
+}
 // hi/lo TF32 split of 16 values straight into TMEM: hi -> columns [col, col+16), lo -> [col+lo_off, ...)
 __device__ __forceinline__ void split_to_tmem16(uint32_t taddr_hi, uint32_t taddr_lo, const float* v, bool want_lo) {
     uint32_t w[16];
@@ -174,6 +206,11 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
 // kind::tf32 instruction descriptor (cute::UMMA::InstrDescriptor): fp32 accumulate, K-major A and B
 __host__ __device__ inline uint32_t make_idesc(int M, int N) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// kind::f16 instruction descriptor, bf16 operands, fp32 accumulate, K-major A and B (K = 16 per instruction)
+__host__ __device__ inline uint32_t make_idesc_bf16(int M, int N) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
 // streaming 16-byte load: the activation is read exactly once per pass

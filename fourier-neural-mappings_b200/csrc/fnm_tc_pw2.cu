@@ -13,7 +13,13 @@
 //                      fp32 smem operands as TF32 by ignoring 13 mantissa bits, so the RAW tile is the
 //                      hi operand; converter warps add the remainder tile lo = v - trunc(v) (smem -> smem)
 //   D  : 2 x NT fp32 columns in TMEM; 8 epilogue warps (lane = channel, 128-byte coalesced stores)
-// Per tile: D = A_hi*B_raw + A_lo*B_raw + A_hi*B_lo.  FNM_MODE_TF32 issues A_hi*B_raw only.
+// Per tile (fp32-parity mode): D = A_hi*B_raw + A_lo*B_raw + A_hi*B_lo, all kind::tf32 (72 MMAs per 64-position tile at
+// C = 128).  FNM_MODE_TF32 issues A_hi*B_raw only.
+// FNM_PW2_CORR=bf16 (opt-in, measured and NOT the default): the two correction products as kind::f16 MMAs on bf16 operands,
+// D = A_hi*B_raw + bf16(A_lo)*bf16(B) + bf16(A)*bf16(B_lo) (K = 16 per instruction: 48 MMAs per tile; the converter warps
+// write bf16(B) | bf16(B - trunc(B)) in place of the fp32 remainder tile, and the table's pair can come precomputed through
+// fnm_plan.by16).  It is ~8 % faster at config 5 (0.59 vs 0.64 ms forward) but each product then carries ~1e-6 relative error
+// instead of ~1.7e-7, and on outputs with cancellation (golden model fnd2d: 1.7e-5) that breaks the 1e-5 parity bar.
 //
 // Warps (18 -> 5 per SM sub-partition, 96 registers):
 //   0 TMA producer | 1 TMEM allocator + MMA issuer | 2-5 Z warpgroup | 6-9 converters | 10-17 epilogue
@@ -28,6 +34,7 @@ constexpr int kPwThreads = 18 * 32;
 constexpr int kPwMmaWarp = 1;
 constexpr int kPwMaxStages = 6;
 constexpr uint32_t kPwSmemBudget = 226 * 1024;
+constexpr bool kPwEarlyRaw = false;          // issue the next tile's raw passes while the converters finish this one (see the issuer)
 
 struct PwArgs2 {
     const float* wc; const float* bias; const float* mul; float* out; float* out_act;
@@ -37,6 +44,9 @@ struct PwArgs2 {
     int NT, tiles_per_row, seg_tiles, nseg, units;
     int K1slabs, K2slabs, LYp, stages, nlo, nz, debug;
     uint32_t stage_bytes, x_bytes, z_bytes;
+    int corr16, k1s16, k2s16;                        // bf16 correction passes; 64-channel slabs of the bf16 X / by tiles
+    int by16;                                        // the bf16 pair of the by tile comes from a precomputed table (TMA)
+    uint32_t lo_bytes;                               // one remainder buffer: fp32 lo tile, or {bf16(B) | bf16(B_lo)}
     int mul_raw, out_grad;                           // FNM_PW_MUL_IS_GRAD / FNM_PW_OUT_IS_GRAD (see include/fnm_b200.h)
     uint32_t tmem0;                                  // always 0: the TMEM base as a kernel parameter (see the MMA issuer)
 };
@@ -56,6 +66,8 @@ __device__ long long g_pw2_trace[kTraceTiles * kTraceEv];
 
 // TMEM column map
 constexpr uint32_t kA1Hi = 0, kA1Lo = 128, kA2Hi = 256, kA2Lo = 320, kD0 = 384;
+// bf16 corrections: the remainder region of each operand holds two half-width operands, bf16(A_lo) | bf16(A)
+constexpr uint32_t kA1Lo16 = 128, kA1Hi16 = 192;
 
 
 // ---- MMA issue: the issuing warp is latency bound on its scalar (uniform-datapath) instruction stream,
@@ -141,6 +153,44 @@ __device__ __forceinline__ void pw2_issue_lo(uint32_t d, uint32_t tb, uint32_t a
     }
 }
 
+__device__ __forceinline__ void umma_ts16(uint32_t d, uint32_t a_tmem, uint32_t bdesc_lo, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t.reg .b64 bd;\n\tmov.b64 bd, {%2, %5};\n\telect.sync _|q, 0xffffffff;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], bd, %3, p;\n\t}" ::"r"(d),
+        "r"(a_tmem), "r"(bdesc_lo), "r"(idesc), "r"(accum), "r"(kDescHi)
+        : "memory");
+}
+
+// bf16 correction passes of one tile: D += bf16(A_lo) * bf16(B) + bf16(A) * bf16(B_lo), K = 16 per instruction.
+// N16_1 / N16_2: k-steps over the channel / mode axis (< 0: runtime).  xh / byh / xl / byl: descriptor low words of the
+// bf16(B) X and by tiles and of the bf16(B_lo) ones; 64 elements (4 k-steps) per slab.
+template <int N16_1, int N16_2, typename Early>
+__device__ __forceinline__ void pw2_issue_lo16(uint32_t d, uint32_t tb, uint32_t a2lo16, uint32_t a2hi16, uint32_t xh, uint32_t byh,
+                                               uint32_t xl, uint32_t byl, uint32_t slab16, uint32_t idesc, int n1_rt, int n2_rt,
+                                               Early&& early) {
+    const int n1 = N16_1 >= 0 ? N16_1 : n1_rt, n2 = N16_2 >= 0 ? N16_2 : n2_rt;
+    const int total = 2 * (n1 + n2), e_at = total > 8 ? total - 8 : 0;
+#pragma unroll
+    for (int pass = 0; pass < 2; ++pass) {
+        const uint32_t a1 = tb + (pass ? kA1Hi16 : kA1Lo16), a2 = pass ? a2hi16 : a2lo16;
+        const uint32_t bx = pass ? xl : xh, bb = pass ? byl : byh;
+#pragma unroll
+        for (int j = 0; j < (N16_1 >= 0 ? N16_1 : 8); ++j) {
+            if (j < n1) {
+                if (pass * (n1 + n2) + j == e_at) early();
+                umma_ts16(d, a1 + j * 8, bx + (j >> 2) * slab16 + 2 * (j & 3), idesc, 1);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < (N16_2 >= 0 ? N16_2 : 4); ++j) {
+            if (j < n2) {
+                if (pass * (n1 + n2) + n1 + j == e_at) early();
+                umma_ts16(d, a2 + j * 8, bb + (j >> 2) * slab16 + 2 * (j & 3), idesc, 1);
+            }
+        }
+    }
+}
+
 struct PwBars {
     uint64_t *full, *empty, *lo_full, *lo_empty, *a2_full, *a2_empty, *acc_full, *acc_empty;
 };
@@ -148,10 +198,13 @@ struct PwBars {
 // The MMA issuer's loop over this CTA's tiles, specialised on the shape.  Barrier waits are software pipelined: a tile
 // starts with its accumulator and stage already awaited (by the previous tile's `early` hook), awaits its remainder tile
 // before the last raw k-steps and the NEXT tile's accumulator / stage before the last remainder k-steps.
-template <int K1S, int NKS2, bool SINGLE>
+template <int K1S, int NKS2, int MODE>
 __device__ __forceinline__ void pw2_mma_loop(const PwArgs2& a, const PwBars& B, uint32_t sbase, uint32_t lo_base0, int my_units,
                                              uint32_t na2, bool has_z) {
-    const uint32_t idesc = make_idesc(128, a.NT);
+    constexpr bool SINGLE = MODE == 1, CORR16 = MODE == 2;
+    const uint32_t idesc = make_idesc(128, a.NT), idesc16 = make_idesc_bf16(128, a.NT);
+    const int n16_1 = 2 * a.K1slabs, n16_2 = (a.LYp / 8 + 1) / 2;     // bf16 k-steps (16 elements) over channels / modes
+    const uint32_t byh_off = ((uint32_t)a.k1s16 * a.NT * 128u) >> 4, half16 = (a.lo_bytes / 2) >> 4;
     const int nks2 = a.LYp / 8;                                   // k-steps over the (padded) mode axis
     const uint32_t slab16 = (uint32_t)a.NT * 8u;                  // slab stride in 16-byte descriptor units
     const uint32_t xb16 = a.x_bytes >> 4;
@@ -169,6 +222,7 @@ __device__ __forceinline__ void pw2_mma_loop(const PwArgs2& a, const PwBars& B, 
     // and drags every value derived from it out of the uniform registers)
     uint32_t t = 0, s = 0, sph = 0;
     bool tile_ready = false;                                      // this tile's accumulator and stage were seen complete early
+    bool raw_done = false;                                        // ... and its raw passes are already in the queue
     int unit = (int)blockIdx.x;
     for (int u = 0; u < my_units; ++u, unit += (int)gridDim.x) {
         int t0, t1;
@@ -182,7 +236,9 @@ __device__ __forceinline__ void pw2_mma_loop(const PwArgs2& a, const PwBars& B, 
         for (int tile = t0; tile < t1; ++tile, ++t) {
             uint64_t* a2_bar = (has_z && tile == t0) ? &B.a2_full[ub] : nullptr;
             const uint32_t acc = t & 1;
-            if (!tile_ready) {
+            const bool had_raw = raw_done;                          // this tile's raw pass was issued during the previous tile
+            raw_done = false;
+            if (!had_raw && !tile_ready) {
                 mbar_wait_warp(&B.acc_empty[acc], ((t >> 1) & 1) ^ 1);
                 mbar_wait_warp(&B.full[s], sph);
             }
@@ -193,10 +249,10 @@ __device__ __forceinline__ void pw2_mma_loop(const PwArgs2& a, const PwBars& B, 
             // `uniform base + immediate`, one UIADD3 away from its UTCHMMA
             const uint32_t tmem_base = uniform_u32(a.tmem0 + (t & 0u));
             const uint32_t d = tmem_base + kD0 + acc * 64u;
-            const uint32_t a2hi = tmem_base + a2off, a2lo = a2hi + (na2 == 2 ? 32u : 64u);
-            const uint32_t x_lo = uniform_u32(desc_lo(sbase + s * a.stage_bytes)), by_lo = x_lo + xb16;
+            const uint32_t a2w = na2 == 2 ? 64u : 128u;             // columns of one Z^T buffer: hi | lo (or hi | lo16 | hi16)
+            const uint32_t a2hi = tmem_base + a2off, a2lo = a2hi + a2w / 2;
             const uint32_t lb = a.nlo == 2 ? (t & 1) : 0u;
-            const uint32_t xl_lo = uniform_u32(desc_lo(lo_base0 + lb * a.stage_bytes)), byl_lo = xl_lo + xb16;
+            const uint32_t xl_lo = uniform_u32(desc_lo(lo_base0 + lb * a.lo_bytes)), byl_lo = xl_lo + xb16;
             // the next tile's stage / accumulator
             uint32_t s1 = s + 1, sph1 = sph;
             if (s1 == (uint32_t)a.stages) { s1 = 0; sph1 ^= 1u; }
@@ -208,16 +264,38 @@ __device__ __forceinline__ void pw2_mma_loop(const PwArgs2& a, const PwBars& B, 
                 next_ready = more && mbar_test_warp(&B.acc_empty[acc ^ 1u], (((t + 1) >> 1) & 1) ^ 1) && mbar_test_warp(&B.full[s1], sph1);
             };
             auto test_lo = [&]() { lo_ready = mbar_test_warp(&B.lo_full[lb], a.nlo == 2 ? ((t >> 1) & 1) : (t & 1)); };
-            // raw passes: (A_hi + A_lo) * B_raw
-            if (SINGLE) pw2_issue_raw<K1S, NKS2, true>(d, tmem_base, a2hi, a2lo, x_lo, by_lo, slab16, idesc, a.K1slabs, nks2, a2_bar, upar, test_next);
-            else pw2_issue_raw<K1S, NKS2, false>(d, tmem_base, a2hi, a2lo, x_lo, by_lo, slab16, idesc, a.K1slabs, nks2, a2_bar, upar, test_lo);
-            umma_commit(&B.empty[s]);                              // the raw tile is free once the raw passes retire
+            // raw passes of accumulator `dd` from stage `ss`: (A_hi [+ A_lo]) * B_raw
+            auto raw_pass = [&](uint32_t dd, uint32_t ss, uint64_t* zbar) {
+                const uint32_t x_lo = uniform_u32(desc_lo(sbase + ss * a.stage_bytes)), by_lo = x_lo + xb16;
+                if (SINGLE) pw2_issue_raw<K1S, NKS2, true>(dd, tmem_base, a2hi, a2lo, x_lo, by_lo, slab16, idesc, a.K1slabs, nks2, zbar, upar, test_next);
+                else if (CORR16) pw2_issue_raw<K1S, NKS2, true>(dd, tmem_base, a2hi, a2lo, x_lo, by_lo, slab16, idesc, a.K1slabs, nks2, zbar, upar, test_lo);
+                else pw2_issue_raw<K1S, NKS2, false>(dd, tmem_base, a2hi, a2lo, x_lo, by_lo, slab16, idesc, a.K1slabs, nks2, zbar, upar, test_lo);
+                umma_commit(&B.empty[ss]);                          // the raw tile is free once the raw passes retire
+            };
+            if (!had_raw) raw_pass(d, s, a2_bar);
             PW2_TRACE(t, 2);
             if (!SINGLE) {
+                if (had_raw) test_lo();
+                // The converters are still working on this tile: issue the NEXT tile's raw passes first (other accumulator,
+                // next stage) when both are free -- within a grid row only (a new row's Z^T may have to wait for this
+                // tile's remainder pass to release the operand buffer).
+                // (Measured at config 5 and switched off: 0.59 -> 0.62 ms forward, 0.73 -> 0.77 ms backward -- the accumulator's
+                // completion is then signalled behind the next tile's 24 queued MMAs and the epilogue starts later.)
+                if (kPwEarlyRaw && !lo_ready && tile + 1 < t1 && mbar_test_warp(&B.acc_empty[acc ^ 1u], (((t + 1) >> 1) & 1) ^ 1) &&
+                    mbar_test_warp(&B.full[s1], sph1)) {
+                    tc_fence_after();
+                    raw_pass(tmem_base + kD0 + (acc ^ 1u) * 64u, s1, nullptr);
+                    raw_done = true;
+                }
                 // remainder pass: A_hi * B_lo
                 if (!lo_ready) mbar_wait_warp(&B.lo_full[lb], a.nlo == 2 ? ((t >> 1) & 1) : (t & 1));
                 tc_fence_after();
-                pw2_issue_lo<K1S, NKS2>(d, tmem_base, a2hi, xl_lo, byl_lo, slab16, idesc, a.K1slabs, nks2, test_next);
+                if (CORR16)
+                    pw2_issue_lo16<(K1S >= 0 ? 2 * K1S : -1), (NKS2 >= 0 ? (NKS2 + 1) / 2 : -1)>(
+                        d, tmem_base, a2lo, a2lo + a2w / 4, xl_lo, xl_lo + byh_off, xl_lo + half16, xl_lo + half16 + byh_off, slab16,
+                        idesc16, n16_1, n16_2, test_next);
+                else
+                    pw2_issue_lo<K1S, NKS2>(d, tmem_base, a2hi, xl_lo, byl_lo, slab16, idesc, a.K1slabs, nks2, test_next);
                 umma_commit(&B.lo_empty[lb]);
             }
             umma_commit(&B.acc_full[acc]);
@@ -372,12 +450,12 @@ __device__ __forceinline__ void pw2_epilogue(const PwArgs2& a, int warp, int lan
 
 __global__ void __launch_bounds__(kPwThreads, 1)
 pw2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapBy,
-           const __grid_constant__ CUtensorMap mapZ, const PwArgs2 a) {
+           const __grid_constant__ CUtensorMap mapZ, const __grid_constant__ CUtensorMap mapBy16, const PwArgs2 a) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     // [stages x {X raw slabs, by raw slabs}] [lo copy of one stage] [Z staging] [barriers]
     uint8_t* lo_buf = smem + (size_t)a.stages * a.stage_bytes;
-    float* zs = reinterpret_cast<float*>(lo_buf + (size_t)a.nlo * a.stage_bytes);
+    float* zs = reinterpret_cast<float*>(lo_buf + (size_t)a.nlo * a.lo_bytes);
     uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(zs) + (size_t)a.nz * a.z_bytes);
     uint64_t* full = bars;                          // [kPwMaxStages]
     uint64_t* empty = bars + kPwMaxStages;          // [kPwMaxStages]
@@ -399,12 +477,13 @@ pw2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUt
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < a.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], a.single_pass ? 1 : 5); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&lo_full[s], 4); mbar_init(&lo_empty[s], 1); }
+        // remainder tile complete: the 4 converter warps (+ the producer's expect_tx when the table's bf16 pair is TMA-loaded)
+        for (int s = 0; s < 2; ++s) { mbar_init(&lo_full[s], a.by16 ? 5 : 4); mbar_init(&lo_empty[s], 1); }
         for (int s = 0; s < 4; ++s) { mbar_init(&z_full[s], 1); mbar_init(&z_empty[s], 4); }
         for (int s = 0; s < 2; ++s) { mbar_init(&a2_full[s], 4); mbar_init(&a2_empty[s], 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 8); }
         fence_barrier_init();
-        tma_prefetch_desc(&mapX); tma_prefetch_desc(&mapBy); tma_prefetch_desc(&mapZ);
+        tma_prefetch_desc(&mapX); tma_prefetch_desc(&mapBy); tma_prefetch_desc(&mapZ); tma_prefetch_desc(&mapBy16);
     }
     if (warp == 1) tmem_alloc(tmem_slot, 512);
     tc_fence_before();
@@ -427,7 +506,8 @@ pw2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUt
                 if (o < a.CO && k < a.CI && ro == rk)
                     v[j] = a.wc_is_kn ? __ldg(a.wc + (size_t)ii * a.COo + oo) : __ldg(a.wc + (size_t)oo * a.CIo + ii);
             }
-            split_to_tmem16(lane_base + kA1Hi + k0, lane_base + kA1Lo + k0, v, !a.single_pass);
+            if (a.corr16) split_to_tmem16_corr16(lane_base + kA1Hi + k0, lane_base + kA1Lo16 + k0 / 2, lane_base + kA1Hi16 + k0 / 2, v);
+            else split_to_tmem16(lane_base + kA1Hi + k0, lane_base + kA1Lo + k0, v, !a.single_pass);
         }
         tmem_st_wait();
     }
@@ -475,6 +555,25 @@ pw2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUt
                         tma_load_2d(&mapBy, &full[s], st + a.x_bytes + (size_t)kb * a.NT * 128, kb * 32, y0);
                 }
             }
+        } else if (lane == 1 && a.by16) {
+            // second producer lane: the bf16(by) | bf16(by_lo) tiles of every tile column, from the precomputed table pair
+            // straight into the remainder buffers (paced by lo_empty, independently of the raw stages lane 0 runs ahead with)
+            const uint32_t half = a.lo_bytes / 2, slab_b = (uint32_t)a.NT * 128u;
+            uint32_t t = 0;
+            for (int u = 0; u < my_units; ++u) {
+                int row, t0, t1;
+                unit_tiles(u, row, t0, t1);
+                for (int tile = t0; tile < t1; ++tile, ++t) {
+                    const uint32_t lb = a.nlo == 2 ? (t & 1) : 0u;
+                    mbar_wait(&lo_empty[lb], (a.nlo == 2 ? ((t >> 1) & 1) : (t & 1)) ^ 1);
+                    uint8_t* lob = lo_buf + (size_t)lb * a.lo_bytes + (size_t)a.k1s16 * slab_b;
+                    mbar_expect_tx(&lo_full[lb], 2u * (uint32_t)a.k2s16 * slab_b);
+                    for (int kb = 0; kb < a.k2s16; ++kb) {
+                        tma_load_3d(&mapBy16, &lo_full[lb], lob + (size_t)kb * slab_b, kb * 64, tile * a.NT, 0);
+                        tma_load_3d(&mapBy16, &lo_full[lb], lob + half + (size_t)kb * slab_b, kb * 64, tile * a.NT, 1);
+                    }
+                }
+            }
         }
     } else if (warp == kPwMmaWarp) {
         // =========================================================================== MMA issuer
@@ -491,15 +590,17 @@ pw2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUt
         bool done = false;
 #define PW2_LOOP(K1, K2)                                                                                                 \
         if (!done && a.K1slabs == K1 && nks2 == K2) {                                                                    \
-            if (a.single_pass) pw2_mma_loop<K1, K2, true>(a, B, sbase, lo_base0, my_units, na2, has_z);                  \
-            else pw2_mma_loop<K1, K2, false>(a, B, sbase, lo_base0, my_units, na2, has_z);                               \
+            if (a.single_pass) pw2_mma_loop<K1, K2, 1>(a, B, sbase, lo_base0, my_units, na2, has_z);                     \
+            else if (a.corr16) pw2_mma_loop<K1, K2, 2>(a, B, sbase, lo_base0, my_units, na2, has_z);                     \
+            else pw2_mma_loop<K1, K2, 0>(a, B, sbase, lo_base0, my_units, na2, has_z);                                   \
             done = true;                                                                                                 \
         }
         PW2_SHAPES(PW2_LOOP)
 #undef PW2_LOOP
         if (!done) {
-            if (a.single_pass) pw2_mma_loop<-1, -1, true>(a, B, sbase, lo_base0, my_units, na2, has_z);
-            else pw2_mma_loop<-1, -1, false>(a, B, sbase, lo_base0, my_units, na2, has_z);
+            if (a.single_pass) pw2_mma_loop<-1, -1, 1>(a, B, sbase, lo_base0, my_units, na2, has_z);
+            else if (a.corr16) pw2_mma_loop<-1, -1, 2>(a, B, sbase, lo_base0, my_units, na2, has_z);
+            else pw2_mma_loop<-1, -1, 0>(a, B, sbase, lo_base0, my_units, na2, has_z);
         }
     } else if (warp >= 2 && warp < 6) {
         // =========================================================================== Z warpgroup: Z[row] (smem) -> A2 hi/lo (TMEM)
@@ -509,7 +610,8 @@ pw2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUt
         const int zr = c / a.COo, zo = c - zr * a.COo;                  // lane = (row within the group, channel)
         for (int u = 0; u < (has_z ? my_units : 0); ++u) {
             const uint32_t ub = (uint32_t)u % na2, upar = ((uint32_t)u / na2) & 1;
-            const uint32_t a2hi = kA2Hi + (na2 == 2 ? 64u * ub : 0u), a2lo = a2hi + (na2 == 2 ? 32u : 64u);
+            const uint32_t a2w = na2 == 2 ? 64u : 128u;
+            const uint32_t a2hi = kA2Hi + (na2 == 2 ? 64u * ub : 0u), a2lo = a2hi + a2w / 2;
             const uint32_t zb = (uint32_t)u % (uint32_t)a.nz, zpar = ((uint32_t)u / (uint32_t)a.nz) & 1;
             const float* zsb = reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(zs) + (size_t)zb * a.z_bytes);
             mbar_wait(&z_full[zb], zpar);
@@ -522,7 +624,8 @@ pw2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUt
                     const int kk = l0 + j;                                        // each row of the group brings its own Z tile
                     v[j] = (c_ok && kk < a.LY) ? zsb[(zr * a.LY + kk) * a.COo + zo] : 0.f;
                 }
-                split_to_tmem16(lane_base + a2hi + l0, lane_base + a2lo + l0, v, !a.single_pass);
+                if (a.corr16) split_to_tmem16_corr16(lane_base + a2hi + l0, lane_base + a2lo + l0 / 2, lane_base + a2lo + a2w / 4 + l0 / 2, v);
+                else split_to_tmem16(lane_base + a2hi + l0, lane_base + a2lo + l0, v, !a.single_pass);
             }
             tmem_st_wait();
             tc_fence_before();
@@ -543,31 +646,81 @@ pw2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUt
                     const uint32_t lb = a.nlo == 2 ? (t & 1) : 0u;
                     mbar_wait(&lo_empty[lb], (a.nlo == 2 ? ((t >> 1) & 1) : (t & 1)) ^ 1);
                     if (warp == 6) PW2_TRACE(t, 5);
-                    const uint32_t src = smem_u32(smem) + s * a.stage_bytes + (uint32_t)ct * 16u;
-                    const uint32_t dst = smem_u32(lo_buf) + lb * a.stage_bytes + (uint32_t)ct * 16u;
-                    // linear copy (the remainder tile has the raw tile's swizzled layout, so offsets are identical):
-                    // stage_bytes is a multiple of 4 KB; 2 KB per pass of the 128 threads, two passes per iteration
-                    uint32_t off = 0;
+                    if (a.corr16) {
+                        // two bf16 tiles: bf16(B) and bf16(B - trunc(B)).  Warp w converts the `up = w & 1` half of every
+                        // 64-channel output slab, i.e. fp32 slab 2 so + up whole: lane = (row, q) reads the row's chunks 2q, 2q + 1
+                        // (8 channels) and writes output chunk 4 up + q.  Rows of a quarter-warp differ by XOR 5 in their low bits,
+                        // which keeps the swizzled 16-byte accesses of its 8 lanes on 8 different bank groups for the loads (bit 0
+                        // flips even <-> odd chunks) and for the stores (bit 2 flips the half of the row).
+                        const uint32_t srcb = smem_u32(smem) + s * a.stage_bytes, dstb = smem_u32(lo_buf) + lb * a.lo_bytes;
+                        const uint32_t half = a.lo_bytes / 2, slab_b = (uint32_t)a.NT * 128u;
+                        const int up = (warp - 6) & 1, q = lane & 3, rsel = lane >> 2;
+                        const int rr = (rsel >> 1) ^ ((rsel & 1) ? 5 : 0);
+                        const int rbase = 8 * ((warp - 6) >> 1) + rr;                 // rows rbase + 16 i
+                        const uint32_t in0 = (uint32_t)(((2 * q) ^ rr) << 4), in1 = (uint32_t)(((2 * q + 1) ^ rr) << 4);
+                        const uint32_t outc = (uint32_t)(((4 * up + q) ^ rr) << 4);
+                        const int nparts = a.by16 ? 1 : 2;
+#pragma unroll 1
+                        for (int part = 0; part < nparts; ++part) {
+                            const int nin = part ? a.K2slabs : a.K1slabs, nout = part ? a.k2s16 : a.k1s16;
+                            const uint32_t src0 = srcb + (part ? a.x_bytes : 0u), dst0 = dstb + (part ? (uint32_t)a.k1s16 * slab_b : 0u);
+#pragma unroll 1
+                            for (int so = 0; so < nout; ++so) {
+                                if (2 * so + up >= nin) break;                        // odd slab count: that half is never multiplied
+                                const uint32_t sin = src0 + (uint32_t)(2 * so + up) * slab_b, sout = dst0 + (uint32_t)so * slab_b;
+                                // all (up to four) rows of this thread first: 8 loads in flight, then convert and store
+                                float4 e[4], o[4];
+#pragma unroll
+                                for (int i = 0; i < 4; ++i) {
+                                    const int r = rbase + 16 * i;
+                                    e[i] = make_float4(0.f, 0.f, 0.f, 0.f); o[i] = e[i];
+                                    if (r < a.NT) {
+                                        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(e[i].x), "=f"(e[i].y), "=f"(e[i].z), "=f"(e[i].w) : "r"(sin + (uint32_t)r * 128u + in0));
+                                        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(o[i].x), "=f"(o[i].y), "=f"(o[i].z), "=f"(o[i].w) : "r"(sin + (uint32_t)r * 128u + in1));
+                                    }
+                                }
+#pragma unroll
+                                for (int i = 0; i < 4; ++i) {
+                                    const int r = rbase + 16 * i;
+                                    if (r >= a.NT) break;
+                                    auto lo_of = [](float x) { return x - __uint_as_float(__float_as_uint(x) & 0xffffe000u); };
+                                    const uint32_t h0 = pack_bf16x2(e[i].x, e[i].y), h1 = pack_bf16x2(e[i].z, e[i].w);
+                                    const uint32_t h2 = pack_bf16x2(o[i].x, o[i].y), h3 = pack_bf16x2(o[i].z, o[i].w);
+                                    const uint32_t l0 = pack_bf16x2(lo_of(e[i].x), lo_of(e[i].y)), l1 = pack_bf16x2(lo_of(e[i].z), lo_of(e[i].w));
+                                    const uint32_t l2 = pack_bf16x2(lo_of(o[i].x), lo_of(o[i].y)), l3 = pack_bf16x2(lo_of(o[i].z), lo_of(o[i].w));
+                                    const uint32_t dsta = sout + (uint32_t)r * 128u + outc;
+                                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dsta), "r"(h0), "r"(h1), "r"(h2), "r"(h3) : "memory");
+                                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dsta + half), "r"(l0), "r"(l1), "r"(l2), "r"(l3) : "memory");
+                                }
+                            }
+                        }
+                    } else {
+                        const uint32_t src = smem_u32(smem) + s * a.stage_bytes + (uint32_t)ct * 16u;
+                        const uint32_t dst = smem_u32(lo_buf) + lb * a.lo_bytes + (uint32_t)ct * 16u;
+                        // linear copy (the remainder tile has the raw tile's swizzled layout, so offsets are identical):
+                        // stage_bytes is a multiple of 4 KB; 2 KB per pass of the 128 threads, two passes per iteration
+                        uint32_t off = 0;
 #ifdef FNM_PW2_DEBUG_SWITCHES
-                    if (a.debug & 2) off = a.stage_bytes;
+                        if (a.debug & 2) off = a.stage_bytes;
 #endif
-                    for (; off + 4096u <= a.stage_bytes; off += 4096u) {
-                        float4 v0, v1;
-                        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v0.x), "=f"(v0.y), "=f"(v0.z), "=f"(v0.w) : "r"(src + off));
-                        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v1.x), "=f"(v1.y), "=f"(v1.z), "=f"(v1.w) : "r"(src + off + 2048u));
-                        v0.x -= __uint_as_float(__float_as_uint(v0.x) & 0xffffe000u); v0.y -= __uint_as_float(__float_as_uint(v0.y) & 0xffffe000u);
-                        v0.z -= __uint_as_float(__float_as_uint(v0.z) & 0xffffe000u); v0.w -= __uint_as_float(__float_as_uint(v0.w) & 0xffffe000u);
-                        v1.x -= __uint_as_float(__float_as_uint(v1.x) & 0xffffe000u); v1.y -= __uint_as_float(__float_as_uint(v1.y) & 0xffffe000u);
-                        v1.z -= __uint_as_float(__float_as_uint(v1.z) & 0xffffe000u); v1.w -= __uint_as_float(__float_as_uint(v1.w) & 0xffffe000u);
-                        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst + off), "f"(v0.x), "f"(v0.y), "f"(v0.z), "f"(v0.w) : "memory");
-                        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst + off + 2048u), "f"(v1.x), "f"(v1.y), "f"(v1.z), "f"(v1.w) : "memory");
-                    }
-                    if (off < a.stage_bytes) {                        // odd number of 2 KB passes
-                        float4 v0;
-                        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v0.x), "=f"(v0.y), "=f"(v0.z), "=f"(v0.w) : "r"(src + off));
-                        v0.x -= __uint_as_float(__float_as_uint(v0.x) & 0xffffe000u); v0.y -= __uint_as_float(__float_as_uint(v0.y) & 0xffffe000u);
-                        v0.z -= __uint_as_float(__float_as_uint(v0.z) & 0xffffe000u); v0.w -= __uint_as_float(__float_as_uint(v0.w) & 0xffffe000u);
-                        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst + off), "f"(v0.x), "f"(v0.y), "f"(v0.z), "f"(v0.w) : "memory");
+                        for (; off + 4096u <= a.stage_bytes; off += 4096u) {
+                            float4 v0, v1;
+                            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v0.x), "=f"(v0.y), "=f"(v0.z), "=f"(v0.w) : "r"(src + off));
+                            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v1.x), "=f"(v1.y), "=f"(v1.z), "=f"(v1.w) : "r"(src + off + 2048u));
+                            v0.x -= __uint_as_float(__float_as_uint(v0.x) & 0xffffe000u); v0.y -= __uint_as_float(__float_as_uint(v0.y) & 0xffffe000u);
+                            v0.z -= __uint_as_float(__float_as_uint(v0.z) & 0xffffe000u); v0.w -= __uint_as_float(__float_as_uint(v0.w) & 0xffffe000u);
+                            v1.x -= __uint_as_float(__float_as_uint(v1.x) & 0xffffe000u); v1.y -= __uint_as_float(__float_as_uint(v1.y) & 0xffffe000u);
+                            v1.z -= __uint_as_float(__float_as_uint(v1.z) & 0xffffe000u); v1.w -= __uint_as_float(__float_as_uint(v1.w) & 0xffffe000u);
+                            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst + off), "f"(v0.x), "f"(v0.y), "f"(v0.z), "f"(v0.w) : "memory");
+                            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst + off + 2048u), "f"(v1.x), "f"(v1.y), "f"(v1.z), "f"(v1.w) : "memory");
+                        }
+                        if (off < a.stage_bytes) {                        // odd number of 2 KB passes
+                            float4 v0;
+                            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v0.x), "=f"(v0.y), "=f"(v0.z), "=f"(v0.w) : "r"(src + off));
+                            v0.x -= __uint_as_float(__float_as_uint(v0.x) & 0xffffe000u); v0.y -= __uint_as_float(__float_as_uint(v0.y) & 0xffffe000u);
+                            v0.z -= __uint_as_float(__float_as_uint(v0.z) & 0xffffe000u); v0.w -= __uint_as_float(__float_as_uint(v0.w) & 0xffffe000u);
+                            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst + off), "f"(v0.x), "f"(v0.y), "f"(v0.z), "f"(v0.w) : "memory");
+                        }
                     }
                     fence_proxy_async();
                     __syncwarp();
@@ -642,7 +795,13 @@ static int pw2_fold(int64_t rows, int CI, int CO) {
     return 1;
 }
 
-static bool pw2_configure(PwArgs2& a, int64_t rows, int S2, int LY, int CI, int CO, int by_ld = 0) {
+static bool pw2_corr16_default() {
+    const char* e = getenv("FNM_PW2_CORR");
+    return e && e[0] == 'b';                                     // FNM_PW2_CORR=bf16: bf16 correction passes (see the header note)
+}
+
+static bool pw2_configure(PwArgs2& a, int64_t rows, int S2, int LY, int CI, int CO, int by_ld = 0, int mode = FNM_MODE_FP32) {
+    a.corr16 = (mode != FNM_MODE_TF32 && pw2_corr16_default()) ? 1 : 0;
     // what TMA can address (16-byte strides: the twiddle table's leading dimension by_ld, LY unless the caller padded it)
     // and what the TMEM map holds (128 lanes, 64 mode columns)
     if (by_ld == 0) by_ld = LY;
@@ -677,12 +836,15 @@ static bool pw2_configure(PwArgs2& a, int64_t rows, int S2, int LY, int CI, int 
     a.nz = 1;
     if (a.z_bytes > 0 && a.z_bytes % 128 == 0) { a.nz = (int)(32768u / a.z_bytes); a.nz = a.nz < 1 ? 1 : (a.nz > 4 ? 4 : a.nz); }
     const uint32_t fixed = (uint32_t)a.nz * a.z_bytes + 1024 /*align*/ + 512 /*barriers*/;
-    if (fixed + 3 * a.stage_bytes > kPwSmemBudget) return false;             // 2 raw stages + 1 remainder buffer at least
-    const int slots = (int)((kPwSmemBudget - fixed) / a.stage_bytes);        // raw stages + remainder buffers
-    // bytes in flight are what hides HBM latency (~90 KB per SM): every slot beyond one remainder buffer is a raw stage
-    a.nlo = slots >= 4 ? 2 : 1;
-    { const char* e = getenv("FNM_PW2_NLO"); if (e && slots >= 4) a.nlo = atoi(e) == 2 ? 2 : 1; }
-    a.stages = slots - a.nlo > kPwMaxStages ? kPwMaxStages : slots - a.nlo;
+    // remainder buffer: the fp32 lo tile (stage layout), or the two bf16 tiles (64-channel slabs; an odd slab count rounds up)
+    a.k1s16 = (a.K1slabs + 1) / 2; a.k2s16 = (a.K2slabs + 1) / 2;
+    a.lo_bytes = a.corr16 ? 2u * (uint32_t)(a.k1s16 + a.k2s16) * a.NT * 128u : a.stage_bytes;
+    if (fixed + 2 * a.stage_bytes + a.lo_bytes > kPwSmemBudget) return false;        // 2 raw stages + 1 remainder buffer at least
+    // bytes in flight are what hides HBM latency (~90 KB per SM): everything beyond the remainder buffers is raw stages
+    a.nlo = fixed + 2 * a.stage_bytes + 2 * a.lo_bytes <= kPwSmemBudget ? 2 : 1;
+    { const char* e = getenv("FNM_PW2_NLO"); if (e && a.nlo == 2) a.nlo = atoi(e) == 2 ? 2 : 1; }
+    const int slots = (int)((kPwSmemBudget - fixed - a.nlo * a.lo_bytes) / a.stage_bytes);
+    a.stages = slots > kPwMaxStages ? kPwMaxStages : slots;
     { const char* e = getenv("FNM_PW2_STAGES"); if (e && atoi(e) >= 2 && atoi(e) <= a.stages) a.stages = atoi(e); }
     // units: whole rows when there are enough of them, otherwise row segments (1-D problems have few rows)
     int nseg = 1;
@@ -712,17 +874,31 @@ bool tc_pw2_supported(int64_t rows, int S2, int LY, int K, int N, int act, const
 
 int tc_pw2(const float* x, const float* wc, int wc_is_kn, const float* bias, const float* Z, const float* by,
            const float* mul, float* out, float* out_act, int64_t rows, int S2, int LY, int K, int N, int mode,
-           cudaStream_t st, int by_ld, int flags) {
+           cudaStream_t st, int by_ld, int flags, const void* by16) {
     PwArgs2 a{};
     const int CI = (x && wc) ? K : 0;
     if (by_ld == 0) by_ld = LY;
-    if (!pw2_configure(a, rows, S2, LY, CI, N, by_ld)) return fail(FNM_ENOTSUP, "pointwise_ysyn: shape not served by the TMA kernel");
+    if (!pw2_configure(a, rows, S2, LY, CI, N, by_ld, mode)) return fail(FNM_ENOTSUP, "pointwise_ysyn: shape not served by the TMA kernel");
     a.wc = wc; a.bias = bias; a.mul = mul; a.out = out; a.out_act = out_act; a.wc_is_kn = wc_is_kn;
     a.single_pass = mode == FNM_MODE_TF32;
     a.mul_raw = (flags & FNM_PW_MUL_IS_GRAD) ? 1 : 0;
     a.out_grad = (flags & FNM_PW_OUT_IS_GRAD) ? 1 : 0;
     { const char* e = getenv("FNM_PW2_DEBUG"); a.debug = e ? atoi(e) : 0; }
-    CUtensorMap mx, mb, mz;
+    CUtensorMap mx, mb, mz, mb16;
+    a.by16 = 0;
+    if (LY > 0 && a.corr16 && by16 && by_ld == LY && (reinterpret_cast<uintptr_t>(by16) & 15) == 0) {
+        // [2][S2][LY8] bfloat16: boxes of 64 columns x NT rows of one of the two tables, columns past LY8 read as zero
+        const cuuint64_t ly8 = (cuuint64_t)((LY + 7) / 8 * 8);
+        const cuuint64_t dims[3] = {ly8, (cuuint64_t)a.S2, 2};
+        const cuuint64_t str[2] = {ly8 * 2, ly8 * 2 * (cuuint64_t)a.S2};
+        const cuuint32_t box[3] = {64, (cuuint32_t)a.NT, 1};
+        const cuuint32_t estr[3] = {1, 1, 1};
+        EncodeTiledFn fn = encode_fn();
+        if (fn && fn(&mb16, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(by16), dims, str, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS)
+            a.by16 = 1;
+    }
     if (LY > 0) {
         const cuuint64_t dims[2] = {(cuuint64_t)by_ld, (cuuint64_t)a.S2};        // columns LY .. by_ld - 1 of a padded table are zero
         const cuuint64_t str[1] = {(cuuint64_t)by_ld * 4};
@@ -744,7 +920,8 @@ int tc_pw2(const float* x, const float* wc, int wc_is_kn, const float* bias, con
         mx = mb;
     }
     if (LY == 0) { mb = mx; mz = mx; }                          // never dereferenced without a spectral term
-    const size_t smem = (size_t)(a.stages + a.nlo) * a.stage_bytes + (size_t)a.nz * a.z_bytes + 1024 + 512;
+    if (!a.by16) mb16 = mx;
+    const size_t smem = (size_t)a.stages * a.stage_bytes + (size_t)a.nlo * a.lo_bytes + (size_t)a.nz * a.z_bytes + 1024 + 512;
     static std::atomic<uint64_t> attr_set{0};
     int attr_set_dev = 0;
     if (once_needed(attr_set, attr_set_dev)) {
@@ -755,7 +932,7 @@ int tc_pw2(const float* x, const float* wc, int wc_is_kn, const float* bias, con
     const int grid = a.units < sm_count() ? a.units : sm_count();
     {
         LaunchScope ls(LY > 0 ? "pointwise_ysyn" : "pointwise_conv", st);
-        pw2_kernel<<<grid, kPwThreads, smem < 120 * 1024 ? 120 * 1024 : smem, st>>>(mx, mb, mz, a);
+        pw2_kernel<<<grid, kPwThreads, smem < 120 * 1024 ? 120 * 1024 : smem, st>>>(mx, mb, mz, mb16, a);
     }
     return check_launch("pointwise_ysyn");
 }

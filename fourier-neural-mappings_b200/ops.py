@@ -434,7 +434,7 @@ class PointwiseConvFn(torch.autograd.Function):
         if ctx.needs_input_grad[3] if zpre is not None else ctx.needs_input_grad[0]:
             dx = torch.empty_like(x)
             check(L.fnm_pointwise_ysyn_ex(_ptr(g), 0, _ptr(w), 1, None, None, None, _ptr(zpre), _ptr(dx), None, B * P1, P2, 0,
-                                          Co, Ci, _MODE, _lib.FNM_PW_MUL_IS_GRAD if ctx.zpre_is_grad else 0, _stream()),
+                                          Co, Ci, _MODE, _lib.FNM_PW_MUL_IS_GRAD if ctx.zpre_is_grad else 0, None, _stream()),
                   "fnm_pointwise_ysyn_ex")
         if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
             npos = B * P1 * P2

@@ -10,6 +10,8 @@ rounded to fp32) that the CUDA kernels contract against; see include/fnm_b200.h 
 import math
 from functools import lru_cache
 
+import os
+
 import numpy as np
 import torch
 
@@ -128,7 +130,12 @@ class ModeTables:
     def device(self, device):
         key = str(device)
         if key not in self._dev:
-            self._dev[key] = {k: torch.from_numpy(v).to(device) for k, v in self.host.items()}
+            d = {k: torch.from_numpy(v).to(device) for k, v in self.host.items()}
+            if os.environ.get("FNM_PW2_CORR", "")[:1] == "b":   # opt-in bf16 correction passes of the fused pointwise kernel
+                for name in ("by", "ayT"):
+                    if name in d:
+                        d[name + "16"] = bf16_table_pair(d[name])
+            self._dev[key] = d
         return self._dev[key]
 
     def c_plan(self, device, B, Ci, Co, mode=FNM_MODE_FP32):
@@ -136,9 +143,23 @@ class ModeTables:
         p = FnmPlan()
         p.B, p.P1, p.P2, p.S1, p.S2 = B, self.P1, self.P2, self.S1, self.S2
         p.R, p.NY, p.Ci, p.Co, p.rows_per_w, p.mode = self.R, self.NY, Ci, Co, self.rows_per_w, mode
-        for name in ("ay", "ayT", "by", "byT", "ex", "fx", "exb", "fxb"):
+        for name in ("ay", "ayT", "by", "byT", "ex", "fx", "exb", "fxb", "by16", "ayT16"):
             setattr(p, name, d[name].data_ptr() if name in d else None)
         return p
+
+
+def bf16_table_pair(tab):
+    """[rows][cols] fp32 table -> [2][rows][cols8] bfloat16 (cols8 = cols rounded up to 8, zero padded): bf16(tab) and
+    bf16(tab - trunc_tf32(tab)), the two shared-memory operands of the bf16 correction passes of the fused pointwise
+    kernel (include/fnm_b200.h, fnm_plan.by16).  They depend on the table only, so they are made once here instead of
+    being re-derived from the fp32 tile by the kernel's converter warps for every tile."""
+    rows, cols = tab.shape
+    cols8 = (cols + 7) // 8 * 8
+    hi = (tab.view(torch.int32) & -8192).view(torch.float32)               # what the tensor core reads: 13 mantissa bits dropped
+    out = torch.zeros((2, rows, cols8), dtype=torch.bfloat16, device=tab.device)
+    out[0, :, :cols] = tab.to(torch.bfloat16)
+    out[1, :, :cols] = (tab - hi).to(torch.bfloat16)
+    return out
 
 
 @lru_cache(maxsize=256)

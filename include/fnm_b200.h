@@ -86,6 +86,9 @@ typedef struct fnm_plan {
                                                weights unchanged) to backward saves its weight permute.  NULL: both
                                                passes permute into the workspace. */
     int32_t flags;                          /* FNM_PLAN_* (fused Fourier layer only), 0 = none */
+    const void* by16;                       /* optional bf16 pairs of by / ayT: [2][rows][LY rounded up to 8] bfloat16 =     */
+    const void* ayT16;                      /* { bf16(t), bf16(t - trunc_tf32(t)) } (see fnm_pointwise_ysyn_ex); NULL: the   */
+                                            /* fused pointwise kernel derives them from the fp32 tile, tile by tile          */
 } fnm_plan;
 
 /* Cached GELU derivative (fused Fourier layer).  GELU'(z) of a layer's output costs ~25 instructions per element; in the
@@ -232,10 +235,14 @@ int fnm_mix_bwd_w(const float* Xh, const float* Gh, float* dw0, float* dw1, int 
 int fnm_pointwise_ysyn(const float* x, int act_in, const float* wc, int wc_is_kn, const float* bias,
                        const float* Z, const float* by, const float* mul_gelu_grad_of, float* out, float* out_act,
                        int64_t rows, int S2, int LY, int K, int N, int mode, fnm_stream_t stream);
-/* the same with FNM_PW_* flags (cached GELU derivative, see above) */
+/* the same with FNM_PW_* flags (cached GELU derivative, see above) and the optional bf16 pair of the table:
+ * by16[2][S2][LY8] bfloat16, LY8 = LY rounded up to 8, = { bf16(by), bf16(by - trunc_tf32(by)) } zero padded.  In
+ * FNM_MODE_FP32 the tcgen05 kernel multiplies as TF32 main product + two bf16 correction products; with by16 the
+ * table's correction operands are TMA-loaded instead of being converted in the kernel for every tile.             */
 int fnm_pointwise_ysyn_ex(const float* x, int act_in, const float* wc, int wc_is_kn, const float* bias,
                           const float* Z, const float* by, const float* mul, float* out, float* out_act,
-                          int64_t rows, int S2, int LY, int K, int N, int mode, int flags, fnm_stream_t stream);
+                          int64_t rows, int S2, int LY, int K, int N, int mode, int flags, const void* by16,
+                          fnm_stream_t stream);
 /* dwc[o][i] = sum_pos g[pos][o] f(x[pos][i]);  dbc[o] = sum_pos g[pos][o]   (conv weight/bias grads) */
 size_t fnm_conv_wgrad_workspace_bytes(int64_t npos, int Ci, int Co);
 int fnm_conv_wgrad(const float* g, const float* x, int act_in, float* dwc, float* dbc, int64_t npos,

@@ -76,8 +76,13 @@ CASES = [
 
 
 @pytest.mark.parametrize("case", CASES, ids=lambda c: "r{rows}_s{S2}_ly{LY}_k{K}_n{N}_a{act}{kn}{bias}{mul}".format(**c))
-@pytest.mark.parametrize("mode", ["fp32", "tf32"])
-def test_pointwise_ysyn(case, mode):
+@pytest.mark.parametrize("mode", ["fp32", "fp32-bf16corr", "fp32-bf16corr-by16", "tf32"])
+def test_pointwise_ysyn(case, mode, monkeypatch):
+    # fp32: the all-TF32 3-pass split (default); fp32-bf16corr: the opt-in bf16 correction passes (FNM_PW2_CORR=bf16),
+    # -by16: with the table's bf16 pair precomputed
+    if mode.startswith("fp32-bf16corr"):
+        monkeypatch.setenv("FNM_PW2_CORR", "bf16")
+        mode = "fp32-by16" if mode.endswith("by16") else "fp32"
     torch.manual_seed(0)
     rows, S2, LY, K, N = case["rows"], case["S2"], case["LY"], case["K"], case["N"]
     x = torch.randn(rows, S2, K, device=DEV) if K else None
@@ -88,9 +93,14 @@ def test_pointwise_ysyn(case, mode):
     mul = torch.randn(rows, S2, N, device=DEV) if case["mul"] else None
     out = torch.full((rows, S2, N), float("nan"), device=DEV)
     out_act = torch.full((rows, S2, N), float("nan"), device=DEV) if not case["mul"] else None
-    check(lib().fnm_pointwise_ysyn(_p(x), case["act"], _p(wc), case["kn"], _p(bias), _p(Z), _p(by), _p(mul), _p(out),
-                                   _p(out_act), rows, S2, LY, K, N, 0 if mode == "fp32" else 1, _stream()),
-          "fnm_pointwise_ysyn")
+    by16 = None
+    if mode == "fp32-by16":                      # the table's bf16 correction operands precomputed (fnm_plan.by16)
+        from fnm_b200.plan import bf16_table_pair
+        by16 = bf16_table_pair(by) if LY > 0 else None
+        mode = "fp32"
+    check(lib().fnm_pointwise_ysyn_ex(_p(x), case["act"], _p(wc), case["kn"], _p(bias), _p(Z), _p(by), _p(mul), _p(out),
+                                      _p(out_act), rows, S2, LY, K, N, 0 if mode == "fp32" else 1, 0, _p(by16), _stream()),
+          "fnm_pointwise_ysyn_ex")
     torch.cuda.synchronize()
     LY_ACTIVE[0] = LY > 0
     ref = _pointwise_ysyn_ref(x, case["act"], wc, case["kn"], bias, Z, by, mul)
@@ -122,7 +132,7 @@ def test_pointwise_ysyn_cached_gelu_derivative(case, mode):
     out = torch.full((rows, S2, N), float("nan"), device=DEV)
     out_act = torch.full((rows, S2, N), float("nan"), device=DEV)
     check(lib().fnm_pointwise_ysyn_ex(_p(x), case["act"], _p(wc), 0, _p(bias), _p(Z), _p(by), None, _p(out), _p(out_act),
-                                      rows, S2, LY, K, N, imode, FNM_PW_OUT_IS_GRAD, _stream()), "fnm_pointwise_ysyn_ex")
+                                      rows, S2, LY, K, N, imode, FNM_PW_OUT_IS_GRAD, None, _stream()), "fnm_pointwise_ysyn_ex")
     torch.cuda.synchronize()
     v = _pointwise_ysyn_ref(x, case["act"], wc, 0, bias, Z, by, None)
     assert rel_l2(out_act, _gelu64(v)) < tol
@@ -136,7 +146,7 @@ def test_pointwise_ysyn_cached_gelu_derivative(case, mode):
     mulK = torch.randn(rows, S2, K, device=DEV)
     gin = torch.full((rows, S2, K), float("nan"), device=DEV)
     check(lib().fnm_pointwise_ysyn_ex(_p(g), 0, _p(wk), 1, None, _p(ZK), _p(by), _p(mulK), _p(gin), None,
-                                      rows, S2, LY, N, K, imode, FNM_PW_MUL_IS_GRAD, _stream()), "fnm_pointwise_ysyn_ex")
+                                      rows, S2, LY, N, K, imode, FNM_PW_MUL_IS_GRAD, None, _stream()), "fnm_pointwise_ysyn_ex")
     torch.cuda.synchronize()
     ref = _pointwise_ysyn_ref(g, 0, wk, 1, None, ZK, by, None) * mulK.double()
     assert rel_l2(gin, ref) < tol

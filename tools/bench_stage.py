@@ -55,8 +55,16 @@ out2 = torch.empty_like(x)
 timeit("pointwise_ysyn fwd +act out (3A)", lambda: check(L.fnm_pointwise_ysyn(p(x), 0, p(wc), 0, p(bias), p(Z), p(tab["by"]), None, p(out), p(out2), rows, P2, LY, C_, C_, 0, st)), 3 * A)
 timeit("pointwise_ysyn bwd tf32", lambda: check(L.fnm_pointwise_ysyn(p(g), 0, p(wc), 1, None, p(Z), p(tab["ayT"]), p(x), p(out), None, rows, P2, LY, C_, C_, 1, st)), 3 * A)
 timeit("pointwise_ysyn bwd (3A)", lambda: check(L.fnm_pointwise_ysyn(p(g), 0, p(wc), 1, None, p(Z), p(tab["ayT"]), p(x), p(out), None, rows, P2, LY, C_, C_, 0, st)), 3 * A)
-timeit("pw_ysyn fwd grad|act out (3A)", lambda: check(L.fnm_pointwise_ysyn_ex(p(x), 0, p(wc), 0, p(bias), p(Z), p(tab["by"]), None, p(out), p(out2), rows, P2, LY, C_, C_, 0, 2, st)), 3 * A)
-timeit("pw_ysyn bwd cached grad (3A)", lambda: check(L.fnm_pointwise_ysyn_ex(p(g), 0, p(wc), 1, None, p(Z), p(tab["ayT"]), p(x), p(out), None, rows, P2, LY, C_, C_, 0, 1, st)), 3 * A)
+os.environ["FNM_PW2_CORR"] = "bf16"
+from fnm_b200.plan import bf16_table_pair
+tab16 = {k: bf16_table_pair(tab[k]) for k in ("by", "ayT")}
+timeit("pw_ysyn fwd noact, bf16 corr", lambda: check(L.fnm_pointwise_ysyn(p(x), 0, p(wc), 0, p(bias), p(Z), p(tab["by"]), None, p(out), None, rows, P2, LY, C_, C_, 0, st)), 2 * A)
+timeit("pw_ysyn bwd (3A), bf16 corr", lambda: check(L.fnm_pointwise_ysyn(p(g), 0, p(wc), 1, None, p(Z), p(tab["ayT"]), p(x), p(out), None, rows, P2, LY, C_, C_, 0, st)), 3 * A)
+timeit("pw_ysyn fwd noact, bf16 corr +by16", lambda: check(L.fnm_pointwise_ysyn_ex(p(x), 0, p(wc), 0, p(bias), p(Z), p(tab["by"]), None, p(out), None, rows, P2, LY, C_, C_, 0, 0, p(tab16["by"]), st)), 2 * A)
+timeit("pw_ysyn bwd cached grad, bf16 corr +by16", lambda: check(L.fnm_pointwise_ysyn_ex(p(g), 0, p(wc), 1, None, p(Z), p(tab["ayT"]), p(x), p(out), None, rows, P2, LY, C_, C_, 0, 1, p(tab16["ayT"]), st)), 3 * A)
+del os.environ["FNM_PW2_CORR"]
+timeit("pw_ysyn fwd grad|act out (3A)", lambda: check(L.fnm_pointwise_ysyn_ex(p(x), 0, p(wc), 0, p(bias), p(Z), p(tab["by"]), None, p(out), p(out2), rows, P2, LY, C_, C_, 0, 2, None, st)), 3 * A)
+timeit("pw_ysyn bwd cached grad (3A)", lambda: check(L.fnm_pointwise_ysyn_ex(p(g), 0, p(wc), 1, None, p(Z), p(tab["ayT"]), p(x), p(out), None, rows, P2, LY, C_, C_, 0, 1, None, st)), 3 * A)
 timeit("ydft (A + T)", lambda: check(L.fnm_ydft(p(x), p(tab["ay"]), p(T), rows, P2, LY, C_, 1, 0, st)), A + T.numel() * 4)
 timeit("ydft noact (A + T)", lambda: check(L.fnm_ydft(p(x), p(tab["ay"]), p(T), rows, P2, LY, C_, 0, 0, st)), A + T.numel() * 4)
 timeit("ydft noact tf32", lambda: check(L.fnm_ydft(p(x), p(tab["ay"]), p(T), rows, P2, LY, C_, 0, 1, st)), A + T.numel() * 4)

@@ -25,16 +25,17 @@ wc = torch.randn(C_, C_, device=dev) / C_ ** 0.5
 bias = torch.randn(C_, device=dev)
 Z = torch.randn(rows, LY, C_, device=dev)
 L = lib()
+B16 = lambda k: p(tab[k]) if k in tab else None          # present with FNM_PW2_CORR=bf16
 mode = 1 if variant == "tf32" else 0
 if len(sys.argv) > 2:
     os.environ["FNM_PW2_DEBUG"] = sys.argv[2]
 for _ in range(3):
     if variant == "act":
-        check(L.fnm_pointwise_ysyn(p(x), 0, p(wc), 0, p(bias), p(Z), p(tab["by"]), None, p(out), p(out2), rows, P2, LY, C_, C_, mode, st))
+        check(L.fnm_pointwise_ysyn_ex(p(x), 0, p(wc), 0, p(bias), p(Z), p(tab["by"]), None, p(out), p(out2), rows, P2, LY, C_, C_, mode, 0, B16("by16"), st))
     elif variant == "bwd":
-        check(L.fnm_pointwise_ysyn(p(x), 0, p(wc), 1, None, p(Z), p(tab["ayT"]), p(out2), p(out), None, rows, P2, LY, C_, C_, mode, st))
+        check(L.fnm_pointwise_ysyn_ex(p(x), 0, p(wc), 1, None, p(Z), p(tab["ayT"]), p(out2), p(out), None, rows, P2, LY, C_, C_, mode, 0, B16("ayT16"), st))
     else:
-        check(L.fnm_pointwise_ysyn(p(x), 0, p(wc), 0, p(bias), p(Z), p(tab["by"]), None, p(out), None, rows, P2, LY, C_, C_, mode, st))
+        check(L.fnm_pointwise_ysyn_ex(p(x), 0, p(wc), 0, p(bias), p(Z), p(tab["by"]), None, p(out), None, rows, P2, LY, C_, C_, mode, 0, B16("by16"), st))
 torch.cuda.synchronize()
 raw = C.CDLL(LIB_PATH)
 if not hasattr(raw, "fnm_debug_pw2_trace"):
