@@ -164,7 +164,7 @@ int fnm_ydft(const float* x, const float* tab, float* T, int64_t rows, int P2, i
              fnm_stream_t stream) {
     FNM_REQUIRE(x && tab && T, "ydft: NULL pointer");
     FNM_REQUIRE(rows >= 0 && P2 > 0 && LY > 0 && C > 0, "ydft: bad extents");
-    if (tc_ydft_tma_supported(x, tab, rows, P2, LY, C, act_in)) return tc_ydft_tma(x, tab, T, rows, P2, LY, mode, as_stream(stream));
+    if (tc_ydft_tma_supported(x, tab, rows, P2, LY, C, act_in)) return tc_ydft_tma(x, tab, T, rows, P2, LY, C, mode, as_stream(stream));
     if (tc_ydft_supported(rows, P2, LY, C)) return tc_ydft(x, tab, T, rows, P2, LY, C, act_in, mode, as_stream(stream));
     return simt_ydft(x, tab, T, rows, P2, LY, C, act_in, as_stream(stream));
 }

@@ -50,7 +50,7 @@ bool tc_ydft_supported(int64_t rows, int P2, int LY, int C);
 int tc_ydft(const float* x, const float* tab, float* T, int64_t rows, int P2, int LY, int C, int act, int mode,
             cudaStream_t st);
 bool tc_ydft_tma_supported(const float* x, const float* tab, int64_t rows, int P2, int LY, int C, int act);
-int tc_ydft_tma(const float* x, const float* tab, float* T, int64_t rows, int P2, int LY, int mode, cudaStream_t st);
+int tc_ydft_tma(const float* x, const float* tab, float* T, int64_t rows, int P2, int LY, int C, int mode, cudaStream_t st);
 bool tc_xdft_supported(int B, int P1, int R, int NY, int C);
 int tc_xdft(const float* T, const float* ex, float* Xh, int B, int P1, int R, int NY, int C, int mode, cudaStream_t st);
 bool tc_resample_supported(int64_t G, int K, int M, int inner, int C);

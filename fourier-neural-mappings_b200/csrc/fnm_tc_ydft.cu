@@ -1,6 +1,10 @@
-// tc_ydft_tma -- the truncated DFT along y of a 128-channel channels-last activation with TMA-fed operands:
+// tc_ydft_tma -- the truncated DFT along y of a channels-last activation with TMA-fed operands:
 //
-//     T[row][l'][c] = sum_y tab[l'][y] * x[row][y][c]          row = (sample, x) grid row, l' < LY <= 64, c < 128
+//     T[row][l'][c] = sum_y tab[l'][y] * x[row][y][c]          row = (sample, x) grid row, l' < LY <= 64, c < C
+//
+// C = 128, or C = 32 / 64 with F = 128 / C consecutive grid rows FOLDED into the 128 TMEM lanes (lane = (row in group,
+// channel): the 32-channel blocks of the A tile are simply TMA-loaded from F different rows; everything below says "row" for
+// such a row group).
 //
 // x[row] is [y][c] with c contiguous: MN-major for the contraction over y, so it is the A operand (M = c, lanes = c)
 // straight from TMA boxes of 32 y x 32 c in the SWIZZLE_128B_BASE32B layout (see fnm_tc_wgrad.cu); the table chunk
@@ -30,9 +34,10 @@ constexpr int kYdThreads = 14 * 32;
 
 struct YdArgs {
     float* out;
-    long long rows;
+    long long rows, groups;                 // grid rows; row groups (F rows each)
     int P2, LY, NT, nch, single_pass;
-    long long pairs;
+    int C, F, gpi;                          // channels, rows folded per group, groups per work item (2: one table chunk serves both)
+    long long pairs;                        // work items
 };
 
 __device__ __forceinline__ uint64_t yd_desc_mn32(uint32_t saddr) {
@@ -85,12 +90,14 @@ ydft_tma(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUten
                 const uint32_t it = q / nch, ch = q - it * nch, s = q % kYdRaw;
                 const long long pair = (long long)blockIdx.x + (long long)it * gridDim.x;
                 mbar_wait(&raw_empty[s], ((q / kYdRaw) & 1) ^ 1);
-                const bool two = pair * 2 + 1 < a.rows;
+                const bool two = a.gpi == 2 && pair * 2 + 1 < a.groups;
                 mbar_expect_tx(&raw_full[s], (two ? 2u : 1u) * kYdATile + 8192u);
                 uint8_t* st = smem + (size_t)s * kYdStage;
+                const int bpr = a.C / 32;                                // 32-channel blocks per grid row
                 for (int j = 0; j < (two ? 2 : 1); ++j)
-                    for (int cb = 0; cb < 4; ++cb)
-                        tma_load_3d(&mapX, &raw_full[s], st + j * kYdATile + cb * 4096, cb * 32, (int)ch * 32, (int)(pair * 2 + j));
+                    for (int cb = 0; cb < 4; ++cb)                       // rows past the end read as zeros (TMA bounds)
+                        tma_load_3d(&mapX, &raw_full[s], st + j * kYdATile + cb * 4096, (cb % bpr) * 32, (int)ch * 32,
+                                    (int)((pair * a.gpi + j) * a.F + cb / bpr));
                 tma_load_2d(&mapT, &raw_full[s], st + 2 * kYdATile, (int)ch * 32, 0);
             }
         }
@@ -141,6 +148,7 @@ ydft_tma(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUten
                 for (int j = 0; j < 2; ++j) {
                     const uint32_t d = tb + (uint32_t)j * 256u + (ch & 1u) * 128u;
                     if (j == 1 && a.single_pass) test_next();
+                    if (j == 1 && a.gpi == 1) break;
 #pragma unroll
                     for (int ks = 0; ks < 4; ++ks)
                         mma(d, (st16 + (uint32_t)(j * (kYdATile >> 4) + ks * 64)) | kALoF, (t16 + 2u * ks) | kBLoF,
@@ -151,6 +159,7 @@ ydft_tma(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUten
                     for (int j = 0; j < 2; ++j) {
                         const uint32_t dc = tb + (uint32_t)j * 256u + (ch & 1u) * 128u + 64u;
                         if (j == 1) test_next();
+                        if (j == 1 && a.gpi == 1) break;
 #pragma unroll
                         for (int ks = 0; ks < 4; ++ks)
                             mma(dc, (lt16 + (uint32_t)(j * (kYdATile >> 4) + ks * 64)) | kALoF, (t16 + 2u * ks) | kBLoF, idesc64, 1u);
@@ -192,6 +201,7 @@ ydft_tma(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUten
         // =========================================================================== epilogue (8 warps)
         const int q4 = warp & 3, half = (warp - 6) >> 2;             // TMEM lane quarter, column half of the 64 table rows
         const int c = q4 * 32 + lane;
+        const int fr = c / a.C, cc = c - fr * a.C;                      // lane = (row within the group, channel)
         const int l0 = half * 32;
         for (uint32_t it = 0; it < (uint32_t)my_pairs; ++it) {
             const long long pair = (long long)blockIdx.x + (long long)it * gridDim.x;
@@ -199,7 +209,8 @@ ydft_tma(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUten
             tc_fence_after();
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
-                const long long row = pair * 2 + j;
+                if (j >= a.gpi) break;
+                const long long row = (pair * a.gpi + j) * a.F + fr;
                 const uint32_t taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)j * 256u + (uint32_t)l0;
                 uint32_t m0[32], m1[32];
                 tmem_ld32(taddr, m0);                               // main of the even chunks
@@ -216,10 +227,10 @@ ydft_tma(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUten
                     for (int i = 0; i < 32; ++i) v[i] += __uint_as_float(m0[i]) + (nch > 1 ? __uint_as_float(m1[i]) : 0.f);
                 }
                 if (row < a.rows) {
-                    float* op = a.out + ((size_t)row * a.LY + l0) * 128 + c;
+                    float* op = a.out + ((size_t)row * a.LY + l0) * a.C + cc;
 #pragma unroll
                     for (int i = 0; i < 32; ++i)
-                        if (l0 + i < a.LY) op[(size_t)i * 128] = v[i];
+                        if (l0 + i < a.LY) op[(size_t)i * a.C] = v[i];
                 }
             }
             tc_fence_before();
@@ -238,21 +249,28 @@ ydft_tma(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUten
 using namespace tc;
 
 bool tc_ydft_tma_supported(const float* x, const float* tab, int64_t rows, int P2, int LY, int C, int act) {
-    if (!tc_enabled() || act != 0 || C != 128 || LY < 8 || LY > 64 || P2 % 4 != 0 || rows < 1 || rows >= (1LL << 30)) return false;
+    if (!tc_enabled() || act != 0 || (C != 128 && C != 64 && C != 32) || LY < 8 || LY > 64 || P2 % 4 != 0 || rows < 1 ||
+        rows >= (1LL << 30))
+        return false;
     if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(tab)) & 15) return false;
+    // an item is a whole (folded) grid row: problems with few long rows (1-D) stay on the segmenting register-path kernel
+    if (C != 128 && rows / (128 / C) < sm_count()) return false;
     const char* e = getenv("FNM_YDFT_NO_TMA");
     return !(e && e[0] == '1');
 }
 
-int tc_ydft_tma(const float* x, const float* tab, float* T, int64_t rows, int P2, int LY, int mode, cudaStream_t st) {
+int tc_ydft_tma(const float* x, const float* tab, float* T, int64_t rows, int P2, int LY, int C, int mode, cudaStream_t st) {
     YdArgs a{};
     a.out = T; a.rows = rows; a.P2 = P2; a.LY = LY; a.NT = (LY + 15) / 16 * 16; a.nch = (P2 + 31) / 32;
     a.single_pass = mode == FNM_MODE_TF32;
-    a.pairs = (rows + 1) / 2;
+    a.C = C; a.F = 128 / C;
+    a.groups = (rows + a.F - 1) / a.F;
+    a.gpi = a.groups >= 4LL * sm_count() ? 2 : 1;            // pair the groups when there are enough of them to keep every SM busy
+    a.pairs = (a.groups + a.gpi - 1) / a.gpi;
     CUtensorMap mx, mt;
     {
-        const cuuint64_t dims[3] = {128, (cuuint64_t)P2, (cuuint64_t)rows};
-        const cuuint64_t str[2] = {128 * 4, (cuuint64_t)P2 * 128 * 4};
+        const cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)P2, (cuuint64_t)rows};
+        const cuuint64_t str[2] = {(cuuint64_t)C * 4, (cuuint64_t)P2 * C * 4};
         const cuuint32_t box[3] = {32, 32, 1};
         if (!tc_make_map_swz(&mx, x, 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return fail(FNM_ECUDA, "ydft: tensor map (x) failed");
     }

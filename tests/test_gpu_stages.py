@@ -195,6 +195,12 @@ TAB_CASES = [
     dict(B=3, P1=7, P2=100, R=6, NY=12, C=128),
     dict(B=1, P1=5, P2=36, R=4, NY=5, C=128),
     dict(B=2, P1=9, P2=28, R=2, NY=3, C=128),
+    # 32 / 64 channels folded into the 128 lanes of the TMA-fed ydft (4 / 2 grid rows per group; it takes over once there are
+    # at least as many groups as SMs): single groups, paired groups with a ragged last group and a half-empty last pair
+    dict(B=9, P1=72, P2=72, R=24, NY=12, C=32),
+    dict(B=5, P1=144, P2=144, R=32, NY=17, C=64),
+    dict(B=11, P1=119, P2=40, R=8, NY=6, C=64),
+    dict(B=21, P1=119, P2=36, R=8, NY=4, C=32),
     # ... and the TMA-fed xdft (even P1): one ragged chunk, two chunks, rows of the next sample behind the last chunk
     dict(B=3, P1=10, P2=24, R=6, NY=4, C=128),
     dict(B=2, P1=22, P2=32, R=8, NY=5, C=128),
