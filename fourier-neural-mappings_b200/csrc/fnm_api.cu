@@ -335,6 +335,37 @@ int fnm_counter_inc(int32_t* counter, fnm_stream_t stream) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// F2V local branch in one pass (fc1 + GELU + trapezoid-weighted sum)
+// ------------------------------------------------------------------------------------------------
+size_t fnm_local_functional_workspace_bytes(int B, int P1, int P2, int K, int N) {
+    const int parts = tc_local_functional_parts((int64_t)B * P1, P2, K, N);
+    return parts > 0 ? align_up((size_t)B * P1 * parts * N * sizeof(float), 256) : 0;
+}
+
+int fnm_local_functional_fwd(const float* x, const float* w1, const float* b1, const float* wx, const float* wy, float* S,
+                             int B, int P1, int P2, int K, int N, void* workspace, size_t workspace_bytes, int mode,
+                             fnm_stream_t stream) {
+    FNM_REQUIRE(x && w1 && wx && wy && S && workspace, "local_functional_fwd: NULL pointer");
+    FNM_REQUIRE(B > 0 && P1 > 0 && P2 > 0 && K > 0 && N > 0, "local_functional_fwd: bad extents");
+    const int64_t rows = (int64_t)B * P1;
+    if (!tc_local_functional_supported(rows, P2, K, N, x)) return fail(FNM_ENOTSUP, "local_functional_fwd: shape not served");
+    const int parts = tc_local_functional_parts(rows, P2, K, N);
+    if (workspace_bytes < fnm_local_functional_workspace_bytes(B, P1, P2, K, N)) return fail(FNM_EWORKSPACE, "local_functional_fwd: workspace too small");
+    float* partial = static_cast<float*>(workspace);
+    FNM_TRY(tc_local_functional(x, w1, b1, wx, wy, nullptr, partial, rows, P1, P2, K, N, mode, as_stream(stream)));
+    return batch_reduce(partial, S, B, P1 * parts, N, "local_functional_reduce", as_stream(stream));
+}
+
+int fnm_local_functional_bwd(const float* x, const float* w1, const float* b1, const float* wx, const float* wy, const float* gS,
+                             float* g_h1, int B, int P1, int P2, int K, int N, int mode, fnm_stream_t stream) {
+    FNM_REQUIRE(x && w1 && wx && wy && gS && g_h1, "local_functional_bwd: NULL pointer");
+    FNM_REQUIRE(B > 0 && P1 > 0 && P2 > 0 && K > 0 && N > 0, "local_functional_bwd: bad extents");
+    const int64_t rows = (int64_t)B * P1;
+    if (!tc_local_functional_supported(rows, P2, K, N, x)) return fail(FNM_ENOTSUP, "local_functional_bwd: shape not served");
+    return tc_local_functional(x, w1, b1, wx, wy, gS, g_h1, rows, P1, P2, K, N, mode, as_stream(stream));
+}
+
+// ------------------------------------------------------------------------------------------------
 // fused Fourier layer
 // ------------------------------------------------------------------------------------------------
 size_t fnm_fourier_layer_shadow_bytes(const fnm_plan* plan) {

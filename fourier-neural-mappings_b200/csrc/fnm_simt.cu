@@ -694,4 +694,33 @@ int mode_reduce(const float* src, const float* cc, float* out, int nmodes, int n
     return check_launch(what);
 }
 
+//   batch reduce: out[b][n] = sum_{j < J} in[b][j][n]; 32 outputs x 8 groups of j per CTA, fixed summation order
+__global__ void __launch_bounds__(256) batch_reduce_kernel(const float* __restrict__ in, float* __restrict__ out, int J, int N) {
+    __shared__ float part[8][33];
+    const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
+    const int n = blockIdx.x * 32 + lane;
+    const float* src = in + (size_t)blockIdx.y * J * N;
+    float acc = 0.f;
+    if (n < N)
+        for (int j = grp; j < J; j += 8) acc += __ldg(src + (size_t)j * N + n);
+    part[grp][lane] = acc;
+    __syncthreads();
+    if (grp == 0 && n < N) {
+        float s = 0.f;
+#pragma unroll
+        for (int g = 0; g < 8; ++g) s += part[g][lane];
+        out[(size_t)blockIdx.y * N + n] = s;
+    }
+}
+
+int batch_reduce(const float* in, float* out, int B, int J, int N, const char* what, cudaStream_t st) {
+    if (B <= 0 || N <= 0) return FNM_OK;
+    if (B > 65535) return fail(FNM_ENOTSUP, "%s: batch extent %d exceeds the grid limit", what, B);
+    {
+        LaunchScope ls(what, st);
+        batch_reduce_kernel<<<dim3((N + 31) / 32, B), 256, 0, st>>>(in, out, J, N);
+    }
+    return check_launch(what);
+}
+
 }  // namespace fnm

@@ -36,6 +36,7 @@ int simt_ldec_bwd_v(const float* Gh, const float* w, float* dv, float* partial, 
 // real (B, C) matrix <-> planar per-mode spectrum (F2V / V2F ends on the mixing kernels)
 int mode_spread(const float* src, const float* cc, float* dst, int nmodes, int n, const char* what, cudaStream_t st);
 int mode_reduce(const float* src, const float* cc, float* out, int nmodes, int n, const char* what, cudaStream_t st);
+int batch_reduce(const float* in, float* out, int B, int J, int N, const char* what, cudaStream_t st);   // out[b][n] = sum_j in[b][j][n]
 
 // ---- optimiser / elementwise (fnm_adam.cu)
 int adam_launch(int n, float* const* p, const float* const* g, float* const* m, float* const* v, float* const* vmax,
@@ -76,6 +77,10 @@ bool tc_pw2_supported(int64_t rows, int S2, int LY, int K, int N, int act, const
 int tc_pw2(const float* x, const float* wc, int wc_is_kn, const float* bias, const float* Z, const float* by,
            const float* mul, float* out, float* out_act, int64_t rows, int S2, int LY, int K, int N, int mode,
            cudaStream_t st, int by_ld = 0, int flags = 0, const void* by16 = nullptr);
+bool tc_local_functional_supported(int64_t rows, int S2, int K, int N, const void* x);
+int tc_local_functional_parts(int64_t rows, int S2, int K, int N);
+int tc_local_functional(const float* x, const float* w1, const float* b1, const float* wx, const float* wy, const float* gS,
+                        float* out, int64_t rows, int P1, int S2, int K, int N, int mode, cudaStream_t st);
 int tc_set_sm_limit(int n);                // fnm_set_sm_limit
 bool tc_pointwise_ysyn_supported(int64_t rows, int S2, int LY, int K, int N);
 int tc_pointwise_ysyn(const float* x, int act, const float* wc, int wc_is_kn, const float* bias, const float* Z,

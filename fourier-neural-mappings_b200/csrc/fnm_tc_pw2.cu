@@ -48,6 +48,10 @@ struct PwArgs2 {
     int by16;                                        // the bf16 pair of the by tile comes from a precomputed table (TMA)
     uint32_t lo_bytes;                               // one remainder buffer: fp32 lo tile, or {bf16(B) | bf16(B_lo)}
     int mul_raw, out_grad;                           // FNM_PW_MUL_IS_GRAD / FNM_PW_OUT_IS_GRAD (see include/fnm_b200.h)
+    // F2V local branch (fnm_local_functional_*): wsum = 1: out[row][seg][half][o] = wx[x] sum_y wy[y] GELU(v) (nothing spatial
+    // is written); wsum = 2: out = gS[b][o] wx[x] wy[y] GELU'(v).  row = b * P1w + x.
+    int wsum, P1w;
+    const float* wx; const float* wy; const float* gS;
     uint32_t tmem0;                                  // always 0: the TMEM base as a kernel parameter (see the MMA issuer)
 };
 
@@ -316,7 +320,9 @@ __device__ __forceinline__ void pw2_mma_loop(const PwArgs2& a, const PwBars& B, 
 // streams through once per tile, and ncu showed those warps stalled on instruction fetch for 40 % of their samples
 // while pacing the whole kernel.  The GELU' operand of step c+1 is loaded while step c is computed.
 // HAS_MUL: 0 none, 1 multiply by GELU'(mul), 2 multiply by mul (a cached derivative); HAS_ACT: 0 none, 1 out_act = GELU(out),
-// 2 out = GELU'(v) and out_act = GELU(v) from one rcp / ex2 pair (the next layer's backward then multiplies without any math)
+// 2 out = GELU'(v) and out_act = GELU(v) from one rcp / ex2 pair (the next layer's backward then multiplies without any math),
+// 3 trapezoid-weighted GELU sum over the row (F2V local branch: one partial per (row, segment, column half, channel), no
+// spatial store), 4 its gradient out = gS[b][o] wx[x] wy[y] GELU'(v)
 template <int HAS_MUL, int HAS_ACT>
 __device__ __forceinline__ void pw2_epilogue(const PwArgs2& a, int warp, int lane, uint32_t tmem_base, int my_units,
                                              uint64_t* acc_full, uint64_t* acc_empty) {
@@ -335,6 +341,12 @@ __device__ __forceinline__ void pw2_epilogue(const PwArgs2& a, int warp, int lan
         const int t0 = seg * a.seg_tiles, t1 = min(a.tiles_per_row, t0 + a.seg_tiles);
         const long long row = (long long)rg * a.F + fr;
         const bool o_ok = o < a.CO && row < a.rows;
+        float wsum_acc = 0.f, wrow = 0.f;                           // HAS_ACT 3 / 4: running sum, wx[x] (times gS[b][o])
+        if (HAS_ACT >= 3 && o_ok) {
+            const long long bb = row / a.P1w;
+            wrow = __ldg(a.wx + (int)(row - bb * a.P1w));
+            if (HAS_ACT == 4) wrow *= __ldg(a.gS + bb * a.COo + oo);
+        }
         for (int tile = t0; tile < t1; ++tile, ++t) {
             const uint32_t acc = t & 1;
             const int yb = tile * a.NT + half * hc;                 // first position of this warp's columns
@@ -404,7 +416,7 @@ __device__ __forceinline__ void pw2_epilogue(const PwArgs2& a, int warp, int lan
                 }
                 tmem_ld_wait();
                 float* op = a.out + base + (size_t)(c * 8) * cstride;
-                float* ap = HAS_ACT ? a.out_act + base + (size_t)(c * 8) * cstride : nullptr;
+                float* ap = (HAS_ACT == 1 || HAS_ACT == 2) ? a.out_act + base + (size_t)(c * 8) * cstride : nullptr;
                 float v[8];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
@@ -415,6 +427,17 @@ __device__ __forceinline__ void pw2_epilogue(const PwArgs2& a, int warp, int lan
 #ifdef FNM_PW2_DEBUG_SWITCHES
                 if ((a.debug & 1) && v[0] != 123.456f) continue;
 #endif
+                if (HAS_ACT >= 3) {
+                    // F2V local branch: the weights of the 8 positions are warp-uniform loads
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int y = yb + c * 8 + j;
+                        const float wyj = (c * 8 + j < nv) ? __ldg(a.wy + y) : 0.f;
+                        if (HAS_ACT == 3) wsum_acc = fmaf(wyj, gelu_fast(v[j]), wsum_acc);
+                        else v[j] = wrow * wyj * gelu_grad_fast(v[j]);
+                    }
+                    if (HAS_ACT == 3) continue;
+                }
                 float ga[8];
                 if (HAS_ACT == 2) {
 #pragma unroll
@@ -426,7 +449,7 @@ __device__ __forceinline__ void pw2_epilogue(const PwArgs2& a, int warp, int lan
                 if (full) {
 #pragma unroll
                     for (int j = 0; j < 8; ++j) *at_w(op, offs[j]) = v[j];
-                    if (HAS_ACT) {
+                    if (HAS_ACT == 1 || HAS_ACT == 2) {
 #pragma unroll
                         for (int j = 0; j < 8; ++j) *at_w(ap, offs[j]) = ga[j];
                     }
@@ -435,7 +458,7 @@ __device__ __forceinline__ void pw2_epilogue(const PwArgs2& a, int warp, int lan
                     for (int j = 0; j < 8; ++j) {
                         if (c * 8 + j < nv) {
                             *at_w(op, offs[j]) = v[j];
-                            if (HAS_ACT) *at_w(ap, offs[j]) = ga[j];
+                            if (HAS_ACT == 1 || HAS_ACT == 2) *at_w(ap, offs[j]) = ga[j];
                         }
                     }
                 }
@@ -445,6 +468,8 @@ __device__ __forceinline__ void pw2_epilogue(const PwArgs2& a, int warp, int lan
             if (lane == 0) mbar_arrive(&acc_empty[acc]);
             if (warp == 10) PW2_TRACE(t, 9);
         }
+        if (HAS_ACT == 3 && o_ok)                                   // one partial per (row, segment, column half, channel)
+            a.out[(((size_t)row * a.nseg + seg) * 2 + half) * a.COo + oo] = wrow * wsum_acc;
     }
 }
 
@@ -733,8 +758,10 @@ pw2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUt
         // =========================================================================== epilogue (8 warps)
         // explicitly specialised on (GELU' operand, GELU copy): with the flags tested per element the loop is
         // 2x slower, and whether ptxas unswitches it on its own changes with unrelated edits (measured)
-        const int mm = a.mul ? (a.mul_raw ? 2 : 1) : 0, am = a.out_act ? (a.out_grad ? 2 : 1) : 0;
-        if (mm == 0 && am == 0) pw2_epilogue<0, 0>(a, warp, lane, tmem_base, my_units, acc_full, acc_empty);
+        const int mm = a.mul ? (a.mul_raw ? 2 : 1) : 0, am = a.wsum ? 2 + a.wsum : (a.out_act ? (a.out_grad ? 2 : 1) : 0);
+        if (am == 3) pw2_epilogue<0, 3>(a, warp, lane, tmem_base, my_units, acc_full, acc_empty);
+        else if (am == 4) pw2_epilogue<0, 4>(a, warp, lane, tmem_base, my_units, acc_full, acc_empty);
+        else if (mm == 0 && am == 0) pw2_epilogue<0, 0>(a, warp, lane, tmem_base, my_units, acc_full, acc_empty);
         else if (mm == 0 && am == 1) pw2_epilogue<0, 1>(a, warp, lane, tmem_base, my_units, acc_full, acc_empty);
         else if (mm == 0 && am == 2) pw2_epilogue<0, 2>(a, warp, lane, tmem_base, my_units, acc_full, acc_empty);
         else if (mm == 1 && am == 0) pw2_epilogue<1, 0>(a, warp, lane, tmem_base, my_units, acc_full, acc_empty);
@@ -935,6 +962,48 @@ int tc_pw2(const float* x, const float* wc, int wc_is_kn, const float* bias, con
         pw2_kernel<<<grid, kPwThreads, smem < 120 * 1024 ? 120 * 1024 : smem, st>>>(mx, mb, mz, mb16, a);
     }
     return check_launch("pointwise_ysyn");
+}
+
+// F2V local branch on the fused pointwise kernel (no spectral term): the hidden tensor h1 = fc1(x) never reaches HBM.
+//   forward : partial[row][seg][half][h] = wx[x] sum_{y in segment half} wy[y] GELU(h1[row][y][h])
+//   backward: g_h1[row][y][h] = gS[b][h] wx[x] wy[y] GELU'(h1[row][y][h])      (h1 recomputed from x)
+bool tc_local_functional_supported(int64_t rows, int S2, int K, int N, const void* x) {
+    return tc_pw2_supported(rows, S2, 0, K, N, 0, x, nullptr, nullptr);
+}
+
+int tc_local_functional_parts(int64_t rows, int S2, int K, int N) {      // partials per (row, channel): 2 * segments
+    PwArgs2 a{};
+    if (!pw2_configure(a, rows, S2, 0, K, N)) return 0;
+    return 2 * a.nseg;
+}
+
+int tc_local_functional(const float* x, const float* w1, const float* b1, const float* wx, const float* wy, const float* gS,
+                        float* out, int64_t rows, int P1, int S2, int K, int N, int mode, cudaStream_t st) {
+    PwArgs2 a{};
+    if (!pw2_configure(a, rows, S2, 0, K, N, 0, mode)) return fail(FNM_ENOTSUP, "local_functional: shape not served by the TMA kernel");
+    a.wc = w1; a.bias = b1; a.mul = nullptr; a.out = out; a.out_act = nullptr; a.wc_is_kn = 0;
+    a.single_pass = mode == FNM_MODE_TF32;
+    a.wsum = gS ? 2 : 1; a.P1w = P1; a.wx = wx; a.wy = wy; a.gS = gS;
+    CUtensorMap mx;
+    const cuuint64_t dims[3] = {(cuuint64_t)a.CIo, (cuuint64_t)a.S2, (cuuint64_t)rows};
+    const cuuint64_t str[2] = {(cuuint64_t)a.CIo * 4, (cuuint64_t)a.S2 * a.CIo * 4};
+    const cuuint32_t box[3] = {32, (cuuint32_t)a.NT, 1};
+    if (!tc_make_map(&mx, x, 3, dims, str, box, true)) return fail(FNM_ECUDA, "local_functional: tensor map (x) failed");
+    const size_t smem = (size_t)a.stages * a.stage_bytes + (size_t)a.nlo * a.lo_bytes + (size_t)a.nz * a.z_bytes + 1024 + 512;
+    static std::atomic<uint64_t> attr_set{0};
+    int attr_set_dev = 0;
+    if (once_needed(attr_set, attr_set_dev)) {
+        const cudaError_t e = cudaFuncSetAttribute(pw2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return fail(FNM_ECUDA, "local_functional: smem attribute: %s", cudaGetErrorString(e));
+        once_done(attr_set, attr_set_dev);
+    }
+    const int grid = a.units < sm_count() ? a.units : sm_count();
+    const char* what = gS ? "local_functional_bwd" : "local_functional_fwd";
+    {
+        LaunchScope ls(what, st);
+        pw2_kernel<<<grid, kPwThreads, smem < 120 * 1024 ? 120 * 1024 : smem, st>>>(mx, mx, mx, mx, a);
+    }
+    return check_launch(what);
 }
 
 }  // namespace fnm

@@ -17,6 +17,9 @@ from ..shared import projector1d, projector2d
 # FNM_CACHE_GELU_GRAD=0 keeps z between fused layers (the derivative is then evaluated in the consumer's backward)
 _CACHE_GELU_GRAD = os.environ.get("FNM_CACHE_GELU_GRAD", "1") != "0"
 
+# FNM_ONE_PASS_LOCAL=0: F2V local branch as fc1 kernel + weighted-sum kernel (the hidden tensor is materialised)
+_ONE_PASS_LOCAL = os.environ.get("FNM_ONE_PASS_LOCAL", "1") != "0"
+
 _TORCH_ACTS = {"tanh": torch.tanh, "relu": F.relu, "elu": F.elu, "leaky_relu": F.leaky_relu}
 
 
@@ -189,12 +192,15 @@ def functional_end(state, lfunc0, mlpfunc0, head, one_d):
         # trapezoid-weighted GELU sum; fc2 is linear, so it commutes with the integration and acts on (B, H)
         wy = _trapz_weights(P2, z.device)
         wx = _trapz_weights(P1, z.device) if not one_d else torch.ones(1, device=z.device)
-        if state.act and state.x is not None:
-            # fc1 reads the cached GELU(z); its backward multiplies the input gradient by GELU'(z) in the epilogue
-            h1 = ops.pointwise_conv(state.x, fc1.weight, fc1.bias, zpre=z, zpre_is_grad=state.zgrad)
+        cached = state.act and state.x is not None
+        xin = state.x if cached else state.value()
+        if _ONE_PASS_LOCAL and fc1.bias is not None and ops.local_functional_supported(xin, fc1.weight):
+            # fc1 + GELU + integration in ONE kernel: the (B, P1, P2, width_final) hidden tensor is never written in forward
+            S = ops.local_functional(xin, fc1.weight, fc1.bias, wx, wy, zpre=z if cached else None, zpre_is_grad=state.zgrad)
         else:
-            h1 = ops.pointwise_conv(state.value(), fc1.weight, fc1.bias)
-        S = ops.weighted_gelu_sum(h1, wx, wy)
+            # fc1 reads the cached GELU(z); its backward multiplies the input gradient by GELU'(z) in the epilogue
+            h1 = ops.pointwise_conv(xin, fc1.weight, fc1.bias, zpre=z if cached else None, zpre_is_grad=state.zgrad)
+            S = ops.weighted_gelu_sum(h1, wx, wy)
         h = F.linear(S, fc2.weight)
         if fc2.bias is not None:
             h = h + fc2.bias * (((P2 - 1.0) / P2) * (1.0 if one_d else (P1 - 1.0) / P1))   # integral of the constant

@@ -584,6 +584,65 @@ class WeightedGeluSumFn(torch.autograd.Function):
         return g, None, None
 
 
+class LocalFunctionalFn(torch.autograd.Function):
+    """S[b, h] = sum_{x,y} wx[x] wy[y] GELU(fc1(x)[b, x, y, h]) in one pass: fc1 on the tcgen05 pointwise kernel whose
+    epilogue integrates (func_to_vec2d.py:100-104 without the hidden tensor).  ``zpre`` as in PointwiseConvFn: ``x`` is then
+    the cached GELU(zpre) and the input gradient goes to ``zpre``.  backward recomputes fc1 from ``x``."""
+
+    @staticmethod
+    @_on_tensor_device
+    def forward(ctx, x, w1, b1, wx, wy, zpre=None, zpre_is_grad=False):
+        _need_cuda(x, w1, b1, wx, wy, zpre)
+        x, w1, b1 = _f32c(x), _f32c(w1), _f32c(b1)
+        B, P1, P2, Ci = x.shape
+        H = w1.shape[0]
+        S = torch.empty((B, H), dtype=torch.float32, device=x.device)
+        L = lib()
+        ws = _workspace(x.device, L.fnm_local_functional_workspace_bytes(B, P1, P2, Ci, H))
+        check(L.fnm_local_functional_fwd(_ptr(x), _ptr(w1), _ptr(b1), _ptr(wx), _ptr(wy), _ptr(S), B, P1, P2, Ci, H,
+                                         _ptr(ws), ws.numel(), _MODE, _stream()), "fnm_local_functional_fwd")
+        ctx.save_for_backward(x, w1, b1, wx, wy, _f32c(zpre) if zpre is not None else None)
+        ctx.zpre_is_grad = bool(zpre_is_grad) and zpre is not None
+        return S
+
+    @staticmethod
+    @_on_tensor_device
+    def backward(ctx, gS):
+        x, w1, b1, wx, wy, zpre = ctx.saved_tensors
+        B, P1, P2, Ci = x.shape
+        H = w1.shape[0]
+        L = lib()
+        g = torch.empty((B, P1, P2, H), dtype=torch.float32, device=x.device)
+        check(L.fnm_local_functional_bwd(_ptr(x), _ptr(w1), _ptr(b1), _ptr(wx), _ptr(wy), _ptr(_f32c(gS)), _ptr(g), B, P1, P2,
+                                         Ci, H, _MODE, _stream()), "fnm_local_functional_bwd")
+        dx = dw = db = None
+        if ctx.needs_input_grad[5] if zpre is not None else ctx.needs_input_grad[0]:
+            dx = torch.empty_like(x)
+            check(L.fnm_pointwise_ysyn_ex(_ptr(g), 0, _ptr(w1), 1, None, None, None, _ptr(zpre), _ptr(dx), None, B * P1, P2, 0,
+                                          H, Ci, _MODE, _lib.FNM_PW_MUL_IS_GRAD if ctx.zpre_is_grad else 0, None, _stream()),
+                  "fnm_pointwise_ysyn_ex")
+        if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
+            npos = B * P1 * P2
+            dw = torch.empty_like(w1)
+            db = torch.empty((H,), dtype=torch.float32, device=x.device)
+            ws = _workspace(x.device, L.fnm_conv_wgrad_workspace_bytes(npos, Ci, H))
+            check(L.fnm_conv_wgrad(_ptr(g), _ptr(x), 0, _ptr(dw), _ptr(db), npos, Ci, H, _ptr(ws), ws.numel(), _MODE,
+                                   _stream()), "fnm_conv_wgrad")
+        if zpre is not None:
+            return None, dw, db, None, None, dx, None
+        return dx, dw, db, None, None, None, None
+
+
+def local_functional_supported(x, w1):
+    """Whether the one-pass F2V local branch serves this shape (otherwise: pointwise_conv + weighted_gelu_sum)."""
+    B, P1, P2, Ci = x.shape
+    return x.is_cuda and lib().fnm_local_functional_workspace_bytes(B, P1, P2, Ci, w1.shape[0]) > 0 and B <= 65535
+
+
+def local_functional(x, w1, b1, wx, wy, zpre=None, zpre_is_grad=False):
+    return LocalFunctionalFn.apply(x, w1, b1, wx, wy, zpre, zpre_is_grad)
+
+
 def weighted_gelu_sum(h1, wx, wy):
     return WeightedGeluSumFn.apply(h1, wx, wy)
 

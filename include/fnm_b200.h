@@ -272,6 +272,19 @@ int fnm_mlp_head_bwd(const float* h1, const float* g_out, const float* w2, float
  *      torch.trapz.  fc2 is linear, so only S[b][h] = sum_{x,y} wx[x] wy[y] GELU(h1[b][x][y][h]) touches the field
  *      (h1 = fc1 output, fnm_pointwise_ysyn with LY = 0); wx / wy hold the trapezoid weights dx*(1/2, 1, ..., 1, 1/2).
  *      backward: g_h1 = gS[b][h] wx[x] wy[y] GELU'(h1).                                                           */
+/* The same branch in ONE pass over the layer's activation (no (B, P1, P2, H) tensor in forward at all):
+ *   S[b][h] = sum_{x,y} wx[x] wy[y] GELU( sum_i w1[h][i] x[b][x][y][i] + b1[h] )
+ * fc1 runs on the tcgen05 pointwise kernel and its epilogue integrates; returns FNM_ENOTSUP for shapes that kernel does
+ * not serve (the caller then uses fnm_pointwise_ysyn + fnm_wsum_gelu_fwd).  backward recomputes h1 from x and writes
+ *   g_h1[b][x][y][h] = gS[b][h] wx[x] wy[y] GELU'(h1)
+ * from which fnm_pointwise_ysyn (input gradient) and fnm_conv_wgrad (dW1, db1) proceed as for any pointwise layer.   */
+size_t fnm_local_functional_workspace_bytes(int B, int P1, int P2, int K, int N);
+int fnm_local_functional_fwd(const float* x, const float* w1, const float* b1, const float* wx, const float* wy, float* S,
+                             int B, int P1, int P2, int K, int N, void* workspace, size_t workspace_bytes, int mode,
+                             fnm_stream_t stream);
+int fnm_local_functional_bwd(const float* x, const float* w1, const float* b1, const float* wx, const float* wy,
+                             const float* gS, float* g_h1, int B, int P1, int P2, int K, int N, int mode,
+                             fnm_stream_t stream);
 size_t fnm_wsum_gelu_workspace_bytes(int B, int H);
 int fnm_wsum_gelu_fwd(const float* h1, const float* wx, const float* wy, float* S, int B, int P1, int P2, int H,
                       void* workspace, size_t workspace_bytes, fnm_stream_t stream);

@@ -792,3 +792,33 @@ def test_ends_mode_major_weights_match_reference_ordered_weights(end, width):
     assert rel_l2(mod.weights.grad, wref.grad) < TOL_FP32
     gx_r = xcl.grad.permute(0, 3, 1, 2) if end == "f2v" else xcl.grad
     assert rel_l2(x.grad, gx_r) < TOL_FP32
+
+
+@pytest.mark.parametrize("family", ["fnf2d", "fnf1d", "fnn2d"])
+def test_one_pass_local_branch_matches_the_two_kernel_form(family):
+    """The F2V end's local branch (mlpfunc0 + trapz) in one kernel against fc1 kernel + weighted-sum kernel."""
+    from fnm_b200.models import _trunk
+    torch.manual_seed(5)
+    if family == "fnf2d":
+        model = fnm_b200.FNF2d(6, 6, 32, d_in=1, d_out=2, n_layers=3).to(DEV)
+        x = torch.randn(3, 1, 40, 32, device=DEV)
+    elif family == "fnf1d":
+        model = fnm_b200.FNF1d(8, 64, d_in=1, d_out=2, n_layers=3).to(DEV)
+        x = torch.randn(3, 1, 256, device=DEV)
+    else:
+        model = fnm_b200.FNN2d(5, 3, s_latentspace=(24, 24), modes1=6, modes2=6, width=32, n_layers=4).to(DEV)
+        x = torch.randn(3, 5, device=DEV)
+    res = {}
+    for on in (True, False):
+        old = _trunk._ONE_PASS_LOCAL
+        _trunk._ONE_PASS_LOCAL = on
+        try:
+            model.zero_grad(set_to_none=True)
+            out = model(x)
+            out.square().sum().backward()
+            res[on] = (out.detach().clone(), {k: p.grad.detach().clone() for k, p in model.named_parameters()})
+        finally:
+            _trunk._ONE_PASS_LOCAL = old
+    assert rel_l2(res[True][0], res[False][0]) < 2e-6
+    for k in res[True][1]:
+        assert rel_l2(res[True][1][k], res[False][1][k]) < 5e-6, k

@@ -422,3 +422,35 @@ def test_gelu_kernels():
     zz = z.clone().requires_grad_(True)
     fnm_b200.ops.gelu(zz).backward(g)
     assert rel_l2(zz.grad, g.double() * _gelu_grad64(z.double())) < 1e-6
+
+
+@pytest.mark.parametrize("B,P1,P2,K,H", [(3, 20, 24, 32, 128), (2, 1, 50, 64, 128), (5, 9, 57, 32, 128), (2, 248, 57, 32, 128),
+                                         (4, 7, 72, 32, 64)])
+@pytest.mark.parametrize("mode", ["fp32", "tf32"])
+def test_local_functional_one_pass(B, P1, P2, K, H, mode):
+    """fnm_local_functional_fwd / _bwd: fc1 + GELU + trapezoid-weighted sum in one pass (and its gradient with fc1
+    recomputed) against float64 (include/fnm_b200.h; func_to_vec2d.py:100-104)."""
+    torch.manual_seed(4)
+    L = lib()
+    imode = 0 if mode == "fp32" else 1
+    tol = TOL_FP32 if mode == "fp32" else TOL_TF32
+    x = torch.randn(B, P1, P2, K, device=DEV)
+    w1 = torch.randn(H, K, device=DEV) / K ** 0.5
+    b1 = torch.randn(H, device=DEV)
+    wx = torch.rand(P1, device=DEV) + 0.5
+    wy = torch.rand(P2, device=DEV) + 0.5
+    nbytes = L.fnm_local_functional_workspace_bytes(B, P1, P2, K, H)
+    assert nbytes > 0
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=DEV)
+    S = torch.full((B, H), float("nan"), device=DEV)
+    check(L.fnm_local_functional_fwd(_p(x), _p(w1), _p(b1), _p(wx), _p(wy), _p(S), B, P1, P2, K, H, _p(ws), ws.numel(), imode,
+                                     _stream()), "fnm_local_functional_fwd")
+    h1 = torch.einsum("bxyk,hk->bxyh", x.double(), w1.double()) + b1.double()
+    ref = torch.einsum("x,y,bxyh->bh", wx.double(), wy.double(), _gelu64(h1))
+    assert rel_l2(S, ref) < tol
+    gS = torch.randn(B, H, device=DEV)
+    g = torch.full((B, P1, P2, H), float("nan"), device=DEV)
+    check(L.fnm_local_functional_bwd(_p(x), _p(w1), _p(b1), _p(wx), _p(wy), _p(gS), _p(g), B, P1, P2, K, H, imode, _stream()),
+          "fnm_local_functional_bwd")
+    gref = torch.einsum("bh,x,y,bxyh->bxyh", gS.double(), wx.double(), wy.double(), _gelu_grad64(h1))
+    assert rel_l2(g, gref) < tol
