@@ -34,7 +34,6 @@ constexpr int kPwThreads = 18 * 32;
 constexpr int kPwMmaWarp = 1;
 constexpr int kPwMaxStages = 6;
 constexpr uint32_t kPwSmemBudget = 226 * 1024;
-constexpr bool kPwEarlyRaw = false;          // issue the next tile's raw passes while the converters finish this one (see the issuer)
 
 struct PwArgs2 {
     const float* wc; const float* bias; const float* mul; float* out; float* out_act;
@@ -226,7 +225,6 @@ __device__ __forceinline__ void pw2_mma_loop(const PwArgs2& a, const PwBars& B, 
     // and drags every value derived from it out of the uniform registers)
     uint32_t t = 0, s = 0, sph = 0;
     bool tile_ready = false;                                      // this tile's accumulator and stage were seen complete early
-    bool raw_done = false;                                        // ... and its raw passes are already in the queue
     int unit = (int)blockIdx.x;
     for (int u = 0; u < my_units; ++u, unit += (int)gridDim.x) {
         int t0, t1;
@@ -240,9 +238,7 @@ __device__ __forceinline__ void pw2_mma_loop(const PwArgs2& a, const PwBars& B, 
         for (int tile = t0; tile < t1; ++tile, ++t) {
             uint64_t* a2_bar = (has_z && tile == t0) ? &B.a2_full[ub] : nullptr;
             const uint32_t acc = t & 1;
-            const bool had_raw = raw_done;                          // this tile's raw pass was issued during the previous tile
-            raw_done = false;
-            if (!had_raw && !tile_ready) {
+            if (!tile_ready) {
                 mbar_wait_warp(&B.acc_empty[acc], ((t >> 1) & 1) ^ 1);
                 mbar_wait_warp(&B.full[s], sph);
             }
@@ -253,8 +249,8 @@ __device__ __forceinline__ void pw2_mma_loop(const PwArgs2& a, const PwBars& B, 
             // `uniform base + immediate`, one UIADD3 away from its UTCHMMA
             const uint32_t tmem_base = uniform_u32(a.tmem0 + (t & 0u));
             const uint32_t d = tmem_base + kD0 + acc * 64u;
-            const uint32_t a2w = na2 == 2 ? 64u : 128u;             // columns of one Z^T buffer: hi | lo (or hi | lo16 | hi16)
-            const uint32_t a2hi = tmem_base + a2off, a2lo = a2hi + a2w / 2;
+            const uint32_t a2hi = tmem_base + a2off, a2lo = a2hi + (na2 == 2 ? 32u : 64u);      // lo, or (lo16 | hi16)
+            const uint32_t x_lo = uniform_u32(desc_lo(sbase + s * a.stage_bytes)), by_lo = x_lo + xb16;
             const uint32_t lb = a.nlo == 2 ? (t & 1) : 0u;
             const uint32_t xl_lo = uniform_u32(desc_lo(lo_base0 + lb * a.lo_bytes)), byl_lo = xl_lo + xb16;
             // the next tile's stage / accumulator
@@ -263,41 +259,27 @@ __device__ __forceinline__ void pw2_mma_loop(const PwArgs2& a, const PwBars& B, 
             const bool more = t + 1 < total;
             // The hooks only TEST (non-blocking): a barrier that is not complete yet is awaited where it is needed, as
             // before -- blocking here would tie this tile's completion to the NEXT tile's data and cost a pipeline stage.
+            // (Issuing the next tile's raw passes while the converters still work on this one was measured at config 5 and
+            // dropped: 0.59 -> 0.62 ms forward; the accumulator's completion is then signalled behind 24 more queued MMAs.)
             bool next_ready = false, lo_ready = false;
             auto test_next = [&]() {
                 next_ready = more && mbar_test_warp(&B.acc_empty[acc ^ 1u], (((t + 1) >> 1) & 1) ^ 1) && mbar_test_warp(&B.full[s1], sph1);
             };
             auto test_lo = [&]() { lo_ready = mbar_test_warp(&B.lo_full[lb], a.nlo == 2 ? ((t >> 1) & 1) : (t & 1)); };
-            // raw passes of accumulator `dd` from stage `ss`: (A_hi [+ A_lo]) * B_raw
-            auto raw_pass = [&](uint32_t dd, uint32_t ss, uint64_t* zbar) {
-                const uint32_t x_lo = uniform_u32(desc_lo(sbase + ss * a.stage_bytes)), by_lo = x_lo + xb16;
-                if (SINGLE) pw2_issue_raw<K1S, NKS2, true>(dd, tmem_base, a2hi, a2lo, x_lo, by_lo, slab16, idesc, a.K1slabs, nks2, zbar, upar, test_next);
-                else if (CORR16) pw2_issue_raw<K1S, NKS2, true>(dd, tmem_base, a2hi, a2lo, x_lo, by_lo, slab16, idesc, a.K1slabs, nks2, zbar, upar, test_lo);
-                else pw2_issue_raw<K1S, NKS2, false>(dd, tmem_base, a2hi, a2lo, x_lo, by_lo, slab16, idesc, a.K1slabs, nks2, zbar, upar, test_lo);
-                umma_commit(&B.empty[ss]);                          // the raw tile is free once the raw passes retire
-            };
-            if (!had_raw) raw_pass(d, s, a2_bar);
+            // raw passes: (A_hi [+ A_lo]) * B_raw
+            if (SINGLE) pw2_issue_raw<K1S, NKS2, true>(d, tmem_base, a2hi, a2lo, x_lo, by_lo, slab16, idesc, a.K1slabs, nks2, a2_bar, upar, test_next);
+            else if (CORR16) pw2_issue_raw<K1S, NKS2, true>(d, tmem_base, a2hi, a2lo, x_lo, by_lo, slab16, idesc, a.K1slabs, nks2, a2_bar, upar, test_lo);
+            else pw2_issue_raw<K1S, NKS2, false>(d, tmem_base, a2hi, a2lo, x_lo, by_lo, slab16, idesc, a.K1slabs, nks2, a2_bar, upar, test_lo);
+            umma_commit(&B.empty[s]);                              // the raw tile is free once the raw passes retire
             PW2_TRACE(t, 2);
             if (!SINGLE) {
-                if (had_raw) test_lo();
-                // The converters are still working on this tile: issue the NEXT tile's raw passes first (other accumulator,
-                // next stage) when both are free -- within a grid row only (a new row's Z^T may have to wait for this
-                // tile's remainder pass to release the operand buffer).
-                // (Measured at config 5 and switched off: 0.59 -> 0.62 ms forward, 0.73 -> 0.77 ms backward -- the accumulator's
-                // completion is then signalled behind the next tile's 24 queued MMAs and the epilogue starts later.)
-                if (kPwEarlyRaw && !lo_ready && tile + 1 < t1 && mbar_test_warp(&B.acc_empty[acc ^ 1u], (((t + 1) >> 1) & 1) ^ 1) &&
-                    mbar_test_warp(&B.full[s1], sph1)) {
-                    tc_fence_after();
-                    raw_pass(tmem_base + kD0 + (acc ^ 1u) * 64u, s1, nullptr);
-                    raw_done = true;
-                }
                 // remainder pass: A_hi * B_lo
                 if (!lo_ready) mbar_wait_warp(&B.lo_full[lb], a.nlo == 2 ? ((t >> 1) & 1) : (t & 1));
                 tc_fence_after();
                 if (CORR16)
                     pw2_issue_lo16<(K1S >= 0 ? 2 * K1S : -1), (NKS2 >= 0 ? (NKS2 + 1) / 2 : -1)>(
-                        d, tmem_base, a2lo, a2lo + a2w / 4, xl_lo, xl_lo + byh_off, xl_lo + half16, xl_lo + half16 + byh_off, slab16,
-                        idesc16, n16_1, n16_2, test_next);
+                        d, tmem_base, a2lo, a2lo + (na2 == 2 ? 16u : 32u), xl_lo, xl_lo + byh_off, xl_lo + half16,
+                        xl_lo + half16 + byh_off, slab16, idesc16, n16_1, n16_2, test_next);
                 else
                     pw2_issue_lo<K1S, NKS2>(d, tmem_base, a2hi, xl_lo, byl_lo, slab16, idesc, a.K1slabs, nks2, test_next);
                 umma_commit(&B.lo_empty[lb]);
@@ -473,6 +455,10 @@ __device__ __forceinline__ void pw2_epilogue(const PwArgs2& a, int warp, int lan
     }
 }
 
+// CORR16: the opt-in bf16-correction variant as its own instantiation, so that the default kernel's code (register allocation,
+// scheduling of the Z and converter warps) does not depend on it: with run-time `corr16` branches in one kernel the default
+// path lost 25 % at the 32-channel shapes.
+template <bool CORR16>
 __global__ void __launch_bounds__(kPwThreads, 1)
 pw2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapBy,
            const __grid_constant__ CUtensorMap mapZ, const __grid_constant__ CUtensorMap mapBy16, const PwArgs2 a) {
@@ -503,7 +489,7 @@ pw2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUt
     if (threadIdx.x == 0) {
         for (int s = 0; s < a.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], a.single_pass ? 1 : 5); }
         // remainder tile complete: the 4 converter warps (+ the producer's expect_tx when the table's bf16 pair is TMA-loaded)
-        for (int s = 0; s < 2; ++s) { mbar_init(&lo_full[s], a.by16 ? 5 : 4); mbar_init(&lo_empty[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&lo_full[s], (CORR16 && a.by16) ? 5 : 4); mbar_init(&lo_empty[s], 1); }
         for (int s = 0; s < 4; ++s) { mbar_init(&z_full[s], 1); mbar_init(&z_empty[s], 4); }
         for (int s = 0; s < 2; ++s) { mbar_init(&a2_full[s], 4); mbar_init(&a2_empty[s], 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 8); }
@@ -531,7 +517,7 @@ pw2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUt
                 if (o < a.CO && k < a.CI && ro == rk)
                     v[j] = a.wc_is_kn ? __ldg(a.wc + (size_t)ii * a.COo + oo) : __ldg(a.wc + (size_t)oo * a.CIo + ii);
             }
-            if (a.corr16) split_to_tmem16_corr16(lane_base + kA1Hi + k0, lane_base + kA1Lo16 + k0 / 2, lane_base + kA1Hi16 + k0 / 2, v);
+            if (CORR16) split_to_tmem16_corr16(lane_base + kA1Hi + k0, lane_base + kA1Lo16 + k0 / 2, lane_base + kA1Hi16 + k0 / 2, v);
             else split_to_tmem16(lane_base + kA1Hi + k0, lane_base + kA1Lo + k0, v, !a.single_pass);
         }
         tmem_st_wait();
@@ -580,7 +566,7 @@ pw2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUt
                         tma_load_2d(&mapBy, &full[s], st + a.x_bytes + (size_t)kb * a.NT * 128, kb * 32, y0);
                 }
             }
-        } else if (lane == 1 && a.by16) {
+        } else if (CORR16 && lane == 1 && a.by16) {
             // second producer lane: the bf16(by) | bf16(by_lo) tiles of every tile column, from the precomputed table pair
             // straight into the remainder buffers (paced by lo_empty, independently of the raw stages lane 0 runs ahead with)
             const uint32_t half = a.lo_bytes / 2, slab_b = (uint32_t)a.NT * 128u;
@@ -615,16 +601,16 @@ pw2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUt
         bool done = false;
 #define PW2_LOOP(K1, K2)                                                                                                 \
         if (!done && a.K1slabs == K1 && nks2 == K2) {                                                                    \
-            if (a.single_pass) pw2_mma_loop<K1, K2, 1>(a, B, sbase, lo_base0, my_units, na2, has_z);                     \
-            else if (a.corr16) pw2_mma_loop<K1, K2, 2>(a, B, sbase, lo_base0, my_units, na2, has_z);                     \
+            if (CORR16) pw2_mma_loop<K1, K2, 2>(a, B, sbase, lo_base0, my_units, na2, has_z);                            \
+            else if (a.single_pass) pw2_mma_loop<K1, K2, 1>(a, B, sbase, lo_base0, my_units, na2, has_z);                \
             else pw2_mma_loop<K1, K2, 0>(a, B, sbase, lo_base0, my_units, na2, has_z);                                   \
             done = true;                                                                                                 \
         }
         PW2_SHAPES(PW2_LOOP)
 #undef PW2_LOOP
         if (!done) {
-            if (a.single_pass) pw2_mma_loop<-1, -1, 1>(a, B, sbase, lo_base0, my_units, na2, has_z);
-            else if (a.corr16) pw2_mma_loop<-1, -1, 2>(a, B, sbase, lo_base0, my_units, na2, has_z);
+            if (CORR16) pw2_mma_loop<-1, -1, 2>(a, B, sbase, lo_base0, my_units, na2, has_z);
+            else if (a.single_pass) pw2_mma_loop<-1, -1, 1>(a, B, sbase, lo_base0, my_units, na2, has_z);
             else pw2_mma_loop<-1, -1, 0>(a, B, sbase, lo_base0, my_units, na2, has_z);
         }
     } else if (warp >= 2 && warp < 6) {
@@ -649,7 +635,7 @@ pw2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUt
                     const int kk = l0 + j;                                        // each row of the group brings its own Z tile
                     v[j] = (c_ok && kk < a.LY) ? zsb[(zr * a.LY + kk) * a.COo + zo] : 0.f;
                 }
-                if (a.corr16) split_to_tmem16_corr16(lane_base + a2hi + l0, lane_base + a2lo + l0 / 2, lane_base + a2lo + a2w / 4 + l0 / 2, v);
+                if (CORR16) split_to_tmem16_corr16(lane_base + a2hi + l0, lane_base + a2lo + l0 / 2, lane_base + a2lo + a2w / 4 + l0 / 2, v);
                 else split_to_tmem16(lane_base + a2hi + l0, lane_base + a2lo + l0, v, !a.single_pass);
             }
             tmem_st_wait();
@@ -671,7 +657,7 @@ pw2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUt
                     const uint32_t lb = a.nlo == 2 ? (t & 1) : 0u;
                     mbar_wait(&lo_empty[lb], (a.nlo == 2 ? ((t >> 1) & 1) : (t & 1)) ^ 1);
                     if (warp == 6) PW2_TRACE(t, 5);
-                    if (a.corr16) {
+                    if (CORR16) {
                         // two bf16 tiles: bf16(B) and bf16(B - trunc(B)).  Warp w converts the `up = w & 1` half of every
                         // 64-channel output slab, i.e. fp32 slab 2 so + up whole: lane = (row, q) reads the row's chunks 2q, 2q + 1
                         // (8 channels) and writes output chunk 4 up + q.  Rows of a quarter-warp differ by XOR 5 in their low bits,
@@ -952,14 +938,16 @@ int tc_pw2(const float* x, const float* wc, int wc_is_kn, const float* bias, con
     static std::atomic<uint64_t> attr_set{0};
     int attr_set_dev = 0;
     if (once_needed(attr_set, attr_set_dev)) {
-        const cudaError_t e = cudaFuncSetAttribute(pw2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(pw2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(pw2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return fail(FNM_ECUDA, "pointwise_ysyn: smem attribute: %s", cudaGetErrorString(e));
         once_done(attr_set, attr_set_dev);
     }
     const int grid = a.units < sm_count() ? a.units : sm_count();
     {
         LaunchScope ls(LY > 0 ? "pointwise_ysyn" : "pointwise_conv", st);
-        pw2_kernel<<<grid, kPwThreads, smem < 120 * 1024 ? 120 * 1024 : smem, st>>>(mx, mb, mz, mb16, a);
+        if (a.corr16) pw2_kernel<true><<<grid, kPwThreads, smem < 120 * 1024 ? 120 * 1024 : smem, st>>>(mx, mb, mz, mb16, a);
+        else pw2_kernel<false><<<grid, kPwThreads, smem < 120 * 1024 ? 120 * 1024 : smem, st>>>(mx, mb, mz, mb16, a);
     }
     return check_launch("pointwise_ysyn");
 }
@@ -993,7 +981,8 @@ int tc_local_functional(const float* x, const float* w1, const float* b1, const 
     static std::atomic<uint64_t> attr_set{0};
     int attr_set_dev = 0;
     if (once_needed(attr_set, attr_set_dev)) {
-        const cudaError_t e = cudaFuncSetAttribute(pw2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(pw2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(pw2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return fail(FNM_ECUDA, "local_functional: smem attribute: %s", cudaGetErrorString(e));
         once_done(attr_set, attr_set_dev);
     }
@@ -1001,7 +990,8 @@ int tc_local_functional(const float* x, const float* w1, const float* b1, const 
     const char* what = gS ? "local_functional_bwd" : "local_functional_fwd";
     {
         LaunchScope ls(what, st);
-        pw2_kernel<<<grid, kPwThreads, smem < 120 * 1024 ? 120 * 1024 : smem, st>>>(mx, mx, mx, mx, a);
+        if (a.corr16) pw2_kernel<true><<<grid, kPwThreads, smem < 120 * 1024 ? 120 * 1024 : smem, st>>>(mx, mx, mx, mx, a);
+        else pw2_kernel<false><<<grid, kPwThreads, smem < 120 * 1024 ? 120 * 1024 : smem, st>>>(mx, mx, mx, mx, a);
     }
     return check_launch(what);
 }
