@@ -31,8 +31,10 @@ ws = torch.empty(L.fnm_conv_wgrad_workspace_bytes(rows * P2, C_, C_), dtype=torc
 dwc, dbc = torch.empty(C_, C_, device=dev), torch.empty(C_, device=dev)
 for _ in range(reps):
     check(L.fnm_pointwise_ysyn(p(x), 0, p(wc), 0, p(bias), p(Z), p(tab["by"]), None, p(out), None, rows, P2, LY, C_, C_, 0, st))
-    check(L.fnm_pointwise_ysyn(p(x), 0, p(wc), 0, p(bias), p(Z), p(tab["by"]), None, p(out), p(out2), rows, P2, LY, C_, C_, 0, st))
-    check(L.fnm_pointwise_ysyn(p(g), 0, p(wc), 1, None, p(Z), p(tab["ayT"]), p(x), p(out), None, rows, P2, LY, C_, C_, 0, st))
+    # what the trunk runs since round 2: forward writes GELU'(z) | GELU(z) (FNM_PW_OUT_IS_GRAD = 2), backward multiplies by the
+    # cached derivative (FNM_PW_MUL_IS_GRAD = 1)
+    check(L.fnm_pointwise_ysyn_ex(p(x), 0, p(wc), 0, p(bias), p(Z), p(tab["by"]), None, p(out), p(out2), rows, P2, LY, C_, C_, 0, 2, None, st))
+    check(L.fnm_pointwise_ysyn_ex(p(g), 0, p(wc), 1, None, p(Z), p(tab["ayT"]), p(x), p(out), None, rows, P2, LY, C_, C_, 0, 1, None, st))
     check(L.fnm_ydft(p(x), p(tab["ay"]), p(T), rows, P2, LY, C_, 0, 0, st))
     check(L.fnm_xdft(p(T), p(tab["ex"]), p(Xh), B, P1, R, NY, C_, 0, st))
     check(L.fnm_xsyn(p(Xh), p(tab["fx"]), p(Z), B, P1, R, NY, C_, 0, st))
