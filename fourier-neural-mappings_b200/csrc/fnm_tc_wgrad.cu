@@ -241,7 +241,9 @@ __global__ void __launch_bounds__(kCwThreads, 1) conv_wgrad_tc(const CwArgs a) {
 // the `fold` diagonal blocks of the (fold*C) x (fold*C) result.
 __global__ void conv_wgrad_tc_reduce(const float* __restrict__ part, int nparts, int Ci, int Co, int fold,
                                      float* __restrict__ dwc, float* __restrict__ dbc) {
-    // one warp per output element; lanes stride over (partial, diagonal block) and shuffle-reduce
+    // one warp per output element; lanes stride over (partial, diagonal block) and shuffle-reduce.  (A coalesced
+    // 32-outputs x 32-groups block was measured slower at config 1: 13 vs 9 us -- the partials are L2 resident and the
+    // 1056 warps of this form spread over every SM.)
     const int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     const int Cif = Ci * fold, Cof = Co * fold;
     const size_t stride = cw_part_floats(Cif, Cof);
