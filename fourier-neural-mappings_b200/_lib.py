@@ -74,6 +74,9 @@ PROTOTYPES = {
     "fnm_mlp_head_fwd": (_i32, [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _vp]),
     "fnm_mlp_head_bwd_workspace_bytes": (_sz, [_i32, _i32]),
     "fnm_mlp_head_bwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _vp, _sz, _vp]),
+    "fnm_rel_l2_workspace_bytes": (_sz, [_i32]),
+    "fnm_rel_l2_fwd": (_i32, [_vp, _vp, _vp, _vp, _i32, _i64, C.c_float, _vp, _sz, _vp]),
+    "fnm_rel_l2_bwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _i32, _i64, _vp]),
     "fnm_local_functional_workspace_bytes": (_sz, [_i32] * 5),
     "fnm_local_functional_fwd": (_i32, [_vp] * 6 + [_i32] * 5 + [_vp, _sz, _i32, _vp]),
     "fnm_local_functional_bwd": (_i32, [_vp] * 7 + [_i32] * 5 + [_i32, _vp]),

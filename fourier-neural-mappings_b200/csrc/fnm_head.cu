@@ -389,6 +389,84 @@ constexpr int kEndBlocks = 148 * 4;
 
 static bool lift_ok(int Din, int C, int ngrid) { return Din >= 0 && Din + ngrid >= 1 && Din + ngrid <= kLiftMaxJ && C % 4 == 0 && C >= 4 && C <= 1024; }
 
+// ---- training loss of the reference harness: LpLoss(size_average=False) = sum_b ||out_b - y_b||_2 / (||y_b||_2 + eps)
+// (util/utilities_module.py:188-204; train_fno.py:98).  Three launches instead of the ~12 elementwise / reduction kernels the
+// torch statement and its autograd graph take -- what the launch-bound small configurations notice.
+constexpr int kLossChunks = 64;                     // partial sums per sample
+
+__global__ void __launch_bounds__(256) rel_l2_partial_kernel(const float* __restrict__ out, const float* __restrict__ y,
+                                                            float* __restrict__ part, long long n, int vec) {
+    // grid (chunk, sample): part[b][chunk] = (sum (out - y)^2, sum y^2) over the chunk's strided float4 groups
+    // (vec == 0: sample rows are not 16-byte aligned, everything goes through the scalar tail on chunk 0)
+    const long long base = (long long)blockIdx.y * n;
+    float sn = 0.f, sd = 0.f;
+    const long long n4 = vec ? n / 4 : 0;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n4; i += (long long)gridDim.x * 256) {
+        const float4 a = *reinterpret_cast<const float4*>(out + base + 4 * i), b = *reinterpret_cast<const float4*>(y + base + 4 * i);
+        const float d0 = a.x - b.x, d1 = a.y - b.y, d2 = a.z - b.z, d3 = a.w - b.w;
+        sn += d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
+        sd += b.x * b.x + b.y * b.y + b.z * b.z + b.w * b.w;
+    }
+    if (blockIdx.x == 0 || !vec)
+        for (long long i = 4 * n4 + (vec ? 0 : (long long)blockIdx.x * 256) + threadIdx.x; i < n; i += (vec ? 256 : (long long)gridDim.x * 256)) {
+            const float a = out[base + i], b = y[base + i];
+            sn += (a - b) * (a - b);
+            sd += b * b;
+        }
+    __shared__ float s0[8], s1[8];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) { sn += __shfl_xor_sync(0xffffffffu, sn, d); sd += __shfl_xor_sync(0xffffffffu, sd, d); }
+    if ((threadIdx.x & 31) == 0) { s0[threadIdx.x >> 5] = sn; s1[threadIdx.x >> 5] = sd; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float tn = 0.f, td = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) { tn += s0[w]; td += s1[w]; }
+        part[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 2 + 0] = tn;
+        part[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 2 + 1] = td;
+    }
+}
+
+// one block: per-sample norms, coef[b] = 1 / (||out_b - y_b|| (||y_b|| + eps)) (0 where the numerator vanishes: the subgradient
+// torch.norm's backward uses), loss = sum_b ||.|| / (||y_b|| + eps) in sample order (deterministic)
+__global__ void __launch_bounds__(256) rel_l2_finish_kernel(const float* __restrict__ part, int nchunks, int B, float eps,
+                                                           float* __restrict__ loss, float* __restrict__ coef) {
+    __shared__ float terms[256];
+    float acc = 0.f;
+    for (int b0 = 0; b0 < B; b0 += 256) {
+        const int b = b0 + threadIdx.x;
+        float t = 0.f;
+        if (b < B) {
+            float sn = 0.f, sd = 0.f;
+            for (int c = 0; c < nchunks; ++c) { sn += part[((size_t)b * nchunks + c) * 2]; sd += part[((size_t)b * nchunks + c) * 2 + 1]; }
+            const float num = sqrtf(sn), den = sqrtf(sd) + eps;
+            t = num / den;
+            coef[b] = num > 0.f ? 1.f / (num * den) : 0.f;
+        }
+        terms[threadIdx.x] = t;
+        __syncthreads();
+        if (threadIdx.x == 0)
+            for (int i = 0; i < 256 && b0 + i < B; ++i) acc += terms[i];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *loss = acc;
+}
+
+__global__ void __launch_bounds__(256) rel_l2_bwd_kernel(const float* __restrict__ out, const float* __restrict__ y,
+                                                        const float* __restrict__ coef, const float* __restrict__ gloss,
+                                                        float* __restrict__ gout, long long n, int vec) {
+    const long long base = (long long)blockIdx.y * n;
+    const float c = __ldg(coef + blockIdx.y) * __ldg(gloss);
+    const long long n4 = vec ? n / 4 : 0;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n4; i += (long long)gridDim.x * 256) {
+        const float4 a = *reinterpret_cast<const float4*>(out + base + 4 * i), b = *reinterpret_cast<const float4*>(y + base + 4 * i);
+        *reinterpret_cast<float4*>(gout + base + 4 * i) = make_float4(c * (a.x - b.x), c * (a.y - b.y), c * (a.z - b.z), c * (a.w - b.w));
+    }
+    if (blockIdx.x == 0 || !vec)
+        for (long long i = 4 * n4 + (vec ? 0 : (long long)blockIdx.x * 256) + threadIdx.x; i < n; i += (vec ? 256 : (long long)gridDim.x * 256))
+            gout[base + i] = c * (out[base + i] - y[base + i]);
+}
+
 }  // namespace fnm
 
 using namespace fnm;
@@ -552,6 +630,50 @@ int fnm_wsum_gelu_bwd(const float* h1, const float* wx, const float* wy, const f
         wsum_bwd_kernel<<<dim3(gx, B), 256, 0, as_stream(stream)>>>(a);
     }
     return check_launch("wsum_gelu_bwd");
+}
+
+size_t fnm_rel_l2_workspace_bytes(int B) { return align_up((size_t)(B > 0 ? B : 0) * kLossChunks * 2 * sizeof(float), 256); }
+
+int fnm_rel_l2_fwd(const float* out, const float* y, float* loss, float* coef, int B, int64_t n, float eps, void* workspace,
+                   size_t workspace_bytes, fnm_stream_t stream) {
+    FNM_REQUIRE(out && y && loss && coef && workspace, "rel_l2_fwd: NULL pointer");
+    FNM_REQUIRE(B > 0 && B <= 65535 && n > 0, "rel_l2_fwd: bad extents");
+    if (workspace_bytes < fnm_rel_l2_workspace_bytes(B)) return fail(FNM_EWORKSPACE, "rel_l2_fwd: workspace too small");
+    if ((reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(y)) & 3) return fail(FNM_ENOTSUP, "rel_l2_fwd: unaligned tensors");
+    // float4 path when every sample row starts on a 16-byte boundary, scalar path otherwise
+    const int vec = !(((reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(y)) & 15) || (n % 4 != 0 && B > 1));
+    cudaStream_t st = as_stream(stream);
+    const long long want = ((vec ? n / 4 : n) + 255) / 256;
+    const int chunks = (int)(want < 1 ? 1 : (want < kLossChunks ? want : kLossChunks));
+    float* part = static_cast<float*>(workspace);
+    {
+        LaunchScope ls("rel_l2_partial", st);
+        rel_l2_partial_kernel<<<dim3(chunks, B), 256, 0, st>>>(out, y, part, n, vec);
+    }
+    FNM_TRY(check_launch("rel_l2_partial"));
+    {
+        LaunchScope ls("rel_l2_finish", st);
+        rel_l2_finish_kernel<<<1, 256, 0, st>>>(part, chunks, B, eps, loss, coef);
+    }
+    return check_launch("rel_l2_finish");
+}
+
+int fnm_rel_l2_bwd(const float* out, const float* y, const float* coef, const float* gloss, float* gout, int B, int64_t n,
+                   fnm_stream_t stream) {
+    FNM_REQUIRE(out && y && coef && gloss && gout, "rel_l2_bwd: NULL pointer");
+    FNM_REQUIRE(B > 0 && B <= 65535 && n > 0, "rel_l2_bwd: bad extents");
+    if ((reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(gout)) & 3)
+        return fail(FNM_ENOTSUP, "rel_l2_bwd: unaligned tensors");
+    const int vec = !(((reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(gout)) & 15) ||
+                      (n % 4 != 0 && B > 1));
+    cudaStream_t st = as_stream(stream);
+    const long long want = ((vec ? n / 4 : n) + 255) / 256;
+    const int gx = (int)(want < 1 ? 1 : (want < 148 * 8 ? want : 148 * 8));
+    {
+        LaunchScope ls("rel_l2_bwd", st);
+        rel_l2_bwd_kernel<<<dim3(gx, B), 256, 0, st>>>(out, y, coef, gloss, gout, n, vec);
+    }
+    return check_launch("rel_l2_bwd");
 }
 
 }  // extern "C"

@@ -460,7 +460,10 @@ conv_wgrad_tma(const __grid_constant__ CUtensorMap mapG, const __grid_constant__
 static int cw_grid(int64_t npos, bool for_workspace = false) {
     const int64_t chunks = (npos + 31) / 32;
     const int sms = for_workspace ? sm_count_max() : sm_count();     // the workspace must hold any later SM budget
-    return (int)(chunks < sms ? chunks : sms);
+    // at least 16 chunks per CTA: on the small L2-resident problems every extra CTA is one more 66 KB partial for the
+    // reduction kernel, while the main kernel's time is its prologue either way
+    const int64_t want = (chunks + 15) / 16;
+    return (int)(want < 1 ? 1 : (want < sms ? want : sms));
 }
 
 }  // namespace tc

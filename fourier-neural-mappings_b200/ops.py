@@ -81,9 +81,20 @@ def _grad_sink(w):
     if sink is None or not (torch.is_grad_enabled() and w.requires_grad):
         return None
     if w._fnm_sink_uses:
-        raise RuntimeError("direct gradient sinks need every spectral weight to enter one autograd Function per "
+        raise RuntimeError("direct gradient sinks need every weight to enter one autograd Function per "
                            "step (and FlatGradients.zero_() before each backward)")
     w._fnm_sink_uses = 1
+    return sink
+
+
+def _real_sink(p):
+    """Sink of a real (conv / linear) parameter as a tensor the kernels can write densely, or None."""
+    sink = _grad_sink(p)
+    if sink is None:
+        return None
+    if not sink.is_contiguous():                               # cannot happen for the flat buffer's views of contiguous parameters
+        p._fnm_sink_uses = 0
+        return None
     return sink
 
 
@@ -176,7 +187,7 @@ class FourierLayerFn(torch.autograd.Function):
         ctx.save_for_backward(xk, _f32c(zin) if cached else None, w0, w1, wc, xh)
         ctx.tables, ctx.kact, ctx.has_bias = tables, kact, bc is not None
         ctx.pre_is_grad = bool(pre_is_grad)
-        ctx.sinks = sinks
+        ctx.sinks = tuple(sinks) + (None,) * (4 - len(sinks))
         ctx.w_version = (w0._version, w1._version if w1 is not None else 0)
         # the GELU copy carries no gradient: without this autograd would MATERIALISE a zero tensor of its size
         # (one activation-sized fill per layer) just to hand it to backward
@@ -206,7 +217,7 @@ class FourierLayerFn(torch.autograd.Function):
         need_x, _, need_w0, need_w1, need_wc, need_bc = ctx.needs_input_grad[:6]
         g_in = torch.empty_like(xk) if need_x else None
         want_w = need_w0 or (w1 is not None and need_w1)
-        s0, s1 = ctx.sinks
+        s0, s1, swc, sbc = ctx.sinks
         w0r, w1r, plan.w_layout = _spectral_weights(w0, w1)
         # gradients in the memory order the kernels were told the weights have; a sink in another order gets a copy
         mm = plan.w_layout == _lib.FNM_W_MODE_MAJOR
@@ -219,8 +230,10 @@ class FourierLayerFn(torch.autograd.Function):
             return torch.empty_like(w, memory_format=torch.preserve_format if mm else torch.contiguous_format)
 
         dw0, dw1 = grad_buffer(s0, w0), grad_buffer(s1, w1)
-        dwc = torch.empty_like(wc) if (wc is not None and need_wc) else None
-        dbc = torch.empty((Co,), dtype=torch.float32, device=xk.device) if (ctx.has_bias and need_bc) else None
+        # conv weight / bias: straight into their sinks when the flat gradient buffer registered them
+        dwc = (swc if swc is not None else torch.empty_like(wc)) if (wc is not None and need_wc) else None
+        dbc = (sbc if sbc is not None else torch.empty((Co,), dtype=torch.float32, device=xk.device)) \
+            if (ctx.has_bias and need_bc) else None
         wcc = _f32c(wc.reshape(Co, Ci)) if wc is not None else None
         L = lib()
         nbytes = L.fnm_fourier_layer_workspace_bytes(C.byref(plan))
@@ -237,8 +250,8 @@ class FourierLayerFn(torch.autograd.Function):
             ready = getattr(sink, "_fnm_on_ready", None) if sink is not None else None
             if ready is not None:
                 ready()                                             # FlatGradients(overlap=True): start this slot's exchange
-        return (g_in, None, None if s0 is not None else dw0, None if s1 is not None else dw1, dwc, dbc, None, None, None, None,
-                None, None)
+        return (g_in, None, None if s0 is not None else dw0, None if s1 is not None else dw1,
+                None if swc is not None else dwc, None if sbc is not None else dbc, None, None, None, None, None, None)
 
 
 class LinearFunctionalFn(torch.autograd.Function):
@@ -372,8 +385,9 @@ class LiftFn(torch.autograd.Function):
 
     @staticmethod
     @_on_tensor_device
-    def forward(ctx, x, w, b, P1, P2, ngrid):
+    def forward(ctx, x, w, b, P1, P2, ngrid, sinks=(None, None)):
         _need_cuda(x, w, b)
+        ctx.sinks = sinks
         x, w, b = _f32c(x), _f32c(w), _f32c(b)
         B, Din, N1, N2 = x.shape
         Cw = w.shape[0]
@@ -391,13 +405,14 @@ class LiftFn(torch.autograd.Function):
         B, Din, N1, N2, P1, P2, Cw, ngrid = ctx.dims
         g = _f32c(g)
         J = Din + ngrid
-        dw = torch.empty((Cw, J), dtype=torch.float32, device=g.device)
-        db = torch.empty((Cw,), dtype=torch.float32, device=g.device)
+        sw, sb = ctx.sinks
+        dw = sw if sw is not None else torch.empty((Cw, J), dtype=torch.float32, device=g.device)
+        db = sb if sb is not None else torch.empty((Cw,), dtype=torch.float32, device=g.device)
         L = lib()
         ws = _workspace(g.device, L.fnm_lift_bwd_workspace_bytes(Cw, J))
         check(L.fnm_lift_bwd(_ptr(g), _ptr(x), _ptr(dw), _ptr(db), B, Din, N1, N2, P1, P2, Cw, ngrid,
                              _ptr(ws), ws.numel(), _stream()), "fnm_lift_bwd")
-        return None, dw, db, None, None, None
+        return None, None if sw is not None else dw, None if sb is not None else db, None, None, None, None
 
 
 class PointwiseConvFn(torch.autograd.Function):
@@ -409,9 +424,10 @@ class PointwiseConvFn(torch.autograd.Function):
 
     @staticmethod
     @_on_tensor_device
-    def forward(ctx, x, w, b, zpre=None, zpre_is_grad=False):
+    def forward(ctx, x, w, b, zpre=None, zpre_is_grad=False, sinks=(None, None)):
         _need_cuda(x, w, b, zpre)
         ctx.zpre_is_grad = bool(zpre_is_grad) and zpre is not None
+        ctx.sinks = sinks
         x, w = _f32c(x), _f32c(w)
         B, P1, P2, Ci = x.shape
         Co = w.shape[0]
@@ -436,18 +452,20 @@ class PointwiseConvFn(torch.autograd.Function):
             check(L.fnm_pointwise_ysyn_ex(_ptr(g), 0, _ptr(w), 1, None, None, None, _ptr(zpre), _ptr(dx), None, B * P1, P2, 0,
                                           Co, Ci, _MODE, _lib.FNM_PW_MUL_IS_GRAD if ctx.zpre_is_grad else 0, None, _stream()),
                   "fnm_pointwise_ysyn_ex")
+        sw, sb = ctx.sinks
         if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
             npos = B * P1 * P2
-            dw = torch.empty_like(w)
-            db = torch.empty((Co,), dtype=torch.float32, device=g.device)
+            dw = sw if sw is not None else torch.empty_like(w)
+            db = sb if sb is not None else torch.empty((Co,), dtype=torch.float32, device=g.device)
             ws = _workspace(g.device, L.fnm_conv_wgrad_workspace_bytes(npos, Ci, Co))
             check(L.fnm_conv_wgrad(_ptr(g), _ptr(x), 0, _ptr(dw), _ptr(db), npos, Ci, Co, _ptr(ws), ws.numel(), _MODE,
                                    _stream()), "fnm_conv_wgrad")
             if not ctx.has_bias:
                 db = None
+        dw, db = (None if sw is not None else dw), (None if sb is not None else db)
         if zpre is not None:
-            return None, dw, db, dx, None
-        return dx, dw, db, None, None
+            return None, dw, db, dx, None, None
+        return dx, dw, db, None, None, None
 
 
 class CachedGeluFn(torch.autograd.Function):
@@ -526,8 +544,9 @@ class MlpHeadFn(torch.autograd.Function):
 
     @staticmethod
     @_on_tensor_device
-    def forward(ctx, h1, w2, b2):
+    def forward(ctx, h1, w2, b2, sinks=(None, None)):
         _need_cuda(h1, w2, b2)
+        ctx.sinks = sinks
         h1, w2 = _f32c(h1), _f32c(w2)
         H, D = h1.shape[-1], w2.shape[0]
         npos = h1.numel() // H
@@ -546,13 +565,16 @@ class MlpHeadFn(torch.autograd.Function):
         H, D = h1.shape[-1], w2.shape[0]
         npos = h1.numel() // H
         g_h1 = torch.empty_like(h1)
-        dw2 = torch.empty_like(w2)
-        db2 = torch.empty((D,), dtype=torch.float32, device=g.device)
+        sw, sb = ctx.sinks
+        if not ctx.has_bias:
+            sb = None
+        dw2 = sw if sw is not None else torch.empty_like(w2)
+        db2 = sb if sb is not None else torch.empty((D,), dtype=torch.float32, device=g.device)
         L = lib()
         ws = _workspace(g.device, L.fnm_mlp_head_bwd_workspace_bytes(H, D))
         check(L.fnm_mlp_head_bwd(_ptr(h1), _ptr(g), _ptr(w2), _ptr(g_h1), _ptr(dw2), _ptr(db2), npos, H, D,
                                  _ptr(ws), ws.numel(), _stream()), "fnm_mlp_head_bwd")
-        return g_h1, dw2, (db2 if ctx.has_bias else None)
+        return g_h1, None if sw is not None else dw2, (db2 if (ctx.has_bias and sb is None) else None), None
 
 
 class WeightedGeluSumFn(torch.autograd.Function):
@@ -591,8 +613,9 @@ class LocalFunctionalFn(torch.autograd.Function):
 
     @staticmethod
     @_on_tensor_device
-    def forward(ctx, x, w1, b1, wx, wy, zpre=None, zpre_is_grad=False):
+    def forward(ctx, x, w1, b1, wx, wy, zpre=None, zpre_is_grad=False, sinks=(None, None)):
         _need_cuda(x, w1, b1, wx, wy, zpre)
+        ctx.sinks = sinks
         x, w1, b1 = _f32c(x), _f32c(w1), _f32c(b1)
         B, P1, P2, Ci = x.shape
         H = w1.shape[0]
@@ -621,16 +644,18 @@ class LocalFunctionalFn(torch.autograd.Function):
             check(L.fnm_pointwise_ysyn_ex(_ptr(g), 0, _ptr(w1), 1, None, None, None, _ptr(zpre), _ptr(dx), None, B * P1, P2, 0,
                                           H, Ci, _MODE, _lib.FNM_PW_MUL_IS_GRAD if ctx.zpre_is_grad else 0, None, _stream()),
                   "fnm_pointwise_ysyn_ex")
+        sw, sb = ctx.sinks
         if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
             npos = B * P1 * P2
-            dw = torch.empty_like(w1)
-            db = torch.empty((H,), dtype=torch.float32, device=x.device)
+            dw = sw if sw is not None else torch.empty_like(w1)
+            db = sb if sb is not None else torch.empty((H,), dtype=torch.float32, device=x.device)
             ws = _workspace(x.device, L.fnm_conv_wgrad_workspace_bytes(npos, Ci, H))
             check(L.fnm_conv_wgrad(_ptr(g), _ptr(x), 0, _ptr(dw), _ptr(db), npos, Ci, H, _ptr(ws), ws.numel(), _MODE,
                                    _stream()), "fnm_conv_wgrad")
+        dw, db = (None if sw is not None else dw), (None if sb is not None else db)
         if zpre is not None:
-            return None, dw, db, None, None, dx, None
-        return dx, dw, db, None, None, None, None
+            return None, dw, db, None, None, dx, None, None
+        return dx, dw, db, None, None, None, None, None
 
 
 def local_functional_supported(x, w1):
@@ -640,7 +665,51 @@ def local_functional_supported(x, w1):
 
 
 def local_functional(x, w1, b1, wx, wy, zpre=None, zpre_is_grad=False):
-    return LocalFunctionalFn.apply(x, w1, b1, wx, wy, zpre, zpre_is_grad)
+    return LocalFunctionalFn.apply(x, w1, b1, wx, wy, zpre, zpre_is_grad, (_real_sink(w1), _real_sink(b1)))
+
+
+class RelL2SumFn(torch.autograd.Function):
+    """sum_b ||out_b - y_b||_2 / (||y_b||_2 + eps): the reference's training loss (LpLoss(size_average=False),
+    util/utilities_module.py:188-204) in two launches forward and one backward."""
+
+    @staticmethod
+    @_on_tensor_device
+    def forward(ctx, out, y, eps):
+        _need_cuda(out, y)
+        out, y = _f32c(out), _f32c(y)
+        B = out.shape[0]
+        n = out.numel() // B
+        loss = torch.empty((), dtype=torch.float32, device=out.device)
+        coef = torch.empty((B,), dtype=torch.float32, device=out.device)
+        L = lib()
+        ws = _workspace(out.device, L.fnm_rel_l2_workspace_bytes(B))
+        check(L.fnm_rel_l2_fwd(_ptr(out), _ptr(y), _ptr(loss), _ptr(coef), B, n, float(eps), _ptr(ws), ws.numel(), _stream()),
+              "fnm_rel_l2_fwd")
+        ctx.save_for_backward(out, y, coef)
+        return loss
+
+    @staticmethod
+    @_on_tensor_device
+    def backward(ctx, gloss):
+        out, y, coef = ctx.saved_tensors
+        B = out.shape[0]
+        n = out.numel() // B
+        g = torch.empty_like(out)
+        check(lib().fnm_rel_l2_bwd(_ptr(out), _ptr(y), _ptr(coef), _ptr(_f32c(gloss)), _ptr(g), B, n, _stream()),
+              "fnm_rel_l2_bwd")
+        return g, None, None
+
+
+def rel_l2_sum_supported(out, y):
+    if not (out.is_cuda and y.is_cuda and out.dtype == torch.float32 and y.dtype == torch.float32 and out.shape == y.shape):
+        return False
+    B = out.shape[0]
+    n = out.numel() // max(B, 1)
+    return 0 < B <= 65535 and n > 0 and not y.requires_grad
+
+
+def rel_l2_sum(out, y, eps=1e-6):
+    return RelL2SumFn.apply(out, y, eps)
 
 
 def weighted_gelu_sum(h1, wx, wy):
@@ -648,15 +717,15 @@ def weighted_gelu_sum(h1, wx, wy):
 
 
 def lift(x, w, b, P1, P2, ngrid):
-    return LiftFn.apply(x, w, b, P1, P2, ngrid)
+    return LiftFn.apply(x, w, b, P1, P2, ngrid, (_real_sink(w), _real_sink(b)))
 
 
 def pointwise_conv(x, w, b, zpre=None, zpre_is_grad=False):
-    return PointwiseConvFn.apply(x, w, b, zpre, zpre_is_grad)
+    return PointwiseConvFn.apply(x, w, b, zpre, zpre_is_grad, (_real_sink(w), _real_sink(b)))
 
 
 def mlp_head(h1, w2, b2):
-    return MlpHeadFn.apply(h1, w2, b2)
+    return MlpHeadFn.apply(h1, w2, b2, (_real_sink(w2), _real_sink(b2)))
 
 
 def fourier_layer(zin, w0, w1, wc, bc, tables, act_in=False, xact=None, want_act_out=False, pre_is_grad=False,
@@ -666,8 +735,8 @@ def fourier_layer(zin, w0, w1, wc, bc, tables, act_in=False, xact=None, want_act
     Cached GELU derivative (include/fnm_b200.h, FNM_PLAN_*): with ``grad_out`` (and want_act_out) the first result
     holds GELU'(z) INSTEAD of z -- only a fused layer called with ``pre_is_grad`` may consume it (it multiplies its
     outgoing gradient by that buffer instead of evaluating GELU' of it); the gradient it receives is still dL/dz."""
-    return FourierLayerFn.apply(zin, xact, w0, w1, wc, bc, tables, act_in, want_act_out, (_grad_sink(w0), _grad_sink(w1)),
-                                pre_is_grad, grad_out)
+    return FourierLayerFn.apply(zin, xact, w0, w1, wc, bc, tables, act_in, want_act_out,
+                                (_grad_sink(w0), _grad_sink(w1), _real_sink(wc), _real_sink(bc)), pre_is_grad, grad_out)
 
 
 def linear_functional(zin, w, tables, act_in=False, xact=None, pre_is_grad=False):

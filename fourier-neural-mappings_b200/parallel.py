@@ -18,10 +18,11 @@ import torch.distributed as dist
 class FlatGradients:
     """Owns the flat gradient buffer of ``params`` and keeps ``p.grad`` pointing into it.
 
-    ``direct_spectral=True`` additionally makes the complex (spectral) weights' slots *gradient sinks*: the
-    backward kernels of ops.py write dW straight into the slot and hand autograd no gradient, which removes
-    the AccumulateGrad pass (read dW, read grad, write grad: 3 x 1.07 GB at config 5) and lets ``zero_`` skip
-    those slots.  It assumes what holds for every model here: each spectral weight enters exactly one
+    ``direct_spectral=True`` additionally makes the slots *gradient sinks*: the backward kernels of ops.py write
+    dW straight into the slot and hand autograd no gradient, which removes the AccumulateGrad pass (for the spectral
+    weights: read dW, read grad, write grad, 3 x 1.07 GB at config 5; for the conv / lifting / projection weights one
+    small kernel each, which is what the launch-bound small configurations notice) and lets ``zero_`` skip the complex
+    slots.  It assumes what holds for every model here: each spectral weight enters exactly one
     autograd Function per step and ``zero_()`` is called before every backward (a second use raises)."""
 
     def __init__(self, params, direct_spectral=False, overlap=False):
@@ -57,9 +58,13 @@ class FlatGradients:
             # address parameter and gradient storage element by element
             view = torch.as_strided(flat, p.shape, p.stride()) if _dense(p) else flat.view(p.shape)
             p.grad = view
-            if self.direct and p.is_complex():
+            if self.direct:
+                # every parameter's slot is a sink: the backward kernels that compute a gradient write it there and autograd
+                # gets None (no AccumulateGrad kernel).  Real parameters that reach their gradient through torch ops instead
+                # simply accumulate into the (zeroed) slot as usual.
                 p._fnm_grad_sink, p._fnm_sink_uses = view, 0
-                view._fnm_on_ready = (lambda c=chunk, q=p: self._sink_ready(c, q)) if self.overlap else None
+                if p.is_complex():
+                    view._fnm_on_ready = (lambda c=chunk, q=p: self._sink_ready(c, q)) if self.overlap else None
 
     def zero_(self):
         """Replacement for ``optimizer.zero_grad()``: keeps the views alive (set_to_none would drop them)."""
@@ -70,8 +75,7 @@ class FlatGradients:
                 break
         if self.direct:
             for p in self.params:
-                if p.is_complex():
-                    p._fnm_sink_uses = 0
+                p._fnm_sink_uses = 0
 
     def _sink_ready(self, chunk, param):
         if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
@@ -230,6 +234,9 @@ class GraphedTrainStep:
 
 def rel_l2_sum(out, y, eps=1e-6):
     """The reference's training loss: LpLoss(size_average=False) (utilities_module.py:188-204)."""
+    from . import ops
+    if ops.rel_l2_sum_supported(out, y):                       # CUDA: three launches instead of ~12 (ops.RelL2SumFn)
+        return ops.rel_l2_sum(out, y, eps)
     b = out.shape[0]
     num = torch.norm(out.reshape(b, -1) - y.reshape(b, -1), 2, 1)
     den = torch.norm(y.reshape(b, -1), 2, 1) + eps

@@ -268,6 +268,16 @@ size_t fnm_mlp_head_bwd_workspace_bytes(int H, int D);
 int fnm_mlp_head_bwd(const float* h1, const float* g_out, const float* w2, float* g_h1, float* dw2, float* db2,
                      int64_t npos, int H, int D, void* workspace, size_t workspace_bytes, fnm_stream_t stream);
 
+/* ---- training loss of the reference harness (adjacent): LpLoss(size_average=False).rel
+ *      (util/utilities_module.py:188-204):  loss = sum_b ||out_b - y_b||_2 / (||y_b||_2 + eps)  over B samples of n floats.
+ *      forward also leaves coef[b] = 1 / (||out_b - y_b|| (||y_b|| + eps)) for backward:
+ *      gout[b][i] = gloss * coef[b] * (out[b][i] - y[b][i]).  Sample rows that are 16-byte aligned take the float4 path. */
+size_t fnm_rel_l2_workspace_bytes(int B);
+int fnm_rel_l2_fwd(const float* out, const float* y, float* loss, float* coef, int B, int64_t n, float eps, void* workspace,
+                   size_t workspace_bytes, fnm_stream_t stream);
+int fnm_rel_l2_bwd(const float* out, const float* y, const float* coef, const float* gloss, float* gout, int B, int64_t n,
+                   fnm_stream_t stream);
+
 /* ---- F2V local branch (func_to_vec2d.py:100-104, vec_to_vec2d.py:107-111): mlpfunc0 then two
  *      torch.trapz.  fc2 is linear, so only S[b][h] = sum_{x,y} wx[x] wy[y] GELU(h1[b][x][y][h]) touches the field
  *      (h1 = fc1 output, fnm_pointwise_ysyn with LY = 0); wx / wy hold the trapezoid weights dx*(1/2, 1, ..., 1, 1/2).

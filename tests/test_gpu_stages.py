@@ -454,3 +454,27 @@ def test_local_functional_one_pass(B, P1, P2, K, H, mode):
           "fnm_local_functional_bwd")
     gref = torch.einsum("bh,x,y,bxyh->bxyh", gS.double(), wx.double(), wy.double(), _gelu_grad64(h1))
     assert rel_l2(g, gref) < tol
+
+
+@pytest.mark.parametrize("shape", [(20, 1, 64, 64), (64, 1, 1024), (128, 2), (1, 3, 7, 5), (5, 1, 12)])
+def test_rel_l2_loss_kernels(shape):
+    """fnm_rel_l2_fwd / _bwd through ops.rel_l2_sum against the torch statement of LpLoss(size_average=False).rel
+    (util/utilities_module.py:188-204), value and gradient."""
+    from fnm_b200 import ops
+    from fnm_b200.parallel import rel_l2_sum
+    torch.manual_seed(6)
+    out = torch.randn(*shape, device=DEV, requires_grad=True)
+    y = torch.randn(*shape, device=DEV)
+    assert ops.rel_l2_sum_supported(out, y)
+    loss = rel_l2_sum(out, y)
+    (3.0 * loss).backward()
+    o64 = out.detach().double().requires_grad_(True)
+    b = shape[0]
+    ref = (torch.norm(o64.reshape(b, -1) - y.double().reshape(b, -1), 2, 1) / (torch.norm(y.double().reshape(b, -1), 2, 1) + 1e-6)).sum()
+    (3.0 * ref).backward()
+    assert abs(loss.item() - ref.item()) <= 2e-6 * abs(ref.item())
+    assert rel_l2(out.grad, o64.grad) < 2e-6
+    # a sample that matches its target exactly: zero gradient (torch.norm's subgradient), not NaN
+    out2 = y.clone().requires_grad_(True)
+    rel_l2_sum(out2, y).backward()
+    assert torch.equal(out2.grad, torch.zeros_like(out2))
