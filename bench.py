@@ -301,7 +301,9 @@ def kernel_algorithmic_bytes(name, wl, model, launches=None):
         # fwd: read x, write z (2A; the activated copy some launches also write is a design choice, not counted);
         # bwd: read g_z, z_prev, write g_in (3A; the first layer has no GELU' operand: 2A)
         "pointwise_ysyn": L * 2 * A + (L - 1) * 3 * A + 2 * A,
-        "ydft": 2 * L * A * (1 + lyf),                  # fwd + bwd analysis: read A, write the LY/P2 partial transform
+        "ydft": (launches or 2 * L) * A * (1 + lyf),    # fwd (+ bwd) analysis: read A, write the LY/P2 partial transform
+        # backward analysis fused with the conv weight gradient: ONE read of g, one of x, the partial transform written
+        "ydft_conv_wgrad": (launches or L) * A * (2 + lyf),
         "conv_wgrad": (launches or L) * 2 * A,          # read g and x (one more launch for the projection's fc1)
         "pointwise_conv": 2 * 2 * A,                    # projection fc1 forward + its input gradient
         "lift_fwd": A, "lift_bwd": A, "mlp_head_fwd": A, "mlp_head_bwd": 2 * A,

@@ -85,6 +85,7 @@ PROTOTYPES = {
     "fnm_wsum_gelu_bwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),
     "fnm_conv_wgrad_workspace_bytes": (_sz, [_i64, _i32, _i32]),
     "fnm_conv_wgrad": (_i32, [_vp, _vp, _i32, _vp, _vp, _i64, _i32, _i32, _vp, _sz, _i32, _vp]),
+    "fnm_ydft_conv_wgrad": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp, _sz, _i32, _vp]),
 }
 
 _lib = None

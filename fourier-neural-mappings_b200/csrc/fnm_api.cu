@@ -307,6 +307,18 @@ int fnm_conv_wgrad(const float* g, const float* x, int act_in, float* dwc, float
     return conv_wgrad(g, x, act_in, dwc, dbc, npos, Ci, Co, static_cast<float*>(workspace), mode, as_stream(stream));
 }
 
+int fnm_ydft_conv_wgrad(const float* g, const float* x, const float* tab, float* T, float* dwc, float* dbc, int64_t rows, int S2,
+                        int LY, int C, void* workspace, size_t workspace_bytes, int mode, fnm_stream_t stream) {
+    FNM_REQUIRE(g && x && tab && T && workspace, "ydft_conv_wgrad: NULL pointer");
+    FNM_REQUIRE(rows > 0 && S2 > 0 && LY > 0 && C > 0, "ydft_conv_wgrad: bad extents");
+    if (workspace_bytes < conv_wgrad_workspace(rows * S2, C, C)) return fail(FNM_EWORKSPACE, "ydft_conv_wgrad: workspace too small");
+    cudaStream_t st = as_stream(stream);
+    if (tc_gz_pass_supported(g, x, tab, rows, S2, LY, C, C, 0))
+        return tc_gz_pass(g, x, tab, T, dwc, dbc, rows, S2, LY, static_cast<float*>(workspace), mode, st);
+    FNM_TRY(fnm_ydft(g, tab, T, rows, S2, LY, C, 0, mode, stream));
+    return conv_wgrad(g, x, 0, dwc, dbc, rows * S2, C, C, static_cast<float*>(workspace), mode, st);
+}
+
 int fnm_gelu_fwd(const float* z, float* y, int64_t n, fnm_stream_t stream) {
     FNM_REQUIRE(z && y, "gelu_fwd: NULL pointer");
     return gelu_launch(nullptr, z, y, n, false, as_stream(stream));
@@ -436,7 +448,11 @@ int fnm_fourier_layer_bwd(const fnm_plan* p, const float* g_z, const float* xin,
     float* partial = cv.take(w.partial);
     const int LY = 2 * p->NY;
     // analysis of g_z (c_l/N folded into byT), A.2 first line
-    FNM_TRY(fnm_ydft(g_z, p->byT, Tg, (int64_t)p->B * p->S1, p->S2, LY, p->Co, 0, p->mode, stream));
+    // ... fused with the conv weight gradient when both can share one read of g_z (gz_pass_tma, fnm_tc_wgrad.cu)
+    const bool want_cw = wc && (dwc || dbc);
+    const bool gz_fused = want_cw && tc_gz_pass_supported(g_z, xin, p->byT, (int64_t)p->B * p->S1, p->S2, LY, p->Ci, p->Co, act_in);
+    if (gz_fused) FNM_TRY(tc_gz_pass(g_z, xin, p->byT, Tg, dwc, dbc, (int64_t)p->B * p->S1, p->S2, LY, partial, p->mode, st));
+    else FNM_TRY(fnm_ydft(g_z, p->byT, Tg, (int64_t)p->B * p->S1, p->S2, LY, p->Co, 0, p->mode, stream));
     FNM_TRY(fnm_xdft(Tg, p->exb, Gh, p->B, p->S1, p->R, p->NY, p->Co, p->mode, stream));
     float* shadowA = w.shadow ? cv.take(w.shadow) : nullptr;
     float* shadowB = w.shadow ? cv.take(w.shadow) : nullptr;
@@ -452,7 +468,7 @@ int fnm_fourier_layer_bwd(const fnm_plan* p, const float* g_z, const float* xin,
             FNM_TRY(simt_mix_bwd_w(xh_save, Gh, dw0, dw1, p->rows_per_w, p->B, p->R, p->NY, p->Ci, p->Co, st, mm));
         }
     }
-    if (wc && (dwc || dbc))
+    if (want_cw && !gz_fused)
         FNM_TRY(conv_wgrad(g_z, xin, act_in, dwc, dbc, (int64_t)p->B * p->S1 * p->S2, p->Ci, p->Co, partial, p->mode, st));
     if (g_in) {
         const int w1_layout = p->Co % 2 == 0 ? 1 : 0;                  // W1[m][i][o] rows readable with 16-byte loads

@@ -457,6 +457,251 @@ conv_wgrad_tma(const __grid_constant__ CUtensorMap mapG, const __grid_constant__
     if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// gz_pass_tma: the two passes of a layer's backward that each read the incoming gradient g in full, as ONE read of g
+// ("read once"; models/func_to_func2d.py:89-95 backward):
+//     T[row][l][c] = sum_y tab[l][y] g[row][y][c]                                   (ydft_tma's product, fnm_tc_ydft.cu)
+//     dWc[o][i]    = sum_pos g[pos][o] x[pos][i],   dbc[o] = sum_pos g[pos][o]      (conv_wgrad_tma's products, above)
+// Both contract over positions with g^T as the A operand (M = channel of g = TMEM lane), so the MN-major TMA tile of g and
+// its remainder tile serve both; the B operands are the stacked [x_raw ; x_lo] tile (MN-major, N = 256) and the stacked
+// [tab ; tab_lo] chunk (K-major, N = 128).  Per 32-position chunk and k-step:
+//     Dy(main | corr) += g_raw * [tab ; tab_lo]      Dy(corr) += g_lo * tab
+//     Dc(main | corr) += g_raw * [x_raw ; x_lo]      Dc(corr) += g_lo * x_raw
+// A work item is one grid row: its ydft accumulator (128 columns, double buffered) goes to T, the conv accumulator (256
+// columns, single buffered) is flushed into the registers of the 8 epilogue warps after every row -- chains of 32 (main) and
+// 64 (corrections) MMAs at 256 positions per row.  The next row's first ydft MMAs are issued before the issuer waits for
+// that flush, so the tensor pipe has work while the epilogue drains the conv accumulator.
+// Stage: g 16 KB | x 16 KB | x_lo 16 KB | tab 8 KB | tab_lo 8 KB; g_lo in its own ring.
+// Warps: 0 TMA producer | 1 MMA issuer | 2-5 converters (+ column sums of g for dbc) | 6-13 epilogue.
+constexpr int kGzRaw = 3, kGzLo = 2;
+constexpr uint32_t kGzStage = 65536, kGzXOff = 16384, kGzTabOff = 49152;
+constexpr uint32_t kGzLoTile = 16384;
+constexpr int kGzThreads = 14 * 32;
+
+struct GzArgs {
+    float* T; float* part;
+    long long rows;
+    int S2, LY, nch, single_pass;
+};
+
+__global__ void __launch_bounds__(kGzThreads, 1)
+gz_pass_tma(const __grid_constant__ CUtensorMap mapG, const __grid_constant__ CUtensorMap mapX,
+            const __grid_constant__ CUtensorMap mapT, const GzArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* lo_ring = smem + kGzRaw * kGzStage;
+    float* dbs = reinterpret_cast<float*>(lo_ring + kGzLo * kGzLoTile);                    // [128] column sums of g
+    uint64_t* bars = reinterpret_cast<uint64_t*>(dbs + 128);
+    uint64_t* raw_full = bars;                     // [kGzRaw] TMA transaction barriers
+    uint64_t* raw_empty = bars + kGzRaw;           // [kGzRaw] MMA commit + 4 converter warps
+    uint64_t* lo_full = bars + 2 * kGzRaw;         // [kGzLo]  4 converter warps
+    uint64_t* lo_empty = lo_full + kGzLo;          // [kGzLo]  MMA commit
+    uint64_t* cv_full = lo_empty + kGzLo;          // [1] conv accumulator of a row complete
+    uint64_t* cv_empty = cv_full + 1;              // [1] 8 epilogue warps
+    uint64_t* yd_full = cv_empty + 1;              // [2]
+    uint64_t* yd_empty = yd_full + 2;              // [2] 8 epilogue warps
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(yd_empty + 2);
+
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kGzRaw; ++s) { mbar_init(&raw_full[s], 1); mbar_init(&raw_empty[s], 5); }
+        for (int s = 0; s < kGzLo; ++s) { mbar_init(&lo_full[s], 4); mbar_init(&lo_empty[s], 1); }
+        mbar_init(cv_full, 1); mbar_init(cv_empty, 8);
+        for (int s = 0; s < 2; ++s) { mbar_init(&yd_full[s], 1); mbar_init(&yd_empty[s], 8); }
+        fence_barrier_init();
+        tma_prefetch_desc(&mapG); tma_prefetch_desc(&mapX); tma_prefetch_desc(&mapT);
+    }
+    if (threadIdx.x < 128) dbs[threadIdx.x] = 0.f;
+    if (warp == 1) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+
+    const uint32_t my_rows = (uint32_t)((a.rows - (long long)blockIdx.x + (long long)gridDim.x - 1) / (long long)gridDim.x);
+    const uint32_t nch = (uint32_t)a.nch;
+    const uint32_t total = my_rows * nch;
+
+    if (warp == 0) {
+        // =========================================================================== TMA producer
+        if (lane == 0) {
+            uint32_t it = 0, ch = 0;
+            for (uint32_t q = 0; q < total; ++q) {
+                const uint32_t s = q % kGzRaw;
+                const int row = (int)(blockIdx.x + it * gridDim.x);
+                mbar_wait(&raw_empty[s], ((q / kGzRaw) & 1) ^ 1);
+                mbar_expect_tx(&raw_full[s], 2u * 16384u + 8192u);
+                uint8_t* st = smem + (size_t)s * kGzStage;
+                for (int j = 0; j < 4; ++j) {                      // positions past the end of the row read as zeros (TMA bounds)
+                    tma_load_3d(&mapG, &raw_full[s], st + j * 4096, j * 32, (int)ch * 32, row);
+                    tma_load_3d(&mapX, &raw_full[s], st + kGzXOff + j * 4096, j * 32, (int)ch * 32, row);
+                }
+                tma_load_2d(&mapT, &raw_full[s], st + kGzTabOff, (int)ch * 32, 0);
+                if (++ch == nch) { ch = 0; ++it; }
+            }
+        }
+    } else if (warp == 1) {
+        // =========================================================================== MMA issuer
+        const uint32_t sbase = smem_u32(smem), lbase = smem_u32(lo_ring);
+        const uint32_t idc128 = make_idesc(128, 128) | (1u << 15) | (1u << 16);       // conv: A and B MN-major
+        const uint32_t idc256 = make_idesc(128, 256) | (1u << 15) | (1u << 16);
+        const uint32_t idy64 = make_idesc(128, 64) | (1u << 15);                      // ydft: A MN-major, B K-major
+        const uint32_t idy128 = make_idesc(128, 128) | (1u << 15);
+        uint32_t q = 0;
+        for (uint32_t it = 0; it < my_rows; ++it) {
+            const uint32_t ybuf = it & 1u;
+            const uint32_t dy = tmem_base + 256u + ybuf * 128u;
+            for (uint32_t ch = 0; ch < nch; ++ch, ++q) {
+                const uint32_t s = q % kGzRaw, l = q % kGzLo;
+                mbar_wait(&raw_full[s], (q / kGzRaw) & 1);
+                if (!a.single_pass) mbar_wait(&lo_full[l], (q / kGzLo) & 1);
+                if (ch == 0) mbar_wait(&yd_empty[ybuf], ((it >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t g_raw = sbase + s * kGzStage, x_raw = g_raw + kGzXOff, tabb = g_raw + kGzTabOff;
+                const uint32_t g_lo = lbase + l * kGzLoTile;
+                const uint32_t first = ch == 0 ? 0u : 1u;
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks)          // (main | corr) of the row's DFT: g_raw * [tab ; tab_lo]
+                    umma_ss(dy, desc_mn32(g_raw + ks * 1024u), make_desc(tabb + ks * 32u), a.single_pass ? idy64 : idy128,
+                            ks == 0 ? first : 1u);
+                if (!a.single_pass) {
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks) umma_ss(dy + 64u, desc_mn32(g_lo + ks * 1024u), make_desc(tabb + ks * 32u), idy64, 1u);
+                }
+                if (ch == 0) {                          // the previous row's conv accumulator must have been flushed
+                    mbar_wait(cv_empty, (it & 1) ^ 1);
+                    tc_fence_after();
+                }
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks)          // (main | g_raw x_lo)
+                    umma_ss(tmem_base, desc_mn32(g_raw + ks * 1024u), desc_mn32(x_raw + ks * 1024u), a.single_pass ? idc128 : idc256,
+                            ks == 0 ? first : 1u);
+                if (!a.single_pass) {
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks)
+                        umma_ss(tmem_base + 128u, desc_mn32(g_lo + ks * 1024u), desc_mn32(x_raw + ks * 1024u), idc128, 1u);
+                    umma_commit(&lo_empty[l]);
+                }
+                umma_commit(&raw_empty[s]);
+                if (ch == nch - 1) { umma_commit(cv_full); umma_commit(&yd_full[ybuf]); }
+                __syncwarp();
+            }
+        }
+    } else if (warp < 6) {
+        // =========================================================================== converters: lo = raw - trunc(raw), db
+        const int ct = (int)threadIdx.x - 64;                        // 0..127
+        const int pair = ct & 31, rgrp = ct >> 5;                    // (channel block j, 16-byte chunk c) and row group
+        const int j = pair >> 3, c = pair & 7;
+        float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (uint32_t q = 0; q < total; ++q) {
+            const uint32_t s = q % kGzRaw, l = q % kGzLo;
+            mbar_wait(&raw_full[s], (q / kGzRaw) & 1);
+            const uint32_t src0 = smem_u32(smem) + s * kGzStage, dst0 = smem_u32(lo_ring) + l * kGzLoTile;
+            if (!a.single_pass) mbar_wait(&lo_empty[l], ((q / kGzLo) & 1) ^ 1);
+#pragma unroll
+            for (int rr = 0; rr < 8; ++rr) {
+                const uint32_t r = (uint32_t)(rgrp + 4 * rr);
+                const uint32_t off = (uint32_t)j * 4096u + r * 128u + ((((uint32_t)c >> 1) ^ (r & 3u)) << 5) + ((uint32_t)c & 1u) * 16u;
+                float4 vg, vx;
+                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(vg.x), "=f"(vg.y), "=f"(vg.z), "=f"(vg.w) : "r"(src0 + off));
+                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(vx.x), "=f"(vx.y), "=f"(vx.z), "=f"(vx.w) : "r"(src0 + kGzXOff + off));
+                sum.x += vg.x; sum.y += vg.y; sum.z += vg.z; sum.w += vg.w;
+                if (!a.single_pass) {
+                    vg.x -= __uint_as_float(__float_as_uint(vg.x) & 0xffffe000u); vg.y -= __uint_as_float(__float_as_uint(vg.y) & 0xffffe000u);
+                    vg.z -= __uint_as_float(__float_as_uint(vg.z) & 0xffffe000u); vg.w -= __uint_as_float(__float_as_uint(vg.w) & 0xffffe000u);
+                    vx.x -= __uint_as_float(__float_as_uint(vx.x) & 0xffffe000u); vx.y -= __uint_as_float(__float_as_uint(vx.y) & 0xffffe000u);
+                    vx.z -= __uint_as_float(__float_as_uint(vx.z) & 0xffffe000u); vx.w -= __uint_as_float(__float_as_uint(vx.w) & 0xffffe000u);
+                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst0 + off), "f"(vg.x), "f"(vg.y), "f"(vg.z), "f"(vg.w) : "memory");
+                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(src0 + 2u * kGzXOff + off), "f"(vx.x), "f"(vx.y), "f"(vx.z), "f"(vx.w) : "memory");
+                }
+            }
+            if (!a.single_pass) {
+                // the table chunk into the second half of its stacked slab (layout-preserving copy, 2 KB per pass)
+                const uint32_t tsrc = src0 + kGzTabOff + (uint32_t)ct * 16u;
+#pragma unroll
+                for (uint32_t off = 0; off < 8192u; off += 2048u) {
+                    float4 v;
+                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(tsrc + off));
+                    v.x -= __uint_as_float(__float_as_uint(v.x) & 0xffffe000u); v.y -= __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
+                    v.z -= __uint_as_float(__float_as_uint(v.z) & 0xffffe000u); v.w -= __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
+                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(tsrc + off + 8192u), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+                }
+                fence_proxy_async();
+            }
+            __syncwarp();
+            if (lane == 0) {
+                if (!a.single_pass) mbar_arrive(&lo_full[l]);
+                mbar_arrive(&raw_empty[s]);
+            }
+        }
+        // bias gradient: channel 32 j + 4 c + {0..3}; the four row groups meet in shared memory
+        atomicAdd(&dbs[32 * j + 4 * c + 0], sum.x); atomicAdd(&dbs[32 * j + 4 * c + 1], sum.y);
+        atomicAdd(&dbs[32 * j + 4 * c + 2], sum.z); atomicAdd(&dbs[32 * j + 4 * c + 3], sum.w);
+    } else {
+        // =========================================================================== epilogue (8 warps)
+        const int ew = warp - 6, q4 = warp & 3, half = ew >> 2;      // TMEM lane quarter = warp % 4
+        const int o = q4 * 32 + lane;
+        const uint32_t lane_base = tmem_base + ((uint32_t)(q4 * 32) << 16);
+        float acc[64];
+#pragma unroll
+        for (int i = 0; i < 64; ++i) acc[i] = 0.f;
+        for (uint32_t it = 0; it < my_rows; ++it) {
+            const long long row = (long long)blockIdx.x + (long long)it * gridDim.x;
+            const uint32_t ybuf = it & 1u;
+            // conv accumulator of the row -> registers (the issuer waits for this before the next row's conv MMAs)
+            mbar_wait(cv_full, it & 1);
+            tc_fence_after();
+#pragma unroll
+            for (int g4 = 0; g4 < 4; ++g4) {
+                uint32_t r[16], r2[16];
+                tmem_ld16(lane_base + (uint32_t)half * 64u + g4 * 16, r);
+                if (!a.single_pass) tmem_ld16(lane_base + 128u + (uint32_t)half * 64u + g4 * 16, r2);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 16; ++i)
+                    acc[g4 * 16 + i] += __uint_as_float(r[i]) + (a.single_pass ? 0.f : __uint_as_float(r2[i]));
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(cv_empty);
+            // the row's transform: 32 of the 64 table rows per warp, 128-byte coalesced stores (lane = channel)
+            mbar_wait(&yd_full[ybuf], (it >> 1) & 1);
+            tc_fence_after();
+            const int l0 = half * 32;
+            float* op = a.T + ((size_t)row * a.LY + l0) * 128 + o;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                uint32_t m0[16], m1[16];
+                const uint32_t ty = lane_base + 256u + ybuf * 128u + (uint32_t)(l0 + h * 16);
+                tmem_ld16(ty, m0);
+                if (!a.single_pass) tmem_ld16(ty + 64u, m1);
+                tmem_ld_wait();
+                if (h == 1) {                                        // both halves read: the buffer is free for the row after next
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&yd_empty[ybuf]);
+                }
+#pragma unroll
+                for (int i = 0; i < 16; ++i)
+                    if (l0 + h * 16 + i < a.LY)
+                        op[(size_t)(h * 16 + i) * 128] = __uint_as_float(m0[i]) + (a.single_pass ? 0.f : __uint_as_float(m1[i]));
+            }
+        }
+        float* pd = a.part + (size_t)blockIdx.x * cw_part_floats(128, 128) + (size_t)o * 128 + half * 64;
+#pragma unroll
+        for (int i = 0; i < 64; i += 4) *reinterpret_cast<float4*>(pd + i) = make_float4(acc[i], acc[i + 1], acc[i + 2], acc[i + 3]);
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x < 128) {
+        float* pb = a.part + (size_t)blockIdx.x * cw_part_floats(128, 128) + (size_t)128 * 128;
+        pb[threadIdx.x] = dbs[threadIdx.x];
+        for (int w = 1; w < kCwLoaderWgs; ++w) pb[w * 128 + threadIdx.x] = 0.f;
+    }
+    if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
 static int cw_grid(int64_t npos, bool for_workspace = false) {
     const int64_t chunks = (npos + 31) / 32;
     const int sms = for_workspace ? sm_count_max() : sm_count();     // the workspace must hold any later SM budget
@@ -545,6 +790,58 @@ int tc_conv_wgrad(const float* g, const float* x, int act, float* dwc, float* db
     {
         LaunchScope ls("conv_wgrad_reduce", st);
         conv_wgrad_tc_reduce<<<(count * 32 + 255) / 256, 256, 0, st>>>(partial, grid, Ci, Co, fold, dwc, dbc);
+    }
+    return check_launch("conv_wgrad_reduce");
+}
+
+
+// fused ydft(g) + conv weight gradient (gz_pass_tma): 128 channels on both sides, no activation on load, whole grid rows as
+// work items, and enough rows that the conv-wgrad workspace (sized by tc_conv_wgrad_workspace) holds one partial per CTA
+bool tc_gz_pass_supported(const float* g, const float* x, const float* tab, int64_t rows, int S2, int LY, int Ci, int Co, int act) {
+    if (!tc_enabled() || act != 0 || Ci != 128 || Co != 128 || LY < 8 || LY > 64 || S2 % 4 != 0 || S2 < 4) return false;
+    if (rows < 2LL * sm_count_max() || rows * S2 < 512LL * sm_count_max() || rows >= (1LL << 30)) return false;
+    if ((reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(tab)) & 15) return false;
+    const char* e = getenv("FNM_NO_GZPASS");
+    return !(e && e[0] == '1');
+}
+
+int tc_gz_pass(const float* g, const float* x, const float* tab, float* T, float* dwc, float* dbc, int64_t rows, int S2, int LY,
+               float* partial, int mode, cudaStream_t st) {
+    GzArgs a{};
+    a.T = T; a.part = partial; a.rows = rows; a.S2 = S2; a.LY = LY; a.nch = (S2 + 31) / 32;
+    a.single_pass = mode == FNM_MODE_TF32;
+    CUtensorMap mg, mx, mt;
+    {
+        const cuuint64_t dims[3] = {128, (cuuint64_t)S2, (cuuint64_t)rows};
+        const cuuint64_t str[2] = {128 * 4, (cuuint64_t)S2 * 128 * 4};
+        const cuuint32_t box[3] = {32, 32, 1};
+        if (!tc_make_map_swz(&mg, g, 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B) ||
+            !tc_make_map_swz(&mx, x, 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))
+            return fail(FNM_ECUDA, "ydft_conv_wgrad: tensor map (g / x) failed");
+    }
+    {
+        const cuuint64_t dims[2] = {(cuuint64_t)S2, (cuuint64_t)LY};
+        const cuuint64_t str[1] = {(cuuint64_t)S2 * 4};
+        const cuuint32_t box[2] = {32, 64};
+        if (!tc_make_map(&mt, tab, 2, dims, str, box, true)) return fail(FNM_ECUDA, "ydft_conv_wgrad: tensor map (table) failed");
+    }
+    const size_t smem = (size_t)kGzRaw * kGzStage + (size_t)kGzLo * kGzLoTile + 128 * 4 + 1024 + 256;
+    static std::atomic<uint64_t> attr_set{0};
+    int attr_set_dev = 0;
+    if (once_needed(attr_set, attr_set_dev)) {
+        const cudaError_t e = cudaFuncSetAttribute(gz_pass_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return fail(FNM_ECUDA, "ydft_conv_wgrad: smem attribute: %s", cudaGetErrorString(e));
+        once_done(attr_set, attr_set_dev);
+    }
+    const int grid = rows < sm_count() ? (int)rows : sm_count();
+    {
+        LaunchScope ls("ydft_conv_wgrad", st);
+        gz_pass_tma<<<grid, kGzThreads, smem, st>>>(mg, mx, mt, a);
+    }
+    FNM_TRY(check_launch("ydft_conv_wgrad"));
+    {
+        LaunchScope ls("conv_wgrad_reduce", st);
+        conv_wgrad_tc_reduce<<<((128 * 128 + 128) * 32 + 255) / 256, 256, 0, st>>>(partial, grid, 128, 128, 1, dwc, dbc);
     }
     return check_launch("conv_wgrad_reduce");
 }

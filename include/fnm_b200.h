@@ -247,6 +247,12 @@ int fnm_pointwise_ysyn_ex(const float* x, int act_in, const float* wc, int wc_is
 size_t fnm_conv_wgrad_workspace_bytes(int64_t npos, int Ci, int Co);
 int fnm_conv_wgrad(const float* g, const float* x, int act_in, float* dwc, float* dbc, int64_t npos,
                    int Ci, int Co, void* workspace, size_t workspace_bytes, int mode, fnm_stream_t stream);
+/* The two backward passes that read a layer's incoming gradient g[rows][S2][C] in full, as one read of g:
+ *   T[row][l][c] = sum_y tab[l][y] g[row][y][c]  (fnm_ydft)   and   dwc / dbc of the C x C 1x1 conv (fnm_conv_wgrad, x = the
+ *   layer input, no activation on load).  Backward of func_to_func2d.py:89-95 (x1 = speconv(x); x2 = w(x)).  Shapes the fused
+ *   kernel does not serve run as the two separate calls.  workspace: fnm_conv_wgrad_workspace_bytes(rows * S2, C, C). */
+int fnm_ydft_conv_wgrad(const float* g, const float* x, const float* tab, float* T, float* dwc, float* dbc, int64_t rows,
+                        int S2, int LY, int C, void* workspace, size_t workspace_bytes, int mode, fnm_stream_t stream);
 
 /* ---- the two ends of the trunk (adjacent ops) -----------------------------------
  * lift: fc0 applied to [data channels | grid coordinates] + zero padding at the end of each axis

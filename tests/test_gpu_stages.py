@@ -264,6 +264,42 @@ def test_conv_wgrad(npos, Ci, Co, act, mode):
     assert rel_l2(dbc, g.double().sum(0)) < 1e-5
 
 
+# rows, S2, LY: the fused kernel needs >= 2 x 148 rows and 512 x 148 positions; (40, 64, 24) takes the two-call route behind
+# the same entry.  Ragged row lengths (72, 100: last chunk partly past the row), odd row counts, LY < 64 and LY % 4 != 0.
+@pytest.mark.parametrize("rows,S2,LY", [(2048, 256, 64), (1101, 72, 24), (999, 100, 26), (40, 64, 24), (4097, 32, 8)])
+@pytest.mark.parametrize("mode", ["fp32", "tf32"])
+def test_ydft_conv_wgrad_fused(rows, S2, LY, mode):
+    """fnm_ydft_conv_wgrad (one read of g for the backward y-DFT and the conv weight / bias gradient) against float64, and
+    against the two separate entry points it replaces."""
+    torch.manual_seed(11)
+    C = 128
+    g = torch.randn(rows, S2, C, device=DEV) + 0.2                       # a mean: the DC column of the transform is large
+    x = torch.randn(rows, S2, C, device=DEV) + 0.3
+    tab = torch.randn(LY, S2, device=DEV) / S2 ** 0.5
+    L = lib()
+    m = 0 if mode == "fp32" else 1
+    ws = torch.empty(L.fnm_conv_wgrad_workspace_bytes(rows * S2, C, C), dtype=torch.uint8, device=DEV)
+    T = torch.full((rows, LY, C), float("nan"), device=DEV)
+    dwc = torch.full((C, C), float("nan"), device=DEV)
+    dbc = torch.full((C,), float("nan"), device=DEV)
+    check(L.fnm_ydft_conv_wgrad(_p(g), _p(x), _p(tab), _p(T), _p(dwc), _p(dbc), rows, S2, LY, C, _p(ws), ws.numel(), m, _stream()),
+          "fnm_ydft_conv_wgrad")
+    tol = TOL_FP32 if mode == "fp32" else TOL_TF32
+    g64 = g.double()
+    assert rel_l2(T, torch.einsum("ly,ryc->rlc", tab.double(), g64)) < tol
+    assert rel_l2(dwc, g64.reshape(-1, C).t() @ x.double().reshape(-1, C)) < tol
+    assert rel_l2(dbc, g64.reshape(-1, C).sum(0)) < 1e-5
+    # the non-DC content of T at the accuracy of the separate kernel (truncating accumulation must not leak the mean)
+    T2 = torch.empty_like(T)
+    check(L.fnm_ydft(_p(g), _p(tab), _p(T2), rows, S2, LY, C, 0, m, _stream()), "fnm_ydft")
+    assert rel_l2(T, T2.double()) < tol
+    # gradient-only calls: either output may be NULL
+    dw2 = torch.full((C, C), float("nan"), device=DEV)
+    check(L.fnm_ydft_conv_wgrad(_p(g), _p(x), _p(tab), _p(T2), _p(dw2), None, rows, S2, LY, C, _p(ws), ws.numel(), m, _stream()),
+          "fnm_ydft_conv_wgrad")
+    assert torch.equal(dw2, dwc) and torch.equal(T2, T)
+
+
 @pytest.mark.parametrize("B,R,NY,rpw,Ci,Co", [(20, 24, 12, 12, 32, 32), (32, 8, 32, 4, 128, 128), (64, 1, 16, 1, 64, 64),
                                               (5, 6, 5, 3, 20, 24), (40, 4, 7, 4, 48, 32), (3, 2, 3, 1, 8, 16)])
 @pytest.mark.parametrize("mode", ["fp32", "tf32"])

@@ -84,6 +84,7 @@ timeit("mix_bwd_w", lambda: check(L.fnm_mix_bwd_w(p(Xh), p(Oh), p(dw0), p(dw1), 
 ws = torch.empty(L.fnm_conv_wgrad_workspace_bytes(rows * P2, C_, C_), dtype=torch.uint8, device=dev)
 dwc, dbc = torch.empty(C_, C_, device=dev), torch.empty(C_, device=dev)
 timeit("conv_wgrad noact (2A)", lambda: check(L.fnm_conv_wgrad(p(g), p(x), 0, p(dwc), p(dbc), rows * P2, C_, C_, p(ws), ws.numel(), 0, st)), 2 * A)
+timeit("ydft + conv_wgrad fused (2A + T)", lambda: check(L.fnm_ydft_conv_wgrad(p(g), p(x), p(tab["ay"]), p(T), p(dwc), p(dbc), rows, P2, LY, C_, p(ws), ws.numel(), 0, st)), 2 * A + T.numel() * 4)
 timeit("conv_wgrad (2A)", lambda: check(L.fnm_conv_wgrad(p(g), p(x), 1, p(dwc), p(dbc), rows * P2, C_, C_, p(ws), ws.numel(), 0, st)), 2 * A)
 y = torch.empty_like(x)
 timeit("torch copy (2A) reference", lambda: y.copy_(x), 2 * A)
