@@ -314,7 +314,7 @@ int fnm_ydft_conv_wgrad(const float* g, const float* x, const float* tab, float*
     if (workspace_bytes < conv_wgrad_workspace(rows * S2, C, C)) return fail(FNM_EWORKSPACE, "ydft_conv_wgrad: workspace too small");
     cudaStream_t st = as_stream(stream);
     if (tc_gz_pass_supported(g, x, tab, rows, S2, LY, C, C, 0))
-        return tc_gz_pass(g, x, tab, T, dwc, dbc, rows, S2, LY, static_cast<float*>(workspace), mode, st);
+        return tc_gz_pass(g, x, tab, T, dwc, dbc, rows, S2, LY, C, static_cast<float*>(workspace), mode, st);
     FNM_TRY(fnm_ydft(g, tab, T, rows, S2, LY, C, 0, mode, stream));
     return conv_wgrad(g, x, 0, dwc, dbc, rows * S2, C, C, static_cast<float*>(workspace), mode, st);
 }
@@ -451,7 +451,7 @@ int fnm_fourier_layer_bwd(const fnm_plan* p, const float* g_z, const float* xin,
     // ... fused with the conv weight gradient when both can share one read of g_z (gz_pass_tma, fnm_tc_wgrad.cu)
     const bool want_cw = wc && (dwc || dbc);
     const bool gz_fused = want_cw && tc_gz_pass_supported(g_z, xin, p->byT, (int64_t)p->B * p->S1, p->S2, LY, p->Ci, p->Co, act_in);
-    if (gz_fused) FNM_TRY(tc_gz_pass(g_z, xin, p->byT, Tg, dwc, dbc, (int64_t)p->B * p->S1, p->S2, LY, partial, p->mode, st));
+    if (gz_fused) FNM_TRY(tc_gz_pass(g_z, xin, p->byT, Tg, dwc, dbc, (int64_t)p->B * p->S1, p->S2, LY, p->Co, partial, p->mode, st));
     else FNM_TRY(fnm_ydft(g_z, p->byT, Tg, (int64_t)p->B * p->S1, p->S2, LY, p->Co, 0, p->mode, stream));
     FNM_TRY(fnm_xdft(Tg, p->exb, Gh, p->B, p->S1, p->R, p->NY, p->Co, p->mode, stream));
     float* shadowA = w.shadow ? cv.take(w.shadow) : nullptr;

@@ -74,7 +74,7 @@ int tc_conv_wgrad(const float* g, const float* x, int act, float* dwc, float* db
                   float* partial, int mode, cudaStream_t st);
 bool tc_gz_pass_supported(const float* g, const float* x, const float* tab, int64_t rows, int S2, int LY, int Ci, int Co, int act);
 int tc_gz_pass(const float* g, const float* x, const float* tab, float* T, float* dwc, float* dbc, int64_t rows, int S2, int LY,
-               float* partial, int mode, cudaStream_t st);
+               int C, float* partial, int mode, cudaStream_t st);
 bool tc_pw2_supported(int64_t rows, int S2, int LY, int K, int N, int act, const void* x, const void* Z, const void* by,
                       int by_ld = 0);
 int tc_pw2(const float* x, const float* wc, int wc_is_kn, const float* bias, const float* Z, const float* by,

@@ -471,6 +471,9 @@ conv_wgrad_tma(const __grid_constant__ CUtensorMap mapG, const __grid_constant__
 // columns, single buffered) is flushed into the registers of the 8 epilogue warps after every row -- chains of 32 (main) and
 // 64 (corrections) MMAs at 256 positions per row.  The next row's first ydft MMAs are issued before the issuer waits for
 // that flush, so the tensor pipe has work while the epilogue drains the conv accumulator.
+// C = 32 / 64: F = 128 / C consecutive grid rows are folded into the 128 lanes as in ydft_tma (the 32-channel blocks of the g
+// and x tiles come from F different rows); the conv product then holds the wanted C x C blocks on its diagonal, which is
+// the folded partial format conv_wgrad_tc_reduce already sums.
 // Stage: g 16 KB | x 16 KB | x_lo 16 KB | tab 8 KB | tab_lo 8 KB; g_lo in its own ring.
 // Warps: 0 TMA producer | 1 MMA issuer | 2-5 converters (+ column sums of g for dbc) | 6-13 epilogue.
 constexpr int kGzRaw = 3, kGzLo = 2;
@@ -480,8 +483,9 @@ constexpr int kGzThreads = 14 * 32;
 
 struct GzArgs {
     float* T; float* part;
-    long long rows;
+    long long rows, groups;               // grid rows; row groups of F rows (the work items)
     int S2, LY, nch, single_pass;
+    int C, F, cshift;                     // channels (= 1 << cshift); C = 32 / 64: F = 128 / C consecutive grid rows share the 128 lanes
 };
 
 __global__ void __launch_bounds__(kGzThreads, 1)
@@ -518,7 +522,7 @@ gz_pass_tma(const __grid_constant__ CUtensorMap mapG, const __grid_constant__ CU
     tc_fence_after();
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
-    const uint32_t my_rows = (uint32_t)((a.rows - (long long)blockIdx.x + (long long)gridDim.x - 1) / (long long)gridDim.x);
+    const uint32_t my_rows = (uint32_t)((a.groups - (long long)blockIdx.x + (long long)gridDim.x - 1) / (long long)gridDim.x);
     const uint32_t nch = (uint32_t)a.nch;
     const uint32_t total = my_rows * nch;
 
@@ -528,13 +532,14 @@ gz_pass_tma(const __grid_constant__ CUtensorMap mapG, const __grid_constant__ CU
             uint32_t it = 0, ch = 0;
             for (uint32_t q = 0; q < total; ++q) {
                 const uint32_t s = q % kGzRaw;
-                const int row = (int)(blockIdx.x + it * gridDim.x);
+                const int row0 = (int)(blockIdx.x + it * gridDim.x) * a.F;
+                const int bpr = a.C / 32;                          // 32-channel blocks per grid row
                 mbar_wait(&raw_empty[s], ((q / kGzRaw) & 1) ^ 1);
                 mbar_expect_tx(&raw_full[s], 2u * 16384u + 8192u);
                 uint8_t* st = smem + (size_t)s * kGzStage;
-                for (int j = 0; j < 4; ++j) {                      // positions past the end of the row read as zeros (TMA bounds)
-                    tma_load_3d(&mapG, &raw_full[s], st + j * 4096, j * 32, (int)ch * 32, row);
-                    tma_load_3d(&mapX, &raw_full[s], st + kGzXOff + j * 4096, j * 32, (int)ch * 32, row);
+                for (int j = 0; j < 4; ++j) {                      // positions / rows past the end read as zeros (TMA bounds)
+                    tma_load_3d(&mapG, &raw_full[s], st + j * 4096, (j % bpr) * 32, (int)ch * 32, row0 + j / bpr);
+                    tma_load_3d(&mapX, &raw_full[s], st + kGzXOff + j * 4096, (j % bpr) * 32, (int)ch * 32, row0 + j / bpr);
                 }
                 tma_load_2d(&mapT, &raw_full[s], st + kGzTabOff, (int)ch * 32, 0);
                 if (++ch == nch) { ch = 0; ++it; }
@@ -641,12 +646,13 @@ gz_pass_tma(const __grid_constant__ CUtensorMap mapG, const __grid_constant__ CU
         // =========================================================================== epilogue (8 warps)
         const int ew = warp - 6, q4 = warp & 3, half = ew >> 2;      // TMEM lane quarter = warp % 4
         const int o = q4 * 32 + lane;
+        const int fr = o >> a.cshift, cc = o & (a.C - 1);            // lane = (row within the group, channel)
         const uint32_t lane_base = tmem_base + ((uint32_t)(q4 * 32) << 16);
         float acc[64];
 #pragma unroll
         for (int i = 0; i < 64; ++i) acc[i] = 0.f;
         for (uint32_t it = 0; it < my_rows; ++it) {
-            const long long row = (long long)blockIdx.x + (long long)it * gridDim.x;
+            const long long row = ((long long)blockIdx.x + (long long)it * gridDim.x) * a.F + fr;
             const uint32_t ybuf = it & 1u;
             // conv accumulator of the row -> registers (the issuer waits for this before the next row's conv MMAs)
             mbar_wait(cv_full, it & 1);
@@ -668,7 +674,8 @@ gz_pass_tma(const __grid_constant__ CUtensorMap mapG, const __grid_constant__ CU
             mbar_wait(&yd_full[ybuf], (it >> 1) & 1);
             tc_fence_after();
             const int l0 = half * 32;
-            float* op = a.T + ((size_t)row * a.LY + l0) * 128 + o;
+            float* op = a.T + ((((size_t)row * a.LY + l0) << a.cshift) + cc);
+            const int lmax = row < a.rows ? a.LY - l0 : 0;           // valid table rows of this warp's half
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 uint32_t m0[16], m1[16];
@@ -683,8 +690,8 @@ gz_pass_tma(const __grid_constant__ CUtensorMap mapG, const __grid_constant__ CU
                 }
 #pragma unroll
                 for (int i = 0; i < 16; ++i)
-                    if (l0 + h * 16 + i < a.LY)
-                        op[(size_t)(h * 16 + i) * 128] = __uint_as_float(m0[i]) + (a.single_pass ? 0.f : __uint_as_float(m1[i]));
+                    if (h * 16 + i < lmax)
+                        op[(size_t)(h * 16 + i) << a.cshift] = __uint_as_float(m0[i]) + (a.single_pass ? 0.f : __uint_as_float(m1[i]));
             }
         }
         float* pd = a.part + (size_t)blockIdx.x * cw_part_floats(128, 128) + (size_t)o * 128 + half * 64;
@@ -795,25 +802,30 @@ int tc_conv_wgrad(const float* g, const float* x, int act, float* dwc, float* db
 }
 
 
-// fused ydft(g) + conv weight gradient (gz_pass_tma): 128 channels on both sides, no activation on load, whole grid rows as
-// work items, and enough rows that the conv-wgrad workspace (sized by tc_conv_wgrad_workspace) holds one partial per CTA
+// fused ydft(g) + conv weight gradient (gz_pass_tma): 128 channels on both sides (or 32 / 64 with grid rows folded into the
+// lanes), no activation on load, whole row groups as work items -- problems with few long rows (1-D) keep the separate,
+// row-segmenting kernels.  The grid never exceeds the partial count tc_conv_wgrad_workspace sized the workspace for.
 bool tc_gz_pass_supported(const float* g, const float* x, const float* tab, int64_t rows, int S2, int LY, int Ci, int Co, int act) {
-    if (!tc_enabled() || act != 0 || Ci != 128 || Co != 128 || LY < 8 || LY > 64 || S2 % 4 != 0 || S2 < 4) return false;
-    if (rows < 2LL * sm_count_max() || rows * S2 < 512LL * sm_count_max() || rows >= (1LL << 30)) return false;
+    if (!tc_enabled() || act != 0 || Ci != Co || (Ci != 128 && Ci != 64 && Ci != 32) || LY < 8 || LY > 64 || S2 % 4 != 0 || S2 < 4)
+        return false;
+    const int F = 128 / Ci;
+    // (small L2-resident problems are launch bound either way and do better with every SM on the separate kernels)
+    if (rows >= (1LL << 30) || (rows + F - 1) / F < 4LL * sm_count() || (rows * S2) % F != 0) return false;
     if ((reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(tab)) & 15) return false;
     const char* e = getenv("FNM_NO_GZPASS");
     return !(e && e[0] == '1');
 }
 
 int tc_gz_pass(const float* g, const float* x, const float* tab, float* T, float* dwc, float* dbc, int64_t rows, int S2, int LY,
-               float* partial, int mode, cudaStream_t st) {
+               int C, float* partial, int mode, cudaStream_t st) {
     GzArgs a{};
     a.T = T; a.part = partial; a.rows = rows; a.S2 = S2; a.LY = LY; a.nch = (S2 + 31) / 32;
     a.single_pass = mode == FNM_MODE_TF32;
+    a.C = C; a.F = 128 / C; a.cshift = C == 128 ? 7 : (C == 64 ? 6 : 5); a.groups = (rows + a.F - 1) / a.F;
     CUtensorMap mg, mx, mt;
     {
-        const cuuint64_t dims[3] = {128, (cuuint64_t)S2, (cuuint64_t)rows};
-        const cuuint64_t str[2] = {128 * 4, (cuuint64_t)S2 * 128 * 4};
+        const cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)S2, (cuuint64_t)rows};
+        const cuuint64_t str[2] = {(cuuint64_t)C * 4, (cuuint64_t)S2 * C * 4};
         const cuuint32_t box[3] = {32, 32, 1};
         if (!tc_make_map_swz(&mg, g, 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B) ||
             !tc_make_map_swz(&mx, x, 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))
@@ -833,7 +845,10 @@ int tc_gz_pass(const float* g, const float* x, const float* tab, float* T, float
         if (e != cudaSuccess) return fail(FNM_ECUDA, "ydft_conv_wgrad: smem attribute: %s", cudaGetErrorString(e));
         once_done(attr_set, attr_set_dev);
     }
-    const int grid = rows < sm_count() ? (int)rows : sm_count();
+    // as many CTAs as conv_wgrad would use on the same (folded) problem: the workspace holds that many partials, and the small
+    // L2-resident problems get few partials for the reduction kernel
+    const int cap = cw_grid(rows * S2 / a.F);
+    const int grid = a.groups < cap ? (int)a.groups : cap;
     {
         LaunchScope ls("ydft_conv_wgrad", st);
         gz_pass_tma<<<grid, kGzThreads, smem, st>>>(mg, mx, mt, a);
@@ -841,7 +856,7 @@ int tc_gz_pass(const float* g, const float* x, const float* tab, float* T, float
     FNM_TRY(check_launch("ydft_conv_wgrad"));
     {
         LaunchScope ls("conv_wgrad_reduce", st);
-        conv_wgrad_tc_reduce<<<((128 * 128 + 128) * 32 + 255) / 256, 256, 0, st>>>(partial, grid, 128, 128, 1, dwc, dbc);
+        conv_wgrad_tc_reduce<<<((C * C + C) * 32 + 255) / 256, 256, 0, st>>>(partial, grid, C, C, a.F, dwc, dbc);
     }
     return check_launch("conv_wgrad_reduce");
 }

@@ -207,35 +207,44 @@ ydft_tma(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUten
             const long long pair = (long long)blockIdx.x + (long long)it * gridDim.x;
             mbar_wait(d_full, it & 1);
             tc_fence_after();
+            // accumulators -> registers for BOTH rows first, then the buffer is handed back: the issuer starts the next pair
+            // while this warp's 64 global stores are still in flight (the accumulators are single buffered)
+            float v[2][32];
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
                 if (j >= a.gpi) break;
-                const long long row = (pair * a.gpi + j) * a.F + fr;
                 const uint32_t taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)j * 256u + (uint32_t)l0;
-                uint32_t m0[32], m1[32];
-                tmem_ld32(taddr, m0);                               // main of the even chunks
-                if (nch > 1) tmem_ld32(taddr + 128u, m1);           // main of the odd chunks
-                tmem_ld_wait();
-                float v[32];
 #pragma unroll
-                for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(m0[i]) + (nch > 1 ? __uint_as_float(m1[i]) : 0.f);
-                if (!a.single_pass) {
-                    tmem_ld32(taddr + 64u, m0);                     // corrections, even / odd chunks
-                    if (nch > 1) tmem_ld32(taddr + 192u, m1);
+                for (int h = 0; h < 2; ++h) {                       // 16 columns at a time: 64 results + 32 temporaries live
+                    uint32_t m0[16], m1[16];
+                    tmem_ld16(taddr + h * 16, m0);                  // main of the even chunks
+                    if (nch > 1) tmem_ld16(taddr + 128u + h * 16, m1);      // main of the odd chunks
                     tmem_ld_wait();
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) v[i] += __uint_as_float(m0[i]) + (nch > 1 ? __uint_as_float(m1[i]) : 0.f);
-                }
-                if (row < a.rows) {
-                    float* op = a.out + ((size_t)row * a.LY + l0) * a.C + cc;
+                    for (int i = 0; i < 16; ++i) v[j][h * 16 + i] = __uint_as_float(m0[i]) + (nch > 1 ? __uint_as_float(m1[i]) : 0.f);
+                    if (!a.single_pass) {
+                        tmem_ld16(taddr + 64u + h * 16, m0);        // corrections, even / odd chunks
+                        if (nch > 1) tmem_ld16(taddr + 192u + h * 16, m1);
+                        tmem_ld_wait();
 #pragma unroll
-                    for (int i = 0; i < 32; ++i)
-                        if (l0 + i < a.LY) op[(size_t)i * a.C] = v[i];
+                        for (int i = 0; i < 16; ++i) v[j][h * 16 + i] += __uint_as_float(m0[i]) + (nch > 1 ? __uint_as_float(m1[i]) : 0.f);
+                    }
                 }
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(d_empty);
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                if (j >= a.gpi) break;
+                const long long row = (pair * a.gpi + j) * a.F + fr;
+                if (row < a.rows) {
+                    float* op = a.out + ((size_t)row * a.LY + l0) * a.C + cc;
+#pragma unroll
+                    for (int i = 0; i < 32; ++i)
+                        if (l0 + i < a.LY) op[(size_t)i * a.C] = v[j][i];
+                }
+            }
         }
     }
 

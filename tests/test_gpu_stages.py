@@ -266,13 +266,16 @@ def test_conv_wgrad(npos, Ci, Co, act, mode):
 
 # rows, S2, LY: the fused kernel needs >= 2 x 148 rows and 512 x 148 positions; (40, 64, 24) takes the two-call route behind
 # the same entry.  Ragged row lengths (72, 100: last chunk partly past the row), odd row counts, LY < 64 and LY % 4 != 0.
-@pytest.mark.parametrize("rows,S2,LY", [(2048, 256, 64), (1101, 72, 24), (999, 100, 26), (40, 64, 24), (4097, 32, 8)])
+@pytest.mark.parametrize("rows,S2,LY,C", [(2048, 256, 64, 128), (1101, 72, 24, 128), (999, 100, 26, 128), (40, 64, 24, 128),
+                                          (4097, 32, 8, 128),
+                                          # 32 / 64 channels: 4 / 2 grid rows folded into the 128 lanes (config-1 and config-4
+                                          # shapes; a row count that leaves the last group half empty)
+                                          (1440, 72, 24, 32), (2880, 144, 34, 64), (4098, 72, 24, 32), (2403, 40, 16, 64)])
 @pytest.mark.parametrize("mode", ["fp32", "tf32"])
-def test_ydft_conv_wgrad_fused(rows, S2, LY, mode):
+def test_ydft_conv_wgrad_fused(rows, S2, LY, C, mode):
     """fnm_ydft_conv_wgrad (one read of g for the backward y-DFT and the conv weight / bias gradient) against float64, and
     against the two separate entry points it replaces."""
     torch.manual_seed(11)
-    C = 128
     g = torch.randn(rows, S2, C, device=DEV) + 0.2                       # a mean: the DC column of the transform is large
     x = torch.randn(rows, S2, C, device=DEV) + 0.3
     tab = torch.randn(LY, S2, device=DEV) / S2 ** 0.5

@@ -39,5 +39,7 @@ for _ in range(reps):
     check(L.fnm_xdft(p(T), p(tab["ex"]), p(Xh), B, P1, R, NY, C_, 0, st))
     check(L.fnm_xsyn(p(Xh), p(tab["fx"]), p(Z), B, P1, R, NY, C_, 0, st))
     check(L.fnm_conv_wgrad(p(g), p(x), 0, p(dwc), p(dbc), rows * P2, C_, C_, p(ws), ws.numel(), 0, st))
+    # backward y-DFT of g fused with the conv weight gradient (one read of g)
+    check(L.fnm_ydft_conv_wgrad(p(g), p(x), p(tab["ay"]), p(T), p(dwc), p(dbc), rows, P2, LY, C_, p(ws), ws.numel(), 0, st))
 torch.cuda.synchronize()
 print("ok")
