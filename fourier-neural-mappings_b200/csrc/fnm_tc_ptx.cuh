@@ -203,6 +203,18 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
     d |= (uint64_t)2 << 61;                  // SWIZZLE_128B
     return d;
 }
+// The same descriptor as (constant high word, 32-bit low word): an issue loop then spends ONE 32-bit uniform add per MMA
+// operand instead of re-assembling 64-bit descriptors (the issuing warp is latency bound on its scalar instruction stream).
+constexpr uint32_t kKmajDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);
+__device__ __forceinline__ uint32_t kmaj_desc_lo(uint32_t saddr) { return ((saddr >> 4) & 0x3fffu) | (1u << 16); }
+// D[tmem] (+)= A[tmem] * B[K-major SWIZZLE_128B smem, low descriptor word]^T, kind::tf32
+__device__ __forceinline__ void umma_ts_lo(uint32_t d, uint32_t a_tmem, uint32_t bdesc_lo, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t.reg .b64 bd;\n\tmov.b64 bd, {%2, %5};\n\telect.sync _|q, 0xffffffff;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], bd, %3, p;\n\t}" ::"r"(d),
+        "r"(a_tmem), "r"(bdesc_lo), "r"(idesc), "r"(accum), "r"(kKmajDescHi)
+        : "memory");
+}
 // kind::tf32 instruction descriptor (cute::UMMA::InstrDescriptor): fp32 accumulate, K-major A and B
 __host__ __device__ inline uint32_t make_idesc(int M, int N) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
@@ -306,6 +318,11 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* ba
 __device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2) {
     asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
                  ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_load_5d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2, int c3, int c4) {
+    asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+                 ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
                  : "memory");
 }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {

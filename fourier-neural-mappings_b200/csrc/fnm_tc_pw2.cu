@@ -784,7 +784,7 @@ bool tc_make_map_swz(CUtensorMap* m, const float* ptr, int rank, const cuuint64_
                      const cuuint32_t* box, CUtensorMapSwizzle swizzle) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return false;
-    const cuuint32_t estr[3] = {1, 1, 1};
+    const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
     const CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<float*>(ptr), dims, strides_bytes,
                           box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

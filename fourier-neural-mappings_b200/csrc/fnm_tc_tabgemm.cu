@@ -10,9 +10,13 @@
 // Formulation: channels are the MMA M dimension (128 TMEM lanes; C < 128 packs 128/C groups side
 // by side, C > 128 splits into 128-channel blocks), the table rows are N, k is K:
 //     D[lane = (g_local, c)][m] = sum_k A[lane][k] * tab[m][k]
-//   A : activations, read with coalesced 128-byte warp loads (lane = channel), converted in REGISTERS
-//       (optional GELU, hi/lo TF32 split) and written to TMEM with tcgen05.st -- they never touch
-//       shared memory;
+//   A : activations, converted in REGISTERS (lane = channel; optional GELU, hi/lo TF32 split) and written to TMEM
+//       with tcgen05.st.  They reach the registers through a TMA-fed shared-memory ring of [32 k][128 lanes] chunks
+//       (a_tma; one 5-D tensor map covers the two-level strides of g and k): TMEM has room for only two to four A
+//       buffers next to the accumulators, and with global loads straight into registers that hand-over depth was also
+//       the number of chunks in flight from HBM (xdft / xsyn ran latency bound at 2 TB/s); the ring keeps up to six
+//       chunks (96 KB) in flight per SM independently of it.  Shapes TMA cannot address fall back to coalesced
+//       128-byte warp loads;
 //   B : table slabs [m][32 k] in the canonical K-major SWIZZLE_128B layout, hi and lo parts, either
 //       resident for the whole kernel (ydft) or streamed through a ring (xdft / xsyn);
 //   D : fp32 accumulator in TMEM; epilogue warps tcgen05.ld it and store 128 contiguous bytes per
@@ -26,6 +30,7 @@
 //   warps 16-19 table loaders (group 1) when the table is streamed, otherwise idle register donors
 #include "fnm_tc_ptx.cuh"
 
+#include <cstdio>
 #include <cstdlib>
 
 namespace fnm {
@@ -48,7 +53,14 @@ struct TgArgs {
     int act, single_pass, tab_vec4;
     int pairs;                                             // A loaders take pairs of chunks (needs 4 A buffers) instead of single chunks
     int tab_tma;                                           // streamed table: raw slabs arrive by TMA, the table warps only derive the remainder
+    int a_tma, a_slots, a_kb;                              // A chunks through a TMA-fed ring of a_slots x 16 KB; k rows per TMA box (32 or 8)
+    int lslots;                                            // tab_tma: `slots` counts RAW slabs (TMA targets), the remainder slabs have their own ring
 };
+
+constexpr int kTgLoBar = 32;                               // tab_full / tab_empty index of the first remainder-ring barrier
+
+constexpr int kTgMaxARing = 8;
+constexpr uint32_t kTgAChunk = 16384;                      // [32 k][128 lanes] fp32
 
 __device__ __forceinline__ float ld_stream1(const float* p) {
     float v;
@@ -56,11 +68,18 @@ __device__ __forceinline__ float ld_stream1(const float* p) {
     return v;
 }
 
-__global__ void __launch_bounds__(kTgThreads, 1) tabgemm_tc(const __grid_constant__ CUtensorMap mapT, const TgArgs a) {
+__global__ void __launch_bounds__(kTgThreads, 1) tabgemm_tc(const __grid_constant__ CUtensorMap mapT, const __grid_constant__ CUtensorMap mapA,
+                                                            const TgArgs a) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const uint32_t slot_bytes = (uint32_t)a.NT * 256u;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)a.slots * slot_bytes);
+    // streamed table by TMA: [slots raw slabs][lslots remainder slabs], NT x 128 bytes each -- a slab in flight from L2 then
+    // takes 16 KB, not a whole (hi | lo) slot, and the ring is deep enough to cover the L2 latency (xdft / xsyn were bound
+    // by exactly that: one slab ahead per loader group)
+    const uint32_t raw_bytes = (uint32_t)a.NT * 128u;
+    uint8_t* lo_ring = smem + (size_t)a.slots * raw_bytes;
+    uint8_t* aring = a.tab_tma ? lo_ring + (size_t)a.lslots * raw_bytes : smem + (size_t)a.slots * slot_bytes;   // [a_slots][GL][32 k][min(C, 128)] (a_tma)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(aring + (size_t)a.a_slots * kTgAChunk);
     uint64_t* tab_full = bars;                                 // [kTgMaxSlots]
     uint64_t* tab_empty = bars + kTgMaxSlots;                  // [kTgMaxSlots]
     uint64_t* tab_raw = bars + 2 * kTgMaxSlots;                // [kTgMaxSlots] TMA transaction barriers (tab_tma)
@@ -68,7 +87,9 @@ __global__ void __launch_bounds__(kTgThreads, 1) tabgemm_tc(const __grid_constan
     uint64_t* a_empty = a_full + kTgMaxBuf;                    // [kTgMaxBuf]
     uint64_t* d_full = a_empty + kTgMaxBuf;                    // [2]
     uint64_t* d_empty = d_full + 2;                            // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d_empty + 2);
+    uint64_t* ar_full = d_empty + 2;                           // [kTgMaxARing] TMA transaction barriers of the A ring
+    uint64_t* ar_empty = ar_full + kTgMaxARing;                // [kTgMaxARing] the 4 warps of the consuming warpgroup
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ar_empty + kTgMaxARing);
 
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
 
@@ -78,10 +99,13 @@ __global__ void __launch_bounds__(kTgThreads, 1) tabgemm_tc(const __grid_constan
             mbar_init(&tab_empty[s], 1);
             mbar_init(&tab_raw[s], 1);
         }
+        for (int s = 0; s < a.lslots; ++s) { mbar_init(&tab_full[kTgLoBar + s], (s & 1) ? 4 : kTgTabWarps); mbar_init(&tab_empty[kTgLoBar + s], 1); }
         for (int s = 0; s < a.nbuf; ++s) { mbar_init(&a_full[s], 4); mbar_init(&a_empty[s], 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(&d_full[s], 1); mbar_init(&d_empty[s], 4); }
+        for (int s = 0; s < a.a_slots; ++s) { mbar_init(&ar_full[s], 1); mbar_init(&ar_empty[s], 4); }
         fence_barrier_init();
         if (a.tab_tma) tma_prefetch_desc(&mapT);
+        if (a.a_tma) tma_prefetch_desc(&mapA);
     }
     if (warp == 4) tmem_alloc(tmem_slot, 512);
     tc_fence_before();
@@ -159,9 +183,16 @@ __global__ void __launch_bounds__(kTgThreads, 1) tabgemm_tc(const __grid_constan
         asm volatile("setmaxnreg.dec.sync.aligned.u32 72;\n");
         const uint32_t sbase = smem_u32(smem);
         const uint32_t idesc = make_idesc(128, a.NT);
-        uint32_t qa = 0, qs = 0, dcount = 0;
+        // Ring positions and phases advance incrementally: the issuer is a single instruction stream, and a `q % slots` /
+        // `q / slots` with a run-time divisor is a ~25-instruction dependent sequence -- with five of them per chunk the issuer,
+        // not the data, paced xdft / xsyn (ncu stall sampling: the issuing warp never waited).
+        uint32_t ab = 0, aph = 0;                 // A buffer of the next chunk and its phase
+        uint32_t slot = 0, sph = 0;               // streamed table: raw (or hi | lo) slot and phase
+        uint32_t ls = 0, lph = 0;                 // tab_tma: remainder slot and phase
+        uint32_t dcount = 0;
+        const uint32_t nbuf = (uint32_t)a.nbuf, nslots = (uint32_t)a.slots, nls = (uint32_t)a.lslots;
         for (int it = 0; it < my_items; ++it) {
-            const uint32_t qa_item = qa;
+            const uint32_t ab_item = ab, aph_item = aph;
             for (int nt = 0; nt < a.ntiles; ++nt, ++dcount) {
                 const int dbuf = a.dbl ? (int)(dcount & 1) : 0;
                 const uint32_t dpar = a.dbl ? ((dcount >> 1) & 1) : (dcount & 1);
@@ -176,40 +207,73 @@ __global__ void __launch_bounds__(kTgThreads, 1) tabgemm_tc(const __grid_constan
                 // MMAs of the next one.
                 const uint32_t dstride = (uint32_t)((a.nmain + a.ncorr) * a.NT);
                 const uint32_t d0 = tmem_base + dcol0 + (uint32_t)dbuf * dstride, dc = a.ncorr ? d0 + (uint32_t)(a.nmain * a.NT) : d0;
-                uint32_t accum = 0, accum_m[2] = {0u, 0u};
-                for (int ch = 0; ch < a.nchunks; ++ch) {
-                    uint32_t q;
-                    bool first_use, last_use;
-                    if (a.reuse) { q = qa_item + ch; first_use = nt == 0; last_use = nt == a.ntiles - 1; }
-                    else { q = qa++; first_use = last_use = true; }
-                    const uint32_t ab = q % (uint32_t)a.nbuf;
-                    if (first_use) mbar_wait(&a_full[ab], (q / (uint32_t)a.nbuf) & 1);
-                    uint32_t slot, spar;
-                    if (a.resident) { slot = (uint32_t)(nt * a.nchunks + ch); spar = 0; }
-                    else { slot = qs % (uint32_t)a.slots; spar = (qs / (uint32_t)a.slots) & 1; ++qs; }
-                    mbar_wait(&tab_full[slot], spar);
-                    tc_fence_after();
-                    const uint32_t a_hi = tmem_base + ab * 64u, a_lo = a_hi + 32u;
-                    const uint32_t sb = sbase + slot * slot_bytes;
-                    const uint64_t bhi = make_desc(sb), blo = make_desc(sb + (uint32_t)a.NT * 128u);
-                    const int nks = min(4, (a.Kt - ch * 32 + 7) / 8);
-                    for (int ks = 0; ks < nks; ++ks) {
-                        const int mi = a.nmain == 2 ? (ch & 1) : 0;
-                        umma_ts(d0 + (uint32_t)(mi * a.NT), a_hi + ks * 8, bhi + 2 * ks, idesc, accum_m[mi]);
-                        accum_m[mi] = 1;
-                        if (!a.single_pass) {
-                            umma_ts(dc, a_lo + ks * 8, bhi + 2 * ks, idesc, a.ncorr ? accum : 1u);
-                            umma_ts(dc, a_hi + ks * 8, blo + 2 * ks, idesc, 1);
+                uint32_t accum = 0, accum0 = 0, accum1 = 0;
+                if (a.reuse) { ab = ab_item; aph = aph_item; }        // every table tile re-reads the item's A chunks
+                const bool first_use = !a.reuse || nt == 0, last_use = !a.reuse || nt == a.ntiles - 1;
+                int krem = a.Kt;
+                for (int ch = 0; ch < a.nchunks; ++ch, krem -= 32) {
+                    if (first_use) mbar_wait(&a_full[ab], aph);
+                    uint32_t bhi, blo;                               // low descriptor words of the hi / remainder slab
+                    uint32_t eslot, elslot = 0;
+                    if (a.tab_tma) {
+                        // raw slab and remainder slab live in separate rings; the remainder's barrier also covers the raw slab
+                        // (the converting warps waited for it)
+                        mbar_wait(&tab_full[kTgLoBar + ls], lph);
+                        bhi = uniform_u32(kmaj_desc_lo(sbase + slot * raw_bytes));
+                        blo = uniform_u32(kmaj_desc_lo(sbase + (nslots + ls) * raw_bytes));
+                        eslot = slot; elslot = (uint32_t)kTgLoBar + ls;
+                        if (++slot == nslots) { slot = 0; sph ^= 1u; }
+                        if (++ls == nls) { ls = 0; lph ^= 1u; }
+                    } else {
+                        if (a.resident) { eslot = (uint32_t)(nt * a.nchunks + ch); mbar_wait(&tab_full[eslot], 0); }
+                        else {
+                            eslot = slot;
+                            mbar_wait(&tab_full[eslot], sph);
+                            if (++slot == nslots) { slot = 0; sph ^= 1u; }
                         }
-                        accum = 1;
+                        const uint32_t sb = sbase + eslot * slot_bytes;
+                        bhi = uniform_u32(kmaj_desc_lo(sb)); blo = bhi + (((uint32_t)a.NT * 128u) >> 4);
                     }
+                    tc_fence_after();
+                    const uint32_t a_hi = uniform_u32(tmem_base + ab * 64u), a_lo = a_hi + 32u;
+                    const int nks = krem >= 32 ? 4 : (krem + 7) >> 3;
+                    const bool odd = a.nmain == 2 && (ch & 1);
+                    const uint32_t dm = uniform_u32(odd ? d0 + (uint32_t)a.NT : d0);
+                    uint32_t acc_m = odd ? accum1 : accum0;
+                    const uint32_t acc_c = a.ncorr ? accum : 1u;
+                    if (nks == 4) {
+                        // the common chunk, fully unrolled: every operand is `uniform base + immediate`
+                        if (a.single_pass) {
+#pragma unroll
+                            for (int ks = 0; ks < 4; ++ks) umma_ts_lo(dm, a_hi + ks * 8, bhi + 2 * ks, idesc, ks == 0 ? acc_m : 1u);
+                        } else {
+#pragma unroll
+                            for (int ks = 0; ks < 4; ++ks) {
+                                umma_ts_lo(dm, a_hi + ks * 8, bhi + 2 * ks, idesc, ks == 0 ? acc_m : 1u);
+                                umma_ts_lo(dc, a_lo + ks * 8, bhi + 2 * ks, idesc, ks == 0 ? acc_c : 1u);
+                                umma_ts_lo(dc, a_hi + ks * 8, blo + 2 * ks, idesc, 1u);
+                            }
+                        }
+                    } else {
+                        for (int ks = 0; ks < nks; ++ks) {
+                            umma_ts_lo(dm, a_hi + ks * 8, bhi + 2 * ks, idesc, acc_m);
+                            acc_m = 1;
+                            if (!a.single_pass) {
+                                umma_ts_lo(dc, a_lo + ks * 8, bhi + 2 * ks, idesc, (ks == 0) ? acc_c : 1u);
+                                umma_ts_lo(dc, a_hi + ks * 8, blo + 2 * ks, idesc, 1);
+                            }
+                        }
+                    }
+                    accum = 1;
+                    if (odd) accum1 = 1; else accum0 = 1;
                     if (last_use) umma_commit(&a_empty[ab]);
-                    if (!a.resident) umma_commit(&tab_empty[slot]);
+                    if (!a.resident) umma_commit(&tab_empty[eslot]);
+                    if (a.tab_tma) umma_commit(&tab_empty[elslot]);
+                    if (++ab == nbuf) { ab = 0; aph ^= 1u; }
                 }
                 umma_commit(&d_full[dbuf]);
                 __syncwarp();
             }
-            if (a.reuse) qa += (uint32_t)a.nchunks;
         }
     } else if (warp < kTgFirstA || warp >= kTgFirstA + 4 * kTgNwg) {
         // =========================================================================== table loaders
@@ -275,27 +339,35 @@ __global__ void __launch_bounds__(kTgThreads, 1) tabgemm_tc(const __grid_constan
                 const uint32_t r = q % per_item;
                 const int nt = (int)(r / (uint32_t)a.nchunks), ch = (int)(r - (uint32_t)nt * a.nchunks);
                 mbar_wait(&tab_empty[slot], ((q / (uint32_t)a.slots) & 1) ^ 1);
-                mbar_expect_tx(&tab_raw[slot], (uint32_t)a.NT * 128u);
-                tma_load_2d(&mapT, &tab_raw[slot], smem + (size_t)slot * slot_bytes, ch * 32, nt * a.NT);
+                mbar_expect_tx(&tab_raw[slot], raw_bytes);
+                tma_load_2d(&mapT, &tab_raw[slot], smem + (size_t)slot * raw_bytes, ch * 32, nt * a.NT);
             };
             if (issuer)
                 for (uint32_t q = (uint32_t)grp; q < total && q < (uint32_t)grp + 2u * ahead; q += 2) issue(q);   // slots empty: no wait
             for (uint32_t q = (uint32_t)grp; q < total; q += 2) {
-                const uint32_t slot = q % (uint32_t)a.slots;
+                const uint32_t slot = q % (uint32_t)a.slots, ls = q % (uint32_t)a.lslots;
                 mbar_wait(&tab_raw[slot], (q / (uint32_t)a.slots) & 1);
-                const uint32_t raw0 = smem_u32(smem) + slot * slot_bytes + (uint32_t)tt * 16u;
-                const uint32_t half = (uint32_t)a.NT * 128u;
-                for (uint32_t off = (uint32_t)tt * 16u; off < half; off += (uint32_t)gthreads * 16u) {
-                    float4 v;
-                    const uint32_t src = raw0 + (off - (uint32_t)tt * 16u);
-                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(src));
+                mbar_wait(&tab_empty[kTgLoBar + ls], ((q / (uint32_t)a.lslots) & 1) ^ 1);
+                const uint32_t raw0 = smem_u32(smem) + slot * raw_bytes, lo0 = smem_u32(lo_ring) + ls * raw_bytes;
+                // two 16-byte pieces per thread and pass: the loads of a pass are in flight together
+                for (uint32_t off = (uint32_t)tt * 16u; off < raw_bytes; off += (uint32_t)gthreads * 32u) {
+                    float4 v, w;
+                    const uint32_t off2 = off + (uint32_t)gthreads * 16u;
+                    const bool two = off2 < raw_bytes;
+                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(raw0 + off));
+                    if (two) asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(w.x), "=f"(w.y), "=f"(w.z), "=f"(w.w) : "r"(raw0 + off2));
                     v.x -= __uint_as_float(__float_as_uint(v.x) & 0xffffe000u); v.y -= __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
                     v.z -= __uint_as_float(__float_as_uint(v.z) & 0xffffe000u); v.w -= __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
-                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(src + half), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(lo0 + off), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+                    if (two) {
+                        w.x -= __uint_as_float(__float_as_uint(w.x) & 0xffffe000u); w.y -= __uint_as_float(__float_as_uint(w.y) & 0xffffe000u);
+                        w.z -= __uint_as_float(__float_as_uint(w.z) & 0xffffe000u); w.w -= __uint_as_float(__float_as_uint(w.w) & 0xffffe000u);
+                        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(lo0 + off2), "f"(w.x), "f"(w.y), "f"(w.z), "f"(w.w) : "memory");
+                    }
                 }
                 fence_proxy_async();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&tab_full[slot]);
+                if (lane == 0) mbar_arrive(&tab_full[kTgLoBar + ls]);
                 // refill the ring AFTER handing slab q over: the slot wanted is the one slab q - 2 occupied, whose MMAs
                 // have usually retired by now, so the conversion above never waits behind this
                 if (issuer && q + 2u * ahead < total) issue(q + 2u * ahead);
@@ -378,7 +450,56 @@ __global__ void __launch_bounds__(kTgThreads, 1) tabgemm_tc(const __grid_constan
         // With a streamed table TMEM only has room for two A buffers (three accumulators): each warpgroup
         // then takes single chunks, alternating, so one warpgroup's loads fly while the other converts.
         float va[32], vb[32];
-        if (a.pairs) {
+        if (a.a_tma) {
+            // TMA-fed ring.  This warpgroup's chunks, in order: n = 0, 1, ... -> q(n) (single chunks: every other one; pairs:
+            // two consecutive ones out of four).  Thread 0 of the warpgroup issues the boxes of chunk n + ahead once the four
+            // warps have read chunk n out of the slot it reuses (q(n + ahead) = q(n) + a_slots: the slots are private to a
+            // warpgroup), so up to a_slots chunks are in flight per SM whatever the TMEM hand-over depth is.
+            const uint32_t ahead = (uint32_t)a.a_slots / 2u;
+            auto qof = [&](uint32_t n) { return a.pairs ? 4u * (n >> 1) + 2u * (uint32_t)wg + (n & 1u) : (uint32_t)wg + 2u * n; };
+            const bool issuer = q4 == 0 && lane == 0;
+            const int Cb = a.C >= 128 ? 128 : a.C;
+            auto issue = [&](uint32_t n) {
+                const uint32_t q = qof(n);
+                if (q >= total) return;
+                const uint32_t slot = q % (uint32_t)a.a_slots;
+                mbar_wait(&ar_empty[slot], ((q / (uint32_t)a.a_slots) & 1) ^ 1);
+                mbar_expect_tx(&ar_full[slot], kTgAChunk);
+                const int it = (int)(q / (uint32_t)per_item);
+                const int ch = (int)(q - (uint32_t)it * per_item) % a.nchunks;
+                const int item = (int)blockIdx.x + it * (int)gridDim.x;
+                uint8_t* dst = aring + (size_t)slot * kTgAChunk;
+                for (int gl = 0; gl < a.GL; ++gl) {
+                    int g, c0;
+                    if (a.C >= 128) { g = item / a.CB; c0 = (item - g * a.CB) * 128; }
+                    else { g = item * a.GL + gl; c0 = 0; }
+                    // groups / k rows past the end are outside the tensor map and read as zeros
+                    const int gq = a.gin_div >= a.G ? 0 : g / a.gin_div, gr = a.gin_div >= a.G ? g : g - gq * a.gin_div;
+                    for (int kk = 0; kk < 32; kk += a.a_kb) {
+                        const int k = ch * 32 + kk;
+                        const int kq = a.kin_div >= a.Kt ? 0 : k / a.kin_div, kr = a.kin_div >= a.Kt ? k : k - kq * a.kin_div;
+                        tma_load_5d(&mapA, &ar_full[slot], dst + ((size_t)gl * 32 + kk) * Cb * 4, c0, kr, kq, gr, gq);
+                    }
+                }
+            };
+            if (issuer)
+                for (uint32_t n = 0; n < ahead; ++n) issue(n);
+            const int gl_me = a.C >= 128 ? 0 : L / a.C, c_me = a.C >= 128 ? L : L % a.C;
+            for (uint32_t n = 0;; ++n) {
+                const uint32_t q = qof(n);
+                if (q >= total) break;
+                const uint32_t slot = q % (uint32_t)a.a_slots;
+                mbar_wait(&ar_full[slot], (q / (uint32_t)a.a_slots) & 1);
+                const float* src = reinterpret_cast<const float*>(aring + (size_t)slot * kTgAChunk) + (size_t)gl_me * 32 * Cb + c_me;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) va[j] = src[j * Cb];
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&ar_empty[slot]);
+                if (issuer) issue(n + ahead);
+                __syncwarp();                                       // the issuing lane rejoins before the warp-wide TMEM stores
+                process(va, q);
+            }
+        } else if (a.pairs) {
             for (uint32_t q = 2u * (uint32_t)wg; q < total; q += 2u * kTgNwg) {
                 load(va, q);
                 const bool two = q + 1 < total;
@@ -462,8 +583,6 @@ static bool tab_tma_enabled() {
 static int tg_launch(TgArgs& a, const char* what, cudaStream_t st) {
     if (!tg_configure(a)) return fail(FNM_ENOTSUP, "%s: shape not served by the tcgen05 table GEMM", what);
     a.tab_vec4 = (a.Kt % 4 == 0 && (reinterpret_cast<uintptr_t>(a.tab) & 15) == 0) ? 1 : 0;
-    size_t smem = (size_t)a.slots * a.NT * 256 + 1024 + (3 * kTgMaxSlots + 2 * kTgMaxBuf + 4) * 8 + 16;
-    if (smem < 120 * 1024) smem = 120 * 1024;                    // one CTA per SM (each owns all 512 TMEM columns)
     static std::atomic<uint64_t> attr_set{0};
     int attr_set_dev = 0;
     if (once_needed(attr_set, attr_set_dev)) {
@@ -471,19 +590,58 @@ static int tg_launch(TgArgs& a, const char* what, cudaStream_t st) {
         if (e != cudaSuccess) return fail(FNM_ECUDA, "%s: smem attribute: %s", what, cudaGetErrorString(e));
         once_done(attr_set, attr_set_dev);
     }
-    // streamed table: TMA the raw slabs when the rows are 16-byte aligned and each group can keep a slab ahead
-    CUtensorMap mapT{};
-    a.tab_tma = 0;
-    if (!a.resident && a.slots >= 4 && a.Kt % 4 == 0 && (reinterpret_cast<uintptr_t>(a.tab) & 15) == 0 && tab_tma_enabled()) {
+    const size_t bar_bytes = 1024 + (3 * kTgMaxSlots + 2 * kTgMaxBuf + 4 + 2 * kTgMaxARing) * 8 + 16, total_smem = 227u * 1024u;
+    // A chunks through a TMA-fed ring when one 5-D tensor map can address them: dims (c, k_lo, k_hi, g_lo, g_hi), chunks of
+    // 32 k that never straddle a k_hi step (boxes of 32 or 8 rows), 16-byte aligned base and strides
+    CUtensorMap mapA{}, mapT{};
+    a.a_tma = 0; a.a_kb = 32; a.a_slots = 0; a.tab_tma = 0; a.lslots = 0;
+    const bool k_uniform = a.kin_div >= a.Kt, g_uniform = a.gin_div >= a.G;
+    const int kb = (k_uniform || a.kin_div % 32 == 0) ? 32 : (a.kin_div % 8 == 0 ? 8 : 0);
+    bool a_ok;
+    {
+        const char* e = getenv("FNM_TAB_NO_ATMA");
+        a_ok = !(e && e[0] == '1') && kb && (reinterpret_cast<uintptr_t>(a.in) & 15) == 0 &&
+               (k_uniform || a.Kt % a.kin_div == 0) && (g_uniform || a.G % a.gin_div == 0) &&
+               a.k_s0 % 4 == 0 && a.gin_s0 % 4 == 0 && (k_uniform || a.k_s1 % 4 == 0) && (g_uniform || a.gin_s1 % 4 == 0);
+    }
+    // streamed table: TMA the raw slabs when the rows are 16-byte aligned.  Ring of raw slabs (as many as fit next to four
+    // remainder slabs and a four-chunk A ring) + ring of remainder slabs
+    if (!a.resident && a.Kt % 4 == 0 && (reinterpret_cast<uintptr_t>(a.tab) & 15) == 0 && tab_tma_enabled()) {
+        const size_t raw = (size_t)a.NT * 128, want_a = a_ok ? 4 * (size_t)kTgAChunk : 0;
+        int rs = (int)((total_smem - bar_bytes - want_a - 4 * raw) / raw);
+        rs = (rs > 14 ? 14 : rs) & ~1;
         const cuuint64_t dims[2] = {(cuuint64_t)a.Kt, (cuuint64_t)a.Mt};
         const cuuint64_t str[1] = {(cuuint64_t)a.Kt * 4};
         const cuuint32_t box[2] = {32, (cuuint32_t)a.NT};
-        if (tc_make_map(&mapT, a.tab, 2, dims, str, box, true)) a.tab_tma = 1;
+        if (rs >= 4 && tc_make_map(&mapT, a.tab, 2, dims, str, box, true)) { a.tab_tma = 1; a.slots = rs; a.lslots = 4; }
+    }
+    const size_t tab_bytes = a.tab_tma ? (size_t)(a.slots + a.lslots) * a.NT * 128 : (size_t)a.slots * a.NT * 256;
+    if (a_ok) {
+        const cuuint64_t any = (cuuint64_t)a.C * 4;               // stride of an extent-1 dimension (never used)
+        const cuuint64_t dims[5] = {(cuuint64_t)a.C, (cuuint64_t)(k_uniform ? a.Kt : a.kin_div), (cuuint64_t)(k_uniform ? 1 : a.Kt / a.kin_div),
+                                    (cuuint64_t)(g_uniform ? a.G : a.gin_div), (cuuint64_t)(g_uniform ? 1 : a.G / a.gin_div)};
+        const cuuint64_t str[4] = {(cuuint64_t)a.k_s0 * 4, k_uniform ? any : (cuuint64_t)a.k_s1 * 4, (cuuint64_t)a.gin_s0 * 4,
+                                   g_uniform ? any : (cuuint64_t)a.gin_s1 * 4};
+        const cuuint32_t box[5] = {(cuuint32_t)(a.C >= 128 ? 128 : a.C), (cuuint32_t)kb, 1, 1, 1};
+        // the ring takes what the table leaves of the shared memory: 4 to 8 chunks (pairs: whole groups of 4)
+        int as = tab_bytes + bar_bytes < total_smem ? (int)((total_smem - tab_bytes - bar_bytes) / kTgAChunk) : 0;
+        as = as > 6 && !a.pairs ? 6 : as;
+        as = a.pairs ? (as >= 8 ? 8 : (as >= 4 ? 4 : 0)) : (as & ~1);
+        if (as >= 4 && tc_make_map_swz(&mapA, a.in, 5, dims, str, box, CU_TENSOR_MAP_SWIZZLE_NONE)) { a.a_tma = 1; a.a_kb = kb; a.a_slots = as; }
+    }
+    size_t smem = tab_bytes + (size_t)a.a_slots * kTgAChunk + bar_bytes;
+    if (smem < 120 * 1024) smem = 120 * 1024;                    // one CTA per SM (each owns all 512 TMEM columns)
+    {
+        const char* e = getenv("FNM_TG_DEBUG");
+        if (e && e[0] == '1')
+            fprintf(stderr, "[tabgemm %s] C=%d G=%d Kt=%d Mt=%d NT=%d ntiles=%d nchunks=%d nbuf=%d nmain=%d ncorr=%d dbl=%d resident=%d slots=%d lslots=%d "
+                    "pairs=%d tab_tma=%d a_tma=%d a_slots=%d a_kb=%d smem=%zu\n", what, a.C, a.G, a.Kt, a.Mt, a.NT, a.ntiles, a.nchunks, a.nbuf,
+                    a.nmain, a.ncorr, a.dbl, a.resident, a.slots, a.lslots, a.pairs, a.tab_tma, a.a_tma, a.a_slots, a.a_kb, smem);
     }
     const int grid = a.items < sm_count() ? a.items : sm_count();
     {
         LaunchScope ls(what, st);
-        tabgemm_tc<<<grid, kTgThreads, smem, st>>>(mapT, a);
+        tabgemm_tc<<<grid, kTgThreads, smem, st>>>(mapT, mapA, a);
     }
     return check_launch(what);
 }
