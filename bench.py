@@ -241,6 +241,11 @@ def cpu_baseline(workload, budget_s=25.0):
             "sample": f"batch {cpu_batch} of {batch} (largest that fits the {budget_s:.0f} s budget), {n} steps after 1 warm-up, {dt:.1f} s"}
 
 
+# SMs reserved for (and CTAs granted to) the NCCL kernels of the overlapped gradient exchange, by world size: ring
+# channels at 2 GPUs need more CTAs than the NVLS (in-switch) reduction at 4 and 8
+DP_SMS = {2: 16, 4: 16, 8: 16}
+
+
 def gpu_comparator(workload, steps, warmup, allow_tf32, dev):
     """The reference's OWN GPU path on this box: the oracle port -- the same torch.fft.rfft2 / irfft2
     (cuFFT), einsum (cuBLAS), 1x1 Conv (cuDNN), F.gelu and reference-semantics Adam calls as /root/reference/models/shared.py:
@@ -318,6 +323,15 @@ def run_ours(args, rank, world):
     # NCCL's log level is the caller's to choose (the driver reads the communicator lines); only a default is set here,
     # and it is NOT silenced.  The JSON line is the last line of stdout either way.
     os.environ.setdefault("NCCL_DEBUG", "WARN")
+    if world > 1:
+        # The gradient exchange runs UNDER the backward pass: the persistent kernels leave DP_SMS[world] SMs free while an
+        # all-reduce is in flight and NCCL is held to as many CTAs (measured with tools/dp_timeline.py, profiles/README.md).
+        # Both are defaults the caller's environment overrides.
+        k = os.environ.setdefault("FNM_DP_SM_RESERVE", str(DP_SMS.get(world, 12)))
+        if int(k) > 0:
+            os.environ.setdefault("NCCL_MAX_CTAS", k)
+            os.environ.setdefault("NCCL_MAX_NCHANNELS", k)
+            os.environ.setdefault("NCCL_NVLS_NCHANNELS", k)
     import torch.distributed as dist
     import fnm_b200
     from fnm_b200 import _lib
@@ -526,7 +540,7 @@ def run_ours(args, rank, world):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32" if args.mode == "fp32" else "tf32", "data": "synthetic",
         "config": {"workload": f"{args.workload}: {desc}", "batch_per_gpu": batch, "global_batch": batch * world,
-                   "parallelism": f"dp{world}", "sm_reserve_backward": sm_reserve, "compute_mode": fnm_b200.get_compute_mode(), "cuda_graph": bool(args.graph),
+                   "parallelism": f"dp{world}", "sm_reserve_backward": sm_reserve, "nccl_max_ctas": os.environ.get("NCCL_MAX_CTAS") if world > 1 else None, "compute_mode": fnm_b200.get_compute_mode(), "cuda_graph": bool(args.graph),
                    "tcgen05": bool(_lib.lib().fnm_has_tcgen05()),
                    "l2": ("working set %.0f MB per activation, larger than the 126 MB L2" % (wl["A"] / 1e6))
                    if wl["A"] > 126e6 else "working set fits L2 (back-to-back steps, no flush)",

@@ -13,6 +13,7 @@ CSRC_DIR = os.path.join(_HERE, "csrc")
 
 FNM_W_REFERENCE, FNM_W_MODE_MAJOR = 0, 1
 FNM_PLAN_ZOUT_IS_GELU_GRAD, FNM_PLAN_PRE_IS_GELU_GRAD = 1, 2
+FNM_PLAN_BWD_WEIGHTS_ONLY, FNM_PLAN_BWD_INPUT_ONLY = 4, 8
 FNM_PW_MUL_IS_GRAD, FNM_PW_OUT_IS_GRAD = 1, 2
 FNM_MODE_FP32 = 0
 FNM_MODE_TF32 = 1

@@ -112,20 +112,27 @@ class Adam(Optimizer):
         self.sync_steps()
         return super().state_dict()
 
+    supports_partial_step = True
+
     @torch.no_grad()
-    def step(self, closure=None):
+    def step(self, closure=None, params=None, continued=False):
+        """``params`` (extension): update only these parameters -- one optimizer step may then be spread over several
+        calls with disjoint subsets (``continued=True`` on every call but the first: they share the step's device counter
+        increment).  The data-parallel train step uses it to update each group as soon as its gradients have been exchanged."""
         loss = None
         if closure is not None:
             with torch.enable_grad():
                 loss = closure()
-        self._ctr_bumped = False
+        only = None if params is None else {id(p) for p in params}
+        if not continued:
+            self._ctr_bumped = False
         if self.capturable and self._step_dev.get("ctr") is not None and not torch.cuda.is_current_stream_capturing():
             self.sync_steps()                                  # graph replays since the last eager step moved the counter
         for group in self.param_groups:
             beta1, beta2 = group["betas"]
             by_step = {}
             for p in group["params"]:
-                if p.grad is None:
+                if p.grad is None or (only is not None and id(p) not in only):
                     continue
                 if p.grad.is_sparse:
                     raise RuntimeError("Adam does not support sparse gradients, please consider SparseAdam instead")

@@ -449,16 +449,21 @@ int fnm_fourier_layer_bwd(const fnm_plan* p, const float* g_z, const float* xin,
     const int LY = 2 * p->NY;
     // analysis of g_z (c_l/N folded into byT), A.2 first line
     // ... fused with the conv weight gradient when both can share one read of g_z (gz_pass_tma, fnm_tc_wgrad.cu)
-    const bool want_cw = wc && (dwc || dbc);
+    // two-call form (FNM_PLAN_BWD_*): the second call finds the gradient spectrum Gh where the first one left it
+    const bool do_w = !(p->flags & FNM_PLAN_BWD_INPUT_ONLY), do_x = !(p->flags & FNM_PLAN_BWD_WEIGHTS_ONLY);
+    FNM_REQUIRE(do_w || do_x, "layer_bwd: FNM_PLAN_BWD_WEIGHTS_ONLY and FNM_PLAN_BWD_INPUT_ONLY exclude each other");
+    const bool want_cw = do_w && wc && (dwc || dbc);
     const bool gz_fused = want_cw && tc_gz_pass_supported(g_z, xin, p->byT, (int64_t)p->B * p->S1, p->S2, LY, p->Ci, p->Co, act_in);
-    if (gz_fused) FNM_TRY(tc_gz_pass(g_z, xin, p->byT, Tg, dwc, dbc, (int64_t)p->B * p->S1, p->S2, LY, p->Co, partial, p->mode, st));
-    else FNM_TRY(fnm_ydft(g_z, p->byT, Tg, (int64_t)p->B * p->S1, p->S2, LY, p->Co, 0, p->mode, stream));
-    FNM_TRY(fnm_xdft(Tg, p->exb, Gh, p->B, p->S1, p->R, p->NY, p->Co, p->mode, stream));
+    if (do_w) {
+        if (gz_fused) FNM_TRY(tc_gz_pass(g_z, xin, p->byT, Tg, dwc, dbc, (int64_t)p->B * p->S1, p->S2, LY, p->Co, partial, p->mode, st));
+        else FNM_TRY(fnm_ydft(g_z, p->byT, Tg, (int64_t)p->B * p->S1, p->S2, LY, p->Co, 0, p->mode, stream));
+        FNM_TRY(fnm_xdft(Tg, p->exb, Gh, p->B, p->S1, p->R, p->NY, p->Co, p->mode, stream));
+    }
     float* shadowA = w.shadow ? cv.take(w.shadow) : nullptr;
     float* shadowB = w.shadow ? cv.take(w.shadow) : nullptr;
     const int mm = p->w_layout == FNM_W_MODE_MAJOR;
     const int nmodes = p->R * p->NY, m_split = p->rows_per_w * p->NY;
-    if (dw0) {
+    if (dw0 && do_w) {
         if (w.shadow && mm) {
             FNM_TRY(tc_mix_wgrad(xh_save, Gh, dw0, dw1, m_split, nmodes, p->B, p->Ci, p->Co, p->mode, st));   // written in place
         } else if (w.shadow) {
@@ -470,7 +475,7 @@ int fnm_fourier_layer_bwd(const fnm_plan* p, const float* g_z, const float* xin,
     }
     if (want_cw && !gz_fused)
         FNM_TRY(conv_wgrad(g_z, xin, act_in, dwc, dbc, (int64_t)p->B * p->S1 * p->S2, p->Ci, p->Co, partial, p->mode, st));
-    if (g_in) {
+    if (g_in && do_x) {
         const int w1_layout = p->Co % 2 == 0 ? 1 : 0;                  // W1[m][i][o] rows readable with 16-byte loads
         if (w.shadow && mm && w1_layout) {
             FNM_TRY(tc_mix_apply(w0, w1, m_split, Gh, Gxh, nmodes, p->B, p->Co, p->Ci, 1, 1, p->mode, "mix_bwd_x", st));

@@ -238,18 +238,37 @@ class FourierLayerFn(torch.autograd.Function):
         L = lib()
         nbytes = L.fnm_fourier_layer_workspace_bytes(C.byref(plan))
         ws = _workspace(xk.device, nbytes)
-        check(L.fnm_fourier_layer_bwd(
-            C.byref(plan), _ptr(gz), _ptr(xk), ctx.kact, _ptr(zpre), _ptr(w0r), _ptr(w1r), _ptr(wcc), _ptr(xh),
-            _ptr(g_in), _ptr(torch.view_as_real(dw0)) if dw0 is not None else None,
-            _ptr(torch.view_as_real(dw1)) if dw1 is not None else None, _ptr(dwc), _ptr(dbc),
-            _ptr(ws), ws.numel(), _stream()), "fnm_fourier_layer_bwd")
-        # a sink already holds the gradient: autograd gets None and runs no AccumulateGrad for that weight
-        for sink, dw in ((s0, dw0), (s1, dw1)):
-            if sink is not None and dw is not None and dw is not sink:
-                sink.copy_(dw)
-            ready = getattr(sink, "_fnm_on_ready", None) if sink is not None else None
-            if ready is not None:
-                ready()                                             # FlatGradients(overlap=True): start this slot's exchange
+        def run(phase):
+            flags0 = plan.flags
+            plan.flags = flags0 | phase
+            check(L.fnm_fourier_layer_bwd(
+                C.byref(plan), _ptr(gz), _ptr(xk), ctx.kact, _ptr(zpre), _ptr(w0r), _ptr(w1r), _ptr(wcc), _ptr(xh),
+                _ptr(g_in), _ptr(torch.view_as_real(dw0)) if dw0 is not None else None,
+                _ptr(torch.view_as_real(dw1)) if dw1 is not None else None, _ptr(dwc), _ptr(dbc),
+                _ptr(ws), ws.numel(), _stream()), "fnm_fourier_layer_bwd")
+            plan.flags = flags0
+
+        def sinks_done():
+            # a sink already holds the gradient: autograd gets None and runs no AccumulateGrad for that weight
+            for sink, dw in ((s0, dw0), (s1, dw1)):
+                if sink is not None and dw is not None and dw is not sink:
+                    sink.copy_(dw)
+                ready = getattr(sink, "_fnm_on_ready", None) if sink is not None else None
+                if ready is not None:
+                    ready()                                         # FlatGradients(overlap=True): this slot is ready for its exchange
+            for flush in {id(f): f for f in (getattr(s, "_fnm_flush", None) for s in (s0, s1) if s is not None) if f is not None}.values():
+                flush()                                             # ... and the layer's slots go out as one all-reduce
+
+        overlapped = any(getattr(s, "_fnm_on_ready", None) is not None for s in (s0, s1) if s is not None)
+        if overlapped and need_x and want_w:
+            # weight gradients first, their exchange started, THEN the input gradient (mix_bwd_x, x-synthesis, fused pass):
+            # the all-reduce of this layer's slots runs under those kernels instead of waiting for the end of the layer
+            run(_lib.FNM_PLAN_BWD_WEIGHTS_ONLY)
+            sinks_done()
+            run(_lib.FNM_PLAN_BWD_INPUT_ONLY)
+        else:
+            run(0)
+            sinks_done()
         return (g_in, None, None if s0 is not None else dw0, None if s1 is not None else dw1,
                 None if swc is not None else dwc, None if sbc is not None else dbc, None, None, None, None, None, None)
 

@@ -31,7 +31,8 @@ class FlatGradients:
         # that fills it has been enqueued (asynchronously, on the process group's stream), so the exchange of the deep
         # layers runs under the backward pass of the shallow ones; all_reduce() then handles the rest and joins.
         self.overlap = bool(overlap and direct_spectral)
-        self._pending = []
+        self._pending, self._staged = [], []
+        self._reserve_sms, self._limit_prev = 0, None
         if not self.params:
             raise ValueError("no trainable parameters")
         self.direct = bool(direct_spectral)
@@ -64,7 +65,8 @@ class FlatGradients:
                 # simply accumulate into the (zeroed) slot as usual.
                 p._fnm_grad_sink, p._fnm_sink_uses = view, 0
                 if p.is_complex():
-                    view._fnm_on_ready = (lambda c=chunk, q=p: self._sink_ready(c, q)) if self.overlap else None
+                    view._fnm_on_ready = (lambda o=off, m=n, q=p: self._sink_ready(o, m, q)) if self.overlap else None
+                    view._fnm_flush = self.flush_ready if self.overlap else None
 
     def zero_(self):
         """Replacement for ``optimizer.zero_grad()``: keeps the views alive (set_to_none would drop them)."""
@@ -77,9 +79,42 @@ class FlatGradients:
             for p in self.params:
                 p._fnm_sink_uses = 0
 
-    def _sink_ready(self, chunk, param):
+    def _sink_ready(self, off, n, param):
+        """A backward kernel that fills the slot [off, off + n) has been enqueued: stage it for the next ``flush_ready``."""
         if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            self._pending.append((dist.all_reduce(chunk, op=dist.ReduceOp.SUM, async_op=True), [param]))
+            self._staged.append((off, n, param))
+
+    def flush_ready(self):
+        """Start the exchange of the staged slots: adjacent ones (the two spectral weights of a layer) travel as ONE
+        all-reduce -- per message NCCL's NVLS kernels need ~0.1 ms to get up to speed, and the exchange of the last
+        layer is what remains exposed after backward."""
+        staged, self._staged = sorted(self._staged, key=lambda t: t[0]), []
+        runs = []
+        for off, n, q in staged:
+            if runs and runs[-1][1] == off:
+                runs[-1][1] = off + (n + 63) // 64 * 64
+                runs[-1][2].append(q)
+            else:
+                runs.append([off, off + (n + 63) // 64 * 64, [q]])
+        for lo, hi, ps in runs:
+            chunk = self.flat[lo:min(hi, self.flat.numel())]
+            self._pending.append((dist.all_reduce(chunk, op=dist.ReduceOp.SUM, async_op=True), ps))
+            if self._reserve_sms > 0 and self._limit_prev is None:
+                # from the first exchange in flight on, the persistent kernels leave `_reserve_sms` SMs to the NCCL kernels
+                # (train_step lifts the cap after backward); the kernels before it keep every SM
+                from ._lib import set_sm_limit
+                sms = torch.cuda.get_device_properties(chunk.device).multi_processor_count
+                self._limit_prev = set_sm_limit(max(1, sms - self._reserve_sms))
+
+    def reserve_begin(self, sms):
+        """Arm the SM reservation for the backward pass that follows (see ``train_step``)."""
+        self._reserve_sms, self._limit_prev = int(sms), None
+
+    def reserve_end(self):
+        if self._limit_prev is not None:
+            from ._lib import set_sm_limit
+            set_sm_limit(self._limit_prev)
+        self._reserve_sms, self._limit_prev = 0, None
 
     def all_reduce(self, group=None, async_op=False, join=True):
         """SUM over ranks; no-op in a single-process run.  With ``overlap`` the sinks are already in flight: this
@@ -87,6 +122,8 @@ class FlatGradients:
         (``join=False`` leaves the waiting to whoever iterates ``update_groups()``)."""
         if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
             return None
+        if self._staged:
+            self.flush_ready()
         if self.overlap and self._pending:
             work = dist.all_reduce(self.flat[:self.head], op=dist.ReduceOp.SUM, group=group, async_op=True)
             sunk = {id(q) for _, ps in self._pending for q in ps}
@@ -138,27 +175,36 @@ def train_step(model, optimizer, grads, loss_fn, x, y, group=None, sm_reserve=0)
     """zero_grad -> forward -> loss -> backward -> SUM all-reduce -> Adam (train_fno.py:187-197 +
     the exchange).  Returns the LOCAL loss tensor (no host sync).
 
-    ``sm_reserve`` (overlapped exchange only): SMs the persistent backward kernels leave free, so that the NCCL
-    kernels of the slots already in flight have somewhere to run (include/fnm_b200.h, fnm_set_sm_limit)."""
+    ``sm_reserve`` (overlapped exchange only): SMs the persistent backward kernels leave free from the moment the first
+    slot's all-reduce is in flight, so that the NCCL kernels have somewhere to run (include/fnm_b200.h, fnm_set_sm_limit);
+    it should equal the number of CTAs NCCL launches (NCCL_MAX_CTAS)."""
     grads.zero_()
     out = model(x)
     loss = loss_fn(out, y)
     reserve = int(sm_reserve) if (grads.overlap and dist.is_available() and dist.is_initialized()
                                   and dist.get_world_size(group) > 1) else 0
     if reserve > 0:
-        from ._lib import set_sm_limit
-        sms = torch.cuda.get_device_properties(x.device).multi_processor_count
-        prev = set_sm_limit(max(1, sms - reserve))
+        grads.reserve_begin(reserve)
         try:
             loss.backward()
         finally:
-            set_sm_limit(prev)
+            grads.reserve_end()
     else:
         loss.backward()
-    # (Updating each parameter group as soon as ITS exchange has landed -- several Adam launches driven by
-    # update_groups() -- was measured at 2 GPUs and is no faster than joining first: 23.5 vs 23.4 ms per step.)
-    grads.all_reduce(group)
-    optimizer.step()
+    if grads.overlap and getattr(optimizer, "supports_partial_step", False) and dist.is_available() \
+            and dist.is_initialized() and dist.get_world_size(group) > 1:
+        # every parameter group is updated as soon as ITS exchange has landed (in issue order: deepest layer first, the
+        # small real parameters last): the all-reduce of the last layer's slots finishes under the Adam launches of the others
+        grads.all_reduce(group, join=False)
+        first = True
+        for ps in grads.update_groups():
+            optimizer.step(params=ps, continued=not first)
+            first = False
+        if first:
+            optimizer.step()
+    else:
+        grads.all_reduce(group)
+        optimizer.step()
     return loss
 
 

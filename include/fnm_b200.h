@@ -98,7 +98,11 @@ typedef struct fnm_plan {
  * FNM_PLAN_PRE_IS_GELU_GRAD and multiplies by it directly.  z itself is then never stored: nothing else needs it.   */
 enum {
     FNM_PLAN_ZOUT_IS_GELU_GRAD = 1,         /* forward:  z_out := GELU'(z) (requires x_act_out != NULL) */
-    FNM_PLAN_PRE_IS_GELU_GRAD = 2           /* backward (fourier_layer_bwd, lfunc_bwd): zin_pre holds GELU'(zin), not zin */
+    FNM_PLAN_PRE_IS_GELU_GRAD = 2,          /* backward (fourier_layer_bwd, lfunc_bwd): zin_pre holds GELU'(zin), not zin */
+    /* fnm_fourier_layer_bwd in two calls on the same stream, workspace and arguments, so that the caller can start the
+     * exchange of the weight gradients (data parallel training) while the input gradient is still being computed:        */
+    FNM_PLAN_BWD_WEIGHTS_ONLY = 4,          /* analysis of g_z, dW0 / dW1, dWc / dbc; leaves the gradient spectrum in the workspace */
+    FNM_PLAN_BWD_INPUT_ONLY = 8             /* g_in from the spectrum the WEIGHTS_ONLY call left in the workspace */
 };
 /* flags of fnm_pointwise_ysyn_ex */
 enum {

@@ -70,7 +70,7 @@ def main():
                 if first is None:
                     first = {k: p.grad.detach().clone() for k, p in model.named_parameters()}
         else:
-            step = GraphedTrainStep(model, opt, grads, rel_l2_sum, xs, ys, warmup=3)
+            step = GraphedTrainStep(model, opt, grads, rel_l2_sum, xs, ys, warmup=3, sm_reserve=8)    # with the SM reservation of the bench
             graphs.append(step)
             for _ in range(2):
                 step(xs, ys)

@@ -82,7 +82,8 @@ def test_two_rank_sum_allreduce_equals_global_batch_gradient():
 
 
 def _worker_overlap(rank, world, port, out):
-    """Sink slots exchanged one by one (what the CUDA backward triggers through ``_fnm_on_ready``), the rest after:
+    """Sink slots exchanged as the backward fills them (``_fnm_on_ready`` stages a slot, ``_fnm_flush`` starts the
+    all-reduce of the staged, adjacent slots), the rest after:
     the result must be the plain flat SUM.  The spectral weight is stored mode-major like the drop-in modules' own."""
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -90,13 +91,19 @@ def _worker_overlap(rank, world, port, out):
         torch.manual_seed(3)
         model = Toy()
         model.w = torch.nn.Parameter(model.w.detach().permute(2, 0, 1).contiguous().permute(1, 2, 0))   # mode-major storage
+        model.w2 = torch.nn.Parameter(model.w.detach().clone(memory_format=torch.preserve_format))      # a layer's second weight
         broadcast_parameters(model)                          # storage-order view of a non-contiguous parameter
         grads = FlatGradients(model.parameters(), direct_spectral=True, overlap=True)
         assert model.w.grad.stride() == model.w.stride() and grads.head < grads.flat.numel()
         grads.zero_()
         grads.flat.copy_(torch.arange(grads.flat.numel(), dtype=torch.float32) * (rank + 1))
-        model.w._fnm_grad_sink._fnm_on_ready()               # the backward kernel would do this after writing the slot
-        assert len(grads._pending) == 1
+        sink, sink2 = model.w._fnm_grad_sink, model.w2._fnm_grad_sink
+        sink2._fnm_on_ready()                                # the backward kernel would do this after writing a slot ...
+        sink._fnm_on_ready()
+        assert len(grads._staged) == 2 and not grads._pending
+        sink._fnm_flush()                                    # ... and this once the layer's slots are staged: the two
+        assert len(grads._pending) == 1 and not grads._staged    # adjacent slots travel as ONE all-reduce
+        assert [id(q) for q in grads._pending[0][1]] == [id(model.w), id(model.w2)]
         grads.all_reduce()
         assert not grads._pending
         if rank == 0:

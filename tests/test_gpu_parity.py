@@ -416,6 +416,52 @@ def test_direct_gradient_sinks_match_autograd_accumulation(family):
                            torch.view_as_real(w1[k]) if w1[k].is_complex() else w1[k]), k
 
 
+def test_two_call_backward_and_partial_adam_steps_are_bit_identical():
+    """What the overlapped data-parallel step adds on each rank, checked on one GPU: (a) fnm_fourier_layer_bwd in two
+    calls (FNM_PLAN_BWD_WEIGHTS_ONLY, then FNM_PLAN_BWD_INPUT_ONLY -- the exchange of the layer's dW starts between
+    them), (b) one optimizer step spread over several Adam.step(params=...) calls.  Gradients and parameters after two
+    steps must equal the single-call path bit for bit, eagerly and with Adam(capturable=True)."""
+    torch.manual_seed(5)
+    x = torch.randn(3, 1, 24, 24, device=DEV)
+    results = []
+    for split, capturable in ((False, False), (True, False), (True, True)):
+        torch.manual_seed(11)
+        model = fnm_b200.FNO2d(4, 4, 32, n_layers=3, width_final=32).to(DEV)
+        opt = fnm_b200.Adam(model.parameters(), lr=1e-3, weight_decay=1e-4, capturable=capturable)
+        grads = fnm_b200.parallel.FlatGradients(model.parameters(), direct_spectral=True, overlap=split)
+        staged = []
+        if split:
+            assert grads.overlap
+            grads._sink_ready = lambda off, n, q: staged.append(q)      # single process: record instead of exchanging
+        y = None
+        for _ in range(2):
+            grads.zero_()
+            out = model(x)
+            y = torch.ones_like(out) if y is None else y
+            fnm_b200.parallel.rel_l2_sum(out, y).backward()
+            g = {k: p.grad.clone() for k, p in model.named_parameters()}
+            if split:
+                cplx = [p for p in model.parameters() if p.is_complex()]
+                rest = [p for p in model.parameters() if not p.is_complex()]
+                opt.step(params=cplx[2:])
+                opt.step(params=cplx[:2], continued=True)
+                opt.step(params=rest, continued=True)
+            else:
+                opt.step()
+        if capturable:
+            opt.sync_steps()
+        assert {int(opt.state[p]["step"]) for p in model.parameters()} == {2}
+        results.append((g, {k: v.clone() for k, v in model.state_dict().items()}))
+        if split:
+            assert len(staged) == 2 * sum(p.is_complex() for p in model.parameters())
+    fr = lambda t: torch.view_as_real(t) if t.is_complex() else t
+    for g1, w1 in results[1:]:
+        for k in results[0][0]:
+            assert torch.equal(fr(results[0][0][k]), fr(g1[k])), k
+        for k in results[0][1]:
+            assert torch.equal(fr(results[0][1][k]), fr(w1[k])), k
+
+
 def test_spectral_weights_live_mode_major_and_skip_the_layout_copies():
     """The drop-in modules keep weights1 / weights2 in (kx, ky, Cin, Cout) memory order behind the reference's
     logical shape: a train step launches no weight permutes, gradients and Adam state share the order, and the
