@@ -490,12 +490,12 @@ int tc_pointwise_ysyn(const float* x, int act, const float* wc, int wc_is_kn, co
     if (a1_tmem) {
         e = cudaFuncSetAttribute(pointwise_ysyn_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return fail(FNM_ECUDA, "tc_pointwise_ysyn: smem attribute: %s", cudaGetErrorString(e));
-        LaunchScope ls("pointwise_ysyn", st);
+        LaunchScope ls("pointwise_ysyn.v1", st);
         pointwise_ysyn_tc<true><<<grid, kThreads, smem, st>>>(a);
     } else {
         e = cudaFuncSetAttribute(pointwise_ysyn_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return fail(FNM_ECUDA, "tc_pointwise_ysyn: smem attribute: %s", cudaGetErrorString(e));
-        LaunchScope ls("pointwise_ysyn", st);
+        LaunchScope ls("pointwise_ysyn.v1", st);
         pointwise_ysyn_tc<false><<<grid, kThreads, smem, st>>>(a);
     }
     return check_launch("tc_pointwise_ysyn");

@@ -153,6 +153,29 @@ def test_pointwise_ysyn_cached_gelu_derivative(case, mode):
     del dgrad
 
 
+def test_engine_selection_of_the_fused_pass():
+    """Which kernel serves which call (profile names of include/fnm_b200.h: fnm_profile_begin/_end): activations that are
+    already activated (every launch of the trunk since the GELU copies are cached) run on `pw2_kernel`
+    ("pointwise_ysyn"); GELU ON LOAD -- callers of the C ABI without a cached copy -- keeps the first tcgen05 kernel of
+    fnm_tc.cu ("pointwise_ysyn.v1"), and channel counts outside both envelopes the SIMT engine (".simt")."""
+    from fnm_b200._lib import profile_begin, profile_end
+    torch.manual_seed(0)
+    got = {}
+    for tag, case in (("tma", CASES[10]), ("v1", CASES[2]), ("simt", CASES[19])):
+        rows, S2, LY, K, N = case["rows"], case["S2"], case["LY"], case["K"], case["N"]
+        x, wc = torch.randn(rows, S2, K, device=DEV), torch.randn(N, K, device=DEV)
+        Z, by = torch.randn(rows, LY, N, device=DEV), torch.randn(S2, LY, device=DEV)
+        out = torch.empty(rows, S2, N, device=DEV)
+        profile_begin()
+        check(lib().fnm_pointwise_ysyn(_p(x), case["act"], _p(wc), 0, None, _p(Z), _p(by), None, _p(out), None,
+                                       rows, S2, LY, K, N, 0, _stream()), "fnm_pointwise_ysyn")
+        torch.cuda.synchronize()
+        got[tag] = set(profile_end())
+    assert got["tma"] == {"pointwise_ysyn"}, got
+    assert got["v1"] == {"pointwise_ysyn.v1"}, got
+    assert all(k.endswith(".simt") for k in got["simt"]) and got["simt"], got
+
+
 def test_ydft_xdft_xsyn_roundtrip_stages():
     """ydft -> xdft -> xsyn -> ysyn with identity mixing reproduces the band-limited projection."""
     from fnm_b200.plan import spectral_tables
