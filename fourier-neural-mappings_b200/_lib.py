@@ -28,7 +28,7 @@ class FnmPlan(C.Structure):
                 ("rows_per_w", C.c_int32), ("mode", C.c_int32), ("w_layout", C.c_int32),
                 ("ay", _vp), ("ayT", _vp), ("by", _vp), ("byT", _vp),
                 ("ex", _vp), ("fx", _vp), ("exb", _vp), ("fxb", _vp), ("w_shadow", _vp), ("flags", C.c_int32),
-                ("by16", _vp), ("ayT16", _vp)]
+                ("by16", _vp), ("ayT16", _vp), ("ay4", _vp), ("byT4", _vp)]
 
 
 _PP = C.POINTER(FnmPlan)

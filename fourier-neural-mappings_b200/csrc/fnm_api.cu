@@ -164,9 +164,19 @@ int fnm_ydft(const float* x, const float* tab, float* T, int64_t rows, int P2, i
              fnm_stream_t stream) {
     FNM_REQUIRE(x && tab && T, "ydft: NULL pointer");
     FNM_REQUIRE(rows >= 0 && P2 > 0 && LY > 0 && C > 0, "ydft: bad extents");
-    if (tc_ydft_tma_supported(x, tab, rows, P2, LY, C, act_in)) return tc_ydft_tma(x, tab, T, rows, P2, LY, C, mode, as_stream(stream));
+    if (tc_ydft_tma_supported(x, tab, P2, rows, P2, LY, C, act_in)) return tc_ydft_tma(x, tab, P2, T, rows, P2, LY, C, mode, as_stream(stream));
     if (tc_ydft_supported(rows, P2, LY, C)) return tc_ydft(x, tab, T, rows, P2, LY, C, act_in, mode, as_stream(stream));
     return simt_ydft(x, tab, T, rows, P2, LY, C, act_in, as_stream(stream));
+}
+
+// y-DFT of a plan's entry points: `tab4` is the plan's copy of `tab` with rows padded to a multiple of 4 floats (fnm_plan.ay4 /
+// byT4, may be NULL) -- with it the TMA-fed kernel also serves row lengths that are no multiple of 4
+static int plan_ydft(const float* x, const float* tab, const float* tab4, float* T, int64_t rows, int P2, int LY, int C, int act_in,
+                     int mode, fnm_stream_t stream) {
+    const int ld4 = (P2 + 3) & ~3;
+    if (P2 % 4 != 0 && tab4 && tc_ydft_tma_supported(x, tab4, ld4, rows, P2, LY, C, act_in))
+        return tc_ydft_tma(x, tab4, ld4, T, rows, P2, LY, C, mode, as_stream(stream));
+    return fnm_ydft(x, tab, T, rows, P2, LY, C, act_in, mode, stream);
 }
 
 int fnm_xdft(const float* T, const float* ex, float* Xh, int B, int P1, int R, int NY, int C, int mode,
@@ -313,8 +323,8 @@ int fnm_ydft_conv_wgrad(const float* g, const float* x, const float* tab, float*
     FNM_REQUIRE(rows > 0 && S2 > 0 && LY > 0 && C > 0, "ydft_conv_wgrad: bad extents");
     if (workspace_bytes < conv_wgrad_workspace(rows * S2, C, C)) return fail(FNM_EWORKSPACE, "ydft_conv_wgrad: workspace too small");
     cudaStream_t st = as_stream(stream);
-    if (tc_gz_pass_supported(g, x, tab, rows, S2, LY, C, C, 0))
-        return tc_gz_pass(g, x, tab, T, dwc, dbc, rows, S2, LY, C, static_cast<float*>(workspace), mode, st);
+    if (tc_gz_pass_supported(g, x, tab, S2, rows, S2, LY, C, C, 0))
+        return tc_gz_pass(g, x, tab, S2, T, dwc, dbc, rows, S2, LY, C, static_cast<float*>(workspace), mode, st);
     FNM_TRY(fnm_ydft(g, tab, T, rows, S2, LY, C, 0, mode, stream));
     return conv_wgrad(g, x, 0, dwc, dbc, rows * S2, C, C, static_cast<float*>(workspace), mode, st);
 }
@@ -407,7 +417,7 @@ int fnm_fourier_layer_fwd(const fnm_plan* p, const float* xin, int act_in, const
     float* Oh = cv.take(w.Oh);
     float* Z = cv.take(w.Z);
     const int LY = 2 * p->NY;
-    FNM_TRY(fnm_ydft(xin, p->ay, T, (int64_t)p->B * p->P1, p->P2, LY, p->Ci, act_in, p->mode, stream));
+    FNM_TRY(plan_ydft(xin, p->ay, p->ay4, T, (int64_t)p->B * p->P1, p->P2, LY, p->Ci, act_in, p->mode, stream));
     FNM_TRY(fnm_xdft(T, p->ex, xh_save, p->B, p->P1, p->R, p->NY, p->Ci, p->mode, stream));
     const int mm = p->w_layout == FNM_W_MODE_MAJOR;
     const int nmodes = p->R * p->NY, m_split = p->rows_per_w * p->NY;
@@ -453,10 +463,14 @@ int fnm_fourier_layer_bwd(const fnm_plan* p, const float* g_z, const float* xin,
     const bool do_w = !(p->flags & FNM_PLAN_BWD_INPUT_ONLY), do_x = !(p->flags & FNM_PLAN_BWD_WEIGHTS_ONLY);
     FNM_REQUIRE(do_w || do_x, "layer_bwd: FNM_PLAN_BWD_WEIGHTS_ONLY and FNM_PLAN_BWD_INPUT_ONLY exclude each other");
     const bool want_cw = do_w && wc && (dwc || dbc);
-    const bool gz_fused = want_cw && tc_gz_pass_supported(g_z, xin, p->byT, (int64_t)p->B * p->S1, p->S2, LY, p->Ci, p->Co, act_in);
+    // table of the backward analysis as TMA can address it: byT itself, or its padded copy when S2 is no multiple of 4
+    const bool s2_pad = p->S2 % 4 != 0 && p->byT4;
+    const float* gtab = s2_pad ? p->byT4 : p->byT;
+    const int gld = s2_pad ? ((p->S2 + 3) & ~3) : p->S2;
+    const bool gz_fused = want_cw && tc_gz_pass_supported(g_z, xin, gtab, gld, (int64_t)p->B * p->S1, p->S2, LY, p->Ci, p->Co, act_in);
     if (do_w) {
-        if (gz_fused) FNM_TRY(tc_gz_pass(g_z, xin, p->byT, Tg, dwc, dbc, (int64_t)p->B * p->S1, p->S2, LY, p->Co, partial, p->mode, st));
-        else FNM_TRY(fnm_ydft(g_z, p->byT, Tg, (int64_t)p->B * p->S1, p->S2, LY, p->Co, 0, p->mode, stream));
+        if (gz_fused) FNM_TRY(tc_gz_pass(g_z, xin, gtab, gld, Tg, dwc, dbc, (int64_t)p->B * p->S1, p->S2, LY, p->Co, partial, p->mode, st));
+        else FNM_TRY(plan_ydft(g_z, p->byT, p->byT4, Tg, (int64_t)p->B * p->S1, p->S2, LY, p->Co, 0, p->mode, stream));
         FNM_TRY(fnm_xdft(Tg, p->exb, Gh, p->B, p->S1, p->R, p->NY, p->Co, p->mode, stream));
     }
     float* shadowA = w.shadow ? cv.take(w.shadow) : nullptr;
@@ -536,7 +550,7 @@ int fnm_lfunc_fwd(const fnm_plan* p, const float* xin, int act_in, const float* 
     float* partial = cv.take(simt_mode_split_workspace(p->R * p->NY, p->B, p->Co) / sizeof(float));
     float* Oh = cv.take(ends_spectrum_floats(p));
     const int mm = p->w_layout == FNM_W_MODE_MAJOR, nmodes = p->R * p->NY;
-    FNM_TRY(fnm_ydft(xin, p->ay, T, (int64_t)p->B * p->P1, p->P2, LY, p->Ci, act_in, p->mode, stream));
+    FNM_TRY(plan_ydft(xin, p->ay, p->ay4, T, (int64_t)p->B * p->P1, p->P2, LY, p->Ci, act_in, p->mode, stream));
     FNM_TRY(fnm_xdft(T, p->ex, xh_save, p->B, p->P1, p->R, p->NY, p->Ci, p->mode, stream));
     if (ends_on_mix(p)) {
         FNM_TRY(tc_mix_apply(w, nullptr, 0, xh_save, Oh, nmodes, p->B, p->Ci, p->Co, 0, 0, p->mode, "lfunc_contract", st));
@@ -626,7 +640,7 @@ int fnm_ldec_bwd(const fnm_plan* p, const float* g_y, const float* v, const floa
     float* Gxh = cv.take(ends_spectrum_floats(p));
     const int mm = p->w_layout == FNM_W_MODE_MAJOR, nmodes = p->R * p->NY;
     const bool on_mix = ends_on_mix(p);
-    FNM_TRY(fnm_ydft(g_y, p->byT, Tg, (int64_t)p->B * p->S1, p->S2, LY, p->Co, 0, p->mode, stream));
+    FNM_TRY(plan_ydft(g_y, p->byT, p->byT4, Tg, (int64_t)p->B * p->S1, p->S2, LY, p->Co, 0, p->mode, stream));
     FNM_TRY(fnm_xdft(Tg, p->exb, Gh, p->B, p->S1, p->R, p->NY, p->Co, p->mode, stream));
     if (dw) {
         if (on_mix) {

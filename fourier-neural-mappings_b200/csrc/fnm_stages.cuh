@@ -50,8 +50,8 @@ int tc_available();
 bool tc_ydft_supported(int64_t rows, int P2, int LY, int C);
 int tc_ydft(const float* x, const float* tab, float* T, int64_t rows, int P2, int LY, int C, int act, int mode,
             cudaStream_t st);
-bool tc_ydft_tma_supported(const float* x, const float* tab, int64_t rows, int P2, int LY, int C, int act);
-int tc_ydft_tma(const float* x, const float* tab, float* T, int64_t rows, int P2, int LY, int C, int mode, cudaStream_t st);
+bool tc_ydft_tma_supported(const float* x, const float* tab, int ld, int64_t rows, int P2, int LY, int C, int act);   // ld: row stride of tab
+int tc_ydft_tma(const float* x, const float* tab, int ld, float* T, int64_t rows, int P2, int LY, int C, int mode, cudaStream_t st);
 bool tc_xdft_supported(int B, int P1, int R, int NY, int C);
 int tc_xdft(const float* T, const float* ex, float* Xh, int B, int P1, int R, int NY, int C, int mode, cudaStream_t st);
 bool tc_resample_supported(int64_t G, int K, int M, int inner, int C);
@@ -72,8 +72,8 @@ bool tc_conv_wgrad_supported(int64_t npos, int Ci, int Co);
 size_t tc_conv_wgrad_workspace(int64_t npos, int Ci, int Co);
 int tc_conv_wgrad(const float* g, const float* x, int act, float* dwc, float* dbc, int64_t npos, int Ci, int Co,
                   float* partial, int mode, cudaStream_t st);
-bool tc_gz_pass_supported(const float* g, const float* x, const float* tab, int64_t rows, int S2, int LY, int Ci, int Co, int act);
-int tc_gz_pass(const float* g, const float* x, const float* tab, float* T, float* dwc, float* dbc, int64_t rows, int S2, int LY,
+bool tc_gz_pass_supported(const float* g, const float* x, const float* tab, int ld, int64_t rows, int S2, int LY, int Ci, int Co, int act);
+int tc_gz_pass(const float* g, const float* x, const float* tab, int ld, float* T, float* dwc, float* dbc, int64_t rows, int S2, int LY,
                int C, float* partial, int mode, cudaStream_t st);
 bool tc_pw2_supported(int64_t rows, int S2, int LY, int K, int N, int act, const void* x, const void* Z, const void* by,
                       int by_ld = 0);

@@ -805,8 +805,9 @@ int tc_conv_wgrad(const float* g, const float* x, int act, float* dwc, float* db
 // fused ydft(g) + conv weight gradient (gz_pass_tma): 128 channels on both sides (or 32 / 64 with grid rows folded into the
 // lanes), no activation on load, whole row groups as work items -- problems with few long rows (1-D) keep the separate,
 // row-segmenting kernels.  The grid never exceeds the partial count tc_conv_wgrad_workspace sized the workspace for.
-bool tc_gz_pass_supported(const float* g, const float* x, const float* tab, int64_t rows, int S2, int LY, int Ci, int Co, int act) {
-    if (!tc_enabled() || act != 0 || Ci != Co || (Ci != 128 && Ci != 64 && Ci != 32) || LY < 8 || LY > 64 || S2 % 4 != 0 || S2 < 4)
+bool tc_gz_pass_supported(const float* g, const float* x, const float* tab, int ld, int64_t rows, int S2, int LY, int Ci, int Co, int act) {
+    // ld: row stride of the table in floats (S2 itself, or the padded copy fnm_plan.byT4 when S2 is no multiple of 4)
+    if (!tc_enabled() || act != 0 || Ci != Co || (Ci != 128 && Ci != 64 && Ci != 32) || LY < 8 || LY > 64 || ld % 4 != 0 || ld < S2 || S2 < 4)
         return false;
     const int F = 128 / Ci;
     // (small L2-resident problems are launch bound either way and do better with every SM on the separate kernels)
@@ -816,7 +817,7 @@ bool tc_gz_pass_supported(const float* g, const float* x, const float* tab, int6
     return !(e && e[0] == '1');
 }
 
-int tc_gz_pass(const float* g, const float* x, const float* tab, float* T, float* dwc, float* dbc, int64_t rows, int S2, int LY,
+int tc_gz_pass(const float* g, const float* x, const float* tab, int ld, float* T, float* dwc, float* dbc, int64_t rows, int S2, int LY,
                int C, float* partial, int mode, cudaStream_t st) {
     GzArgs a{};
     a.T = T; a.part = partial; a.rows = rows; a.S2 = S2; a.LY = LY; a.nch = (S2 + 31) / 32;
@@ -833,7 +834,7 @@ int tc_gz_pass(const float* g, const float* x, const float* tab, float* T, float
     }
     {
         const cuuint64_t dims[2] = {(cuuint64_t)S2, (cuuint64_t)LY};
-        const cuuint64_t str[1] = {(cuuint64_t)S2 * 4};
+        const cuuint64_t str[1] = {(cuuint64_t)ld * 4};
         const cuuint32_t box[2] = {32, 64};
         if (!tc_make_map(&mt, tab, 2, dims, str, box, true)) return fail(FNM_ECUDA, "ydft_conv_wgrad: tensor map (table) failed");
     }

@@ -257,9 +257,10 @@ ydft_tma(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUten
 
 using namespace tc;
 
-bool tc_ydft_tma_supported(const float* x, const float* tab, int64_t rows, int P2, int LY, int C, int act) {
-    if (!tc_enabled() || act != 0 || (C != 128 && C != 64 && C != 32) || LY < 8 || LY > 64 || P2 % 4 != 0 || rows < 1 ||
-        rows >= (1LL << 30))
+bool tc_ydft_tma_supported(const float* x, const float* tab, int ld, int64_t rows, int P2, int LY, int C, int act) {
+    // ld: row stride of the table in floats (TMA wants 16-byte strides: P2 itself, or the padded copy fnm_plan.ay4 / byT4)
+    if (!tc_enabled() || act != 0 || (C != 128 && C != 64 && C != 32) || LY < 8 || LY > 64 || ld % 4 != 0 || ld < P2 || P2 < 4 ||
+        rows < 1 || rows >= (1LL << 30))
         return false;
     if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(tab)) & 15) return false;
     // an item is a whole (folded) grid row: problems with few long rows (1-D) stay on the segmenting register-path kernel
@@ -268,7 +269,7 @@ bool tc_ydft_tma_supported(const float* x, const float* tab, int64_t rows, int P
     return !(e && e[0] == '1');
 }
 
-int tc_ydft_tma(const float* x, const float* tab, float* T, int64_t rows, int P2, int LY, int C, int mode, cudaStream_t st) {
+int tc_ydft_tma(const float* x, const float* tab, int ld, float* T, int64_t rows, int P2, int LY, int C, int mode, cudaStream_t st) {
     YdArgs a{};
     a.out = T; a.rows = rows; a.P2 = P2; a.LY = LY; a.NT = (LY + 15) / 16 * 16; a.nch = (P2 + 31) / 32;
     a.single_pass = mode == FNM_MODE_TF32;
@@ -285,7 +286,7 @@ int tc_ydft_tma(const float* x, const float* tab, float* T, int64_t rows, int P2
     }
     {
         const cuuint64_t dims[2] = {(cuuint64_t)P2, (cuuint64_t)LY};
-        const cuuint64_t str[1] = {(cuuint64_t)P2 * 4};
+        const cuuint64_t str[1] = {(cuuint64_t)ld * 4};
         const cuuint32_t box[2] = {32, 64};
         if (!tc_make_map(&mt, tab, 2, dims, str, box, true)) return fail(FNM_ECUDA, "ydft: tensor map (table) failed");
     }

@@ -131,6 +131,10 @@ class ModeTables:
         key = str(device)
         if key not in self._dev:
             d = {k: torch.from_numpy(v).to(device) for k, v in self.host.items()}
+            for name in ("ay", "byT"):                        # TMA needs 16-byte row strides (fnm_plan.ay4 / byT4)
+                if name in d and d[name].shape[1] % 4:
+                    t = d[name]
+                    d[name + "4"] = torch.nn.functional.pad(t, (0, -t.shape[1] % 4)).contiguous()
             if os.environ.get("FNM_PW2_CORR", "")[:1] == "b":   # opt-in bf16 correction passes of the fused pointwise kernel
                 for name in ("by", "ayT"):
                     if name in d:
@@ -143,7 +147,7 @@ class ModeTables:
         p = FnmPlan()
         p.B, p.P1, p.P2, p.S1, p.S2 = B, self.P1, self.P2, self.S1, self.S2
         p.R, p.NY, p.Ci, p.Co, p.rows_per_w, p.mode = self.R, self.NY, Ci, Co, self.rows_per_w, mode
-        for name in ("ay", "ayT", "by", "byT", "ex", "fx", "exb", "fxb", "by16", "ayT16"):
+        for name in ("ay", "ayT", "by", "byT", "ex", "fx", "exb", "fxb", "by16", "ayT16", "ay4", "byT4"):
             setattr(p, name, d[name].data_ptr() if name in d else None)
         return p
 

@@ -89,6 +89,11 @@ typedef struct fnm_plan {
     const void* by16;                       /* optional bf16 pairs of by / ayT: [2][rows][LY rounded up to 8] bfloat16 =     */
     const void* ayT16;                      /* { bf16(t), bf16(t - trunc_tf32(t)) } (see fnm_pointwise_ysyn_ex); NULL: the   */
                                             /* fused pointwise kernel derives them from the fp32 tile, tile by tile          */
+    const float *ay4, *byT4;                /* optional: copies of ay ([2 NY][P2]) and byT ([2 NY][S2]) whose rows are zero-  */
+                                            /* padded to a multiple of 4 floats (row stride (P2 + 3) & ~3, (S2 + 3) & ~3).    */
+                                            /* TMA needs 16-byte row strides: with them the TMA-fed y-DFT kernels also serve  */
+                                            /* grids whose row length is no multiple of 4 (e.g. 221 x 51 padded to 248 x 57); */
+                                            /* NULL: such grids take the register-path kernels                                */
 } fnm_plan;
 
 /* Cached GELU derivative (fused Fourier layer).  GELU'(z) of a layer's output costs ~25 instructions per element; in the

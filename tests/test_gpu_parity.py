@@ -275,6 +275,26 @@ def check_fused_layers(B, C, P, m, seed=5):
         assert rel_l2(got[k].grad, v.grad) < TOL_FP32, k
 
 
+@pytest.mark.parametrize("shape", [
+    dict(B=12, C=32, P=(248, 57), m=(12, 12)),        # config 3 grid: 57-point rows, four rows folded into the lanes
+    dict(B=10, C=64, P=(130, 54), m=(9, 14)),         # 64 channels, rows of 54
+    dict(B=5, C=128, P=(130, 61), m=(8, 20)),         # 128 channels, odd row length
+])
+def test_fused_layers_ragged_rows_on_the_tma_kernels(shape):
+    """Row lengths that are no multiple of 4 with enough rows for the TMA-fed y-DFT kernels: the plan hands them the
+    analysis tables with rows padded to 16-byte strides (fnm_plan.ay4 / byT4).  Same check as above, plus: the backward
+    y-DFT really ran fused with the conv weight gradient (profile name `ydft_conv_wgrad`)."""
+    from fnm_b200._lib import profile_begin, profile_end
+    profile_begin()
+    try:
+        check_fused_layers(shape["B"], shape["C"], shape["P"], shape["m"], seed=9)
+    finally:
+        torch.cuda.synchronize()
+        names = profile_end()
+    assert "ydft_conv_wgrad" in names, sorted(names)
+    assert not any(k.endswith(".simt") for k in names), sorted(names)
+
+
 @pytest.mark.parametrize("act", ["gelu", "relu", "tanh"])
 def test_full_model_config1_shape_vs_oracle(act):
     """FNO2d at the config-1 architecture (64x64, modes 12, width 32, 4 layers), batch 4."""
