@@ -36,6 +36,7 @@ _PP = C.POINTER(FnmPlan)
 # name -> (restype, argtypes); mirrors include/fnm_b200.h one to one
 PROTOTYPES = {
     "fnm_version": (C.c_char_p, []),
+    "fnm_plan_sizeof": (C.c_size_t, []),
     "fnm_last_error": (C.c_char_p, []),
     "fnm_has_tcgen05": (_i32, []),
     "fnm_launch_count": (_i64, []),
@@ -119,6 +120,9 @@ def lib():
         for name, (res, args) in PROTOTYPES.items():
             fn = getattr(handle, name)          # AttributeError if the .so does not export it
             fn.restype, fn.argtypes = res, args
+        if handle.fnm_plan_sizeof() != C.sizeof(FnmPlan):
+            raise FnmError(f"{LIB_PATH}: struct fnm_plan has {handle.fnm_plan_sizeof()} bytes, this binding's mirror "
+                           f"{C.sizeof(FnmPlan)} -- rebuild the library (make -C {CSRC_DIR}) or update _lib.FnmPlan")
         _lib = handle
     return _lib
 

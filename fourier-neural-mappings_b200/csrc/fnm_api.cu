@@ -112,7 +112,8 @@ using namespace fnm;
 
 extern "C" {
 
-const char* fnm_version(void) { return "fnm_b200 0.1 (sm_100a)"; }
+const char* fnm_version(void) { return "fnm_b200 0.2 (sm_100a)"; }
+size_t fnm_plan_sizeof(void) { return sizeof(fnm_plan); }
 const char* fnm_last_error(void) { return err_buf(); }
 int fnm_has_tcgen05(void) { return tc_available(); }
 

@@ -116,6 +116,9 @@ enum {
 };
 
 const char* fnm_version(void);
+/* sizeof(fnm_plan) as this library was compiled: a binding checks its own struct against it at load time (the plan grows
+ * by optional trailing fields; a stale mirror of it would make the library read garbage pointers) */
+size_t fnm_plan_sizeof(void);
 const char* fnm_last_error(void);
 /* 1 when the library was built with the tcgen05/TMA kernels (sm_100a) */
 int fnm_has_tcgen05(void);

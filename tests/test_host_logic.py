@@ -243,6 +243,17 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(handle, name), name
     assert b"fnm_b200" in handle.fnm_version()
+    # the ctypes mirror of struct fnm_plan has the size the library was compiled with (checked at load time too), and
+    # its field names are the header's, in order
+    import ctypes
+    assert handle.fnm_plan_sizeof() == ctypes.sizeof(fnm_b200._lib.FnmPlan)
+    body = re.search(r"typedef struct fnm_plan \{(.*?)\} fnm_plan;", header, flags=re.S).group(1)
+    names = []
+    for decl in body.split(";"):
+        decl = decl.strip()
+        if decl:
+            names += [n.strip(" *") for n in re.sub(r"^(const\s+)?\w+\s*\*?", "", decl, count=1).split(",")]
+    assert names == [n for n, _ in fnm_b200._lib.FnmPlan._fields_], names
 
 
 def test_c_abi_rejects_bad_arguments_without_gpu():
