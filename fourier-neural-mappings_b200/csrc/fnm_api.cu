@@ -184,6 +184,7 @@ int fnm_xdft(const float* T, const float* ex, float* Xh, int B, int P1, int R, i
              fnm_stream_t stream) {
     FNM_REQUIRE(T && ex && Xh, "xdft: NULL pointer");
     FNM_REQUIRE(B > 0 && P1 > 0 && R > 0 && NY > 0 && C > 0, "xdft: bad extents");
+    if (thin_xform_supported(T, Xh, 2 * P1, 2 * R, C)) return thin_xdft(T, ex, Xh, B, P1, R, NY, C, as_stream(stream));
     if (tc_xdft_supported(B, P1, R, NY, C)) return tc_xdft(T, ex, Xh, B, P1, R, NY, C, mode, as_stream(stream));
     return simt_xdft(T, ex, Xh, B, P1, R, NY, C, as_stream(stream));
 }
@@ -192,6 +193,7 @@ int fnm_xsyn(const float* Oh, const float* fx, float* Z, int B, int S1, int R, i
              fnm_stream_t stream) {
     FNM_REQUIRE(Oh && fx && Z, "xsyn: NULL pointer");
     FNM_REQUIRE(B > 0 && S1 > 0 && R > 0 && NY > 0 && C > 0, "xsyn: bad extents");
+    if (thin_xform_supported(Oh, Z, 2 * R, 2 * S1, C)) return thin_xsyn(Oh, fx, Z, B, S1, R, NY, C, as_stream(stream));
     if (tc_xsyn_supported(B, S1, R, NY, C)) return tc_xsyn(Oh, fx, Z, B, S1, R, NY, C, mode, as_stream(stream));
     return simt_xsyn(Oh, fx, Z, B, S1, R, NY, C, as_stream(stream));
 }

@@ -494,6 +494,72 @@ int simt_xsyn(const float* Oh, const float* fx, float* Z, int B, int S1, int R, 
     return launch_auto(p, B, st, "xsyn");
 }
 
+// ---- thin x-transforms: 1-D models have P1 = S1 = R = 1, so xdft / xsyn contract over TWO values (re, im) with a 2 x 2
+// table and otherwise only change the layout between T / Z ([b][x, ri][ky][c]) and the mode-major spectra
+// ([kx][ky][ri][b][c]).  On the table-GEMM kernel such a launch costs its fixed 12-20 us (TMEM, barriers, table
+// staging) for half a megabyte of data -- 16 launches, a fifth of a config-2 step.  Here: one thread per (sample, four
+// channels of one mode column), K <= 8 loads and M <= 8 stores of 16 bytes, fp32 FMA (exact to rounding).
+constexpr int kThinMax = 8;
+struct ThinArgs {
+    const float* in; const float* tab; float* out;
+    int B, K, M, R, NY, C;                     // K / M: contracted / produced table extent (2 P1 or 2 R, 2 R or 2 S1)
+};
+
+template <bool SYN>
+__global__ void __launch_bounds__(256) thin_xform_kernel(const ThinArgs a) {
+    const int C4 = a.C >> 2, n4 = a.NY * C4;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)a.B * n4) return;
+    const int b = (int)(i / n4), r4 = (int)(i - (long long)b * n4), l = r4 / C4, c = (r4 - l * C4) * 4;
+    const size_t N = (size_t)a.NY * a.C;
+    // spectra element (k or m = ri * R + r) of this thread: Xh / Oh[r][l][ri][b][c]
+    auto spec = [&](int q) { const int ri = q / a.R, r = q - ri * a.R; return ((((size_t)r * a.NY + l) * 2 + ri) * a.B + b) * a.C + c; };
+    float4 v[kThinMax];
+#pragma unroll
+    for (int k = 0; k < kThinMax; ++k)
+        if (k < a.K)
+            v[k] = __ldg(reinterpret_cast<const float4*>(a.in + (SYN ? spec(k) : ((size_t)b * a.K + k) * N + (size_t)l * a.C + c)));
+#pragma unroll
+    for (int m = 0; m < kThinMax; ++m) {
+        if (m < a.M) {
+            float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int k = 0; k < kThinMax; ++k)
+                if (k < a.K) {
+                    const float t = __ldg(a.tab + (size_t)m * a.K + k);
+                    s.x = fmaf(t, v[k].x, s.x); s.y = fmaf(t, v[k].y, s.y); s.z = fmaf(t, v[k].z, s.z); s.w = fmaf(t, v[k].w, s.w);
+                }
+            *reinterpret_cast<float4*>(a.out + (SYN ? ((size_t)b * a.M + m) * N + (size_t)l * a.C + c : spec(m))) = s;
+        }
+    }
+}
+
+bool thin_xform_supported(const float* in, const float* out, int K, int M, int C) {
+    return K >= 1 && M >= 1 && K <= kThinMax && M <= kThinMax && C % 4 == 0 &&
+           ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
+}
+
+static int thin_launch(const ThinArgs& a, bool syn, const char* what, cudaStream_t st) {
+    const long long n = (long long)a.B * a.NY * (a.C / 4);
+    if (n <= 0) return FNM_OK;
+    {
+        LaunchScope ls(what, st);
+        if (syn) thin_xform_kernel<true><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(a);
+        else thin_xform_kernel<false><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(a);
+    }
+    return check_launch(what);
+}
+
+int thin_xdft(const float* T, const float* ex, float* Xh, int B, int P1, int R, int NY, int C, cudaStream_t st) {
+    ThinArgs a{T, ex, Xh, B, 2 * P1, 2 * R, R, NY, C};
+    return thin_launch(a, false, "xdft", st);
+}
+
+int thin_xsyn(const float* Oh, const float* fx, float* Z, int B, int S1, int R, int NY, int C, cudaStream_t st) {
+    ThinArgs a{Oh, fx, Z, B, 2 * R, 2 * S1, R, NY, C};
+    return thin_launch(a, true, "xsyn", st);
+}
+
 static WeightRef make_w(const float* w0, const float* w1, int rpw, int NY, int Co, int Ci = 0, int mm = 0) {
     WeightRef w;
     w.w0 = reinterpret_cast<const float2*>(w0);

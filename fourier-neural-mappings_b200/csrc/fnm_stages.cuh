@@ -8,6 +8,10 @@ namespace fnm {
 int simt_ydft(const float* x, const float* tab, float* T, int64_t rows, int P2, int LY, int C, int act, cudaStream_t st);
 int simt_xdft(const float* T, const float* ex, float* Xh, int B, int P1, int R, int NY, int C, cudaStream_t st);
 int simt_xsyn(const float* Oh, const float* fx, float* Z, int B, int S1, int R, int NY, int C, cudaStream_t st);
+// thin x-transforms of the 1-D models (2 P1, 2 R, 2 S1 <= 8): one elementwise pass instead of a table GEMM launch
+bool thin_xform_supported(const float* in, const float* out, int K, int M, int C);
+int thin_xdft(const float* T, const float* ex, float* Xh, int B, int P1, int R, int NY, int C, cudaStream_t st);
+int thin_xsyn(const float* Oh, const float* fx, float* Z, int B, int S1, int R, int NY, int C, cudaStream_t st);
 int simt_mix_fwd(const float* Xh, const float* w0, const float* w1, int rpw, float* Oh, int B, int R, int NY, int Ci,
                  int Co, cudaStream_t st, int mode_major = 0);
 int simt_mix_bwd_x(const float* Gh, const float* w0, const float* w1, int rpw, float* Gxh, int B, int R, int NY, int Ci,

@@ -227,6 +227,9 @@ TAB_CASES = [
     # ... and the TMA-fed xdft (even P1): one ragged chunk, two chunks, rows of the next sample behind the last chunk
     dict(B=3, P1=10, P2=24, R=6, NY=4, C=128),
     dict(B=2, P1=22, P2=32, R=8, NY=5, C=128),
+    # thin x-transforms (2 P1, 2 R, 2 S1 <= 8: the 1-D models and the folded cross-dimension ones): elementwise kernel
+    dict(B=130, P1=1, P2=40, R=1, NY=3, C=12),
+    dict(B=7, P1=2, P2=24, R=2, NY=5, C=20),
 ]
 
 

@@ -24,12 +24,18 @@ graph = os.environ.get("FNM_TL_GRAPH", "1") == "1"
 batch = int(os.environ.get("FNM_TL_BATCH", "32"))
 reserve = int(os.environ.get("FNM_DP_SM_RESERVE", "0")) if world > 1 else 0
 torch.manual_seed(0)
-model = fnm_b200.FNO2d(32, 32, 128).to(dev)
+workload = os.environ.get("FNM_TL_WORKLOAD", "cfg5")            # any bench.py workload (single-GPU timelines of the small configs)
+import bench as _bench
+_desc, _family, _kw, _wbatch, _xshape, _ = _bench.WORKLOADS[workload]
+if "FNM_TL_BATCH" not in os.environ:
+    batch = _wbatch
+model = _bench.build_model(_family, _kw).to(dev)
 fnm_b200.parallel.broadcast_parameters(model)
 opt = fnm_b200.Adam(model.parameters(), lr=1e-3, weight_decay=1e-4, capturable=graph)
 grads = FlatGradients(model.parameters(), direct_spectral=True, overlap=os.environ.get("FNM_BENCH_OVERLAP", "1") == "1")
-x = torch.randn(batch, 1, 256, 256, device=dev)
-y = torch.randn(batch, 1, 256, 256, device=dev)
+x = torch.randn(batch, *_xshape, device=dev)
+with torch.no_grad():
+    y = torch.randn_like(model(x))
 if graph:
     g = GraphedTrainStep(model, opt, grads, rel_l2_sum, x, y, warmup=3, sm_reserve=reserve)
     step = lambda: g(x, y)
@@ -63,7 +69,7 @@ if rank == 0:
     evs = evs[len(evs) // 2:]                                  # the second of the two profiled steps
     t0 = evs[0].start_ns()
     short = lambda n: n.replace("void ", "").replace("fnm::", "").replace("tc::", "").split("(")[0][:46]
-    lines = [f"# world {world} graph {int(graph)} reserve {reserve} overlap {int(grads.overlap)}: {ms:.3f} ms/step (5 steps, events)"]
+    lines = [f"# {workload} world {world} graph {int(graph)} reserve {reserve} overlap {int(grads.overlap)}: {ms:.3f} ms/step (5 steps, events)"]
     nccl = [(e.start_ns() - t0, e.end_ns() - t0) for e in evs if "nccl" in e.name().lower()]
     span = (max(e.end_ns() for e in evs) - t0) / 1e6
     lines.append(f"# profiled step span {span:.3f} ms, {len(evs)} kernels, NCCL kernels {len(nccl)}, NCCL busy {sum(b - a for a, b in nccl) / 1e6:.3f} ms")
