@@ -98,6 +98,10 @@ static LayerWs layer_ws(const fnm_plan* p) {
     const size_t cmax = p->Ci > p->Co ? p->Ci : p->Co;
     const size_t rows = (size_t)p->B * (p->P1 > p->S1 ? p->P1 : p->S1);
     w.T = rows * LY * cmax;                               // T / Tg, then reused as Z / Zg
+    if (p->P1 == 1 && p->S1 == 1) {                       // 1-D: room for the partial transforms of the segmented y-DFT
+        const int si = tc_ydft_tma_segments(p->B, p->P2, p->Ci), so = tc_ydft_tma_segments(p->B, p->S2, p->Co);
+        w.T *= (size_t)(si > so ? si : so);
+    }
     w.Oh = (size_t)p->R * p->NY * 2 * p->B * cmax;        // Oh / Gxh
     w.Z = rows * LY * cmax;
     w.Gh = (size_t)p->R * p->NY * 2 * p->B * cmax;
@@ -168,6 +172,30 @@ int fnm_ydft(const float* x, const float* tab, float* T, int64_t rows, int P2, i
     if (tc_ydft_tma_supported(x, tab, P2, rows, P2, LY, C, act_in)) return tc_ydft_tma(x, tab, P2, T, rows, P2, LY, C, mode, as_stream(stream));
     if (tc_ydft_supported(rows, P2, LY, C)) return tc_ydft(x, tab, T, rows, P2, LY, C, act_in, mode, as_stream(stream));
     return simt_ydft(x, tab, T, rows, P2, LY, C, act_in, as_stream(stream));
+}
+
+static int plan_ydft(const float* x, const float* tab, const float* tab4, float* T, int64_t rows, int P2, int LY, int C, int act_in,
+                     int mode, fnm_stream_t stream);
+
+// y-DFT followed by the x-DFT of the fused layer.  1-D models (P1 = 1) have few, long rows -- config 2: 64 rows of 1152 points,
+// 32 work items for 148 SMs -- so the TMA-fed y-DFT splits each row into K segments, every (segment, row pair) an item, and the
+// thin x-transform (which only re-lays the two values of a 1-D "x spectrum" out) adds the partial transforms up.  T must hold
+// tc_ydft_tma_segments() partials (layer_ws).
+static int plan_ydft_xdft(const float* x, const float* tab, const float* tab4, float* T, const float* ex, float* Xh, int B, int P1,
+                          int P2, int R, int NY, int C, int act_in, int mode, fnm_stream_t stream) {
+    const int LY = 2 * NY;
+    if (P1 == 1 && act_in == 0 && thin_xform_supported(T, Xh, 2, 2 * R, C)) {
+        const int nseg = tc_ydft_tma_segments(B, P2, C);
+        const bool pad = P2 % 4 != 0;
+        const float* t = pad ? tab4 : tab;
+        const int ld = pad ? ((P2 + 3) & ~3) : P2;
+        if (nseg > 1 && t && tc_ydft_tma_supported(x, t, ld, B, P2, LY, C, 0, nseg)) {
+            FNM_TRY(tc_ydft_tma(x, t, ld, T, B, P2, LY, C, mode, as_stream(stream), nseg));
+            return thin_xdft(T, ex, Xh, B, 1, R, NY, C, as_stream(stream), nseg);
+        }
+    }
+    FNM_TRY(plan_ydft(x, tab, tab4, T, (int64_t)B * P1, P2, LY, C, act_in, mode, stream));
+    return fnm_xdft(T, ex, Xh, B, P1, R, NY, C, mode, stream);
 }
 
 // y-DFT of a plan's entry points: `tab4` is the plan's copy of `tab` with rows padded to a multiple of 4 floats (fnm_plan.ay4 /
@@ -420,8 +448,7 @@ int fnm_fourier_layer_fwd(const fnm_plan* p, const float* xin, int act_in, const
     float* Oh = cv.take(w.Oh);
     float* Z = cv.take(w.Z);
     const int LY = 2 * p->NY;
-    FNM_TRY(plan_ydft(xin, p->ay, p->ay4, T, (int64_t)p->B * p->P1, p->P2, LY, p->Ci, act_in, p->mode, stream));
-    FNM_TRY(fnm_xdft(T, p->ex, xh_save, p->B, p->P1, p->R, p->NY, p->Ci, p->mode, stream));
+    FNM_TRY(plan_ydft_xdft(xin, p->ay, p->ay4, T, p->ex, xh_save, p->B, p->P1, p->P2, p->R, p->NY, p->Ci, act_in, p->mode, stream));
     const int mm = p->w_layout == FNM_W_MODE_MAJOR;
     const int nmodes = p->R * p->NY, m_split = p->rows_per_w * p->NY;
     if (w.shadow && mm) {
@@ -472,9 +499,12 @@ int fnm_fourier_layer_bwd(const fnm_plan* p, const float* g_z, const float* xin,
     const int gld = s2_pad ? ((p->S2 + 3) & ~3) : p->S2;
     const bool gz_fused = want_cw && tc_gz_pass_supported(g_z, xin, gtab, gld, (int64_t)p->B * p->S1, p->S2, LY, p->Ci, p->Co, act_in);
     if (do_w) {
-        if (gz_fused) FNM_TRY(tc_gz_pass(g_z, xin, gtab, gld, Tg, dwc, dbc, (int64_t)p->B * p->S1, p->S2, LY, p->Co, partial, p->mode, st));
-        else FNM_TRY(plan_ydft(g_z, p->byT, p->byT4, Tg, (int64_t)p->B * p->S1, p->S2, LY, p->Co, 0, p->mode, stream));
-        FNM_TRY(fnm_xdft(Tg, p->exb, Gh, p->B, p->S1, p->R, p->NY, p->Co, p->mode, stream));
+        if (gz_fused) {
+            FNM_TRY(tc_gz_pass(g_z, xin, gtab, gld, Tg, dwc, dbc, (int64_t)p->B * p->S1, p->S2, LY, p->Co, partial, p->mode, st));
+            FNM_TRY(fnm_xdft(Tg, p->exb, Gh, p->B, p->S1, p->R, p->NY, p->Co, p->mode, stream));
+        } else {
+            FNM_TRY(plan_ydft_xdft(g_z, p->byT, p->byT4, Tg, p->exb, Gh, p->B, p->S1, p->S2, p->R, p->NY, p->Co, 0, p->mode, stream));
+        }
     }
     float* shadowA = w.shadow ? cv.take(w.shadow) : nullptr;
     float* shadowB = w.shadow ? cv.take(w.shadow) : nullptr;

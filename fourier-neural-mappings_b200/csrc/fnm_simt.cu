@@ -503,6 +503,7 @@ constexpr int kThinMax = 8;
 struct ThinArgs {
     const float* in; const float* tab; float* out;
     int B, K, M, R, NY, C;                     // K / M: contracted / produced table extent (2 P1 or 2 R, 2 R or 2 S1)
+    int nsum; long long sum_stride;            // xdft: the input is the sum of nsum partial transforms (segmented 1-D y-DFT)
 };
 
 template <bool SYN>
@@ -517,8 +518,14 @@ __global__ void __launch_bounds__(256) thin_xform_kernel(const ThinArgs a) {
     float4 v[kThinMax];
 #pragma unroll
     for (int k = 0; k < kThinMax; ++k)
-        if (k < a.K)
-            v[k] = __ldg(reinterpret_cast<const float4*>(a.in + (SYN ? spec(k) : ((size_t)b * a.K + k) * N + (size_t)l * a.C + c)));
+        if (k < a.K) {
+            const float* src = a.in + (SYN ? spec(k) : ((size_t)b * a.K + k) * N + (size_t)l * a.C + c);
+            v[k] = __ldg(reinterpret_cast<const float4*>(src));
+            for (int s = 1; s < a.nsum; ++s) {                      // fixed order: deterministic
+                const float4 w = __ldg(reinterpret_cast<const float4*>(src + (size_t)s * a.sum_stride));
+                v[k].x += w.x; v[k].y += w.y; v[k].z += w.z; v[k].w += w.w;
+            }
+        }
 #pragma unroll
     for (int m = 0; m < kThinMax; ++m) {
         if (m < a.M) {
@@ -550,13 +557,13 @@ static int thin_launch(const ThinArgs& a, bool syn, const char* what, cudaStream
     return check_launch(what);
 }
 
-int thin_xdft(const float* T, const float* ex, float* Xh, int B, int P1, int R, int NY, int C, cudaStream_t st) {
-    ThinArgs a{T, ex, Xh, B, 2 * P1, 2 * R, R, NY, C};
+int thin_xdft(const float* T, const float* ex, float* Xh, int B, int P1, int R, int NY, int C, cudaStream_t st, int nsum) {
+    ThinArgs a{T, ex, Xh, B, 2 * P1, 2 * R, R, NY, C, nsum > 1 ? nsum : 1, (long long)B * 2 * P1 * NY * C};
     return thin_launch(a, false, "xdft", st);
 }
 
 int thin_xsyn(const float* Oh, const float* fx, float* Z, int B, int S1, int R, int NY, int C, cudaStream_t st) {
-    ThinArgs a{Oh, fx, Z, B, 2 * R, 2 * S1, R, NY, C};
+    ThinArgs a{Oh, fx, Z, B, 2 * R, 2 * S1, R, NY, C, 1, 0};
     return thin_launch(a, true, "xsyn", st);
 }
 

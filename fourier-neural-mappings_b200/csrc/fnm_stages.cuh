@@ -10,7 +10,7 @@ int simt_xdft(const float* T, const float* ex, float* Xh, int B, int P1, int R, 
 int simt_xsyn(const float* Oh, const float* fx, float* Z, int B, int S1, int R, int NY, int C, cudaStream_t st);
 // thin x-transforms of the 1-D models (2 P1, 2 R, 2 S1 <= 8): one elementwise pass instead of a table GEMM launch
 bool thin_xform_supported(const float* in, const float* out, int K, int M, int C);
-int thin_xdft(const float* T, const float* ex, float* Xh, int B, int P1, int R, int NY, int C, cudaStream_t st);
+int thin_xdft(const float* T, const float* ex, float* Xh, int B, int P1, int R, int NY, int C, cudaStream_t st, int nsum = 1);   // nsum: partial T's to add up
 int thin_xsyn(const float* Oh, const float* fx, float* Z, int B, int S1, int R, int NY, int C, cudaStream_t st);
 int simt_mix_fwd(const float* Xh, const float* w0, const float* w1, int rpw, float* Oh, int B, int R, int NY, int Ci,
                  int Co, cudaStream_t st, int mode_major = 0);
@@ -54,8 +54,10 @@ int tc_available();
 bool tc_ydft_supported(int64_t rows, int P2, int LY, int C);
 int tc_ydft(const float* x, const float* tab, float* T, int64_t rows, int P2, int LY, int C, int act, int mode,
             cudaStream_t st);
-bool tc_ydft_tma_supported(const float* x, const float* tab, int ld, int64_t rows, int P2, int LY, int C, int act);   // ld: row stride of tab
-int tc_ydft_tma(const float* x, const float* tab, int ld, float* T, int64_t rows, int P2, int LY, int C, int mode, cudaStream_t st);
+bool tc_ydft_tma_supported(const float* x, const float* tab, int ld, int64_t rows, int P2, int LY, int C, int act, int nseg = 1);   // ld: row stride of tab
+int tc_ydft_tma_segments(int64_t rows, int P2, int C);        // K segments worth using for few long rows (1 = none)
+int tc_ydft_tma(const float* x, const float* tab, int ld, float* T, int64_t rows, int P2, int LY, int C, int mode, cudaStream_t st,
+                int nseg = 1);                           // nseg > 1: T receives nseg PARTIAL transforms [seg][row][l'][c]
 bool tc_xdft_supported(int B, int P1, int R, int NY, int C);
 int tc_xdft(const float* T, const float* ex, float* Xh, int B, int P1, int R, int NY, int C, int mode, cudaStream_t st);
 bool tc_resample_supported(int64_t G, int K, int M, int inner, int C);

@@ -38,6 +38,10 @@ struct YdArgs {
     int P2, LY, NT, nch, single_pass;
     int C, F, gpi;                          // channels, rows folded per group, groups per work item (2: one table chunk serves both)
     long long pairs;                        // work items
+    // K segments (1-D models: few, long rows): an item is (segment, row pair) and covers `nch` chunks starting at chunk
+    // seg * nch; segment s writes its PARTIAL transform to out + s * seg_stride (the consumer sums them).  nseg = 1: none.
+    int nseg;
+    long long pairs0, seg_stride;           // row pairs per segment; floats between the partial outputs
 };
 
 __device__ __forceinline__ uint64_t yd_desc_mn32(uint32_t saddr) {
@@ -87,8 +91,10 @@ ydft_tma(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUten
         // =========================================================================== TMA producer
         if (lane == 0) {
             for (uint32_t q = 0; q < total; ++q) {
-                const uint32_t it = q / nch, ch = q - it * nch, s = q % kYdRaw;
-                const long long pair = (long long)blockIdx.x + (long long)it * gridDim.x;
+                const uint32_t it = q / nch, s = q % kYdRaw;
+                uint32_t ch = q - it * nch;
+                long long pair = (long long)blockIdx.x + (long long)it * gridDim.x;
+                if (a.nseg > 1) { const long long seg = pair / a.pairs0; pair -= seg * a.pairs0; ch += (uint32_t)seg * nch; }
                 mbar_wait(&raw_empty[s], ((q / kYdRaw) & 1) ^ 1);
                 const bool two = a.gpi == 2 && pair * 2 + 1 < a.groups;
                 mbar_expect_tx(&raw_full[s], (two ? 2u : 1u) * kYdATile + 8192u);
@@ -204,7 +210,9 @@ ydft_tma(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUten
         const int fr = c / a.C, cc = c - fr * a.C;                      // lane = (row within the group, channel)
         const int l0 = half * 32;
         for (uint32_t it = 0; it < (uint32_t)my_pairs; ++it) {
-            const long long pair = (long long)blockIdx.x + (long long)it * gridDim.x;
+            long long pair = (long long)blockIdx.x + (long long)it * gridDim.x;
+            float* outp = a.out;
+            if (a.nseg > 1) { const long long seg = pair / a.pairs0; pair -= seg * a.pairs0; outp += seg * a.seg_stride; }
             mbar_wait(d_full, it & 1);
             tc_fence_after();
             // accumulators -> registers for BOTH rows first, then the buffer is handed back: the issuer starts the next pair
@@ -239,7 +247,7 @@ ydft_tma(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUten
                 if (j >= a.gpi) break;
                 const long long row = (pair * a.gpi + j) * a.F + fr;
                 if (row < a.rows) {
-                    float* op = a.out + ((size_t)row * a.LY + l0) * a.C + cc;
+                    float* op = outp + ((size_t)row * a.LY + l0) * a.C + cc;
 #pragma unroll
                     for (int i = 0; i < 32; ++i)
                         if (l0 + i < a.LY) op[(size_t)i * a.C] = v[j][i];
@@ -257,19 +265,34 @@ ydft_tma(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUten
 
 using namespace tc;
 
-bool tc_ydft_tma_supported(const float* x, const float* tab, int ld, int64_t rows, int P2, int LY, int C, int act) {
+// K segments for problems with few long rows (the 1-D models): as many as bring the item count up to the SM count, at most 8,
+// at least two 32-point chunks each; 1 = no split.  Uses the device's SM count, not the caller's current budget, so that
+// workspace sizes do not depend on fnm_set_sm_limit.
+int tc_ydft_tma_segments(int64_t rows, int P2, int C) {
+    if (C != 128 && C != 64 && C != 32) return 1;
+    const long long groups = (rows + 128 / C - 1) / (128 / C);
+    const int nch = (P2 + 31) / 32;
+    if (groups < 1 || groups * 2 > sm_count_max()) return 1;
+    long long n = sm_count_max() / groups;
+    if (n > 8) n = 8;
+    if (n > nch / 2) n = nch / 2;
+    return n < 2 ? 1 : (int)n;
+}
+
+bool tc_ydft_tma_supported(const float* x, const float* tab, int ld, int64_t rows, int P2, int LY, int C, int act, int nseg) {
     // ld: row stride of the table in floats (TMA wants 16-byte strides: P2 itself, or the padded copy fnm_plan.ay4 / byT4)
     if (!tc_enabled() || act != 0 || (C != 128 && C != 64 && C != 32) || LY < 8 || LY > 64 || ld % 4 != 0 || ld < P2 || P2 < 4 ||
         rows < 1 || rows >= (1LL << 30))
         return false;
     if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(tab)) & 15) return false;
     // an item is a whole (folded) grid row: problems with few long rows (1-D) stay on the segmenting register-path kernel
-    if (C != 128 && rows / (128 / C) < sm_count()) return false;
+    if (C != 128 && rows / (128 / C) < sm_count() && nseg <= 1) return false;
     const char* e = getenv("FNM_YDFT_NO_TMA");
     return !(e && e[0] == '1');
 }
 
-int tc_ydft_tma(const float* x, const float* tab, int ld, float* T, int64_t rows, int P2, int LY, int C, int mode, cudaStream_t st) {
+int tc_ydft_tma(const float* x, const float* tab, int ld, float* T, int64_t rows, int P2, int LY, int C, int mode, cudaStream_t st,
+                int nseg) {
     YdArgs a{};
     a.out = T; a.rows = rows; a.P2 = P2; a.LY = LY; a.NT = (LY + 15) / 16 * 16; a.nch = (P2 + 31) / 32;
     a.single_pass = mode == FNM_MODE_TF32;
@@ -277,6 +300,11 @@ int tc_ydft_tma(const float* x, const float* tab, int ld, float* T, int64_t rows
     a.groups = (rows + a.F - 1) / a.F;
     a.gpi = a.groups >= 4LL * sm_count() ? 2 : 1;            // pair the groups when there are enough of them to keep every SM busy
     a.pairs = (a.groups + a.gpi - 1) / a.gpi;
+    a.nseg = nseg > 1 ? nseg : 1; a.pairs0 = a.pairs; a.seg_stride = (long long)rows * LY * C;
+    if (a.nseg > 1) {                                        // T holds nseg partial transforms [seg][row][l'][c]
+        a.nch = (a.nch + a.nseg - 1) / a.nseg;               // chunks past the row's end read as zeros (TMA bounds)
+        a.pairs = a.pairs0 * a.nseg;
+    }
     CUtensorMap mx, mt;
     {
         const cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)P2, (cuuint64_t)rows};

@@ -229,6 +229,10 @@ def _oracle_layer(x, w1, w2, wc, bc, act):
     dict(B=5, C=128, P=(20, 33), m=(4, 9)),           # batch / mode counts that are no multiples of 4 on the tcgen05 kernels
     dict(B=1, C=16, P=(17, 30), m=(3, 5)),            # single sample, 16 channels (8 rows folded into the 128 lanes)
     dict(B=3, C=96, P=(18, 24), m=(7, 6)),            # 96 channels: not a power of two, above 64
+    # 1-D, few long rows: the y-DFT splits every row into K segments whose partial transforms the thin x-transform adds up
+    dict(B=64, C=64, P=(1152,), m=(16,)),             # config 2 at its own batch (4 segments of 9 chunks)
+    dict(B=3, C=128, P=(300,), m=(20,)),              # last segment runs past the end of the row
+    dict(B=5, C=32, P=(203,), m=(9,)),                # row length that is no multiple of 4 (padded table), ragged row group
 ])
 def test_fused_layers_vs_oracle(shape):
     """Two chained fused layers (GELU between them is applied on load) + trailing GELU, forward and
