@@ -25,8 +25,9 @@ class FlatGradients:
     slots.  It assumes what holds for every model here: each spectral weight enters exactly one
     autograd Function per step and ``zero_()`` is called before every backward (a second use raises)."""
 
-    def __init__(self, params, direct_spectral=False, overlap=False):
+    def __init__(self, params, direct_spectral=False, overlap=False, group=None):
         self.params = [p for p in params if p.requires_grad]
+        self.group = group                                     # process group of the exchange (None: the default group)
         # overlap (needs direct_spectral): each spectral weight's slot is all-reduced as soon as the backward kernel
         # that fills it has been enqueued (asynchronously, on the process group's stream), so the exchange of the deep
         # layers runs under the backward pass of the shallow ones; all_reduce() then handles the rest and joins.
@@ -81,7 +82,7 @@ class FlatGradients:
 
     def _sink_ready(self, off, n, param):
         """A backward kernel that fills the slot [off, off + n) has been enqueued: stage it for the next ``flush_ready``."""
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
             self._staged.append((off, n, param))
 
     def flush_ready(self):
@@ -98,7 +99,7 @@ class FlatGradients:
                 runs.append([off, off + (n + 63) // 64 * 64, [q]])
         for lo, hi, ps in runs:
             chunk = self.flat[lo:min(hi, self.flat.numel())]
-            self._pending.append((dist.all_reduce(chunk, op=dist.ReduceOp.SUM, async_op=True), ps))
+            self._pending.append((dist.all_reduce(chunk, op=dist.ReduceOp.SUM, group=self.group, async_op=True), ps))
             if self._reserve_sms > 0 and self._limit_prev is None:
                 # from the first exchange in flight on, the persistent kernels leave `_reserve_sms` SMs to the NCCL kernels
                 # (train_step lifts the cap after backward); the kernels before it keep every SM
@@ -120,6 +121,7 @@ class FlatGradients:
         """SUM over ranks; no-op in a single-process run.  With ``overlap`` the sinks are already in flight: this
         exchanges the head (everything that is not a sink) and, unless ``join=False``, waits for all of it
         (``join=False`` leaves the waiting to whoever iterates ``update_groups()``)."""
+        group = self.group if group is None else group
         if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
             return None
         if self._staged:
@@ -178,6 +180,7 @@ def train_step(model, optimizer, grads, loss_fn, x, y, group=None, sm_reserve=0)
     ``sm_reserve`` (overlapped exchange only): SMs the persistent backward kernels leave free from the moment the first
     slot's all-reduce is in flight, so that the NCCL kernels have somewhere to run (include/fnm_b200.h, fnm_set_sm_limit);
     it should equal the number of CTAs NCCL launches (NCCL_MAX_CTAS)."""
+    group = getattr(grads, "group", None) if group is None else group
     grads.zero_()
     out = model(x)
     loss = loss_fn(out, y)
