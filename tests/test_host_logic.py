@@ -256,6 +256,30 @@ def test_library_exports_every_declared_symbol():
     assert names == [n for n, _ in fnm_b200._lib.FnmPlan._fields_], names
 
 
+def test_layer_workspace_holds_the_partial_transforms_of_the_segmented_1d_ydft():
+    """1-D models have few long rows: the TMA-fed y-DFT splits each row into K segments and the x-transform adds the partial
+    transforms up, so the layer workspace of a 1-D plan holds that many copies of T (sized from the device's SM count --
+    148 when no GPU is present -- and independent of fnm_set_sm_limit); many-row 1-D plans get no copies."""
+    import ctypes
+    from fnm_b200.plan import spectral_tables
+    L = fnm_b200._lib.lib()
+
+    def ws(tables, B, C):
+        plan = tables.c_plan(torch.device("cpu"), B, C, C)
+        return L.fnm_fourier_layer_workspace_bytes(ctypes.byref(plan))
+
+    t1 = spectral_tables(1, 1152, 1, 16, one_d=True)
+    few, many = ws(t1, 64, 64), ws(t1, 640, 64)                     # 32 row groups -> 4 segments; 320 groups -> none
+    per_sample_T = 4 * 32 * 64                                      # bytes of one sample's T: LY = 32 rows of 64 channels
+    assert few - 64 * per_sample_T * 3 > 0
+    assert few / 64 > many / 640 + 2.5 * per_sample_T               # three extra copies of T per sample
+    prev = L.fnm_set_sm_limit(100)
+    try:
+        assert ws(t1, 64, 64) == few                                # workspace sizes do not follow the SM budget
+    finally:
+        L.fnm_set_sm_limit(prev)
+
+
 def test_c_abi_rejects_bad_arguments_without_gpu():
     L = fnm_b200._lib.lib()
     assert L.fnm_gelu_fwd(None, None, 4, None) == 1                  # FNM_EINVAL
