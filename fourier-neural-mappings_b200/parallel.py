@@ -272,9 +272,38 @@ class GraphedTrainStep:
         self.graph = None
         self.loss = None
 
-    def __call__(self, x, y):
-        self.x.copy_(x, non_blocking=True)
-        self.y.copy_(y, non_blocking=True)
+    def stage(self, x, y):
+        """Start copying the NEXT step's inputs (pinned host or device tensors) into a staging pair on a side stream and
+        return at once; the following ``__call__()`` without arguments consumes them.  An input pipeline calls this right
+        after launching step i, so the host-to-device copy of step i + 1 runs under step i's kernels (the graph itself
+        reads fixed buffers, which cannot be overwritten while a replay is in flight)."""
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream(device=self.x.device)
+            self._stage_x, self._stage_y = torch.empty_like(self.x), torch.empty_like(self.y)
+            self._ev_ready = torch.cuda.Event()
+            self._ev_taken = None
+        if self._ev_taken is not None:                         # the previous step's copy out of the staging pair
+            self._copy_stream.wait_event(self._ev_taken)
+        with torch.cuda.stream(self._copy_stream):
+            self._stage_x.copy_(x, non_blocking=True)
+            self._stage_y.copy_(y, non_blocking=True)
+            self._ev_ready.record()
+        self._staged = True
+
+    def __call__(self, x=None, y=None):
+        if x is None:
+            if not getattr(self, "_staged", False):
+                raise RuntimeError("GraphedTrainStep(): no inputs given and none staged (call stage(x, y) first)")
+            cur = torch.cuda.current_stream(self.x.device)
+            cur.wait_event(self._ev_ready)
+            self.x.copy_(self._stage_x, non_blocking=True)     # device to device: microseconds
+            self.y.copy_(self._stage_y, non_blocking=True)
+            self._ev_taken = torch.cuda.Event()
+            self._ev_taken.record(cur)
+            self._staged = False
+        else:
+            self.x.copy_(x, non_blocking=True)
+            self.y.copy_(y, non_blocking=True)
         self.graph.replay()
         if hasattr(self.optimizer, "graph_replayed"):
             self.optimizer.graph_replayed()
