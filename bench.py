@@ -381,7 +381,7 @@ def run_ours(args, rank, world):
     if args.graph:
         # the step recorded once in a CUDA graph; every timed step below is one replay of the full step
         try:
-            graphed = fnm_b200.parallel.GraphedTrainStep(model, opt, grads, rel_l2_sum, x, y, warmup=args.warmup,
+            graphed = fnm_b200.parallel.GraphedTrainStep(model, opt, grads, rel_l2_sum, x, y, warmup=max(3, args.warmup),   # capture warm-up (undone)
                                                              sm_reserve=sm_reserve)
         except Exception as e:                             # noqa: BLE001 -- e.g. a collective that cannot be captured
             sys.stderr.write(f"[bench] CUDA-graph capture failed ({type(e).__name__}: {e}); running eagerly\n")
