@@ -112,6 +112,93 @@ def _worker_overlap(rank, world, port, out):
         dist.destroy_process_group()
 
 
+class _SinkFn(torch.autograd.Function):
+    """Stand-in for ops.FourierLayerFn on CPU: y = sum(x) * (|w|^2 + |w2|^2).sum(); backward writes dW straight into the
+    weights' gradient sinks, marks them ready, flushes (one merged all-reduce) and hands autograd no gradient for them."""
+
+    @staticmethod
+    def forward(ctx, x, w, w2):
+        ctx.save_for_backward(x, w, w2)
+        ctx.sinks = (w._fnm_grad_sink, w2._fnm_grad_sink)
+        return x.sum() * ((w.abs() ** 2).sum() + (w2.abs() ** 2).sum())
+
+    @staticmethod
+    def backward(ctx, g):
+        x, w, w2 = ctx.saved_tensors
+        for sink, q in zip(ctx.sinks, (w, w2)):
+            sink.copy_(2 * q.detach() * x.sum() * g)
+            sink._fnm_on_ready()
+        ctx.sinks[0]._fnm_flush()
+        return g * ((w.abs() ** 2).sum() + (w2.abs() ** 2).sum()) * torch.ones_like(x), None, None
+
+
+class _RecordingSGD:
+    """Optimizer stand-in with Adam's partial-step interface: records which parameters each call updated."""
+    supports_partial_step = True
+
+    def __init__(self, params):
+        self.params, self.calls = list(params), []
+
+    def step(self, closure=None, params=None, continued=False):
+        ps = self.params if params is None else list(params)
+        self.calls.append(([id(p) for p in ps], continued))
+        with torch.no_grad():
+            for p in ps:
+                p.sub_(0.01 * p.grad)
+
+
+def _worker_train_step(rank, world, port, out):
+    """parallel.train_step with the overlapped exchange and the grouped update, end to end on CPU: the spectral slots are
+    exchanged from inside backward (merged), the rest after it; every parameter group is updated once, in the order its
+    exchange was issued, with the SUM of the ranks' gradients."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.manual_seed(3)
+        model = Toy()
+        model.w2 = torch.nn.Parameter(model.w.detach().clone() * 0.5)
+        scale = torch.nn.Parameter(torch.ones(3))                         # a real parameter that goes through autograd
+        params = [scale, model.w, model.w2]
+        grads = FlatGradients(params, direct_spectral=True, overlap=True)
+        opt = _RecordingSGD(params)
+        before = [p.detach().clone() for p in params]
+        x = torch.full((4,), float(rank + 1))
+        net = lambda inp: _SinkFn.apply(inp * scale.sum(), model.w, model.w2)
+        fnm_b200.parallel.train_step(net, opt, grads, lambda o, y: o, x, None)
+        assert not grads._pending and not grads._staged
+        if rank == 0:
+            out.put({"calls": opt.calls, "ids": [id(p) for p in params], "before": before,
+                     "after": [p.detach().clone() for p in params], "grads": [p.grad.detach().clone() for p in params]})
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_two_rank_train_step_overlapped_exchange_and_grouped_update():
+    world = 2
+    ctx = mp.get_context("spawn")
+    out = ctx.SimpleQueue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_train_step, args=(r, world, port, out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = out.get()
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    scale_id, w_id, w2_id = res["ids"]
+    # two update calls: the merged spectral group first (its exchange was issued inside backward), then the rest
+    assert res["calls"] == [([w_id, w2_id], False), ([scale_id], True)]
+    # gradients are the SUM over ranks (x = 1 on rank 0, 2 on rank 1: sum(x) * scale.sum() = 12 and 24)
+    w0, w20 = res["before"][1], res["before"][2]
+    assert torch.allclose(res["grads"][1], 2 * w0 * (12.0 + 24.0), rtol=1e-5)
+    assert torch.allclose(res["grads"][2], 2 * w20 * (12.0 + 24.0), rtol=1e-5)
+    q = ((w0.abs() ** 2).sum() + (w20.abs() ** 2).sum())
+    assert torch.allclose(res["grads"][0], torch.full((3,), float(q) * (4.0 + 8.0)), rtol=1e-5)
+    for b, a, g in zip(res["before"], res["after"], res["grads"]):
+        assert torch.allclose(a, b - 0.01 * g, rtol=1e-6, atol=1e-7)      # every parameter updated exactly once
+
+
 @pytest.mark.timeout(120)
 def test_two_rank_overlapped_slot_exchange_equals_flat_sum():
     world = 2
